@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the encode+decode transform path (BASELINE.json metric: images/s at 512^2, patch 14).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One "step" = one pass of the whole path over one batch of synthetic images:
+  RGB -> IPT -> truncated 2-D DCT -> token grid -> score / sort / pack -> PatchNorm -> LFQ
+  -> inverse PatchNorm -> un-patchify -> truncated IDCT -> IPT -> RGB
+(BASELINE config 2: B=256 RGB fp32 512x512, patch 14, max 32x32 tiles, beta=0, max_seq_len 3072,
+LFQ 14 codebooks x 14 bits).  Multi-GPU (torchrun, one rank per GPU): the batch is sharded by image,
+weak scaling, no data-path collective; the PatchNorm statistic fit (with its all-reduce) runs once
+before the timed region.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the oracle port of the reference's CPU
+algorithm on the host cores instead (bounded sample per step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "encode+decode images/sec at 512^2 patch14"
+UNIT = "images/s"
+WORKLOAD = dict(workload="config2: synthetic 512x512 RGB fp32, patch 14, max_patch 32x32, beta=0, "
+                         "max_seq_len 3072, PatchNorm frozen, LFQ 14x14bit, decode to RGB",
+                image_size=512, patch_size=14)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="also print per-stage timings to stderr")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    """Runs the oracle pipeline on a chunk of images in one process."""
+    seed, n, size = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import dcta_oracle as O
+    rng = np.random.default_rng(seed)
+    x = rng.random((n, 3, size, size), dtype=np.float32)
+    fe = O.FeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+    pn = O.PatchNorm(32, 32, 14, 3)
+    pn.frozen = True      # identity-like tables: same arithmetic per token as fitted ones
+    lfq = O.LFQ(codebook_size=2 ** 14, num_codebooks=14)
+    t0 = time.perf_counter()
+    rec, codes = O.run_pipeline(x, fe, pn, lfq)
+    return time.perf_counter() - t0, float(rec[0].sum())
+
+
+def cpu_reference_throughput(n_images: int, size: int, procs: int):
+    """images/s of the oracle port over `procs` worker processes (one image chunk each)."""
+    import multiprocessing as mp
+    procs = max(1, min(procs, n_images))
+    chunks = [n_images // procs + (1 if i < n_images % procs else 0) for i in range(procs)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_cpu_worker, [(0, 1, 64)] * procs)            # warm the workers (imports)
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(i + 1, c, size) for i, c in enumerate(chunks)])
+        dt = time.perf_counter() - t0
+    return n_images / dt, dt, procs
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per_step = a.cpu_sample or 16 * cores
+    # bounded: about (warmup + steps) * per_step images in total
+    times = []
+    for i in range(a.warmup + a.steps):
+        ips, dt, procs = cpu_reference_throughput(per_step, a.size, cores)
+        if i >= a.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = per_step * len(times) / total
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=1e3 * total / len(times), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(WORKLOAD, global_batch=per_step),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=procs, kind="port",
+                                  sample=f"{per_step} images of 512x512 per step over {procs} worker processes "
+                                         "(oracle/dcta_oracle.py run_pipeline)"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import dct_autoencoder_b200 as D
+    from dct_autoencoder_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    B, S = a.batch, a.size
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+    pn = D.PatchNorm(32, 32, 14, 3).to(dev)
+    lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).to(dev).eval()
+    pipe = D.TransformPipeline(fe, pn, lfq)
+
+    # PatchNorm statistics fitted on a different batch (all-reduced over the ranks when world > 1)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    fit_x = torch.rand(min(B, 64), 3, S, S, device=dev, generator=g)
+    t0 = time.perf_counter()
+    pipe.fit_norm(fit_x)
+    torch.cuda.synchronize()
+    fit_ms = 1e3 * (time.perf_counter() - t0)
+    del fit_x
+
+    g.manual_seed(rank)
+    x = torch.rand(B, 3, S, S, device=dev, generator=g)        # 805 MB at B=256: larger than the 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- device-resident throughput (value)
+    def step():
+        rec, codes = pipe.roundtrip(x)
+        return rec, codes
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(a.warmup):
+        step()
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count
+    ms = timed(step, a.steps, 0)
+    launches = _lib.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    value = world * B * a.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with HOST buffers (pinned in, pinned out)
+    hx = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
+    hx.copy_(x)
+    h_rec = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
+    h_codes = torch.empty((B, 3072, 14), dtype=torch.int64).pin_memory()
+
+    def step_e2e():
+        rec, codes = pipe.roundtrip(hx)          # host tensor in: staged H2D inside the call
+        h_rec.copy_(rec, non_blocking=True)
+        h_codes.copy_(codes, non_blocking=True)
+
+    e2e_steps = max(2, min(a.steps, 5))
+    ms_e2e = timed(step_e2e, e2e_steps, 1)
+    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
+
+    # ---- per-stage device times (CUDA events around each public call) for the roofline object
+    stages = stage_times(torch, D, pipe, x, dev, reps=3)
+    K = 448
+    flops_fwd = 3 * 2 * S * K * (S + K) * B          # C*2*H*K*(W+K) per image
+    dct_ms = stages["dct_fwd"]
+    achieved = flops_fwd / (dct_ms / 1e3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
+    roofline = dict(bound="tensor", kernel="sgemm_tile_kernel (forward DCT: 2 launches)", achieved=achieved,
+                    peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=None, peak_source=peak_src,
+                    note="exact-fp32 FFMA GEMM; algorithmic flops 3*2*H*K*(W+K) per image")
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    staged_bytes = 26004480 * B
+    pipeline_hbm = dict(bound="hbm", achieved=staged_bytes * a.steps / (ms / 1e3) / 1e9, peak=hbm, unit="GB/s",
+                        note="whole step, staged-API algorithmic bytes 26,004,480 B/img (SURVEY 8d)")
+    pipeline_hbm["frac"] = pipeline_hbm["achieved"] / hbm
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
+                ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(WORKLOAD, global_batch=B * world, per_gpu_batch=B, parallelism=f"image-sharded x{world}",
+                            l2="inputs (805 MB/GPU at B=256) larger than L2, no flush needed",
+                            patchnorm_fit_ms=fit_ms),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=hx.numel() * 4 * world,
+                         d2h_bytes_per_step=(h_rec.numel() * 4 + h_codes.numel() * 8) * world,
+                         ms_per_step=ms_e2e / e2e_steps),
+                gpu_launches=launches, clocks=clocks, roofline=roofline, pipeline_hbm=pipeline_hbm,
+                stages_ms=stages)
+
+    if rank == 0 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = a.cpu_sample or 32 * cores
+        ips, dt, procs = cpu_reference_throughput(n, S, cores)
+        line["cpu_baseline"] = dict(value=ips, unit=UNIT, cores=procs, kind="port",
+                                    sample=f"{n} images of {S}x{S} over {procs} worker processes, {dt:.1f} s "
+                                           "(oracle/dcta_oracle.py run_pipeline)")
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def stage_times(torch, D, pipe, x, dev, reps=3):
+    """Median device time (ms) of each stage of one step, CUDA events on the launching stream."""
+    fe, pn, lfq = pipe.extractor, pipe.norm, pipe.quantizer
+    out = {}
+
+    def t(name, fn):
+        res = None
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        out[name] = statistics.median(ts)
+        return res
+
+    ipt = t("rgb_to_ipt", lambda: D.util.rgb_to_ipt(x))
+    tiles = t("dct_fwd", lambda: D.util.dct2_truncated(ipt, 448, 448, tile_p=14, channels=3))
+    del ipt
+    t("score_sort", lambda: fe._sorted_order(tiles))
+    del tiles
+    batch = t("encode_total(process_batch)", lambda: fe.process_batch(x))
+    normed = t("patchnorm_fwd", lambda: pn(batch))
+    q = t("lfq", lambda: lfq(normed, mask=~batch.key_pad_mask))[0]
+    b2 = batch.shallow_copy()
+    b2.patches = q
+    inv = t("patchnorm_inv", lambda: pn.inverse_norm(b2))
+    b2.patches = inv
+    planes = t("unpatchify", lambda: fe._render_planes(b2, clip=True))[0][1]
+    ipt2 = t("dct_inv", lambda: D.util.idct2_truncated(planes, x.shape[-2], x.shape[-1]))
+    t("ipt_to_rgb", lambda: D.util.ipt_to_rgb(ipt2))
+    return out
+
+
+if __name__ == "__main__":
+    args = parse()
+    sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))

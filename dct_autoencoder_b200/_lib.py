@@ -1,0 +1,129 @@
+"""ctypes binding of libdcta.so (include/dcta.h).  There is NO fallback: if the library is
+missing or a call fails, the product path raises."""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdcta.so")
+
+ABI_VERSION = 1
+
+
+class DctaError(RuntimeError):
+    pass
+
+
+class Segment(ctypes.Structure):
+    """dcta_segment"""
+    _fields_ = [("row", c_int32), ("offset", c_int32), ("k", c_int32), ("image_id", c_int32),
+                ("img", c_int64)]
+
+
+P = c_void_p
+# name -> argtypes (every function returns int unless listed in _RESTYPES)
+SIGNATURES = {
+    "dcta_last_error": [],
+    "dcta_abi_version": [],
+    "dcta_compiled_arch": [],
+    "dcta_rgb_to_ipt": [P, P, c_int64, c_int64, P, P, P],
+    "dcta_ipt_to_rgb": [P, P, c_int64, c_int64, P, P, P],
+    "dcta_dct2_fwd": [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "dcta_dct2_inv": [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
+    "dcta_patchify": [P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "dcta_tile_scores": [P, P, c_int64, c_int, c_int, c_int, c_int, c_float, P, P],
+    "dcta_sort_tokens": [P, P, c_int64, c_int, P],
+    "dcta_pack_tiles": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P],
+    "dcta_pack_lists": [P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P],
+    "dcta_patchnorm_apply": [P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, P],
+    "dcta_patchnorm_build_lists": [P, P, P, c_int64, c_int, c_int, c_int, P, P, P, P, P],
+    "dcta_patchnorm_batch_median": [P, P, P, c_int, c_int, P, P],
+    "dcta_patchnorm_update_median": [P, P, P, c_int, c_int, P],
+    "dcta_patchnorm_abs_dev": [P, P, P, P, c_int, c_int, P, P],
+    "dcta_patchnorm_update_b": [P, P, P, P, c_int, c_int, P],
+    "dcta_zero_padding": [P, P, P, c_int64, c_int, P],
+    "dcta_lfq_quantize": [P, P, P, c_int64, c_int, c_int, c_float, P],
+    "dcta_lfq_indices_to_codes": [P, P, c_int64, c_int, c_int, c_float, P],
+    "dcta_lfq_commit_loss": [P, P, P, P, c_int64, c_int, c_float, P],
+    "dcta_lfq_distance": [P, P, c_int64, c_int, c_int, c_float, P],
+    "dcta_entropy_loss": [P, P, P, P, c_int64, c_int, c_int, c_float, c_float, P],
+    "dcta_perplexity": [P, c_int64, c_int, c_int64, P, P, P],
+    "dcta_vq_nearest": [P, P, P, P, P, c_int64, c_int, c_int, P],
+    "dcta_build_slot_map": [P, P, P, P, P, c_int, c_int, c_int64, c_int, c_int, c_int, P, P],
+    "dcta_unpatchify": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
+}
+_RESTYPES = {"dcta_last_error": c_char_p}
+REDUCE_SCRATCH = 2048  # DCTA_REDUCE_SCRATCH
+
+# kernels launched by one call of each entry point (memsets not counted)
+KERNELS_PER_CALL = {
+    "dcta_rgb_to_ipt": 1, "dcta_ipt_to_rgb": 1, "dcta_dct2_fwd": 2, "dcta_dct2_inv": 2, "dcta_patchify": 1,
+    "dcta_tile_scores": 1, "dcta_sort_tokens": 1, "dcta_pack_tiles": 1, "dcta_pack_lists": 1,
+    "dcta_patchnorm_apply": 1, "dcta_patchnorm_build_lists": 4, "dcta_patchnorm_batch_median": 1,
+    "dcta_patchnorm_update_median": 1, "dcta_patchnorm_abs_dev": 1, "dcta_patchnorm_update_b": 2,
+    "dcta_zero_padding": 1, "dcta_lfq_quantize": 1, "dcta_lfq_indices_to_codes": 1, "dcta_lfq_commit_loss": 2,
+    "dcta_lfq_distance": 1, "dcta_entropy_loss": 2, "dcta_perplexity": 2, "dcta_vq_nearest": 2,
+    "dcta_build_slot_map": 1, "dcta_unpatchify": 1,
+}
+launch_count = 0
+
+_lib = None
+
+
+def load():
+    """Loads libdcta.so once; raises DctaError if it is absent or its ABI differs."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DctaError(
+            f"{LIB_PATH} not found: build it with `python dct_autoencoder_b200/csrc/build.py` "
+            "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    if lib.dcta_abi_version() != ABI_VERSION:
+        raise DctaError(f"libdcta.so ABI {lib.dcta_abi_version()} != binding {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().dcta_last_error().decode()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise DctaError("libdcta kernels need CUDA tensors (no CPU fallback); got a tensor on " + str(t.device))
+
+
+def call(name: str, *args):
+    """Calls an entry point; raises DctaError with dcta_last_error() on a non-zero status."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    launch_count += KERNELS_PER_CALL.get(name, 0)
+    if rc != 0:
+        raise DctaError(f"{name} failed ({rc}): {lib.dcta_last_error().decode()}")
+
+
+def host_floats(values):
+    """A ctypes float array (host pointer argument)."""
+    vals = [float(v) for v in values]
+    return (c_float * len(vals))(*vals)

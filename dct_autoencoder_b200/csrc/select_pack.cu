@@ -1,0 +1,251 @@
+// Token importance scores, per-image descending sort, and gather + pad-and-stack packing
+// (reference: feature_extraction_dct_autoencoder.py:403-452 and 455-605, util.py:149-164).
+// All three are HBM-bound streaming kernels: one warp per token, 128-bit accesses.
+#include "common.cuh"
+
+namespace dcta {
+
+struct Importances {
+    float v[8];
+};
+
+// ------------------------------------------------------------------------------ scores
+// FE:409-416.  fp32 arithmetic in the reference's order with NO fma contraction, so that the
+// scores (and therefore the selection order) are bit-identical for identical coefficients:
+//   mags = amax|tile| * w ;  dist = float(-(th+tw)) / imp[c] ;  score = mags + dist
+template <int kVec>
+__global__ void __launch_bounds__(256) tile_scores_kernel(const float* __restrict__ tiles,
+                                                          float* __restrict__ scores,
+                                                          int64_t n_tokens_total, int th, int tw,
+                                                          int channels, int z, float mag_weight,
+                                                          Importances imp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int per_img = th * tw * channels;
+    for (int64_t tok = warp0; tok < n_tokens_total; tok += n_warps) {
+        const float* src = tiles + tok * z;
+        float m = 0.0f;
+        if (kVec == 4) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            for (int i = lane; i < z / 4; i += 32) {
+                float4 v = ld_stream(s4 + i);
+                m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            }
+        } else {
+            for (int i = lane; i < z; i += 32) m = fmaxf(m, fabsf(__ldg(src + i)));
+        }
+        m = warp_max(m);
+        if (lane == 0) {
+            const int t = (int)(tok % per_img);
+            const int c = t % channels;
+            const int tile = t / channels;
+            const int h = tile / tw, w = tile - h * tw;
+            const float mags = __fmul_rn(m, mag_weight);
+            const float dist = __fdiv_rn((float)(-(h + w)), imp.v[c]);
+            scores[tok] = __fadd_rn(mags, dist);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ sort
+// Per-image bitonic sort in shared memory on 64-bit keys  (~orderable(score)) << 32 | index :
+// ascending key order == descending score, ties by ascending flat index.  NaN scores sort first
+// (torch.sort treats NaN as the largest value).
+__device__ __forceinline__ uint32_t orderable(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(1024) sort_tokens_kernel(const float* __restrict__ scores,
+                                                           int32_t* __restrict__ order, int n_tok,
+                                                           int n_pad) {
+    extern __shared__ unsigned long long keys[];
+    const int64_t img = blockIdx.x;
+    const float* s = scores + img * n_tok;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        unsigned long long k = ~0ull;
+        if (i < n_tok) k = ((unsigned long long)(~orderable(s[i])) << 32) | (unsigned)i;
+        keys[i] = k;
+    }
+    __syncthreads();
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (n_pad >> 1); t += blockDim.x) {
+                const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                const int hi = lo | stride;
+                const bool up = ((lo & size) == 0);
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a > b) == up) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n_tok; i += blockDim.x)
+        order[img * n_tok + i] = (int32_t)(keys[i] & 0xffffffffu);
+}
+
+// ------------------------------------------------------------------------------ pack
+// One warp per output slot (row, s).  kTiles: source is the token grid + sort order;
+// otherwise per-image token lists through pointer tables.
+template <bool kTiles, int kVec>
+__global__ void __launch_bounds__(256) pack_kernel(
+    const float* __restrict__ tiles, const int32_t* __restrict__ order,
+    const float* const* __restrict__ src_patches, const int64_t* const* __restrict__ src_positions,
+    const int64_t* const* __restrict__ src_channels, const dcta_segment* __restrict__ segs,
+    const int32_t* __restrict__ row_seg_start, int n_rows, int s, int tw, int channels,
+    int n_tok_img, int z, float* __restrict__ patches, int64_t* __restrict__ positions,
+    int64_t* __restrict__ channels_out, int64_t* __restrict__ image_ids,
+    uint8_t* __restrict__ key_pad_mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = (int64_t)n_rows * s;
+    for (int64_t slot = warp0; slot < total; slot += n_warps) {
+        const int row = (int)(slot / s);
+        const int off = (int)(slot - (int64_t)row * s);
+        // locate the segment of this row that covers `off` (rows hold few segments)
+        int lo = row_seg_start[row], hi = row_seg_start[row + 1];
+        int seg = -1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const int so = segs[mid].offset;
+            if (off < so) hi = mid;
+            else if (off >= so + segs[mid].k) lo = mid + 1;
+            else { seg = mid; break; }
+        }
+        float* dst = patches + slot * z;
+        if (seg < 0) {  // padding slot (UT:155-157 zeros; FE:574-576 mask = True)
+            if (kVec == 4) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                for (int i = lane; i < z / 4; i += 32) st_stream(d4 + i, make_float4(0.f, 0.f, 0.f, 0.f));
+            } else {
+                for (int i = lane; i < z; i += 32) dst[i] = 0.0f;
+            }
+            if (lane == 0) {
+                positions[slot * 2] = 0;
+                positions[slot * 2 + 1] = 0;
+                channels_out[slot] = 0;
+                if (image_ids) image_ids[slot] = 0;
+                if (key_pad_mask) key_pad_mask[slot] = 1;
+            }
+            continue;
+        }
+        const dcta_segment sg = segs[seg];
+        const int j = off - sg.offset;
+        const float* src;
+        int64_t ph, pw, pc;
+        if (kTiles) {
+            const int tok = order[sg.img * n_tok_img + j];
+            src = tiles + (sg.img * n_tok_img + tok) * z;
+            pc = tok % channels;
+            const int tile = tok / channels;
+            ph = tile / tw;
+            pw = tile - (tile / tw) * tw;
+        } else {
+            src = src_patches[sg.img] + (int64_t)j * z;
+            ph = pw = pc = 0;
+            if (lane == 0) {
+                ph = src_positions[sg.img][2 * j];
+                pw = src_positions[sg.img][2 * j + 1];
+                pc = src_channels[sg.img][j];
+            }
+        }
+        if (kVec == 4) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = lane; i < z / 4; i += 32) st_stream(d4 + i, ld_stream(s4 + i));
+        } else {
+            for (int i = lane; i < z; i += 32) dst[i] = __ldg(src + i);
+        }
+        if (lane == 0) {
+            positions[slot * 2] = ph;
+            positions[slot * 2 + 1] = pw;
+            channels_out[slot] = pc;
+            if (image_ids) image_ids[slot] = sg.image_id;
+            if (key_pad_mask) key_pad_mask[slot] = 0;
+        }
+    }
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace dcta
+
+using namespace dcta;
+
+extern "C" int dcta_tile_scores(const float* tiles, float* scores, int64_t n_img, int th, int tw,
+                                int channels, int z, float mag_weight,
+                                const float* channel_importances_host, void* stream) {
+    DCTA_REQUIRE(tiles && scores && channel_importances_host, "tile_scores: null pointer");
+    DCTA_REQUIRE(channels >= 1 && channels <= 8, "tile_scores: 1..8 channels supported, got %d", channels);
+    DCTA_REQUIRE(th > 0 && tw > 0 && z > 0 && n_img >= 0, "tile_scores: bad sizes");
+    if (n_img == 0) return DCTA_OK;
+    Importances imp;
+    for (int i = 0; i < 8; ++i) imp.v[i] = i < channels ? channel_importances_host[i] : 1.0f;
+    const int64_t total = n_img * th * tw * channels;
+    const int grid = grid_for(total, 8);
+    if (z % 4 == 0 && al16(tiles))
+        tile_scores_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(tiles, scores, total, th, tw, channels, z, mag_weight, imp);
+    else
+        tile_scores_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(tiles, scores, total, th, tw, channels, z, mag_weight, imp);
+    return check_launch("tile_scores");
+}
+
+extern "C" int dcta_sort_tokens(const float* scores, int32_t* order, int64_t n_img, int n_tok,
+                                void* stream) {
+    DCTA_REQUIRE(scores && order, "sort_tokens: null pointer");
+    DCTA_REQUIRE(n_tok > 0 && n_tok <= 16384, "sort_tokens: n_tok=%d outside 1..16384", n_tok);
+    if (n_img == 0) return DCTA_OK;
+    int n_pad = 2;
+    while (n_pad < n_tok) n_pad <<= 1;
+    const size_t smem = (size_t)n_pad * sizeof(unsigned long long);
+    if (smem > 48 * 1024)  // per-device attribute: set on every call that needs it (cheap)
+        cudaFuncSetAttribute(sort_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    int threads = n_pad / 2;
+    if (threads > 1024) threads = 1024;
+    if (threads < 32) threads = 32;
+    sort_tokens_kernel<<<(unsigned)n_img, threads, smem, as_stream(stream)>>>(scores, order, n_tok, n_pad);
+    return check_launch("sort_tokens");
+}
+
+extern "C" int dcta_pack_tiles(const float* tiles, const int32_t* order, const dcta_segment* segs,
+                               const int32_t* row_seg_start, int n_rows, int s, int th, int tw,
+                               int channels, int z, float* patches, int64_t* positions,
+                               int64_t* channels_out, int64_t* image_ids, uint8_t* key_pad_mask,
+                               void* stream) {
+    DCTA_REQUIRE(tiles && order && segs && row_seg_start && patches && positions && channels_out,
+                 "pack_tiles: null pointer");
+    DCTA_REQUIRE(n_rows >= 0 && s > 0 && th > 0 && tw > 0 && channels > 0 && z > 0, "pack_tiles: bad sizes");
+    if (n_rows == 0) return DCTA_OK;
+    const int grid = grid_for((int64_t)n_rows * s, 8);
+    const int n_tok_img = th * tw * channels;
+    if (z % 4 == 0 && al16(tiles) && al16(patches))
+        pack_kernel<true, 4><<<grid, 256, 0, as_stream(stream)>>>(tiles, order, nullptr, nullptr, nullptr, segs, row_seg_start, n_rows, s, tw, channels, n_tok_img, z, patches, positions, channels_out, image_ids, key_pad_mask);
+    else
+        pack_kernel<true, 1><<<grid, 256, 0, as_stream(stream)>>>(tiles, order, nullptr, nullptr, nullptr, segs, row_seg_start, n_rows, s, tw, channels, n_tok_img, z, patches, positions, channels_out, image_ids, key_pad_mask);
+    return check_launch("pack_tiles");
+}
+
+extern "C" int dcta_pack_lists(const float* const* src_patches, const int64_t* const* src_positions,
+                               const int64_t* const* src_channels, const dcta_segment* segs,
+                               const int32_t* row_seg_start, int n_rows, int s, int z,
+                               float* patches, int64_t* positions, int64_t* channels_out,
+                               int64_t* image_ids, uint8_t* key_pad_mask, void* stream) {
+    DCTA_REQUIRE(src_patches && src_positions && src_channels && segs && row_seg_start && patches &&
+                     positions && channels_out, "pack_lists: null pointer");
+    DCTA_REQUIRE(n_rows >= 0 && s > 0 && z > 0, "pack_lists: bad sizes");
+    if (n_rows == 0) return DCTA_OK;
+    const int grid = grid_for((int64_t)n_rows * s, 8);
+    // per-image sources are torch allocations (>= 16-byte aligned at offset 0) but may be views:
+    // the 128-bit path needs z*4 % 16 == 0 AND every base aligned; the host shim guarantees the
+    // latter by passing contiguous tensors, else it asks for the scalar path via z's alignment.
+    if (z % 4 == 0 && al16(patches))
+        pack_kernel<false, 4><<<grid, 256, 0, as_stream(stream)>>>(nullptr, nullptr, src_patches, src_positions, src_channels, segs, row_seg_start, n_rows, s, 0, 0, 0, z, patches, positions, channels_out, image_ids, key_pad_mask);
+    else
+        pack_kernel<false, 1><<<grid, 256, 0, as_stream(stream)>>>(nullptr, nullptr, src_patches, src_positions, src_channels, segs, row_seg_start, n_rows, s, 0, 0, 0, z, patches, positions, channels_out, image_ids, key_pad_mask);
+    return check_launch("pack_lists");
+}

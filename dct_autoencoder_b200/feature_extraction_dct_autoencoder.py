@@ -1,0 +1,452 @@
+"""GPU feature extractor for the DCT autoencoder: image <-> packed rows of DCT-coefficient tokens.
+
+Drop-in for the reference's ``DCTAutoencoderFeatureExtractor``
+(feature_extraction_dct_autoencoder.py:107-656): same constructor arguments, same public methods
+(``preprocess``, ``iter_batches``, ``postprocess``, ``revert_patching``), same replaceable hooks
+(``_transform_image_in`` / ``_transform_image_out``), same quirks (next-fit packing, rows padded to
+``max_seq_len``, tail dropping in streaming mode, single-shot ``batch_size=None``).  The work is
+done by libdcta kernels; host code only decides geometry, draws ``k`` from Python's RNG in the
+reference's order and lays out the packing tables.
+
+Additions that the reference does not have (its API is per-image):
+``process_batch`` (a whole same-size batch -> ``DCTPatches`` in 5 kernel launches) and
+``postprocess_batch``.  They produce exactly what the per-image path followed by
+``iter_batches(batch_size=None)`` / ``postprocess`` produces.
+"""
+from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .dct_patches import DCTPatches
+from .util import (dct2, dct2_truncated, exp_trunc_dist, idct2, idct2_truncated, ipt_to_rgb,
+                   rgb_to_ipt, to_device_f32)
+
+_SEG_DTYPE = np.dtype([("row", "<i4"), ("offset", "<i4"), ("k", "<i4"), ("image_id", "<i4"), ("img", "<i8")])
+assert _SEG_DTYPE.itemsize == 24
+
+_RESERVED_KEYS = ("patches", "positions", "channels", "original_sizes", "patch_sizes")
+
+
+class _PackState:
+    """Next-fit packing state carried across ``iter_batches`` steps
+    (the reference's GroupPatchesState, feature_extraction_dct_autoencoder.py:96-104)."""
+
+    def __init__(self):
+        self.rows: List[List[int]] = []   # closed rows, each a list of indices into `items`
+        self.row: List[int] = []          # the open row
+        self.seq_len = 0
+
+
+class DCTAutoencoderFeatureExtractor:
+    def __init__(
+        self,
+        channels: int,
+        patch_size: int,
+        sample_patches_beta: float,
+        max_patch_h: int,
+        max_patch_w: int,
+        max_seq_len: int,
+        channel_importances: Tuple[float, ...] = (8.0, 1.0, 1.0),
+        patch_sample_magnitude_weight: float = 0.1,
+        device=None,
+    ):
+        self.channels = channels
+        self.patch_size = patch_size
+        self.sample_patches_beta = sample_patches_beta
+        self.max_patch_h = max_patch_h
+        self.max_patch_w = max_patch_w
+        self.max_seq_len = max_seq_len
+        self.channel_importances = torch.Tensor(channel_importances)
+        self.patch_sample_magnitude_weight = patch_sample_magnitude_weight
+        self.device = torch.device(device) if device is not None else None
+        self._table_cache: Dict[bytes, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _dev(self, like: Optional[torch.Tensor] = None) -> torch.device:
+        if like is not None and like.is_cuda:
+            return like.device
+        if self.device is not None:
+            return self.device
+        if not torch.cuda.is_available():
+            raise _lib.DctaError("no CUDA device: the feature extractor has no CPU path")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _hooks_overridden(self, name: str) -> bool:
+        return name in self.__dict__ or getattr(type(self), name) is not getattr(DCTAutoencoderFeatureExtractor, name)
+
+    def _get_crop_dims(self, h: int, w: int):
+        """feature_extraction_dct_autoencoder.py:312-345."""
+        assert h >= self.patch_size
+        assert w >= self.patch_size
+        p_h = max(int(h / self.patch_size), 1)
+        p_w = max(int(w / self.patch_size), 1)
+        return p_h * self.patch_size, p_w * self.patch_size
+
+    def _geometry(self, h: int, w: int):
+        """(ph, pw): tiles of the cropped plane (FE:166); (th, tw): tiles that can be selected
+        (FE:393); the kept coefficient block is (th*p, tw*p)."""
+        ch, cw = self._get_crop_dims(h, w)
+        ph, pw = ch // self.patch_size, cw // self.patch_size
+        return ph, pw, min(ph, self.max_patch_h), min(pw, self.max_patch_w)
+
+    # ------------------------------------------------------------------ replaceable transforms
+    @torch.no_grad()
+    def _transform_image_in(self, x: torch.Tensor) -> torch.Tensor:
+        """FE:130-142: RGB in [0, 1] -> IPT -> orthonormal 2-D DCT-II (computed in fp32)."""
+        og = x.dtype
+        y = dct2(rgb_to_ipt(to_device_f32(x, self._dev(x))), "ortho")
+        return y.to(og)
+
+    @torch.no_grad()
+    def _transform_image_out(self, x: torch.Tensor) -> torch.Tensor:
+        """FE:144-152."""
+        og = x.dtype
+        y = ipt_to_rgb(idct2(to_device_f32(x, self._dev(x)), "ortho"))
+        return y.to(og)
+
+    @torch.no_grad()
+    def _crop_image(self, x: torch.Tensor) -> torch.Tensor:
+        """FE:348-362."""
+        c, h, w = x.shape[-3:]
+        assert c == self.channels
+        c_h, c_w = self._get_crop_dims(h, w)
+        return x[..., :c_h, :c_w]
+
+    # ------------------------------------------------------------------ encode: kernels
+    def _token_grid(self, x: torch.Tensor) -> torch.Tensor:
+        """(b, c, h, w) fp32 CUDA images -> token grid (b, th, tw, c, p*p) in the reference's
+        pre-sort order (FE:374-399)."""
+        b, c, h, w = x.shape
+        assert c == self.channels
+        p = self.patch_size
+        _, _, th, tw = self._geometry(h, w)
+        if not self._hooks_overridden("_transform_image_in"):
+            # fused geometry: crop (FE:360) and max_patch clip (FE:393) only remove high
+            # frequencies, so only the first th*p x tw*p coefficients are ever computed
+            assert c == 3, "the IPT colour transform is defined for 3 channels"
+            ipt = rgb_to_ipt(x)
+            return dct2_truncated(ipt, th * p, tw * p, tile_p=p, channels=c)
+        planes = torch.stack([to_device_f32(self._transform_image_in(im), x.device) for im in x])
+        planes = self._crop_image(planes).contiguous()
+        tiles = torch.empty((b, th, tw, c, p * p), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("dcta_patchify", _lib.ptr(planes), _lib.ptr(tiles), b, c, planes.shape[-2],
+                      planes.shape[-1], th, tw, p, _lib.stream_ptr(x.device))
+        return tiles
+
+    def _sorted_order(self, tiles: torch.Tensor) -> torch.Tensor:
+        """FE:403-418: importance scores and their descending order, (b, th*tw*c) int32."""
+        b, th, tw, c, z = tiles.shape
+        n_tok = th * tw * c
+        scores = torch.empty((b, n_tok), dtype=torch.float32, device=tiles.device)
+        order = torch.empty((b, n_tok), dtype=torch.int32, device=tiles.device)
+        imp = _lib.host_floats(self.channel_importances.tolist()[:c] + [1.0] * max(0, c - len(self.channel_importances)))
+        with torch.cuda.device(tiles.device):
+            st = _lib.stream_ptr(tiles.device)
+            _lib.call("dcta_tile_scores", _lib.ptr(tiles), _lib.ptr(scores), b, th, tw, c, z,
+                      float(self.patch_sample_magnitude_weight), imp, st)
+            _lib.call("dcta_sort_tokens", _lib.ptr(scores), _lib.ptr(order), b, n_tok, st)
+        return order
+
+    def _choose_k(self, n: int) -> int:
+        """FE:429-435; consumes one draw of Python's global RNG when beta > 0, like the reference."""
+        k = n
+        if self.sample_patches_beta > 0.0:
+            k = min(round(exp_trunc_dist(self.sample_patches_beta)), k)
+            k = max(1, k)
+        return min(k, self.max_seq_len)
+
+    def _next_fit(self, ks: Sequence[int], state: Optional[_PackState] = None, first: int = 0) -> _PackState:
+        """FE:455-513."""
+        state = state or _PackState()
+        for i, k in enumerate(ks):
+            assert (k <= self.max_patch_h * self.max_patch_w * self.channels and k <= self.max_seq_len), \
+                f"patch with len {k} exceeds maximum sequence length"
+            if state.seq_len + k > self.max_seq_len:
+                state.rows.append(state.row)
+                state.row = []
+                state.seq_len = 0
+            state.row.append(first + i)
+            state.seq_len += k
+        return state
+
+    def _tables(self, rows: List[List[int]], ks: Dict[int, int], device, extra: Optional[np.ndarray] = None):
+        """Segment table + row starts (+ optional pointer tables) in ONE host->device copy.
+        Returns (device byte buffer, offsets dict)."""
+        n_seg = sum(len(r) for r in rows)
+        segs = np.zeros(n_seg, dtype=_SEG_DTYPE)
+        row_start = np.zeros(len(rows) + 1, dtype=np.int32)
+        i = 0
+        for r, row in enumerate(rows):
+            off = 0
+            for image_id, img in enumerate(row):
+                segs[i] = (r, off, ks[img], image_id, img)
+                off += ks[img]
+                i += 1
+            row_start[r + 1] = i
+        parts = [segs.view(np.uint8).reshape(-1), row_start.view(np.uint8).reshape(-1)]
+        if extra is not None:
+            parts.append(extra.view(np.uint8).reshape(-1))
+        offs, blobs, cur = [], [], 0
+        for part in parts:
+            offs.append(cur)
+            pad = (-len(part)) % 16
+            blobs.append(part)
+            if pad:
+                blobs.append(np.zeros(pad, np.uint8))
+            cur += len(part) + pad
+        blob = np.concatenate(blobs) if cur else np.zeros(16, np.uint8)
+        key = blob.tobytes() if extra is None else None
+        if key is not None and key in self._table_cache:
+            return self._table_cache[key], offs
+        dev = torch.from_numpy(blob).pin_memory().to(device, non_blocking=True)
+        if key is not None:
+            if len(self._table_cache) > 16:
+                self._table_cache.clear()
+            self._table_cache[key] = dev
+        return dev, offs
+
+    def _alloc_batch(self, n_rows: int, device):
+        s, z = self.max_seq_len, self.patch_size ** 2
+        return (torch.empty((n_rows, s, z), dtype=torch.float32, device=device),
+                torch.empty((n_rows, s, 2), dtype=torch.int64, device=device),
+                torch.empty((n_rows, s), dtype=torch.int64, device=device),
+                torch.empty((n_rows, s), dtype=torch.int64, device=device),
+                torch.empty((n_rows, s), dtype=torch.bool, device=device))
+
+    # ------------------------------------------------------------------ encode: public
+    @torch.no_grad()
+    def preprocess(self, im: torch.Tensor):
+        """FE:155-177: one (c, h, w) image -> dict(patches (k, p*p), positions (k, 2),
+        channels (k,), original_sizes (h, w), patch_sizes (ph, pw))."""
+        og = im.dtype
+        x = to_device_f32(im, self._dev(im))[None]
+        _, c, h, w = x.shape
+        ph, pw, th, tw = self._geometry(h, w)
+        tiles = self._token_grid(x)
+        order = self._sorted_order(tiles)
+        n_tok = th * tw * c
+        k = self._choose_k(n_tok)
+        z = self.patch_size ** 2
+        patches = torch.empty((1, k, z), dtype=torch.float32, device=x.device)
+        pos = torch.empty((1, k, 2), dtype=torch.int64, device=x.device)
+        chan = torch.empty((1, k), dtype=torch.int64, device=x.device)
+        tab, offs = self._tables([[0]], {0: k}, x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("dcta_pack_tiles", _lib.ptr(tiles), _lib.ptr(order), tab.data_ptr() + offs[0],
+                      tab.data_ptr() + offs[1], 1, k, th, tw, c, z, _lib.ptr(patches), _lib.ptr(pos),
+                      _lib.ptr(chan), None, None, _lib.stream_ptr(x.device))
+        patches = patches[0] if og == torch.float32 else patches[0].to(og)
+        return dict(patches=patches, positions=pos[0], channels=chan[0],
+                    original_sizes=(h, w), patch_sizes=(ph, pw))
+
+    @torch.no_grad()
+    def process_batch(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None) -> DCTPatches:
+        """Whole-batch encode of (b, c, h, w) same-size images: equals
+        ``next(iter_batches(iter([dict_collate([preprocess(im) for im in images])]), None))``."""
+        x = to_device_f32(images, self._dev(images))
+        b, c, h, w = x.shape
+        ph, pw, th, tw = self._geometry(h, w)
+        tiles = self._token_grid(x)
+        order = self._sorted_order(tiles)
+        n_tok = th * tw * c
+        if ks is None:
+            ks = [self._choose_k(n_tok) for _ in range(b)]
+        state = self._next_fit(ks)
+        rows = state.rows + ([state.row] if state.row else [])
+        tab, offs = self._tables(rows, dict(enumerate(ks)), x.device)
+        patches, pos, chan, ids, pad = self._alloc_batch(len(rows), x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("dcta_pack_tiles", _lib.ptr(tiles), _lib.ptr(order), tab.data_ptr() + offs[0],
+                      tab.data_ptr() + offs[1], len(rows), self.max_seq_len, th, tw, c,
+                      self.patch_size ** 2, _lib.ptr(patches), _lib.ptr(pos), _lib.ptr(chan),
+                      _lib.ptr(ids), _lib.ptr(pad), _lib.stream_ptr(x.device))
+        if images.dtype != torch.float32:
+            patches = patches.to(images.dtype)
+        return DCTPatches(patches=patches, key_pad_mask=pad, batched_image_ids=ids,
+                          patch_channels=chan, patch_positions=pos,
+                          patch_sizes=[(ph, pw)] * b, original_sizes=[(h, w)] * b,
+                          _data={}, _row_num_images=[len(r) for r in rows])
+
+    def _group_patches_by_max_seq_len(self, batched_patches, batched_positions=None,
+                                      batched_channels=None, state: Optional[_PackState] = None,
+                                      first: int = 0) -> _PackState:
+        """FE:455-513 (only the token counts matter for the grouping)."""
+        return self._next_fit([p.shape[0] for p in batched_patches], state, first)
+
+    @torch.no_grad()
+    def _batch_groups(self, rows: List[List[int]], items: Dict[int, dict], **dct_patch_kwargs) -> DCTPatches:
+        """FE:516-605 + util.py:149-164: concatenate each row's per-image token lists, right-pad
+        to ``max_seq_len``, build masks/ids -- one kernel over pointer tables."""
+        order = [i for row in rows for i in row]
+        device = self._dev(items[order[0]]["patches"]) if order else self._dev()
+        src = {}
+        for i in order:
+            it = items[i]
+            pt = to_device_f32(it["patches"], device)
+            if pt.data_ptr() % 16:
+                pt = pt.clone()
+            src[i] = (pt, it["positions"].to(device, torch.int64).contiguous(),
+                      it["channels"].to(device, torch.int64).contiguous())
+        local = {g: j for j, g in enumerate(order)}
+        ptrs = np.array([[src[g][0].data_ptr() for g in order], [src[g][1].data_ptr() for g in order],
+                         [src[g][2].data_ptr() for g in order]], dtype=np.int64).reshape(3, -1)
+        rows_local = [[local[g] for g in row] for row in rows]
+        ks = {local[g]: src[g][0].shape[0] for g in order}
+        tab, offs = self._tables(rows_local, ks, device, extra=ptrs)
+        patches, pos, chan, ids, pad = self._alloc_batch(len(rows), device)
+        n = len(order)
+        base = tab.data_ptr() + offs[2]
+        with torch.cuda.device(device):
+            _lib.call("dcta_pack_lists", base, base + 8 * n, base + 16 * n, tab.data_ptr() + offs[0],
+                      tab.data_ptr() + offs[1], len(rows), self.max_seq_len, self.patch_size ** 2,
+                      _lib.ptr(patches), _lib.ptr(pos), _lib.ptr(chan), _lib.ptr(ids), _lib.ptr(pad),
+                      _lib.stream_ptr(device))
+        # `src` tensors are freed in stream order on the launching stream, after the kernel
+        dt = items[order[0]]["patches"].dtype if order else torch.float32
+        if dt != torch.float32:
+            patches = patches.to(dt)
+        return DCTPatches(patches=patches, key_pad_mask=pad, batched_image_ids=ids,
+                          patch_channels=chan, patch_positions=pos,
+                          _row_num_images=[len(r) for r in rows], **dct_patch_kwargs)
+
+    @torch.no_grad()
+    def iter_batches(self, dataloader: Iterator[dict], batch_size: Optional[int] = None):
+        """FE:180-287.  ``dataloader`` yields dicts of lists (``dict_collate``, dataset.py:8-15)
+        with keys patches, positions, channels, original_sizes, patch_sizes (+ passthrough keys).
+
+        Streaming mode (``batch_size`` given): a batch of exactly ``batch_size`` rows is emitted
+        whenever MORE than ``batch_size`` rows are closed (FE:233); the tail is never emitted.
+        ``batch_size=None``: everything seen so far, including the open row, is emitted at once;
+        like the reference this mode is single-shot (every caller takes ``next(iter(...))``)."""
+        dataloader = iter(dataloader)
+        state = _PackState()
+        items: Dict[int, dict] = {}
+        n_seen = 0
+        n_emitted = 0
+        while True:
+            try:
+                d = next(dataloader)
+            except StopIteration:
+                return
+            n = len(d["patches"])
+            for i in range(n):
+                items[n_seen + i] = {k: v[i] for k, v in d.items()}
+            state = self._group_patches_by_max_seq_len(d["patches"], state=state, first=n_seen)
+            n_seen += n
+            if batch_size is None and state.row:                      # FE:220-229
+                state.rows.append(state.row)
+                state.row, state.seq_len = [], 0
+            if batch_size is None or len(state.rows) > batch_size:    # FE:233
+                emit = state.rows[:batch_size]
+                state.rows = state.rows[batch_size:] if batch_size is not None else state.rows
+                idx = [i for row in emit for i in row]
+                assert idx == list(range(n_emitted, n_emitted + len(idx)))
+                misc = {}
+                for i in idx:
+                    for k, v in items[i].items():
+                        if k not in _RESERVED_KEYS:
+                            misc.setdefault(k, []).append(v)
+                batch = self._batch_groups(
+                    emit, items,
+                    original_sizes=[tuple(items[i]["original_sizes"]) for i in idx],
+                    patch_sizes=[tuple(items[i]["patch_sizes"]) for i in idx],
+                    _data=misc)
+                for i in idx:
+                    del items[i]
+                n_emitted += len(idx)
+                yield batch
+                if batch_size is None:
+                    return
+
+    # ------------------------------------------------------------------ decode
+    def _slot_map(self, x: DCTPatches, th: int, tw: int):
+        b, s, _ = x.patches.shape
+        counts = x.row_num_images()
+        n_img = int(sum(counts))
+        base = np.zeros(b, dtype=np.int32)
+        if b > 1:
+            base[1:] = np.cumsum(counts[:-1])
+        dev = x.patches.device
+        key = b"base" + base.tobytes()
+        base_dev = self._table_cache.get(key)
+        if base_dev is None or base_dev.device != dev:
+            base_dev = torch.from_numpy(base).pin_memory().to(dev, non_blocking=True)
+            self._table_cache[key] = base_dev
+        slot_map = torch.empty((n_img, self.channels, th, tw), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("dcta_build_slot_map", _lib.ptr(x.patch_channels), _lib.ptr(x.patch_positions),
+                      _lib.ptr(x.batched_image_ids), _lib.ptr(x.key_pad_mask), _lib.ptr(base_dev), b, s,
+                      n_img, self.channels, th, tw, _lib.ptr(slot_map), _lib.stream_ptr(dev))
+        return slot_map, n_img
+
+    def _render_planes(self, x: DCTPatches, clip: bool):
+        """Token rows -> coefficient planes, grouped by plane size.  Returns
+        [(image indices, planes (n, c, rows, cols))]."""
+        _lib.require_cuda(x.patches, x.patch_positions, x.patch_channels, x.batched_image_ids, x.key_pad_mask)
+        p = self.patch_size
+        patches = to_device_f32(x.patches)
+        sizes = [tuple(int(v) for v in ps) for ps in x.patch_sizes]
+        if clip:
+            sizes = [(min(a, self.max_patch_h), min(b, self.max_patch_w)) for a, b in sizes]
+        th = max(a for a, _ in sizes)
+        tw = max(b for _, b in sizes)
+        slot_map, n_img = self._slot_map(x, th, tw)
+        assert n_img == len(sizes), f"{n_img} images in the rows but {len(sizes)} patch_sizes"
+        groups: Dict[Tuple[int, int], List[int]] = {}
+        for i, sz in enumerate(sizes):
+            groups.setdefault(sz, []).append(i)
+        out = []
+        dev = patches.device
+        for (gh, gw), idx in groups.items():
+            planes = torch.empty((len(idx), self.channels, gh * p, gw * p), dtype=torch.float32, device=dev)
+            sel = None
+            if len(groups) > 1 or idx != list(range(n_img)):
+                sel = torch.tensor(idx, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+            with torch.cuda.device(dev):
+                _lib.call("dcta_unpatchify", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), len(idx),
+                          self.channels, th, tw, p, gh * p, gw * p, _lib.ptr(planes), _lib.stream_ptr(dev))
+            out.append((idx, planes))
+        return out
+
+    @torch.no_grad()
+    def revert_patching(self, output: DCTPatches) -> List[torch.Tensor]:
+        """FE:607-656: one (c, ph*p, pw*p) coefficient plane per image, zeros where no token."""
+        res: List[Optional[torch.Tensor]] = [None] * len(output.patch_sizes)
+        for idx, planes in self._render_planes(output, clip=False):
+            for j, i in enumerate(idx):
+                res[i] = planes[j] if output.patches.dtype == torch.float32 else planes[j].to(output.patches.dtype)
+        return res
+
+    @torch.no_grad()
+    def postprocess(self, x: DCTPatches) -> List[torch.Tensor]:
+        """FE:289-310: un-normalised ``DCTPatches`` -> list of (c, h, w) RGB images."""
+        og = x.patches.dtype
+        res: List[Optional[torch.Tensor]] = [None] * len(x.patch_sizes)
+        if self._hooks_overridden("_transform_image_out"):
+            for i, (plane, (h, w)) in enumerate(zip(self.revert_patching(x), x.original_sizes)):
+                ch, cw = plane.shape[-2:]
+                pad = torch.zeros(self.channels, h, w, device=plane.device, dtype=plane.dtype)
+                pad[:, :ch, :cw] = plane
+                res[i] = self._transform_image_out(pad)
+            return res
+        for idx, planes in self._render_planes(x, clip=True):
+            by_size: Dict[Tuple[int, int], List[int]] = {}
+            for j, i in enumerate(idx):
+                by_size.setdefault(tuple(int(v) for v in x.original_sizes[i]), []).append(j)
+            for (h, w), js in by_size.items():
+                sub = planes if len(js) == len(idx) else planes[js].contiguous()
+                rgb = ipt_to_rgb(idct2_truncated(sub, h, w))   # zero padding of FE:300-304 is implicit
+                for n, j in enumerate(js):
+                    res[idx[j]] = rgb[n] if og == torch.float32 else rgb[n].to(og)
+        return res
+
+    @torch.no_grad()
+    def postprocess_batch(self, x: DCTPatches) -> torch.Tensor:
+        """Same as ``torch.stack(postprocess(x))`` for batches whose images share one size."""
+        assert len(set(map(tuple, x.original_sizes))) == 1 and len(set(map(tuple, x.patch_sizes))) == 1
+        (idx, planes), = self._render_planes(x, clip=True)
+        h, w = x.original_sizes[0]
+        return ipt_to_rgb(idct2_truncated(planes, int(h), int(w)))

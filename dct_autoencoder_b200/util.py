@@ -1,0 +1,210 @@
+"""Math utilities of the transform path, backed by libdcta kernels.
+
+Mirrors the functions of the reference's ``dct_autoencoder/util.py`` that the hot path uses
+(same names and argument meaning): ``rgb_to_ipt``/``ipt_to_rgb`` (util.py:70-97), ``dct2``/``idct2``
+(util.py:333-338), ``exp_trunc_dist`` (util.py:167-172), ``power_of_two`` (util.py:184-189),
+``masked_mean`` (util.py:346-353), ``compute_entropy_loss`` (util.py:355-387) and
+``calculate_perplexity`` (util.py:391-410).  All tensor work runs on the GPU.
+"""
+import math
+import random
+from functools import lru_cache
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# --- colour-space constants, built exactly as the reference builds them: fp32 torch ops on the
+# --- host at import time (util.py:21-43), so the kernels see bit-identical matrices.
+MsRGB = torch.tensor([[0.4124564, 0.3575761, 0.1804375],
+                      [0.2126729, 0.7151522, 0.0721750],
+                      [0.0193339, 0.1191920, 0.9503041]], dtype=torch.float32)
+MHPE = torch.tensor([[0.4002, 0.7076, -0.0807],
+                     [-0.2280, 1.1500, 0.0612],
+                     [0.0, 0.0, 0.9184]], dtype=torch.float32)
+Mipt = torch.tensor([[0.4, 0.4, 0.2],
+                     [4.455, -4.851, 0.3960],
+                     [0.8056, 0.3572, -1.1628]], dtype=torch.float32)
+Trgb2lms = MHPE @ MsRGB
+Tlms2rgb = Trgb2lms.inverse()
+IPT_GAMMA = 0.43
+
+_M_RGB2LMS = _lib.host_floats(Trgb2lms.flatten().tolist())
+_M_IPT = _lib.host_floats(Mipt.flatten().tolist())
+_M_IPT_INV = _lib.host_floats(Mipt.inverse().flatten().tolist())
+_M_LMS2RGB = _lib.host_floats(Tlms2rgb.flatten().tolist())
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.DctaError("no CUDA device: dct_autoencoder_b200 has no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device_f32(x: torch.Tensor, device=None) -> torch.Tensor:
+    """fp32, contiguous, on the GPU (host tensors are staged through pinned memory)."""
+    if not x.is_cuda:
+        device = device or default_device()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        if not x.is_pinned():
+            x = x.pin_memory()
+        return x.to(device, non_blocking=True)
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous()
+
+
+def _colorspace(x: torch.Tensor, fn: str, a, b) -> torch.Tensor:
+    og_dtype = x.dtype
+    x = to_device_f32(x)
+    if x.ndim < 3 or x.shape[-3] != 3:
+        raise ValueError(f"expected (..., 3, h, w), got {tuple(x.shape)}")
+    out = torch.empty_like(x)
+    plane = x.shape[-1] * x.shape[-2]
+    n_img = x.numel() // (3 * plane) if plane else 0
+    with torch.cuda.device(x.device):
+        _lib.call(fn, _lib.ptr(x), _lib.ptr(out), n_img, plane, a, b, _lib.stream_ptr(x.device))
+    return out if og_dtype == torch.float32 else out.to(og_dtype)
+
+
+def rgb_to_ipt(x: torch.Tensor) -> torch.Tensor:
+    """util.py:70-82."""
+    return _colorspace(x, "dcta_rgb_to_ipt", _M_RGB2LMS, _M_IPT)
+
+
+def ipt_to_rgb(x: torch.Tensor) -> torch.Tensor:
+    """util.py:85-97."""
+    return _colorspace(x, "dcta_ipt_to_rgb", _M_IPT_INV, _M_LMS2RGB)
+
+
+@lru_cache(maxsize=64)
+def _basis_host(n: int, k: int) -> np.ndarray:
+    q = np.arange(k, dtype=np.float64)[:, None]
+    m = np.arange(n, dtype=np.float64)[None, :]
+    c = np.cos(np.pi * (2 * m + 1) * q / (2 * n)) * math.sqrt(2.0 / n)
+    c[0, :] = math.sqrt(1.0 / n)
+    return c.astype(np.float32)
+
+
+_BASIS_CACHE = {}
+
+
+def dct_basis(n: int, k: int, device) -> torch.Tensor:
+    """First ``k`` rows of the orthonormal DCT-II matrix of size ``n`` as an fp32 (k, n) device
+    tensor; generated in float64 on the host, cached per (n, k, device)."""
+    device = torch.device(device)
+    key = (n, k, device.type, device.index)
+    t = _BASIS_CACHE.get(key)
+    if t is None:
+        t = torch.from_numpy(_basis_host(n, k)).to(device)
+        _BASIS_CACHE[key] = t
+    return t
+
+
+def dct2_truncated(x: torch.Tensor, kh: int, kw: int, tile_p: int = 0, channels: int = 1) -> torch.Tensor:
+    """``CH[:kh] . x . CW[:kw]^T`` over the last two axes of an fp32 CUDA tensor (..., h, w).
+    ``tile_p > 0`` writes the token-grid layout (n_img, kh/p, kw/p, channels, p*p) instead."""
+    h, w = x.shape[-2:]
+    n_planes = x.numel() // (h * w)
+    ch, cw = dct_basis(h, kh, x.device), dct_basis(w, kw, x.device)
+    work = torch.empty((n_planes, h, kw), dtype=torch.float32, device=x.device)
+    if tile_p:
+        y = torch.empty((n_planes // channels, kh // tile_p, kw // tile_p, channels, tile_p * tile_p),
+                        dtype=torch.float32, device=x.device)
+    else:
+        y = torch.empty(x.shape[:-2] + (kh, kw), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dcta_dct2_fwd", _lib.ptr(x), _lib.ptr(ch), _lib.ptr(cw), _lib.ptr(work), _lib.ptr(y),
+                  n_planes, h, w, kh, kw, tile_p, channels, _lib.stream_ptr(x.device))
+    return y
+
+
+def idct2_truncated(y: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    """``CH[:kh]^T . y . CW[:kw]`` : (..., kh, kw) coefficients -> (..., h, w) samples."""
+    kh, kw = y.shape[-2:]
+    n_planes = y.numel() // (kh * kw)
+    ch, cw = dct_basis(h, kh, y.device), dct_basis(w, kw, y.device)
+    work = torch.empty((n_planes, h, kw), dtype=torch.float32, device=y.device)
+    x = torch.empty(y.shape[:-2] + (h, w), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.call("dcta_dct2_inv", _lib.ptr(y), _lib.ptr(ch), _lib.ptr(cw), _lib.ptr(work), _lib.ptr(x),
+                  n_planes, h, w, kh, kw, _lib.stream_ptr(y.device))
+    return x
+
+
+def _check_norm(norm):
+    if norm != "ortho":
+        raise NotImplementedError("only norm='ortho' is implemented (the only mode the reference uses: "
+                                  "feature_extraction_dct_autoencoder.py:140,149)")
+
+
+def dct2(x: torch.Tensor, norm: Optional[str] = None) -> torch.Tensor:
+    """util.py:333-334 (torch_dct.dct_2d): orthonormal 2-D DCT-II over the last two axes."""
+    _check_norm(norm)
+    og = x.dtype
+    x = to_device_f32(x)
+    y = dct2_truncated(x, x.shape[-2], x.shape[-1])
+    return y if og == torch.float32 else y.to(og)
+
+
+def idct2(x: torch.Tensor, norm: Optional[str] = None) -> torch.Tensor:
+    """util.py:337-338 (torch_dct.idct_2d)."""
+    _check_norm(norm)
+    og = x.dtype
+    x = to_device_f32(x)
+    y = idct2_truncated(x, x.shape[-2], x.shape[-1])
+    return y if og == torch.float32 else y.to(og)
+
+
+def exp_trunc_dist(a: float) -> float:
+    """util.py:167-172: one draw of Python's module-global RNG (kept on the host so that the
+    number of kept patches follows the reference's random stream exactly)."""
+    x = random.random()
+    return -1 / a * math.log(x)
+
+
+def power_of_two(target: int) -> int:
+    """util.py:184-189."""
+    if target > 1:
+        for i in range(1, int(target)):
+            if 2 ** i >= target:
+                return 2 ** i
+    return 1
+
+
+def masked_mean(x: torch.Tensor, m: torch.Tensor, dim=None):
+    """util.py:346-353 (host-side composition of torch ops; tiny tensors only)."""
+    m = m.to(x.dtype)
+    x = x * m.reshape(m.shape + (1,) * (x.ndim - m.ndim))
+    x = x / m.sum()
+    return x.sum() if dim is None else x.sum(dim=dim)
+
+
+def compute_entropy_loss(affinity: torch.Tensor, mask: torch.Tensor, temperature=0.01, eps=1e-9):
+    """util.py:355-387 on a dense ``affinity`` (b, s, d, z); ``mask`` (b, s) False at padding."""
+    og = affinity.dtype
+    a = to_device_f32(affinity)
+    b, s, d, z = a.shape
+    m = mask.to(a.device).reshape(b * s).to(torch.uint8).contiguous()
+    scratch = torch.empty(z + 2, dtype=torch.float32, device=a.device)
+    result = torch.empty(1, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("dcta_entropy_loss", _lib.ptr(a), _lib.ptr(m), _lib.ptr(scratch), _lib.ptr(result),
+                  b * s, d, z, float(temperature), float(eps), _lib.stream_ptr(a.device))
+    return result[0].to(og)
+
+
+def calculate_perplexity(codes: torch.Tensor, codebook_size: int, null_index=-1):
+    """util.py:391-410."""
+    _lib.require_cuda(codes)
+    c = codes.reshape(-1).to(torch.int64).contiguous()
+    counts = torch.empty(codebook_size, dtype=torch.int64, device=c.device)
+    result = torch.empty(1, dtype=torch.float32, device=c.device)
+    with torch.cuda.device(c.device):
+        _lib.call("dcta_perplexity", _lib.ptr(c), c.numel(), codebook_size, int(null_index),
+                  _lib.ptr(counts), _lib.ptr(result), _lib.stream_ptr(c.device))
+    return result[0]

@@ -1,0 +1,154 @@
+"""VectorQuantize, eval (nearest-codebook) path, on the GPU.
+
+Mirrors the inference behaviour of the reference's ``VectorQuantize`` with a Euclidean codebook
+(vector_quantize.py:680-1050 -> EuclideanCodebook.forward :436-507 -> cdist :29-33, argmax :469,
+gather :222-226): ``forward(x, indices=None, mask=None, ...) -> (quantize, embed_ind, loss)``,
+``codebook`` property, ``get_codes_from_indices``, ``get_output_from_indices``; module/buffer
+names follow the reference (``_codebook.embed`` ...) so its checkpoints load.
+
+Codebook LEARNING (k-means init, EMA updates, dead-code expiry, affine re-parametrisation, cosine
+codebooks, gumbel/reinmax sampling, orthogonal regularisation and their all-reduces) is outside
+the transform path and is not implemented: ``forward`` in training mode raises.
+"""
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from .util import to_device_f32
+
+
+def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = True):
+    """x (T, d), embed (C, d) fp32 CUDA -> (indices int64 (T,), embed[indices] or None)."""
+    T, d = x.shape
+    C = embed.shape[0]
+    idx = torch.empty(T, dtype=torch.int64, device=x.device)
+    q = torch.empty_like(x) if return_quantized else None
+    e2 = torch.empty(C, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dcta_vq_nearest", _lib.ptr(x), _lib.ptr(embed), _lib.ptr(e2), _lib.ptr(idx), _lib.ptr(q),
+                  T, C, d, _lib.stream_ptr(x.device))
+    return idx, q
+
+
+class EuclideanCodebook(nn.Module):
+    """State holder with the reference's buffer names (vector_quantize.py:287-296)."""
+
+    def __init__(self, dim, codebook_size, num_codebooks=1):
+        super().__init__()
+        embed = torch.empty(num_codebooks, codebook_size, dim)
+        nn.init.kaiming_uniform_(embed)                       # uniform_init, vector_quantize.py:52-55
+        self.codebook_size = codebook_size
+        self.num_codebooks = num_codebooks
+        self.register_buffer("initted", torch.Tensor([True]))
+        self.register_buffer("cluster_size", torch.zeros(num_codebooks, codebook_size))
+        self.register_buffer("embed_avg", embed.clone())
+        self.register_buffer("embed", embed)
+
+
+class VectorQuantize(nn.Module):
+    def __init__(self, dim, codebook_size, codebook_dim=None, heads=1, separate_codebook_per_head=False,
+                 channel_last=True, accept_image_fmap=False, use_cosine_sim=False, affine_param=False,
+                 **training_kwargs):
+        super().__init__()
+        if use_cosine_sim or affine_param:
+            raise NotImplementedError("cosine-similarity / affine-parametrised codebooks are training "
+                                      "machinery outside the transform path")
+        self.dim = dim
+        self.heads = heads
+        self.separate_codebook_per_head = separate_codebook_per_head
+        codebook_dim = codebook_dim if codebook_dim is not None else dim
+        codebook_input_dim = codebook_dim * heads
+        requires_projection = codebook_input_dim != dim
+        self.project_in = nn.Linear(dim, codebook_input_dim) if requires_projection else nn.Identity()
+        self.project_out = nn.Linear(codebook_input_dim, dim) if requires_projection else nn.Identity()
+        self.has_projections = requires_projection
+        self._codebook = EuclideanCodebook(codebook_dim, codebook_size,
+                                           num_codebooks=heads if separate_codebook_per_head else 1)
+        self.codebook_size = codebook_size
+        self.accept_image_fmap = accept_image_fmap
+        self.channel_last = channel_last
+        self.training_kwargs = training_kwargs
+
+    @property
+    def codebook(self):
+        cb = self._codebook.embed
+        return cb if self.separate_codebook_per_head else cb[0]
+
+    @codebook.setter
+    def codebook(self, codes):
+        if not self.separate_codebook_per_head:
+            codes = codes[None]
+        self._codebook.embed.copy_(codes)
+
+    def get_codes_from_indices(self, indices):
+        """vector_quantize.py:814-831."""
+        codebook = self.codebook
+        if codebook.ndim <= 2:
+            codes = codebook[indices]
+            return codes.reshape(*codes.shape[:-2], -1) if self.heads > 1 else codes
+        b = indices.shape[0]
+        flat = indices.reshape(b, -1, indices.shape[-1])                    # b n h
+        h = flat.shape[-1]
+        codes = torch.stack([codebook[i][flat[..., i]] for i in range(h)], dim=2)  # b n h d
+        return codes.reshape(*indices.shape[:-1], -1)
+
+    def get_output_from_indices(self, indices):
+        return self.project_out(self.get_codes_from_indices(indices))
+
+    def forward(self, x, indices=None, mask=None, sample_codebook_temp=None, freeze_codebook=False):
+        """vector_quantize.py:837-1050, eval branch."""
+        if self.training:
+            raise NotImplementedError("VectorQuantize training (codebook learning) is outside the transform "
+                                      "path; call .eval()")
+        if indices is not None:
+            raise NotImplementedError("cross-entropy loss on given indices is a training feature")
+        orig_input = x
+        only_one = x.ndim == 2
+        if only_one:
+            assert mask is None
+            x = x[:, None]
+        need_transpose = not self.channel_last and not self.accept_image_fmap
+        if self.accept_image_fmap:
+            height, width = x.shape[-2:]
+            x = x.flatten(2).transpose(1, 2)                                # 'b c h w -> b (h w) c'
+        if need_transpose:
+            x = x.transpose(1, 2)
+        _lib.require_cuda(x)
+        x = self.project_in(x)
+        b, n, _ = x.shape
+        h, embed = self.heads, self._codebook.embed
+        d = embed.shape[-1]
+        xf = to_device_f32(x)
+        ef = to_device_f32(embed)
+        if h > 1 and self.separate_codebook_per_head:
+            xs = xf.reshape(b, n, h, d).permute(2, 0, 1, 3).contiguous()    # 'h b n d'
+            outs = [nearest_code(xs[i].reshape(b * n, d), ef[i].contiguous()) for i in range(h)]
+            ind = torch.stack([o[0].reshape(b, n) for o in outs], dim=-1)   # b n h
+            q = torch.stack([o[1].reshape(b, n, d) for o in outs], dim=2).reshape(b, n, h * d)
+        elif h > 1:
+            # shared codebook: heads are folded into the batch, '1 (b h) n d' (vector_quantize.py:874-875)
+            idx, qf = nearest_code(xf.reshape(b * n * h, d), ef[0].contiguous())
+            ind = idx.reshape(b, n, h)
+            q = qf.reshape(b, n, h * d)
+        else:
+            idx, qf = nearest_code(xf.reshape(b * n, d), ef[0].contiguous())
+            ind = idx.reshape(b, n)
+            q = qf.reshape(b, n, d)
+        q = q.to(x.dtype)
+        if self.accept_image_fmap:
+            ind = ind.reshape(b, height, width, *ind.shape[2:])
+        if only_one:
+            ind = ind[:, 0]
+        loss = torch.tensor([0.0], device=x.device)
+        q = self.project_out(q)
+        if need_transpose:
+            q = q.transpose(1, 2)
+        if self.accept_image_fmap:
+            q = q.transpose(1, 2).reshape(b, -1, height, width)
+        if only_one:
+            q = q[:, 0]
+        if mask is not None:
+            q = torch.where(mask[..., None], q, orig_input)                 # vector_quantize.py:1043-1048
+        return q, ind, loss

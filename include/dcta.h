@@ -1,0 +1,197 @@
+/*
+ * dcta.h -- C ABI of libdcta.so: the B200 (sm_100a) kernels behind the dct-autoencoder
+ * encode/decode transform path.
+ *
+ * The reference (theAdamColton/dct-autoencoder) is pure Python: there is no FFI to mirror.  The
+ * drop-in boundary is the Python surface listed in SURVEY.md 8(b); this header is what that
+ * surface binds to (dct_autoencoder_b200/_lib.py, ctypes).  Each entry point names the reference
+ * lines it replaces (paths relative to the reference's dct_autoencoder/ package: FE =
+ * feature_extraction_dct_autoencoder.py, UT = util.py, PN = patchnorm.py, VQ = vector_quantize.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense, row-major, in the shapes written next to them; float = fp32,
+ *     i64 = int64_t (the reference's index dtype), u8 = uint8_t (torch.bool storage);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it;
+ *   - nothing is allocated or freed: outputs and workspaces are caller-owned;
+ *   - return value: 0 = ok, <0 = DCTA_ERR_*; dcta_last_error() gives the message of the last
+ *     failure on the calling thread.  No call throws, no call synchronises the device.
+ */
+#ifndef DCTA_H_
+#define DCTA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCTA_OK 0
+#define DCTA_ERR_INVALID_ARG (-1)
+#define DCTA_ERR_LAUNCH (-2)
+#define DCTA_ERR_UNSUPPORTED (-3)
+
+const char* dcta_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int dcta_abi_version(void);
+/* Compute capability the library was compiled for (100 for sm_100a). */
+int dcta_compiled_arch(void);
+
+/* ------------------------------------------------------------------ colour space ---------- */
+/* UT:70-82 rgb_to_ipt (rgb_to_lms UT:56-60, channel_mult UT:46-47).
+ * rgb, ipt: (n_img, 3, plane).  m_rgb2lms_host, m_ipt_host: 3x3 row-major fp32 HOST matrices
+ * (the reference's Trgb2lms UT:40 and Mipt UT:37-39).  rgb and ipt must not overlap. */
+int dcta_rgb_to_ipt(const float* rgb, float* ipt, int64_t n_img, int64_t plane,
+                    const float* m_rgb2lms_host, const float* m_ipt_host, void* stream);
+/* UT:85-97 ipt_to_rgb.  m_ipt_inv_host = Mipt.inverse() (UT:91), m_lms2rgb_host = Tlms2rgb (UT:41). */
+int dcta_ipt_to_rgb(const float* ipt, float* rgb, int64_t n_img, int64_t plane,
+                    const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream);
+
+/* ------------------------------------------------------------------ DCT / IDCT ------------ */
+/* Truncated orthonormal 2-D DCT-II of n_planes planes (FE:140 + the crop of FE:348-362 and the
+ * max_patch clip of FE:393 folded into the basis):  Y = CH[:kh] . X . CW[:kw]^T.
+ *   x    (n_planes, h, w)
+ *   ch   (kh, h), cw (kw, w)      basis rows (host-generated in float64, rounded to fp32)
+ *   work (n_planes, h, kw)        scratch
+ * Output layout:
+ *   tile_p == 0 : y (n_planes, kh, kw) planes
+ *   tile_p  > 0 : token-grid layout of FE:374-380, y (n_planes / channels, kh/p, kw/p, channels, p*p)
+ *                 (kh, kw multiples of p; n_planes multiple of channels). */
+int dcta_dct2_fwd(const float* x, const float* ch, const float* cw, float* work, float* y,
+                  int64_t n_planes, int h, int w, int kh, int kw, int tile_p, int channels,
+                  void* stream);
+/* Truncated inverse (FE:149 with the zero padding of FE:300-304 folded into the basis):
+ *   X = CH[:kh]^T . Y . CW[:kw];  y (n_planes, kh, kw), work (n_planes, h, kw), x (n_planes, h, w). */
+int dcta_dct2_inv(const float* y, const float* ch, const float* cw, float* work, float* x,
+                  int64_t n_planes, int h, int w, int kh, int kw, void* stream);
+
+/* FE:374-380 rearrange "c (h p1) (w p2) -> (h w) c (p1 p2)" with the max_patch clip of FE:393-394,
+ * for coefficient planes produced by a caller-supplied transform:
+ *   planes (n_img, channels, rows, cols) -> tiles (n_img, th, tw, channels, p*p); th*p<=rows, tw*p<=cols. */
+int dcta_patchify(const float* planes, float* tiles, int64_t n_img, int channels_n, int rows,
+                  int cols, int th, int tw, int p, void* stream);
+
+/* ------------------------------------------------------------------ select / pack --------- */
+/* FE:403-416 importance scores of every token of the token grid, in the reference's pre-sort
+ * flat order (tile-major, channel-minor):  0.1*max|tile| - (th+tw)/channel_importance[c].
+ *   tiles (n_img, th, tw, channels, z)  ->  scores (n_img, th*tw*channels) */
+int dcta_tile_scores(const float* tiles, float* scores, int64_t n_img, int th, int tw, int channels,
+                     int z, float mag_weight, const float* channel_importances_host, void* stream);
+/* FE:418 per-image descending sort of the scores (ties: ascending flat index).
+ *   scores (n_img, n_tok) -> order (n_img, n_tok) int32.  n_tok <= 16384. */
+int dcta_sort_tokens(const float* scores, int32_t* order, int64_t n_img, int n_tok, void* stream);
+
+/* One packed row segment: k tokens of image `img` placed at slots [offset, offset+k) of row `row`
+ * with batched_image_id `image_id` (FE:455-513 next-fit result, computed on the host). */
+typedef struct {
+    int32_t row, offset, k, image_id;
+    int64_t img; /* tile mode: image index into tiles/order; list mode: index into the ptr tables */
+} dcta_segment;
+
+/* FE:437-452 gather by sorted index + FE:516-605 / UT:149-164 pad-and-stack, in one pass.
+ * Every element of every output is written exactly once (padding: zeros, key_pad_mask = 1).
+ *   segs (n_seg) device array sorted by (row, offset); row_seg_start (n_rows + 1) device
+ *   tiles (n_img, th*tw*channels, z), order (n_img, th*tw*channels)
+ *   patches (n_rows, s, z), positions (n_rows, s, 2) i64, channels_out (n_rows, s) i64,
+ *   image_ids (n_rows, s) i64 [nullable], key_pad_mask (n_rows, s) u8 [nullable] */
+int dcta_pack_tiles(const float* tiles, const int32_t* order, const dcta_segment* segs,
+                    const int32_t* row_seg_start, int n_rows, int s, int th, int tw, int channels,
+                    int z, float* patches, int64_t* positions, int64_t* channels_out,
+                    int64_t* image_ids, uint8_t* key_pad_mask, void* stream);
+/* Same packing for per-image token lists produced earlier by preprocess (FE:180-287 iter_batches
+ * path): src_* are device arrays of n_src device pointers, indexed by seg.img. */
+int dcta_pack_lists(const float* const* src_patches, const int64_t* const* src_positions,
+                    const int64_t* const* src_channels, const dcta_segment* segs,
+                    const int32_t* row_seg_start, int n_rows, int s, int z, float* patches,
+                    int64_t* positions, int64_t* channels_out, int64_t* image_ids,
+                    uint8_t* key_pad_mask, void* stream);
+
+/* ------------------------------------------------------------------ PatchNorm ------------- */
+/* PN:157-165 (inverse == 0):  clamp((x - median[c,h,w]) / (b[c,h,w]*sqrt(2) + eps), lo, hi)
+ * PN:167-177 (inverse != 0):  x * (b[c,h,w]*sqrt(2) + eps) + median[c,h,w]
+ *   x, out (n_tok, z); channels (n_tok) i64; positions (n_tok, 2) i64; median, b (C, H, W, z).
+ * Padding tokens are transformed with the statistics at (0,0,0) exactly as the reference does. */
+int dcta_patchnorm_apply(const float* x, const int64_t* channels, const int64_t* positions,
+                         const float* median, const float* b, float* out, int64_t n_tok, int z,
+                         int C, int H, int W, float eps, float lo, float hi, int inverse,
+                         void* stream);
+
+/* PN:101-150 statistic fitting, split where a multi-GPU sum can be inserted.
+ * Step 1 -- per-position token lists (deterministic: sorted by flat token index):
+ *   counts (n_pos) i32 out, offsets (n_pos + 1) i32 out, cursor (n_pos) i32 scratch,
+ *   list (2 * n_tok) i32: first half = sorted lists (out), second half scratch; n_pos = C*H*W.
+ *   key_pad_mask (n_tok) u8: 1 = padding, skipped (PN:105-108). */
+int dcta_patchnorm_build_lists(const int64_t* channels, const int64_t* positions,
+                               const uint8_t* key_pad_mask, int64_t n_tok, int C, int H, int W,
+                               int32_t* counts, int32_t* offsets, int32_t* cursor, int32_t* list,
+                               void* stream);
+/* Step 2 -- PN:123-130 per-position batch median (lower middle, as torch.median) and PN:112-119
+ * batch_n.  Writes the reduce-ready buffer  packed = [batch_n (n_pos) | batch_median*batch_n (n_pos*z)]. */
+int dcta_patchnorm_batch_median(const float* x, const int32_t* offsets, const int32_t* list,
+                                int n_pos, int z, float* packed, void* stream);
+/* Step 3 -- PN:135-138 running-median update from the (possibly all-reduced) packed buffer:
+ *   median <- (median*n + sum(batch_median*batch_n)) / clamp(n + batch_n, 1). */
+int dcta_patchnorm_update_median(float* median, const float* n, const float* packed, int n_pos,
+                                 int z, void* stream);
+/* Step 4 -- PN:140-143: abs_dev (n_pos*z) = sum over the position's tokens |x - median_new|. */
+int dcta_patchnorm_abs_dev(const float* x, const int32_t* offsets, const int32_t* list,
+                           const float* median, int n_pos, int z, float* abs_dev, void* stream);
+/* Step 5 -- PN:144-150 from the (possibly all-reduced) abs_dev and packed batch_n:
+ *   b <- (b*n + (abs_dev/clamp(batch_n,1))*batch_n) / clamp(n + batch_n, 1);  n <- n + batch_n. */
+int dcta_patchnorm_update_b(float* b, float* n, const float* packed, const float* abs_dev,
+                            int n_pos, int z, void* stream);
+/* PN:153-155: out = x with padding tokens zeroed. */
+int dcta_zero_padding(const float* x, const uint8_t* key_pad_mask, float* out, int64_t n_tok, int z,
+                      void* stream);
+
+/* ------------------------------------------------------------------ LFQ ------------------- */
+/* lfq.py:168-187 (eval): q = where(x > 0, +scale, -scale); indices[t, c] = sum_i (x>0) << (d-1-i).
+ *   x, q (n_tok, c*d) [q nullable]; indices (n_tok, c) i64.  d <= 62. */
+int dcta_lfq_quantize(const float* x, float* q, int64_t* indices, int64_t n_tok, int c, int d,
+                      float scale, void* stream);
+/* lfq.py:105-134: codes (n_tok, c*d) = bit ? +scale : -scale, MSB first. */
+int dcta_lfq_indices_to_codes(const int64_t* indices, float* codes, int64_t n_tok, int c, int d,
+                              float scale, void* stream);
+/* lfq.py:195-200 masked commitment loss:  sum over VALID tokens of (x - q)^2, divided by
+ * (n_valid * c * d).  mask (n_tok) u8, 1 = valid.  result: one float (device).
+ * scratch2: DCTA_REDUCE_SCRATCH floats (deterministic two-stage reduction). */
+#define DCTA_REDUCE_SCRATCH 2048
+int dcta_lfq_commit_loss(const float* x, const uint8_t* mask, float* result, float* scratch2,
+                         int64_t n_tok, int cd, float scale, void* stream);
+/* lfq.py:191: distance (n_tok, c, 2^d) = -2 * <x[t, c, :], codebook[j, :]>  (d <= 16). */
+int dcta_lfq_distance(const float* x, float* distance, int64_t n_tok, int c, int d, float scale,
+                      void* stream);
+/* UT:355-387 compute_entropy_loss on a dense affinity (n_tok, c, n_codes), mask (n_tok) u8 1=valid.
+ * scratch: (c * n_codes + 2) floats, zeroed by the call.  result: one float (device). */
+int dcta_entropy_loss(const float* affinity, const uint8_t* mask, float* scratch, float* result,
+                      int64_t n_tok, int c, int n_codes, float temperature, float eps, void* stream);
+/* UT:391-410 calculate_perplexity: counts (codebook_size) i64 scratch, result one float. */
+int dcta_perplexity(const int64_t* codes, int64_t n, int codebook_size, int64_t null_index,
+                    int64_t* counts, float* result, void* stream);
+
+/* ------------------------------------------------------------------ VectorQuantize -------- */
+/* VQ:29-33 cdist + VQ:467-469 argmax(-dist) + VQ:222-226/477 gather, never materialising the
+ * (n_tok, n_codes) distance matrix.
+ *   x (n_tok, d); embed (n_codes, d); e2 (n_codes) scratch (sum of squares, filled by the call);
+ *   indices (n_tok) i64; quantized (n_tok, d) [nullable] = embed[indices]. */
+int dcta_vq_nearest(const float* x, const float* embed, float* e2, int64_t* indices,
+                    float* quantized, int64_t n_tok, int n_codes, int d, void* stream);
+
+/* ------------------------------------------------------------------ un-patchify ----------- */
+/* FE:619-643: slot_map (n_img, channels, th, tw) i32 = flat token index (row*s + slot) of the LAST
+ * valid token at that position, -1 where none (the call fills it).
+ *   row_img_base (n_rows) i32: global index of the first image of each row. */
+int dcta_build_slot_map(const int64_t* channels, const int64_t* positions, const int64_t* image_ids,
+                        const uint8_t* key_pad_mask, const int32_t* row_img_base, int n_rows, int s,
+                        int64_t n_img, int channels_n, int th, int tw, int32_t* slot_map,
+                        void* stream);
+/* FE:635-653: planes (n_sel, channels, rows, cols) <- tokens, zero where no token.
+ *   img_sel (n_sel) i32 [nullable = identity]: which images of slot_map to render. */
+int dcta_unpatchify(const float* patches, const int32_t* slot_map, const int32_t* img_sel,
+                    int64_t n_sel, int channels_n, int th, int tw, int p, int rows, int cols,
+                    float* planes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCTA_H_ */

@@ -1,0 +1,228 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/dcta.h declares,
+host-side packing logic matches the oracle, the product path refuses to run without CUDA, and the
+multi-rank statistic protocol (gloo, world_size 2) reproduces the sequential reference rule."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import dcta_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def D():
+    import dct_autoencoder_b200 as d
+    return d
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "dcta.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return set(re.findall(r"\b(dcta_[a-z0-9_]+)\s*\(", src))
+
+
+def test_library_exports_every_declared_symbol(D):
+    lib = D._lib.load()      # raises if libdcta.so is missing or a symbol cannot be bound
+    syms = header_symbols()
+    assert len(syms) >= 28
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert set(D._lib.SIGNATURES) == syms
+    assert lib.dcta_abi_version() == D._lib.ABI_VERSION
+    assert lib.dcta_compiled_arch() == 100
+    out = subprocess.run(["nm", "-D", D._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (dcta_[a-z0-9_]+)", out))
+    assert syms <= exported
+
+
+def test_invalid_arguments_return_error_codes_without_a_gpu(D):
+    lib = D._lib.load()
+    rc = lib.dcta_dct2_fwd(None, None, None, None, None, 1, 8, 8, 8, 8, 0, 1, None)
+    assert rc == -1 and "null pointer" in D._lib.last_error()
+    rc = lib.dcta_sort_tokens(1, 1, 1, 1 << 20, None)
+    assert rc == -1 and "16384" in D._lib.last_error()
+    with pytest.raises(D._lib.DctaError):
+        D._lib.call("dcta_lfq_quantize", 1, 1, 1, 4, 1, 63, 1.0, None)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dct_autoencoder_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "dcta_oracle" not in src and "torch_dct_standin" not in src and "ref_shim" not in src, f
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_cuda(D):
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+    with pytest.raises(D._lib.DctaError):
+        fe.preprocess(torch.rand(3, 64, 64))
+    with pytest.raises(D._lib.DctaError):
+        D.util.rgb_to_ipt(torch.rand(3, 8, 8))
+    with pytest.raises(D._lib.DctaError):
+        D.LFQ(codebook_size=16, num_codebooks=2)(torch.rand(1, 4, 8), torch.ones(1, 4, dtype=torch.bool))
+
+
+def test_constants_match_reference_fixture(D, golden):
+    g = golden("constants")
+    assert np.array_equal(D.util.Trgb2lms.numpy(), g["Trgb2lms"])
+    assert np.array_equal(D.util.Tlms2rgb.numpy(), g["Tlms2rgb"])
+    assert np.array_equal(D.util.Mipt.numpy(), g["Mipt"])
+    assert np.array_equal(D.util.Mipt.inverse().numpy(), g["MiptInv"])
+    np.testing.assert_allclose(D.util._basis_host(45, 20), O.dct_basis(45, 20), atol=1e-7)
+
+
+def test_geometry_and_next_fit_match_oracle(D):
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+    ofe = O.FeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+    for h, w in [(512, 512), (1024, 1024), (256, 256), (300, 451), (14, 14), (27, 500)]:
+        assert fe._get_crop_dims(h, w) == ofe._get_crop_dims(h, w)
+    assert fe._geometry(512, 512) == (36, 36, 32, 32)
+    assert fe._geometry(1024, 1024) == (73, 73, 32, 32)
+    assert fe._geometry(256, 256) == (18, 18, 18, 18)
+    with pytest.raises(AssertionError):
+        fe._get_crop_dims(13, 100)
+    rng = np.random.default_rng(0)
+    fe.max_seq_len = ofe.max_seq_len = 1000
+    ks = rng.integers(1, 1001, 200).tolist()
+    st = fe._next_fit(ks)
+    ost = ofe.group_by_max_seq_len(ks)
+    assert st.rows == ost["groups"] and st.row == ost["group"] and st.seq_len == ost["seq_len"]
+    with pytest.raises(AssertionError):
+        fe._next_fit([1001])
+    for beta in (0.0, 0.02, 0.004, 0.5):
+        assert D.get_max_seq_length(32, 32, 3, beta) == O.get_max_seq_length(32, 32, 3, beta)
+    assert [D.util.power_of_two(i) for i in range(0, 20)] == [O.power_of_two(i) for i in range(0, 20)]
+
+
+def test_k_follows_the_reference_random_stream(D):
+    import random
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.01, 32, 32, 512)
+    ofe = O.FeatureExtractor(3, 14, 0.01, 32, 32, 512)
+    random.seed(42)
+    a = [fe._choose_k(3072) for _ in range(50)]
+    random.seed(42)
+    b = [ofe._choose_k(3072) for _ in range(50)]
+    assert a == b and min(a) >= 1 and max(a) <= 512
+
+
+def test_dct_patches_container(D):
+    ids = torch.tensor([[0, 0, 1, 1, 0], [0, 1, 2, 0, 0]])
+    pad = torch.tensor([[False, False, False, False, True], [False, False, False, True, True]])
+    dp = D.DCTPatches(patches=torch.zeros(2, 5, 4), key_pad_mask=pad, batched_image_ids=ids,
+                      patch_channels=torch.zeros(2, 5, dtype=torch.long),
+                      patch_positions=torch.arange(20).reshape(2, 5, 2),
+                      patch_sizes=[(1, 1)] * 5, original_sizes=[(4, 4)] * 5)
+    op = O.Patches(dp.patches.numpy(), pad.numpy(), ids.numpy(), dp.patch_channels.numpy(),
+                   dp.patch_positions.numpy(), [], [])
+    assert dp._attn_mask is None                               # lazy
+    assert np.array_equal(dp.attn_mask.numpy(), op.attn_mask)  # reference polarity, FE:580-584
+    assert tuple(dp.attn_mask.shape) == (2, 1, 5, 5)
+    assert dp.row_num_images() == [2, 3]
+    assert torch.equal(dp.h_indices, dp.patch_positions[..., 0])
+    cp = dp.shallow_copy()
+    cp.patches = torch.ones(2, 5, 4)
+    assert float(dp.patches.sum()) == 0.0 and cp.key_pad_mask is dp.key_pad_mask
+    assert dp.to(torch.device("cpu")) is dp
+    codes = torch.arange(2 * 5 * 3).reshape(2, 5, 3)
+    objs = D.to_dict(dp, codes)
+    assert len(objs) == 5 and [len(o["codes"]) for o in objs] == [2, 2, 1, 1, 1]
+    assert objs[1]["codes"][0] == {"c": 0, "h": 4, "w": 5, "data": [6, 7, 8]}
+    back, bc = D.from_dict(objs[0])
+    assert bc.tolist() == [[0, 1, 2], [3, 4, 5]] and back.patch_positions.tolist() == [[[0, 1], [2, 3]]]
+
+
+def test_segment_table_layout(D):
+    fe = D.DCTAutoencoderFeatureExtractor(3, 4, 0.0, 4, 4, 48)
+    from dct_autoencoder_b200.feature_extraction_dct_autoencoder import _SEG_DTYPE
+    import ctypes
+    assert ctypes.sizeof(D._lib.Segment) == _SEG_DTYPE.itemsize == 24
+    assert [f[0] for f in D._lib.Segment._fields_] == list(_SEG_DTYPE.names)
+
+
+# --------------------------------------------------------------------------- multi-rank protocol
+_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "oracle"))
+import dcta_oracle as O
+from dct_autoencoder_b200.patchnorm import all_reduce_sum_, stats_sync_enabled
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", rank=rank, world_size=2)
+assert stats_sync_enabled()
+C, H, W, p = 2, 3, 3, 2
+z = p * p
+n_pos = C * H * W
+def shard(r):
+    rng = np.random.default_rng(100 + r)
+    T = 60 + 10 * r
+    return (rng.standard_normal((T, z)).astype(np.float32), rng.integers(0, C, T), rng.integers(0, H, T), rng.integers(0, W, T))
+x, c, h, w = shard(rank)
+flat = c * H * W + h * W + w
+# phase 1: what dcta_patchnorm_batch_median writes -- [batch_n | batch_median * batch_n]
+packed = np.zeros(n_pos + n_pos * z, np.float32)
+for pid in range(n_pos):
+    rows = x[flat == pid]
+    packed[pid] = len(rows)
+    if len(rows):
+        packed[n_pos + pid * z: n_pos + (pid + 1) * z] = np.partition(rows, (len(rows) - 1) // 2, axis=0)[(len(rows) - 1) // 2] * np.float32(len(rows))
+t = torch.from_numpy(packed)
+all_reduce_sum_(t)
+g = t.numpy()
+n0 = np.zeros(n_pos, np.float32)
+median = (np.zeros((n_pos, z), np.float32) * n0[:, None] + g[n_pos:].reshape(n_pos, z)) / np.maximum(n0 + g[:n_pos], 1)[:, None]
+# phase 2: sum |x - median|
+ad = np.zeros((n_pos, z), np.float32)
+np.add.at(ad, flat, np.abs(x - median[flat]))
+t2 = torch.from_numpy(ad)
+all_reduce_sum_(t2)
+b = (np.ones((n_pos, z), np.float32) * n0[:, None] + (t2.numpy() / np.maximum(g[:n_pos], 1)[:, None]) * g[:n_pos, None]) / np.maximum(n0 + g[:n_pos], 1)[:, None]
+# oracle: the reference rule applied sequentially to each rank's shard in rank order (SURVEY 8e)
+pn = O.PatchNorm(H, W, p, C)
+for r in range(2):
+    xs, cs, hs, ws = shard(r)
+    pn.update_stats(xs, cs, hs, ws)
+assert np.array_equal(pn.n.reshape(-1), g[:n_pos])
+np.testing.assert_allclose(median, pn.median.reshape(n_pos, z), rtol=1e-5, atol=1e-6)
+# b: the sequential reference measures deviations around INTERMEDIATE medians, so it is compared with
+# the rule itself evaluated on the concatenated shards: sum_all |x - median_global| / n_total
+xa = np.concatenate([shard(r)[0] for r in range(2)])
+fa = np.concatenate([shard(r)[1] * H * W + shard(r)[2] * W + shard(r)[3] for r in range(2)])
+eb = np.zeros((n_pos, z), np.float64)
+np.add.at(eb, fa, np.abs(xa - median[fa]).astype(np.float64))
+eb = eb / np.maximum(g[:n_pos], 1)[:, None]
+seen = g[:n_pos] > 0
+np.testing.assert_allclose(b[seen], eb[seen], rtol=1e-5, atol=1e-6)
+assert np.all(b[~seen] == 0)          # unseen positions: b goes 1 -> 0 on the first update (PN:146-148)
+# and equals the single-process result on the concatenated batch when medians agree: check determinism
+gathered = [torch.zeros_like(t2) for _ in range(2)]
+dist.all_gather(gathered, torch.from_numpy(b.astype(np.float32)))
+assert torch.equal(gathered[0], gathered[1])      # every rank ends with identical tables
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_patchnorm_stat_sync_protocol_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o
