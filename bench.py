@@ -121,11 +121,21 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            t0 = time.time()          # nvidia-smi needs a moment to start: wait for its first line
+            while time.time() - t0 < 5.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def mark(self):
+        """Number of samples taken so far (samples after this belong to the timed region)."""
+        try:
+            return sum(1 for _ in open(self.path))
+        except Exception:
+            return 0
+
+    def stop(self, skip: int = 0):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
         if self.proc is None:
             return out
@@ -136,7 +146,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         try:
-            for ln in open(self.path):
+            for i, ln in enumerate(open(self.path)):
+                if i < skip:
+                    continue
                 f = [x.strip() for x in ln.split(",")]
                 if len(f) < 9:
                     continue
@@ -221,14 +233,21 @@ def run_ours(a):
         return rec, codes
 
     sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(a.warmup):
-        step()
     if sampler:
         sampler.start()
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    skip = sampler.mark() if sampler else 0
     l0 = _lib.launch_count
     ms = timed(step, a.steps, 0)
     launches = _lib.launch_count - l0
-    clocks = sampler.stop() if sampler else None
+    if sampler and ms < 400:       # keep the GPU under the same load until a few samples exist
+        t_end = time.time() + 0.5
+        while time.time() < t_end:
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop(skip) if sampler else None
     value = world * B * a.steps / (ms / 1e3)
 
     # ---- end to end through the public API with HOST buffers (pinned in, pinned out)

@@ -509,6 +509,7 @@ def test_pipeline_matches_oracle_with_bit_level_exemptions(D):
     """encode on seeded images vs the oracle: LFQ bits equal except where |normalised value| < EPS_LFQ."""
     torch.manual_seed(3)
     x = torch.rand(3, 3, 112, 84)
+    x_fit = torch.rand(8, 3, 112, 84)     # statistics from OTHER images (else 1/3 of the values sit on the median)
     fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
     ofe = O.FeatureExtractor(3, 14, 0.0, 32, 32, 3072)
     pn = D.PatchNorm(32, 32, 14, 3).cuda()
@@ -516,12 +517,15 @@ def test_pipeline_matches_oracle_with_bit_level_exemptions(D):
     lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).cuda().eval()
     olfq = O.LFQ(codebook_size=2 ** 14, num_codebooks=14)
     pipe = D.TransformPipeline(fe, pn, lfq)
-    pipe.fit_norm(x.cuda())
-    items = [ofe.preprocess(im.numpy()) for im in x]
-    ob = next(ofe.iter_batches(iter([{k: [it[k] for it in items] for k in items[0]}]), None))
-    opn.forward(ob)
+    pipe.fit_norm(x_fit.cuda())
+    collate = lambda its: {k: [it[k] for it in its] for k in its[0]}
+    fit_items = [ofe.preprocess(im.numpy()) for im in x_fit]
+    opn.forward(next(ofe.iter_batches(iter([collate(fit_items)]), None)))
     opn.frozen = True
     np.testing.assert_allclose(npy(pn.median), opn.median, atol=2e-5)
+    np.testing.assert_allclose(npy(pn.b), opn.b, atol=2e-5)
+    items = [ofe.preprocess(im.numpy()) for im in x]
+    ob = next(ofe.iter_batches(iter([collate(items)]), None))
     batch, q, codes = pipe.encode(x.cuda())
     ob.patches = opn.forward(ob)
     oq, ocodes, _, _ = olfq.forward(ob.patches, ~ob.key_pad_mask)
@@ -529,7 +533,7 @@ def test_pipeline_matches_oracle_with_bit_level_exemptions(D):
     assert tok_same.mean() > 0.98
     bits_diff = (npy(q) != oq) & tok_same[..., None]
     assert np.all(np.abs(ob.patches[bits_diff]) < 1e-3)   # differences only next to the sign boundary
-    assert bits_diff.mean() < 1e-3
+    assert bits_diff.mean() < 2e-4
     rec = pipe.decode(batch, q)
     ob.patches = oq
     ob.patches = opn.inverse_norm(ob)
@@ -560,7 +564,8 @@ def test_config2_shape_properties(D):
     y1 = D.util.dct2_truncated(ipt[:1], 448, 448)
     y2 = D.util.dct2_truncated(ipt[1:2], 448, 448)
     y12 = D.util.dct2_truncated(ipt[:1] + ipt[1:2], 448, 448)
-    assert float((y12 - y1 - y2).abs().max()) <= COEF_RTOL * float(y12.abs().max())
+    # three independently rounded results: 3x the single-transform tolerance
+    assert float((y12 - y1 - y2).abs().max()) <= 3 * COEF_RTOL * float(y12.abs().max())
     # decode(encode) with nothing quantised == low-pass of the image: IDCT of the kept block
     rec = fe.postprocess_batch(b)
     ref = D.util.ipt_to_rgb(D.util.idct2_truncated(coef, 512, 512))
