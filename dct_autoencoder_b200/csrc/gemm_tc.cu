@@ -1,0 +1,694 @@
+// Split-precision tensor-core GEMM for the DCT / IDCT basis contractions (sm_100a: TMA + tcgen05 + TMEM).
+//
+//   D[b] (M x N, fp32) = sum_k A[b][m,k] * B[b][n,k]          (both operands K-major)
+//
+// Every fp32 operand v is carried as two fp16 planes  v*2^s = hi + lo  (hi = rn16(v*2^s),
+// lo = rn16(v*2^s - hi): 22 significand bits, fp16 subnormals keep the absolute error at 2^-25).
+// The product is accumulated in fp32 in TMEM from three tcgen05.mma per k-step:
+//   hi*hi + hi*lo + lo*hi        (the dropped lo*lo term is 2^-22 relative)
+// at the fp16 tensor rate, i.e. fp32-class accuracy at 1/3 of the dense fp16 peak.
+//
+// Kernel shape (one 128x128 output tile per CTA, 2 CTAs per SM so one CTA's epilogue overlaps the
+// other's main loop):
+//   warp 0 / one lane : TMA producer  -- 4 tiles (A_hi, A_lo, B_hi, B_lo) of 128 x 32 fp16 per stage,
+//                       SWIZZLE_64B, 3-stage mbarrier ring (96 KB)
+//   warp 1 / one lane : tcgen05.mma issuer, M=128 N=128 K=16, accumulator = 128 TMEM columns
+//   all 4 warps       : epilogue: tcgen05.ld 32x32b -> registers -> (scale) -> shared-memory
+//                       transpose (reusing the pipeline buffers) -> coalesced global stores in one
+//                       of three layouts (fp32 planes, fp16 hi/lo planes for the next GEMM, or the
+//                       token grid of feature_extraction_dct_autoencoder.py:374-380).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace dcta {
+
+constexpr int TM = 128, TN = 128, TK = 32, STAGES = 3;
+constexpr int TILE_BYTES = TM * TK * 2;          // 8 KB: one 128 x 32 fp16 operand tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
+constexpr int EPI_PITCH = TN + 1;                // fp32 staging pitch (odd: conflict-free)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+static_assert(TM * EPI_PITCH * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the ring");
+
+struct EpiArgs {
+    int mode;                 // 0: fp32 planes, 1: fp16 hi/lo planes, 2: fp32 token grid
+    float* out_f32;
+    __half* out_hi;
+    __half* out_lo;
+    int64_t ld, batch_stride; // element pitch / per-batch stride of the plane outputs
+    const float* row_scale;   // optional per-row (m) factor
+    float alpha;              // global factor
+    const float* dc;          // optional per-batch constant handled outside the GEMM (see dc_mode)
+    int dc_mode;              // 0: none, 1: add dc[b] to element (0,0), 2: add dc[b] to every element
+    int M, N;
+    int tile_p, channels, tiles_h, tiles_w;
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    uint32_t ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s at 1.9 GHz
+    }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile, rows of TK*2 = 64 bytes, SWIZZLE_64B: 8-row atoms of 512 B stacked along M/N
+// (SBO = 512 B, LBO unused), descriptor version 1 (sm_100), layout type 4.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffff) >> 4);            // start address  [0,14)
+    d |= (uint64_t)(512 >> 4) << 32;                     // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                              // version = 1
+    d |= (uint64_t)4 << 61;                              // SWIZZLE_64B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=TN
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// ------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(128, 2)
+gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  int a_batched, int b_batched, int num_k_blocks, EpiArgs ep) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t acc_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * TN, m0 = blockIdx.y * TM, batch = blockIdx.z;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, TN);   // 128 fp32 accumulator columns
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer
+        const int ab = a_batched ? batch : 0, bb = b_batched ? batch : 0;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* st = smem + s * STAGE_BYTES;
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_3d(&map_a_hi, &full_bar[s], st, kb * TK, m0, ab);
+            tma_load_3d(&map_a_lo, &full_bar[s], st + TILE_BYTES, kb * TK, m0, ab);
+            tma_load_3d(&map_b_hi, &full_bar[s], st + 2 * TILE_BYTES, kb * TK, n0, bb);
+            tma_load_3d(&map_b_lo, &full_bar[s], st + 3 * TILE_BYTES, kb * TK, n0, bb);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t base = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < TK / 16; ++k) {
+                const uint32_t ko = k * 32;  // 16 fp16 = 32 bytes along K inside the swizzle atom
+                const uint64_t a_hi = smem_desc_sw64(base + ko);
+                const uint64_t a_lo = smem_desc_sw64(base + TILE_BYTES + ko);
+                const uint64_t b_hi = smem_desc_sw64(base + 2 * TILE_BYTES + ko);
+                const uint64_t b_lo = smem_desc_sw64(base + 3 * TILE_BYTES + ko);
+                umma_f16(tmem_acc, a_lo, b_hi, kIdesc, (kb | k) ? 1u : 0u);   // small terms first
+                umma_f16(tmem_acc, a_hi, b_lo, kIdesc, 1u);
+                umma_f16(tmem_acc, a_hi, b_hi, kIdesc, 1u);
+            }
+            umma_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
+        }
+        umma_commit(&acc_bar);                   // accumulator complete
+    }
+    __syncwarp();
+
+    // ---------------- epilogue (all 4 warps; warp w owns TMEM lanes / tile rows 32w .. 32w+31)
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    float* stage_f32 = reinterpret_cast<float*>(smem);   // the ring is idle now: all MMAs have completed
+    const int row = warp * 32 + lane;
+    const int gm = m0 + row;
+    float rs = ep.alpha;
+    if (ep.row_scale != nullptr && gm < ep.M) rs *= __ldg(ep.row_scale + gm);
+#pragma unroll
+    for (int c = 0; c < TN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + c * 32, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage_f32[row * EPI_PITCH + c * 32 + j] = __uint_as_float(r[j]) * rs;
+    }
+    __syncwarp();
+    const float dcv = ep.dc_mode ? __ldg(ep.dc + batch) : 0.0f;
+    // each warp streams out its own 32 rows, lanes along n (coalesced)
+    for (int rr = 0; rr < 32; ++rr) {
+        const int m = m0 + warp * 32 + rr;
+        if (m >= ep.M) break;
+        const float* src = stage_f32 + (warp * 32 + rr) * EPI_PITCH;
+#pragma unroll
+        for (int q = 0; q < TN / 32; ++q) {
+            const int n = n0 + q * 32 + lane;
+            if (n >= ep.N) continue;
+            float v = src[q * 32 + lane];
+            if (ep.dc_mode == 2 || (ep.dc_mode == 1 && m == 0 && n == 0)) v += dcv;
+            if (ep.mode == 0) {
+                ep.out_f32[(int64_t)batch * ep.batch_stride + (int64_t)m * ep.ld + n] = v;
+            } else if (ep.mode == 1) {
+                const __half h = __float2half_rn(v);
+                const __half l = __float2half_rn(v - __half2float(h));
+                const int64_t o = (int64_t)batch * ep.batch_stride + (int64_t)m * ep.ld + n;
+                ep.out_hi[o] = h;
+                ep.out_lo[o] = l;
+            } else {
+                const int p = ep.tile_p;
+                const int64_t img = batch / ep.channels;
+                const int ch = batch - (int)img * ep.channels;
+                const int th = m / p, pi = m - th * p;
+                const int tw = n / p, pj = n - tw * p;
+                const int64_t tok = ((img * ep.tiles_h + th) * ep.tiles_w + tw) * ep.channels + ch;
+                ep.out_f32[tok * (p * p) + pi * p + pj] = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_acc, TN);
+}
+
+// ------------------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// rows x k fp16 matrix with pitch `ld` elements, `batch` of them `batch_stride` elements apart
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int k, int64_t ld, int64_t batch, int64_t batch_stride) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return DCTA_ERR_UNSUPPORTED; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) || (batch > 1 && batch_stride % 8)) {
+        set_error("gemm_split: operand planes need 16-byte aligned base, pitch and batch stride");
+        return DCTA_ERR_INVALID_ARG;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? batch_stride : (int64_t)rows * ld) * 2};
+    cuuint32_t box[3] = {TK, TM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return DCTA_ERR_LAUNCH; }
+    return DCTA_OK;
+}
+
+struct Operand {
+    const __half* hi;
+    const __half* lo;
+    int rows;
+    int64_t ld, batch_stride;   // batch_stride == 0: shared by every batch item
+};
+
+static int launch_gemm_split(const Operand& A, const Operand& B, int K, int64_t batch, const EpiArgs& ep, void* stream) {
+    if (batch == 0 || ep.M == 0 || ep.N == 0) return DCTA_OK;
+    if (batch > 65535) { set_error("gemm_split: more than 65535 batch items per call"); return DCTA_ERR_UNSUPPORTED; }
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    const int64_t ab = A.batch_stride ? batch : 1, bb = B.batch_stride ? batch : 1;
+    if ((rc = make_map(&ma_hi, A.hi, A.rows, K, A.ld, ab, A.batch_stride))) return rc;
+    if ((rc = make_map(&ma_lo, A.lo, A.rows, K, A.ld, ab, A.batch_stride))) return rc;
+    if ((rc = make_map(&mb_hi, B.hi, B.rows, K, B.ld, bb, B.batch_stride))) return rc;
+    if ((rc = make_map(&mb_lo, B.lo, B.rows, K, B.ld, bb, B.batch_stride))) return rc;
+    cudaFuncSetAttribute(gemm_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    dim3 grid((unsigned)ceil_div(ep.N, TN), (unsigned)ceil_div(ep.M, TM), (unsigned)batch);
+    gemm_split_kernel<<<grid, 128, SMEM_BYTES, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, A.batch_stride != 0,
+                                                                      B.batch_stride != 0, (int)ceil_div(K, TK), ep);
+    return check_launch("gemm_split");
+}
+
+// ------------------------------------------------------------------------------ split producers
+// The tensor core accumulates in fp32 with truncation, so a large common-mode term (the image mean /
+// the DC coefficient) would bias every partial sum the same way.  The producers therefore remove a
+// per-plane constant before the split and hand it to the GEMM epilogue, which adds its exact
+// contribution back (DCT of a constant is the DC coefficient only).
+constexpr int kSumChunks = 32;   // deterministic two-level plane sums: [plane][chunk]
+
+__device__ __forceinline__ void split16(float v, float scale, __half& h, __half& l) {
+    const float s = v * scale;
+    h = __float2half_rn(s);
+    l = __float2half_rn(s - __half2float(h));
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (wid == 0) {
+        t = lane < 8 ? red[lane] : 0.f;
+        t = warp_sum(t);
+    }
+    return t;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo, int64_t n, float scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        split16(x[i], scale, hi[i], lo[i]);
+}
+
+// sums[plane][chunk] = sum of every `stride`-th element-quad of the chunk (an ESTIMATE of the plane
+// sum is enough: whatever constant is removed is added back exactly)
+__global__ void __launch_bounds__(256) plane_sums_kernel(const float* __restrict__ x, float* __restrict__ sums,
+                                                         int64_t plane4, int stride) {
+    __shared__ float red[8];
+    const int64_t pl = blockIdx.y;
+    const int64_t per = (plane4 + kSumChunks - 1) / kSumChunks;
+    const int64_t beg = blockIdx.x * per, end = min(plane4, beg + per);
+    const float4* src = reinterpret_cast<const float4*>(x) + pl * plane4;
+    float s = 0.f;
+    for (int64_t i = beg + (int64_t)threadIdx.x * stride; i < end; i += (int64_t)blockDim.x * stride) {
+        const float4 v = ld_stream(src + i);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    s = block_sum_256(s, red);
+    if (threadIdx.x == 0) sums[pl * kSumChunks + blockIdx.x] = s;
+}
+
+// number of quads plane_sums_kernel visits in a plane (so that mean = sum / (4 * count))
+static int64_t sampled_quads(int64_t plane4, int stride) {
+    const int64_t per = (plane4 + kSumChunks - 1) / kSumChunks;
+    int64_t cnt = 0;
+    for (int c = 0; c < kSumChunks; ++c) {
+        const int64_t beg = c * per, end = plane4 < beg + per ? plane4 : beg + per;
+        if (end > beg) cnt += (end - beg + stride - 1) / stride;
+    }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(256) split_centered_kernel(const float* __restrict__ x, const float* __restrict__ sums,
+                                                             __half* __restrict__ hi, __half* __restrict__ lo,
+                                                             float* __restrict__ dc, int64_t n_planes, int64_t plane4,
+                                                             float inv_count, float dc_factor, float scale) {
+    const int64_t total = n_planes * plane4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pl = i / plane4, q = i - pl * plane4;
+        float mu = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < kSumChunks; ++c) mu += __ldg(sums + pl * kSumChunks + c);
+        mu *= inv_count;
+        if (q == 0) dc[pl] = mu * dc_factor;
+        const float4 v = ld_stream(reinterpret_cast<const float4*>(x) + i);
+        __half oh[4], ol[4];
+        split16(v.x - mu, scale, oh[0], ol[0]);
+        split16(v.y - mu, scale, oh[1], ol[1]);
+        split16(v.z - mu, scale, oh[2], ol[2]);
+        split16(v.w - mu, scale, oh[3], ol[3]);
+        reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<const uint2*>(oh);
+        reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<const uint2*>(ol);
+    }
+}
+
+__device__ __forceinline__ float signed_pow_tc(float v, float g) {
+    const float a = powf(fabsf(v), g);
+    return v < 0.0f ? -a : a;
+}
+
+__device__ __forceinline__ void rgb_px_to_ipt(float r, float g, float b, const Mat3& A, const Mat3& B, float& o0,
+                                              float& o1, float& o2) {
+    float l = fmaf(A.m[2], b, fmaf(A.m[1], g, A.m[0] * r));
+    float m = fmaf(A.m[5], b, fmaf(A.m[4], g, A.m[3] * r));
+    float s = fmaf(A.m[8], b, fmaf(A.m[7], g, A.m[6] * r));
+    l = signed_pow_tc(l, 0.43f);
+    m = signed_pow_tc(m, 0.43f);
+    s = signed_pow_tc(s, 0.43f);
+    o0 = fmaf(B.m[2], s, fmaf(B.m[1], m, B.m[0] * l));
+    o1 = fmaf(B.m[5], s, fmaf(B.m[4], m, B.m[3] * l));
+    o2 = fmaf(B.m[8], s, fmaf(B.m[7], m, B.m[6] * l));
+}
+
+// IPT plane sums of a subsample of the pixels (every `stride`-th quad): sums[img*3 + c][chunk]
+__global__ void __launch_bounds__(256) ipt_sums_kernel(const float* __restrict__ rgb, float* __restrict__ sums,
+                                                       int64_t plane4, int stride, Mat3 A, Mat3 B) {
+    __shared__ float red[8];
+    const int64_t img = blockIdx.y;
+    const int64_t per = (plane4 + kSumChunks - 1) / kSumChunks;
+    const int64_t beg = blockIdx.x * per, end = min(plane4, beg + per);
+    const float4* src = reinterpret_cast<const float4*>(rgb) + img * 3 * plane4;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int64_t i = beg + (int64_t)threadIdx.x * stride; i < end; i += (int64_t)blockDim.x * stride) {
+        const float4 c0 = ld_stream(src + i), c1 = ld_stream(src + plane4 + i), c2 = ld_stream(src + 2 * plane4 + i);
+        const float r[4] = {c0.x, c0.y, c0.z, c0.w}, g[4] = {c1.x, c1.y, c1.z, c1.w}, b[4] = {c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float o0, o1, o2;
+            rgb_px_to_ipt(r[j], g[j], b[j], A, B, o0, o1, o2);
+            s0 += o0; s1 += o1; s2 += o2;
+        }
+    }
+    s0 = block_sum_256(s0, red);
+    s1 = block_sum_256(s1, red);
+    s2 = block_sum_256(s2, red);
+    if (threadIdx.x == 0) {
+        sums[(img * 3 + 0) * kSumChunks + blockIdx.x] = s0;
+        sums[(img * 3 + 1) * kSumChunks + blockIdx.x] = s1;
+        sums[(img * 3 + 2) * kSumChunks + blockIdx.x] = s2;
+    }
+}
+
+// util.py:70-82 rgb_to_ipt, writing the centred, scaled fp16 hi/lo operand planes of the forward GEMM
+__global__ void __launch_bounds__(256) rgb_to_ipt_split_kernel(const float* __restrict__ rgb, const float* __restrict__ sums,
+                                                               __half* __restrict__ hi, __half* __restrict__ lo,
+                                                               float* __restrict__ dc, int64_t n_img, int64_t plane4,
+                                                               Mat3 A, Mat3 B, float inv_count, float dc_factor,
+                                                               float scale) {
+    const int64_t total = n_img * plane4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = i / plane4, q = i - img * plane4;
+        float mu[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll 8
+            for (int k = 0; k < kSumChunks; ++k) mu[c] += __ldg(sums + (img * 3 + c) * kSumChunks + k);
+            mu[c] *= inv_count;
+            if (q == 0) dc[img * 3 + c] = mu[c] * dc_factor;
+        }
+        const float4* src = reinterpret_cast<const float4*>(rgb) + img * 3 * plane4 + q;
+        const float4 c0 = ld_stream(src), c1 = ld_stream(src + plane4), c2 = ld_stream(src + 2 * plane4);
+        const float r[4] = {c0.x, c0.y, c0.z, c0.w}, g[4] = {c1.x, c1.y, c1.z, c1.w}, b[4] = {c2.x, c2.y, c2.z, c2.w};
+        __half oh[3][4], ol[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float o0, o1, o2;
+            rgb_px_to_ipt(r[j], g[j], b[j], A, B, o0, o1, o2);
+            split16(o0 - mu[0], scale, oh[0][j], ol[0][j]);
+            split16(o1 - mu[1], scale, oh[1][j], ol[1][j]);
+            split16(o2 - mu[2], scale, oh[2][j], ol[2][j]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int64_t o = (img * 3 + c) * plane4 + q;   // in units of 4 halves (8 bytes)
+            reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(oh[c]);
+            reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(ol[c]);
+        }
+    }
+}
+
+// feature_extraction_dct_autoencoder.py:635-653 un-patchify, writing scaled fp16 hi/lo planes with pitch `ld`.
+// The DC coefficient goes to dc[plane] (already multiplied by dc_factor = 1/sqrt(h*w)) and is stored as 0.
+__global__ void __launch_bounds__(256) unpatchify_split_kernel(const float* __restrict__ patches,
+                                                               const int32_t* __restrict__ slot_map, int64_t n_img,
+                                                               int C, int th, int tw, int p, int rows, int cols,
+                                                               int64_t ld, __half* __restrict__ hi,
+                                                               __half* __restrict__ lo, float* __restrict__ dc,
+                                                               float dc_factor, float scale) {
+    const int z = p * p;
+    const int cols4 = (int)(ld / 4);
+    const int64_t total = n_img * C * rows * cols4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xv = (int)(i % cols4);
+        int64_t r = i / cols4;
+        const int y = (int)(r % rows);
+        r /= rows;
+        const int c = (int)(r % C);
+        const int64_t img = r / C;
+        const int ty = y / p, py = y - ty * p;
+        __half oh[4], ol[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = xv * 4 + j;
+            const int tx = x / p, px = x - tx * p;
+            float val = 0.0f;
+            if (x < cols && ty < th && tx < tw) {
+                const int32_t slot = __ldg(slot_map + ((img * C + c) * th + ty) * tw + tx);
+                if (slot >= 0) val = __ldg(patches + (int64_t)slot * z + py * p + px);
+            }
+            if (y == 0 && x == 0) {
+                dc[img * C + c] = val * dc_factor;
+                val = 0.0f;
+            }
+            split16(val, scale, oh[j], ol[j]);
+        }
+        const int64_t o = ((img * C + c) * rows + y) * (ld / 4) + xv;
+        reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(oh);
+        reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(ol);
+    }
+}
+
+}  // namespace dcta
+
+using namespace dcta;
+
+// Scales of the split operands (powers of two, exact): images/IPT 2^8, forward intermediate 2^6,
+// coefficient planes 2^4, inverse intermediate 2^6; basis 2^10 (folded into row_scale / alpha).
+static const float kScaleX = 256.f, kScaleP = 64.f, kScaleY = 16.f, kScaleQ = 64.f, kScaleBasis = 1024.f;
+static const int kSumStride = 4;   // plane-mean estimate from every 4th quad
+
+extern "C" int dcta_gemm_split(const void* a_hi, const void* a_lo, int a_rows, int64_t a_ld, int64_t a_batch_stride,
+                               const void* b_hi, const void* b_lo, int b_rows, int64_t b_ld, int64_t b_batch_stride,
+                               int k, int64_t batch, const float* row_scale, float alpha, float* out, int64_t out_ld,
+                               int64_t out_batch_stride, void* stream) {
+    DCTA_REQUIRE(a_hi && a_lo && b_hi && b_lo && out, "gemm_split: null pointer");
+    DCTA_REQUIRE(a_rows > 0 && b_rows > 0 && k > 0 && batch >= 0, "gemm_split: bad sizes");
+    Operand A{(const __half*)a_hi, (const __half*)a_lo, a_rows, a_ld, a_batch_stride};
+    Operand B{(const __half*)b_hi, (const __half*)b_lo, b_rows, b_ld, b_batch_stride};
+    EpiArgs ep{};
+    ep.mode = 0; ep.out_f32 = out; ep.ld = out_ld; ep.batch_stride = out_batch_stride;
+    ep.row_scale = row_scale; ep.alpha = alpha; ep.M = a_rows; ep.N = b_rows;
+    return launch_gemm_split(A, B, k, batch, ep, stream);
+}
+
+extern "C" int dcta_split_f32(const float* x, void* hi, void* lo, int64_t n, float scale, void* stream) {
+    DCTA_REQUIRE(x && hi && lo && n >= 0, "split_f32: bad args");
+    if (n == 0) return DCTA_OK;
+    split_f32_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, (__half*)hi, (__half*)lo, n, scale);
+    return check_launch("split_f32");
+}
+
+extern "C" int dcta_split_planes_centered(const float* x, void* hi, void* lo, float* dc, float* sums_scratch,
+                                          int64_t n_planes, int h, int w, void* stream) {
+    DCTA_REQUIRE(x && hi && lo && dc && sums_scratch, "split_planes_centered: null pointer");
+    const int64_t plane = (int64_t)h * w;
+    DCTA_REQUIRE(plane % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && n_planes <= 65535,
+                 "split_planes_centered: plane %% 4 != 0, unaligned input or too many planes");
+    if (n_planes == 0) return DCTA_OK;
+    cudaStream_t st = as_stream(stream);
+    plane_sums_kernel<<<dim3(kSumChunks, (unsigned)n_planes), 256, 0, st>>>(x, sums_scratch, plane / 4, kSumStride);
+    const float inv_count = 1.0f / (4.0f * (float)sampled_quads(plane / 4, kSumStride));
+    split_centered_kernel<<<grid_for(n_planes * (plane / 4), 256), 256, 0, st>>>(
+        x, sums_scratch, (__half*)hi, (__half*)lo, dc, n_planes, plane / 4, inv_count, sqrtf((float)h * (float)w), kScaleX);
+    return check_launch("split_planes_centered");
+}
+
+extern "C" int dcta_rgb_to_ipt_split(const float* rgb, void* ipt_hi, void* ipt_lo, float* dc, float* sums_scratch,
+                                     int64_t n_img, int h, int w, const float* m_rgb2lms_host,
+                                     const float* m_ipt_host, void* stream) {
+    DCTA_REQUIRE(rgb && ipt_hi && ipt_lo && dc && sums_scratch && m_rgb2lms_host && m_ipt_host,
+                 "rgb_to_ipt_split: null pointer");
+    const int64_t plane = (int64_t)h * w;
+    DCTA_REQUIRE(plane % 4 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 && n_img <= 65535,
+                 "rgb_to_ipt_split: plane %% 4 != 0, unaligned input or too many images");
+    if (n_img == 0 || plane == 0) return DCTA_OK;
+    Mat3 A, B;
+    for (int i = 0; i < 9; ++i) { A.m[i] = m_rgb2lms_host[i]; B.m[i] = m_ipt_host[i]; }
+    cudaStream_t st = as_stream(stream);
+    ipt_sums_kernel<<<dim3(kSumChunks, (unsigned)n_img), 256, 0, st>>>(rgb, sums_scratch, plane / 4, kSumStride, A, B);
+    const float inv_count = 1.0f / (4.0f * (float)sampled_quads(plane / 4, kSumStride));
+    rgb_to_ipt_split_kernel<<<grid_for(n_img * (plane / 4), 256), 256, 0, st>>>(
+        rgb, sums_scratch, (__half*)ipt_hi, (__half*)ipt_lo, dc, n_img, plane / 4, A, B, inv_count,
+        sqrtf((float)h * (float)w), kScaleX);
+    return check_launch("rgb_to_ipt_split");
+}
+
+extern "C" int dcta_unpatchify_split(const float* patches, const int32_t* slot_map, int64_t n_img, int channels_n,
+                                     int th, int tw, int p, int rows, int cols, int64_t ld, int out_h, int out_w,
+                                     void* y_hi, void* y_lo, float* dc, void* stream) {
+    DCTA_REQUIRE(patches && slot_map && y_hi && y_lo && dc, "unpatchify_split: null pointer");
+    DCTA_REQUIRE(ld % 8 == 0 && ld >= cols && rows > 0 && cols > 0 && p > 0 && out_h > 0 && out_w > 0,
+                 "unpatchify_split: bad sizes");
+    if (n_img == 0) return DCTA_OK;
+    const int64_t total = n_img * channels_n * rows * (ld / 4);
+    unpatchify_split_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+        patches, slot_map, n_img, channels_n, th, tw, p, rows, cols, ld, (__half*)y_hi, (__half*)y_lo, dc,
+        1.0f / sqrtf((float)out_h * (float)out_w), kScaleY);
+    return check_launch("unpatchify_split");
+}
+
+// forward: centred x planes (n_planes, h, w) as hi/lo (scale 2^8) + their removed DC -> token grid or planes (fp32)
+//   basis_w = CW'[:kw] (kw x w, hi/lo, pitch w), basis_h = CH'[:kh] (kh x h, pitch ld_h); rs_w/rs_h their row scales
+extern "C" int dcta_dct2_fwd_tc(const void* x_hi, const void* x_lo, const float* dc, const void* bw_hi,
+                                const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
+                                const float* rs_h, void* work_hi, void* work_lo, float* y, int64_t n_planes, int h,
+                                int w, int kh, int kw, int64_t ld_h, int tile_p, int channels, void* stream) {
+    DCTA_REQUIRE(x_hi && x_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && y,
+                 "dct2_fwd_tc: null pointer");
+    DCTA_REQUIRE(w % 8 == 0 && ld_h % 8 == 0 && ld_h >= h && kh <= h && kw <= w && kh > 0 && kw > 0,
+                 "dct2_fwd_tc: needs w %% 8 == 0 and an 8-aligned pitch");
+    if (tile_p > 0)
+        DCTA_REQUIRE(channels > 0 && kh % tile_p == 0 && kw % tile_p == 0 && n_planes % channels == 0,
+                     "dct2_fwd_tc: kh/kw must be multiples of the patch size");
+    // pass 1: P^T[kw, h] = sum_w CW'[kw,w] * X'[h,w]  -> hi/lo planes (kw x ld_h), scale 2^6
+    Operand A1{(const __half*)bw_hi, (const __half*)bw_lo, kw, w, 0};
+    Operand B1{(const __half*)x_hi, (const __half*)x_lo, h, w, (int64_t)h * w};
+    EpiArgs e1{};
+    e1.mode = 1; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
+    e1.ld = ld_h; e1.batch_stride = (int64_t)kw * ld_h;
+    e1.row_scale = rs_w; e1.alpha = kScaleP / kScaleX; e1.M = kw; e1.N = h;
+    int rc = launch_gemm_split(A1, B1, w, n_planes, e1, stream);
+    if (rc) return rc;
+    // pass 2: Y[kh, kw] = sum_h CH'[kh,h] * P'^T[kw,h]   (+ the removed constant's DC at [0,0])
+    Operand A2{(const __half*)bh_hi, (const __half*)bh_lo, kh, ld_h, 0};
+    Operand B2{(const __half*)work_hi, (const __half*)work_lo, kw, ld_h, (int64_t)kw * ld_h};
+    EpiArgs e2{};
+    e2.out_f32 = y; e2.row_scale = rs_h; e2.alpha = 1.0f / kScaleP; e2.M = kh; e2.N = kw;
+    e2.dc = dc; e2.dc_mode = dc ? 1 : 0;
+    if (tile_p > 0) {
+        e2.mode = 2; e2.tile_p = tile_p; e2.channels = channels; e2.tiles_h = kh / tile_p; e2.tiles_w = kw / tile_p;
+    } else {
+        e2.mode = 0; e2.ld = kw; e2.batch_stride = (int64_t)kh * kw;
+    }
+    return launch_gemm_split(A2, B2, h, n_planes, e2, stream);
+}
+
+// inverse: y planes (n_planes, kh, ld_kw) hi/lo (scale 2^4, DC removed into dc[]) -> x (n_planes, h, w) fp32
+//   bwt = CW'^T (w x kw, pitch ld_kw), bht = CH'^T (h x kh, pitch ld_kh); work planes (w x ld_kh)
+extern "C" int dcta_dct2_inv_tc(const void* y_hi, const void* y_lo, const float* dc, const void* bwt_hi,
+                                const void* bwt_lo, const void* bht_hi, const void* bht_lo, void* work_hi,
+                                void* work_lo, float* x, int64_t n_planes, int h, int w, int kh, int kw,
+                                int64_t ld_kh, int64_t ld_kw, void* stream) {
+    DCTA_REQUIRE(y_hi && y_lo && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && x,
+                 "dct2_inv_tc: null pointer");
+    DCTA_REQUIRE(ld_kh % 8 == 0 && ld_kw % 8 == 0 && ld_kh >= kh && ld_kw >= kw && kh > 0 && kw > 0,
+                 "dct2_inv_tc: pitches must be 8-aligned");
+    // pass 1: Q^T[w, kh] = sum_kw CW'^T[w,kw] * Y'[kh,kw]  -> hi/lo planes (w x ld_kh), scale 2^6
+    Operand A1{(const __half*)bwt_hi, (const __half*)bwt_lo, w, ld_kw, 0};
+    Operand B1{(const __half*)y_hi, (const __half*)y_lo, kh, ld_kw, (int64_t)kh * ld_kw};
+    EpiArgs e1{};
+    e1.mode = 1; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
+    e1.ld = ld_kh; e1.batch_stride = (int64_t)w * ld_kh;
+    e1.alpha = kScaleQ / (kScaleBasis * kScaleY); e1.M = w; e1.N = kh;
+    int rc = launch_gemm_split(A1, B1, kw, n_planes, e1, stream);
+    if (rc) return rc;
+    // pass 2: X[h, w] = sum_kh CH'^T[h,kh] * Q'^T[w,kh]   (+ the DC coefficient's constant everywhere)
+    Operand A2{(const __half*)bht_hi, (const __half*)bht_lo, h, ld_kh, 0};
+    Operand B2{(const __half*)work_hi, (const __half*)work_lo, w, ld_kh, (int64_t)w * ld_kh};
+    EpiArgs e2{};
+    e2.mode = 0; e2.out_f32 = x; e2.ld = w; e2.batch_stride = (int64_t)h * w;
+    e2.alpha = 1.0f / (kScaleBasis * kScaleQ); e2.M = h; e2.N = w;
+    e2.dc = dc; e2.dc_mode = dc ? 2 : 0;
+    return launch_gemm_split(A2, B2, kh, n_planes, e2, stream);
+}
+
+// fp32 coefficient planes (n_planes, kh, kw) -> split planes (n_planes, kh, ld_kw) with the DC moved to dc[]
+namespace dcta {
+__global__ void __launch_bounds__(256) split_coef_kernel(const float* __restrict__ y, __half* __restrict__ hi,
+                                                         __half* __restrict__ lo, float* __restrict__ dc,
+                                                         int64_t n_planes, int kh, int kw, int64_t ld, float dc_factor,
+                                                         float scale) {
+    const int64_t total = n_planes * kh * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % ld);
+        const int64_t r = i / ld;
+        const int yy = (int)(r % kh);
+        const int64_t pl = r / kh;
+        float v = x < kw ? y[(pl * kh + yy) * kw + x] : 0.f;
+        if (x == 0 && yy == 0) { dc[pl] = v * dc_factor; v = 0.f; }
+        split16(v, scale, hi[i], lo[i]);
+    }
+}
+}  // namespace dcta
+
+extern "C" int dcta_split_coef_planes(const float* y, void* hi, void* lo, float* dc, int64_t n_planes, int kh,
+                                      int kw, int64_t ld, int out_h, int out_w, void* stream) {
+    DCTA_REQUIRE(y && hi && lo && dc && ld % 8 == 0 && ld >= kw && kh > 0 && kw > 0, "split_coef_planes: bad args");
+    if (n_planes == 0) return DCTA_OK;
+    split_coef_kernel<<<grid_for(n_planes * kh * ld, 256), 256, 0, as_stream(stream)>>>(
+        y, (__half*)hi, (__half*)lo, dc, n_planes, kh, kw, ld, 1.0f / sqrtf((float)out_h * (float)out_w), kScaleY);
+    return check_launch("split_coef_planes");
+}

@@ -208,3 +208,163 @@ def calculate_perplexity(codes: torch.Tensor, codebook_size: int, null_index=-1)
         _lib.call("dcta_perplexity", _lib.ptr(c), c.numel(), codebook_size, int(null_index),
                   _lib.ptr(counts), _lib.ptr(result), _lib.stream_ptr(c.device))
     return result[0]
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core (split-precision) DCT path -- see csrc/gemm_tc.cu
+# ----------------------------------------------------------------------------------------------
+_SCALE_BASIS = 1024.0   # 2^10, must match kScaleBasis in gemm_tc.cu
+_SPLIT_CACHE = {}
+
+
+def _round8(v: int) -> int:
+    return (v + 7) // 8 * 8
+
+
+def _split_host(m: np.ndarray):
+    """float64 matrix -> (hi, lo) fp16 with hi + lo == m to ~2^-22 relative."""
+    hi = m.astype(np.float16)
+    lo = (m - hi.astype(np.float64)).astype(np.float16)
+    return hi, lo
+
+
+def split_basis(n: int, k: int, device, transposed: bool):
+    """fp16 hi/lo planes of the scaled orthonormal DCT-II basis C_n[:k].
+
+    forward  (transposed=False): (k, ld=round8(n)) planes of C*2^10, with row 0 (the constant
+             1/sqrt(n)) stored as exactly 32 so that the DC sum carries no systematic rounding;
+             also returns the fp32 per-row factors that undo the scaling.
+    inverse  (transposed=True):  (n, ld=round8(k)) planes of (C*2^10)^T; returns row_scale None."""
+    device = torch.device(device)
+    key = (n, k, transposed, device.type, device.index)
+    hit = _SPLIT_CACHE.get(key)
+    if hit is not None:
+        return hit
+    q = np.arange(k, dtype=np.float64)[:, None]
+    m = np.arange(n, dtype=np.float64)[None, :]
+    c = np.cos(np.pi * (2 * m + 1) * q / (2 * n)) * math.sqrt(2.0 / n)
+    c[0, :] = math.sqrt(1.0 / n)
+    if not transposed:
+        ld = _round8(n)
+        s = np.zeros((k, ld), np.float64)
+        s[:, :n] = c * _SCALE_BASIS
+        s[0, :n] = 32.0
+        rs = np.full(k, 1.0 / _SCALE_BASIS, np.float64)
+        rs[0] = math.sqrt(1.0 / n) / 32.0
+        row_scale = torch.from_numpy(rs.astype(np.float32)).to(device)
+    else:
+        ld = _round8(k)
+        s = np.zeros((n, ld), np.float64)
+        s[:, :k] = (c * _SCALE_BASIS).T
+        row_scale = None
+    hi, lo = _split_host(s)
+    out = (torch.from_numpy(hi).to(device), torch.from_numpy(lo).to(device), row_scale, ld)
+    _SPLIT_CACHE[key] = out
+    return out
+
+
+def split_f32(x: torch.Tensor, scale: float):
+    """fp32 CUDA tensor -> (hi, lo) fp16 tensors with x*scale == hi + lo (22 bits)."""
+    x = x.contiguous()
+    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(x.device):
+        _lib.call("dcta_split_f32", _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), x.numel(), float(scale),
+                  _lib.stream_ptr(x.device))
+    return hi, lo
+
+
+def rgb_to_ipt_split(x: torch.Tensor):
+    """util.py:70-82 fused with the operand split: (b, 3, h, w) fp32 RGB -> centred IPT*2^8 as fp16
+    hi/lo planes + dc (b*3,) = plane mean * sqrt(h*w) (added back to coefficient [0,0])."""
+    b, c, h, w = x.shape
+    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    dc = torch.empty(b * 3, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(b * 3 * 32, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dcta_rgb_to_ipt_split", _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc), _lib.ptr(scratch),
+                  b, h, w, _M_RGB2LMS, _M_IPT, _lib.stream_ptr(x.device))
+    return hi, lo, dc
+
+
+def split_planes_centered(x: torch.Tensor):
+    """fp32 planes (..., h, w) -> centred hi/lo (scale 2^8) + dc (n_planes,)."""
+    x = x.contiguous()
+    h, w = x.shape[-2:]
+    n_planes = x.numel() // (h * w)
+    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    dc = torch.empty(n_planes, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(n_planes * 32, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dcta_split_planes_centered", _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc),
+                  _lib.ptr(scratch), n_planes, h, w, _lib.stream_ptr(x.device))
+    return hi, lo, dc
+
+
+def tc_forward_ok(h: int, w: int) -> bool:
+    """The tensor-core forward path needs TMA-legal image planes (pitch multiple of 8 fp16)."""
+    return w % 8 == 0 and (h * w) % 4 == 0
+
+
+def dct2_fwd_tc(x_hi: torch.Tensor, x_lo: torch.Tensor, dc: Optional[torch.Tensor], kh: int, kw: int,
+                tile_p: int = 0, channels: int = 1):
+    """Truncated forward DCT on tensor cores from centred split planes (..., h, w) (scale 2^8)."""
+    h, w = x_hi.shape[-2:]
+    n_planes = x_hi.numel() // (h * w)
+    dev = x_hi.device
+    bw_hi, bw_lo, rs_w, _ = split_basis(w, kw, dev, False)
+    bh_hi, bh_lo, rs_h, ld_h = split_basis(h, kh, dev, False)
+    work_hi = torch.empty((n_planes, kw, ld_h), dtype=torch.float16, device=dev)
+    work_lo = torch.empty_like(work_hi)
+    if tile_p:
+        y = torch.empty((n_planes // channels, kh // tile_p, kw // tile_p, channels, tile_p * tile_p),
+                        dtype=torch.float32, device=dev)
+    else:
+        y = torch.empty(x_hi.shape[:-2] + (kh, kw), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_dct2_fwd_tc", _lib.ptr(x_hi), _lib.ptr(x_lo), _lib.ptr(dc), _lib.ptr(bw_hi), _lib.ptr(bw_lo),
+                  _lib.ptr(rs_w), _lib.ptr(bh_hi), _lib.ptr(bh_lo), _lib.ptr(rs_h), _lib.ptr(work_hi),
+                  _lib.ptr(work_lo), _lib.ptr(y), n_planes, h, w, kh, kw, ld_h, tile_p, channels, _lib.stream_ptr(dev))
+    return y
+
+
+def dct2_inv_tc(y_hi: torch.Tensor, y_lo: torch.Tensor, dc: Optional[torch.Tensor], kw: int, h: int, w: int):
+    """Truncated inverse DCT on tensor cores from split coefficient planes (..., kh, ld_kw) (scale 2^4,
+    DC coefficient carried separately in ``dc``)."""
+    kh, ld_kw = y_hi.shape[-2:]
+    n_planes = y_hi.numel() // (kh * ld_kw)
+    dev = y_hi.device
+    bwt_hi, bwt_lo, _, ld_kw_b = split_basis(w, kw, dev, True)
+    bht_hi, bht_lo, _, ld_kh = split_basis(h, kh, dev, True)
+    assert ld_kw_b == ld_kw
+    work_hi = torch.empty((n_planes, w, ld_kh), dtype=torch.float16, device=dev)
+    work_lo = torch.empty_like(work_hi)
+    x = torch.empty(y_hi.shape[:-2] + (h, w), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_dct2_inv_tc", _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc), _lib.ptr(bwt_hi), _lib.ptr(bwt_lo),
+                  _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(x),
+                  n_planes, h, w, kh, kw, ld_kh, ld_kw, _lib.stream_ptr(dev))
+    return x
+
+
+def dct2_truncated_tc(x: torch.Tensor, kh: int, kw: int, tile_p: int = 0, channels: int = 1):
+    """fp32 planes -> truncated DCT through the tensor-core path (|x - mean| must stay below 2^7)."""
+    hi, lo, dc = split_planes_centered(x)
+    return dct2_fwd_tc(hi, lo, dc, kh, kw, tile_p, channels)
+
+
+def idct2_truncated_tc(y: torch.Tensor, h: int, w: int):
+    """fp32 coefficient planes (..., kh, kw) -> samples through the tensor-core path (AC |y| < 2^11)."""
+    y = y.contiguous()
+    kh, kw = y.shape[-2:]
+    ld = _round8(kw)
+    n_planes = y.numel() // (kh * kw)
+    hi = torch.empty(y.shape[:-1] + (ld,), dtype=torch.float16, device=y.device)
+    lo = torch.empty_like(hi)
+    dc = torch.empty(n_planes, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.call("dcta_split_coef_planes", _lib.ptr(y), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc), n_planes, kh, kw,
+                  ld, h, w, _lib.stream_ptr(y.device))
+    return dct2_inv_tc(hi, lo, dc, kw, h, w)

@@ -65,6 +65,59 @@ int dcta_dct2_fwd(const float* x, const float* ch, const float* cw, float* work,
 int dcta_dct2_inv(const float* y, const float* ch, const float* cw, float* work, float* x,
                   int64_t n_planes, int h, int w, int kh, int kw, void* stream);
 
+/* ------------------------------------------------------------------ DCT / IDCT on tensor cores */
+/* Split-precision path (csrc/gemm_tc.cu): every fp32 operand is carried as two fp16 planes
+ * v * 2^s = hi + lo and each contraction is three tcgen05.mma (hi*hi + hi*lo + lo*hi) accumulated in
+ * fp32 in TMEM.  `half` pointers are passed as void*.  All hi/lo planes are K-major with an element
+ * pitch that is a multiple of 8 and a 16-byte aligned base (TMA).
+ *
+ * dcta_gemm_split: D[b] (a_rows x b_rows, fp32, pitch out_ld) = alpha * row_scale[m] *
+ *   sum_k A[b][m,k] * B[b][n,k];  a/b_batch_stride == 0 means the operand is shared by all b. */
+int dcta_gemm_split(const void* a_hi, const void* a_lo, int a_rows, int64_t a_ld, int64_t a_batch_stride,
+                    const void* b_hi, const void* b_lo, int b_rows, int64_t b_ld, int64_t b_batch_stride,
+                    int k, int64_t batch, const float* row_scale, float alpha, float* out, int64_t out_ld,
+                    int64_t out_batch_stride, void* stream);
+/* hi = rn16(x*scale), lo = rn16(x*scale - hi), elementwise over n values. */
+int dcta_split_f32(const float* x, void* hi, void* lo, int64_t n, float scale, void* stream);
+/* The tensor core accumulates in fp32 with truncation, so the producers below remove a per-plane
+ * constant (the plane mean / the DC coefficient) before the split and pass it in `dc`; the GEMM
+ * epilogue adds its exact contribution back (the DCT of a constant is the DC coefficient only).
+ * DCTA_SUM_SCRATCH floats of scratch per plane are needed by the mean estimate. */
+#define DCTA_SUM_SCRATCH 32
+/* fp32 planes (n_planes, h, w) -> centred hi/lo (scale 2^8) + dc[n_planes] = mean * sqrt(h*w). */
+int dcta_split_planes_centered(const float* x, void* hi, void* lo, float* dc, float* sums_scratch,
+                               int64_t n_planes, int h, int w, void* stream);
+/* fp32 coefficient planes (n_planes, kh, kw) -> hi/lo (n_planes, kh, ld) scale 2^4 with the DC
+ * coefficient moved to dc[n_planes] = Y[0,0] / sqrt(out_h*out_w). */
+int dcta_split_coef_planes(const float* y, void* hi, void* lo, float* dc, int64_t n_planes, int kh,
+                           int kw, int64_t ld, int out_h, int out_w, void* stream);
+/* UT:70-82 rgb_to_ipt producing the forward GEMM's operand planes directly: (ipt - mean)*2^8 as
+ * hi/lo (n_img, 3, h, w) and dc (n_img*3); h*w % 4 == 0; sums_scratch (n_img*3*DCTA_SUM_SCRATCH). */
+int dcta_rgb_to_ipt_split(const float* rgb, void* ipt_hi, void* ipt_lo, float* dc, float* sums_scratch,
+                          int64_t n_img, int h, int w, const float* m_rgb2lms_host,
+                          const float* m_ipt_host, void* stream);
+/* FE:635-653 un-patchify producing the inverse GEMM's operand planes: y*2^4 as hi/lo
+ * (n_img, channels, rows, ld), columns >= cols zero-filled, DC moved to dc (n_img*channels) scaled
+ * by 1/sqrt(out_h*out_w). */
+int dcta_unpatchify_split(const float* patches, const int32_t* slot_map, int64_t n_img, int channels_n,
+                          int th, int tw, int p, int rows, int cols, int64_t ld, int out_h, int out_w,
+                          void* y_hi, void* y_lo, float* dc, void* stream);
+/* Forward truncated DCT (same contract as dcta_dct2_fwd) from centred split planes.
+ *   x_hi/lo (n_planes, h, w) scale 2^8, dc (n_planes) [nullable];  bw = CW'[:kw] (kw, w),
+ *   bh = CH'[:kh] (kh, ld_h): basis * 2^10 with row 0 stored as the constant 32 (exact) -- rs_w / rs_h
+ *   (kw / kh floats) undo those scales;  work_hi/lo (n_planes, kw, ld_h). */
+int dcta_dct2_fwd_tc(const void* x_hi, const void* x_lo, const float* dc, const void* bw_hi,
+                     const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
+                     const float* rs_h, void* work_hi, void* work_lo, float* y, int64_t n_planes, int h,
+                     int w, int kh, int kw, int64_t ld_h, int tile_p, int channels, void* stream);
+/* Inverse truncated DCT (same contract as dcta_dct2_inv) from split coefficient planes.
+ *   y_hi/lo (n_planes, kh, ld_kw) scale 2^4, dc (n_planes) [nullable];  bwt = (CW' * 2^10)^T
+ *   (w, ld_kw), bht = (CH' * 2^10)^T (h, ld_kh); work_hi/lo (n_planes, w, ld_kh);  x (n_planes, h, w). */
+int dcta_dct2_inv_tc(const void* y_hi, const void* y_lo, const float* dc, const void* bwt_hi,
+                     const void* bwt_lo, const void* bht_hi, const void* bht_lo, void* work_hi,
+                     void* work_lo, float* x, int64_t n_planes, int h, int w, int kh, int kw,
+                     int64_t ld_kh, int64_t ld_kw, void* stream);
+
 /* FE:374-380 rearrange "c (h p1) (w p2) -> (h w) c (p1 p2)" with the max_patch clip of FE:393-394,
  * for coefficient planes produced by a caller-supplied transform:
  *   planes (n_img, channels, rows, cols) -> tiles (n_img, th, tw, channels, p*p); th*p<=rows, tw*p<=cols. */
