@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stages", action="store_true", help="also print per-stage timings to stderr")
+    ap.add_argument("--dct-impl", default="tc", choices=["tc", "fp32"],
+                    help="tc = tcgen05 split-precision GEMMs (default), fp32 = exact FFMA GEMMs")
     return ap.parse_args()
 
 
@@ -187,7 +188,7 @@ def run_ours(a):
     _lib.load()
 
     B, S = a.batch, a.size
-    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072, dct_impl=a.dct_impl)
     pn = D.PatchNorm(32, 32, 14, 3).to(dev)
     lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).to(dev).eval()
     pipe = D.TransformPipeline(fe, pn, lfq)
@@ -278,9 +279,15 @@ def run_ours(a):
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
-    roofline = dict(bound="tensor", kernel="sgemm_tile_kernel (forward DCT: 2 launches)", achieved=achieved,
-                    peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=None, peak_source=peak_src,
-                    note="exact-fp32 FFMA GEMM; algorithmic flops 3*2*H*K*(W+K) per image")
+    if fe.dct_impl == "tc":
+        kname = "gemm_split_kernel (forward DCT: 2 launches, tcgen05 fp16x3 split precision)"
+        note = ("algorithmic flops 3*2*H*K*(W+K) per image; the kernel executes 3x that many tensor flops "
+                "(hi*hi + hi*lo + lo*hi), so frac <= 1/3 by construction")
+    else:
+        kname = "sgemm_tile_kernel (forward DCT: 2 launches, exact-fp32 FFMA)"
+        note = "algorithmic flops 3*2*H*K*(W+K) per image"
+    roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak_tf, unit="TFLOP/s",
+                    frac=achieved / peak_tf, traffic=None, peak_source=peak_src, note=note)
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     staged_bytes = 26004480 * B
     pipeline_hbm = dict(bound="hbm", achieved=staged_bytes * a.steps / (ms / 1e3) / 1e9, peak=hbm, unit="GB/s",
@@ -291,6 +298,7 @@ def run_ours(a):
                 ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic",
                 config=dict(WORKLOAD, global_batch=B * world, per_gpu_batch=B, parallelism=f"image-sharded x{world}",
+                            dct_impl=a.dct_impl,
                             l2="inputs (805 MB/GPU at B=256) larger than L2, no flush needed",
                             patchnorm_fit_ms=fit_ms),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=hx.numel() * 4 * world,
@@ -331,9 +339,18 @@ def stage_times(torch, D, pipe, x, dev, reps=3):
         out[name] = statistics.median(ts)
         return res
 
-    ipt = t("rgb_to_ipt", lambda: D.util.rgb_to_ipt(x))
-    tiles = t("dct_fwd", lambda: D.util.dct2_truncated(ipt, 448, 448, tile_p=14, channels=3))
-    del ipt
+    from dct_autoencoder_b200 import _lib
+    U = D.util
+    H, W = x.shape[-2:]
+    tc = fe.dct_impl == "tc"
+    if tc:
+        hi, lo, dc = t("rgb_to_ipt_split", lambda: U.rgb_to_ipt_split(x))
+        tiles = t("dct_fwd", lambda: U.dct2_fwd_tc(hi, lo, dc, 448, 448, tile_p=14, channels=3))
+        del hi, lo
+    else:
+        ipt = t("rgb_to_ipt", lambda: U.rgb_to_ipt(x))
+        tiles = t("dct_fwd", lambda: U.dct2_truncated(ipt, 448, 448, tile_p=14, channels=3))
+        del ipt
     t("score_sort", lambda: fe._sorted_order(tiles))
     del tiles
     batch = t("encode_total(process_batch)", lambda: fe.process_batch(x))
@@ -343,9 +360,22 @@ def stage_times(torch, D, pipe, x, dev, reps=3):
     b2.patches = q
     inv = t("patchnorm_inv", lambda: pn.inverse_norm(b2))
     b2.patches = inv
-    planes = t("unpatchify", lambda: fe._render_planes(b2, clip=True))[0][1]
-    ipt2 = t("dct_inv", lambda: D.util.idct2_truncated(planes, x.shape[-2], x.shape[-1]))
-    t("ipt_to_rgb", lambda: D.util.ipt_to_rgb(ipt2))
+    n = len(b2.patch_sizes)
+    slot_map, _ = t("slot_map", lambda: fe._slot_map(b2, 32, 32))
+    st = _lib.stream_ptr(dev)
+    if tc:
+        y_hi = torch.empty((n, 3, 448, 448), dtype=torch.float16, device=dev)
+        y_lo = torch.empty_like(y_hi)
+        dc2 = torch.empty(n * 3, dtype=torch.float32, device=dev)
+        t("unpatchify", lambda: _lib.call("dcta_unpatchify_split", _lib.ptr(inv), _lib.ptr(slot_map), None, n, 3, 32, 32,
+                                          14, 448, 448, 448, H, W, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc2), st))
+        ipt2 = t("dct_inv", lambda: U.dct2_inv_tc(y_hi, y_lo, dc2, 448, H, W))
+    else:
+        planes = torch.empty((n, 3, 448, 448), dtype=torch.float32, device=dev)
+        t("unpatchify", lambda: _lib.call("dcta_unpatchify", _lib.ptr(inv), _lib.ptr(slot_map), None, n, 3, 32, 32, 14,
+                                          448, 448, _lib.ptr(planes), st))
+        ipt2 = t("dct_inv", lambda: U.idct2_truncated(planes, H, W))
+    t("ipt_to_rgb", lambda: U.ipt_to_rgb(ipt2))
     return out
 
 

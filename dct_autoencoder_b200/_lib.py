@@ -38,7 +38,7 @@ SIGNATURES = {
     "dcta_split_planes_centered": [P, P, P, P, P, c_int64, c_int, c_int, P],
     "dcta_split_coef_planes": [P, P, P, P, c_int64, c_int, c_int, c_int64, c_int, c_int, P],
     "dcta_rgb_to_ipt_split": [P, P, P, P, P, c_int64, c_int, c_int, P, P, P],
-    "dcta_unpatchify_split": [P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, c_int,
+    "dcta_unpatchify_split": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, c_int,
                               P, P, P, P],
     "dcta_dct2_fwd_tc": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int64, c_int,
                          c_int, P],

@@ -483,7 +483,8 @@ __global__ void __launch_bounds__(256) rgb_to_ipt_split_kernel(const float* __re
 // feature_extraction_dct_autoencoder.py:635-653 un-patchify, writing scaled fp16 hi/lo planes with pitch `ld`.
 // The DC coefficient goes to dc[plane] (already multiplied by dc_factor = 1/sqrt(h*w)) and is stored as 0.
 __global__ void __launch_bounds__(256) unpatchify_split_kernel(const float* __restrict__ patches,
-                                                               const int32_t* __restrict__ slot_map, int64_t n_img,
+                                                               const int32_t* __restrict__ slot_map,
+                                                               const int32_t* __restrict__ img_sel, int64_t n_img,
                                                                int C, int th, int tw, int p, int rows, int cols,
                                                                int64_t ld, __half* __restrict__ hi,
                                                                __half* __restrict__ lo, float* __restrict__ dc,
@@ -497,7 +498,8 @@ __global__ void __launch_bounds__(256) unpatchify_split_kernel(const float* __re
         const int y = (int)(r % rows);
         r /= rows;
         const int c = (int)(r % C);
-        const int64_t img = r / C;
+        const int64_t sel = r / C;
+        const int64_t img = img_sel ? img_sel[sel] : sel;
         const int ty = y / p, py = y - ty * p;
         __half oh[4], ol[4];
 #pragma unroll
@@ -510,12 +512,12 @@ __global__ void __launch_bounds__(256) unpatchify_split_kernel(const float* __re
                 if (slot >= 0) val = __ldg(patches + (int64_t)slot * z + py * p + px);
             }
             if (y == 0 && x == 0) {
-                dc[img * C + c] = val * dc_factor;
+                dc[sel * C + c] = val * dc_factor;
                 val = 0.0f;
             }
             split16(val, scale, oh[j], ol[j]);
         }
-        const int64_t o = ((img * C + c) * rows + y) * (ld / 4) + xv;
+        const int64_t o = ((sel * C + c) * rows + y) * (ld / 4) + xv;
         reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(oh);
         reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(ol);
     }
@@ -586,7 +588,8 @@ extern "C" int dcta_rgb_to_ipt_split(const float* rgb, void* ipt_hi, void* ipt_l
     return check_launch("rgb_to_ipt_split");
 }
 
-extern "C" int dcta_unpatchify_split(const float* patches, const int32_t* slot_map, int64_t n_img, int channels_n,
+extern "C" int dcta_unpatchify_split(const float* patches, const int32_t* slot_map, const int32_t* img_sel,
+                                     int64_t n_img, int channels_n,
                                      int th, int tw, int p, int rows, int cols, int64_t ld, int out_h, int out_w,
                                      void* y_hi, void* y_lo, float* dc, void* stream) {
     DCTA_REQUIRE(patches && slot_map && y_hi && y_lo && dc, "unpatchify_split: null pointer");
@@ -595,7 +598,7 @@ extern "C" int dcta_unpatchify_split(const float* patches, const int32_t* slot_m
     if (n_img == 0) return DCTA_OK;
     const int64_t total = n_img * channels_n * rows * (ld / 4);
     unpatchify_split_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-        patches, slot_map, n_img, channels_n, th, tw, p, rows, cols, ld, (__half*)y_hi, (__half*)y_lo, dc,
+        patches, slot_map, img_sel, n_img, channels_n, th, tw, p, rows, cols, ld, (__half*)y_hi, (__half*)y_lo, dc,
         1.0f / sqrtf((float)out_h * (float)out_w), kScaleY);
     return check_launch("unpatchify_split");
 }

@@ -20,8 +20,8 @@ import torch
 
 from . import _lib
 from .dct_patches import DCTPatches
-from .util import (dct2, dct2_truncated, exp_trunc_dist, idct2, idct2_truncated, ipt_to_rgb,
-                   rgb_to_ipt, to_device_f32)
+from .util import (_round8, dct2, dct2_fwd_tc, dct2_inv_tc, dct2_truncated, exp_trunc_dist, idct2,
+                   idct2_truncated, ipt_to_rgb, rgb_to_ipt, rgb_to_ipt_split, tc_forward_ok, to_device_f32)
 
 _SEG_DTYPE = np.dtype([("row", "<i4"), ("offset", "<i4"), ("k", "<i4"), ("image_id", "<i4"), ("img", "<i8")])
 assert _SEG_DTYPE.itemsize == 24
@@ -51,7 +51,12 @@ class DCTAutoencoderFeatureExtractor:
         channel_importances: Tuple[float, ...] = (8.0, 1.0, 1.0),
         patch_sample_magnitude_weight: float = 0.1,
         device=None,
+        dct_impl: str = "tc",
     ):
+        """``dct_impl``: "tc" = tcgen05 split-precision GEMMs (fp32-class accuracy, images in the
+        documented [0, 1] range; |IPT - plane mean| must stay below 2^7), "fp32" = exact-fp32 FFMA GEMMs."""
+        assert dct_impl in ("tc", "fp32")
+        self.dct_impl = dct_impl
         self.channels = channels
         self.patch_size = patch_size
         self.sample_patches_beta = sample_patches_beta
@@ -126,6 +131,10 @@ class DCTAutoencoderFeatureExtractor:
             # fused geometry: crop (FE:360) and max_patch clip (FE:393) only remove high
             # frequencies, so only the first th*p x tw*p coefficients are ever computed
             assert c == 3, "the IPT colour transform is defined for 3 channels"
+            if self.dct_impl == "tc" and tc_forward_ok(h, w):
+                # tensor cores: colour transform writes the centred fp16 hi/lo operand planes directly
+                hi, lo, dc = rgb_to_ipt_split(x)
+                return dct2_fwd_tc(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c)
             ipt = rgb_to_ipt(x)
             return dct2_truncated(ipt, th * p, tw * p, tile_p=p, channels=c)
         planes = torch.stack([to_device_f32(self._transform_image_in(im), x.device) for im in x])
@@ -432,21 +441,51 @@ class DCTAutoencoderFeatureExtractor:
                 pad[:, :ch, :cw] = plane
                 res[i] = self._transform_image_out(pad)
             return res
-        for idx, planes in self._render_planes(x, clip=True):
-            by_size: Dict[Tuple[int, int], List[int]] = {}
-            for j, i in enumerate(idx):
-                by_size.setdefault(tuple(int(v) for v in x.original_sizes[i]), []).append(j)
-            for (h, w), js in by_size.items():
-                sub = planes if len(js) == len(idx) else planes[js].contiguous()
-                rgb = ipt_to_rgb(idct2_truncated(sub, h, w))   # zero padding of FE:300-304 is implicit
-                for n, j in enumerate(js):
-                    res[idx[j]] = rgb[n] if og == torch.float32 else rgb[n].to(og)
+        for idx, rgb in self._decode_groups(x):
+            for n, i in enumerate(idx):
+                res[i] = rgb[n] if og == torch.float32 else rgb[n].to(og)
         return res
+
+    def _decode_groups(self, x: DCTPatches):
+        """Token rows -> RGB, one kernel sequence per group of images that share (tile grid,
+        original size).  Yields (image indices, rgb (n, c, h, w)).  The zero padding of FE:300-304
+        is implicit in the truncated inverse basis."""
+        _lib.require_cuda(x.patches, x.patch_positions, x.patch_channels, x.batched_image_ids, x.key_pad_mask)
+        p, C = self.patch_size, self.channels
+        patches = to_device_f32(x.patches)
+        dev = patches.device
+        tiles = [(min(int(a), self.max_patch_h), min(int(b), self.max_patch_w)) for a, b in x.patch_sizes]
+        th, tw = max(a for a, _ in tiles), max(b for _, b in tiles)
+        slot_map, n_img = self._slot_map(x, th, tw)
+        assert n_img == len(tiles), f"{n_img} images in the rows but {len(tiles)} patch_sizes"
+        groups: Dict[Tuple[int, int, int, int], List[int]] = {}
+        for i, (t, o) in enumerate(zip(tiles, x.original_sizes)):
+            groups.setdefault((t[0], t[1], int(o[0]), int(o[1])), []).append(i)
+        for (gh, gw, h, w), idx in groups.items():
+            sel = None
+            if len(groups) > 1:
+                sel = torch.tensor(idx, dtype=torch.int32).pin_memory().to(dev, non_blocking=True)
+            n, kh, kw = len(idx), gh * p, gw * p
+            with torch.cuda.device(dev):
+                st = _lib.stream_ptr(dev)
+                if self.dct_impl == "tc":
+                    ld = _round8(kw)
+                    y_hi = torch.empty((n, C, kh, ld), dtype=torch.float16, device=dev)
+                    y_lo = torch.empty_like(y_hi)
+                    dc = torch.empty(n * C, dtype=torch.float32, device=dev)
+                    _lib.call("dcta_unpatchify_split", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
+                              th, tw, p, kh, kw, ld, h, w, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc), st)
+                    ipt = dct2_inv_tc(y_hi, y_lo, dc, kw, h, w)
+                else:
+                    planes = torch.empty((n, C, kh, kw), dtype=torch.float32, device=dev)
+                    _lib.call("dcta_unpatchify", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C, th, tw,
+                              p, kh, kw, _lib.ptr(planes), st)
+                    ipt = idct2_truncated(planes, h, w)
+            yield idx, ipt_to_rgb(ipt)
 
     @torch.no_grad()
     def postprocess_batch(self, x: DCTPatches) -> torch.Tensor:
         """Same as ``torch.stack(postprocess(x))`` for batches whose images share one size."""
         assert len(set(map(tuple, x.original_sizes))) == 1 and len(set(map(tuple, x.patch_sizes))) == 1
-        (idx, planes), = self._render_planes(x, clip=True)
-        h, w = x.original_sizes[0]
-        return ipt_to_rgb(idct2_truncated(planes, int(h), int(w)))
+        (idx, rgb), = self._decode_groups(x)
+        return rgb

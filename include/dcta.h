@@ -98,10 +98,10 @@ int dcta_rgb_to_ipt_split(const float* rgb, void* ipt_hi, void* ipt_lo, float* d
                           const float* m_ipt_host, void* stream);
 /* FE:635-653 un-patchify producing the inverse GEMM's operand planes: y*2^4 as hi/lo
  * (n_img, channels, rows, ld), columns >= cols zero-filled, DC moved to dc (n_img*channels) scaled
- * by 1/sqrt(out_h*out_w). */
-int dcta_unpatchify_split(const float* patches, const int32_t* slot_map, int64_t n_img, int channels_n,
-                          int th, int tw, int p, int rows, int cols, int64_t ld, int out_h, int out_w,
-                          void* y_hi, void* y_lo, float* dc, void* stream);
+ * by 1/sqrt(out_h*out_w).  img_sel (n_img) i32 [nullable = identity] picks images of slot_map. */
+int dcta_unpatchify_split(const float* patches, const int32_t* slot_map, const int32_t* img_sel,
+                          int64_t n_img, int channels_n, int th, int tw, int p, int rows, int cols,
+                          int64_t ld, int out_h, int out_w, void* y_hi, void* y_lo, float* dc, void* stream);
 /* Forward truncated DCT (same contract as dcta_dct2_fwd) from centred split planes.
  *   x_hi/lo (n_planes, h, w) scale 2^8, dc (n_planes) [nullable];  bw = CW'[:kw] (kw, w),
  *   bh = CH'[:kh] (kh, ld_h): basis * 2^10 with row 0 stored as the constant 32 (exact) -- rs_w / rs_h

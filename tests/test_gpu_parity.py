@@ -569,7 +569,7 @@ def test_config2_shape_properties(D):
     # decode(encode) with nothing quantised == low-pass of the image: IDCT of the kept block
     rec = fe.postprocess_batch(b)
     ref = D.util.ipt_to_rgb(D.util.idct2_truncated(coef, 512, 512))
-    assert torch.equal(rec, ref)
+    assert float((rec - ref).abs().max()) <= 2e-5     # tensor-core decode vs exact-fp32 decode
     # scores are sorted: descending per image
     tiles = fe._token_grid(x)
     order = fe._sorted_order(tiles).long()
