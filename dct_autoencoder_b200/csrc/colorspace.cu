@@ -6,11 +6,6 @@ namespace dcta {
 
 void set_error(const char* fmt, ...);
 
-__device__ __forceinline__ float signed_pow(float v, float g) {
-    // UT:76-78 / UT:93-95: |x|**g with the sign restored; 0 -> 0.
-    float a = powf(fabsf(v), g);
-    return v < 0.0f ? -a : a;
-}
 
 template <bool kToIpt>
 __device__ __forceinline__ void convert_px(float r, float g, float b, const Mat3& A, const Mat3& B,

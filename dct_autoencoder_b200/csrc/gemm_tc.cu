@@ -395,10 +395,7 @@ __global__ void __launch_bounds__(256) split_centered_kernel(const float* __rest
     }
 }
 
-__device__ __forceinline__ float signed_pow_tc(float v, float g) {
-    const float a = powf(fabsf(v), g);
-    return v < 0.0f ? -a : a;
-}
+__device__ __forceinline__ float signed_pow_tc(float v, float g) { return signed_pow(v, g); }
 
 __device__ __forceinline__ void rgb_px_to_ipt(float r, float g, float b, const Mat3& A, const Mat3& B, float& o0,
                                               float& o1, float& o2) {

@@ -69,3 +69,41 @@ class TransformPipeline:
     def roundtrip(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None):
         batch, q, codes = self.encode(images, ks)
         return self.decode(batch, q), codes
+
+    @torch.no_grad()
+    def roundtrip_host(self, images: torch.Tensor, out_images: Optional[torch.Tensor] = None,
+                       out_codes: Optional[torch.Tensor] = None, chunk: int = 32, device=None):
+        """Host-to-host round trip of a (n, c, h, w) HOST batch (pinned memory for full speed):
+        the batch is streamed through the GPU in chunks so that the host->device copy of chunk i+1,
+        the kernels of chunk i and the device->host copy of chunk i-1 overlap (three streams).
+        Image-independent work only, so chunking does not change any result.
+        Returns (out_images (n, c, h, w) fp32, out_codes (n, s, codebooks) int64) on the host."""
+        assert not images.is_cuda, "roundtrip_host takes host tensors; use roundtrip() for device tensors"
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        n = images.shape[0]
+        if not hasattr(self, "_copy_streams"):
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._copy_streams
+        main = torch.cuda.current_stream(dev)
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        for i in range(0, n, chunk):
+            sl = slice(i, min(n, i + chunk))
+            with torch.cuda.stream(s_in):
+                x = images[sl].to(dev, non_blocking=True)
+                ev_in = s_in.record_event()
+            main.wait_event(ev_in)
+            x.record_stream(main)
+            rec, codes = self.roundtrip(x)
+            if out_images is None:
+                out_images = torch.empty((n,) + tuple(rec.shape[1:]), dtype=rec.dtype).pin_memory()
+                out_codes = torch.empty((n,) + tuple(codes.shape[1:]), dtype=codes.dtype).pin_memory()
+            ev_done = main.record_event()
+            s_out.wait_event(ev_done)
+            with torch.cuda.stream(s_out):
+                out_images[sl].copy_(rec, non_blocking=True)
+                out_codes[sl].copy_(codes, non_blocking=True)
+            rec.record_stream(s_out)
+            codes.record_stream(s_out)
+        main.wait_stream(s_out)
+        return out_images, out_codes

@@ -1,0 +1,78 @@
+"""GPU tests of the assembled pipeline helpers (host streaming, both DCT implementations)."""
+import numpy as np
+import pytest
+import torch
+
+import dcta_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def D():
+    import dct_autoencoder_b200 as d
+    d._lib.load()
+    return d
+
+
+def _pipe(D, impl):
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072, dct_impl=impl)
+    pn = D.PatchNorm(32, 32, 14, 3).cuda()
+    lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).cuda().eval()
+    return D.TransformPipeline(fe, pn, lfq)
+
+
+def test_roundtrip_host_equals_device_roundtrip(D):
+    torch.manual_seed(0)
+    x = torch.rand(10, 3, 128, 160)
+    pipe = _pipe(D, "tc")
+    pipe.fit_norm(torch.rand(6, 3, 128, 160).cuda())
+    rec, codes = pipe.roundtrip(x.cuda())
+    hx = x.pin_memory()
+    out_images, out_codes = pipe.roundtrip_host(hx, chunk=4)      # 3 chunks, last one ragged
+    torch.cuda.synchronize()
+    assert torch.equal(out_images, rec.cpu()) and torch.equal(out_codes, codes.cpu())
+    o2 = torch.empty_like(out_images).pin_memory()
+    c2 = torch.empty_like(out_codes).pin_memory()
+    pipe.roundtrip_host(hx, o2, c2, chunk=16)
+    torch.cuda.synchronize()
+    assert torch.equal(o2, rec.cpu()) and torch.equal(c2, codes.cpu())
+
+
+def test_tc_and_fp32_pipelines_agree(D):
+    """The tensor-core and exact-fp32 DCT implementations give the same codes (outside the sign
+    boundary) and the same images to 2e-5."""
+    torch.manual_seed(1)
+    x = torch.rand(4, 3, 256, 256).cuda()
+    fit = torch.rand(8, 3, 256, 256).cuda()
+    a, b = _pipe(D, "tc"), _pipe(D, "fp32")
+    a.fit_norm(fit)
+    b.fit_norm(fit)
+    assert float((a.norm.median - b.norm.median).abs().max()) < 2e-5
+    ba, qa, ca = a.encode(x)
+    bb, qb, cb = b.encode(x)
+    same_tok = (ba.patch_channels == bb.patch_channels) & (ba.patch_positions == bb.patch_positions).all(-1)
+    assert float(same_tok.float().mean()) > 0.99
+    diff = (qa != qb) & same_tok[..., None]
+    assert float(diff.float().mean()) < 2e-4
+    assert float(bb.patches[diff].abs().max() if diff.any() else 0.0) < 1e-3
+    ra, rb = a.decode(ba, qa), b.decode(bb, qb)
+    # decode the SAME quantised tokens with both implementations
+    rb2 = b.decode(ba, qa)
+    assert float((ra - rb2).abs().max()) < 2e-5
+
+
+def test_odd_sizes_fall_back_to_exact_fp32_forward(D):
+    """w % 8 != 0 is not TMA-legal: the extractor uses the FFMA forward there (same API, same results
+    within tolerance) and the tensor-core inverse (padded pitches)."""
+    torch.manual_seed(2)
+    x = torch.rand(2, 3, 90, 101).cuda()
+    fe_tc = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072, dct_impl="tc")
+    fe_32 = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072, dct_impl="fp32")
+    b1, b2 = fe_tc.process_batch(x), fe_32.process_batch(x)
+    assert torch.equal(b1.patches, b2.patches)
+    r1, r2 = fe_tc.postprocess_batch(b1), fe_32.postprocess_batch(b2)
+    assert float((r1 - r2).abs().max()) < 2e-5
+    ofe = O.FeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+    it = ofe.preprocess(x[0].cpu().numpy())
+    assert np.abs(b1.patches[0, : it["patches"].shape[0]].cpu().numpy() - it["patches"]).max() < 1e-4
