@@ -27,7 +27,7 @@ namespace dcta {
 constexpr int TM = 128, TN = 128, TK = 32, STAGES = 3;
 constexpr int TILE_BYTES = TM * TK * 2;          // 8 KB: one 128 x 32 fp16 operand tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
-constexpr int EPI_PITCH = TN + 1;                // fp32 staging pitch (odd: conflict-free)
+constexpr int EPI_PITCH = TN + 4;                // fp32 staging pitch (conflict-free 128-bit accesses)
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 static_assert(TM * EPI_PITCH * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the ring");
 
@@ -137,7 +137,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     __shared__ __align__(8) uint64_t acc_bar;
     __shared__ uint32_t tmem_base_slot;
 
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment computed in the shared window so that the pointer stays a shared pointer
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * TN, m0 = blockIdx.y * TM, batch = blockIdx.z;
 
@@ -201,7 +202,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     // ---------------- epilogue (all 4 warps; warp w owns TMEM lanes / tile rows 32w .. 32w+31)
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
-    float* stage_f32 = reinterpret_cast<float*>(smem);   // the ring is idle now: all MMAs have completed
+    // The ring is idle now (all MMAs have completed): reuse it as a 128 x 132 fp32 staging tile.
+    // Pitch 132 keeps 128-bit accesses conflict-free in both directions: the TMEM side writes one
+    // row per lane (8 lanes x 4 words x stride 4 banks = 32 banks), the store side reads one row per
+    // warp with 4 consecutive columns per lane.
+    const uint32_t stage = smem_u32(smem);
     const int row = warp * 32 + lane;
     const int gm = m0 + row;
     float rs = ep.alpha;
@@ -210,38 +215,78 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     for (int c = 0; c < TN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + c * 32, r);
+        const uint32_t dst = stage + (uint32_t)(row * EPI_PITCH + c * 32) * 4;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stage_f32[row * EPI_PITCH + c * 32 + j] = __uint_as_float(r[j]) * rs;
+        for (int j = 0; j < 32; j += 4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + j * 4),
+                         "f"(__uint_as_float(r[j]) * rs), "f"(__uint_as_float(r[j + 1]) * rs),
+                         "f"(__uint_as_float(r[j + 2]) * rs), "f"(__uint_as_float(r[j + 3]) * rs) : "memory");
     }
     __syncwarp();
     const float dcv = ep.dc_mode ? __ldg(ep.dc + batch) : 0.0f;
-    // each warp streams out its own 32 rows, lanes along n (coalesced)
+    const int n = n0 + lane * 4;                 // this lane's 4 consecutive output columns
+    const int n_valid = ep.N - n;                // >= 4: all four in range
+    // per-lane column offsets of the token-grid layout (constant over the rows)
+    int64_t col_off[4] = {0, 0, 0, 0};
+    int64_t plane_off = 0;
+    const int p = ep.tile_p, zz = p * p;
+    if (ep.mode == 2) {
+        const int64_t img = batch / ep.channels;
+        const int ch = batch - (int)img * ep.channels;
+        plane_off = (img * ep.tiles_h * ep.tiles_w * ep.channels + ch) * (int64_t)zz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int tw = (n + j) / p;
+            col_off[j] = (int64_t)tw * ep.channels * zz + ((n + j) - tw * p);
+        }
+    } else {
+        plane_off = (int64_t)batch * ep.batch_stride + n;
+    }
+    const bool pair_ok = (p % 2 == 0);           // columns (n, n+1) and (n+2, n+3) never straddle a tile
     for (int rr = 0; rr < 32; ++rr) {
         const int m = m0 + warp * 32 + rr;
         if (m >= ep.M) break;
-        const float* src = stage_f32 + (warp * 32 + rr) * EPI_PITCH;
-#pragma unroll
-        for (int q = 0; q < TN / 32; ++q) {
-            const int n = n0 + q * 32 + lane;
-            if (n >= ep.N) continue;
-            float v = src[q * 32 + lane];
-            if (ep.dc_mode == 2 || (ep.dc_mode == 1 && m == 0 && n == 0)) v += dcv;
-            if (ep.mode == 0) {
-                ep.out_f32[(int64_t)batch * ep.batch_stride + (int64_t)m * ep.ld + n] = v;
-            } else if (ep.mode == 1) {
-                const __half h = __float2half_rn(v);
-                const __half l = __float2half_rn(v - __half2float(h));
-                const int64_t o = (int64_t)batch * ep.batch_stride + (int64_t)m * ep.ld + n;
-                ep.out_hi[o] = h;
-                ep.out_lo[o] = l;
+        if (n_valid <= 0) continue;
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"(stage + (uint32_t)((warp * 32 + rr) * EPI_PITCH + lane * 4) * 4));
+        if (ep.dc_mode == 2) { v.x += dcv; v.y += dcv; v.z += dcv; v.w += dcv; }
+        else if (ep.dc_mode == 1 && m == 0 && n == 0) v.x += dcv;
+        if (ep.mode == 0) {
+            float* dst = ep.out_f32 + plane_off + (int64_t)m * ep.ld;
+            if (n_valid >= 4 && (ep.ld & 3) == 0) {
+                *reinterpret_cast<float4*>(dst) = v;
             } else {
-                const int p = ep.tile_p;
-                const int64_t img = batch / ep.channels;
-                const int ch = batch - (int)img * ep.channels;
-                const int th = m / p, pi = m - th * p;
-                const int tw = n / p, pj = n - tw * p;
-                const int64_t tok = ((img * ep.tiles_h + th) * ep.tiles_w + tw) * ep.channels + ch;
-                ep.out_f32[tok * (p * p) + pi * p + pj] = v;
+                const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < n_valid) dst[j] = a[j];
+            }
+        } else if (ep.mode == 1) {
+            const float a[4] = {v.x, v.y, v.z, v.w};
+            __half h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                h[j] = __float2half_rn(a[j]);
+                l[j] = __float2half_rn(a[j] - __half2float(h[j]));
+            }
+            const int64_t o = plane_off + (int64_t)m * ep.ld;   // ld % 8 == 0, n % 4 == 0: 8-byte aligned
+            if (n_valid >= 4) {
+                *reinterpret_cast<uint2*>(ep.out_hi + o) = *reinterpret_cast<const uint2*>(h);
+                *reinterpret_cast<uint2*>(ep.out_lo + o) = *reinterpret_cast<const uint2*>(l);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < n_valid) { ep.out_hi[o + j] = h[j]; ep.out_lo[o + j] = l[j]; }
+            }
+        } else {
+            const int th = m / p, pi = m - th * p;
+            float* dst = ep.out_f32 + plane_off + (int64_t)th * ep.tiles_w * ep.channels * zz + pi * p;
+            if (pair_ok && n_valid >= 4) {
+                *reinterpret_cast<float2*>(dst + col_off[0]) = make_float2(v.x, v.y);
+                *reinterpret_cast<float2*>(dst + col_off[2]) = make_float2(v.z, v.w);
+            } else {
+                const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < n_valid) dst[col_off[j]] = a[j];
             }
         }
     }

@@ -77,7 +77,9 @@ class TransformPipeline:
         the batch is streamed through the GPU in chunks so that the host->device copy of chunk i+1,
         the kernels of chunk i and the device->host copy of chunk i-1 overlap (three streams).
         Image-independent work only, so chunking does not change any result.
-        Returns (out_images (n, c, h, w) fp32, out_codes (n, s, codebooks) int64) on the host."""
+        Returns (out_images (n, c, h, w) fp32, out_codes (n, s, codebooks) int64) on the host.
+        Codes are returned per IMAGE, so every image must fill its own row (k == max_seq_len, as in
+        the benchmark configuration); use roundtrip() per chunk for packed rows."""
         assert not images.is_cuda, "roundtrip_host takes host tensors; use roundtrip() for device tensors"
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         n = images.shape[0]
@@ -95,6 +97,7 @@ class TransformPipeline:
             main.wait_event(ev_in)
             x.record_stream(main)
             rec, codes = self.roundtrip(x)
+            assert codes.shape[0] == x.shape[0], "roundtrip_host needs one image per row (k == max_seq_len)"
             if out_images is None:
                 out_images = torch.empty((n,) + tuple(rec.shape[1:]), dtype=rec.dtype).pin_memory()
                 out_codes = torch.empty((n,) + tuple(codes.shape[1:]), dtype=codes.dtype).pin_memory()
