@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--chunk", type=int, default=32, help="images per chunk of the host streaming round trip")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dct-impl", default="tc", choices=["tc", "fp32"],
@@ -260,7 +261,7 @@ def run_ours(a):
     def step_e2e():
         # public host-to-host call: pinned host images in, pinned host images + codes out;
         # H2D, kernels and D2H of successive 32-image chunks overlap on three streams
-        pipe.roundtrip_host(hx, h_rec, h_codes, chunk=32)
+        pipe.roundtrip_host(hx, h_rec, h_codes, chunk=a.chunk)
 
     e2e_steps = max(2, min(a.steps, 5))
     ms_e2e = timed(step_e2e, e2e_steps, 1)

@@ -62,6 +62,9 @@ SIGNATURES = {
     "dcta_entropy_loss": [P, P, P, P, c_int64, c_int, c_int, c_float, c_float, P],
     "dcta_perplexity": [P, c_int64, c_int, c_int64, P, P, P],
     "dcta_vq_nearest": [P, P, P, P, P, c_int64, c_int, c_int, P],
+    "dcta_row_sumsq": [P, P, c_int64, c_int, P],
+    "dcta_split_rows": [P, P, P, c_int64, c_int, c_int64, P, P],
+    "dcta_vq_nearest_tc": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int64, P],
     "dcta_build_slot_map": [P, P, P, P, P, c_int, c_int, c_int64, c_int, c_int, c_int, P, P],
     "dcta_unpatchify": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
 }
@@ -80,6 +83,7 @@ KERNELS_PER_CALL = {
     "dcta_gemm_split": 1, "dcta_split_f32": 1, "dcta_rgb_to_ipt_split": 2, "dcta_unpatchify_split": 1,
     "dcta_split_planes_centered": 2, "dcta_split_coef_planes": 1,
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,
+    "dcta_row_sumsq": 1, "dcta_split_rows": 1, "dcta_vq_nearest_tc": 2,
 }
 launch_count = 0
 

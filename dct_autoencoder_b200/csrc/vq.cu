@@ -170,3 +170,10 @@ extern "C" int dcta_vq_nearest(const float* x, const float* embed, float* e2, in
     vq_nearest_kernel<<<(unsigned)grid, 256, 0, st>>>(x, embed, e2, indices, quantized, n_tok, n_codes, d);
     return check_launch("vq_nearest");
 }
+
+extern "C" int dcta_row_sumsq(const float* x, float* out, int64_t n, int d, void* stream) {
+    DCTA_REQUIRE(x && out && n >= 0 && n < (1ll << 26) && d > 0, "row_sumsq: bad args");
+    if (n == 0) return DCTA_OK;
+    row_sumsq_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, as_stream(stream)>>>(x, out, (int)n, d);
+    return check_launch("row_sumsq");
+}

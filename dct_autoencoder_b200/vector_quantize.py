@@ -19,16 +19,51 @@ from . import _lib
 from .util import to_device_f32
 
 
-def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = True):
-    """x (T, d), embed (C, d) fp32 CUDA -> (indices int64 (T,), embed[indices] or None)."""
+def _pow2_scale(t: torch.Tensor) -> torch.Tensor:
+    """Device scalar 2^k with max|t| * 2^k in [2^10, 2^11): the fp16 hi/lo split then keeps 22
+    bits of every element that matters.  Stays on the device (no host read of the data)."""
+    amax = t.abs().amax().clamp_min(1e-30)
+    return torch.exp2(10.0 - torch.ceil(torch.log2(amax))).reshape(1).float()
+
+
+def _split_rows(t: torch.Tensor, scale: torch.Tensor, ld: int):
+    n, d = t.shape
+    hi = torch.empty((n, ld), dtype=torch.float16, device=t.device)
+    lo = torch.empty_like(hi)
+    _lib.call("dcta_split_rows", _lib.ptr(t), _lib.ptr(hi), _lib.ptr(lo), n, d, ld, _lib.ptr(scale),
+              _lib.stream_ptr(t.device))
+    return hi, lo
+
+
+def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = True, impl: str = "tc"):
+    """x (T, d), embed (C, d) fp32 CUDA -> (indices int64 (T,), embed[indices] or None).
+
+    impl="tc": x.e on tensor cores (split-precision tcgen05 GEMM, arg-min fused in the epilogue);
+    impl="fp32": exact-fp32 FFMA kernel in the reference's operation order."""
     T, d = x.shape
     C = embed.shape[0]
-    idx = torch.empty(T, dtype=torch.int64, device=x.device)
+    dev = x.device
+    idx = torch.empty(T, dtype=torch.int64, device=dev)
     q = torch.empty_like(x) if return_quantized else None
-    e2 = torch.empty(C, dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        _lib.call("dcta_vq_nearest", _lib.ptr(x), _lib.ptr(embed), _lib.ptr(e2), _lib.ptr(idx), _lib.ptr(q),
-                  T, C, d, _lib.stream_ptr(x.device))
+    e2 = torch.empty(C, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        if impl == "fp32":
+            _lib.call("dcta_vq_nearest", _lib.ptr(x), _lib.ptr(embed), _lib.ptr(e2), _lib.ptr(idx), _lib.ptr(q),
+                      T, C, d, st)
+            return idx, q
+        ld = (d + 7) // 8 * 8
+        sx, se = _pow2_scale(x), _pow2_scale(embed)
+        alpha = (-2.0 / (sx * se)).float().contiguous()
+        x_hi, x_lo = _split_rows(x, sx, ld)
+        e_hi, e_lo = _split_rows(embed, se, ld)
+        _lib.call("dcta_row_sumsq", _lib.ptr(embed), _lib.ptr(e2), C, d, st)
+        n_tiles = (C + 127) // 128
+        part_val = torch.empty((T, n_tiles), dtype=torch.float32, device=dev)
+        part_idx = torch.empty((T, n_tiles), dtype=torch.int32, device=dev)
+        _lib.call("dcta_vq_nearest_tc", _lib.ptr(x), _lib.ptr(x_hi), _lib.ptr(x_lo), _lib.ptr(embed), _lib.ptr(e_hi),
+                  _lib.ptr(e_lo), _lib.ptr(e2), _lib.ptr(alpha), _lib.ptr(part_val), _lib.ptr(part_idx), _lib.ptr(idx),
+                  _lib.ptr(q), T, C, d, ld, st)
     return idx, q
 
 
@@ -50,8 +85,10 @@ class EuclideanCodebook(nn.Module):
 class VectorQuantize(nn.Module):
     def __init__(self, dim, codebook_size, codebook_dim=None, heads=1, separate_codebook_per_head=False,
                  channel_last=True, accept_image_fmap=False, use_cosine_sim=False, affine_param=False,
-                 **training_kwargs):
+                 vq_impl: str = "tc", **training_kwargs):
         super().__init__()
+        assert vq_impl in ("tc", "fp32")
+        self.vq_impl = vq_impl      # "tc": tcgen05 split-precision distance GEMM; "fp32": exact FFMA kernel
         if use_cosine_sim or affine_param:
             raise NotImplementedError("cosine-similarity / affine-parametrised codebooks are training "
                                       "machinery outside the transform path")
@@ -124,16 +161,16 @@ class VectorQuantize(nn.Module):
         ef = to_device_f32(embed)
         if h > 1 and self.separate_codebook_per_head:
             xs = xf.reshape(b, n, h, d).permute(2, 0, 1, 3).contiguous()    # 'h b n d'
-            outs = [nearest_code(xs[i].reshape(b * n, d), ef[i].contiguous()) for i in range(h)]
+            outs = [nearest_code(xs[i].reshape(b * n, d), ef[i].contiguous(), impl=self.vq_impl) for i in range(h)]
             ind = torch.stack([o[0].reshape(b, n) for o in outs], dim=-1)   # b n h
             q = torch.stack([o[1].reshape(b, n, d) for o in outs], dim=2).reshape(b, n, h * d)
         elif h > 1:
             # shared codebook: heads are folded into the batch, '1 (b h) n d' (vector_quantize.py:874-875)
-            idx, qf = nearest_code(xf.reshape(b * n * h, d), ef[0].contiguous())
+            idx, qf = nearest_code(xf.reshape(b * n * h, d), ef[0].contiguous(), impl=self.vq_impl)
             ind = idx.reshape(b, n, h)
             q = qf.reshape(b, n, h * d)
         else:
-            idx, qf = nearest_code(xf.reshape(b * n, d), ef[0].contiguous())
+            idx, qf = nearest_code(xf.reshape(b * n, d), ef[0].contiguous(), impl=self.vq_impl)
             ind = idx.reshape(b, n)
             q = qf.reshape(b, n, d)
         q = q.to(x.dtype)

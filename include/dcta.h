@@ -230,6 +230,22 @@ int dcta_perplexity(const int64_t* codes, int64_t n, int codebook_size, int64_t 
 int dcta_vq_nearest(const float* x, const float* embed, float* e2, int64_t* indices,
                     float* quantized, int64_t n_tok, int n_codes, int d, void* stream);
 
+/* out[i] = sum_k x[i,k]^2 for n rows of d floats. */
+int dcta_row_sumsq(const float* x, float* out, int64_t n, int d, void* stream);
+/* rows (n, d) fp32 -> fp16 hi/lo planes (n, ld) of x * (*scale_dev); *scale_dev is a power of two
+ * chosen on the device (no host read of the data range). */
+int dcta_split_rows(const float* x, void* hi, void* lo, int64_t n, int d, int64_t ld,
+                    const float* scale_dev, void* stream);
+/* Same contract as dcta_vq_nearest on tensor cores: the x.e products run through the split-precision
+ * tcgen05 GEMM, each 128x128 tile is reduced to one (min, argmin) pair per token in the epilogue
+ * (part_val / part_idx: n_tok * ceil(n_codes/128) scratch) and merged in the sqrt domain.
+ *   x_hi/lo (n_tok, ld), e_hi/lo (n_codes, ld): dcta_split_rows outputs; e2 = dcta_row_sumsq(embed);
+ *   *alpha_dev = -2 / (scale_x * scale_e). */
+int dcta_vq_nearest_tc(const float* x, const void* x_hi, const void* x_lo, const float* embed,
+                       const void* e_hi, const void* e_lo, const float* e2, const float* alpha_dev,
+                       float* part_val, int32_t* part_idx, int64_t* indices, float* quantized,
+                       int64_t n_tok, int n_codes, int d, int64_t ld, void* stream);
+
 /* ------------------------------------------------------------------ un-patchify ----------- */
 /* FE:619-643: slot_map (n_img, channels, th, tw) i32 = flat token index (row*s + slot) of the LAST
  * valid token at that position, -1 where none (the call fills it).

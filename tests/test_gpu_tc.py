@@ -116,3 +116,41 @@ def test_tc_natural_image_statistics(D):
     yf = D.util.dct2_truncated(torch.from_numpy(x).cuda(), 252, 252).cpu().numpy()
     print("natural: tc", np.abs(y - y64).max(), "ffma", np.abs(yf - y64).max(), "max|Y|", np.abs(y64).max())
     assert np.abs(y - y64).max() <= TC_RTOL * np.abs(y64).max()
+
+
+@pytest.mark.parametrize("T,C,d", [(1000, 512, 64), (3000, 8192, 256), (129, 100, 7), (257, 130, 20)])
+def test_vq_tc_matches_oracle(D, T, C, d):
+    """tensor-core nearest-code search vs the numpy oracle (reference formula); indices may differ
+    only where the two best squared distances are within 1e-4 relative."""
+    from dct_autoencoder_b200.vector_quantize import nearest_code
+    rng = np.random.default_rng(T + C)
+    x = (rng.standard_normal((T, d)) * 3).astype(np.float32)
+    e = rng.standard_normal((C, d)).astype(np.float32)
+    e[C // 2] = e[3]                      # exact duplicate code: the first index must win
+    x[0] = e[3]
+    xt, et = torch.from_numpy(x).cuda(), torch.from_numpy(e).cuda()
+    idx, q = nearest_code(xt, et, impl="tc")
+    idx32, _ = nearest_code(xt, et, impl="fp32")
+    oi, best, second = O.vq_nearest(x, e)
+    got = idx.cpu().numpy()
+    diff = got != oi
+    if diff.any():
+        d2 = ((x[diff] - e[got[diff]]) ** 2).sum(-1)
+        assert np.all(np.abs(d2 - best[diff]) <= 1e-4 * np.abs(best[diff]) + 1e-6)
+    assert diff.mean() < 0.01
+    assert int(idx[0]) == 3
+    assert np.array_equal(q.cpu().numpy(), e[got])
+    assert float((idx != idx32).float().mean()) < 0.01
+
+
+def test_vq_module_uses_tc_by_default(D):
+    torch.manual_seed(0)
+    v = D.VectorQuantize(64, 256).cuda().eval()
+    v32 = D.VectorQuantize(64, 256, vq_impl="fp32").cuda().eval()
+    v32.codebook = v.codebook
+    x = torch.randn(2, 500, 64, device="cuda")
+    q, ind, _ = v(x)
+    q2, ind2, _ = v32(x)
+    assert float((ind != ind2).float().mean()) < 0.005
+    same = ind == ind2
+    assert torch.equal(q[same], q2[same])
