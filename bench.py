@@ -251,6 +251,12 @@ def run_ours(a):
         torch.cuda.synchronize()
     clocks = sampler.stop(skip) if sampler else None
     value = world * B * a.steps / (ms / 1e3)
+    mode = "fused PatchNorm+LFQ inside pack/un-patchify (bit-identical to staged)" if pipe.fusable() else "staged"
+
+    # ---- the same job through the drop-in modules one by one (every intermediate materialised)
+    staged_steps = max(2, min(a.steps, 5))
+    ms_staged = timed(lambda: pipe.roundtrip_staged(x), staged_steps, 1)
+    staged_value = world * B * staged_steps / (ms_staged / 1e3)
 
     # ---- end to end through the public API with HOST buffers (pinned in, pinned out)
     hx = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
@@ -291,7 +297,8 @@ def run_ours(a):
                     frac=achieved / peak_tf, traffic=None, peak_source=peak_src, note=note)
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     staged_bytes = 26004480 * B
-    pipeline_hbm = dict(bound="hbm", achieved=staged_bytes * a.steps / (ms / 1e3) / 1e9, peak=hbm, unit="GB/s",
+    pipeline_hbm = dict(bound="hbm", mode="staged API (roundtrip_staged)",
+                        achieved=staged_bytes * staged_steps / (ms_staged / 1e3) / 1e9, peak=hbm, unit="GB/s",
                         note="whole step, staged-API algorithmic bytes 26,004,480 B/img (SURVEY 8d)")
     pipeline_hbm["frac"] = pipeline_hbm["achieved"] / hbm
 
@@ -299,13 +306,15 @@ def run_ours(a):
                 ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic",
                 config=dict(WORKLOAD, global_batch=B * world, per_gpu_batch=B, parallelism=f"image-sharded x{world}",
-                            dct_impl=a.dct_impl,
+                            dct_impl=a.dct_impl, mode=mode,
                             l2="inputs (805 MB/GPU at B=256) larger than L2, no flush needed",
                             patchnorm_fit_ms=fit_ms),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=hx.numel() * 4 * world,
                          d2h_bytes_per_step=(h_rec.numel() * 4 + h_codes.numel() * 8) * world,
                          ms_per_step=ms_e2e / e2e_steps),
                 gpu_launches=launches, clocks=clocks, roofline=roofline, pipeline_hbm=pipeline_hbm,
+                staged=dict(value=staged_value, unit=UNIT, ms_per_step=ms_staged / staged_steps,
+                            note="same job through the drop-in modules one by one (roundtrip_staged)"),
                 stages_ms=stages)
 
     if rank == 0 and not a.no_cpu_baseline:
@@ -377,6 +386,10 @@ def stage_times(torch, D, pipe, x, dev, reps=3):
                                           448, 448, _lib.ptr(planes), st))
         ipt2 = t("dct_inv", lambda: U.idct2_truncated(planes, H, W))
     t("ipt_to_rgb", lambda: U.ipt_to_rgb(ipt2))
+    if pipe.fusable():
+        del ipt2, inv, q, normed
+        fb, fcodes = t("fused:encode_codes(total)", lambda: pipe.encode_codes(x))
+        t("fused:decode_codes(total)", lambda: pipe.decode_codes(fb, fcodes))
     return out
 
 

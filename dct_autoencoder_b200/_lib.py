@@ -62,6 +62,10 @@ SIGNATURES = {
     "dcta_entropy_loss": [P, P, P, P, c_int64, c_int, c_int, c_float, c_float, P],
     "dcta_perplexity": [P, c_int64, c_int, c_int64, P, P, P],
     "dcta_vq_nearest": [P, P, P, P, P, c_int64, c_int, c_int, P],
+    "dcta_pack_codes_lfq": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_float,
+                            c_float, c_float, c_int, c_int, c_float, P, P, P, P, P, P],
+    "dcta_decode_codes_split": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, c_int,
+                                P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P],
     "dcta_row_sumsq": [P, P, c_int64, c_int, P],
     "dcta_split_rows": [P, P, P, c_int64, c_int, c_int64, P, P],
     "dcta_vq_nearest_tc": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int64, P],
@@ -84,6 +88,7 @@ KERNELS_PER_CALL = {
     "dcta_split_planes_centered": 2, "dcta_split_coef_planes": 1,
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,
     "dcta_row_sumsq": 1, "dcta_split_rows": 1, "dcta_vq_nearest_tc": 2,
+    "dcta_pack_codes_lfq": 1, "dcta_decode_codes_split": 1,
 }
 launch_count = 0
 

@@ -1,0 +1,206 @@
+// Fused encode-to-codes and decode-from-codes kernels for the PatchNorm + LFQ bottleneck
+// (reference: feature_extraction_dct_autoencoder.py:437-452, 516-605; patchnorm.py:157-177;
+//  lfq.py:105-134, 168-187; feature_extraction_dct_autoencoder.py:635-653).
+//
+// The staged API materialises gathered patches, normalised patches, quantised patches and
+// de-normalised patches (4 x 2.4 MB per image, each written once and read once).  When the
+// quantiser is a projection-free LFQ and PatchNorm is frozen, the same arithmetic can run in
+// registers between two tensors that must exist anyway:
+//   encode: token grid (GEMM output) --[gather by rank, normalise, sign, bit-pack]--> codes
+//   decode: codes --[slot map, unpack bit, *std + median, fp16 split]--> coefficient planes (GEMM input)
+// Every fp32 operation is the one the staged kernels execute (explicit _rn intrinsics, same
+// order), so codes and planes are bit-identical to the staged path.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace dcta {
+
+constexpr float kSqrt2f = 1.41421356237309504880f;
+
+struct LfqNormParams {
+    const float* median;   // (C, H, W, z)
+    const float* b;        // (C, H, W, z)
+    int C, H, W, z;
+    float eps, lo, hi;     // PatchNorm eps / clamp
+    int c, d;              // LFQ codebooks x bits, c * d == z
+    float scale;           // LFQ codebook_scale
+};
+
+// one warp per output slot (row, s)
+__global__ void __launch_bounds__(256) pack_codes_kernel(
+    const float* __restrict__ tiles, const int32_t* __restrict__ order, const dcta_segment* __restrict__ segs,
+    const int32_t* __restrict__ row_seg_start, int n_rows, int s, int tw, int channels, int n_tok_img,
+    LfqNormParams q, int64_t* __restrict__ codes, int64_t* __restrict__ positions, int64_t* __restrict__ channels_out,
+    int64_t* __restrict__ image_ids, uint8_t* __restrict__ key_pad_mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = (int64_t)n_rows * s;
+    const int z = q.z;
+    for (int64_t slot = warp0; slot < total; slot += n_warps) {
+        const int row = (int)(slot / s);
+        const int off = (int)(slot - (int64_t)row * s);
+        int lo = row_seg_start[row], hi = row_seg_start[row + 1];
+        int seg = -1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const int so = segs[mid].offset;
+            if (off < so) hi = mid;
+            else if (off >= so + segs[mid].k) lo = mid + 1;
+            else { seg = mid; break; }
+        }
+        const float* src = nullptr;
+        int ph = 0, pw = 0, pc = 0, image_id = 0;
+        if (seg >= 0) {
+            const dcta_segment sg = segs[seg];
+            const int tok = order[sg.img * n_tok_img + (off - sg.offset)];
+            src = tiles + (sg.img * n_tok_img + tok) * z;
+            pc = tok % channels;
+            const int tile = tok / channels;
+            ph = tile / tw;
+            pw = tile - ph * tw;
+            image_id = sg.image_id;
+        }
+        // padding slots are quantised like the reference does: zeros normalised with the statistics
+        // at (0, 0, 0)  (patchnorm.py:157-161 runs on padding rows too)
+        const int64_t pid = ((int64_t)pc * q.H + ph) * q.W + pw;
+        const float* ms = q.median + pid * z;
+        const float* bs = q.b + pid * z;
+        // sign bits of up to 256 elements: lane k keeps word k (bit (e & 31) of word e >> 5)
+        unsigned my_word = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int e = lane + 32 * k;
+            bool bit = false;
+            if (k * 32 < z && e < z) {
+                const float xv = src ? __ldg(src + e) : 0.0f;
+                const float sd = __fadd_rn(__fmul_rn(__ldg(bs + e), kSqrt2f), q.eps);
+                float y = __fdiv_rn(__fsub_rn(xv, __ldg(ms + e)), sd);
+                y = y < q.lo ? q.lo : (y > q.hi ? q.hi : y);
+                bit = y > 0.0f;                                     // lfq.py:175
+            }
+            const unsigned w = __ballot_sync(0xffffffffu, bit);
+            if (lane == k) my_word = w;
+        }
+        // lfq.py:187: code[cb] = sum_i bit(cb*d + i) << (d-1-i); lane cb assembles codebook cb
+        for (int cb0 = 0; cb0 < q.c; cb0 += 32) {
+            const int cb = cb0 + lane;
+            unsigned long long code = 0;
+            for (int i = 0; i < q.d; ++i) {
+                const int e = min(cb * q.d + i, z - 1);
+                const unsigned w = __shfl_sync(0xffffffffu, my_word, e >> 5);
+                code = (code << 1) | ((w >> (e & 31)) & 1u);
+            }
+            if (cb < q.c) codes[slot * q.c + cb] = (int64_t)code;
+        }
+        if (lane == 0) {
+            positions[slot * 2] = ph;
+            positions[slot * 2 + 1] = pw;
+            channels_out[slot] = pc;
+            if (image_ids) image_ids[slot] = image_id;
+            if (key_pad_mask) key_pad_mask[slot] = seg < 0;
+        }
+    }
+}
+
+__device__ __forceinline__ void split16f(float v, float scale, __half& h, __half& l) {
+    const float s = v * scale;
+    h = __float2half_rn(s);
+    l = __float2half_rn(s - __half2float(h));
+}
+
+// one thread per 4 consecutive plane columns; planes are the inverse GEMM's fp16 hi/lo operand
+__global__ void __launch_bounds__(256) decode_codes_split_kernel(
+    const int64_t* __restrict__ codes, const int32_t* __restrict__ slot_map, const int32_t* __restrict__ img_sel,
+    int64_t n_img, int th, int tw, int p, int rows, int cols, int64_t ld, LfqNormParams q, __half* __restrict__ hi,
+    __half* __restrict__ lo, float* __restrict__ dc, float dc_factor, float scale) {
+    const int C = q.C;
+    const int cols4 = (int)(ld / 4);
+    const int64_t total = n_img * C * rows * cols4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xv = (int)(i % cols4);
+        int64_t r = i / cols4;
+        const int y = (int)(r % rows);
+        r /= rows;
+        const int c = (int)(r % C);
+        const int64_t sel = r / C;
+        const int64_t img = img_sel ? img_sel[sel] : sel;
+        const int ty = y / p, py = y - ty * p;
+        __half oh[4], ol[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = xv * 4 + j;
+            const int tx = x / p, px = x - tx * p;
+            float val = 0.0f;
+            if (x < cols && ty < th && tx < tw) {
+                const int32_t slot = __ldg(slot_map + ((img * C + c) * th + ty) * tw + tx);
+                if (slot >= 0) {
+                    const int e = py * p + px;
+                    const int cb = e / q.d, bi = e - cb * q.d;
+                    const long long code = __ldg(codes + (int64_t)slot * q.c + cb);
+                    const float qv = ((code >> (q.d - 1 - bi)) & 1) ? q.scale : -q.scale;     // lfq.py:118-120
+                    const int64_t pe = (((int64_t)c * q.H + ty) * q.W + tx) * q.z + e;
+                    const float sd = __fadd_rn(__fmul_rn(__ldg(q.b + pe), kSqrt2f), q.eps);
+                    val = __fadd_rn(__fmul_rn(qv, sd), __ldg(q.median + pe));                  // patchnorm.py:177
+                }
+            }
+            if (y == 0 && x == 0) {
+                dc[sel * C + c] = val * dc_factor;
+                val = 0.0f;
+            }
+            split16f(val, scale, oh[j], ol[j]);
+        }
+        const int64_t o = ((sel * C + c) * rows + y) * (ld / 4) + xv;
+        reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(oh);
+        reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(ol);
+    }
+}
+
+}  // namespace dcta
+
+using namespace dcta;
+
+static int check_params(const char* who, const float* median, const float* b, int C, int H, int W, int z, int c, int d) {
+    DCTA_REQUIRE(median && b, "%s: null statistics", who);
+    DCTA_REQUIRE(C > 0 && H > 0 && W > 0 && z > 0 && z <= 256, "%s: z=%d outside 1..256", who, z);
+    DCTA_REQUIRE(c > 0 && d > 0 && d <= 62 && c * d == z, "%s: needs a projection-free LFQ (c*d == z)", who);
+    return DCTA_OK;
+}
+
+extern "C" int dcta_pack_codes_lfq(const float* tiles, const int32_t* order, const dcta_segment* segs,
+                                   const int32_t* row_seg_start, int n_rows, int s, int th, int tw, int channels,
+                                   int z, const float* median, const float* b, int H, int W, float eps, float lo,
+                                   float hi, int c, int d, float scale, int64_t* codes, int64_t* positions,
+                                   int64_t* channels_out, int64_t* image_ids, uint8_t* key_pad_mask, void* stream) {
+    DCTA_REQUIRE(tiles && order && segs && row_seg_start && codes && positions && channels_out, "pack_codes_lfq: null pointer");
+    DCTA_REQUIRE(n_rows >= 0 && s > 0 && th > 0 && tw > 0 && channels > 0 && th <= H && tw <= W,
+                 "pack_codes_lfq: bad sizes (token grid must fit the PatchNorm tables)");
+    int rc = check_params("pack_codes_lfq", median, b, channels, H, W, z, c, d);
+    if (rc) return rc;
+    if (n_rows == 0) return DCTA_OK;
+    LfqNormParams q{median, b, channels, H, W, z, eps, lo, hi, c, d, scale};
+    pack_codes_kernel<<<grid_for((int64_t)n_rows * s, 8), 256, 0, as_stream(stream)>>>(
+        tiles, order, segs, row_seg_start, n_rows, s, tw, channels, th * tw * channels, q, codes, positions,
+        channels_out, image_ids, key_pad_mask);
+    return check_launch("pack_codes_lfq");
+}
+
+extern "C" int dcta_decode_codes_split(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel,
+                                       int64_t n_img, int channels_n, int th, int tw, int p, int rows, int cols,
+                                       int64_t ld, int out_h, int out_w, const float* median, const float* b, int H,
+                                       int W, float eps, int c, int d, float scale, void* y_hi, void* y_lo,
+                                       float* dc, void* stream) {
+    DCTA_REQUIRE(codes && slot_map && y_hi && y_lo && dc, "decode_codes_split: null pointer");
+    DCTA_REQUIRE(ld % 8 == 0 && ld >= cols && rows > 0 && cols > 0 && p > 0 && out_h > 0 && out_w > 0 && th <= H && tw <= W,
+                 "decode_codes_split: bad sizes");
+    int rc = check_params("decode_codes_split", median, b, channels_n, H, W, p * p, c, d);
+    if (rc) return rc;
+    if (n_img == 0) return DCTA_OK;
+    LfqNormParams q{median, b, channels_n, H, W, p * p, eps, 0.f, 0.f, c, d, scale};
+    const int64_t total = n_img * channels_n * rows * (ld / 4);
+    decode_codes_split_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
+        codes, slot_map, img_sel, n_img, th, tw, p, rows, cols, ld, q, (__half*)y_hi, (__half*)y_lo, dc,
+        1.0f / sqrtf((float)out_h * (float)out_w), 16.0f);
+    return check_launch("decode_codes_split");
+}

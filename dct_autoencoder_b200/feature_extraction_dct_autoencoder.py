@@ -279,6 +279,59 @@ class DCTAutoencoderFeatureExtractor:
                           patch_sizes=[(ph, pw)] * b, original_sizes=[(h, w)] * b,
                           _data={}, _row_num_images=[len(r) for r in rows])
 
+    # ------------------------------------------------------------------ fused PatchNorm + LFQ path
+    @staticmethod
+    def _lfq_fusable(norm, lfq) -> bool:
+        """Projection-free LFQ in eval mode on frozen (or eval) fp32 PatchNorm tables."""
+        return (getattr(lfq, "has_projections", True) is False and not lfq.training
+                and (norm.frozen or not norm.training)
+                and lfq.num_codebooks * lfq.codebook_dim == norm.patch_size ** 2 <= 256
+                and norm.median.dtype == torch.float32 and norm.median.is_cuda)
+
+    @torch.no_grad()
+    def process_batch_to_codes(self, images: torch.Tensor, norm, lfq, ks: Optional[Sequence[int]] = None):
+        """``process_batch`` -> ``norm(batch)`` -> ``lfq(., mask)`` with the three intermediate patch
+        tensors kept in registers (csrc/fused_lfq.cu).  Returns (DCTPatches with ``patches=None``,
+        codes (rows, s, codebooks) int64), bit-identical to the staged calls."""
+        assert self._lfq_fusable(norm, lfq)
+        x = to_device_f32(images, self._dev(images))
+        b, c, h, w = x.shape
+        ph, pw, th, tw = self._geometry(h, w)
+        tiles = self._token_grid(x)
+        order = self._sorted_order(tiles)
+        n_tok = th * tw * c
+        if ks is None:
+            ks = [self._choose_k(n_tok) for _ in range(b)]
+        state = self._next_fit(ks)
+        rows = state.rows + ([state.row] if state.row else [])
+        tab, offs = self._tables(rows, dict(enumerate(ks)), x.device)
+        n_rows, s = len(rows), self.max_seq_len
+        codes = torch.empty((n_rows, s, lfq.num_codebooks), dtype=torch.int64, device=x.device)
+        pos = torch.empty((n_rows, s, 2), dtype=torch.int64, device=x.device)
+        chan = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
+        ids = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
+        pad = torch.empty((n_rows, s), dtype=torch.bool, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("dcta_pack_codes_lfq", _lib.ptr(tiles), _lib.ptr(order), tab.data_ptr() + offs[0],
+                      tab.data_ptr() + offs[1], n_rows, s, th, tw, c, self.patch_size ** 2,
+                      _lib.ptr(norm.median.data), _lib.ptr(norm.b.data), norm.max_patch_h, norm.max_patch_w,
+                      float(norm.eps), float(norm.min_val), float(norm.max_val), lfq.num_codebooks,
+                      lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(codes), _lib.ptr(pos), _lib.ptr(chan),
+                      _lib.ptr(ids), _lib.ptr(pad), _lib.stream_ptr(x.device))
+        batch = DCTPatches(patches=None, key_pad_mask=pad, batched_image_ids=ids, patch_channels=chan,
+                           patch_positions=pos, patch_sizes=[(ph, pw)] * b, original_sizes=[(h, w)] * b,
+                           _data={}, _row_num_images=[len(r) for r in rows])
+        return batch, codes
+
+    @torch.no_grad()
+    def postprocess_codes_batch(self, x: DCTPatches, codes: torch.Tensor, norm, lfq) -> torch.Tensor:
+        """``lfq.indices_to_codes`` -> ``norm.inverse_norm`` -> ``postprocess_batch`` with the
+        de-quantised patches kept in registers; same-size batches, tensor-core DCT path."""
+        assert self._lfq_fusable(norm, lfq) and self.dct_impl == "tc"
+        assert len(set(map(tuple, x.original_sizes))) == 1 and len(set(map(tuple, x.patch_sizes))) == 1
+        (idx, rgb), = self._decode_groups(x, codes=codes.contiguous(), norm=norm, lfq=lfq)
+        return rgb
+
     def _group_patches_by_max_seq_len(self, batched_patches, batched_positions=None,
                                       batched_channels=None, state: Optional[_PackState] = None,
                                       first: int = 0) -> _PackState:
@@ -372,13 +425,13 @@ class DCTAutoencoderFeatureExtractor:
 
     # ------------------------------------------------------------------ decode
     def _slot_map(self, x: DCTPatches, th: int, tw: int):
-        b, s, _ = x.patches.shape
+        b, s = x.key_pad_mask.shape
         counts = x.row_num_images()
         n_img = int(sum(counts))
         base = np.zeros(b, dtype=np.int32)
         if b > 1:
             base[1:] = np.cumsum(counts[:-1])
-        dev = x.patches.device
+        dev = x.key_pad_mask.device
         key = b"base" + base.tobytes()
         base_dev = self._table_cache.get(key)
         if base_dev is None or base_dev.device != dev:
@@ -446,14 +499,20 @@ class DCTAutoencoderFeatureExtractor:
                 res[i] = rgb[n] if og == torch.float32 else rgb[n].to(og)
         return res
 
-    def _decode_groups(self, x: DCTPatches):
+    def _decode_groups(self, x: DCTPatches, codes: Optional[torch.Tensor] = None, norm=None, lfq=None):
         """Token rows -> RGB, one kernel sequence per group of images that share (tile grid,
         original size).  Yields (image indices, rgb (n, c, h, w)).  The zero padding of FE:300-304
-        is implicit in the truncated inverse basis."""
-        _lib.require_cuda(x.patches, x.patch_positions, x.patch_channels, x.batched_image_ids, x.key_pad_mask)
+        is implicit in the truncated inverse basis.  With ``codes`` the tokens are de-quantised and
+        de-normalised on the fly (fused LFQ + PatchNorm decode) instead of being read from ``patches``."""
+        _lib.require_cuda(x.patch_positions, x.patch_channels, x.batched_image_ids, x.key_pad_mask)
         p, C = self.patch_size, self.channels
-        patches = to_device_f32(x.patches)
-        dev = patches.device
+        if codes is None:
+            _lib.require_cuda(x.patches)
+            patches = to_device_f32(x.patches)
+            dev = patches.device
+        else:
+            patches = None
+            dev = codes.device
         tiles = [(min(int(a), self.max_patch_h), min(int(b), self.max_patch_w)) for a, b in x.patch_sizes]
         th, tw = max(a for a, _ in tiles), max(b for _, b in tiles)
         slot_map, n_img = self._slot_map(x, th, tw)
@@ -473,8 +532,15 @@ class DCTAutoencoderFeatureExtractor:
                     y_hi = torch.empty((n, C, kh, ld), dtype=torch.float16, device=dev)
                     y_lo = torch.empty_like(y_hi)
                     dc = torch.empty(n * C, dtype=torch.float32, device=dev)
-                    _lib.call("dcta_unpatchify_split", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
-                              th, tw, p, kh, kw, ld, h, w, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc), st)
+                    if codes is not None:
+                        _lib.call("dcta_decode_codes_split", _lib.ptr(codes), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
+                                  th, tw, p, kh, kw, ld, h, w, _lib.ptr(norm.median.data), _lib.ptr(norm.b.data),
+                                  norm.max_patch_h, norm.max_patch_w, float(norm.eps), lfq.num_codebooks,
+                                  lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(y_hi), _lib.ptr(y_lo),
+                                  _lib.ptr(dc), st)
+                    else:
+                        _lib.call("dcta_unpatchify_split", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
+                                  th, tw, p, kh, kw, ld, h, w, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc), st)
                     ipt = dct2_inv_tc(y_hi, y_lo, dc, kw, h, w)
                 else:
                     planes = torch.empty((n, C, kh, kw), dtype=torch.float32, device=dev)

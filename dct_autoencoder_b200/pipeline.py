@@ -65,10 +65,50 @@ class TransformPipeline:
         b.patches = self.norm.inverse_norm(b)
         return self.extractor.postprocess_batch(b)
 
+    def fusable(self) -> bool:
+        """True when PatchNorm + LFQ can run inside the pack / un-patchify kernels (projection-free
+        LFQ in eval mode, frozen fp32 statistics, tensor-core DCT path)."""
+        fe = self.extractor
+        return (fe.dct_impl == "tc" and not fe._hooks_overridden("_transform_image_in")
+                and not fe._hooks_overridden("_transform_image_out")
+                and fe._lfq_fusable(self.norm, self.quantizer))
+
     @torch.no_grad()
-    def roundtrip(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None):
+    def encode_codes(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None):
+        """Images -> (batch metadata, codes); uses the fused kernel when ``fusable()``."""
+        if self.fusable():
+            return self.extractor.process_batch_to_codes(images, self.norm, self.quantizer, ks)
+        batch, _, codes = self.encode(images, ks)
+        return batch, codes
+
+    @torch.no_grad()
+    def decode_codes(self, batch: DCTPatches, codes: torch.Tensor) -> torch.Tensor:
+        """(batch metadata, codes) -> (n, c, h, w) RGB (modeling_dct_autoencoder.py:157-163
+        decode_from_codes without the transformer); fused when ``fusable()``."""
+        if self.fusable():
+            return self.extractor.postprocess_codes_batch(batch, codes, self.norm, self.quantizer)
+        b = batch.shallow_copy()
+        b.patches = self.quantizer.indices_to_codes(codes)
+        b.patches = self.norm.inverse_norm(b)
+        return self.extractor.postprocess_batch(b)
+
+    @torch.no_grad()
+    def roundtrip_staged(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None):
+        """The round trip through the drop-in modules one by one (every intermediate tensor
+        materialised, as a user of the reference's API would write it)."""
         batch, q, codes = self.encode(images, ks)
         return self.decode(batch, q), codes
+
+    @torch.no_grad()
+    def roundtrip(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None, fused: Optional[bool] = None):
+        """images -> (reconstructed images, codes).  ``fused=None`` picks the fused PatchNorm+LFQ
+        kernels when they apply; results are bit-identical to ``roundtrip_staged``."""
+        if fused is None:
+            fused = self.fusable()
+        if not fused:
+            return self.roundtrip_staged(images, ks)
+        batch, codes = self.encode_codes(images, ks)
+        return self.decode_codes(batch, codes), codes
 
     @torch.no_grad()
     def roundtrip_host(self, images: torch.Tensor, out_images: Optional[torch.Tensor] = None,

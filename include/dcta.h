@@ -222,6 +222,26 @@ int dcta_entropy_loss(const float* affinity, const uint8_t* mask, float* scratch
 int dcta_perplexity(const int64_t* codes, int64_t n, int codebook_size, int64_t null_index,
                     int64_t* counts, float* result, void* stream);
 
+/* ------------------------------------------------------------------ fused PatchNorm + LFQ -- */
+/* Encode to codes without materialising the gathered / normalised / quantised patches:
+ * dcta_pack_tiles' gather (FE:437-452, FE:516-605) + PN:157-165 + lfq.py:168-187 in registers.
+ * Requires a projection-free LFQ (c*d == z <= 256) and frozen statistics.  Padding slots are
+ * quantised as the reference does (zeros normalised with the statistics at (0,0,0)).
+ * Outputs are bit-identical to dcta_pack_tiles -> dcta_patchnorm_apply -> dcta_lfq_quantize. */
+int dcta_pack_codes_lfq(const float* tiles, const int32_t* order, const dcta_segment* segs,
+                        const int32_t* row_seg_start, int n_rows, int s, int th, int tw, int channels,
+                        int z, const float* median, const float* b, int H, int W, float eps, float lo,
+                        float hi, int c, int d, float scale, int64_t* codes, int64_t* positions,
+                        int64_t* channels_out, int64_t* image_ids, uint8_t* key_pad_mask, void* stream);
+/* Decode from codes straight into the inverse GEMM's operand planes: lfq.py:105-134 unpack +
+ * PN:167-177 de-normalise + FE:635-653 un-patchify + fp16 hi/lo split (scale 2^4, DC to dc[]).
+ * Bit-identical to dcta_lfq_indices_to_codes -> dcta_patchnorm_apply(inverse) -> dcta_unpatchify_split. */
+int dcta_decode_codes_split(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel,
+                            int64_t n_img, int channels_n, int th, int tw, int p, int rows, int cols,
+                            int64_t ld, int out_h, int out_w, const float* median, const float* b, int H,
+                            int W, float eps, int c, int d, float scale, void* y_hi, void* y_lo,
+                            float* dc, void* stream);
+
 /* ------------------------------------------------------------------ VectorQuantize -------- */
 /* VQ:29-33 cdist + VQ:467-469 argmax(-dist) + VQ:222-226/477 gather, never materialising the
  * (n_tok, n_codes) distance matrix.

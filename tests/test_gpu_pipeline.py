@@ -76,3 +76,45 @@ def test_odd_sizes_fall_back_to_exact_fp32_forward(D):
     ofe = O.FeatureExtractor(3, 14, 0.0, 32, 32, 3072)
     it = ofe.preprocess(x[0].cpu().numpy())
     assert np.abs(b1.patches[0, : it["patches"].shape[0]].cpu().numpy() - it["patches"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("beta,max_seq_len,size", [(0.0, 3072, (256, 256)), (0.0, 972, (256, 256)),
+                                                   (0.01, 512, (128, 160)), (0.0, 200, (128, 160))])
+def test_fused_roundtrip_is_bit_identical_to_staged(D, beta, max_seq_len, size):
+    """encode_codes / decode_codes (PatchNorm + LFQ inside the pack / un-patchify kernels) give the
+    same codes, metadata and images, bit for bit, as the module-by-module path -- including padding
+    slots, several images per row, top-k cuts and variable k."""
+    import random
+    torch.manual_seed(4)
+    h, w = size
+    x = torch.rand(9, 3, h, w).cuda()
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, beta, 32, 32, max_seq_len)
+    pn = D.PatchNorm(32, 32, 14, 3).cuda()
+    lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).cuda().eval()
+    pipe = D.TransformPipeline(fe, pn, lfq)
+    random.seed(3)
+    pipe.fit_norm(torch.rand(8, 3, h, w).cuda())
+    assert pipe.fusable()
+    random.seed(11)
+    rec_s, codes_s = pipe.roundtrip(x, fused=False)
+    random.seed(11)
+    batch_s, q_s, _ = pipe.encode(x)
+    random.seed(11)
+    batch_f, codes_f = pipe.encode_codes(x)
+    assert batch_f.patches is None
+    for f in ("key_pad_mask", "batched_image_ids", "patch_channels", "patch_positions"):
+        assert torch.equal(getattr(batch_f, f), getattr(batch_s, f)), f
+    assert torch.equal(codes_f, codes_s)
+    rec_f = pipe.decode_codes(batch_f, codes_f)
+    assert torch.equal(rec_f, rec_s)
+    random.seed(11)
+    rec_auto, codes_auto = pipe.roundtrip(x)
+    assert torch.equal(rec_auto, rec_s) and torch.equal(codes_auto, codes_s)
+    # decode_codes from codes alone == the reference's decode_from_codes chain
+    b2 = batch_s.shallow_copy()
+    b2.patches = lfq.indices_to_codes(codes_s)
+    b2.patches = pn.inverse_norm(b2)
+    assert torch.equal(fe.postprocess_batch(b2), rec_f)
+    # not fusable -> staged path is used transparently
+    lfq2 = D.LFQ(dim=196, codebook_size=8192, num_codebooks=16).cuda().eval()
+    assert not D.TransformPipeline(fe, pn, lfq2).fusable()
