@@ -76,9 +76,17 @@ __global__ void __launch_bounds__(256) pack_codes_kernel(
             if (k * 32 < z && e < z) {
                 const float xv = src ? __ldg(src + e) : 0.0f;
                 const float sd = __fadd_rn(__fmul_rn(__ldg(bs + e), kSqrt2f), q.eps);
-                float y = __fdiv_rn(__fsub_rn(xv, __ldg(ms + e)), sd);
-                y = y < q.lo ? q.lo : (y > q.hi ? q.hi : y);
-                bit = y > 0.0f;                                     // lfq.py:175
+                const float diff = __fsub_rn(xv, __ldg(ms + e));
+                // bit = clamp(diff / sd) > 0 (patchnorm.py:161-163, lfq.py:175).  For a finite positive
+                // sd and a numerator far from the denormal range the quotient has the numerator's sign;
+                // only otherwise is the IEEE division (and the clamp) evaluated.
+                if (sd > 0.0f && sd < 1e30f && fabsf(diff) > 1e-30f && q.lo < 0.0f && q.hi > 0.0f) {
+                    bit = diff > 0.0f;
+                } else {
+                    float y = __fdiv_rn(diff, sd);
+                    y = y < q.lo ? q.lo : (y > q.hi ? q.hi : y);
+                    bit = y > 0.0f;
+                }
             }
             const unsigned w = __ballot_sync(0xffffffffu, bit);
             if (lane == k) my_word = w;
@@ -110,37 +118,47 @@ __device__ __forceinline__ void split16f(float v, float scale, __half& h, __half
     l = __float2half_rn(s - __half2float(h));
 }
 
-// one thread per 4 consecutive plane columns; planes are the inverse GEMM's fp16 hi/lo operand
-__global__ void __launch_bounds__(256) decode_codes_split_kernel(
+// One CTA per plane row (so the row decomposition is block-uniform and there is no 64-bit index
+// arithmetic per element); each thread produces 4 consecutive columns per step.  Planes are the
+// inverse GEMM's fp16 hi/lo operand.
+__global__ void __launch_bounds__(128) decode_codes_split_kernel(
     const int64_t* __restrict__ codes, const int32_t* __restrict__ slot_map, const int32_t* __restrict__ img_sel,
-    int64_t n_img, int th, int tw, int p, int rows, int cols, int64_t ld, LfqNormParams q, __half* __restrict__ hi,
+    int th, int tw, int p, int rows, int cols, int ld, LfqNormParams q, __half* __restrict__ hi,
     __half* __restrict__ lo, float* __restrict__ dc, float dc_factor, float scale) {
     const int C = q.C;
-    const int cols4 = (int)(ld / 4);
-    const int64_t total = n_img * C * rows * cols4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int xv = (int)(i % cols4);
-        int64_t r = i / cols4;
-        const int y = (int)(r % rows);
-        r /= rows;
-        const int c = (int)(r % C);
-        const int64_t sel = r / C;
-        const int64_t img = img_sel ? img_sel[sel] : sel;
-        const int ty = y / p, py = y - ty * p;
+    const unsigned row_id = blockIdx.x;
+    const int y = (int)(row_id % (unsigned)rows);
+    const unsigned t = row_id / (unsigned)rows;
+    const int c = (int)(t % (unsigned)C);
+    const int sel = (int)(t / (unsigned)C);
+    const int64_t img = img_sel ? img_sel[sel] : sel;
+    const int ty = y / p, py = y - ty * p;
+    const bool row_in = ty < th;
+    const int32_t* smap = slot_map + ((img * C + c) * th + (row_in ? ty : 0)) * tw;
+    const int64_t tab_row = (((int64_t)c * q.H + ty) * q.W) * q.z + py * p;   // + tx * z + px
+    const bool row_codebook = (q.d == p);       // one codebook per patch row (14 x 14 bits at patch 14)
+    __half* hrow = hi + (int64_t)row_id * ld;
+    __half* lrow = lo + (int64_t)row_id * ld;
+    for (int xv = threadIdx.x; xv < ld / 4; xv += blockDim.x) {
+        int x = xv * 4;
+        int tx = x / p, px = x - tx * p;
+        int cur_tx = -1, cur_cb = -1;
+        int32_t slot = -1;
+        long long code = 0;
         __half oh[4], ol[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = xv * 4 + j;
-            const int tx = x / p, px = x - tx * p;
+        for (int j = 0; j < 4; ++j, ++x) {
             float val = 0.0f;
-            if (x < cols && ty < th && tx < tw) {
-                const int32_t slot = __ldg(slot_map + ((img * C + c) * th + ty) * tw + tx);
+            if (row_in && x < cols && tx < tw) {
+                if (tx != cur_tx) { slot = __ldg(smap + tx); cur_tx = tx; cur_cb = -1; }
                 if (slot >= 0) {
                     const int e = py * p + px;
-                    const int cb = e / q.d, bi = e - cb * q.d;
-                    const long long code = __ldg(codes + (int64_t)slot * q.c + cb);
+                    int cb, bi;
+                    if (row_codebook) { cb = py; bi = px; }
+                    else { cb = e / q.d; bi = e - cb * q.d; }
+                    if (cb != cur_cb) { code = __ldg(codes + (int64_t)slot * q.c + cb); cur_cb = cb; }
                     const float qv = ((code >> (q.d - 1 - bi)) & 1) ? q.scale : -q.scale;     // lfq.py:118-120
-                    const int64_t pe = (((int64_t)c * q.H + ty) * q.W + tx) * q.z + e;
+                    const int64_t pe = tab_row + (int64_t)tx * q.z + px;
                     const float sd = __fadd_rn(__fmul_rn(__ldg(q.b + pe), kSqrt2f), q.eps);
                     val = __fadd_rn(__fmul_rn(qv, sd), __ldg(q.median + pe));                  // patchnorm.py:177
                 }
@@ -150,10 +168,10 @@ __global__ void __launch_bounds__(256) decode_codes_split_kernel(
                 val = 0.0f;
             }
             split16f(val, scale, oh[j], ol[j]);
+            if (++px == p) { px = 0; ++tx; }
         }
-        const int64_t o = ((sel * C + c) * rows + y) * (ld / 4) + xv;
-        reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(oh);
-        reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(ol);
+        reinterpret_cast<uint2*>(hrow)[xv] = *reinterpret_cast<const uint2*>(oh);
+        reinterpret_cast<uint2*>(lrow)[xv] = *reinterpret_cast<const uint2*>(ol);
     }
 }
 
@@ -198,9 +216,10 @@ extern "C" int dcta_decode_codes_split(const int64_t* codes, const int32_t* slot
     if (rc) return rc;
     if (n_img == 0) return DCTA_OK;
     LfqNormParams q{median, b, channels_n, H, W, p * p, eps, 0.f, 0.f, c, d, scale};
-    const int64_t total = n_img * channels_n * rows * (ld / 4);
-    decode_codes_split_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-        codes, slot_map, img_sel, n_img, th, tw, p, rows, cols, ld, q, (__half*)y_hi, (__half*)y_lo, dc,
+    const int64_t n_rows_total = n_img * channels_n * rows;
+    DCTA_REQUIRE(n_rows_total < (1ll << 31) && ld < (1ll << 30), "decode_codes_split: too many plane rows for one launch");
+    decode_codes_split_kernel<<<(unsigned)n_rows_total, 128, 0, as_stream(stream)>>>(
+        codes, slot_map, img_sel, th, tw, p, rows, cols, (int)ld, q, (__half*)y_hi, (__half*)y_lo, dc,
         1.0f / sqrtf((float)out_h * (float)out_w), 16.0f);
     return check_launch("decode_codes_split");
 }

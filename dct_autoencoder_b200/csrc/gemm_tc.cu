@@ -556,33 +556,36 @@ __global__ void __launch_bounds__(256) rgb_to_ipt_split_kernel(const float* __re
 
 // feature_extraction_dct_autoencoder.py:635-653 un-patchify, writing scaled fp16 hi/lo planes with pitch `ld`.
 // The DC coefficient goes to dc[plane] (already multiplied by dc_factor = 1/sqrt(h*w)) and is stored as 0.
-__global__ void __launch_bounds__(256) unpatchify_split_kernel(const float* __restrict__ patches,
+__global__ void __launch_bounds__(128) unpatchify_split_kernel(const float* __restrict__ patches,
                                                                const int32_t* __restrict__ slot_map,
-                                                               const int32_t* __restrict__ img_sel, int64_t n_img,
-                                                               int C, int th, int tw, int p, int rows, int cols,
-                                                               int64_t ld, __half* __restrict__ hi,
-                                                               __half* __restrict__ lo, float* __restrict__ dc,
-                                                               float dc_factor, float scale) {
+                                                               const int32_t* __restrict__ img_sel, int C, int th,
+                                                               int tw, int p, int rows, int cols, int ld,
+                                                               __half* __restrict__ hi, __half* __restrict__ lo,
+                                                               float* __restrict__ dc, float dc_factor, float scale) {
+    // one CTA per plane row: the (image, channel, row) decomposition is block-uniform
     const int z = p * p;
-    const int cols4 = (int)(ld / 4);
-    const int64_t total = n_img * C * rows * cols4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int xv = (int)(i % cols4);
-        int64_t r = i / cols4;
-        const int y = (int)(r % rows);
-        r /= rows;
-        const int c = (int)(r % C);
-        const int64_t sel = r / C;
-        const int64_t img = img_sel ? img_sel[sel] : sel;
-        const int ty = y / p, py = y - ty * p;
+    const unsigned row_id = blockIdx.x;
+    const int y = (int)(row_id % (unsigned)rows);
+    const unsigned t = row_id / (unsigned)rows;
+    const int c = (int)(t % (unsigned)C);
+    const int sel = (int)(t / (unsigned)C);
+    const int64_t img = img_sel ? img_sel[sel] : sel;
+    const int ty = y / p, py = y - ty * p;
+    const bool row_in = ty < th;
+    const int32_t* smap = slot_map + ((img * C + c) * th + (row_in ? ty : 0)) * tw;
+    __half* hrow = hi + (int64_t)row_id * ld;
+    __half* lrow = lo + (int64_t)row_id * ld;
+    for (int xv = threadIdx.x; xv < ld / 4; xv += blockDim.x) {
+        int x = xv * 4;
+        int tx = x / p, px = x - tx * p;
+        int cur_tx = -1;
+        int32_t slot = -1;
         __half oh[4], ol[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = xv * 4 + j;
-            const int tx = x / p, px = x - tx * p;
+        for (int j = 0; j < 4; ++j, ++x) {
             float val = 0.0f;
-            if (x < cols && ty < th && tx < tw) {
-                const int32_t slot = __ldg(slot_map + ((img * C + c) * th + ty) * tw + tx);
+            if (row_in && x < cols && tx < tw) {
+                if (tx != cur_tx) { slot = __ldg(smap + tx); cur_tx = tx; }
                 if (slot >= 0) val = __ldg(patches + (int64_t)slot * z + py * p + px);
             }
             if (y == 0 && x == 0) {
@@ -590,10 +593,10 @@ __global__ void __launch_bounds__(256) unpatchify_split_kernel(const float* __re
                 val = 0.0f;
             }
             split16(val, scale, oh[j], ol[j]);
+            if (++px == p) { px = 0; ++tx; }
         }
-        const int64_t o = ((sel * C + c) * rows + y) * (ld / 4) + xv;
-        reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(oh);
-        reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(ol);
+        reinterpret_cast<uint2*>(hrow)[xv] = *reinterpret_cast<const uint2*>(oh);
+        reinterpret_cast<uint2*>(lrow)[xv] = *reinterpret_cast<const uint2*>(ol);
     }
 }
 
@@ -670,9 +673,10 @@ extern "C" int dcta_unpatchify_split(const float* patches, const int32_t* slot_m
     DCTA_REQUIRE(ld % 8 == 0 && ld >= cols && rows > 0 && cols > 0 && p > 0 && out_h > 0 && out_w > 0,
                  "unpatchify_split: bad sizes");
     if (n_img == 0) return DCTA_OK;
-    const int64_t total = n_img * channels_n * rows * (ld / 4);
-    unpatchify_split_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-        patches, slot_map, img_sel, n_img, channels_n, th, tw, p, rows, cols, ld, (__half*)y_hi, (__half*)y_lo, dc,
+    const int64_t n_rows_total = n_img * channels_n * rows;
+    DCTA_REQUIRE(n_rows_total < (1ll << 31) && ld < (1ll << 30), "unpatchify_split: too many plane rows for one launch");
+    unpatchify_split_kernel<<<(unsigned)n_rows_total, 128, 0, as_stream(stream)>>>(
+        patches, slot_map, img_sel, channels_n, th, tw, p, rows, cols, (int)ld, (__half*)y_hi, (__half*)y_lo, dc,
         1.0f / sqrtf((float)out_h * (float)out_w), kScaleY);
     return check_launch("unpatchify_split");
 }
