@@ -118,60 +118,71 @@ __device__ __forceinline__ void split16f(float v, float scale, __half& h, __half
     l = __float2half_rn(s - __half2float(h));
 }
 
-// One CTA per plane row (so the row decomposition is block-uniform and there is no 64-bit index
-// arithmetic per element); each thread produces 4 consecutive columns per step.  Planes are the
-// inverse GEMM's fp16 hi/lo operand.
+// One CTA per tile-row of one plane (p consecutive plane rows): the (image, channel, tile-row)
+// decomposition is block-uniform, each thread owns 4 consecutive columns and walks the p rows, so the
+// slot-map entry is loaded once per tile and the statistics pointers advance by p per row.  Planes are
+// the inverse GEMM's fp16 hi/lo operand.
 __global__ void __launch_bounds__(128) decode_codes_split_kernel(
     const int64_t* __restrict__ codes, const int32_t* __restrict__ slot_map, const int32_t* __restrict__ img_sel,
     int th, int tw, int p, int rows, int cols, int ld, LfqNormParams q, __half* __restrict__ hi,
     __half* __restrict__ lo, float* __restrict__ dc, float dc_factor, float scale) {
     const int C = q.C;
-    const unsigned row_id = blockIdx.x;
-    const int y = (int)(row_id % (unsigned)rows);
-    const unsigned t = row_id / (unsigned)rows;
+    const int tile_rows = rows / p;
+    const unsigned id = blockIdx.x;
+    const int ty = (int)(id % (unsigned)tile_rows);
+    const unsigned t = id / (unsigned)tile_rows;
     const int c = (int)(t % (unsigned)C);
     const int sel = (int)(t / (unsigned)C);
     const int64_t img = img_sel ? img_sel[sel] : sel;
-    const int ty = y / p, py = y - ty * p;
     const bool row_in = ty < th;
     const int32_t* smap = slot_map + ((img * C + c) * th + (row_in ? ty : 0)) * tw;
-    const int64_t tab_row = (((int64_t)c * q.H + ty) * q.W) * q.z + py * p;   // + tx * z + px
+    const float* med_row = q.median + (((int64_t)c * q.H + ty) * q.W) * q.z;   // + tx * z + py * p + px
+    const float* b_row = q.b + (((int64_t)c * q.H + ty) * q.W) * q.z;
     const bool row_codebook = (q.d == p);       // one codebook per patch row (14 x 14 bits at patch 14)
-    __half* hrow = hi + (int64_t)row_id * ld;
-    __half* lrow = lo + (int64_t)row_id * ld;
+    const int64_t plane_row0 = ((int64_t)(sel * C + c) * rows + (int64_t)ty * p) * ld;
     for (int xv = threadIdx.x; xv < ld / 4; xv += blockDim.x) {
-        int x = xv * 4;
-        int tx = x / p, px = x - tx * p;
-        int cur_tx = -1, cur_cb = -1;
-        int32_t slot = -1;
-        long long code = 0;
-        __half oh[4], ol[4];
+        const int x0 = xv * 4;
+        const int tx0 = x0 / p, px0 = x0 - tx0 * p;
+        // the 4 columns touch at most two tiles
+        const int tx1 = tx0 + 1;
+        const int n_first = min(4, p - px0);                       // columns that belong to tile tx0
+        const int32_t slot0 = (row_in && tx0 < tw) ? __ldg(smap + tx0) : -1;
+        const int32_t slot1 = (row_in && n_first < 4 && tx1 < tw) ? __ldg(smap + tx1) : -1;
+        for (int py = 0; py < p; ++py) {
+            __half oh[4], ol[4];
+            long long code0 = 0, code1 = 0;
+            if (row_codebook) {
+                if (slot0 >= 0) code0 = __ldg(codes + (int64_t)slot0 * q.c + py);
+                if (slot1 >= 0) code1 = __ldg(codes + (int64_t)slot1 * q.c + py);
+            }
 #pragma unroll
-        for (int j = 0; j < 4; ++j, ++x) {
-            float val = 0.0f;
-            if (row_in && x < cols && tx < tw) {
-                if (tx != cur_tx) { slot = __ldg(smap + tx); cur_tx = tx; cur_cb = -1; }
-                if (slot >= 0) {
+            for (int j = 0; j < 4; ++j) {
+                const bool first = j < n_first;
+                const int32_t slot = first ? slot0 : slot1;
+                const int tx = first ? tx0 : tx1;
+                const int px = first ? px0 + j : j - n_first;
+                float val = 0.0f;
+                if (slot >= 0 && x0 + j < cols) {
                     const int e = py * p + px;
-                    int cb, bi;
-                    if (row_codebook) { cb = py; bi = px; }
-                    else { cb = e / q.d; bi = e - cb * q.d; }
-                    if (cb != cur_cb) { code = __ldg(codes + (int64_t)slot * q.c + cb); cur_cb = cb; }
+                    long long code;
+                    int bi;
+                    if (row_codebook) { code = first ? code0 : code1; bi = px; }
+                    else { const int cb = e / q.d; bi = e - cb * q.d; code = __ldg(codes + (int64_t)slot * q.c + cb); }
                     const float qv = ((code >> (q.d - 1 - bi)) & 1) ? q.scale : -q.scale;     // lfq.py:118-120
-                    const int64_t pe = tab_row + (int64_t)tx * q.z + px;
-                    const float sd = __fadd_rn(__fmul_rn(__ldg(q.b + pe), kSqrt2f), q.eps);
-                    val = __fadd_rn(__fmul_rn(qv, sd), __ldg(q.median + pe));                  // patchnorm.py:177
+                    const int pe = tx * q.z + e;
+                    const float sd = __fadd_rn(__fmul_rn(__ldg(b_row + pe), kSqrt2f), q.eps);
+                    val = __fadd_rn(__fmul_rn(qv, sd), __ldg(med_row + pe));                    // patchnorm.py:177
                 }
+                if (ty == 0 && py == 0 && x0 + j == 0) {
+                    dc[sel * C + c] = val * dc_factor;
+                    val = 0.0f;
+                }
+                split16f(val, scale, oh[j], ol[j]);
             }
-            if (y == 0 && x == 0) {
-                dc[sel * C + c] = val * dc_factor;
-                val = 0.0f;
-            }
-            split16f(val, scale, oh[j], ol[j]);
-            if (++px == p) { px = 0; ++tx; }
+            const int64_t o = (plane_row0 + (int64_t)py * ld) / 4 + xv;
+            reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(oh);
+            reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(ol);
         }
-        reinterpret_cast<uint2*>(hrow)[xv] = *reinterpret_cast<const uint2*>(oh);
-        reinterpret_cast<uint2*>(lrow)[xv] = *reinterpret_cast<const uint2*>(ol);
     }
 }
 
@@ -216,7 +227,8 @@ extern "C" int dcta_decode_codes_split(const int64_t* codes, const int32_t* slot
     if (rc) return rc;
     if (n_img == 0) return DCTA_OK;
     LfqNormParams q{median, b, channels_n, H, W, p * p, eps, 0.f, 0.f, c, d, scale};
-    const int64_t n_rows_total = n_img * channels_n * rows;
+    DCTA_REQUIRE(rows % p == 0, "decode_codes_split: plane rows must be a multiple of the patch size");
+    const int64_t n_rows_total = n_img * channels_n * (rows / p);
     DCTA_REQUIRE(n_rows_total < (1ll << 31) && ld < (1ll << 30), "decode_codes_split: too many plane rows for one launch");
     decode_codes_split_kernel<<<(unsigned)n_rows_total, 128, 0, as_stream(stream)>>>(
         codes, slot_map, img_sel, th, tw, p, rows, cols, (int)ld, q, (__half*)y_hi, (__half*)y_lo, dc,

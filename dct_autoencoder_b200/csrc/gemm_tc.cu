@@ -420,6 +420,19 @@ __global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict_
         split16(x[i], scale, hi[i], lo[i]);
 }
 
+// Sub-sampling pattern of the plane-mean estimate: runs of kRun consecutive quads (2 KB, so DRAM
+// sectors are fully used) out of every `stride` runs.  The k-th sampled quad of a chunk sits at
+// (k / kRun) * kRun * stride + k % kRun.
+constexpr int kRun = 128;
+__host__ __device__ __forceinline__ int64_t sample_index(int64_t k, int stride) {
+    return (k / kRun) * kRun * stride + (k % kRun);
+}
+__device__ __forceinline__ int64_t next_sample(int64_t cur, int step, int stride) {
+    // cur is a sampled position; advance `step` samples
+    const int64_t k = (cur / (kRun * stride)) * kRun + (cur % (kRun * stride));
+    return sample_index(k + step, stride);
+}
+
 // sums[plane][chunk] = sum of every `stride`-th element-quad of the chunk (an ESTIMATE of the plane
 // sum is enough: whatever constant is removed is added back exactly)
 __global__ void __launch_bounds__(256) plane_sums_kernel(const float* __restrict__ x, float* __restrict__ sums,
@@ -430,7 +443,7 @@ __global__ void __launch_bounds__(256) plane_sums_kernel(const float* __restrict
     const int64_t beg = blockIdx.x * per, end = min(plane4, beg + per);
     const float4* src = reinterpret_cast<const float4*>(x) + pl * plane4;
     float s = 0.f;
-    for (int64_t i = beg + (int64_t)threadIdx.x * stride; i < end; i += (int64_t)blockDim.x * stride) {
+    for (int64_t i = beg + sample_index(threadIdx.x, stride); i < end; i = next_sample(i - beg, blockDim.x, stride) + beg) {
         const float4 v = ld_stream(src + i);
         s += (v.x + v.y) + (v.z + v.w);
     }
@@ -444,23 +457,34 @@ static int64_t sampled_quads(int64_t plane4, int stride) {
     int64_t cnt = 0;
     for (int c = 0; c < kSumChunks; ++c) {
         const int64_t beg = c * per, end = plane4 < beg + per ? plane4 : beg + per;
-        if (end > beg) cnt += (end - beg + stride - 1) / stride;
+        const int64_t len = end - beg;
+        if (len <= 0) continue;
+        const int64_t period = (int64_t)kRun * stride;
+        const int64_t rem = len % period;
+        cnt += (len / period) * kRun + (rem < kRun ? rem : kRun);
     }
     return cnt;
 }
 
-__global__ void __launch_bounds__(256) split_centered_kernel(const float* __restrict__ x, const float* __restrict__ sums,
+// mu[plane] = (sum of the chunk sums in fixed order) * inv_count ;  dc[plane] = mu * dc_factor
+__global__ void finalize_means_kernel(const float* __restrict__ sums, float* __restrict__ mu, float* __restrict__ dc,
+                                      int64_t n_planes, float inv_count, float dc_factor) {
+    const int64_t pl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pl >= n_planes) return;
+    float m = 0.f;
+    for (int c = 0; c < kSumChunks; ++c) m += sums[pl * kSumChunks + c];
+    m *= inv_count;
+    mu[pl] = m;
+    dc[pl] = m * dc_factor;
+}
+
+__global__ void __launch_bounds__(256) split_centered_kernel(const float* __restrict__ x, const float* __restrict__ mus,
                                                              __half* __restrict__ hi, __half* __restrict__ lo,
-                                                             float* __restrict__ dc, int64_t n_planes, int64_t plane4,
-                                                             float inv_count, float dc_factor, float scale) {
+                                                             int64_t n_planes, int64_t plane4, float scale) {
     const int64_t total = n_planes * plane4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pl = i / plane4, q = i - pl * plane4;
-        float mu = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < kSumChunks; ++c) mu += __ldg(sums + pl * kSumChunks + c);
-        mu *= inv_count;
-        if (q == 0) dc[pl] = mu * dc_factor;
+        const int64_t pl = i / plane4;
+        const float mu = __ldg(mus + pl);
         const float4 v = ld_stream(reinterpret_cast<const float4*>(x) + i);
         __half oh[4], ol[4];
         split16(v.x - mu, scale, oh[0], ol[0]);
@@ -496,7 +520,7 @@ __global__ void __launch_bounds__(256) ipt_sums_kernel(const float* __restrict__
     const int64_t beg = blockIdx.x * per, end = min(plane4, beg + per);
     const float4* src = reinterpret_cast<const float4*>(rgb) + img * 3 * plane4;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (int64_t i = beg + (int64_t)threadIdx.x * stride; i < end; i += (int64_t)blockDim.x * stride) {
+    for (int64_t i = beg + sample_index(threadIdx.x, stride); i < end; i = next_sample(i - beg, blockDim.x, stride) + beg) {
         const float4 c0 = ld_stream(src + i), c1 = ld_stream(src + plane4 + i), c2 = ld_stream(src + 2 * plane4 + i);
         const float r[4] = {c0.x, c0.y, c0.z, c0.w}, g[4] = {c1.x, c1.y, c1.z, c1.w}, b[4] = {c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
@@ -517,22 +541,14 @@ __global__ void __launch_bounds__(256) ipt_sums_kernel(const float* __restrict__
 }
 
 // util.py:70-82 rgb_to_ipt, writing the centred, scaled fp16 hi/lo operand planes of the forward GEMM
-__global__ void __launch_bounds__(256) rgb_to_ipt_split_kernel(const float* __restrict__ rgb, const float* __restrict__ sums,
+__global__ void __launch_bounds__(256) rgb_to_ipt_split_kernel(const float* __restrict__ rgb, const float* __restrict__ mus,
                                                                __half* __restrict__ hi, __half* __restrict__ lo,
-                                                               float* __restrict__ dc, int64_t n_img, int64_t plane4,
-                                                               Mat3 A, Mat3 B, float inv_count, float dc_factor,
+                                                               int64_t n_img, int64_t plane4, Mat3 A, Mat3 B,
                                                                float scale) {
     const int64_t total = n_img * plane4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t img = i / plane4, q = i - img * plane4;
-        float mu[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-#pragma unroll 8
-            for (int k = 0; k < kSumChunks; ++k) mu[c] += __ldg(sums + (img * 3 + c) * kSumChunks + k);
-            mu[c] *= inv_count;
-            if (q == 0) dc[img * 3 + c] = mu[c] * dc_factor;
-        }
+        const float mu[3] = {__ldg(mus + img * 3), __ldg(mus + img * 3 + 1), __ldg(mus + img * 3 + 2)};
         const float4* src = reinterpret_cast<const float4*>(rgb) + img * 3 * plane4 + q;
         const float4 c0 = ld_stream(src), c1 = ld_stream(src + plane4), c2 = ld_stream(src + 2 * plane4);
         const float r[4] = {c0.x, c0.y, c0.z, c0.w}, g[4] = {c1.x, c1.y, c1.z, c1.w}, b[4] = {c2.x, c2.y, c2.z, c2.w};
@@ -562,41 +578,43 @@ __global__ void __launch_bounds__(128) unpatchify_split_kernel(const float* __re
                                                                int tw, int p, int rows, int cols, int ld,
                                                                __half* __restrict__ hi, __half* __restrict__ lo,
                                                                float* __restrict__ dc, float dc_factor, float scale) {
-    // one CTA per plane row: the (image, channel, row) decomposition is block-uniform
+    // one CTA per tile-row of one plane (p plane rows): block-uniform decomposition, each thread owns
+    // 4 consecutive columns (at most two tiles) and walks the p rows
     const int z = p * p;
-    const unsigned row_id = blockIdx.x;
-    const int y = (int)(row_id % (unsigned)rows);
-    const unsigned t = row_id / (unsigned)rows;
+    const int tile_rows = rows / p;
+    const unsigned id = blockIdx.x;
+    const int ty = (int)(id % (unsigned)tile_rows);
+    const unsigned t = id / (unsigned)tile_rows;
     const int c = (int)(t % (unsigned)C);
     const int sel = (int)(t / (unsigned)C);
     const int64_t img = img_sel ? img_sel[sel] : sel;
-    const int ty = y / p, py = y - ty * p;
     const bool row_in = ty < th;
     const int32_t* smap = slot_map + ((img * C + c) * th + (row_in ? ty : 0)) * tw;
-    __half* hrow = hi + (int64_t)row_id * ld;
-    __half* lrow = lo + (int64_t)row_id * ld;
+    const int64_t plane_row0 = ((int64_t)(sel * C + c) * rows + (int64_t)ty * p) * ld;
     for (int xv = threadIdx.x; xv < ld / 4; xv += blockDim.x) {
-        int x = xv * 4;
-        int tx = x / p, px = x - tx * p;
-        int cur_tx = -1;
-        int32_t slot = -1;
-        __half oh[4], ol[4];
+        const int x0 = xv * 4;
+        const int tx0 = x0 / p, px0 = x0 - tx0 * p;
+        const int n_first = min(4, p - px0);
+        const int32_t slot0 = (row_in && tx0 < tw) ? __ldg(smap + tx0) : -1;
+        const int32_t slot1 = (row_in && n_first < 4 && tx0 + 1 < tw) ? __ldg(smap + tx0 + 1) : -1;
+        const float* s0 = slot0 >= 0 ? patches + (int64_t)slot0 * z + px0 : nullptr;
+        const float* s1 = slot1 >= 0 ? patches + (int64_t)slot1 * z - n_first : nullptr;
+        for (int py = 0; py < p; ++py) {
+            __half oh[4], ol[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j, ++x) {
-            float val = 0.0f;
-            if (row_in && x < cols && tx < tw) {
-                if (tx != cur_tx) { slot = __ldg(smap + tx); cur_tx = tx; }
-                if (slot >= 0) val = __ldg(patches + (int64_t)slot * z + py * p + px);
+            for (int j = 0; j < 4; ++j) {
+                const float* src = j < n_first ? s0 : s1;
+                float val = (src && x0 + j < cols) ? __ldg(src + py * p + j) : 0.0f;
+                if (ty == 0 && py == 0 && x0 + j == 0) {
+                    dc[sel * C + c] = val * dc_factor;
+                    val = 0.0f;
+                }
+                split16(val, scale, oh[j], ol[j]);
             }
-            if (y == 0 && x == 0) {
-                dc[sel * C + c] = val * dc_factor;
-                val = 0.0f;
-            }
-            split16(val, scale, oh[j], ol[j]);
-            if (++px == p) { px = 0; ++tx; }
+            const int64_t o = (plane_row0 + (int64_t)py * ld) / 4 + xv;
+            reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<const uint2*>(oh);
+            reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<const uint2*>(ol);
         }
-        reinterpret_cast<uint2*>(hrow)[xv] = *reinterpret_cast<const uint2*>(oh);
-        reinterpret_cast<uint2*>(lrow)[xv] = *reinterpret_cast<const uint2*>(ol);
     }
 }
 
@@ -640,8 +658,11 @@ extern "C" int dcta_split_planes_centered(const float* x, void* hi, void* lo, fl
     cudaStream_t st = as_stream(stream);
     plane_sums_kernel<<<dim3(kSumChunks, (unsigned)n_planes), 256, 0, st>>>(x, sums_scratch, plane / 4, kSumStride);
     const float inv_count = 1.0f / (4.0f * (float)sampled_quads(plane / 4, kSumStride));
+    float* mus = sums_scratch + n_planes * kSumChunks;      // scratch holds (kSumChunks + 1) floats per plane
+    finalize_means_kernel<<<(unsigned)ceil_div(n_planes, 128), 128, 0, st>>>(sums_scratch, mus, dc, n_planes, inv_count,
+                                                                             sqrtf((float)h * (float)w));
     split_centered_kernel<<<grid_for(n_planes * (plane / 4), 256), 256, 0, st>>>(
-        x, sums_scratch, (__half*)hi, (__half*)lo, dc, n_planes, plane / 4, inv_count, sqrtf((float)h * (float)w), kScaleX);
+        x, mus, (__half*)hi, (__half*)lo, n_planes, plane / 4, kScaleX);
     return check_launch("split_planes_centered");
 }
 
@@ -659,9 +680,11 @@ extern "C" int dcta_rgb_to_ipt_split(const float* rgb, void* ipt_hi, void* ipt_l
     cudaStream_t st = as_stream(stream);
     ipt_sums_kernel<<<dim3(kSumChunks, (unsigned)n_img), 256, 0, st>>>(rgb, sums_scratch, plane / 4, kSumStride, A, B);
     const float inv_count = 1.0f / (4.0f * (float)sampled_quads(plane / 4, kSumStride));
+    float* mus = sums_scratch + n_img * 3 * kSumChunks;     // scratch holds (kSumChunks + 1) floats per plane
+    finalize_means_kernel<<<(unsigned)ceil_div(n_img * 3, 128), 128, 0, st>>>(sums_scratch, mus, dc, n_img * 3, inv_count,
+                                                                              sqrtf((float)h * (float)w));
     rgb_to_ipt_split_kernel<<<grid_for(n_img * (plane / 4), 256), 256, 0, st>>>(
-        rgb, sums_scratch, (__half*)ipt_hi, (__half*)ipt_lo, dc, n_img, plane / 4, A, B, inv_count,
-        sqrtf((float)h * (float)w), kScaleX);
+        rgb, mus, (__half*)ipt_hi, (__half*)ipt_lo, n_img, plane / 4, A, B, kScaleX);
     return check_launch("rgb_to_ipt_split");
 }
 
@@ -673,7 +696,8 @@ extern "C" int dcta_unpatchify_split(const float* patches, const int32_t* slot_m
     DCTA_REQUIRE(ld % 8 == 0 && ld >= cols && rows > 0 && cols > 0 && p > 0 && out_h > 0 && out_w > 0,
                  "unpatchify_split: bad sizes");
     if (n_img == 0) return DCTA_OK;
-    const int64_t n_rows_total = n_img * channels_n * rows;
+    DCTA_REQUIRE(rows % p == 0, "unpatchify_split: plane rows must be a multiple of the patch size");
+    const int64_t n_rows_total = n_img * channels_n * (rows / p);
     DCTA_REQUIRE(n_rows_total < (1ll << 31) && ld < (1ll << 30), "unpatchify_split: too many plane rows for one launch");
     unpatchify_split_kernel<<<(unsigned)n_rows_total, 128, 0, as_stream(stream)>>>(
         patches, slot_map, img_sel, channels_n, th, tw, p, rows, cols, (int)ld, (__half*)y_hi, (__half*)y_lo, dc,

@@ -281,7 +281,7 @@ def rgb_to_ipt_split(x: torch.Tensor):
     hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     lo = torch.empty_like(hi)
     dc = torch.empty(b * 3, dtype=torch.float32, device=x.device)
-    scratch = torch.empty(b * 3 * 32, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(b * 3 * 33, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.call("dcta_rgb_to_ipt_split", _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc), _lib.ptr(scratch),
                   b, h, w, _M_RGB2LMS, _M_IPT, _lib.stream_ptr(x.device))
@@ -296,7 +296,7 @@ def split_planes_centered(x: torch.Tensor):
     hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     lo = torch.empty_like(hi)
     dc = torch.empty(n_planes, dtype=torch.float32, device=x.device)
-    scratch = torch.empty(n_planes * 32, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(n_planes * 33, dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.call("dcta_split_planes_centered", _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc),
                   _lib.ptr(scratch), n_planes, h, w, _lib.stream_ptr(x.device))

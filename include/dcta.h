@@ -83,7 +83,7 @@ int dcta_split_f32(const float* x, void* hi, void* lo, int64_t n, float scale, v
  * constant (the plane mean / the DC coefficient) before the split and pass it in `dc`; the GEMM
  * epilogue adds its exact contribution back (the DCT of a constant is the DC coefficient only).
  * DCTA_SUM_SCRATCH floats of scratch per plane are needed by the mean estimate. */
-#define DCTA_SUM_SCRATCH 32
+#define DCTA_SUM_SCRATCH 33
 /* fp32 planes (n_planes, h, w) -> centred hi/lo (scale 2^8) + dc[n_planes] = mean * sqrt(h*w). */
 int dcta_split_planes_centered(const float* x, void* hi, void* lo, float* dc, float* sums_scratch,
                                int64_t n_planes, int h, int w, void* stream);
