@@ -112,6 +112,103 @@ __global__ void __launch_bounds__(256) pack_codes_kernel(
     }
 }
 
+// sign of clamp((x - m) / (b*sqrt2 + eps)): decided by the numerator whenever that is safe (see above)
+__device__ __forceinline__ unsigned norm_sign_bit(float xv, float mv, float bv, const LfqNormParams& q) {
+    const float sd = __fadd_rn(__fmul_rn(bv, kSqrt2f), q.eps);
+    const float diff = __fsub_rn(xv, mv);
+    if (sd > 0.0f && sd < 1e30f && fabsf(diff) > 1e-30f && q.lo < 0.0f && q.hi > 0.0f) return diff > 0.0f;
+    float y = __fdiv_rn(diff, sd);
+    y = y < q.lo ? q.lo : (y > q.hi ? q.hi : y);
+    return y > 0.0f;
+}
+
+// Vectorised variant (z % 4 == 0, z <= 256, d <= 32): one warp per slot, 128-bit loads (one quad of
+// 4 elements per lane and pass), sign nibbles OR-reduced inside groups of 8 lanes into element-ordered
+// 32-bit words, codes cut out of the bit string with a funnel shift + bit reversal.
+__global__ void __launch_bounds__(256) pack_codes_vec_kernel(
+    const float* __restrict__ tiles, const int32_t* __restrict__ order, const dcta_segment* __restrict__ segs,
+    const int32_t* __restrict__ row_seg_start, int n_rows, int s, int tw, int channels, int n_tok_img,
+    float inv_channels, float inv_tw, LfqNormParams q, int64_t* __restrict__ codes, int64_t* __restrict__ positions,
+    int64_t* __restrict__ channels_out, int64_t* __restrict__ image_ids, uint8_t* __restrict__ key_pad_mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = (int64_t)n_rows * s;
+    const int z4 = q.z >> 2;
+    const unsigned dmask = q.d == 32 ? 0xffffffffu : ((1u << q.d) - 1u);
+    for (int64_t slot = warp0; slot < total; slot += n_warps) {
+        const int row = (int)(slot / s);
+        const int off = (int)(slot - (int64_t)row * s);
+        int lo = row_seg_start[row], hi = row_seg_start[row + 1];
+        int seg = -1;
+        if (hi - lo == 1) {                       // the common case: one image per row
+            seg = (off >= segs[lo].offset && off < segs[lo].offset + segs[lo].k) ? lo : -1;
+        } else {
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const int so = segs[mid].offset;
+                if (off < so) hi = mid;
+                else if (off >= so + segs[mid].k) lo = mid + 1;
+                else { seg = mid; break; }
+            }
+        }
+        const float4* src = nullptr;
+        int ph = 0, pw = 0, pc = 0, image_id = 0;
+        if (seg >= 0) {
+            const dcta_segment sg = segs[seg];
+            const int tok = order[sg.img * n_tok_img + (off - sg.offset)];
+            src = reinterpret_cast<const float4*>(tiles + (sg.img * n_tok_img + tok) * q.z);
+            const int tile = (int)(((float)tok + 0.5f) * inv_channels);   // exact for tok < 2^22
+            pc = tok - tile * channels;
+            ph = (int)(((float)tile + 0.5f) * inv_tw);
+            pw = tile - ph * tw;
+            image_id = sg.image_id;
+        }
+        const int64_t pid = ((int64_t)pc * q.H + ph) * q.W + pw;
+        const float4* ms = reinterpret_cast<const float4*>(q.median + pid * q.z);
+        const float4* bs = reinterpret_cast<const float4*>(q.b + pid * q.z);
+        unsigned w[2];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int qd = lane + 32 * pass;
+            unsigned nib = 0;
+            if (qd < z4) {
+                const float4 xv = src ? __ldg(src + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 mv = __ldg(ms + qd);
+                const float4 bv = __ldg(bs + qd);
+                nib = norm_sign_bit(xv.x, mv.x, bv.x, q) | (norm_sign_bit(xv.y, mv.y, bv.y, q) << 1) |
+                      (norm_sign_bit(xv.z, mv.z, bv.z, q) << 2) | (norm_sign_bit(xv.w, mv.w, bv.w, q) << 3);
+            }
+            unsigned v = nib << (4 * (lane & 7));
+            v |= __shfl_xor_sync(0xffffffffu, v, 1);
+            v |= __shfl_xor_sync(0xffffffffu, v, 2);
+            v |= __shfl_xor_sync(0xffffffffu, v, 4);
+            w[pass] = v;        // lanes 8j .. 8j+7 hold elements 128*pass + 32*j .. +31 (bit = element & 31)
+        }
+        // lfq.py:187: code[cb] = bits [cb*d, cb*d + d) of the element-ordered string, first element = MSB
+        for (int cb0 = 0; cb0 < q.c; cb0 += 32) {
+            const int cb = min(cb0 + lane, q.c - 1);
+            const int e0 = cb * q.d;
+            const int k0 = e0 >> 5, k1 = min(k0 + 1, 7), sh = e0 & 31;
+            const unsigned a0 = __shfl_sync(0xffffffffu, w[0], 8 * (k0 & 3));
+            const unsigned a1 = __shfl_sync(0xffffffffu, w[1], 8 * (k0 & 3));
+            const unsigned b0 = __shfl_sync(0xffffffffu, w[0], 8 * (k1 & 3));
+            const unsigned b1 = __shfl_sync(0xffffffffu, w[1], 8 * (k1 & 3));
+            const unsigned wlo = (k0 >> 2) ? a1 : a0;
+            const unsigned whi = (k1 >> 2) ? b1 : b0;
+            const unsigned bits = __funnelshift_r(wlo, whi, sh) & dmask;      // LSB = first element
+            const unsigned code = __brev(bits) >> (32 - q.d);
+            if (cb0 + lane < q.c) codes[slot * q.c + cb] = (int64_t)code;
+        }
+        if (lane == 0) {
+            reinterpret_cast<longlong2*>(positions)[slot] = make_longlong2(ph, pw);
+            channels_out[slot] = pc;
+            if (image_ids) image_ids[slot] = image_id;
+            if (key_pad_mask) key_pad_mask[slot] = seg < 0;
+        }
+    }
+}
+
 __device__ __forceinline__ void split16f(float v, float scale, __half& h, __half& l) {
     const float s = v * scale;
     h = __float2half_rn(s);
@@ -209,6 +306,14 @@ extern "C" int dcta_pack_codes_lfq(const float* tiles, const int32_t* order, con
     if (rc) return rc;
     if (n_rows == 0) return DCTA_OK;
     LfqNormParams q{median, b, channels, H, W, z, eps, lo, hi, c, d, scale};
+    const bool aligned = ((reinterpret_cast<uintptr_t>(tiles) | reinterpret_cast<uintptr_t>(median) |
+                           reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(positions)) & 15) == 0;
+    if (z % 4 == 0 && d <= 32 && aligned && th * tw * channels < (1 << 22)) {
+        pack_codes_vec_kernel<<<grid_for((int64_t)n_rows * s, 8), 256, 0, as_stream(stream)>>>(
+            tiles, order, segs, row_seg_start, n_rows, s, tw, channels, th * tw * channels, 1.0f / (float)channels,
+            1.0f / (float)tw, q, codes, positions, channels_out, image_ids, key_pad_mask);
+        return check_launch("pack_codes_lfq");
+    }
     pack_codes_kernel<<<grid_for((int64_t)n_rows * s, 8), 256, 0, as_stream(stream)>>>(
         tiles, order, segs, row_seg_start, n_rows, s, tw, channels, th * tw * channels, q, codes, positions,
         channels_out, image_ids, key_pad_mask);

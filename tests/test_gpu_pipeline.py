@@ -78,9 +78,14 @@ def test_odd_sizes_fall_back_to_exact_fp32_forward(D):
     assert np.abs(b1.patches[0, : it["patches"].shape[0]].cpu().numpy() - it["patches"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("beta,max_seq_len,size", [(0.0, 3072, (256, 256)), (0.0, 972, (256, 256)),
-                                                   (0.01, 512, (128, 160)), (0.0, 200, (128, 160))])
-def test_fused_roundtrip_is_bit_identical_to_staged(D, beta, max_seq_len, size):
+@pytest.mark.parametrize("beta,max_seq_len,size,patch,cb", [
+    (0.0, 3072, (256, 256), 14, (14, 14)), (0.0, 972, (256, 256), 14, (14, 14)),
+    (0.01, 512, (128, 160), 14, (14, 14)), (0.0, 200, (128, 160), 14, (14, 14)),
+    (0.0, 3072, (128, 128), 4, (4, 4)),        # vector kernel, several codebooks per 32-bit word
+    (0.02, 300, (96, 120), 4, (2, 8)),         # codebook != patch row
+    (0.0, 3072, (96, 96), 3, (3, 3)),          # z % 4 != 0: scalar kernel
+])
+def test_fused_roundtrip_is_bit_identical_to_staged(D, beta, max_seq_len, size, patch, cb):
     """encode_codes / decode_codes (PatchNorm + LFQ inside the pack / un-patchify kernels) give the
     same codes, metadata and images, bit for bit, as the module-by-module path -- including padding
     slots, several images per row, top-k cuts and variable k."""
@@ -88,9 +93,9 @@ def test_fused_roundtrip_is_bit_identical_to_staged(D, beta, max_seq_len, size):
     torch.manual_seed(4)
     h, w = size
     x = torch.rand(9, 3, h, w).cuda()
-    fe = D.DCTAutoencoderFeatureExtractor(3, 14, beta, 32, 32, max_seq_len)
-    pn = D.PatchNorm(32, 32, 14, 3).cuda()
-    lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).cuda().eval()
+    fe = D.DCTAutoencoderFeatureExtractor(3, patch, beta, 32, 32, max_seq_len)
+    pn = D.PatchNorm(32, 32, patch, 3).cuda()
+    lfq = D.LFQ(codebook_size=2 ** cb[1], num_codebooks=cb[0]).cuda().eval()
     pipe = D.TransformPipeline(fe, pn, lfq)
     random.seed(3)
     pipe.fit_norm(torch.rand(8, 3, h, w).cuda())
@@ -116,5 +121,5 @@ def test_fused_roundtrip_is_bit_identical_to_staged(D, beta, max_seq_len, size):
     b2.patches = pn.inverse_norm(b2)
     assert torch.equal(fe.postprocess_batch(b2), rec_f)
     # not fusable -> staged path is used transparently
-    lfq2 = D.LFQ(dim=196, codebook_size=8192, num_codebooks=16).cuda().eval()
+    lfq2 = D.LFQ(dim=patch * patch, codebook_size=8192, num_codebooks=16).cuda().eval()
     assert not D.TransformPipeline(fe, pn, lfq2).fusable()
