@@ -32,12 +32,14 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
 static_assert(TM * EPI_PITCH * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the ring");
 
 struct EpiArgs {
-    int mode;                 // 0: fp32 planes, 1: fp16 hi/lo planes, 2: fp32 token grid
+    int mode;                 // 0: fp32 planes, 1: fp16 hi/lo planes, 2: fp32 token grid, 3: arg-min partials,
+                              // 4: fp16 hi/lo planes written TRANSPOSED, out[b][n*ld + m] (persistent kernel)
     float* out_f32;
     __half* out_hi;
     __half* out_lo;
     int64_t ld, batch_stride; // element pitch / per-batch stride of the plane outputs
     const float* row_scale;   // optional per-row (m) factor
+    const float* col_scale;   // optional per-column (n) factor (persistent kernel)
     float alpha;              // global factor
     const float* alpha_dev;   // optional device scalar multiplied into alpha (scale chosen on the device)
     const float* col_bias;    // mode 3: per-column (n) additive term, e.g. |e_j|^2
@@ -345,7 +347,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // rows x k fp16 matrix with pitch `ld` elements, `batch` of them `batch_stride` elements apart
-static int make_map(CUtensorMap* map, const void* ptr, int rows, int k, int64_t ld, int64_t batch, int64_t batch_stride) {
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int k, int64_t ld, int64_t batch, int64_t batch_stride,
+                    int box_rows = TM) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return DCTA_ERR_UNSUPPORTED; }
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) || (batch > 1 && batch_stride % 8)) {
@@ -354,7 +357,7 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int k, int64_t 
     }
     cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? batch_stride : (int64_t)rows * ld) * 2};
-    cuuint32_t box[3] = {TK, TM, 1};
+    cuuint32_t box[3] = {TK, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -385,6 +388,289 @@ static int launch_gemm_split(const Operand& A, const Operand& B, int K, int64_t 
     gemm_split_kernel<<<grid, 128, SMEM_BYTES, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, A.batch_stride != 0,
                                                                       B.batch_stride != 0, (int)ceil_div(K, TK), ep);
     return check_launch("gemm_split");
+}
+
+// ------------------------------------------------------------------------------ persistent kernel
+// Same arithmetic, fewer L2 bytes per flop: 128 x TNP output tiles (TNP = 256, or 224 so that N = 448
+// tiles exactly), one persistent CTA per SM walking a static tile schedule, and the 512 TMEM columns
+// split into two accumulators so that the epilogue of tile i overlaps the main loop of tile i+1.
+//   warp 0 / one lane : TMA producer (ring of PSTAGES stages: A 128x32 hi/lo + B TNPx32 hi/lo)
+//   warp 1 / one lane : tcgen05.mma issuer (M=128, N=TNP), commits free ring stages and publish accumulators
+//   warps 2..5        : epilogue (TMEM lane quarter = warp & 3); accumulator handed back as soon as it has
+//                       been read out, stores proceed from registers / the per-warp staging slice
+constexpr int PSTAGES = 3;
+constexpr int P_EPI_BYTES = TM * EPI_PITCH * 4;          // 128 x 132 fp32 staging (one 128-column half)
+
+template <int TNP>
+struct PCfg {
+    static constexpr int kBTile = TNP * TK * 2;                     // one B operand tile (hi or lo)
+    static constexpr int kStage = 2 * TILE_BYTES + 2 * kBTile;      // A_hi, A_lo, B_hi, B_lo
+    static constexpr int kSmem = PSTAGES * kStage + P_EPI_BYTES + 1024;
+    static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TNP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+};
+
+template <int TNP>
+__global__ void __launch_bounds__(192, 1)
+gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                             const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                             int a_batched, int b_batched, int num_k_blocks, int tiles_m, int tiles_n, int n_batch,
+                             EpiArgs ep) {
+    using Cfg = PCfg<TNP>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[PSTAGES];
+    __shared__ __align__(8) uint64_t empty_bar[PSTAGES];
+    __shared__ __align__(8) uint64_t tmem_full[2];
+    __shared__ __align__(8) uint64_t tmem_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n_tiles = (int64_t)tiles_m * tiles_n * n_batch;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < PSTAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);     // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(&tmem_base_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int tn = (int)(tile % tiles_n);
+            const int64_t r = tile / tiles_n;
+            const int tm = (int)(r % tiles_m);
+            const int batch = (int)(r / tiles_m);
+            const int ab = a_batched ? batch : 0, bb = b_batched ? batch : 0;
+            for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                const int s = it % PSTAGES;
+                mbar_wait(&empty_bar[s], ((it / PSTAGES) & 1) ^ 1);
+                uint8_t* st = smem + s * Cfg::kStage;
+                mbar_expect_tx(&full_bar[s], Cfg::kStage);
+                tma_load_3d(&map_a_hi, &full_bar[s], st, kb * TK, tm * TM, ab);
+                tma_load_3d(&map_a_lo, &full_bar[s], st + TILE_BYTES, kb * TK, tm * TM, ab);
+                tma_load_3d(&map_b_hi, &full_bar[s], st + 2 * TILE_BYTES, kb * TK, tn * TNP, bb);
+                tma_load_3d(&map_b_lo, &full_bar[s], st + 2 * TILE_BYTES + Cfg::kBTile, kb * TK, tn * TNP, bb);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer
+        uint32_t it = 0, tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const int acc = tcount & 1;
+            mbar_wait(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc * 256;
+            for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                const int s = it % PSTAGES;
+                mbar_wait(&full_bar[s], (it / PSTAGES) & 1);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + s * Cfg::kStage);
+#pragma unroll
+                for (int k = 0; k < TK / 16; ++k) {
+                    const uint32_t ko = k * 32;
+                    const uint64_t a_hi = smem_desc_sw64(base + ko);
+                    const uint64_t a_lo = smem_desc_sw64(base + TILE_BYTES + ko);
+                    const uint64_t b_hi = smem_desc_sw64(base + 2 * TILE_BYTES + ko);
+                    const uint64_t b_lo = smem_desc_sw64(base + 2 * TILE_BYTES + Cfg::kBTile + ko);
+                    umma_f16(tmem_acc, a_lo, b_hi, Cfg::kIdesc, (kb | k) ? 1u : 0u);
+                    umma_f16(tmem_acc, a_hi, b_lo, Cfg::kIdesc, 1u);
+                    umma_f16(tmem_acc, a_hi, b_hi, Cfg::kIdesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full[acc]);
+        }
+    } else if (warp >= 2) {
+        // ---------------- epilogue warps
+        const int quarter = warp & 3;                     // TMEM lanes 32*quarter .. +31
+        const uint32_t stage = smem_u32(smem + PSTAGES * Cfg::kStage) + (uint32_t)(quarter * 32 * EPI_PITCH) * 4;
+        const int p = ep.tile_p, zz = p * p;
+        const bool pair_ok = (p % 2 == 0);
+        const float alpha = ep.alpha * (ep.alpha_dev ? __ldg(ep.alpha_dev) : 1.0f);
+        uint32_t tcount = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const int tn = (int)(tile % tiles_n);
+            const int64_t r = tile / tiles_n;
+            const int tm = (int)(r % tiles_m);
+            const int batch = (int)(r / tiles_m);
+            const int acc = tcount & 1;
+            const int m0 = tm * TM, n0 = tn * TNP;
+            const int gm = m0 + quarter * 32 + lane;                  // this thread's accumulator row
+            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
+            float rs = alpha;
+            if (ep.row_scale != nullptr && gm < ep.M) rs *= __ldg(ep.row_scale + gm);
+            const float dcv = ep.dc_mode ? __ldg(ep.dc + batch) : 0.0f;
+
+            if (ep.mode == 4) {
+                // transposed hi/lo store straight from registers: out[b][n * ld + m]; for a fixed column
+                // the 32 lanes of the warp hold 32 consecutive m -> one 64-byte store per plane
+                const int64_t obase = (int64_t)batch * ep.batch_stride + gm;
+#pragma unroll 1
+                for (int c = 0; c < TNP / 32; ++c) {
+                    uint32_t rr[32];
+                    tmem_ld32(tmem_acc + c * 32, rr);
+                    if (c == TNP / 32 - 1) {          // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + c * 32 + j;
+                        if (n < ep.N && gm < ep.M) {
+                            float v = __uint_as_float(rr[j]) * rs;
+                            if (ep.col_scale) v *= __ldg(ep.col_scale + n);
+                            const __half h = __float2half_rn(v);
+                            const __half l = __float2half_rn(v - __half2float(h));
+                            ep.out_hi[obase + (int64_t)n * ep.ld] = h;
+                            ep.out_lo[obase + (int64_t)n * ep.ld] = l;
+                        }
+                    }
+                }
+                continue;
+            }
+
+            // staged modes: two column halves of <= 128 through this warp's 32 x 132 staging slice
+#pragma unroll 1
+            for (int half = 0; half < (TNP + 127) / 128; ++half) {
+                const int cbeg = half * 128;
+                const int ccnt = (TNP - cbeg) < 128 ? (TNP - cbeg) : 128;      // 128 or 96
+                for (int c = 0; c < ccnt / 32; ++c) {
+                    uint32_t rr[32];
+                    tmem_ld32(tmem_acc + cbeg + c * 32, rr);
+                    const uint32_t dst = stage + (uint32_t)(lane * EPI_PITCH + c * 32) * 4;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + j * 4),
+                                     "f"(__uint_as_float(rr[j]) * rs), "f"(__uint_as_float(rr[j + 1]) * rs),
+                                     "f"(__uint_as_float(rr[j + 2]) * rs), "f"(__uint_as_float(rr[j + 3]) * rs) : "memory");
+                }
+                if (cbeg + ccnt >= TNP) {             // last half read: hand the accumulator back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
+                }
+                __syncwarp();
+                const int n = n0 + cbeg + lane * 4;
+                const int n_valid = (lane * 4 < ccnt) ? ep.N - n : 0;
+                int64_t col_off[4] = {0, 0, 0, 0};
+                int64_t plane_off;
+                if (ep.mode == 2) {
+                    const int64_t img = batch / ep.channels;
+                    const int ch = batch - (int)img * ep.channels;
+                    plane_off = (img * ep.tiles_h * ep.tiles_w * ep.channels + ch) * (int64_t)zz;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int tw = (n + j) / p;
+                        col_off[j] = (int64_t)tw * ep.channels * zz + ((n + j) - tw * p);
+                    }
+                } else {
+                    plane_off = (int64_t)batch * ep.batch_stride + n;
+                }
+                for (int rr_ = 0; rr_ < 32; ++rr_) {
+                    const int m = m0 + quarter * 32 + rr_;
+                    if (m >= ep.M) break;
+                    if (n_valid <= 0) continue;
+                    float4 v;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                 : "r"(stage + (uint32_t)(rr_ * EPI_PITCH + lane * 4) * 4));
+                    if (ep.dc_mode == 2) { v.x += dcv; v.y += dcv; v.z += dcv; v.w += dcv; }
+                    else if (ep.dc_mode == 1 && m == 0 && n == 0) v.x += dcv;
+                    if (ep.mode == 0) {
+                        float* dst = ep.out_f32 + plane_off + (int64_t)m * ep.ld;
+                        if (n_valid >= 4 && (ep.ld & 3) == 0) {
+                            *reinterpret_cast<float4*>(dst) = v;
+                        } else {
+                            const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (j < n_valid) dst[j] = a[j];
+                        }
+                    } else if (ep.mode == 1) {
+                        const float a[4] = {v.x, v.y, v.z, v.w};
+                        __half h[4], l[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            h[j] = __float2half_rn(a[j]);
+                            l[j] = __float2half_rn(a[j] - __half2float(h[j]));
+                        }
+                        const int64_t o = plane_off + (int64_t)m * ep.ld;
+                        if (n_valid >= 4) {
+                            *reinterpret_cast<uint2*>(ep.out_hi + o) = *reinterpret_cast<const uint2*>(h);
+                            *reinterpret_cast<uint2*>(ep.out_lo + o) = *reinterpret_cast<const uint2*>(l);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (j < n_valid) { ep.out_hi[o + j] = h[j]; ep.out_lo[o + j] = l[j]; }
+                        }
+                    } else {
+                        const int th = m / p, pi = m - th * p;
+                        float* dst = ep.out_f32 + plane_off + (int64_t)th * ep.tiles_w * ep.channels * zz + pi * p;
+                        if (pair_ok && n_valid >= 4) {
+                            *reinterpret_cast<float2*>(dst + col_off[0]) = make_float2(v.x, v.y);
+                            *reinterpret_cast<float2*>(dst + col_off[2]) = make_float2(v.z, v.w);
+                        } else {
+                            const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (j < n_valid) dst[col_off[j]] = a[j];
+                        }
+                    }
+                }
+                __syncwarp();                         // staging slice is reused by the next half / tile
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int TNP>
+static int launch_gemm_persistent(const Operand& A, const Operand& B, int K, int64_t batch, const EpiArgs& ep, void* stream) {
+    if (batch == 0 || ep.M == 0 || ep.N == 0) return DCTA_OK;
+    if (batch >= (1ll << 31)) { set_error("gemm_split: too many batch items"); return DCTA_ERR_UNSUPPORTED; }
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    const int64_t ab = A.batch_stride ? batch : 1, bb = B.batch_stride ? batch : 1;
+    if ((rc = make_map(&ma_hi, A.hi, A.rows, K, A.ld, ab, A.batch_stride, TM))) return rc;
+    if ((rc = make_map(&ma_lo, A.lo, A.rows, K, A.ld, ab, A.batch_stride, TM))) return rc;
+    if ((rc = make_map(&mb_hi, B.hi, B.rows, K, B.ld, bb, B.batch_stride, TNP))) return rc;
+    if ((rc = make_map(&mb_lo, B.lo, B.rows, K, B.ld, bb, B.batch_stride, TNP))) return rc;
+    cudaFuncSetAttribute(gemm_split_persistent_kernel<TNP>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<TNP>::kSmem);
+    const int tiles_m = (int)ceil_div(ep.M, TM), tiles_n = (int)ceil_div(ep.N, TNP);
+    const int64_t n_tiles = (int64_t)tiles_m * tiles_n * batch;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    gemm_split_persistent_kernel<TNP><<<grid, 192, PCfg<TNP>::kSmem, as_stream(stream)>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, A.batch_stride != 0, B.batch_stride != 0, (int)ceil_div(K, TK), tiles_m, tiles_n,
+        (int)batch, ep);
+    return check_launch("gemm_split_persistent");
+}
+
+// pick the N tile that wastes the least (224 tiles N = 448 exactly, 256 tiles N = 512 exactly)
+static int launch_gemm_auto(const Operand& A, const Operand& B, int K, int64_t batch, const EpiArgs& ep, void* stream) {
+    const int64_t w256 = ceil_div(ep.N, 256) * 256, w224 = ceil_div(ep.N, 224) * 224;
+    if (w224 < w256) return launch_gemm_persistent<224>(A, B, K, batch, ep, stream);
+    return launch_gemm_persistent<256>(A, B, K, batch, ep, stream);
 }
 
 // ------------------------------------------------------------------------------ split producers
@@ -718,14 +1004,15 @@ extern "C" int dcta_dct2_fwd_tc(const void* x_hi, const void* x_lo, const float*
     if (tile_p > 0)
         DCTA_REQUIRE(channels > 0 && kh % tile_p == 0 && kw % tile_p == 0 && n_planes % channels == 0,
                      "dct2_fwd_tc: kh/kw must be multiples of the patch size");
-    // pass 1: P^T[kw, h] = sum_w CW'[kw,w] * X'[h,w]  -> hi/lo planes (kw x ld_h), scale 2^6
-    Operand A1{(const __half*)bw_hi, (const __half*)bw_lo, kw, w, 0};
-    Operand B1{(const __half*)x_hi, (const __half*)x_lo, h, w, (int64_t)h * w};
+    // pass 1: P[h, kw] = sum_w X'[h,w] * CW'[kw,w], written TRANSPOSED as hi/lo planes P^T (kw x ld_h), scale 2^6
+    //         (M = h and N = kw tile without waste: 512 = 4 x 128, 448 = 2 x 224)
+    Operand A1{(const __half*)x_hi, (const __half*)x_lo, h, w, (int64_t)h * w};
+    Operand B1{(const __half*)bw_hi, (const __half*)bw_lo, kw, w, 0};
     EpiArgs e1{};
-    e1.mode = 1; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
+    e1.mode = 4; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
     e1.ld = ld_h; e1.batch_stride = (int64_t)kw * ld_h;
-    e1.row_scale = rs_w; e1.alpha = kScaleP / kScaleX; e1.M = kw; e1.N = h;
-    int rc = launch_gemm_split(A1, B1, w, n_planes, e1, stream);
+    e1.col_scale = rs_w; e1.alpha = kScaleP / kScaleX; e1.M = h; e1.N = kw;
+    int rc = launch_gemm_auto(A1, B1, w, n_planes, e1, stream);
     if (rc) return rc;
     // pass 2: Y[kh, kw] = sum_h CH'[kh,h] * P'^T[kw,h]   (+ the removed constant's DC at [0,0])
     Operand A2{(const __half*)bh_hi, (const __half*)bh_lo, kh, ld_h, 0};
@@ -738,7 +1025,7 @@ extern "C" int dcta_dct2_fwd_tc(const void* x_hi, const void* x_lo, const float*
     } else {
         e2.mode = 0; e2.ld = kw; e2.batch_stride = (int64_t)kh * kw;
     }
-    return launch_gemm_split(A2, B2, h, n_planes, e2, stream);
+    return launch_gemm_auto(A2, B2, h, n_planes, e2, stream);
 }
 
 // inverse: y planes (n_planes, kh, ld_kw) hi/lo (scale 2^4, DC removed into dc[]) -> x (n_planes, h, w) fp32
@@ -758,7 +1045,7 @@ extern "C" int dcta_dct2_inv_tc(const void* y_hi, const void* y_lo, const float*
     e1.mode = 1; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
     e1.ld = ld_kh; e1.batch_stride = (int64_t)w * ld_kh;
     e1.alpha = kScaleQ / (kScaleBasis * kScaleY); e1.M = w; e1.N = kh;
-    int rc = launch_gemm_split(A1, B1, kw, n_planes, e1, stream);
+    int rc = launch_gemm_auto(A1, B1, kw, n_planes, e1, stream);
     if (rc) return rc;
     // pass 2: X[h, w] = sum_kh CH'^T[h,kh] * Q'^T[w,kh]   (+ the DC coefficient's constant everywhere)
     Operand A2{(const __half*)bht_hi, (const __half*)bht_lo, h, ld_kh, 0};
@@ -767,7 +1054,7 @@ extern "C" int dcta_dct2_inv_tc(const void* y_hi, const void* y_lo, const float*
     e2.mode = 0; e2.out_f32 = x; e2.ld = w; e2.batch_stride = (int64_t)h * w;
     e2.alpha = 1.0f / (kScaleBasis * kScaleQ); e2.M = h; e2.N = w;
     e2.dc = dc; e2.dc_mode = dc ? 2 : 0;
-    return launch_gemm_split(A2, B2, kh, n_planes, e2, stream);
+    return launch_gemm_auto(A2, B2, kh, n_planes, e2, stream);
 }
 
 // fp32 coefficient planes (n_planes, kh, kw) -> split planes (n_planes, kh, ld_kw) with the DC moved to dc[]
