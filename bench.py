@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--chunk", type=int, default=32, help="images per chunk of the host streaming round trip")
     ap.add_argument("--cpu-sample", type=int, default=0, help="images in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dct-impl", default="tc", choices=["tc", "fp32"],
+    ap.add_argument("--dct-impl", default="tc", choices=["tc", "tc_plain", "fp32"],
                     help="tc = tcgen05 split-precision GEMMs (default), fp32 = exact FFMA GEMMs")
     return ap.parse_args()
 
@@ -275,7 +275,7 @@ def run_ours(a):
 
     # ---- per-stage device times (CUDA events around each public call) for the roofline object
     stages = stage_times(torch, D, pipe, x, dev, reps=3)
-    K = 448
+    K = min(S // 14, 32) * 14
     flops_fwd = 3 * 2 * S * K * (S + K) * B          # C*2*H*K*(W+K) per image
     dct_ms = stages["dct_fwd"]
     achieved = flops_fwd / (dct_ms / 1e3) / 1e12
@@ -286,7 +286,11 @@ def run_ours(a):
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
-    if fe.dct_impl == "tc":
+    if fe.dct_impl == "tc" and D.util.fold_ok(S, S, K, K):
+        kname = "fold_gemm_kernel (forward DCT: 2 launches, cta_group::2 tcgen05 fp16x3 split precision, folded basis)"
+        note = ("algorithmic flops 3*2*H*K*(W+K) per image (SURVEY 8d, plain basis GEMMs); the folded kernel executes "
+                "1/2 of them, each as 3 tensor MMAs (hi*hi + hi*lo + lo*hi), so frac <= 2/3 by construction")
+    elif fe.dct_impl in ("tc", "tc_plain"):
         kname = "gemm_split_kernel (forward DCT: 2 launches, tcgen05 fp16x3 split precision)"
         note = ("algorithmic flops 3*2*H*K*(W+K) per image; the kernel executes 3x that many tensor flops "
                 "(hi*hi + hi*lo + lo*hi), so frac <= 1/3 by construction")
@@ -352,14 +356,22 @@ def stage_times(torch, D, pipe, x, dev, reps=3):
     from dct_autoencoder_b200 import _lib
     U = D.util
     H, W = x.shape[-2:]
-    tc = fe.dct_impl == "tc"
-    if tc:
+    p = fe.patch_size
+    _, _, th, tw = fe._geometry(H, W)
+    KH, KW = th * p, tw * p
+    fold = fe.dct_impl == "tc" and U.fold_ok(H, W, KH, KW)
+    tc = fe.dct_impl in ("tc", "tc_plain") and not fold
+    if fold:
+        hi, lo, dc = t("rgb_to_ipt_fold", lambda: U.rgb_to_ipt_fold(x))
+        tiles = t("dct_fwd", lambda: U.dct2_fwd_fold(hi, lo, dc, KH, KW, tile_p=p, channels=3))
+        del hi, lo
+    elif tc:
         hi, lo, dc = t("rgb_to_ipt_split", lambda: U.rgb_to_ipt_split(x))
-        tiles = t("dct_fwd", lambda: U.dct2_fwd_tc(hi, lo, dc, 448, 448, tile_p=14, channels=3))
+        tiles = t("dct_fwd", lambda: U.dct2_fwd_tc(hi, lo, dc, KH, KW, tile_p=p, channels=3))
         del hi, lo
     else:
         ipt = t("rgb_to_ipt", lambda: U.rgb_to_ipt(x))
-        tiles = t("dct_fwd", lambda: U.dct2_truncated(ipt, 448, 448, tile_p=14, channels=3))
+        tiles = t("dct_fwd", lambda: U.dct2_truncated(ipt, KH, KW, tile_p=p, channels=3))
         del ipt
     t("score_sort", lambda: fe._sorted_order(tiles))
     del tiles
@@ -371,21 +383,32 @@ def stage_times(torch, D, pipe, x, dev, reps=3):
     inv = t("patchnorm_inv", lambda: pn.inverse_norm(b2))
     b2.patches = inv
     n = len(b2.patch_sizes)
-    slot_map, _ = t("slot_map", lambda: fe._slot_map(b2, 32, 32))
+    slot_map, _ = t("slot_map", lambda: fe._slot_map(b2, th, tw))
     st = _lib.stream_ptr(dev)
-    if tc:
-        y_hi = torch.empty((n, 3, 448, 448), dtype=torch.float16, device=dev)
+    ipt2 = None
+    if fold:
+        y_hi = torch.empty((2, 2, n * 3, KH // 2, U._round8(KW // 2)), dtype=torch.float16, device=dev)
         y_lo = torch.empty_like(y_hi)
         dc2 = torch.empty(n * 3, dtype=torch.float32, device=dev)
-        t("unpatchify", lambda: _lib.call("dcta_unpatchify_split", _lib.ptr(inv), _lib.ptr(slot_map), None, n, 3, 32, 32,
-                                          14, 448, 448, 448, H, W, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc2), st))
-        ipt2 = t("dct_inv", lambda: U.dct2_inv_tc(y_hi, y_lo, dc2, 448, H, W))
+        t("unpatchify", lambda: _lib.call("dcta_unpatchify_fold", _lib.ptr(inv), _lib.ptr(slot_map), None, n, 3, th, tw,
+                                          p, KH, KW, H, W, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc2), st))
+        zq = t("dct_inv", lambda: U.dct2_inv_fold(y_hi, y_lo, KH, KW, H, W))
+        t("unfold_ipt_to_rgb", lambda: U.unfold_ipt_to_rgb(zq, dc2, H, W))
+        del zq
+    elif tc:
+        y_hi = torch.empty((n, 3, KH, U._round8(KW)), dtype=torch.float16, device=dev)
+        y_lo = torch.empty_like(y_hi)
+        dc2 = torch.empty(n * 3, dtype=torch.float32, device=dev)
+        t("unpatchify", lambda: _lib.call("dcta_unpatchify_split", _lib.ptr(inv), _lib.ptr(slot_map), None, n, 3, th, tw,
+                                          p, KH, KW, U._round8(KW), H, W, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc2), st))
+        ipt2 = t("dct_inv", lambda: U.dct2_inv_tc(y_hi, y_lo, dc2, KW, H, W))
     else:
-        planes = torch.empty((n, 3, 448, 448), dtype=torch.float32, device=dev)
-        t("unpatchify", lambda: _lib.call("dcta_unpatchify", _lib.ptr(inv), _lib.ptr(slot_map), None, n, 3, 32, 32, 14,
-                                          448, 448, _lib.ptr(planes), st))
+        planes = torch.empty((n, 3, KH, KW), dtype=torch.float32, device=dev)
+        t("unpatchify", lambda: _lib.call("dcta_unpatchify", _lib.ptr(inv), _lib.ptr(slot_map), None, n, 3, th, tw, p,
+                                          KH, KW, _lib.ptr(planes), st))
         ipt2 = t("dct_inv", lambda: U.idct2_truncated(planes, H, W))
-    t("ipt_to_rgb", lambda: U.ipt_to_rgb(ipt2))
+    if ipt2 is not None:
+        t("ipt_to_rgb", lambda: U.ipt_to_rgb(ipt2))
     if pipe.fusable():
         del ipt2, inv, q, normed
         fb, fcodes = t("fused:encode_codes(total)", lambda: pipe.encode_codes(x))

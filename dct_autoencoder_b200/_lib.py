@@ -43,6 +43,17 @@ SIGNATURES = {
     "dcta_dct2_fwd_tc": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int64, c_int,
                          c_int, P],
     "dcta_dct2_inv_tc": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int64, c_int64, P],
+    "dcta_fold_supported": [c_int, c_int, c_int, c_int],
+    "dcta_rgb_to_ipt_fold": [P, P, P, P, P, c_int64, c_int, c_int, P, P, P],
+    "dcta_fold_planes": [P, P, P, P, P, c_int64, c_int, c_int, P],
+    "dcta_dct2_fwd_fold": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "dcta_unpatchify_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
+    "dcta_decode_codes_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                               P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P],
+    "dcta_fold_coef_planes": [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
+    "dcta_dct2_inv_fold": [P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
+    "dcta_unfold_ipt_to_rgb": [P, P, P, c_int64, c_int, c_int, P, P, P],
+    "dcta_unfold_planes": [P, P, P, c_int64, c_int, c_int, P],
     "dcta_patchify": [P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "dcta_tile_scores": [P, P, c_int64, c_int, c_int, c_int, c_int, c_float, P, P],
     "dcta_sort_tokens": [P, P, c_int64, c_int, P],
@@ -89,6 +100,9 @@ KERNELS_PER_CALL = {
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,
     "dcta_row_sumsq": 1, "dcta_split_rows": 1, "dcta_vq_nearest_tc": 2,
     "dcta_pack_codes_lfq": 1, "dcta_decode_codes_split": 1,
+    "dcta_fold_supported": 0, "dcta_rgb_to_ipt_fold": 3, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
+    "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 1, "dcta_fold_coef_planes": 1, "dcta_dct2_inv_fold": 2,
+    "dcta_unfold_ipt_to_rgb": 1, "dcta_unfold_planes": 1,
 }
 launch_count = 0
 

@@ -1,0 +1,868 @@
+// Folded 2-D DCT / IDCT on tensor cores (sm_100a): half the multiply-adds of the plain basis GEMMs.
+//
+// The DCT-II basis is (anti)symmetric about the centre of the signal, C[k, N-1-n] = (-1)^k C[k, n], so
+//   Y[2j]   = sum_{n < N/2} C[2j,   n] (x[n] + x[N-1-n])        Y[2j+1] = sum_{n < N/2} C[2j+1, n] (x[n] - x[N-1-n])
+// and the 2-D transform of an H x W plane splits into four independent "quadrant" transforms of
+// H/2 x W/2 inputs (row parity a of the coefficient, column parity b):
+//   Y[2i+a, 2j+b] = sum_{h', w'} CH[2i+a, h'] Xq[b][a][h', w'] CW[2j+b, w']
+// with Xq the four sign combinations of the mirrored pixels.  The inverse runs the same four transforms
+// backwards and a final butterfly restores the mirrored pixels.  Reference: util.py:333-338 (dct2 / idct2),
+// feature_extraction_dct_autoencoder.py:140, :149, :300-304, :360, :393.
+//
+// All four GEMM passes have the form  D[r, n] = sum_k Data[r, k] * Basis_g[n, k]  where the data rows of
+// many planes are stacked (M tiles of 128 rows never waste lanes), the basis of a parity group g is tiny
+// and every output element is written TRANSPOSED (the lanes of a warp hold consecutive r, so a store of
+// one column n is one contiguous segment) -- exactly the K-major layout the next pass reads.
+//
+// Kernel: persistent CTA PAIRS (cta_group::2, M = 256 per tcgen05.mma).
+//   * the basis slice (group, N tile) of a pair is loaded ONCE and stays in shared memory, split across the
+//     two CTAs (N/2 rows each): L2 -> SM traffic is the data operand only;
+//   * warp 0: TMA producer (ring of 16 KB stages: this CTA's 128 x 32 fp16 hi and lo tiles),
+//     warp 1 of the leader CTA: tcgen05.mma issuer (3 MMAs per 16-wide k step: lo*hi, hi*lo, hi*hi),
+//     warps 2..9: epilogue, two warps per TMEM lane quarter; the 512 TMEM columns hold two accumulators
+//     so the epilogue of one tile overlaps the main loop of the next.
+#include "lfq_norm.cuh"
+#include "tc_ptx.cuh"
+
+namespace dcta {
+
+constexpr int FK = 32;                    // k block: 32 fp16 = 64-byte rows (SWIZZLE_64B)
+constexpr int F_ATILE = 128 * FK * 2;     // one 128-row operand tile (hi or lo): 8 KB
+constexpr int F_STAGE = 2 * F_ATILE;      // a ring stage: this CTA's A_hi, A_lo
+constexpr int F_THREADS = 320;
+constexpr int F_MAX_STAGES = 8;
+constexpr int F_SMEM_LIMIT = 227 * 1024 - 4096;   // dynamic shared memory we allow ourselves (static: ~2.3 KB)
+
+struct FoldGemm {
+    int n_seg;            // data segments (3rd tensor-map coordinate); basis group of a segment = seg & 1
+    int rows_per_seg;     // stacked data rows in every segment
+    int tiles_per_seg;    // pair tiles (256 rows) per segment
+    int num_kb;           // ceil(K / 32)
+    int n_tile;           // MMA N: basis rows of one slice (multiple of 16, <= 256)
+    int n_ntiles;         // slices per group
+    int n_valid;          // basis rows of a group that exist
+    int stages;
+    uint32_t basis_bytes; // one CTA's resident basis plane (hi or lo): num_kb * (n_tile/2) * 64
+};
+
+struct FoldEpi {
+    int mode;                    // 0: fp16 hi/lo, 1: fp32, 2: fp32 token grid (forward pass 2)
+    __half* out_hi;
+    __half* out_lo;
+    float* out_f32;
+    int rows_per_item;           // stacked rows of one batch item; the row inside the item has output stride 1
+    int64_t seg_stride;          // output elements between segments
+    int64_t item_stride;         // output elements between items
+    int col_mul, col_add;        // output line of basis row n of group g: n * col_mul + g * col_add
+    int col_stride;              // output elements between lines
+    float alpha;
+    const float* basis_scale;    // optional (2, n_valid) per-basis-row factors
+    const float* dc;             // optional per-item constant added to (group 0, basis row 0, row-in-item 0)
+    int p, channels, tiles_h, tiles_w;   // mode 2
+};
+
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 256 (pair), N = n_tile
+__device__ __forceinline__ uint32_t fold_idesc(int n_tile) {
+    return (1u << 4) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int MODE>   // 0: fp16 hi/lo output, 1: fp32 output (plain or token grid)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
+fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 FoldGemm g, FoldEpi ep) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[F_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[F_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full[2];
+    __shared__ __align__(8) uint64_t tmem_empty[2];
+    __shared__ __align__(8) uint64_t basis_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) int32_t col_off[256];
+    __shared__ __align__(16) float col_scale[256];
+
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* basis_hi = smem;
+    uint8_t* basis_lo = smem + g.basis_bytes;
+    uint8_t* ring = smem + 2 * g.basis_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_slices = 2 * g.n_ntiles;
+    const int slice = pair % n_slices;
+    const int grp = slice & 1, nt = slice >> 1;
+    const int pair_in_slice = pair / n_slices, pairs_per_slice = n_pairs / n_slices;
+    const int n_work = (g.n_seg >> 1) * g.tiles_per_seg;        // work items of this slice
+    const int n_lim = min(g.n_tile, g.n_valid - nt * g.n_tile);  // valid columns of this slice
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < F_MAX_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 16);    // 8 epilogue warps in each CTA of the pair
+        }
+        mbar_init(&basis_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // per-slice output tables: where basis row n goes and what it is multiplied by
+    for (int n = threadIdx.x; n < 256; n += blockDim.x) {
+        int32_t off = -1;
+        float sc = 0.f;
+        if (n < n_lim) {
+            const int ng = nt * g.n_tile + n;
+            const int line = ng * ep.col_mul + grp * ep.col_add;
+            if (ep.mode == 2) {
+                const int th = line / ep.p, pi = line - th * ep.p;
+                off = th * ep.tiles_w * ep.channels * ep.p * ep.p + pi * ep.p;
+            } else {
+                off = line * ep.col_stride;
+            }
+            sc = ep.alpha * (ep.basis_scale ? __ldg(ep.basis_scale + grp * g.n_valid + ng) : 1.0f);
+        }
+        col_off[n] = off;
+        col_scale[n] = sc;
+    }
+    if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer (both CTAs; completion bytes are credited to the leader's barriers)
+        const uint32_t basis_bar_leader = mapa_u32(smem_u32(&basis_bar), 0);
+        const int half_rows = g.n_tile >> 1;
+        const uint32_t btile = (uint32_t)half_rows * 64;
+        if (rank == 0) mbar_expect_tx(&basis_bar, 4 * g.basis_bytes);
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+            const int row = nt * g.n_tile + (int)rank * half_rows;
+            tma_load_3d_2sm(&map_b_hi, basis_bar_leader, basis_hi + kb * btile, kb * FK, row, grp);
+            tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * btile, kb * FK, row, grp);
+        }
+        uint32_t it = 0;
+        for (int w = pair_in_slice; w < n_work; w += pairs_per_slice) {
+            const int seg = (w / g.tiles_per_seg) * 2 + grp;
+            const int row0 = (w % g.tiles_per_seg) * 256 + (int)rank * 128;
+            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+                const int s = it % g.stages;
+                mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
+                uint8_t* st = ring + s * F_STAGE;
+                const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * F_STAGE);
+                tma_load_3d_2sm(&map_a_hi, full_leader, st, kb * FK, row0, seg);
+                tma_load_3d_2sm(&map_a_lo, full_leader, st + F_ATILE, kb * FK, row0, seg);
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ---------------- MMA issuer (leader CTA only)
+        const uint32_t idesc = fold_idesc(g.n_tile);
+        const uint32_t btile = (uint32_t)(g.n_tile >> 1) * 64;
+        const uint32_t bh = smem_u32(basis_hi), bl = smem_u32(basis_lo);
+        mbar_wait_cluster(&basis_bar, 0);
+        tc_fence_after();
+        uint32_t it = 0, tcount = 0;
+        for (int w = pair_in_slice; w < n_work; w += pairs_per_slice, ++tcount) {
+            const int acc = tcount & 1;
+            mbar_wait_cluster(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc * 256;
+            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+                const int s = it % g.stages;
+                mbar_wait_cluster(&full_bar[s], (it / g.stages) & 1);
+                tc_fence_after();
+                const uint32_t base = smem_u32(ring + s * F_STAGE);
+#pragma unroll
+                for (int k = 0; k < FK / 16; ++k) {
+                    const uint32_t ko = k * 32;
+                    const uint64_t a_hi = smem_desc_sw64(base + ko);
+                    const uint64_t a_lo = smem_desc_sw64(base + F_ATILE + ko);
+                    const uint64_t b_hi = smem_desc_sw64(bh + kb * btile + ko);
+                    const uint64_t b_lo = smem_desc_sw64(bl + kb * btile + ko);
+                    umma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, (kb | k) ? 1u : 0u);   // small terms first
+                    umma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1u);
+                    umma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1u);
+                }
+                umma_commit_2sm(&empty_bar[s], 3);       // frees the stage in both CTAs
+            }
+            umma_commit_2sm(&tmem_full[acc], 3);         // accumulator complete in both CTAs
+        }
+    } else if (warp >= 2) {
+        // ---------------- epilogue warps: TMEM lane quarter = warp & 3, 32-column chunks alternate between
+        // the two warps of a quarter
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        const int n_chunks = (n_lim + 31) >> 5;
+        const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+        const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+        const bool dc_slice = (ep.dc != nullptr) && grp == 0 && nt == 0;
+        uint32_t tcount = 0;
+        for (int w = pair_in_slice; w < n_work; w += pairs_per_slice, ++tcount) {
+            const int seg = (w / g.tiles_per_seg) * 2 + grp;
+            const int r = (w % g.tiles_per_seg) * 256 + (int)rank * 128 + quarter * 32 + lane;   // stacked row
+            const bool row_ok = r < g.rows_per_seg;
+            const int item = r / ep.rows_per_item, rin = r - item * ep.rows_per_item;
+            int64_t base;
+            if (ep.mode == 2) {
+                const int img = item / ep.channels, ch = item - img * ep.channels;
+                const int tw = rin / ep.p, pj = rin - tw * ep.p;
+                base = (((int64_t)img * ep.tiles_h * ep.tiles_w + tw) * ep.channels + ch) * (ep.p * ep.p) + pj;
+            } else {
+                base = (int64_t)seg * ep.seg_stride + (int64_t)item * ep.item_stride + rin;
+            }
+            const float dcv = (dc_slice && row_ok && rin == 0) ? __ldg(ep.dc + item) : 0.0f;
+            const int acc = tcount & 1;
+            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
+            int last = n_chunks - 1;
+            if ((last & 1) != chalf) --last;                 // this warp's last chunk (may be < first: none)
+            if (last < chalf) {                              // nothing to read: release immediately
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+            }
+#pragma unroll 1
+            for (int c = chalf; c < n_chunks; c += 2) {
+                uint32_t rr[32];
+                tmem_ld32_nowait(tmem_acc + c * 32, rr);
+                tmem_ld_wait();
+                if (c == last) {                             // accumulator read out by this warp: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+                }
+                if (!row_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = c * 32 + j;
+                    const int4 off = *reinterpret_cast<const int4*>(&col_off[n]);
+                    const float4 sc = *reinterpret_cast<const float4*>(&col_scale[n]);
+                    float v0 = __uint_as_float(rr[j]) * sc.x, v1 = __uint_as_float(rr[j + 1]) * sc.y;
+                    float v2 = __uint_as_float(rr[j + 2]) * sc.z, v3 = __uint_as_float(rr[j + 3]) * sc.w;
+                    if (j == 0 && c == 0) v0 += dcv;
+                    if (MODE == 0) {
+                        const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
+                        const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+                        if (off.x >= 0) { ep.out_hi[base + off.x] = __low2half(h01); ep.out_lo[base + off.x] = __low2half(l01); }
+                        if (off.y >= 0) { ep.out_hi[base + off.y] = __high2half(h01); ep.out_lo[base + off.y] = __high2half(l01); }
+                        if (off.z >= 0) { ep.out_hi[base + off.z] = __low2half(h23); ep.out_lo[base + off.z] = __low2half(l23); }
+                        if (off.w >= 0) { ep.out_hi[base + off.w] = __high2half(h23); ep.out_lo[base + off.w] = __high2half(l23); }
+                    } else {
+                        if (off.x >= 0) ep.out_f32[base + off.x] = v0;
+                        if (off.y >= 0) ep.out_f32[base + off.y] = v1;
+                        if (off.z >= 0) ep.out_f32[base + off.z] = v2;
+                        if (off.w >= 0) ep.out_f32[base + off.w] = v3;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------ host: launch
+// 3-D fp16 tensor map (k, rows, segments) with a (32, box_rows, 1) box, SWIZZLE_64B
+static int make_map3(CUtensorMap* map, const void* ptr, int64_t k, int64_t rows, int64_t segs, int64_t ld,
+                     int64_t seg_stride, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return DCTA_ERR_UNSUPPORTED; }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) || (segs > 1 && seg_stride % 8)) {
+        set_error("fold_gemm: operand planes need a 16-byte aligned base, pitch and segment stride");
+        return DCTA_ERR_INVALID_ARG;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)(segs > 0 ? segs : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(segs > 1 ? seg_stride : rows * ld) * 2};
+    cuuint32_t box[3] = {FK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return DCTA_ERR_LAUNCH; }
+    return DCTA_OK;
+}
+
+struct FoldOperand {
+    const __half* hi;
+    const __half* lo;
+    int64_t ld;           // pitch (elements) of a row
+    int64_t seg_stride;   // elements between segments (data) / groups (basis)
+};
+
+// slice geometry for a basis of n_valid rows and K columns: (n_tile, n_ntiles, stages), or false if nothing fits
+static bool fold_geometry(int n_valid, int K, FoldGemm& g) {
+    g.num_kb = (int)ceil_div(K, FK);
+    g.n_valid = n_valid;
+    for (int nn = (int)ceil_div(n_valid, 256); nn <= 16; ++nn) {
+        const int n_tile = (int)ceil_div(ceil_div(n_valid, nn), 16) * 16;
+        const int64_t basis = (int64_t)g.num_kb * (n_tile / 2) * 64;
+        const int64_t stages = (F_SMEM_LIMIT - 1024 - 2 * basis) / F_STAGE;
+        if (n_tile <= 256 && stages >= 3) {
+            g.n_tile = n_tile;
+            g.n_ntiles = nn;
+            g.basis_bytes = (uint32_t)basis;
+            g.stages = (int)(stages < F_MAX_STAGES ? stages : F_MAX_STAGES);
+            return 4 * basis < (1 << 20);      // mbarrier transaction-count range
+        }
+    }
+    return false;
+}
+
+static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_seg, const FoldOperand& Bas, int n_valid,
+                            int K, FoldEpi ep, void* stream) {
+    if (rows_per_seg == 0 || n_seg == 0) return DCTA_OK;
+    FoldGemm g{};
+    if (!fold_geometry(n_valid, K, g)) { set_error("fold_gemm: basis %d x %d does not fit in shared memory", n_valid, K); return DCTA_ERR_UNSUPPORTED; }
+    if (rows_per_seg >= (1ll << 31) - 256 || (n_seg & 1)) { set_error("fold_gemm: bad segment geometry"); return DCTA_ERR_INVALID_ARG; }
+    g.n_seg = n_seg;
+    g.rows_per_seg = (int)rows_per_seg;
+    g.tiles_per_seg = (int)ceil_div(rows_per_seg, 256);
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_map3(&ma_hi, A.hi, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
+    if ((rc = make_map3(&ma_lo, A.lo, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
+    if ((rc = make_map3(&mb_hi, Bas.hi, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
+    if ((rc = make_map3(&mb_lo, Bas.lo, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
+    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_slices = 2 * g.n_ntiles;
+    const int64_t work_per_slice = (int64_t)(n_seg / 2) * g.tiles_per_seg;
+    int64_t pps = (sms / 2) / n_slices;                      // pairs per slice
+    if (pps < 1) pps = 1;
+    if (pps > work_per_slice) pps = work_per_slice;
+    const unsigned grid = (unsigned)(2 * pps * n_slices);
+    cudaError_t e;
+    if (ep.mode == 0) {
+        e = cudaFuncSetAttribute(fold_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess)
+            fold_gemm_kernel<0><<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, g, ep);
+    } else {
+        e = cudaFuncSetAttribute(fold_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess)
+            fold_gemm_kernel<1><<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, g, ep);
+    }
+    if (e != cudaSuccess) { set_error("fold_gemm: %s", cudaGetErrorString(e)); return DCTA_ERR_LAUNCH; }
+    return check_launch("fold_gemm");
+}
+
+// ------------------------------------------------------------------------------ fold / unfold kernels
+__device__ __forceinline__ void split16x4(const float (&v)[4], float scale, uint2& hi, uint2& lo) {
+    const float s0 = v[0] * scale, s1 = v[1] * scale, s2 = v[2] * scale, s3 = v[3] * scale;
+    const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(s0 - f01.x, s1 - f01.y), l23 = __floats2half2_rn(s2 - f23.x, s3 - f23.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+
+__device__ __forceinline__ void rgb_px_to_ipt_f(float r, float g, float b, const Mat3& A, const Mat3& B, float& o0,
+                                                float& o1, float& o2) {
+    float l = fmaf(A.m[2], b, fmaf(A.m[1], g, A.m[0] * r));
+    float m = fmaf(A.m[5], b, fmaf(A.m[4], g, A.m[3] * r));
+    float s = fmaf(A.m[8], b, fmaf(A.m[7], g, A.m[6] * r));
+    l = signed_pow(l, 0.43f);
+    m = signed_pow(m, 0.43f);
+    s = signed_pow(s, 0.43f);
+    o0 = fmaf(B.m[2], s, fmaf(B.m[1], m, B.m[0] * l));
+    o1 = fmaf(B.m[5], s, fmaf(B.m[4], m, B.m[3] * l));
+    o2 = fmaf(B.m[8], s, fmaf(B.m[7], m, B.m[6] * l));
+}
+
+// the four sign combinations of the mirrored samples p1 = x[h', w'], p2 = x[h', W-1-w'], p3 = x[H-1-h', w'],
+// p4 = x[H-1-h', W-1-w']:  q[b*2 + a],  a = row parity of the coefficient, b = column parity
+__device__ __forceinline__ void butterfly4(float p1, float p2, float p3, float p4, float (&q)[4]) {
+    const float s12 = p1 + p2, d12 = p1 - p2, s34 = p3 + p4, d34 = p3 - p4;
+    q[0] = s12 + s34;   // b = 0, a = 0
+    q[1] = s12 - s34;   // b = 0, a = 1
+    q[2] = d12 + d34;   // b = 1, a = 0
+    q[3] = d12 - d34;   // b = 1, a = 1
+}
+
+// util.py:70-82 rgb_to_ipt fused with centring, the 2-D fold and the fp16 hi/lo split:
+// xq[b][a][plane][h'][w'], plane = img * 3 + c.  One thread = 4 consecutive w' of one (img, h').
+__global__ void __launch_bounds__(256) rgb_to_ipt_fold_kernel(const float* __restrict__ rgb, const float* __restrict__ mus,
+                                                              __half* __restrict__ hi, __half* __restrict__ lo,
+                                                              int64_t n_img, int h, int w, Mat3 A, Mat3 B, float scale) {
+    const int h2 = h >> 1, w8 = w >> 3;                 // w8: float4 groups of the half row
+    const int64_t total = n_img * h2 * w8;
+    const int64_t plane4 = (int64_t)h * w / 4, q4 = (int64_t)h2 * (w >> 1) / 4;   // in float4 / uint2 units
+    const int64_t n_planes = n_img * 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xv = (int)(i % w8);
+        const int64_t t = i / w8;
+        const int y = (int)(t % h2);
+        const int64_t img = t / h2;
+        const float4* src = reinterpret_cast<const float4*>(rgb) + img * 3 * plane4;
+        const int64_t top = (int64_t)y * (w >> 2), bot = (int64_t)(h - 1 - y) * (w >> 2);
+        const int xl = xv, xr = (w >> 2) - 1 - xv;
+        float ipt[4][3][4];          // [corner: top-left, top-right, bottom-left, bottom-right][channel][pixel]
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t o = ((k & 2) ? bot : top) + ((k & 1) ? xr : xl);
+            const float4 c0 = ld_stream(src + o), c1 = ld_stream(src + plane4 + o), c2 = ld_stream(src + 2 * plane4 + o);
+            const float r[4] = {c0.x, c0.y, c0.z, c0.w}, gg[4] = {c1.x, c1.y, c1.z, c1.w}, bb[4] = {c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rgb_px_to_ipt_f(r[j], gg[j], bb[j], A, B, ipt[k][0][j], ipt[k][1][j], ipt[k][2][j]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float mu = __ldg(mus + img * 3 + c);
+            float q[4][4];           // [quadrant][pixel]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float qq[4];
+                butterfly4(ipt[0][c][j] - mu, ipt[1][c][3 - j] - mu, ipt[2][c][j] - mu, ipt[3][c][3 - j] - mu, qq);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) q[s][j] = qq[s];
+            }
+            const int64_t o = ((img * 3 + c) * h2 + y) * (int64_t)(w >> 3) + xv;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                uint2 vh, vl;
+                split16x4(q[s], scale, vh, vl);
+                reinterpret_cast<uint2*>(hi)[s * n_planes * q4 + o] = vh;
+                reinterpret_cast<uint2*>(lo)[s * n_planes * q4 + o] = vl;
+            }
+        }
+    }
+}
+
+// fp32 planes -> centred, folded, split quadrants (same layout, any number of planes)
+__global__ void __launch_bounds__(256) fold_planes_kernel(const float* __restrict__ x, const float* __restrict__ mus,
+                                                          __half* __restrict__ hi, __half* __restrict__ lo,
+                                                          int64_t n_planes, int h, int w, float scale) {
+    const int h2 = h >> 1, w8 = w >> 3;
+    const int64_t total = n_planes * h2 * w8;
+    const int64_t plane4 = (int64_t)h * w / 4, q4 = (int64_t)h2 * (w >> 1) / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xv = (int)(i % w8);
+        const int64_t t = i / w8;
+        const int y = (int)(t % h2);
+        const int64_t pl = t / h2;
+        const float4* src = reinterpret_cast<const float4*>(x) + pl * plane4;
+        const int64_t top = (int64_t)y * (w >> 2), bot = (int64_t)(h - 1 - y) * (w >> 2);
+        const int xr = (w >> 2) - 1 - xv;
+        const float4 a4 = ld_stream(src + top + xv), b4 = ld_stream(src + top + xr);
+        const float4 c4 = ld_stream(src + bot + xv), d4 = ld_stream(src + bot + xr);
+        const float mu = __ldg(mus + pl);
+        const float p1[4] = {a4.x, a4.y, a4.z, a4.w}, p2[4] = {b4.w, b4.z, b4.y, b4.x};
+        const float p3[4] = {c4.x, c4.y, c4.z, c4.w}, p4[4] = {d4.w, d4.z, d4.y, d4.x};
+        float q[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float qq[4];
+            butterfly4(p1[j] - mu, p2[j] - mu, p3[j] - mu, p4[j] - mu, qq);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) q[s][j] = qq[s];
+        }
+        const int64_t o = (pl * h2 + y) * (int64_t)w8 + xv;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            uint2 vh, vl;
+            split16x4(q[s], scale, vh, vl);
+            reinterpret_cast<uint2*>(hi)[s * n_planes * q4 + o] = vh;
+            reinterpret_cast<uint2*>(lo)[s * n_planes * q4 + o] = vl;
+        }
+    }
+}
+
+__device__ __forceinline__ void ipt_px_to_rgb_f(float i0, float i1, float i2, const Mat3& A, const Mat3& B, float& o0,
+                                                float& o1, float& o2) {
+    float l = fmaf(A.m[2], i2, fmaf(A.m[1], i1, A.m[0] * i0));
+    float m = fmaf(A.m[5], i2, fmaf(A.m[4], i1, A.m[3] * i0));
+    float s = fmaf(A.m[8], i2, fmaf(A.m[7], i1, A.m[6] * i0));
+    const float gamma = (float)(1.0 / 0.43);
+    l = signed_pow(l, gamma);
+    m = signed_pow(m, gamma);
+    s = signed_pow(s, gamma);
+    o0 = fmaf(B.m[2], s, fmaf(B.m[1], m, B.m[0] * l));
+    o1 = fmaf(B.m[5], s, fmaf(B.m[4], m, B.m[3] * l));
+    o2 = fmaf(B.m[8], s, fmaf(B.m[7], m, B.m[6] * l));
+}
+
+// inverse butterfly: the four mirrored samples from the quadrant transforms z[b*2 + a] (+ the constant of
+// the DC coefficient)
+__device__ __forceinline__ void unbutterfly4(const float (&z)[4], float dcv, float& p1, float& p2, float& p3, float& p4) {
+    const float e = z[0] + z[1], f = z[0] - z[1];     // column-even part at rows h', H-1-h'
+    const float o = z[2] + z[3], g = z[2] - z[3];     // column-odd part
+    p1 = (e + o) + dcv;
+    p2 = (e - o) + dcv;
+    p3 = (f + g) + dcv;
+    p4 = (f - g) + dcv;
+}
+
+// quadrant planes z[s][plane][h'][w'] -> un-folded IPT -> RGB (util.py:85-97); COLOR = false: plain planes out
+template <bool COLOR>
+__global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ z, const float* __restrict__ dc,
+                                                     float* __restrict__ out, int64_t n_items, int h, int w, Mat3 A, Mat3 B) {
+    constexpr int CH = COLOR ? 3 : 1;
+    const int h2 = h >> 1, w8 = w >> 3;
+    const int64_t total = n_items * h2 * w8;
+    const int64_t plane4 = (int64_t)h * w / 4, q4 = (int64_t)h2 * (w >> 1) / 4;
+    const int64_t n_planes = n_items * CH;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xv = (int)(i % w8);
+        const int64_t t = i / w8;
+        const int y = (int)(t % h2);
+        const int64_t item = t / h2;
+        float px[4][CH][4];          // [corner][channel][pixel]
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int64_t pl = item * CH + c;
+            const float dcv = dc ? __ldg(dc + pl) : 0.0f;
+            const int64_t o = (pl * h2 + y) * (int64_t)w8 + xv;
+            float4 q[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) q[s] = ld_stream(reinterpret_cast<const float4*>(z) + s * n_planes * q4 + o);
+            const float qa[4][4] = {{q[0].x, q[0].y, q[0].z, q[0].w}, {q[1].x, q[1].y, q[1].z, q[1].w},
+                                    {q[2].x, q[2].y, q[2].z, q[2].w}, {q[3].x, q[3].y, q[3].z, q[3].w}};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float zz[4] = {qa[0][j], qa[1][j], qa[2][j], qa[3][j]};
+                unbutterfly4(zz, dcv, px[0][c][j], px[1][c][3 - j], px[2][c][j], px[3][c][3 - j]);
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(out) + item * CH * plane4;
+        const int64_t top = (int64_t)y * (w >> 2), bot = (int64_t)(h - 1 - y) * (w >> 2);
+        const int xr = (w >> 2) - 1 - xv;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (COLOR) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float r, gg, bb;
+                    ipt_px_to_rgb_f(px[k][0][j], px[k][CH > 1 ? 1 : 0][j], px[k][CH > 2 ? 2 : 0][j], A, B, r, gg, bb);
+                    px[k][0][j] = r; px[k][CH > 1 ? 1 : 0][j] = gg; px[k][CH > 2 ? 2 : 0][j] = bb;
+                }
+            }
+            const int64_t o = ((k & 2) ? bot : top) + ((k & 1) ? xr : xv);
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                st_stream(dst + c * plane4 + o, make_float4(px[k][c][0], px[k][c][1], px[k][c][2], px[k][c][3]));
+        }
+    }
+}
+
+// feature_extraction_dct_autoencoder.py:635-653 un-patchify (CODES = false) or its fusion with
+// lfq.indices_to_codes + PatchNorm.inverse_norm (CODES = true; lfq.py:105-134, patchnorm.py:167-177),
+// writing the folded coefficient quadrants yq[b][a][plane][i][j] = Y[2i+a, 2j+b] as scaled fp16 hi/lo.
+// One CTA per tile-row of one plane; a thread owns 8 consecutive coefficient columns (4 per column parity).
+template <bool CODES>
+__global__ void __launch_bounds__(128) unpatchify_fold_kernel(const float* __restrict__ patches,
+                                                              const int64_t* __restrict__ codes,
+                                                              const int32_t* __restrict__ slot_map,
+                                                              const int32_t* __restrict__ img_sel, int C, int th, int tw,
+                                                              int p, int rows, int cols, int ldq, int64_t n_planes,
+                                                              LfqNormParams q, __half* __restrict__ hi,
+                                                              __half* __restrict__ lo, float* __restrict__ dc,
+                                                              float dc_factor, float scale) {
+    const int z = p * p;
+    const int tile_rows = rows / p;
+    const unsigned id = blockIdx.x;
+    const int ty = (int)(id % (unsigned)tile_rows);
+    const unsigned t = id / (unsigned)tile_rows;
+    const int c = (int)(t % (unsigned)C);
+    const int sel = (int)(t / (unsigned)C);
+    const int64_t img = img_sel ? img_sel[sel] : sel;
+    const bool row_in = ty < th;
+    const int32_t* smap = slot_map + ((img * C + c) * th + (row_in ? ty : 0)) * tw;
+    const int64_t plane = (int64_t)sel * C + c;
+    const int rows2 = rows >> 1;
+    const int64_t quad = n_planes * rows2 * (int64_t)ldq;          // elements of one quadrant array
+    const float* med_row = nullptr;
+    const float* b_row = nullptr;
+    if (CODES) {
+        med_row = q.median + (((int64_t)c * q.H + ty) * q.W) * q.z;
+        b_row = q.b + (((int64_t)c * q.H + ty) * q.W) * q.z;
+    }
+    for (int xv = threadIdx.x; xv < ldq / 4; xv += blockDim.x) {
+        const int x0 = xv * 8;
+        int32_t slot[8];
+        int px[8], txs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int x = x0 + j;
+            const int tx = x / p;
+            txs[j] = tx;
+            px[j] = x - tx * p;
+            slot[j] = (row_in && tx < tw && x < cols) ? __ldg(smap + tx) : -1;
+        }
+        for (int py = 0; py < p; ++py) {
+            float v[8];
+            long long code = 0;
+            int code_cb = -1;
+            int32_t code_slot = -1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float val = 0.0f;
+                if (slot[j] >= 0) {
+                    const int e = py * p + px[j];
+                    if (CODES) {
+                        const int cb = e / q.d, bi = e - cb * q.d;
+                        if (cb != code_cb || slot[j] != code_slot) {
+                            code = __ldg(codes + (int64_t)slot[j] * q.c + cb);
+                            code_cb = cb;
+                            code_slot = slot[j];
+                        }
+                        const float qv = ((code >> (q.d - 1 - bi)) & 1) ? q.scale : -q.scale;       // lfq.py:118-120
+                        const int pe = txs[j] * q.z + e;
+                        const float sd = __fadd_rn(__fmul_rn(__ldg(b_row + pe), kSqrt2f), q.eps);
+                        val = __fadd_rn(__fmul_rn(qv, sd), __ldg(med_row + pe));                      // patchnorm.py:177
+                    } else {
+                        val = __ldg(patches + (int64_t)slot[j] * z + e);
+                    }
+                }
+                if (ty == 0 && py == 0 && x0 + j == 0) {
+                    dc[plane] = val * dc_factor;
+                    val = 0.0f;
+                }
+                v[j] = val;
+            }
+            const int kh = ty * p + py;
+            const int a = kh & 1, ii = kh >> 1;
+            const int64_t o = ((a * n_planes + plane) * rows2 + ii) * (int64_t)ldq + xv * 4;   // + b * 2 * quad
+            const float ev[4] = {v[0], v[2], v[4], v[6]}, od[4] = {v[1], v[3], v[5], v[7]};
+            uint2 vh, vl;
+            split16x4(ev, scale, vh, vl);
+            *reinterpret_cast<uint2*>(hi + o) = vh;
+            *reinterpret_cast<uint2*>(lo + o) = vl;
+            split16x4(od, scale, vh, vl);
+            *reinterpret_cast<uint2*>(hi + 2 * quad + o) = vh;
+            *reinterpret_cast<uint2*>(lo + 2 * quad + o) = vl;
+        }
+    }
+}
+
+// fp32 coefficient planes (n_planes, kh, kw) -> folded split quadrants (DC moved to dc[])
+__global__ void __launch_bounds__(256) fold_coef_kernel(const float* __restrict__ y, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo, float* __restrict__ dc,
+                                                        int64_t n_planes, int kh, int kw, int ldq, float dc_factor,
+                                                        float scale) {
+    const int kh2 = kh >> 1;
+    const int64_t quad = n_planes * kh2 * (int64_t)ldq;
+    const int64_t total = 4 * quad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % ldq);
+        int64_t r = i / ldq;
+        const int ii = (int)(r % kh2);
+        r /= kh2;
+        const int64_t pl = r % n_planes;
+        const int s = (int)(r / n_planes);           // b * 2 + a
+        const int a = s & 1, b = s >> 1;
+        const int yy = 2 * ii + a, xx = 2 * j + b;
+        float v = xx < kw ? y[(pl * kh + yy) * kw + xx] : 0.f;
+        if (xx == 0 && yy == 0) { dc[pl] = v * dc_factor; v = 0.f; }
+        const float sv = v * scale;
+        const __half hh = __float2half_rn(sv);
+        hi[i] = hh;
+        lo[i] = __float2half_rn(sv - __half2float(hh));
+    }
+}
+
+}  // namespace dcta
+
+using namespace dcta;
+
+// Scales of the split operands (powers of two, exact).  The fold sums up to four samples, so the image
+// quadrants carry 2^6 where the plain path carries 2^8, and the forward intermediate 2^5 instead of 2^6.
+static const float kFScaleX = 64.f, kFScaleP = 32.f, kFScaleY = 16.f, kFScaleQ = 64.f, kFScaleBasis = 1024.f;
+
+static bool fold_dims_ok(int h, int w, int kh, int kw) {
+    return h > 0 && w > 0 && h % 16 == 0 && w % 16 == 0 && kh > 0 && kw > 0 && kh % 2 == 0 && kw % 2 == 0 && kh <= h && kw <= w;
+}
+
+extern "C" int dcta_fold_supported(int h, int w, int kh, int kw) {
+    if (!fold_dims_ok(h, w, kh, kw)) return 0;
+    FoldGemm g{};
+    return fold_geometry(kw / 2, w / 2, g) && fold_geometry(kh / 2, h / 2, g) && fold_geometry(w / 2, kw / 2, g) &&
+           fold_geometry(h / 2, kh / 2, g);
+}
+
+extern "C" int dcta_rgb_to_ipt_fold(const float* rgb, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
+                                    int64_t n_img, int h, int w, const float* m_rgb2lms_host, const float* m_ipt_host,
+                                    void* stream) {
+    DCTA_REQUIRE(rgb && xq_hi && xq_lo && dc && sums_scratch && m_rgb2lms_host && m_ipt_host, "rgb_to_ipt_fold: null pointer");
+    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 && n_img <= 65535,
+                 "rgb_to_ipt_fold: needs h, w multiples of 16, aligned input, at most 65535 images");
+    if (n_img == 0) return DCTA_OK;
+    Mat3 A, B;
+    for (int i = 0; i < 9; ++i) { A.m[i] = m_rgb2lms_host[i]; B.m[i] = m_ipt_host[i]; }
+    cudaStream_t st = as_stream(stream);
+    const float* mus = launch_ipt_plane_means(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
+    rgb_to_ipt_fold_kernel<<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, st>>>(
+        rgb, mus, (__half*)xq_hi, (__half*)xq_lo, n_img, h, w, A, B, kFScaleX);
+    return check_launch("rgb_to_ipt_fold");
+}
+
+extern "C" int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
+                                int64_t n_planes, int h, int w, void* stream) {
+    DCTA_REQUIRE(x && xq_hi && xq_lo && dc && sums_scratch, "fold_planes: null pointer");
+    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && n_planes <= 65535,
+                 "fold_planes: needs h, w multiples of 16, aligned input, at most 65535 planes");
+    if (n_planes == 0) return DCTA_OK;
+    cudaStream_t st = as_stream(stream);
+    const float* mus = launch_plane_means(x, sums_scratch, dc, n_planes, h, w, st);
+    fold_planes_kernel<<<grid_for(n_planes * (h / 2) * (w / 8), 256), 256, 0, st>>>(
+        x, mus, (__half*)xq_hi, (__half*)xq_lo, n_planes, h, w, kFScaleX);
+    return check_launch("fold_planes");
+}
+
+// forward: xq[b][a][plane][h/2][w/2] (scale 2^6) + removed DC -> token grid (tile_p > 0) or planes (n_planes, kh, kw)
+//   bw: (2, kw/2, w/2) folded basis of the width transform, group = column parity b; rs_w (2, kw/2) its row factors
+//   bh: (2, kh/2, h/2) for the height transform, group = row parity a; work: (2, n_planes, kw, h/2) hi/lo
+extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
+                                  const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
+                                  const float* rs_h, void* work_hi, void* work_lo, float* y, int64_t n_planes, int h,
+                                  int w, int kh, int kw, int tile_p, int channels, void* stream) {
+    DCTA_REQUIRE(xq_hi && xq_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && y,
+                 "dct2_fwd_fold: null pointer");
+    DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_fwd_fold: needs h, w multiples of 16 and even kh <= h, kw <= w");
+    if (tile_p > 0)
+        DCTA_REQUIRE(channels > 0 && kh % tile_p == 0 && kw % tile_p == 0 && n_planes % channels == 0,
+                     "dct2_fwd_fold: kh/kw must be multiples of the patch size");
+    if (n_planes == 0) return DCTA_OK;
+    const int h2 = h / 2, w2 = w / 2;
+    // pass 1: P[(a, plane, h'), j] = sum_w' xq[b][a][plane][h', w'] CW[2j+b, w'], stored as P^T[a][plane][kw = 2j+b][h']
+    FoldOperand A1{(const __half*)xq_hi, (const __half*)xq_lo, w2, 2 * n_planes * (int64_t)h2 * w2};
+    FoldOperand B1{(const __half*)bw_hi, (const __half*)bw_lo, w2, (int64_t)(kw / 2) * w2};
+    FoldEpi e1{};
+    e1.mode = 0; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
+    e1.rows_per_item = h2; e1.seg_stride = 0; e1.item_stride = (int64_t)kw * h2;
+    e1.col_mul = 2; e1.col_add = 1; e1.col_stride = h2;
+    e1.alpha = kFScaleP / kFScaleX; e1.basis_scale = rs_w;
+    int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)h2, 2, B1, kw / 2, w2, e1, stream);
+    if (rc) return rc;
+    // pass 2: Y[2i+a, kw] = sum_h' CH[2i+a, h'] P^T[a][plane][kw][h']   (+ the removed constant's DC at [0,0])
+    FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, h2, n_planes * (int64_t)kw * h2};
+    FoldOperand B2{(const __half*)bh_hi, (const __half*)bh_lo, h2, (int64_t)(kh / 2) * h2};
+    FoldEpi e2{};
+    e2.out_f32 = y; e2.rows_per_item = kw; e2.col_mul = 2; e2.col_add = 1;
+    e2.alpha = 1.0f / kFScaleP; e2.basis_scale = rs_h; e2.dc = dc;
+    if (tile_p > 0) {
+        e2.mode = 2; e2.p = tile_p; e2.channels = channels; e2.tiles_h = kh / tile_p; e2.tiles_w = kw / tile_p;
+    } else {
+        e2.mode = 1; e2.seg_stride = 0; e2.item_stride = (int64_t)kh * kw; e2.col_stride = kw;
+    }
+    return launch_fold_gemm(A2, n_planes * (int64_t)kw, 2, B2, kh / 2, h2, e2, stream);
+}
+
+// inverse: yq[b][a][plane][kh/2][ldq] (scale 2^4, DC removed) -> z[b*2+a][plane][h/2][w/2] fp32 quadrant transforms
+//   bwt: (2, w/2, ldq) = CW[2j+b, w']^T, bht: (2, h/2, ldi) = CH[2i+a, h']^T; work: (2, 2, n_planes, w/2, ldi) hi/lo
+extern "C" int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const void* bwt_hi, const void* bwt_lo,
+                                  const void* bht_hi, const void* bht_lo, void* work_hi, void* work_lo, float* z,
+                                  int64_t n_planes, int h, int w, int kh, int kw, void* stream) {
+    DCTA_REQUIRE(yq_hi && yq_lo && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && z,
+                 "dct2_inv_fold: null pointer");
+    DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_inv_fold: needs h, w multiples of 16 and even kh <= h, kw <= w");
+    if (n_planes == 0) return DCTA_OK;
+    const int h2 = h / 2, w2 = w / 2, kh2 = kh / 2, kw2 = kw / 2;
+    const int64_t ldq = ceil_div(kw2, 8) * 8, ldi = ceil_div(kh2, 8) * 8;
+    // pass 1: Q[(a, plane, i), w'] = sum_j yq[b][a][plane][i, j] CW[2j+b, w'], stored as Q^T[b][a][plane][w'][i]
+    FoldOperand A1{(const __half*)yq_hi, (const __half*)yq_lo, ldq, 2 * n_planes * (int64_t)kh2 * ldq};
+    FoldOperand B1{(const __half*)bwt_hi, (const __half*)bwt_lo, ldq, (int64_t)w2 * ldq};
+    FoldEpi e1{};
+    e1.mode = 0; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
+    e1.rows_per_item = kh2; e1.seg_stride = 2 * n_planes * (int64_t)w2 * ldi; e1.item_stride = (int64_t)w2 * ldi;
+    e1.col_mul = 1; e1.col_add = 0; e1.col_stride = (int)ldi;
+    e1.alpha = kFScaleQ / (kFScaleBasis * kFScaleY);
+    int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)kh2, 2, B1, w2, kw2, e1, stream);
+    if (rc) return rc;
+    // pass 2: Z[(b, a)][plane][h', w'] = sum_i CH[2i+a, h'] Q^T[b][a][plane][w'][i]
+    FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, ldi, n_planes * (int64_t)w2 * ldi};
+    FoldOperand B2{(const __half*)bht_hi, (const __half*)bht_lo, ldi, (int64_t)h2 * ldi};
+    FoldEpi e2{};
+    e2.mode = 1; e2.out_f32 = z; e2.rows_per_item = w2;
+    e2.seg_stride = n_planes * (int64_t)h2 * w2; e2.item_stride = (int64_t)h2 * w2;
+    e2.col_mul = 1; e2.col_add = 0; e2.col_stride = w2;
+    e2.alpha = 1.0f / (kFScaleBasis * kFScaleQ);
+    return launch_fold_gemm(A2, n_planes * (int64_t)w2, 4, B2, h2, kh2, e2, stream);
+}
+
+extern "C" int dcta_unfold_ipt_to_rgb(const float* z, const float* dc, float* rgb, int64_t n_img, int h, int w,
+                                      const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream) {
+    DCTA_REQUIRE(z && rgb && m_ipt_inv_host && m_lms2rgb_host, "unfold_ipt_to_rgb: null pointer");
+    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0, "unfold_ipt_to_rgb: bad sizes");
+    if (n_img == 0) return DCTA_OK;
+    Mat3 A, B;
+    for (int i = 0; i < 9; ++i) { A.m[i] = m_ipt_inv_host[i]; B.m[i] = m_lms2rgb_host[i]; }
+    unfold_kernel<true><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, rgb, n_img, h, w, A, B);
+    return check_launch("unfold_ipt_to_rgb");
+}
+
+extern "C" int dcta_unfold_planes(const float* z, const float* dc, float* x, int64_t n_planes, int h, int w, void* stream) {
+    DCTA_REQUIRE(z && x, "unfold_planes: null pointer");
+    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "unfold_planes: bad sizes");
+    if (n_planes == 0) return DCTA_OK;
+    Mat3 A{}, B{};
+    unfold_kernel<false><<<grid_for(n_planes * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, x, n_planes, h, w, A, B);
+    return check_launch("unfold_planes");
+}
+
+extern "C" int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, float* dc, int64_t n_planes, int kh,
+                                     int kw, int out_h, int out_w, void* stream) {
+    DCTA_REQUIRE(y && yq_hi && yq_lo && dc && kh > 0 && kw > 0 && kh % 2 == 0 && kw % 2 == 0, "fold_coef_planes: bad args");
+    if (n_planes == 0) return DCTA_OK;
+    const int ldq = (int)(ceil_div(kw / 2, 8) * 8);
+    fold_coef_kernel<<<grid_for(4 * n_planes * (kh / 2) * ldq, 256), 256, 0, as_stream(stream)>>>(
+        y, (__half*)yq_hi, (__half*)yq_lo, dc, n_planes, kh, kw, ldq, 1.0f / sqrtf((float)out_h * (float)out_w), kFScaleY);
+    return check_launch("fold_coef_planes");
+}
+
+static int launch_unpatchify_fold(bool with_codes, const float* patches, const int64_t* codes, const int32_t* slot_map,
+                                  const int32_t* img_sel, int64_t n_img, int C, int th, int tw, int p, int rows, int cols,
+                                  int out_h, int out_w, const LfqNormParams& q, void* yq_hi, void* yq_lo, float* dc,
+                                  void* stream, const char* who) {
+    DCTA_REQUIRE(slot_map && yq_hi && yq_lo && dc, "%s: null pointer", who);
+    DCTA_REQUIRE(rows > 0 && cols > 0 && p > 0 && out_h > 0 && out_w > 0 && rows % 2 == 0 && cols % 2 == 0 && rows % p == 0,
+                 "%s: needs even plane sizes and rows %% patch == 0", who);
+    if (n_img == 0) return DCTA_OK;
+    const int64_t n_rows_total = n_img * C * (rows / p);
+    DCTA_REQUIRE(n_rows_total < (1ll << 31), "%s: too many plane rows for one launch", who);
+    const int ldq = (int)(ceil_div(cols / 2, 8) * 8);
+    const float dcf = 1.0f / sqrtf((float)out_h * (float)out_w);
+    if (with_codes)
+        unpatchify_fold_kernel<true><<<(unsigned)n_rows_total, 128, 0, as_stream(stream)>>>(
+            patches, codes, slot_map, img_sel, C, th, tw, p, rows, cols, ldq, n_img * C, q, (__half*)yq_hi, (__half*)yq_lo,
+            dc, dcf, kFScaleY);
+    else
+        unpatchify_fold_kernel<false><<<(unsigned)n_rows_total, 128, 0, as_stream(stream)>>>(
+            patches, codes, slot_map, img_sel, C, th, tw, p, rows, cols, ldq, n_img * C, q, (__half*)yq_hi, (__half*)yq_lo,
+            dc, dcf, kFScaleY);
+    return check_launch(who);
+}
+
+extern "C" int dcta_unpatchify_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
+                                    int channels_n, int th, int tw, int p, int rows, int cols, int out_h, int out_w,
+                                    void* yq_hi, void* yq_lo, float* dc, void* stream) {
+    DCTA_REQUIRE(patches, "unpatchify_fold: null pointer");
+    LfqNormParams q{};
+    return launch_unpatchify_fold(false, patches, nullptr, slot_map, img_sel, n_img, channels_n, th, tw, p, rows, cols,
+                                  out_h, out_w, q, yq_hi, yq_lo, dc, stream, "unpatchify_fold");
+}
+
+extern "C" int dcta_decode_codes_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel,
+                                      int64_t n_img, int channels_n, int th, int tw, int p, int rows, int cols, int out_h,
+                                      int out_w, const float* median, const float* b, int H, int W, float eps, int c,
+                                      int d, float scale, void* yq_hi, void* yq_lo, float* dc, void* stream) {
+    DCTA_REQUIRE(codes && median && b, "decode_codes_fold: null pointer");
+    DCTA_REQUIRE(th <= H && tw <= W && c > 0 && d > 0 && d <= 62 && c * d == p * p && rows / p <= H,
+                 "decode_codes_fold: needs a projection-free LFQ (c*d == p*p) and a token grid inside the PatchNorm tables");
+    LfqNormParams q{median, b, channels_n, H, W, p * p, eps, 0.f, 0.f, c, d, scale};
+    return launch_unpatchify_fold(true, nullptr, codes, slot_map, img_sel, n_img, channels_n, th, tw, p, rows, cols,
+                                  out_h, out_w, q, yq_hi, yq_lo, dc, stream, "decode_codes_fold");
+}

@@ -13,19 +13,9 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "lfq_norm.cuh"
 
 namespace dcta {
-
-constexpr float kSqrt2f = 1.41421356237309504880f;
-
-struct LfqNormParams {
-    const float* median;   // (C, H, W, z)
-    const float* b;        // (C, H, W, z)
-    int C, H, W, z;
-    float eps, lo, hi;     // PatchNorm eps / clamp
-    int c, d;              // LFQ codebooks x bits, c * d == z
-    float scale;           // LFQ codebook_scale
-};
 
 // one warp per output slot (row, s)
 __global__ void __launch_bounds__(256) pack_codes_kernel(

@@ -20,8 +20,9 @@ import torch
 
 from . import _lib
 from .dct_patches import DCTPatches
-from .util import (_round8, dct2, dct2_fwd_tc, dct2_inv_tc, dct2_truncated, exp_trunc_dist, idct2,
-                   idct2_truncated, ipt_to_rgb, rgb_to_ipt, rgb_to_ipt_split, tc_forward_ok, to_device_f32)
+from .util import (_round8, dct2, dct2_fwd_fold, dct2_fwd_tc, dct2_inv_fold, dct2_inv_tc, dct2_truncated,
+                   exp_trunc_dist, fold_ok, idct2, idct2_truncated, ipt_to_rgb, rgb_to_ipt, rgb_to_ipt_fold,
+                   rgb_to_ipt_split, tc_forward_ok, to_device_f32, unfold_ipt_to_rgb)
 
 _SEG_DTYPE = np.dtype([("row", "<i4"), ("offset", "<i4"), ("k", "<i4"), ("image_id", "<i4"), ("img", "<i8")])
 assert _SEG_DTYPE.itemsize == 24
@@ -54,8 +55,10 @@ class DCTAutoencoderFeatureExtractor:
         dct_impl: str = "tc",
     ):
         """``dct_impl``: "tc" = tcgen05 split-precision GEMMs (fp32-class accuracy, images in the
-        documented [0, 1] range; |IPT - plane mean| must stay below 2^7), "fp32" = exact-fp32 FFMA GEMMs."""
-        assert dct_impl in ("tc", "fp32")
+        documented [0, 1] range; |IPT - plane mean| must stay below 2^7) -- folded (half the
+        multiply-adds, csrc/dct_fold.cu) whenever the sizes allow it; "tc_plain" = the same without the
+        fold; "fp32" = exact-fp32 FFMA GEMMs."""
+        assert dct_impl in ("tc", "tc_plain", "fp32")
         self.dct_impl = dct_impl
         self.channels = channels
         self.patch_size = patch_size
@@ -131,7 +134,11 @@ class DCTAutoencoderFeatureExtractor:
             # fused geometry: crop (FE:360) and max_patch clip (FE:393) only remove high
             # frequencies, so only the first th*p x tw*p coefficients are ever computed
             assert c == 3, "the IPT colour transform is defined for 3 channels"
-            if self.dct_impl == "tc" and tc_forward_ok(h, w):
+            if self.dct_impl == "tc" and fold_ok(h, w, th * p, tw * p):
+                # folded: the colour transform writes the four mirrored sign combinations of each plane
+                hi, lo, dc = rgb_to_ipt_fold(x)
+                return dct2_fwd_fold(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c)
+            if self.dct_impl in ("tc", "tc_plain") and tc_forward_ok(h, w):
                 # tensor cores: colour transform writes the centred fp16 hi/lo operand planes directly
                 hi, lo, dc = rgb_to_ipt_split(x)
                 return dct2_fwd_tc(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c)
@@ -327,7 +334,7 @@ class DCTAutoencoderFeatureExtractor:
     def postprocess_codes_batch(self, x: DCTPatches, codes: torch.Tensor, norm, lfq) -> torch.Tensor:
         """``lfq.indices_to_codes`` -> ``norm.inverse_norm`` -> ``postprocess_batch`` with the
         de-quantised patches kept in registers; same-size batches, tensor-core DCT path."""
-        assert self._lfq_fusable(norm, lfq) and self.dct_impl == "tc"
+        assert self._lfq_fusable(norm, lfq) and self.dct_impl in ("tc", "tc_plain")
         assert len(set(map(tuple, x.original_sizes))) == 1 and len(set(map(tuple, x.patch_sizes))) == 1
         (idx, rgb), = self._decode_groups(x, codes=codes.contiguous(), norm=norm, lfq=lfq)
         return rgb
@@ -527,7 +534,23 @@ class DCTAutoencoderFeatureExtractor:
             n, kh, kw = len(idx), gh * p, gw * p
             with torch.cuda.device(dev):
                 st = _lib.stream_ptr(dev)
-                if self.dct_impl == "tc":
+                if self.dct_impl == "tc" and C == 3 and fold_ok(h, w, kh, kw):
+                    ldq = _round8(kw // 2)
+                    y_hi = torch.empty((2, 2, n * C, kh // 2, ldq), dtype=torch.float16, device=dev)
+                    y_lo = torch.empty_like(y_hi)
+                    dc = torch.empty(n * C, dtype=torch.float32, device=dev)
+                    if codes is not None:
+                        _lib.call("dcta_decode_codes_fold", _lib.ptr(codes), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
+                                  th, tw, p, kh, kw, h, w, _lib.ptr(norm.median.data), _lib.ptr(norm.b.data),
+                                  norm.max_patch_h, norm.max_patch_w, float(norm.eps), lfq.num_codebooks,
+                                  lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(y_hi), _lib.ptr(y_lo),
+                                  _lib.ptr(dc), st)
+                    else:
+                        _lib.call("dcta_unpatchify_fold", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
+                                  th, tw, p, kh, kw, h, w, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc), st)
+                    yield idx, unfold_ipt_to_rgb(dct2_inv_fold(y_hi, y_lo, kh, kw, h, w), dc, h, w)
+                    continue
+                if self.dct_impl in ("tc", "tc_plain"):
                     ld = _round8(kw)
                     y_hi = torch.empty((n, C, kh, ld), dtype=torch.float16, device=dev)
                     y_lo = torch.empty_like(y_hi)

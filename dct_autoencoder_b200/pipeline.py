@@ -69,7 +69,7 @@ class TransformPipeline:
         """True when PatchNorm + LFQ can run inside the pack / un-patchify kernels (projection-free
         LFQ in eval mode, frozen fp32 statistics, tensor-core DCT path)."""
         fe = self.extractor
-        return (fe.dct_impl == "tc" and not fe._hooks_overridden("_transform_image_in")
+        return (fe.dct_impl in ("tc", "tc_plain") and not fe._hooks_overridden("_transform_image_in")
                 and not fe._hooks_overridden("_transform_image_out")
                 and fe._lfq_fusable(self.norm, self.quantizer))
 

@@ -368,3 +368,153 @@ def idct2_truncated_tc(y: torch.Tensor, h: int, w: int):
         _lib.call("dcta_split_coef_planes", _lib.ptr(y), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc), n_planes, kh, kw,
                   ld, h, w, _lib.stream_ptr(y.device))
     return dct2_inv_tc(hi, lo, dc, kw, h, w)
+
+
+# ----------------------------------------------------------------------------------------------
+# folded tensor-core DCT path (half the multiply-adds) -- see csrc/dct_fold.cu
+# ----------------------------------------------------------------------------------------------
+_FOLD_CACHE = {}
+
+
+def fold_ok(h: int, w: int, kh: int, kw: int) -> bool:
+    """True if the folded path takes these sizes (h, w multiples of 16; kh, kw even; basis fits in shared memory)."""
+    return bool(_lib.load().dcta_fold_supported(int(h), int(w), int(kh), int(kw)))
+
+
+def fold_basis(n: int, k: int, device, transposed: bool):
+    """fp16 hi/lo planes of the folded orthonormal DCT-II basis: group g holds the rows of parity g,
+    C_n[2j+g, :n/2] * 2^10.
+
+    forward  (transposed=False): (2, k/2, n/2); row 0 of group 0 (the constant 1/sqrt(n)) is stored as exactly 32;
+             also returns the fp32 (2, k/2) factors that undo the scaling.
+    inverse  (transposed=True):  (2, n/2, round8(k/2)) = the transposes; row_scale None."""
+    device = torch.device(device)
+    key = (n, k, transposed, device.type, device.index)
+    hit = _FOLD_CACHE.get(key)
+    if hit is not None:
+        return hit
+    k2, n2 = k // 2, n // 2
+    q = np.arange(k, dtype=np.float64)[:, None]
+    m = np.arange(n2, dtype=np.float64)[None, :]
+    c = np.cos(np.pi * (2 * m + 1) * q / (2 * n)) * math.sqrt(2.0 / n)
+    c[0, :] = math.sqrt(1.0 / n)
+    groups = np.stack([c[0::2], c[1::2]])            # (2, k/2, n/2)
+    if not transposed:
+        s = groups * _SCALE_BASIS
+        s[0, 0, :] = 32.0
+        rs = np.full((2, k2), 1.0 / _SCALE_BASIS, np.float64)
+        rs[0, 0] = math.sqrt(1.0 / n) / 32.0
+        row_scale = torch.from_numpy(rs.astype(np.float32)).to(device)
+    else:
+        ld = _round8(k2)
+        s = np.zeros((2, n2, ld), np.float64)
+        s[:, :, :k2] = np.transpose(groups * _SCALE_BASIS, (0, 2, 1))
+        row_scale = None
+    hi, lo = _split_host(s)
+    out = (torch.from_numpy(hi).to(device), torch.from_numpy(lo).to(device), row_scale)
+    _FOLD_CACHE[key] = out
+    return out
+
+
+def rgb_to_ipt_fold(x: torch.Tensor):
+    """util.py:70-82 fused with centring, the 2-D fold and the operand split: (b, 3, h, w) fp32 RGB ->
+    quadrants (2, 2, b*3, h/2, w/2) fp16 hi/lo (scale 2^6) + dc (b*3,)."""
+    b, c, h, w = x.shape
+    hi = torch.empty((2, 2, b * 3, h // 2, w // 2), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    dc = torch.empty(b * 3, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(b * 3 * 33, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dcta_rgb_to_ipt_fold", _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc), _lib.ptr(scratch),
+                  b, h, w, _M_RGB2LMS, _M_IPT, _lib.stream_ptr(x.device))
+    return hi, lo, dc
+
+
+def fold_planes(x: torch.Tensor):
+    """fp32 planes (..., h, w) -> centred folded quadrants (2, 2, n_planes, h/2, w/2) hi/lo + dc."""
+    x = x.contiguous()
+    h, w = x.shape[-2:]
+    n_planes = x.numel() // (h * w)
+    hi = torch.empty((2, 2, n_planes, h // 2, w // 2), dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    dc = torch.empty(n_planes, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(n_planes * 33, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dcta_fold_planes", _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc), _lib.ptr(scratch),
+                  n_planes, h, w, _lib.stream_ptr(x.device))
+    return hi, lo, dc
+
+
+def dct2_fwd_fold(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: Optional[torch.Tensor], kh: int, kw: int,
+                  tile_p: int = 0, channels: int = 1, out_shape=None):
+    """Truncated forward DCT from folded quadrants (2, 2, n_planes, h/2, w/2)."""
+    n_planes, h2, w2 = xq_hi.shape[-3:]
+    h, w = 2 * h2, 2 * w2
+    dev = xq_hi.device
+    bw_hi, bw_lo, rs_w = fold_basis(w, kw, dev, False)
+    bh_hi, bh_lo, rs_h = fold_basis(h, kh, dev, False)
+    work_hi = torch.empty((2, n_planes, kw, h2), dtype=torch.float16, device=dev)
+    work_lo = torch.empty_like(work_hi)
+    if tile_p:
+        y = torch.empty((n_planes // channels, kh // tile_p, kw // tile_p, channels, tile_p * tile_p),
+                        dtype=torch.float32, device=dev)
+    else:
+        y = torch.empty((out_shape or (n_planes,)) + (kh, kw), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_dct2_fwd_fold", _lib.ptr(xq_hi), _lib.ptr(xq_lo), _lib.ptr(dc), _lib.ptr(bw_hi),
+                  _lib.ptr(bw_lo), _lib.ptr(rs_w), _lib.ptr(bh_hi), _lib.ptr(bh_lo), _lib.ptr(rs_h), _lib.ptr(work_hi),
+                  _lib.ptr(work_lo), _lib.ptr(y), n_planes, h, w, kh, kw, tile_p, channels, _lib.stream_ptr(dev))
+    return y
+
+
+def dct2_inv_fold(yq_hi: torch.Tensor, yq_lo: torch.Tensor, kh: int, kw: int, h: int, w: int) -> torch.Tensor:
+    """Folded coefficient quadrants (2, 2, n_planes, kh/2, round8(kw/2)) -> quadrant transforms
+    z (4, n_planes, h/2, w/2) fp32 (to be un-folded by ``unfold_ipt_to_rgb`` / ``unfold_planes``)."""
+    n_planes = yq_hi.shape[2]
+    dev = yq_hi.device
+    bwt_hi, bwt_lo, _ = fold_basis(w, kw, dev, True)
+    bht_hi, bht_lo, _ = fold_basis(h, kh, dev, True)
+    ldi = _round8(kh // 2)
+    work_hi = torch.empty((2, 2, n_planes, w // 2, ldi), dtype=torch.float16, device=dev)
+    work_lo = torch.empty_like(work_hi)
+    z = torch.empty((4, n_planes, h // 2, w // 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_dct2_inv_fold", _lib.ptr(yq_hi), _lib.ptr(yq_lo), _lib.ptr(bwt_hi), _lib.ptr(bwt_lo),
+                  _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z),
+                  n_planes, h, w, kh, kw, _lib.stream_ptr(dev))
+    return z
+
+
+def unfold_ipt_to_rgb(z: torch.Tensor, dc: Optional[torch.Tensor], h: int, w: int) -> torch.Tensor:
+    """Final butterfly of the folded inverse fused with util.py:85-97: z (4, n_img*3, h/2, w/2) -> RGB (n_img, 3, h, w)."""
+    n_img = z.shape[1] // 3
+    rgb = torch.empty((n_img, 3, h, w), dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.call("dcta_unfold_ipt_to_rgb", _lib.ptr(z), _lib.ptr(dc), _lib.ptr(rgb), n_img, h, w, _M_IPT_INV,
+                  _M_LMS2RGB, _lib.stream_ptr(z.device))
+    return rgb
+
+
+def dct2_truncated_fold(x: torch.Tensor, kh: int, kw: int, tile_p: int = 0, channels: int = 1):
+    """fp32 planes (..., h, w) -> truncated DCT through the folded tensor-core path."""
+    hi, lo, dc = fold_planes(x)
+    return dct2_fwd_fold(hi, lo, dc, kh, kw, tile_p, channels, out_shape=tuple(x.shape[:-2]))
+
+
+def idct2_truncated_fold(y: torch.Tensor, h: int, w: int):
+    """fp32 coefficient planes (..., kh, kw) -> samples (..., h, w) through the folded tensor-core path."""
+    y = y.contiguous()
+    kh, kw = y.shape[-2:]
+    n_planes = y.numel() // (kh * kw)
+    ldq = _round8(kw // 2)
+    hi = torch.empty((2, 2, n_planes, kh // 2, ldq), dtype=torch.float16, device=y.device)
+    lo = torch.empty_like(hi)
+    dc = torch.empty(n_planes, dtype=torch.float32, device=y.device)
+    x = torch.empty(y.shape[:-2] + (h, w), dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        st = _lib.stream_ptr(y.device)
+        _lib.call("dcta_fold_coef_planes", _lib.ptr(y), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc), n_planes, kh, kw,
+                  h, w, st)
+        z = dct2_inv_fold(hi, lo, kh, kw, h, w)
+        _lib.call("dcta_unfold_planes", _lib.ptr(z), _lib.ptr(dc), _lib.ptr(x), n_planes, h, w, st)
+    return x

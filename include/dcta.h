@@ -118,6 +118,55 @@ int dcta_dct2_inv_tc(const void* y_hi, const void* y_lo, const float* dc, const 
                      void* work_lo, float* x, int64_t n_planes, int h, int w, int kh, int kw,
                      int64_t ld_kh, int64_t ld_kw, void* stream);
 
+/* ------------------------------------------------------------------ folded DCT / IDCT ----- */
+/* The DCT-II basis is (anti)symmetric about the centre of the signal, so the 2-D transform of an
+ * h x w plane (UT:333-338, called at FE:140 / FE:149) splits into four independent transforms of
+ * (h/2, w/2) "quadrants" xq[b][a] = the four sign combinations of the mirrored samples
+ * x[h',w'], x[h',w-1-w'], x[h-1-h',w'], x[h-1-h',w-1-w']:   Y[2i+a, 2j+b] = CH[2i+a,:h/2] . xq[b][a] . CW[2j+b,:w/2]^T
+ * -- half the multiply-adds.  Requirements: h, w multiples of 16; kh, kw even.
+ * dcta_fold_supported: 1 if these sizes can take the folded path (else use the dcta_*_tc entry points). */
+int dcta_fold_supported(int h, int w, int kh, int kw);
+/* UT:70-82 rgb_to_ipt + centring + fold + fp16 hi/lo split: rgb (n_img, 3, h, w) ->
+ * xq_hi/lo (2, 2, n_img*3, h/2, w/2) [b][a][plane] scale 2^6;  dc, sums_scratch as dcta_rgb_to_ipt_split. */
+int dcta_rgb_to_ipt_fold(const float* rgb, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
+                         int64_t n_img, int h, int w, const float* m_rgb2lms_host, const float* m_ipt_host,
+                         void* stream);
+/* The same for plain fp32 planes x (n_planes, h, w). */
+int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
+                     int64_t n_planes, int h, int w, void* stream);
+/* Forward truncated DCT from the quadrants; output contract of dcta_dct2_fwd (planes or token grid).
+ *   bw_hi/lo (2, kw/2, w/2): CW[2j+b, w'] * 2^10, group b (row 0 of group 0 stored as the constant 32);
+ *   rs_w (2, kw/2) the factors undoing those scales;  bh_hi/lo (2, kh/2, h/2), rs_h likewise (group a);
+ *   work_hi/lo (2, n_planes, kw, h/2) scratch. */
+int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
+                       const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
+                       const float* rs_h, void* work_hi, void* work_lo, float* y, int64_t n_planes, int h,
+                       int w, int kh, int kw, int tile_p, int channels, void* stream);
+/* FE:635-653 un-patchify into folded coefficient quadrants yq_hi/lo (2, 2, n_img*channels, rows/2, ldq)
+ * [b][a][plane][i][j] = Y[2i+a, 2j+b] * 2^4, ldq = round8(cols/2); DC moved to dc as in dcta_unpatchify_split. */
+int dcta_unpatchify_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
+                         int channels_n, int th, int tw, int p, int rows, int cols, int out_h, int out_w,
+                         void* yq_hi, void* yq_lo, float* dc, void* stream);
+/* The same from LFQ codes (contract of dcta_decode_codes_split). */
+int dcta_decode_codes_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel,
+                           int64_t n_img, int channels_n, int th, int tw, int p, int rows, int cols, int out_h,
+                           int out_w, const float* median, const float* b, int H, int W, float eps, int c,
+                           int d, float scale, void* yq_hi, void* yq_lo, float* dc, void* stream);
+/* fp32 coefficient planes y (n_planes, kh, kw) -> folded quadrants. */
+int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, float* dc, int64_t n_planes, int kh,
+                          int kw, int out_h, int out_w, void* stream);
+/* Inverse truncated DCT of the quadrants: z (4, n_planes, h/2, w/2) fp32, index b*2+a.
+ *   bwt_hi/lo (2, w/2, ldq): (CW[2j+b, w'] * 2^10)^T, bht_hi/lo (2, h/2, ldi), ldi = round8(kh/2);
+ *   work_hi/lo (2, 2, n_planes, w/2, ldi) scratch. */
+int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const void* bwt_hi, const void* bwt_lo,
+                       const void* bht_hi, const void* bht_lo, void* work_hi, void* work_lo, float* z,
+                       int64_t n_planes, int h, int w, int kh, int kw, void* stream);
+/* Final butterfly (+ the DC constant dc[plane], nullable) fused with UT:85-97 ipt_to_rgb: rgb (n_img, 3, h, w). */
+int dcta_unfold_ipt_to_rgb(const float* z, const float* dc, float* rgb, int64_t n_img, int h, int w,
+                           const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream);
+/* Final butterfly alone: x (n_planes, h, w). */
+int dcta_unfold_planes(const float* z, const float* dc, float* x, int64_t n_planes, int h, int w, void* stream);
+
 /* FE:374-380 rearrange "c (h p1) (w p2) -> (h w) c (p1 p2)" with the max_patch clip of FE:393-394,
  * for coefficient planes produced by a caller-supplied transform:
  *   planes (n_img, channels, rows, cols) -> tiles (n_img, th, tw, channels, p*p); th*p<=rows, tw*p<=cols. */
