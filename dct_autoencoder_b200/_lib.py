@@ -46,7 +46,8 @@ SIGNATURES = {
     "dcta_fold_supported": [c_int, c_int, c_int, c_int],
     "dcta_rgb_to_ipt_fold": [P, P, P, P, P, c_int64, c_int, c_int, P, P, P],
     "dcta_fold_planes": [P, P, P, P, P, c_int64, c_int, c_int, P],
-    "dcta_dct2_fwd_fold": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "dcta_dct2_fwd_fold": [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "dcta_sort_tokens_maxabs": [P, P, P, c_int64, c_int, c_int, c_int, c_float, P, P],
     "dcta_unpatchify_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
     "dcta_decode_codes_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P],
@@ -102,7 +103,7 @@ KERNELS_PER_CALL = {
     "dcta_pack_codes_lfq": 1, "dcta_decode_codes_split": 1,
     "dcta_fold_supported": 0, "dcta_rgb_to_ipt_fold": 3, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
     "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 1, "dcta_fold_coef_planes": 1, "dcta_dct2_inv_fold": 2,
-    "dcta_unfold_ipt_to_rgb": 1, "dcta_unfold_planes": 1,
+    "dcta_unfold_ipt_to_rgb": 1, "dcta_unfold_planes": 1, "dcta_sort_tokens_maxabs": 1,
 }
 launch_count = 0
 

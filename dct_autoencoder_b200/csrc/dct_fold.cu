@@ -59,11 +59,90 @@ struct FoldEpi {
     const float* basis_scale;    // optional (2, n_valid) per-basis-row factors
     const float* dc;             // optional per-item constant added to (group 0, basis row 0, row-in-item 0)
     int p, channels, tiles_h, tiles_w;   // mode 2
+    float* maxabs;               // mode 2, optional: (n_img, tiles_h, tiles_w, channels) max |coefficient| of every token,
+                                 // accumulated with atomicMax on the bit pattern (the buffer must start at zero)
 };
 
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 256 (pair), N = n_tile
 __device__ __forceinline__ uint32_t fold_idesc(int n_tile) {
     return (1u << 4) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+// Stores at base + 32-bit element offset: one IMAD.WIDE + one STG (the compiler would otherwise rebuild the
+// 64-bit address from the kernel parameters for every column).
+__device__ __forceinline__ void st_h16(uint64_t base, uint32_t off, __half v) {
+    asm volatile("{\n.reg .u64 a;\nmad.wide.u32 a, %1, 2, %0;\nst.global.b16 [a], %2;\n}" ::"l"(base), "r"(off),
+                 "h"(__half_as_ushort(v)) : "memory");
+}
+__device__ __forceinline__ void st_f32(uint64_t base, uint32_t off, float v) {
+    asm volatile("{\n.reg .u64 a;\nmad.wide.u32 a, %1, 4, %0;\nst.global.f32 [a], %2;\n}" ::"l"(base), "r"(off), "f"(v)
+                 : "memory");
+}
+
+// max over the lanes that share `key` (contiguous lane ranges); valid in the first lane of every range
+__device__ __forceinline__ float segmented_max(float m, uint32_t key, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float other = __shfl_down_sync(0xffffffffu, m, o);
+        const uint32_t okey = __shfl_down_sync(0xffffffffu, key, o);
+        if (lane + o < 32 && okey == key) m = fmaxf(m, other);
+    }
+    return m;
+}
+
+struct ScoreCtx {
+    const int32_t* col_grp;   // per column: tile-row index, bit 31 set where a run of columns of one tile row ends
+    unsigned* dst;            // maxabs + token index of this accumulator row at tile row 0 (leaders only)
+    uint32_t key;             // token column identity of this lane (lanes of one token are contiguous)
+    int tile_row_stride;      // tokens between tile rows: tiles_w * channels
+    bool leader;              // first lane of its key range, row valid
+    int lane;
+};
+
+// One 32-column chunk of an accumulator row: scale, (split,) store each column at its table offset.
+// GUARD: offsets < 0 mark columns past the end of the basis (only the last chunk of a slice can have them).
+// SCORE (fp32 token grid): also reduce max |value| per token (feature_extraction_dct_autoencoder.py:409).
+template <int MODE, bool GUARD, bool SCORE>
+__device__ __forceinline__ void store_chunk(const uint32_t (&rr)[32], const int32_t* col_off, const float* col_scale,
+                                            uint64_t p_hi, uint64_t p_lo, uint64_t p_f32, float dcv, const ScoreCtx& sc_) {
+    float m = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const int4 off = *reinterpret_cast<const int4*>(col_off + j);
+        const float4 sc = *reinterpret_cast<const float4*>(col_scale + j);
+        float v0 = __uint_as_float(rr[j]) * sc.x, v1 = __uint_as_float(rr[j + 1]) * sc.y;
+        float v2 = __uint_as_float(rr[j + 2]) * sc.z, v3 = __uint_as_float(rr[j + 3]) * sc.w;
+        if (j == 0) v0 += dcv;
+        if (MODE == 0) {
+            const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
+            const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
+            if (!GUARD || off.x >= 0) { st_h16(p_hi, off.x, __low2half(h01)); st_h16(p_lo, off.x, __low2half(l01)); }
+            if (!GUARD || off.y >= 0) { st_h16(p_hi, off.y, __high2half(h01)); st_h16(p_lo, off.y, __high2half(l01)); }
+            if (!GUARD || off.z >= 0) { st_h16(p_hi, off.z, __low2half(h23)); st_h16(p_lo, off.z, __low2half(l23)); }
+            if (!GUARD || off.w >= 0) { st_h16(p_hi, off.w, __high2half(h23)); st_h16(p_lo, off.w, __high2half(l23)); }
+        } else {
+            if (!GUARD || off.x >= 0) st_f32(p_f32, off.x, v0);
+            if (!GUARD || off.y >= 0) st_f32(p_f32, off.y, v1);
+            if (!GUARD || off.z >= 0) st_f32(p_f32, off.z, v2);
+            if (!GUARD || off.w >= 0) st_f32(p_f32, off.w, v3);
+        }
+        if (SCORE) {
+            const int4 grp = *reinterpret_cast<const int4*>(sc_.col_grp + j);
+            const float vv[4] = {v0, v1, v2, v3};
+            const int gg[4] = {grp.x, grp.y, grp.z, grp.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                m = fmaxf(m, fabsf(vv[u]));
+                if (gg[u] < 0) {          // warp-uniform: the run of this tile row ends here
+                    const float mm = segmented_max(m, sc_.key, sc_.lane);
+                    if (sc_.leader) atomicMax(sc_.dst + (gg[u] & 0x7fffffff) * sc_.tile_row_stride, __float_as_uint(mm));
+                    m = 0.0f;
+                }
+            }
+        }
+    }
 }
 
 template <int MODE>   // 0: fp16 hi/lo output, 1: fp32 output (plain or token grid)
@@ -80,6 +159,8 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) int32_t col_off[256];
     __shared__ __align__(16) float col_scale[256];
+    __shared__ __align__(16) int32_t col_grp[256];
+    __shared__ __align__(16) int32_t neg_off[32];
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* basis_hi = smem;
@@ -129,7 +210,16 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
         col_off[n] = off;
         col_scale[n] = sc;
+        int32_t grp_v = 0;
+        if (ep.mode == 2 && n < n_lim) {
+            const int line = (nt * g.n_tile + n) * ep.col_mul + grp * ep.col_add;
+            const int th = line / ep.p;
+            const bool ends = (n == n_lim - 1) || ((n & 31) == 31) || ((line + ep.col_mul) / ep.p != th);
+            grp_v = th | (ends ? (int32_t)0x80000000 : 0);
+        }
+        col_grp[n] = grp_v;
     }
+    if (threadIdx.x < 32) neg_off[threadIdx.x] = -1;
     if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
     tc_fence_before();
     __syncthreads();
@@ -210,14 +300,28 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const bool row_ok = r < g.rows_per_seg;
             const int item = r / ep.rows_per_item, rin = r - item * ep.rows_per_item;
             int64_t base;
+            ScoreCtx sctx{};
             if (ep.mode == 2) {
                 const int img = item / ep.channels, ch = item - img * ep.channels;
                 const int tw = rin / ep.p, pj = rin - tw * ep.p;
-                base = (((int64_t)img * ep.tiles_h * ep.tiles_w + tw) * ep.channels + ch) * (ep.p * ep.p) + pj;
+                const int64_t tok0 = ((int64_t)img * ep.tiles_h * ep.tiles_w + tw) * ep.channels + ch;   // token at tile row 0
+                base = tok0 * (ep.p * ep.p) + pj;
+                if (ep.maxabs != nullptr) {
+                    sctx.col_grp = col_grp;
+                    sctx.key = row_ok ? (uint32_t)tok0 : 0xffffffffu;
+                    const uint32_t prev = __shfl_up_sync(0xffffffffu, sctx.key, 1);
+                    sctx.leader = row_ok && (lane == 0 || prev != sctx.key);
+                    sctx.dst = reinterpret_cast<unsigned*>(ep.maxabs) + tok0;
+                    sctx.tile_row_stride = ep.tiles_w * ep.channels;
+                    sctx.lane = lane;
+                }
             } else {
                 base = (int64_t)seg * ep.seg_stride + (int64_t)item * ep.item_stride + rin;
             }
             const float dcv = (dc_slice && row_ok && rin == 0) ? __ldg(ep.dc + item) : 0.0f;
+            const uint64_t p_hi = reinterpret_cast<uint64_t>(ep.out_hi + base);
+            const uint64_t p_lo = reinterpret_cast<uint64_t>(ep.out_lo + base);
+            const uint64_t p_f32 = reinterpret_cast<uint64_t>(ep.out_f32 + base);
             const int acc = tcount & 1;
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
             tc_fence_after();
@@ -227,7 +331,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             if (last < chalf) {                              // nothing to read: release immediately
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+                if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
             }
 #pragma unroll 1
             for (int c = chalf; c < n_chunks; c += 2) {
@@ -237,33 +341,21 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 if (c == last) {                             // accumulator read out by this warp: hand it back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+                    if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+                }
+                const float dcc = c == 0 ? dcv : 0.0f;
+                if (MODE == 1 && ep.maxabs != nullptr) {
+                    // every lane takes part in the shuffles of the score reduction: rows past the end store nothing
+                    // (their offsets are replaced by the guard value) and contribute zeros
+                    ScoreCtx sc2 = sctx;
+                    sc2.col_grp = &col_grp[c * 32];
+                    store_chunk<MODE, true, true>(rr, row_ok ? &col_off[c * 32] : neg_off, &col_scale[c * 32], p_hi, p_lo,
+                                                  p_f32, dcc, sc2);
+                    continue;
                 }
                 if (!row_ok) continue;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = c * 32 + j;
-                    const int4 off = *reinterpret_cast<const int4*>(&col_off[n]);
-                    const float4 sc = *reinterpret_cast<const float4*>(&col_scale[n]);
-                    float v0 = __uint_as_float(rr[j]) * sc.x, v1 = __uint_as_float(rr[j + 1]) * sc.y;
-                    float v2 = __uint_as_float(rr[j + 2]) * sc.z, v3 = __uint_as_float(rr[j + 3]) * sc.w;
-                    if (j == 0 && c == 0) v0 += dcv;
-                    if (MODE == 0) {
-                        const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
-                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                        const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
-                        const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
-                        if (off.x >= 0) { ep.out_hi[base + off.x] = __low2half(h01); ep.out_lo[base + off.x] = __low2half(l01); }
-                        if (off.y >= 0) { ep.out_hi[base + off.y] = __high2half(h01); ep.out_lo[base + off.y] = __high2half(l01); }
-                        if (off.z >= 0) { ep.out_hi[base + off.z] = __low2half(h23); ep.out_lo[base + off.z] = __low2half(l23); }
-                        if (off.w >= 0) { ep.out_hi[base + off.w] = __high2half(h23); ep.out_lo[base + off.w] = __high2half(l23); }
-                    } else {
-                        if (off.x >= 0) ep.out_f32[base + off.x] = v0;
-                        if (off.y >= 0) ep.out_f32[base + off.y] = v1;
-                        if (off.z >= 0) ep.out_f32[base + off.z] = v2;
-                        if (off.w >= 0) ep.out_f32[base + off.w] = v3;
-                    }
-                }
+                if (c * 32 + 32 <= n_lim) store_chunk<MODE, false, false>(rr, &col_off[c * 32], &col_scale[c * 32], p_hi, p_lo, p_f32, dcc, sctx);
+                else store_chunk<MODE, true, false>(rr, &col_off[c * 32], &col_scale[c * 32], p_hi, p_lo, p_f32, dcc, sctx);
             }
         }
     }
@@ -561,9 +653,11 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ z
 // feature_extraction_dct_autoencoder.py:635-653 un-patchify (CODES = false) or its fusion with
 // lfq.indices_to_codes + PatchNorm.inverse_norm (CODES = true; lfq.py:105-134, patchnorm.py:167-177),
 // writing the folded coefficient quadrants yq[b][a][plane][i][j] = Y[2i+a, 2j+b] as scaled fp16 hi/lo.
-// One CTA per tile-row of one plane; a thread owns 8 consecutive coefficient columns (4 per column parity).
+// One CTA per tile-row of one plane (p coefficient rows).  Phase 1 evaluates the p x 2*ldq values with the
+// lanes of a warp on CONSECUTIVE columns (token rows, code words and PatchNorm tables are read coalesced) into
+// shared memory; phase 2 de-interleaves the column parities and writes 8-byte hi/lo groups.
 template <bool CODES>
-__global__ void __launch_bounds__(128) unpatchify_fold_kernel(const float* __restrict__ patches,
+__global__ void __launch_bounds__(256) unpatchify_fold_kernel(const float* __restrict__ patches,
                                                               const int64_t* __restrict__ codes,
                                                               const int32_t* __restrict__ slot_map,
                                                               const int32_t* __restrict__ img_sel, int C, int th, int tw,
@@ -571,7 +665,9 @@ __global__ void __launch_bounds__(128) unpatchify_fold_kernel(const float* __res
                                                               LfqNormParams q, __half* __restrict__ hi,
                                                               __half* __restrict__ lo, float* __restrict__ dc,
                                                               float dc_factor, float scale) {
+    extern __shared__ float vals[];                 // [p][2 * ldq]
     const int z = p * p;
+    const int wide = 2 * ldq;
     const int tile_rows = rows / p;
     const unsigned id = blockIdx.x;
     const int ty = (int)(id % (unsigned)tile_rows);
@@ -582,69 +678,63 @@ __global__ void __launch_bounds__(128) unpatchify_fold_kernel(const float* __res
     const bool row_in = ty < th;
     const int32_t* smap = slot_map + ((img * C + c) * th + (row_in ? ty : 0)) * tw;
     const int64_t plane = (int64_t)sel * C + c;
-    const int rows2 = rows >> 1;
-    const int64_t quad = n_planes * rows2 * (int64_t)ldq;          // elements of one quadrant array
     const float* med_row = nullptr;
     const float* b_row = nullptr;
     if (CODES) {
         med_row = q.median + (((int64_t)c * q.H + ty) * q.W) * q.z;
         b_row = q.b + (((int64_t)c * q.H + ty) * q.W) * q.z;
     }
-    for (int xv = threadIdx.x; xv < ldq / 4; xv += blockDim.x) {
-        const int x0 = xv * 8;
-        int32_t slot[8];
-        int px[8], txs[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int x = x0 + j;
-            const int tx = x / p;
-            txs[j] = tx;
-            px[j] = x - tx * p;
-            slot[j] = (row_in && tx < tw && x < cols) ? __ldg(smap + tx) : -1;
+    const bool row_codebook = CODES && (q.d == p);       // one codebook per patch row (14 x 14 bits at patch 14)
+    for (int x = threadIdx.x; x < wide; x += blockDim.x) {
+        const int tx = x / p, px = x - tx * p;
+        const int32_t slot = (row_in && tx < tw && x < cols) ? __ldg(smap + tx) : -1;
+        if (slot < 0) {
+            for (int py = 0; py < p; ++py) vals[py * wide + x] = 0.0f;
+            if (ty == 0 && x == 0) dc[plane] = 0.0f;
+            continue;
         }
+        const float* src = CODES ? nullptr : patches + (int64_t)slot * z + px;
+        const int64_t* cw = CODES ? codes + (int64_t)slot * q.c : nullptr;
+        const int pe0 = tx * z + px;
         for (int py = 0; py < p; ++py) {
-            float v[8];
-            long long code = 0;
-            int code_cb = -1;
-            int32_t code_slot = -1;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float val = 0.0f;
-                if (slot[j] >= 0) {
-                    const int e = py * p + px[j];
-                    if (CODES) {
-                        const int cb = e / q.d, bi = e - cb * q.d;
-                        if (cb != code_cb || slot[j] != code_slot) {
-                            code = __ldg(codes + (int64_t)slot[j] * q.c + cb);
-                            code_cb = cb;
-                            code_slot = slot[j];
-                        }
-                        const float qv = ((code >> (q.d - 1 - bi)) & 1) ? q.scale : -q.scale;       // lfq.py:118-120
-                        const int pe = txs[j] * q.z + e;
-                        const float sd = __fadd_rn(__fmul_rn(__ldg(b_row + pe), kSqrt2f), q.eps);
-                        val = __fadd_rn(__fmul_rn(qv, sd), __ldg(med_row + pe));                      // patchnorm.py:177
-                    } else {
-                        val = __ldg(patches + (int64_t)slot[j] * z + e);
-                    }
-                }
-                if (ty == 0 && py == 0 && x0 + j == 0) {
-                    dc[plane] = val * dc_factor;
-                    val = 0.0f;
-                }
-                v[j] = val;
+            float val;
+            if (CODES) {
+                const int e = py * p + px;
+                int cb, bi;
+                if (row_codebook) { cb = py; bi = px; }
+                else { cb = e / q.d; bi = e - cb * q.d; }
+                const long long code = __ldg(cw + cb);
+                const float qv = ((code >> (q.d - 1 - bi)) & 1) ? q.scale : -q.scale;           // lfq.py:118-120
+                const float sd = __fadd_rn(__fmul_rn(__ldg(b_row + pe0 + py * p), kSqrt2f), q.eps);
+                val = __fadd_rn(__fmul_rn(qv, sd), __ldg(med_row + pe0 + py * p));               // patchnorm.py:177
+            } else {
+                val = __ldg(src + py * p);
             }
-            const int kh = ty * p + py;
-            const int a = kh & 1, ii = kh >> 1;
-            const int64_t o = ((a * n_planes + plane) * rows2 + ii) * (int64_t)ldq + xv * 4;   // + b * 2 * quad
-            const float ev[4] = {v[0], v[2], v[4], v[6]}, od[4] = {v[1], v[3], v[5], v[7]};
-            uint2 vh, vl;
-            split16x4(ev, scale, vh, vl);
-            *reinterpret_cast<uint2*>(hi + o) = vh;
-            *reinterpret_cast<uint2*>(lo + o) = vl;
-            split16x4(od, scale, vh, vl);
-            *reinterpret_cast<uint2*>(hi + 2 * quad + o) = vh;
-            *reinterpret_cast<uint2*>(lo + 2 * quad + o) = vl;
+            if (ty == 0 && py == 0 && x == 0) {
+                dc[plane] = val * dc_factor;
+                val = 0.0f;
+            }
+            vals[py * wide + x] = val;
         }
+    }
+    __syncthreads();
+    const int rows2 = rows >> 1, nxv = ldq >> 2;
+    const int64_t quad = n_planes * rows2 * (int64_t)ldq;          // elements of one quadrant array
+    for (int it = threadIdx.x; it < p * nxv; it += blockDim.x) {
+        const int py = it / nxv, xv = it - py * nxv;
+        const float4 v0 = *reinterpret_cast<const float4*>(&vals[py * wide + xv * 8]);
+        const float4 v1 = *reinterpret_cast<const float4*>(&vals[py * wide + xv * 8 + 4]);
+        const int kh = ty * p + py;
+        const int a = kh & 1, ii = kh >> 1;
+        const int64_t o = ((a * n_planes + plane) * rows2 + ii) * (int64_t)ldq + xv * 4;   // + b * 2 * quad
+        const float ev[4] = {v0.x, v0.z, v1.x, v1.z}, od[4] = {v0.y, v0.w, v1.y, v1.w};
+        uint2 vh, vl;
+        split16x4(ev, scale, vh, vl);
+        *reinterpret_cast<uint2*>(hi + o) = vh;
+        *reinterpret_cast<uint2*>(lo + o) = vl;
+        split16x4(od, scale, vh, vl);
+        *reinterpret_cast<uint2*>(hi + 2 * quad + o) = vh;
+        *reinterpret_cast<uint2*>(lo + 2 * quad + o) = vl;
     }
 }
 
@@ -727,10 +817,11 @@ extern "C" int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float*
 //   bh: (2, kh/2, h/2) for the height transform, group = row parity a; work: (2, n_planes, kw, h/2) hi/lo
 extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
                                   const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
-                                  const float* rs_h, void* work_hi, void* work_lo, float* y, int64_t n_planes, int h,
-                                  int w, int kh, int kw, int tile_p, int channels, void* stream) {
+                                  const float* rs_h, void* work_hi, void* work_lo, float* y, float* maxabs,
+                                  int64_t n_planes, int h, int w, int kh, int kw, int tile_p, int channels, void* stream) {
     DCTA_REQUIRE(xq_hi && xq_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && y,
                  "dct2_fwd_fold: null pointer");
+    DCTA_REQUIRE(maxabs == nullptr || tile_p > 0, "dct2_fwd_fold: maxabs needs the token-grid output");
     DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_fwd_fold: needs h, w multiples of 16 and even kh <= h, kw <= w");
     if (tile_p > 0)
         DCTA_REQUIRE(channels > 0 && kh % tile_p == 0 && kw % tile_p == 0 && n_planes % channels == 0,
@@ -755,6 +846,10 @@ extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const fl
     e2.alpha = 1.0f / kFScaleP; e2.basis_scale = rs_h; e2.dc = dc;
     if (tile_p > 0) {
         e2.mode = 2; e2.p = tile_p; e2.channels = channels; e2.tiles_h = kh / tile_p; e2.tiles_w = kw / tile_p;
+        e2.maxabs = maxabs;
+        if (maxabs)
+            cudaMemsetAsync(maxabs, 0, sizeof(float) * (n_planes / channels) * e2.tiles_h * e2.tiles_w * channels,
+                            as_stream(stream));
     } else {
         e2.mode = 1; e2.seg_stride = 0; e2.item_stride = (int64_t)kh * kw; e2.col_stride = kw;
     }
@@ -835,14 +930,23 @@ static int launch_unpatchify_fold(bool with_codes, const float* patches, const i
     DCTA_REQUIRE(n_rows_total < (1ll << 31), "%s: too many plane rows for one launch", who);
     const int ldq = (int)(ceil_div(cols / 2, 8) * 8);
     const float dcf = 1.0f / sqrtf((float)out_h * (float)out_w);
-    if (with_codes)
-        unpatchify_fold_kernel<true><<<(unsigned)n_rows_total, 128, 0, as_stream(stream)>>>(
-            patches, codes, slot_map, img_sel, C, th, tw, p, rows, cols, ldq, n_img * C, q, (__half*)yq_hi, (__half*)yq_lo,
-            dc, dcf, kFScaleY);
-    else
-        unpatchify_fold_kernel<false><<<(unsigned)n_rows_total, 128, 0, as_stream(stream)>>>(
-            patches, codes, slot_map, img_sel, C, th, tw, p, rows, cols, ldq, n_img * C, q, (__half*)yq_hi, (__half*)yq_lo,
-            dc, dcf, kFScaleY);
+    const int smem_bytes = p * 2 * ldq * (int)sizeof(float);
+    DCTA_REQUIRE(smem_bytes <= 200 * 1024, "%s: tile row of %d bytes does not fit in shared memory", who, smem_bytes);
+    cudaError_t e;
+    if (with_codes) {
+        e = cudaFuncSetAttribute(unpatchify_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess)
+            unpatchify_fold_kernel<true><<<(unsigned)n_rows_total, 256, smem_bytes, as_stream(stream)>>>(
+                patches, codes, slot_map, img_sel, C, th, tw, p, rows, cols, ldq, n_img * C, q, (__half*)yq_hi,
+                (__half*)yq_lo, dc, dcf, kFScaleY);
+    } else {
+        e = cudaFuncSetAttribute(unpatchify_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess)
+            unpatchify_fold_kernel<false><<<(unsigned)n_rows_total, 256, smem_bytes, as_stream(stream)>>>(
+                patches, codes, slot_map, img_sel, C, th, tw, p, rows, cols, ldq, n_img * C, q, (__half*)yq_hi,
+                (__half*)yq_lo, dc, dcf, kFScaleY);
+    }
+    if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return DCTA_ERR_LAUNCH; }
     return check_launch(who);
 }
 

@@ -112,9 +112,64 @@ __device__ __forceinline__ unsigned norm_sign_bit(float xv, float mv, float bv, 
     return y > 0.0f;
 }
 
-// Vectorised variant (z % 4 == 0, z <= 256, d <= 32): one warp per slot, 128-bit loads (one quad of
-// 4 elements per lane and pass), sign nibbles OR-reduced inside groups of 8 lanes into element-ordered
-// 32-bit words, codes cut out of the bit string with a funnel shift + bit reversal.
+// Vectorised variant (z % 4 == 0, z <= 256, d <= 32).  A warp takes 32 consecutive slots: the per-slot
+// metadata chain (segment search -> order -> token address; three dependent global loads) runs ONCE,
+// lane-parallel, and the bookkeeping outputs are written coalesced; then the 32 tokens are streamed two at
+// a time with 128-bit loads (one quad of 4 elements per lane and pass), sign nibbles OR-reduced inside
+// groups of 8 lanes into element-ordered 32-bit words, and the codes cut out of the bit string with a
+// funnel shift + bit reversal.
+struct TokenBits { unsigned w[2]; };
+
+__device__ __forceinline__ void load_token(const float4* src, const float4* ms, const float4* bs, int lane, int z4,
+                                           float4 (&xv)[2], float4 (&mv)[2], float4 (&bv)[2]) {
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int qd = lane + 32 * pass;
+        if (qd < z4) {
+            xv[pass] = src ? __ldg(src + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mv[pass] = __ldg(ms + qd);
+            bv[pass] = __ldg(bs + qd);
+        }
+    }
+}
+
+__device__ __forceinline__ TokenBits token_bits(const float4 (&xv)[2], const float4 (&mv)[2], const float4 (&bv)[2],
+                                                int lane, int z4, const LfqNormParams& q) {
+    TokenBits r;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        unsigned nib = 0;
+        if (lane + 32 * pass < z4)
+            nib = norm_sign_bit(xv[pass].x, mv[pass].x, bv[pass].x, q) | (norm_sign_bit(xv[pass].y, mv[pass].y, bv[pass].y, q) << 1) |
+                  (norm_sign_bit(xv[pass].z, mv[pass].z, bv[pass].z, q) << 2) | (norm_sign_bit(xv[pass].w, mv[pass].w, bv[pass].w, q) << 3);
+        unsigned v = nib << (4 * (lane & 7));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        r.w[pass] = v;          // lanes 8j .. 8j+7 hold elements 128*pass + 32*j .. +31 (bit = element & 31)
+    }
+    return r;
+}
+
+// lfq.py:187: code[cb] = bits [cb*d, cb*d + d) of the element-ordered string, first element = MSB
+__device__ __forceinline__ void write_codes(const TokenBits& tb, int lane, const LfqNormParams& q, unsigned dmask,
+                                            int64_t* __restrict__ dst) {
+    for (int cb0 = 0; cb0 < q.c; cb0 += 32) {
+        const int cb = min(cb0 + lane, q.c - 1);
+        const int e0 = cb * q.d;
+        const int k0 = e0 >> 5, k1 = min(k0 + 1, 7), sh = e0 & 31;
+        const unsigned a0 = __shfl_sync(0xffffffffu, tb.w[0], 8 * (k0 & 3));
+        const unsigned a1 = __shfl_sync(0xffffffffu, tb.w[1], 8 * (k0 & 3));
+        const unsigned b0 = __shfl_sync(0xffffffffu, tb.w[0], 8 * (k1 & 3));
+        const unsigned b1 = __shfl_sync(0xffffffffu, tb.w[1], 8 * (k1 & 3));
+        const unsigned wlo = (k0 >> 2) ? a1 : a0;
+        const unsigned whi = (k1 >> 2) ? b1 : b0;
+        const unsigned bits = __funnelshift_r(wlo, whi, sh) & dmask;      // LSB = first element
+        const unsigned code = __brev(bits) >> (32 - q.d);
+        if (cb0 + lane < q.c) dst[cb] = (int64_t)code;
+    }
+}
+
 __global__ void __launch_bounds__(256) pack_codes_vec_kernel(
     const float* __restrict__ tiles, const int32_t* __restrict__ order, const dcta_segment* __restrict__ segs,
     const int32_t* __restrict__ row_seg_start, int n_rows, int s, int tw, int channels, int n_tok_img,
@@ -126,75 +181,66 @@ __global__ void __launch_bounds__(256) pack_codes_vec_kernel(
     const int64_t total = (int64_t)n_rows * s;
     const int z4 = q.z >> 2;
     const unsigned dmask = q.d == 32 ? 0xffffffffu : ((1u << q.d) - 1u);
-    for (int64_t slot = warp0; slot < total; slot += n_warps) {
-        const int row = (int)(slot / s);
-        const int off = (int)(slot - (int64_t)row * s);
-        int lo = row_seg_start[row], hi = row_seg_start[row + 1];
-        int seg = -1;
-        if (hi - lo == 1) {                       // the common case: one image per row
-            seg = (off >= segs[lo].offset && off < segs[lo].offset + segs[lo].k) ? lo : -1;
-        } else {
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                const int so = segs[mid].offset;
-                if (off < so) hi = mid;
-                else if (off >= so + segs[mid].k) lo = mid + 1;
-                else { seg = mid; break; }
+    for (int64_t slot0 = warp0 * 32; slot0 < total; slot0 += n_warps * 32) {
+        // ---- metadata of slot0 + lane
+        const int64_t slot = slot0 + lane;
+        int64_t src_off = -1;          // element offset of the token in `tiles`, -1 = padding slot
+        int pid = 0;                   // PatchNorm position (pc * H + ph) * W + pw
+        if (slot < total) {
+            const int row = (int)(slot / s);
+            const int off = (int)(slot - (int64_t)row * s);
+            int lo = row_seg_start[row], hi = row_seg_start[row + 1];
+            int seg = -1;
+            if (hi - lo == 1) {                       // the common case: one image per row
+                seg = (off >= segs[lo].offset && off < segs[lo].offset + segs[lo].k) ? lo : -1;
+            } else {
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int so = segs[mid].offset;
+                    if (off < so) hi = mid;
+                    else if (off >= so + segs[mid].k) lo = mid + 1;
+                    else { seg = mid; break; }
+                }
             }
-        }
-        const float4* src = nullptr;
-        int ph = 0, pw = 0, pc = 0, image_id = 0;
-        if (seg >= 0) {
-            const dcta_segment sg = segs[seg];
-            const int tok = order[sg.img * n_tok_img + (off - sg.offset)];
-            src = reinterpret_cast<const float4*>(tiles + (sg.img * n_tok_img + tok) * q.z);
-            const int tile = (int)(((float)tok + 0.5f) * inv_channels);   // exact for tok < 2^22
-            pc = tok - tile * channels;
-            ph = (int)(((float)tile + 0.5f) * inv_tw);
-            pw = tile - ph * tw;
-            image_id = sg.image_id;
-        }
-        const int64_t pid = ((int64_t)pc * q.H + ph) * q.W + pw;
-        const float4* ms = reinterpret_cast<const float4*>(q.median + pid * q.z);
-        const float4* bs = reinterpret_cast<const float4*>(q.b + pid * q.z);
-        unsigned w[2];
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int qd = lane + 32 * pass;
-            unsigned nib = 0;
-            if (qd < z4) {
-                const float4 xv = src ? __ldg(src + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 mv = __ldg(ms + qd);
-                const float4 bv = __ldg(bs + qd);
-                nib = norm_sign_bit(xv.x, mv.x, bv.x, q) | (norm_sign_bit(xv.y, mv.y, bv.y, q) << 1) |
-                      (norm_sign_bit(xv.z, mv.z, bv.z, q) << 2) | (norm_sign_bit(xv.w, mv.w, bv.w, q) << 3);
+            int ph = 0, pw = 0, pc = 0, image_id = 0;
+            if (seg >= 0) {
+                const dcta_segment sg = segs[seg];
+                const int tok = order[sg.img * n_tok_img + (off - sg.offset)];
+                src_off = (sg.img * n_tok_img + tok) * (int64_t)q.z;
+                const int tile = (int)(((float)tok + 0.5f) * inv_channels);   // exact for tok < 2^22
+                pc = tok - tile * channels;
+                ph = (int)(((float)tile + 0.5f) * inv_tw);
+                pw = tile - ph * tw;
+                image_id = sg.image_id;
             }
-            unsigned v = nib << (4 * (lane & 7));
-            v |= __shfl_xor_sync(0xffffffffu, v, 1);
-            v |= __shfl_xor_sync(0xffffffffu, v, 2);
-            v |= __shfl_xor_sync(0xffffffffu, v, 4);
-            w[pass] = v;        // lanes 8j .. 8j+7 hold elements 128*pass + 32*j .. +31 (bit = element & 31)
-        }
-        // lfq.py:187: code[cb] = bits [cb*d, cb*d + d) of the element-ordered string, first element = MSB
-        for (int cb0 = 0; cb0 < q.c; cb0 += 32) {
-            const int cb = min(cb0 + lane, q.c - 1);
-            const int e0 = cb * q.d;
-            const int k0 = e0 >> 5, k1 = min(k0 + 1, 7), sh = e0 & 31;
-            const unsigned a0 = __shfl_sync(0xffffffffu, w[0], 8 * (k0 & 3));
-            const unsigned a1 = __shfl_sync(0xffffffffu, w[1], 8 * (k0 & 3));
-            const unsigned b0 = __shfl_sync(0xffffffffu, w[0], 8 * (k1 & 3));
-            const unsigned b1 = __shfl_sync(0xffffffffu, w[1], 8 * (k1 & 3));
-            const unsigned wlo = (k0 >> 2) ? a1 : a0;
-            const unsigned whi = (k1 >> 2) ? b1 : b0;
-            const unsigned bits = __funnelshift_r(wlo, whi, sh) & dmask;      // LSB = first element
-            const unsigned code = __brev(bits) >> (32 - q.d);
-            if (cb0 + lane < q.c) codes[slot * q.c + cb] = (int64_t)code;
-        }
-        if (lane == 0) {
+            // padding slots are quantised like the reference does: zeros normalised with the statistics at (0,0,0)
+            pid = (pc * q.H + ph) * q.W + pw;
             reinterpret_cast<longlong2*>(positions)[slot] = make_longlong2(ph, pw);
             channels_out[slot] = pc;
             if (image_ids) image_ids[slot] = image_id;
             if (key_pad_mask) key_pad_mask[slot] = seg < 0;
+        }
+        // ---- the tokens, two in flight
+        const int n_here = (int)min((int64_t)32, total - slot0);
+        for (int t = 0; t < n_here; t += 2) {
+            float4 xv[2][2], mv[2][2], bv[2][2];
+            const bool second = t + 1 < n_here;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int64_t so = __shfl_sync(0xffffffffu, src_off, t + u);
+                const int pd = __shfl_sync(0xffffffffu, pid, t + u);
+                if (u == 0 || second)
+                    load_token(so >= 0 ? reinterpret_cast<const float4*>(tiles + so) : nullptr,
+                               reinterpret_cast<const float4*>(q.median + (int64_t)pd * q.z),
+                               reinterpret_cast<const float4*>(q.b + (int64_t)pd * q.z), lane, z4, xv[u], mv[u], bv[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 0 || second) {
+                    const TokenBits tb = token_bits(xv[u], mv[u], bv[u], lane, z4, q);
+                    write_codes(tb, lane, q, dmask, codes + (slot0 + t + u) * q.c);
+                }
+            }
         }
     }
 }
@@ -299,7 +345,7 @@ extern "C" int dcta_pack_codes_lfq(const float* tiles, const int32_t* order, con
     const bool aligned = ((reinterpret_cast<uintptr_t>(tiles) | reinterpret_cast<uintptr_t>(median) |
                            reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(positions)) & 15) == 0;
     if (z % 4 == 0 && d <= 32 && aligned && th * tw * channels < (1 << 22)) {
-        pack_codes_vec_kernel<<<grid_for((int64_t)n_rows * s, 8), 256, 0, as_stream(stream)>>>(
+        pack_codes_vec_kernel<<<grid_for((int64_t)n_rows * s, 256), 256, 0, as_stream(stream)>>>(
             tiles, order, segs, row_seg_start, n_rows, s, tw, channels, th * tw * channels, 1.0f / (float)channels,
             1.0f / (float)tw, q, codes, positions, channels_out, image_ids, key_pad_mask);
         return check_launch("pack_codes_lfq");

@@ -57,15 +57,37 @@ __device__ __forceinline__ uint32_t orderable(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// kFromMax: `scores` holds amax|tile| per token and the score of FE:409-416 is formed here (same
+// arithmetic as tile_scores_kernel); scores_out [nullable] receives it.
+struct ScoreParams {
+    int tw, channels;
+    float mag_weight;
+    Importances imp;
+    float* scores_out;
+};
+
+template <bool kFromMax>
 __global__ void __launch_bounds__(1024) sort_tokens_kernel(const float* __restrict__ scores,
                                                            int32_t* __restrict__ order, int n_tok,
-                                                           int n_pad) {
+                                                           int n_pad, ScoreParams sp) {
     extern __shared__ unsigned long long keys[];
     const int64_t img = blockIdx.x;
     const float* s = scores + img * n_tok;
     for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
         unsigned long long k = ~0ull;
-        if (i < n_tok) k = ((unsigned long long)(~orderable(s[i])) << 32) | (unsigned)i;
+        if (i < n_tok) {
+            float sc = s[i];
+            if (kFromMax) {
+                const int c = i % sp.channels;
+                const int tile = i / sp.channels;
+                const int h = tile / sp.tw, w = tile - h * sp.tw;
+                const float mags = __fmul_rn(sc, sp.mag_weight);
+                const float dist = __fdiv_rn((float)(-(h + w)), sp.imp.v[c]);
+                sc = __fadd_rn(mags, dist);
+                if (sp.scores_out) sp.scores_out[img * n_tok + i] = sc;
+            }
+            k = ((unsigned long long)(~orderable(sc)) << 32) | (unsigned)i;
+        }
         keys[i] = k;
     }
     __syncthreads();
@@ -195,21 +217,43 @@ extern "C" int dcta_tile_scores(const float* tiles, float* scores, int64_t n_img
     return check_launch("tile_scores");
 }
 
-extern "C" int dcta_sort_tokens(const float* scores, int32_t* order, int64_t n_img, int n_tok,
-                                void* stream) {
+static int launch_sort(const float* scores, int32_t* order, int64_t n_img, int n_tok, bool from_max, const ScoreParams& sp,
+                       void* stream) {
     DCTA_REQUIRE(scores && order, "sort_tokens: null pointer");
     DCTA_REQUIRE(n_tok > 0 && n_tok <= 16384, "sort_tokens: n_tok=%d outside 1..16384", n_tok);
     if (n_img == 0) return DCTA_OK;
     int n_pad = 2;
     while (n_pad < n_tok) n_pad <<= 1;
     const size_t smem = (size_t)n_pad * sizeof(unsigned long long);
-    if (smem > 48 * 1024)  // per-device attribute: set on every call that needs it (cheap)
-        cudaFuncSetAttribute(sort_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    if (smem > 48 * 1024) {  // per-device attribute: set on every call that needs it (cheap)
+        cudaFuncSetAttribute(sort_tokens_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+        cudaFuncSetAttribute(sort_tokens_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    }
     int threads = n_pad / 2;
     if (threads > 1024) threads = 1024;
     if (threads < 32) threads = 32;
-    sort_tokens_kernel<<<(unsigned)n_img, threads, smem, as_stream(stream)>>>(scores, order, n_tok, n_pad);
+    if (from_max)
+        sort_tokens_kernel<true><<<(unsigned)n_img, threads, smem, as_stream(stream)>>>(scores, order, n_tok, n_pad, sp);
+    else
+        sort_tokens_kernel<false><<<(unsigned)n_img, threads, smem, as_stream(stream)>>>(scores, order, n_tok, n_pad, sp);
     return check_launch("sort_tokens");
+}
+
+extern "C" int dcta_sort_tokens(const float* scores, int32_t* order, int64_t n_img, int n_tok,
+                                void* stream) {
+    ScoreParams sp{};
+    return launch_sort(scores, order, n_img, n_tok, false, sp, stream);
+}
+
+extern "C" int dcta_sort_tokens_maxabs(const float* maxabs, float* scores, int32_t* order, int64_t n_img, int th, int tw,
+                                       int channels, float mag_weight, const float* channel_importances_host,
+                                       void* stream) {
+    DCTA_REQUIRE(channel_importances_host, "sort_tokens_maxabs: null pointer");
+    DCTA_REQUIRE(channels >= 1 && channels <= 8 && th > 0 && tw > 0, "sort_tokens_maxabs: bad sizes");
+    ScoreParams sp{};
+    sp.tw = tw; sp.channels = channels; sp.mag_weight = mag_weight; sp.scores_out = scores;
+    for (int i = 0; i < 8; ++i) sp.imp.v[i] = i < channels ? channel_importances_host[i] : 1.0f;
+    return launch_sort(maxabs, order, n_img, th * tw * channels, true, sp, stream);
 }
 
 extern "C" int dcta_pack_tiles(const float* tiles, const int32_t* order, const dcta_segment* segs,

@@ -109,6 +109,11 @@ __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// the same without release semantics: for hand-offs that are ordered by tcgen05 fences (TMEM reads), so that
+// the arrive does not wait for the warp's outstanding global stores
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // bounded wait with cluster-scope acquire (the arrivals come from both CTAs of the pair)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);

@@ -70,6 +70,7 @@ class DCTAutoencoderFeatureExtractor:
         self.patch_sample_magnitude_weight = patch_sample_magnitude_weight
         self.device = torch.device(device) if device is not None else None
         self._table_cache: Dict[bytes, torch.Tensor] = {}
+        self._maxabs: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ helpers
     def _dev(self, like: Optional[torch.Tensor] = None) -> torch.device:
@@ -123,9 +124,15 @@ class DCTAutoencoderFeatureExtractor:
         return x[..., :c_h, :c_w]
 
     # ------------------------------------------------------------------ encode: kernels
-    def _token_grid(self, x: torch.Tensor) -> torch.Tensor:
+    def _token_grid(self, x: torch.Tensor, want_maxabs: bool = False):
         """(b, c, h, w) fp32 CUDA images -> token grid (b, th, tw, c, p*p) in the reference's
-        pre-sort order (FE:374-399)."""
+        pre-sort order (FE:374-399).  With ``want_maxabs`` returns (tiles, maxabs or None): the folded
+        tensor-core path reduces amax|tile| (FE:409) in its GEMM epilogue."""
+        if want_maxabs:
+            self._maxabs = None
+            tiles = self._token_grid(x)
+            maxabs, self._maxabs = self._maxabs, None
+            return tiles, maxabs
         b, c, h, w = x.shape
         assert c == self.channels
         p = self.patch_size
@@ -137,7 +144,8 @@ class DCTAutoencoderFeatureExtractor:
             if self.dct_impl == "tc" and fold_ok(h, w, th * p, tw * p):
                 # folded: the colour transform writes the four mirrored sign combinations of each plane
                 hi, lo, dc = rgb_to_ipt_fold(x)
-                return dct2_fwd_fold(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c)
+                tiles, self._maxabs = dct2_fwd_fold(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c, with_maxabs=True)
+                return tiles
             if self.dct_impl in ("tc", "tc_plain") and tc_forward_ok(h, w):
                 # tensor cores: colour transform writes the centred fp16 hi/lo operand planes directly
                 hi, lo, dc = rgb_to_ipt_split(x)
@@ -152,13 +160,19 @@ class DCTAutoencoderFeatureExtractor:
                       planes.shape[-1], th, tw, p, _lib.stream_ptr(x.device))
         return tiles
 
-    def _sorted_order(self, tiles: torch.Tensor) -> torch.Tensor:
-        """FE:403-418: importance scores and their descending order, (b, th*tw*c) int32."""
+    def _sorted_order(self, tiles: torch.Tensor, maxabs: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """FE:403-418: importance scores and their descending order, (b, th*tw*c) int32.
+        ``maxabs`` (b, th, tw, c): amax|tile| already reduced by the DCT kernel (skips the pass over the tiles)."""
         b, th, tw, c, z = tiles.shape
         n_tok = th * tw * c
-        scores = torch.empty((b, n_tok), dtype=torch.float32, device=tiles.device)
         order = torch.empty((b, n_tok), dtype=torch.int32, device=tiles.device)
         imp = _lib.host_floats(self.channel_importances.tolist()[:c] + [1.0] * max(0, c - len(self.channel_importances)))
+        if maxabs is not None:
+            with torch.cuda.device(tiles.device):
+                _lib.call("dcta_sort_tokens_maxabs", _lib.ptr(maxabs), None, _lib.ptr(order), b, th, tw, c,
+                          float(self.patch_sample_magnitude_weight), imp, _lib.stream_ptr(tiles.device))
+            return order
+        scores = torch.empty((b, n_tok), dtype=torch.float32, device=tiles.device)
         with torch.cuda.device(tiles.device):
             st = _lib.stream_ptr(tiles.device)
             _lib.call("dcta_tile_scores", _lib.ptr(tiles), _lib.ptr(scores), b, th, tw, c, z,
@@ -241,8 +255,8 @@ class DCTAutoencoderFeatureExtractor:
         x = to_device_f32(im, self._dev(im))[None]
         _, c, h, w = x.shape
         ph, pw, th, tw = self._geometry(h, w)
-        tiles = self._token_grid(x)
-        order = self._sorted_order(tiles)
+        tiles, maxabs = self._token_grid(x, want_maxabs=True)
+        order = self._sorted_order(tiles, maxabs)
         n_tok = th * tw * c
         k = self._choose_k(n_tok)
         z = self.patch_size ** 2
@@ -265,8 +279,8 @@ class DCTAutoencoderFeatureExtractor:
         x = to_device_f32(images, self._dev(images))
         b, c, h, w = x.shape
         ph, pw, th, tw = self._geometry(h, w)
-        tiles = self._token_grid(x)
-        order = self._sorted_order(tiles)
+        tiles, maxabs = self._token_grid(x, want_maxabs=True)
+        order = self._sorted_order(tiles, maxabs)
         n_tok = th * tw * c
         if ks is None:
             ks = [self._choose_k(n_tok) for _ in range(b)]
@@ -304,8 +318,8 @@ class DCTAutoencoderFeatureExtractor:
         x = to_device_f32(images, self._dev(images))
         b, c, h, w = x.shape
         ph, pw, th, tw = self._geometry(h, w)
-        tiles = self._token_grid(x)
-        order = self._sorted_order(tiles)
+        tiles, maxabs = self._token_grid(x, want_maxabs=True)
+        order = self._sorted_order(tiles, maxabs)
         n_tok = th * tw * c
         if ks is None:
             ks = [self._choose_k(n_tok) for _ in range(b)]

@@ -446,8 +446,9 @@ def fold_planes(x: torch.Tensor):
 
 
 def dct2_fwd_fold(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: Optional[torch.Tensor], kh: int, kw: int,
-                  tile_p: int = 0, channels: int = 1, out_shape=None):
-    """Truncated forward DCT from folded quadrants (2, 2, n_planes, h/2, w/2)."""
+                  tile_p: int = 0, channels: int = 1, out_shape=None, with_maxabs: bool = False):
+    """Truncated forward DCT from folded quadrants (2, 2, n_planes, h/2, w/2).  ``with_maxabs`` (token grid
+    only) also returns amax|tile| per token (n_img, kh/p, kw/p, channels), reduced in the GEMM epilogue."""
     n_planes, h2, w2 = xq_hi.shape[-3:]
     h, w = 2 * h2, 2 * w2
     dev = xq_hi.device
@@ -460,11 +461,16 @@ def dct2_fwd_fold(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: Optional[torch.T
                         dtype=torch.float32, device=dev)
     else:
         y = torch.empty((out_shape or (n_planes,)) + (kh, kw), dtype=torch.float32, device=dev)
+    maxabs = None
+    if with_maxabs:
+        assert tile_p > 0
+        maxabs = torch.empty(y.shape[:4], dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dcta_dct2_fwd_fold", _lib.ptr(xq_hi), _lib.ptr(xq_lo), _lib.ptr(dc), _lib.ptr(bw_hi),
                   _lib.ptr(bw_lo), _lib.ptr(rs_w), _lib.ptr(bh_hi), _lib.ptr(bh_lo), _lib.ptr(rs_h), _lib.ptr(work_hi),
-                  _lib.ptr(work_lo), _lib.ptr(y), n_planes, h, w, kh, kw, tile_p, channels, _lib.stream_ptr(dev))
-    return y
+                  _lib.ptr(work_lo), _lib.ptr(y), _lib.ptr(maxabs), n_planes, h, w, kh, kw, tile_p, channels,
+                  _lib.stream_ptr(dev))
+    return (y, maxabs) if with_maxabs else y
 
 
 def dct2_inv_fold(yq_hi: torch.Tensor, yq_lo: torch.Tensor, kh: int, kw: int, h: int, w: int) -> torch.Tensor:

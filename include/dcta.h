@@ -137,11 +137,13 @@ int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float* dc, float*
 /* Forward truncated DCT from the quadrants; output contract of dcta_dct2_fwd (planes or token grid).
  *   bw_hi/lo (2, kw/2, w/2): CW[2j+b, w'] * 2^10, group b (row 0 of group 0 stored as the constant 32);
  *   rs_w (2, kw/2) the factors undoing those scales;  bh_hi/lo (2, kh/2, h/2), rs_h likewise (group a);
- *   work_hi/lo (2, n_planes, kw, h/2) scratch. */
+ *   work_hi/lo (2, n_planes, kw, h/2) scratch;
+ *   maxabs [nullable, token grid only] (n_planes/channels, kh/p, kw/p, channels): amax|tile| of every token
+ *   (FE:409), reduced in the GEMM epilogue (input of dcta_sort_tokens_maxabs). */
 int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
                        const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
-                       const float* rs_h, void* work_hi, void* work_lo, float* y, int64_t n_planes, int h,
-                       int w, int kh, int kw, int tile_p, int channels, void* stream);
+                       const float* rs_h, void* work_hi, void* work_lo, float* y, float* maxabs, int64_t n_planes,
+                       int h, int w, int kh, int kw, int tile_p, int channels, void* stream);
 /* FE:635-653 un-patchify into folded coefficient quadrants yq_hi/lo (2, 2, n_img*channels, rows/2, ldq)
  * [b][a][plane][i][j] = Y[2i+a, 2j+b] * 2^4, ldq = round8(cols/2); DC moved to dc as in dcta_unpatchify_split. */
 int dcta_unpatchify_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
@@ -182,6 +184,10 @@ int dcta_tile_scores(const float* tiles, float* scores, int64_t n_img, int th, i
 /* FE:418 per-image descending sort of the scores (ties: ascending flat index).
  *   scores (n_img, n_tok) -> order (n_img, n_tok) int32.  n_tok <= 16384. */
 int dcta_sort_tokens(const float* scores, int32_t* order, int64_t n_img, int n_tok, void* stream);
+/* The same from per-token amax|tile| (maxabs (n_img, th, tw, channels)): the scores of FE:409-416 are
+ * formed on the fly with the arithmetic of dcta_tile_scores; scores [nullable] receives them. */
+int dcta_sort_tokens_maxabs(const float* maxabs, float* scores, int32_t* order, int64_t n_img, int th, int tw,
+                            int channels, float mag_weight, const float* channel_importances_host, void* stream);
 
 /* One packed row segment: k tokens of image `img` placed at slots [offset, offset+k) of row `row`
  * with batched_image_id `image_id` (FE:455-513 next-fit result, computed on the host). */

@@ -107,3 +107,16 @@ def test_fold_rgb_round_trip(D):
     z = D.util.dct2_inv_fold(yh, yl, 256, 256, 256, 256)
     rgb = D.util.unfold_ipt_to_rgb(z, dc, 256, 256)
     assert float((rgb - x).abs().max()) <= 2e-5
+
+
+def test_fold_maxabs_matches_tile_scores(D):
+    """amax|tile| reduced in the GEMM epilogue == a pass over the token grid (bit-exact), hence same order."""
+    torch.manual_seed(4)
+    for shape in [(5, 3, 512, 512), (3, 3, 256, 320), (2, 3, 1024, 1024)]:
+        x = torch.rand(*shape, device="cuda")
+        fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+        tiles, maxabs = fe._token_grid(x, want_maxabs=True)
+        assert maxabs is not None
+        ref = tiles.abs().amax(dim=-1)
+        assert torch.equal(maxabs, ref)
+        assert torch.equal(fe._sorted_order(tiles, maxabs), fe._sorted_order(tiles))
