@@ -43,6 +43,7 @@ struct FoldGemm {
     int n_valid;          // basis rows of a group that exist
     int stages;
     uint32_t basis_bytes; // one CTA's resident basis plane (hi or lo): num_kb * (n_tile/2) * 64
+    int score_groups;     // > 0: tile rows of the token grid; a [score_groups][128] max|value| image follows the ring
 };
 
 struct FoldEpi {
@@ -79,24 +80,9 @@ __device__ __forceinline__ void st_f32(uint64_t base, uint32_t off, float v) {
                  : "memory");
 }
 
-// max over the lanes that share `key` (contiguous lane ranges); valid in the first lane of every range
-__device__ __forceinline__ float segmented_max(float m, uint32_t key, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float other = __shfl_down_sync(0xffffffffu, m, o);
-        const uint32_t okey = __shfl_down_sync(0xffffffffu, key, o);
-        if (lane + o < 32 && okey == key) m = fmaxf(m, other);
-    }
-    return m;
-}
-
 struct ScoreCtx {
     const int32_t* col_grp;   // per column: tile-row index, bit 31 set where a run of columns of one tile row ends
-    unsigned* dst;            // maxabs + token index of this accumulator row at tile row 0 (leaders only)
-    uint32_t key;             // token column identity of this lane (lanes of one token are contiguous)
-    int tile_row_stride;      // tokens between tile rows: tiles_w * channels
-    bool leader;              // first lane of its key range, row valid
-    int lane;
+    unsigned* smax;           // shared [tile row][128 accumulator rows] running max |value| bit patterns, + this row
 };
 
 // One 32-column chunk of an accumulator row: scale, (split,) store each column at its table offset.
@@ -136,8 +122,7 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&rr)[32], const int3
             for (int u = 0; u < 4; ++u) {
                 m = fmaxf(m, fabsf(vv[u]));
                 if (gg[u] < 0) {          // warp-uniform: the run of this tile row ends here
-                    const float mm = segmented_max(m, sc_.key, sc_.lane);
-                    if (sc_.leader) atomicMax(sc_.dst + (gg[u] & 0x7fffffff) * sc_.tile_row_stride, __float_as_uint(mm));
+                    atomicMax(sc_.smax + (gg[u] & 0x7fffffff) * 128, __float_as_uint(m));   // |v| >= 0 orders like its bits
                     m = 0.0f;
                 }
             }
@@ -160,12 +145,12 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __shared__ __align__(16) int32_t col_off[256];
     __shared__ __align__(16) float col_scale[256];
     __shared__ __align__(16) int32_t col_grp[256];
-    __shared__ __align__(16) int32_t neg_off[32];
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* basis_hi = smem;
     uint8_t* basis_lo = smem + g.basis_bytes;
     uint8_t* ring = smem + 2 * g.basis_bytes;
+    unsigned* smax = reinterpret_cast<unsigned*>(ring + g.stages * F_STAGE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -219,7 +204,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         }
         col_grp[n] = grp_v;
     }
-    if (threadIdx.x < 32) neg_off[threadIdx.x] = -1;
+    for (int i = threadIdx.x; i < g.score_groups * 128; i += blockDim.x) smax[i] = 0u;
     if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
     tc_fence_before();
     __syncthreads();
@@ -306,15 +291,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 const int tw = rin / ep.p, pj = rin - tw * ep.p;
                 const int64_t tok0 = ((int64_t)img * ep.tiles_h * ep.tiles_w + tw) * ep.channels + ch;   // token at tile row 0
                 base = tok0 * (ep.p * ep.p) + pj;
-                if (ep.maxabs != nullptr) {
-                    sctx.col_grp = col_grp;
-                    sctx.key = row_ok ? (uint32_t)tok0 : 0xffffffffu;
-                    const uint32_t prev = __shfl_up_sync(0xffffffffu, sctx.key, 1);
-                    sctx.leader = row_ok && (lane == 0 || prev != sctx.key);
-                    sctx.dst = reinterpret_cast<unsigned*>(ep.maxabs) + tok0;
-                    sctx.tile_row_stride = ep.tiles_w * ep.channels;
-                    sctx.lane = lane;
-                }
+                sctx.smax = smax + quarter * 32 + lane;
             } else {
                 base = (int64_t)seg * ep.seg_stride + (int64_t)item * ep.item_stride + rin;
             }
@@ -344,18 +321,43 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
                 }
                 const float dcc = c == 0 ? dcv : 0.0f;
-                if (MODE == 1 && ep.maxabs != nullptr) {
-                    // every lane takes part in the shuffles of the score reduction: rows past the end store nothing
-                    // (their offsets are replaced by the guard value) and contribute zeros
-                    ScoreCtx sc2 = sctx;
-                    sc2.col_grp = &col_grp[c * 32];
-                    store_chunk<MODE, true, true>(rr, row_ok ? &col_off[c * 32] : neg_off, &col_scale[c * 32], p_hi, p_lo,
-                                                  p_f32, dcc, sc2);
+                if (MODE == 1 && g.score_groups > 0) {
+                    if (row_ok) {
+                        ScoreCtx sc2 = sctx;
+                        sc2.col_grp = &col_grp[c * 32];
+                        store_chunk<MODE, true, true>(rr, &col_off[c * 32], &col_scale[c * 32], p_hi, p_lo, p_f32, dcc, sc2);
+                    }
                     continue;
                 }
                 if (!row_ok) continue;
                 if (c * 32 + 32 <= n_lim) store_chunk<MODE, false, false>(rr, &col_off[c * 32], &col_scale[c * 32], p_hi, p_lo, p_f32, dcc, sctx);
                 else store_chunk<MODE, true, false>(rr, &col_off[c * 32], &col_scale[c * 32], p_hi, p_lo, p_f32, dcc, sctx);
+            }
+            if (MODE == 1 && g.score_groups > 0) {
+                // max |value| of every token touched by this CTA's 128 accumulator rows: the rows of a token are
+                // p consecutive stacked rows; one thread per (tile row, token column)
+                asm volatile("bar.sync 1, 256;" ::: "memory");          // the 8 epilogue warps
+                const int R0 = (w % g.tiles_per_seg) * 256 + (int)rank * 128;
+                const int Rend = min(R0 + 128, g.rows_per_seg);          // exclusive
+                if (Rend > R0) {
+                    const int s_first = R0 / ep.p, n_cols = (Rend - 1) / ep.p - s_first + 1;
+                    for (int i = (int)threadIdx.x - 64; i < g.score_groups * n_cols; i += 256) {
+                        const int th = i / n_cols, sc = s_first + (i - th * n_cols);
+                        const int lo = max(R0, sc * ep.p) - R0, hi = min(Rend, sc * ep.p + ep.p) - R0;
+                        unsigned m = 0;
+                        for (int rr_ = lo; rr_ < hi; ++rr_) {
+                            m = max(m, smax[th * 128 + rr_]);
+                            smax[th * 128 + rr_] = 0u;
+                        }
+                        if (m != 0u) {
+                            const int plane = sc / ep.tiles_w, tw = sc - plane * ep.tiles_w;
+                            const int img = plane / ep.channels, ch = plane - img * ep.channels;
+                            atomicMax(reinterpret_cast<unsigned*>(ep.maxabs) +
+                                          (((int64_t)img * ep.tiles_h + th) * ep.tiles_w + tw) * ep.channels + ch, m);
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
     }
@@ -395,13 +397,15 @@ struct FoldOperand {
 };
 
 // slice geometry for a basis of n_valid rows and K columns: (n_tile, n_ntiles, stages), or false if nothing fits
-static bool fold_geometry(int n_valid, int K, FoldGemm& g) {
+static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0) {
     g.num_kb = (int)ceil_div(K, FK);
     g.n_valid = n_valid;
+    g.score_groups = score_groups;
+    const int64_t score_bytes = (int64_t)score_groups * 128 * 4;
     for (int nn = (int)ceil_div(n_valid, 256); nn <= 16; ++nn) {
         const int n_tile = (int)ceil_div(ceil_div(n_valid, nn), 16) * 16;
         const int64_t basis = (int64_t)g.num_kb * (n_tile / 2) * 64;
-        const int64_t stages = (F_SMEM_LIMIT - 1024 - 2 * basis) / F_STAGE;
+        const int64_t stages = (F_SMEM_LIMIT - 1024 - 2 * basis - score_bytes) / F_STAGE;
         if (n_tile <= 256 && stages >= 3) {
             g.n_tile = n_tile;
             g.n_ntiles = nn;
@@ -417,7 +421,8 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
                             int K, FoldEpi ep, void* stream) {
     if (rows_per_seg == 0 || n_seg == 0) return DCTA_OK;
     FoldGemm g{};
-    if (!fold_geometry(n_valid, K, g)) { set_error("fold_gemm: basis %d x %d does not fit in shared memory", n_valid, K); return DCTA_ERR_UNSUPPORTED; }
+    const int score_groups = (ep.mode == 2 && ep.maxabs != nullptr) ? ep.tiles_h : 0;
+    if (!fold_geometry(n_valid, K, g, score_groups)) { set_error("fold_gemm: basis %d x %d does not fit in shared memory", n_valid, K); return DCTA_ERR_UNSUPPORTED; }
     if (rows_per_seg >= (1ll << 31) - 256 || (n_seg & 1)) { set_error("fold_gemm: bad segment geometry"); return DCTA_ERR_INVALID_ARG; }
     g.n_seg = n_seg;
     g.rows_per_seg = (int)rows_per_seg;
@@ -428,7 +433,7 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
     if ((rc = make_map3(&ma_lo, A.lo, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
     if ((rc = make_map3(&mb_hi, Bas.hi, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
     if ((rc = make_map3(&mb_lo, Bas.lo, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
-    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE;
+    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -653,88 +658,145 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ z
 // feature_extraction_dct_autoencoder.py:635-653 un-patchify (CODES = false) or its fusion with
 // lfq.indices_to_codes + PatchNorm.inverse_norm (CODES = true; lfq.py:105-134, patchnorm.py:167-177),
 // writing the folded coefficient quadrants yq[b][a][plane][i][j] = Y[2i+a, 2j+b] as scaled fp16 hi/lo.
-// One CTA per tile-row of one plane (p coefficient rows).  Phase 1 evaluates the p x 2*ldq values with the
-// lanes of a warp on CONSECUTIVE columns (token rows, code words and PatchNorm tables are read coalesced) into
-// shared memory; phase 2 de-interleaves the column parities and writes 8-byte hi/lo groups.
-template <bool CODES>
-__global__ void __launch_bounds__(256) unpatchify_fold_kernel(const float* __restrict__ patches,
-                                                              const int64_t* __restrict__ codes,
-                                                              const int32_t* __restrict__ slot_map,
-                                                              const int32_t* __restrict__ img_sel, int C, int th, int tw,
-                                                              int p, int rows, int cols, int ldq, int64_t n_planes,
-                                                              LfqNormParams q, __half* __restrict__ hi,
-                                                              __half* __restrict__ lo, float* __restrict__ dc,
-                                                              float dc_factor, float scale) {
-    extern __shared__ float vals[];                 // [p][2 * ldq]
+// One CTA per (channel, tile row, group of images): p coefficient rows of up to `imgs_per_cta` planes.
+// A thread owns 8 consecutive coefficient columns (4 per column parity: one 8-byte hi and lo store per parity)
+// of one image at a time and walks the p rows of the tile row; the main loop has no block-wide barrier.
+// Tiles are at least 8 columns wide, so the 8 columns of a thread touch at most two tokens.
+// CODES: the PatchNorm statistics of the tile row (divisor b*sqrt2 + eps and median) are staged in shared
+// memory ONCE per CTA as [row][column group][8] (16-byte halves swizzled so that 128-bit reads are
+// conflict-free) and reused for every image.  FAST (one LFQ codebook per patch row, p <= 16): the 2 x p code
+// words of a thread's two tokens are read in one burst and boiled down to one byte of sign bits per row.
+template <bool CODES, bool FAST>
+__global__ void __launch_bounds__(256, 4) unpatchify_fold_kernel(const float* __restrict__ patches,
+                                                                 const int64_t* __restrict__ codes,
+                                                                 const int32_t* __restrict__ slot_map,
+                                                                 const int32_t* __restrict__ img_sel, int64_t n_img,
+                                                                 int imgs_per_cta, int C, int th, int tw, int p, int rows,
+                                                                 int cols, int ldq, LfqNormParams q,
+                                                                 __half* __restrict__ hi, __half* __restrict__ lo,
+                                                                 float* __restrict__ dc, float dc_factor, float scale) {
+    extern __shared__ __align__(16) float smem_f[];
     const int z = p * p;
-    const int wide = 2 * ldq;
+    const int nxv = ldq >> 2;
     const int tile_rows = rows / p;
     const unsigned id = blockIdx.x;
     const int ty = (int)(id % (unsigned)tile_rows);
     const unsigned t = id / (unsigned)tile_rows;
     const int c = (int)(t % (unsigned)C);
-    const int sel = (int)(t / (unsigned)C);
-    const int64_t img = img_sel ? img_sel[sel] : sel;
+    const int64_t sel0 = (int64_t)(t / (unsigned)C) * imgs_per_cta;
+    const int n_here = (int)min((int64_t)imgs_per_cta, n_img - sel0);
     const bool row_in = ty < th;
-    const int32_t* smap = slot_map + ((img * C + c) * th + (row_in ? ty : 0)) * tw;
-    const int64_t plane = (int64_t)sel * C + c;
-    const float* med_row = nullptr;
-    const float* b_row = nullptr;
+    const int n_tx = row_in ? min(tw, cols / p) : 0;          // tiles of this row that can hold a token
+    float4* sd_t = reinterpret_cast<float4*>(smem_f);         // [p][nxv][2] float4
+    float4* med_t = sd_t + p * nxv * 2;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, n_thr = blockDim.x * blockDim.y;
     if (CODES) {
-        med_row = q.median + (((int64_t)c * q.H + ty) * q.W) * q.z;
-        b_row = q.b + (((int64_t)c * q.H + ty) * q.W) * q.z;
-    }
-    const bool row_codebook = CODES && (q.d == p);       // one codebook per patch row (14 x 14 bits at patch 14)
-    for (int x = threadIdx.x; x < wide; x += blockDim.x) {
-        const int tx = x / p, px = x - tx * p;
-        const int32_t slot = (row_in && tx < tw && x < cols) ? __ldg(smap + tx) : -1;
-        if (slot < 0) {
-            for (int py = 0; py < p; ++py) vals[py * wide + x] = 0.0f;
-            if (ty == 0 && x == 0) dc[plane] = 0.0f;
-            continue;
+        const float* med_row = q.median + (((int64_t)c * q.H + ty) * q.W) * q.z;
+        const float* b_row = q.b + (((int64_t)c * q.H + ty) * q.W) * q.z;
+        float* sd_f = reinterpret_cast<float*>(sd_t);
+        float* med_f = reinterpret_cast<float*>(med_t);
+        // zero the column groups past the last tile, then scatter the tile-ordered statistics
+        for (int i = tid; i < p * nxv * 8; i += n_thr) { sd_f[i] = 0.0f; med_f[i] = 0.0f; }
+        __syncthreads();
+        for (int e = tid; e < n_tx * z; e += n_thr) {
+            const int tx = e / z, r = e - tx * z;
+            const int py = r / p, px = r - py * p;
+            const int x = tx * p + px, xv = x >> 3, k = x & 7;
+            const int idx = ((py * nxv + xv) * 2 + ((k >> 2) ^ ((xv >> 2) & 1))) * 4 + (k & 3);
+            sd_f[idx] = __fadd_rn(__fmul_rn(__ldg(b_row + e), kSqrt2f), q.eps);
+            med_f[idx] = __ldg(med_row + e);
         }
-        const float* src = CODES ? nullptr : patches + (int64_t)slot * z + px;
-        const int64_t* cw = CODES ? codes + (int64_t)slot * q.c : nullptr;
-        const int pe0 = tx * z + px;
-        for (int py = 0; py < p; ++py) {
-            float val;
-            if (CODES) {
-                const int e = py * p + px;
-                int cb, bi;
-                if (row_codebook) { cb = py; bi = px; }
-                else { cb = e / q.d; bi = e - cb * q.d; }
-                const long long code = __ldg(cw + cb);
-                const float qv = ((code >> (q.d - 1 - bi)) & 1) ? q.scale : -q.scale;           // lfq.py:118-120
-                const float sd = __fadd_rn(__fmul_rn(__ldg(b_row + pe0 + py * p), kSqrt2f), q.eps);
-                val = __fadd_rn(__fmul_rn(qv, sd), __ldg(med_row + pe0 + py * p));               // patchnorm.py:177
-            } else {
-                val = __ldg(src + py * p);
-            }
-            if (ty == 0 && py == 0 && x == 0) {
-                dc[plane] = val * dc_factor;
-                val = 0.0f;
-            }
-            vals[py * wide + x] = val;
-        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int rows2 = rows >> 1, nxv = ldq >> 2;
+    const int rows2 = rows >> 1;
+    const int64_t n_planes = n_img * C;
     const int64_t quad = n_planes * rows2 * (int64_t)ldq;          // elements of one quadrant array
-    for (int it = threadIdx.x; it < p * nxv; it += blockDim.x) {
-        const int py = it / nxv, xv = it - py * nxv;
-        const float4 v0 = *reinterpret_cast<const float4*>(&vals[py * wide + xv * 8]);
-        const float4 v1 = *reinterpret_cast<const float4*>(&vals[py * wide + xv * 8 + 4]);
-        const int kh = ty * p + py;
-        const int a = kh & 1, ii = kh >> 1;
-        const int64_t o = ((a * n_planes + plane) * rows2 + ii) * (int64_t)ldq + xv * 4;   // + b * 2 * quad
-        const float ev[4] = {v0.x, v0.z, v1.x, v1.z}, od[4] = {v0.y, v0.w, v1.y, v1.w};
-        uint2 vh, vl;
-        split16x4(ev, scale, vh, vl);
-        *reinterpret_cast<uint2*>(hi + o) = vh;
-        *reinterpret_cast<uint2*>(lo + o) = vl;
-        split16x4(od, scale, vh, vl);
-        *reinterpret_cast<uint2*>(hi + 2 * quad + o) = vh;
-        *reinterpret_cast<uint2*>(lo + 2 * quad + o) = vl;
+    for (int k = threadIdx.y; k < n_here; k += blockDim.y) {
+        const int64_t img = img_sel ? img_sel[sel0 + k] : sel0 + k;
+        const int64_t plane = (sel0 + k) * C + c;
+        const int32_t* smap = slot_map + ((img * C + c) * th + (row_in ? ty : 0)) * tw;
+        for (int xv = threadIdx.x; xv < nxv; xv += blockDim.x) {
+            const int x0 = xv * 8;
+            const int tx0 = x0 / p, px0 = x0 - tx0 * p;
+            const int n_first = min(8, p - px0);                      // columns that belong to tile tx0
+            const int32_t slot0 = tx0 < n_tx ? __ldg(smap + tx0) : -1;
+            const int32_t slot1 = (n_first < 8 && tx0 + 1 < n_tx) ? __ldg(smap + tx0 + 1) : -1;
+            const float* src0 = (!CODES && slot0 >= 0) ? patches + (int64_t)slot0 * z + px0 : nullptr;
+            const float* src1 = (!CODES && slot1 >= 0) ? patches + (int64_t)slot1 * z - n_first : nullptr;
+            const int64_t* cw0 = (CODES && slot0 >= 0) ? codes + (int64_t)slot0 * q.c : nullptr;
+            const int64_t* cw1 = (CODES && slot1 >= 0) ? codes + (int64_t)slot1 * q.c : nullptr;
+            // valid8: bit 7-j set where column j has a token
+            const unsigned m_first = (0xffu << (8 - n_first)) & 0xffu;
+            const unsigned valid8 = (slot0 >= 0 ? m_first : 0u) | (slot1 >= 0 ? (0xffu & ~m_first) : 0u);
+            unsigned bpack[4] = {0u, 0u, 0u, 0u};                    // FAST: sign byte of row py in byte py
+            if (CODES && FAST) {
+                // column j < n_first takes bit (d-1 - (px0+j)) of the first token's word, the others bit (d-1 - (j-n_first))
+                // of the second token's: two contiguous bit fields, MSB first
+                const int sh0 = q.d - px0 - n_first, sh1 = q.d - (8 - n_first);
+#pragma unroll
+                for (int py = 0; py < 16; ++py) {
+                    if (py < p) {
+                        const unsigned w0 = cw0 ? (unsigned)__ldg(cw0 + py) : 0u;
+                        const unsigned w1 = cw1 ? (unsigned)__ldg(cw1 + py) : 0u;
+                        const unsigned f0 = (w0 >> sh0) << (8 - n_first);
+                        const unsigned f1 = n_first < 8 ? (w1 >> sh1) & (0xffu >> n_first) : 0u;
+                        bpack[py >> 2] |= ((f0 | f1) & 0xffu) << (8 * (py & 3));
+                    }
+                }
+            }
+#pragma unroll 2
+            for (int py = 0; py < p; ++py) {
+                float v[8];
+                if (CODES) {
+                    const int ti = (py * nxv + xv) * 2, sw = (xv >> 2) & 1;
+                    const float4 s0 = sd_t[ti + sw], s1 = sd_t[ti + (sw ^ 1)];
+                    const float4 m0 = med_t[ti + sw], m1 = med_t[ti + (sw ^ 1)];
+                    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                    const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                    unsigned bits8;
+                    if (FAST) {
+                        bits8 = (bpack[(py >> 2) & 3] >> (8 * (py & 3))) & 0xffu;
+                    } else {
+                        bits8 = 0u;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const bool first = j < n_first;
+                            const int64_t* cw = first ? cw0 : cw1;
+                            const int e = py * p + (first ? px0 + j : j - n_first);
+                            const int cb = e / q.d, bi = e - cb * q.d;
+                            if (cw && (((unsigned long long)__ldg(cw + cb) >> (q.d - 1 - bi)) & 1ull)) bits8 |= 0x80u >> j;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float qv = (bits8 & (0x80u >> j)) ? q.scale : -q.scale;             // lfq.py:118-120
+                        const float val = __fadd_rn(__fmul_rn(qv, sv[j]), mv[j]);                 // patchnorm.py:177
+                        v[j] = (valid8 & (0x80u >> j)) ? val : 0.0f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float* src = j < n_first ? src0 : src1;
+                        v[j] = src ? __ldg(src + py * p + j) : 0.0f;
+                    }
+                }
+                if (ty == 0 && py == 0 && xv == 0) {
+                    dc[plane] = v[0] * dc_factor;
+                    v[0] = 0.0f;
+                }
+                const int kh = ty * p + py;
+                const int a = kh & 1, ii = kh >> 1;
+                const int64_t o = ((a * n_planes + plane) * rows2 + ii) * (int64_t)ldq + xv * 4;   // + b * 2 * quad
+                const float ev[4] = {v[0], v[2], v[4], v[6]}, od[4] = {v[1], v[3], v[5], v[7]};
+                uint2 vh, vl;
+                split16x4(ev, scale, vh, vl);
+                *reinterpret_cast<uint2*>(hi + o) = vh;
+                *reinterpret_cast<uint2*>(lo + o) = vl;
+                split16x4(od, scale, vh, vl);
+                *reinterpret_cast<uint2*>(hi + 2 * quad + o) = vh;
+                *reinterpret_cast<uint2*>(lo + 2 * quad + o) = vl;
+            }
+        }
     }
 }
 
@@ -779,7 +841,7 @@ static bool fold_dims_ok(int h, int w, int kh, int kw) {
 extern "C" int dcta_fold_supported(int h, int w, int kh, int kw) {
     if (!fold_dims_ok(h, w, kh, kw)) return 0;
     FoldGemm g{};
-    return fold_geometry(kw / 2, w / 2, g) && fold_geometry(kh / 2, h / 2, g) && fold_geometry(w / 2, kw / 2, g) &&
+    return fold_geometry(kw / 2, w / 2, g) && fold_geometry(kh / 2, h / 2, g, 64) && fold_geometry(w / 2, kw / 2, g) &&
            fold_geometry(h / 2, kh / 2, g);
 }
 
@@ -926,25 +988,39 @@ static int launch_unpatchify_fold(bool with_codes, const float* patches, const i
     DCTA_REQUIRE(rows > 0 && cols > 0 && p > 0 && out_h > 0 && out_w > 0 && rows % 2 == 0 && cols % 2 == 0 && rows % p == 0,
                  "%s: needs even plane sizes and rows %% patch == 0", who);
     if (n_img == 0) return DCTA_OK;
-    const int64_t n_rows_total = n_img * C * (rows / p);
-    DCTA_REQUIRE(n_rows_total < (1ll << 31), "%s: too many plane rows for one launch", who);
+    DCTA_REQUIRE(p >= 8, "%s: tiles must be at least 8 columns wide", who);
     const int ldq = (int)(ceil_div(cols / 2, 8) * 8);
+    const int nxv = ldq / 4;
+    // threads: x = groups of 8 columns, y = images handled side by side
+    const int bx = nxv < 256 ? nxv : 256;
+    int by = 256 / bx;
+    if (by < 1) by = 1;
+    if (by > n_img) by = (int)n_img;
+    const int imgs_per_cta = (int)(n_img < 2 * by ? n_img : 2 * by);
+    const int64_t n_ctas = ceil_div(n_img, imgs_per_cta) * C * (rows / p);
+    DCTA_REQUIRE(n_ctas < (1ll << 31), "%s: too many plane rows for one launch", who);
     const float dcf = 1.0f / sqrtf((float)out_h * (float)out_w);
-    const int smem_bytes = p * 2 * ldq * (int)sizeof(float);
+    const int smem_bytes = with_codes ? 2 * p * 8 * nxv * (int)sizeof(float) : 0;
     DCTA_REQUIRE(smem_bytes <= 200 * 1024, "%s: tile row of %d bytes does not fit in shared memory", who, smem_bytes);
-    cudaError_t e;
-    if (with_codes) {
-        e = cudaFuncSetAttribute(unpatchify_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    const bool fast = with_codes && q.d == p && p <= 16;      // one codebook per patch row
+    const dim3 block((unsigned)bx, (unsigned)by);
+    cudaError_t e = cudaSuccess;
+    if (with_codes && fast) {
+        e = cudaFuncSetAttribute(unpatchify_fold_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e == cudaSuccess)
-            unpatchify_fold_kernel<true><<<(unsigned)n_rows_total, 256, smem_bytes, as_stream(stream)>>>(
-                patches, codes, slot_map, img_sel, C, th, tw, p, rows, cols, ldq, n_img * C, q, (__half*)yq_hi,
+            unpatchify_fold_kernel<true, true><<<(unsigned)n_ctas, block, smem_bytes, as_stream(stream)>>>(
+                patches, codes, slot_map, img_sel, n_img, imgs_per_cta, C, th, tw, p, rows, cols, ldq, q, (__half*)yq_hi,
+                (__half*)yq_lo, dc, dcf, kFScaleY);
+    } else if (with_codes) {
+        e = cudaFuncSetAttribute(unpatchify_fold_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess)
+            unpatchify_fold_kernel<true, false><<<(unsigned)n_ctas, block, smem_bytes, as_stream(stream)>>>(
+                patches, codes, slot_map, img_sel, n_img, imgs_per_cta, C, th, tw, p, rows, cols, ldq, q, (__half*)yq_hi,
                 (__half*)yq_lo, dc, dcf, kFScaleY);
     } else {
-        e = cudaFuncSetAttribute(unpatchify_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        if (e == cudaSuccess)
-            unpatchify_fold_kernel<false><<<(unsigned)n_rows_total, 256, smem_bytes, as_stream(stream)>>>(
-                patches, codes, slot_map, img_sel, C, th, tw, p, rows, cols, ldq, n_img * C, q, (__half*)yq_hi,
-                (__half*)yq_lo, dc, dcf, kFScaleY);
+        unpatchify_fold_kernel<false, false><<<(unsigned)n_ctas, block, 0, as_stream(stream)>>>(
+            patches, codes, slot_map, img_sel, n_img, imgs_per_cta, C, th, tw, p, rows, cols, ldq, q, (__half*)yq_hi,
+            (__half*)yq_lo, dc, dcf, kFScaleY);
     }
     if (e != cudaSuccess) { set_error("%s: %s", who, cudaGetErrorString(e)); return DCTA_ERR_LAUNCH; }
     return check_launch(who);

@@ -120,28 +120,51 @@ __device__ __forceinline__ unsigned norm_sign_bit(float xv, float mv, float bv, 
 // funnel shift + bit reversal.
 struct TokenBits { unsigned w[2]; };
 
-__device__ __forceinline__ void load_token(const float4* src, const float4* ms, const float4* bs, int lane, int z4,
-                                           float4 (&xv)[2], float4 (&mv)[2], float4 (&bv)[2]) {
+// tame: every PatchNorm b is finite and in [0, 1e18] (checked on the device by b_tame_kernel), i.e. the divisor
+// b*sqrt2 + eps is a positive normal number: the sign of the clamped quotient is then the sign of x - median
+// unless that difference is tiny (< 1e-20: the quotient could underflow) -- only those quads read b and divide.
+__global__ void __launch_bounds__(256) b_tame_kernel(const float* __restrict__ b, int64_t n, int32_t* __restrict__ flag) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(b + i);
+        bad |= !(v >= 0.0f && v <= 1e18f);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(flag, 0);
+}
+
+__device__ __forceinline__ void load_token(const float4* src, const float4* ms, int lane, int z4,
+                                           float4 (&xv)[2], float4 (&mv)[2]) {
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         const int qd = lane + 32 * pass;
         if (qd < z4) {
             xv[pass] = src ? __ldg(src + qd) : make_float4(0.f, 0.f, 0.f, 0.f);
             mv[pass] = __ldg(ms + qd);
-            bv[pass] = __ldg(bs + qd);
         }
     }
 }
 
-__device__ __forceinline__ TokenBits token_bits(const float4 (&xv)[2], const float4 (&mv)[2], const float4 (&bv)[2],
-                                                int lane, int z4, const LfqNormParams& q) {
+__device__ __forceinline__ TokenBits token_bits(const float4 (&xv)[2], const float4 (&mv)[2], const float4* bs,
+                                                bool tame, int lane, int z4, const LfqNormParams& q) {
     TokenBits r;
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         unsigned nib = 0;
-        if (lane + 32 * pass < z4)
-            nib = norm_sign_bit(xv[pass].x, mv[pass].x, bv[pass].x, q) | (norm_sign_bit(xv[pass].y, mv[pass].y, bv[pass].y, q) << 1) |
-                  (norm_sign_bit(xv[pass].z, mv[pass].z, bv[pass].z, q) << 2) | (norm_sign_bit(xv[pass].w, mv[pass].w, bv[pass].w, q) << 3);
+        if (lane + 32 * pass < z4) {
+            bool fast = false;
+            if (tame) {
+                const float d0 = xv[pass].x - mv[pass].x, d1 = xv[pass].y - mv[pass].y;
+                const float d2 = xv[pass].z - mv[pass].z, d3 = xv[pass].w - mv[pass].w;
+                fast = fminf(fminf(fabsf(d0), fabsf(d1)), fminf(fabsf(d2), fabsf(d3))) > 1e-20f && q.eps > 1e-12f &&
+                       q.lo < 0.0f && q.hi > 0.0f;
+                if (fast) nib = (d0 > 0.0f) | ((d1 > 0.0f) << 1) | ((d2 > 0.0f) << 2) | ((d3 > 0.0f) << 3);
+            }
+            if (!fast) {
+                const float4 bv = __ldg(bs + lane + 32 * pass);
+                nib = norm_sign_bit(xv[pass].x, mv[pass].x, bv.x, q) | (norm_sign_bit(xv[pass].y, mv[pass].y, bv.y, q) << 1) |
+                      (norm_sign_bit(xv[pass].z, mv[pass].z, bv.z, q) << 2) | (norm_sign_bit(xv[pass].w, mv[pass].w, bv.w, q) << 3);
+            }
+        }
         unsigned v = nib << (4 * (lane & 7));
         v |= __shfl_xor_sync(0xffffffffu, v, 1);
         v |= __shfl_xor_sync(0xffffffffu, v, 2);
@@ -170,10 +193,11 @@ __device__ __forceinline__ void write_codes(const TokenBits& tb, int lane, const
     }
 }
 
-__global__ void __launch_bounds__(256) pack_codes_vec_kernel(
+__global__ void __launch_bounds__(256, 4) pack_codes_vec_kernel(
     const float* __restrict__ tiles, const int32_t* __restrict__ order, const dcta_segment* __restrict__ segs,
     const int32_t* __restrict__ row_seg_start, int n_rows, int s, int tw, int channels, int n_tok_img,
-    float inv_channels, float inv_tw, LfqNormParams q, int64_t* __restrict__ codes, int64_t* __restrict__ positions,
+    float inv_channels, float inv_tw, LfqNormParams q, const int32_t* __restrict__ tame_flag,
+    int64_t* __restrict__ codes, int64_t* __restrict__ positions,
     int64_t* __restrict__ channels_out, int64_t* __restrict__ image_ids, uint8_t* __restrict__ key_pad_mask) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -181,6 +205,7 @@ __global__ void __launch_bounds__(256) pack_codes_vec_kernel(
     const int64_t total = (int64_t)n_rows * s;
     const int z4 = q.z >> 2;
     const unsigned dmask = q.d == 32 ? 0xffffffffu : ((1u << q.d) - 1u);
+    const bool tame = tame_flag != nullptr && __ldg(tame_flag) != 0;
     for (int64_t slot0 = warp0 * 32; slot0 < total; slot0 += n_warps * 32) {
         // ---- metadata of slot0 + lane
         const int64_t slot = slot0 + lane;
@@ -223,21 +248,22 @@ __global__ void __launch_bounds__(256) pack_codes_vec_kernel(
         // ---- the tokens, two in flight
         const int n_here = (int)min((int64_t)32, total - slot0);
         for (int t = 0; t < n_here; t += 2) {
-            float4 xv[2][2], mv[2][2], bv[2][2];
+            float4 xv[2][2], mv[2][2];
+            const float4* bsp[2];
             const bool second = t + 1 < n_here;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int64_t so = __shfl_sync(0xffffffffu, src_off, t + u);
                 const int pd = __shfl_sync(0xffffffffu, pid, t + u);
+                bsp[u] = reinterpret_cast<const float4*>(q.b + (int64_t)pd * q.z);
                 if (u == 0 || second)
                     load_token(so >= 0 ? reinterpret_cast<const float4*>(tiles + so) : nullptr,
-                               reinterpret_cast<const float4*>(q.median + (int64_t)pd * q.z),
-                               reinterpret_cast<const float4*>(q.b + (int64_t)pd * q.z), lane, z4, xv[u], mv[u], bv[u]);
+                               reinterpret_cast<const float4*>(q.median + (int64_t)pd * q.z), lane, z4, xv[u], mv[u]);
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 if (u == 0 || second) {
-                    const TokenBits tb = token_bits(xv[u], mv[u], bv[u], lane, z4, q);
+                    const TokenBits tb = token_bits(xv[u], mv[u], bsp[u], tame, lane, z4, q);
                     write_codes(tb, lane, q, dmask, codes + (slot0 + t + u) * q.c);
                 }
             }
@@ -333,8 +359,9 @@ static int check_params(const char* who, const float* median, const float* b, in
 extern "C" int dcta_pack_codes_lfq(const float* tiles, const int32_t* order, const dcta_segment* segs,
                                    const int32_t* row_seg_start, int n_rows, int s, int th, int tw, int channels,
                                    int z, const float* median, const float* b, int H, int W, float eps, float lo,
-                                   float hi, int c, int d, float scale, int64_t* codes, int64_t* positions,
-                                   int64_t* channels_out, int64_t* image_ids, uint8_t* key_pad_mask, void* stream) {
+                                   float hi, int c, int d, float scale, int32_t* tame_scratch, int64_t* codes,
+                                   int64_t* positions, int64_t* channels_out, int64_t* image_ids,
+                                   uint8_t* key_pad_mask, void* stream) {
     DCTA_REQUIRE(tiles && order && segs && row_seg_start && codes && positions && channels_out, "pack_codes_lfq: null pointer");
     DCTA_REQUIRE(n_rows >= 0 && s > 0 && th > 0 && tw > 0 && channels > 0 && th <= H && tw <= W,
                  "pack_codes_lfq: bad sizes (token grid must fit the PatchNorm tables)");
@@ -345,9 +372,14 @@ extern "C" int dcta_pack_codes_lfq(const float* tiles, const int32_t* order, con
     const bool aligned = ((reinterpret_cast<uintptr_t>(tiles) | reinterpret_cast<uintptr_t>(median) |
                            reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(positions)) & 15) == 0;
     if (z % 4 == 0 && d <= 32 && aligned && th * tw * channels < (1 << 22)) {
+        if (tame_scratch) {     // is every b a tame divisor?  (2.4 MB table, L2 resident: a few microseconds)
+            cudaMemsetAsync(tame_scratch, 1, sizeof(int32_t), as_stream(stream));
+            const int64_t nb = (int64_t)channels * H * W * z;
+            b_tame_kernel<<<grid_for(nb, 1024, 1), 256, 0, as_stream(stream)>>>(b, nb, tame_scratch);
+        }
         pack_codes_vec_kernel<<<grid_for((int64_t)n_rows * s, 256), 256, 0, as_stream(stream)>>>(
             tiles, order, segs, row_seg_start, n_rows, s, tw, channels, th * tw * channels, 1.0f / (float)channels,
-            1.0f / (float)tw, q, codes, positions, channels_out, image_ids, key_pad_mask);
+            1.0f / (float)tw, q, tame_scratch, codes, positions, channels_out, image_ids, key_pad_mask);
         return check_launch("pack_codes_lfq");
     }
     pack_codes_kernel<<<grid_for((int64_t)n_rows * s, 8), 256, 0, as_stream(stream)>>>(

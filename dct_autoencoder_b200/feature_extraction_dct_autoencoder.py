@@ -144,6 +144,8 @@ class DCTAutoencoderFeatureExtractor:
             if self.dct_impl == "tc" and fold_ok(h, w, th * p, tw * p):
                 # folded: the colour transform writes the four mirrored sign combinations of each plane
                 hi, lo, dc = rgb_to_ipt_fold(x)
+                if th > 64:       # the epilogue's per-token max image covers at most 64 tile rows
+                    return dct2_fwd_fold(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c)
                 tiles, self._maxabs = dct2_fwd_fold(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c, with_maxabs=True)
                 return tiles
             if self.dct_impl in ("tc", "tc_plain") and tc_forward_ok(h, w):
@@ -332,13 +334,14 @@ class DCTAutoencoderFeatureExtractor:
         chan = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
         ids = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
         pad = torch.empty((n_rows, s), dtype=torch.bool, device=x.device)
+        tame = torch.empty(1, dtype=torch.int32, device=x.device)
         with torch.cuda.device(x.device):
             _lib.call("dcta_pack_codes_lfq", _lib.ptr(tiles), _lib.ptr(order), tab.data_ptr() + offs[0],
                       tab.data_ptr() + offs[1], n_rows, s, th, tw, c, self.patch_size ** 2,
                       _lib.ptr(norm.median.data), _lib.ptr(norm.b.data), norm.max_patch_h, norm.max_patch_w,
                       float(norm.eps), float(norm.min_val), float(norm.max_val), lfq.num_codebooks,
-                      lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(codes), _lib.ptr(pos), _lib.ptr(chan),
-                      _lib.ptr(ids), _lib.ptr(pad), _lib.stream_ptr(x.device))
+                      lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(tame), _lib.ptr(codes), _lib.ptr(pos),
+                      _lib.ptr(chan), _lib.ptr(ids), _lib.ptr(pad), _lib.stream_ptr(x.device))
         batch = DCTPatches(patches=None, key_pad_mask=pad, batched_image_ids=ids, patch_channels=chan,
                            patch_positions=pos, patch_sizes=[(ph, pw)] * b, original_sizes=[(h, w)] * b,
                            _data={}, _row_num_images=[len(r) for r in rows])
@@ -548,7 +551,7 @@ class DCTAutoencoderFeatureExtractor:
             n, kh, kw = len(idx), gh * p, gw * p
             with torch.cuda.device(dev):
                 st = _lib.stream_ptr(dev)
-                if self.dct_impl == "tc" and C == 3 and fold_ok(h, w, kh, kw):
+                if self.dct_impl == "tc" and C == 3 and p >= 8 and fold_ok(h, w, kh, kw):
                     ldq = _round8(kw // 2)
                     y_hi = torch.empty((2, 2, n * C, kh // 2, ldq), dtype=torch.float16, device=dev)
                     y_lo = torch.empty_like(y_hi)

@@ -282,11 +282,14 @@ int dcta_perplexity(const int64_t* codes, int64_t n, int codebook_size, int64_t 
  * dcta_pack_tiles' gather (FE:437-452, FE:516-605) + PN:157-165 + lfq.py:168-187 in registers.
  * Requires a projection-free LFQ (c*d == z <= 256) and frozen statistics.  Padding slots are
  * quantised as the reference does (zeros normalised with the statistics at (0,0,0)).
- * Outputs are bit-identical to dcta_pack_tiles -> dcta_patchnorm_apply -> dcta_lfq_quantize. */
+ * Outputs are bit-identical to dcta_pack_tiles -> dcta_patchnorm_apply -> dcta_lfq_quantize.
+ * tame_scratch [nullable]: one device int32 of scratch.  When given, the call first checks on the device that
+ * every b is finite and in [0, 1e18]; if so the kernel reads b only where |x - median| < 1e-20 (the bit is
+ * the sign of x - median everywhere else). */
 int dcta_pack_codes_lfq(const float* tiles, const int32_t* order, const dcta_segment* segs,
                         const int32_t* row_seg_start, int n_rows, int s, int th, int tw, int channels,
                         int z, const float* median, const float* b, int H, int W, float eps, float lo,
-                        float hi, int c, int d, float scale, int64_t* codes, int64_t* positions,
+                        float hi, int c, int d, float scale, int32_t* tame_scratch, int64_t* codes, int64_t* positions,
                         int64_t* channels_out, int64_t* image_ids, uint8_t* key_pad_mask, void* stream);
 /* Decode from codes straight into the inverse GEMM's operand planes: lfq.py:105-134 unpack +
  * PN:167-177 de-normalise + FE:635-653 un-patchify + fp16 hi/lo split (scale 2^4, DC to dc[]).
