@@ -286,25 +286,52 @@ def run_ours(a):
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
-    if fe.dct_impl == "tc" and D.util.fold_ok(S, S, K, K):
-        kname = "fold_gemm_kernel (forward DCT: 2 launches, cta_group::2 tcgen05 fp16x3 split precision, folded basis)"
-        note = ("algorithmic flops 3*2*H*K*(W+K) per image (SURVEY 8d, plain basis GEMMs); the folded kernel executes "
-                "1/2 of them, each as 3 tensor MMAs (hi*hi + hi*lo + lo*hi), so frac <= 2/3 by construction")
-    elif fe.dct_impl in ("tc", "tc_plain"):
-        kname = "gemm_split_kernel (forward DCT: 2 launches, tcgen05 fp16x3 split precision)"
-        note = ("algorithmic flops 3*2*H*K*(W+K) per image; the kernel executes 3x that many tensor flops "
-                "(hi*hi + hi*lo + lo*hi), so frac <= 1/3 by construction")
-    else:
-        kname = "sgemm_tile_kernel (forward DCT: 2 launches, exact-fp32 FFMA)"
-        note = "algorithmic flops 3*2*H*K*(W+K) per image"
-    roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak_tf, unit="TFLOP/s",
-                    frac=achieved / peak_tf, traffic=None, peak_source=peak_src, note=note)
     hbm = float(peaks.get("hbm_gbs", 6650.0))
+    if fe.dct_impl == "tc" and D.util.fold_ok(S, S, K, K):
+        # fold_gemm_kernel: 4 launches per step (forward passes 1-2, inverse passes 1-2).  After the fold the
+        # kernel is bounded by HBM (its operands and outputs stream once), not by the tensor pipe.
+        # Algorithmic bytes per launch: fp16 hi/lo quadrants in, next operand / fp32 tiles out.
+        Kq, Sq = K // 2, S // 2
+        xq = 3 * 4 * Sq * Sq * 4            # image quadrants, hi + lo fp16            (= 3*S*S*4)
+        pt = 3 * 2 * K * Sq * 4             # forward intermediate P^T [a][plane][kw][h/2], hi + lo
+        yt = 3 * K * K * 4                  # fp32 token grid / coefficient quadrants hi + lo (same size)
+        qt = 3 * 4 * Sq * Kq * 4            # inverse intermediate Q^T, hi + lo
+        zq = 3 * 4 * Sq * Sq * 4            # fp32 quadrant transforms
+        alg = [xq + pt, pt + yt, yt + qt, qt + zq]
+        gemm_ms = stages["dct_fwd"] + stages["dct_inv"]
+        achieved_gbs = sum(alg) * B / (gemm_ms / 1e3) / 1e9
+        tens = (flops_fwd / (stages["dct_fwd"] / 1e3) / 1e12)
+        roofline = dict(bound="hbm", kernel="fold_gemm_kernel (4 launches per step: forward passes 1-2, inverse passes 1-2; "
+                        "cta_group::2 tcgen05 fp16x3 split precision, folded basis resident in shared memory)",
+                        achieved=achieved_gbs, peak=hbm, unit="GB/s", frac=achieved_gbs / hbm,
+                        traffic=None, launches_per_step=4, avg_launch_ms=gemm_ms / 4,
+                        algorithmic_bytes_per_launch=sum(alg) * B / 4,
+                        peak_source=("measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"),
+                        tensor=dict(achieved=tens, peak=peak_tf, unit="TFLOP/s", frac=tens / peak_tf,
+                                    note="forward passes: SURVEY 8(d) flops 3*2*H*K*(W+K) per image (plain basis GEMMs); the "
+                                         "folded kernel executes 1/2 of them, each as 3 tensor MMAs, so frac <= 2/3"),
+                        note="achieved = algorithmic operand + output bytes of the 4 launches / their CUDA-event time; "
+                             "traffic: see profiles/ (ncu dram bytes per launch)")
+    else:
+        if fe.dct_impl in ("tc", "tc_plain"):
+            kname = "gemm_split_kernel (forward DCT: 2 launches, tcgen05 fp16x3 split precision)"
+            note = ("algorithmic flops 3*2*H*K*(W+K) per image; the kernel executes 3x that many tensor flops "
+                    "(hi*hi + hi*lo + lo*hi), so frac <= 1/3 by construction")
+        else:
+            kname = "sgemm_tile_kernel (forward DCT: 2 launches, exact-fp32 FFMA)"
+            note = "algorithmic flops 3*2*H*K*(W+K) per image"
+        roofline = dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak_tf, unit="TFLOP/s",
+                        frac=achieved / peak_tf, traffic=None, peak_source=peak_src, note=note)
     staged_bytes = 26004480 * B
     pipeline_hbm = dict(bound="hbm", mode="staged API (roundtrip_staged)",
                         achieved=staged_bytes * staged_steps / (ms_staged / 1e3) / 1e9, peak=hbm, unit="GB/s",
                         note="whole step, staged-API algorithmic bytes 26,004,480 B/img (SURVEY 8d)")
     pipeline_hbm["frac"] = pipeline_hbm["achieved"] / hbm
+    fused_bytes = 6736896 * B * world
+    pipeline_hbm["fused"] = dict(achieved=fused_bytes * a.steps / (ms / 1e3) / 1e9 / world, peak=hbm, unit="GB/s",
+                                 frac=fused_bytes * a.steps / (ms / 1e3) / 1e9 / world / hbm,
+                                 note="the timed step (fused mode) against the fully-fused lower bound of SURVEY 8(d): "
+                                      "6,736,896 B/img (image in, codes + metadata out, image out)")
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                 ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -323,7 +350,7 @@ def run_ours(a):
 
     if rank == 0 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n = a.cpu_sample or 32 * cores
+        n = a.cpu_sample or 160 * cores          # ~10 s of CPU work on all cores
         ips, dt, procs = cpu_reference_throughput(n, S, cores)
         line["cpu_baseline"] = dict(value=ips, unit=UNIT, cores=procs, kind="port",
                                     sample=f"{n} images of {S}x{S} over {procs} worker processes, {dt:.1f} s "

@@ -46,13 +46,13 @@ SIGNATURES = {
     "dcta_fold_supported": [c_int, c_int, c_int, c_int],
     "dcta_rgb_to_ipt_fold": [P, P, P, P, P, c_int64, c_int, c_int, P, P, P],
     "dcta_fold_planes": [P, P, P, P, P, c_int64, c_int, c_int, P],
-    "dcta_dct2_fwd_fold": [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "dcta_dct2_fwd_fold": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "dcta_sort_tokens_maxabs": [P, P, P, c_int64, c_int, c_int, c_int, c_float, P, P],
     "dcta_unpatchify_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
     "dcta_decode_codes_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P],
     "dcta_fold_coef_planes": [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
-    "dcta_dct2_inv_fold": [P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
+    "dcta_dct2_inv_fold": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_unfold_ipt_to_rgb": [P, P, P, c_int64, c_int, c_int, P, P, P],
     "dcta_unfold_planes": [P, P, P, c_int64, c_int, c_int, P],
     "dcta_patchify": [P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
@@ -86,6 +86,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"dcta_last_error": c_char_p}
 REDUCE_SCRATCH = 2048  # DCTA_REDUCE_SCRATCH
+CHAIN_SCRATCH = 4096   # DCTA_CHAIN_SCRATCH
 
 # kernels launched by one call of each entry point (memsets not counted)
 KERNELS_PER_CALL = {

@@ -44,6 +44,8 @@ struct FoldGemm {
     int stages;
     uint32_t basis_bytes; // one CTA's resident basis plane (hi or lo): num_kb * (n_tile/2) * 64
     int score_groups;     // > 0: tile rows of the token grid; a [score_groups][128] max|value| image follows the ring
+    int chunk_w;          // accumulator columns an epilogue warp takes at a time (multiple of 4, <= 32; an even
+                          // number of chunks covers n_tile so that the two warps of a lane quarter get equal shares)
 };
 
 struct FoldEpi {
@@ -85,15 +87,27 @@ struct ScoreCtx {
     unsigned* smax;           // shared [tile row][128 accumulator rows] running max |value| bit patterns, + this row
 };
 
+__device__ __forceinline__ void st_h16_hint(uint64_t base, uint32_t off, __half v, uint64_t pol) {
+    asm volatile("{\n.reg .u64 a;\nmad.wide.u32 a, %1, 2, %0;\nst.global.L2::cache_hint.b16 [a], %2, %3;\n}" ::"l"(base),
+                 "r"(off), "h"(__half_as_ushort(v)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_f32_hint(uint64_t base, uint32_t off, float v, uint64_t pol) {
+    asm volatile("{\n.reg .u64 a;\nmad.wide.u32 a, %1, 4, %0;\nst.global.L2::cache_hint.f32 [a], %2, %3;\n}" ::"l"(base),
+                 "r"(off), "f"(v), "l"(pol) : "memory");
+}
+
 // One 32-column chunk of an accumulator row: scale, (split,) store each column at its table offset.
 // GUARD: offsets < 0 mark columns past the end of the basis (only the last chunk of a slice can have them).
 // SCORE (fp32 token grid): also reduce max |value| per token (feature_extraction_dct_autoencoder.py:409).
-template <int MODE, bool GUARD, bool SCORE>
+// HINT: stores carry the L2 eviction policy `pol`.
+template <int MODE, bool GUARD, bool SCORE, bool HINT = false>
 __device__ __forceinline__ void store_chunk(const uint32_t (&rr)[32], const int32_t* col_off, const float* col_scale,
-                                            uint64_t p_hi, uint64_t p_lo, uint64_t p_f32, float dcv, const ScoreCtx& sc_) {
+                                            uint64_t p_hi, uint64_t p_lo, uint64_t p_f32, float dcv, const ScoreCtx& sc_,
+                                            int width, uint64_t pol = 0) {
     float m = 0.0f;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
+        if (j >= width) break;
         const int4 off = *reinterpret_cast<const int4*>(col_off + j);
         const float4 sc = *reinterpret_cast<const float4*>(col_scale + j);
         float v0 = __uint_as_float(rr[j]) * sc.x, v1 = __uint_as_float(rr[j + 1]) * sc.y;
@@ -104,10 +118,22 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&rr)[32], const int3
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
             const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y);
             const __half2 l23 = __floats2half2_rn(v2 - f23.x, v3 - f23.y);
-            if (!GUARD || off.x >= 0) { st_h16(p_hi, off.x, __low2half(h01)); st_h16(p_lo, off.x, __low2half(l01)); }
-            if (!GUARD || off.y >= 0) { st_h16(p_hi, off.y, __high2half(h01)); st_h16(p_lo, off.y, __high2half(l01)); }
-            if (!GUARD || off.z >= 0) { st_h16(p_hi, off.z, __low2half(h23)); st_h16(p_lo, off.z, __low2half(l23)); }
-            if (!GUARD || off.w >= 0) { st_h16(p_hi, off.w, __high2half(h23)); st_h16(p_lo, off.w, __high2half(l23)); }
+            if (HINT) {
+                if (!GUARD || off.x >= 0) { st_h16_hint(p_hi, off.x, __low2half(h01), pol); st_h16_hint(p_lo, off.x, __low2half(l01), pol); }
+                if (!GUARD || off.y >= 0) { st_h16_hint(p_hi, off.y, __high2half(h01), pol); st_h16_hint(p_lo, off.y, __high2half(l01), pol); }
+                if (!GUARD || off.z >= 0) { st_h16_hint(p_hi, off.z, __low2half(h23), pol); st_h16_hint(p_lo, off.z, __low2half(l23), pol); }
+                if (!GUARD || off.w >= 0) { st_h16_hint(p_hi, off.w, __high2half(h23), pol); st_h16_hint(p_lo, off.w, __high2half(l23), pol); }
+            } else {
+                if (!GUARD || off.x >= 0) { st_h16(p_hi, off.x, __low2half(h01)); st_h16(p_lo, off.x, __low2half(l01)); }
+                if (!GUARD || off.y >= 0) { st_h16(p_hi, off.y, __high2half(h01)); st_h16(p_lo, off.y, __high2half(l01)); }
+                if (!GUARD || off.z >= 0) { st_h16(p_hi, off.z, __low2half(h23)); st_h16(p_lo, off.z, __low2half(l23)); }
+                if (!GUARD || off.w >= 0) { st_h16(p_hi, off.w, __high2half(h23)); st_h16(p_lo, off.w, __high2half(l23)); }
+            }
+        } else if (HINT) {
+            if (!GUARD || off.x >= 0) st_f32_hint(p_f32, off.x, v0, pol);
+            if (!GUARD || off.y >= 0) st_f32_hint(p_f32, off.y, v1, pol);
+            if (!GUARD || off.z >= 0) st_f32_hint(p_f32, off.z, v2, pol);
+            if (!GUARD || off.w >= 0) st_f32_hint(p_f32, off.w, v3, pol);
         } else {
             if (!GUARD || off.x >= 0) st_f32(p_f32, off.x, v0);
             if (!GUARD || off.y >= 0) st_f32(p_f32, off.y, v1);
@@ -142,9 +168,9 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __shared__ __align__(8) uint64_t tmem_empty[2];
     __shared__ __align__(8) uint64_t basis_bar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) int32_t col_off[256];
-    __shared__ __align__(16) float col_scale[256];
-    __shared__ __align__(16) int32_t col_grp[256];
+    __shared__ __align__(16) int32_t col_off[288];     // n_tile + one chunk of slack (guarded reads past the end)
+    __shared__ __align__(16) float col_scale[288];
+    __shared__ __align__(16) int32_t col_grp[288];
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* basis_hi = smem;
@@ -179,7 +205,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // per-slice output tables: where basis row n goes and what it is multiplied by
-    for (int n = threadIdx.x; n < 256; n += blockDim.x) {
+    for (int n = threadIdx.x; n < 288; n += blockDim.x) {
         int32_t off = -1;
         float sc = 0.f;
         if (n < n_lim) {
@@ -199,7 +225,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (ep.mode == 2 && n < n_lim) {
             const int line = (nt * g.n_tile + n) * ep.col_mul + grp * ep.col_add;
             const int th = line / ep.p;
-            const bool ends = (n == n_lim - 1) || ((n & 31) == 31) || ((line + ep.col_mul) / ep.p != th);
+            const bool ends = (n == n_lim - 1) || ((n % g.chunk_w) == g.chunk_w - 1) || ((line + ep.col_mul) / ep.p != th);
             grp_v = th | (ends ? (int32_t)0x80000000 : 0);
         }
         col_grp[n] = grp_v;
@@ -274,7 +300,8 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         // ---------------- epilogue warps: TMEM lane quarter = warp & 3, 32-column chunks alternate between
         // the two warps of a quarter
         const int quarter = warp & 3, chalf = (warp - 2) >> 2;
-        const int n_chunks = (n_lim + 31) >> 5;
+        const int cwid = g.chunk_w;
+        const int n_chunks = (n_lim + cwid - 1) / cwid;
         const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
         const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
         const bool dc_slice = (ep.dc != nullptr) && grp == 0 && nt == 0;
@@ -313,7 +340,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll 1
             for (int c = chalf; c < n_chunks; c += 2) {
                 uint32_t rr[32];
-                tmem_ld32_nowait(tmem_acc + c * 32, rr);
+                tmem_ld32_nowait(tmem_acc + c * cwid, rr);
                 tmem_ld_wait();
                 if (c == last) {                             // accumulator read out by this warp: hand it back
                     tc_fence_before();
@@ -324,14 +351,14 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 if (MODE == 1 && g.score_groups > 0) {
                     if (row_ok) {
                         ScoreCtx sc2 = sctx;
-                        sc2.col_grp = &col_grp[c * 32];
-                        store_chunk<MODE, true, true>(rr, &col_off[c * 32], &col_scale[c * 32], p_hi, p_lo, p_f32, dcc, sc2);
+                        sc2.col_grp = &col_grp[c * cwid];
+                        store_chunk<MODE, true, true>(rr, &col_off[c * cwid], &col_scale[c * cwid], p_hi, p_lo, p_f32, dcc, sc2, cwid);
                     }
                     continue;
                 }
                 if (!row_ok) continue;
-                if (c * 32 + 32 <= n_lim) store_chunk<MODE, false, false>(rr, &col_off[c * 32], &col_scale[c * 32], p_hi, p_lo, p_f32, dcc, sctx);
-                else store_chunk<MODE, true, false>(rr, &col_off[c * 32], &col_scale[c * 32], p_hi, p_lo, p_f32, dcc, sctx);
+                if (c * cwid + cwid <= n_lim) store_chunk<MODE, false, false>(rr, &col_off[c * cwid], &col_scale[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid);
+                else store_chunk<MODE, true, false>(rr, &col_off[c * cwid], &col_scale[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid);
             }
             if (MODE == 1 && g.score_groups > 0) {
                 // max |value| of every token touched by this CTA's 128 accumulator rows: the rows of a token are
@@ -360,6 +387,367 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------ chained passes
+// Both passes of a transform in ONE persistent launch, so that the intermediate operand (P^T / Q^T) is read
+// back out of L2 instead of HBM.  Possible when the two passes use the same basis (square planes, kh == kw):
+// a CTA pair keeps its basis slice resident and alternates between pass-1 tiles of sub-batch s and pass-2
+// tiles of sub-batch s-1 (a sub-batch is `ps` planes, ~20 MB of intermediate).  A pass-2 tile may only start
+// when every pass-1 tile of its sub-batch has been stored: the epilogue warps publish their tiles in a global
+// counter per sub-batch, the TMA producer of a pass-2 tile polls it.  All pairs are co-resident (grid <= SMs,
+// one CTA per SM; the launcher checks it), and every pair finishes its pass-1 tiles of sub-batch s before it
+// waits for anything of sub-batch s, so the wait cannot deadlock.
+struct ChainPass {
+    int units;          // (segment of the group, block) combinations per basis group
+    int blocks;         // blocks of `planes` planes inside one segment
+    int rpp;            // stacked rows per plane
+    int rows_per_seg;   // blocks * planes * rpp
+};
+
+struct ChainSched {
+    ChainPass p[2];
+    int planes;         // planes per block
+    int ps;             // planes per sub-batch
+    int ns;             // sub-batches
+    int lag;            // pass-2 tiles of sub-batch s are scheduled together with the pass-1 tiles of sub-batch s + lag
+    int hints;          // 1: L2 eviction priorities (operands evict-first, intermediate evict-last); 0: none
+    int32_t* done;      // [ns] pass-1 warp completions per sub-batch (zeroed by the launcher)
+};
+
+struct ChainItem {
+    int pass, sb, seg, row0;
+};
+
+struct ChainWalk {
+    const ChainSched& sc;
+    int q, P, grp;
+    int l = -1;            // current list: even l = (pass 1, sb l/2); odd l = (pass 2, sb l/2 - lag)
+    int64_t pos = 0;       // global index of the first item of the current list
+    int j = 0, cnt = 0;    // next local index / size of the current list
+    int pass = 0, sb = 0, np = 0, tpu = 1;
+    __device__ ChainWalk(const ChainSched& s, int q_, int P_, int g_) : sc(s), q(q_), P(P_), grp(g_) {}
+    __device__ int planes_in(int sb_) const { return min(sc.ps, sc.planes - sb_ * sc.ps); }
+    __device__ int list_size(int pass_, int sb_) const {
+        if (sb_ < 0 || sb_ >= sc.ns) return 0;
+        return sc.p[pass_].units * (planes_in(sb_) * sc.p[pass_].rpp / 256);
+    }
+    __device__ bool next(ChainItem& w) {
+        while (true) {
+            if (l >= 0 && j < cnt) {
+                const int u = j / tpu, i = j - u * tpu;
+                const ChainPass& cp = sc.p[pass];
+                const int sg = u / cp.blocks, blk = u - sg * cp.blocks;
+                w.pass = pass;
+                w.sb = sb;
+                w.seg = sg * 2 + grp;
+                w.row0 = (blk * sc.planes + sb * sc.ps) * cp.rpp + i * 256;
+                j += P;
+                return true;
+            }
+            if (l >= 0) pos += cnt;
+            ++l;
+            if (l >= 2 * (sc.ns + sc.lag)) return false;
+            if (l & 1) { pass = 1; sb = (l >> 1) - sc.lag; }
+            else { pass = 0; sb = l >> 1; }
+            cnt = list_size(pass, sb);
+            if (cnt > 0) {
+                np = planes_in(sb);
+                tpu = np * sc.p[pass].rpp / 256;
+            }
+            const int64_t first = ((q - pos) % P + P) % P;       // smallest local index with (pos + j) % P == q
+            j = (int)first;
+        }
+    }
+};
+
+__device__ __forceinline__ void wait_counter(const int32_t* ptr, int expected) {
+    const long long t0 = clock64();
+    while (true) {
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+        if (v >= expected) break;
+        if (clock64() - t0 > 4000000000ll) __trap();
+        __nanosleep(100);
+    }
+    // the tiles were written through the generic proxy by other SMs and are about to be read by TMA
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
+fold_chain_kernel(const __grid_constant__ CUtensorMap map_a1_hi, const __grid_constant__ CUtensorMap map_a1_lo,
+                  const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  FoldGemm g, ChainSched sc, FoldEpi ep1, FoldEpi ep2) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[F_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[F_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full[2];
+    __shared__ __align__(8) uint64_t tmem_empty[2];
+    __shared__ __align__(8) uint64_t basis_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ __align__(16) int32_t col_off[2][288];
+    __shared__ __align__(16) float col_scale[2][288];
+    __shared__ __align__(16) int32_t col_grp[288];
+
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* basis_hi = smem;
+    uint8_t* basis_lo = smem + g.basis_bytes;
+    uint8_t* ring = smem + 2 * g.basis_bytes;
+    unsigned* smax = reinterpret_cast<unsigned*>(ring + g.stages * F_STAGE);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int grp = pair & 1;                                   // one N tile per group (checked by the launcher)
+    const int pair_in_slice = pair >> 1, pairs_per_slice = n_pairs >> 1;
+    const int n_lim = g.n_valid;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_a1_hi);
+        tma_prefetch_desc(&map_a1_lo);
+        tma_prefetch_desc(&map_a2_hi);
+        tma_prefetch_desc(&map_a2_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < F_MAX_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 16);
+        }
+        mbar_init(&basis_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 2 * 288; i += blockDim.x) {
+        const int ps = i / 288, n = i - ps * 288;
+        const FoldEpi& ep = ps ? ep2 : ep1;
+        int32_t off = -1;
+        float scl = 0.f;
+        int32_t grp_v = 0;
+        if (n < n_lim) {
+            const int line = n * ep.col_mul + grp * ep.col_add;
+            if (ep.mode == 2) {
+                const int th = line / ep.p, pi = line - th * ep.p;
+                off = th * ep.tiles_w * ep.channels * ep.p * ep.p + pi * ep.p;
+                const bool ends = (n == n_lim - 1) || ((n % g.chunk_w) == g.chunk_w - 1) || ((line + ep.col_mul) / ep.p != th);
+                grp_v = th | (ends ? (int32_t)0x80000000 : 0);
+            } else {
+                off = line * ep.col_stride;
+            }
+            scl = ep.alpha * (ep.basis_scale ? __ldg(ep.basis_scale + grp * g.n_valid + n) : 1.0f);
+        }
+        col_off[ps][n] = off;
+        col_scale[ps][n] = scl;
+        if (ps) col_grp[n] = grp_v;
+    }
+    for (int i = threadIdx.x; i < g.score_groups * 128; i += blockDim.x) smax[i] = 0u;
+    if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer
+        const uint32_t basis_bar_leader = mapa_u32(smem_u32(&basis_bar), 0);
+        const int half_rows = g.n_tile >> 1;
+        const uint32_t btile = (uint32_t)half_rows * 64;
+        if (rank == 0) mbar_expect_tx(&basis_bar, 4 * g.basis_bytes);
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+            const int row = (int)rank * half_rows;
+            tma_load_3d_2sm(&map_b_hi, basis_bar_leader, basis_hi + kb * btile, kb * FK, row, grp);
+            tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * btile, kb * FK, row, grp);
+        }
+        ChainWalk walk(sc, pair_in_slice, pairs_per_slice, grp);
+        ChainItem w;
+        uint32_t it = 0;
+        int waited_sb = -1;
+        const uint64_t pol_first = sc.hints ? l2_policy_evict_first() : l2_policy_evict_normal();   // operands are read once
+        while (walk.next(w)) {
+            if (w.pass == 1 && w.sb > waited_sb) {
+                // every pass-1 tile of this sub-batch, from both basis groups: 2 groups x tiles x 2 CTAs x 8 warps
+                wait_counter(sc.done + w.sb, 2 * walk.list_size(0, w.sb) * 16);
+                waited_sb = w.sb;
+            }
+            const CUtensorMap* mh = w.pass ? &map_a2_hi : &map_a1_hi;
+            const CUtensorMap* ml = w.pass ? &map_a2_lo : &map_a1_lo;
+            const int row0 = w.row0 + (int)rank * 128;
+            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+                const int s = it % g.stages;
+                mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
+                uint8_t* st = ring + s * F_STAGE;
+                const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * F_STAGE);
+                tma_load_3d_2sm_hint(mh, full_leader, st, kb * FK, row0, w.seg, pol_first);
+                tma_load_3d_2sm_hint(ml, full_leader, st + F_ATILE, kb * FK, row0, w.seg, pol_first);
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ---------------- MMA issuer (leader CTA only): the same basis serves both passes
+        const uint32_t idesc = fold_idesc(g.n_tile);
+        const uint32_t btile = (uint32_t)(g.n_tile >> 1) * 64;
+        const uint32_t bh = smem_u32(basis_hi), bl = smem_u32(basis_lo);
+        mbar_wait_cluster(&basis_bar, 0);
+        tc_fence_after();
+        ChainWalk walk(sc, pair_in_slice, pairs_per_slice, grp);
+        ChainItem w;
+        uint32_t it = 0, tcount = 0;
+        while (walk.next(w)) {
+            const int acc = tcount & 1;
+            mbar_wait_cluster(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc * 256;
+            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+                const int s = it % g.stages;
+                mbar_wait_cluster(&full_bar[s], (it / g.stages) & 1);
+                tc_fence_after();
+                const uint32_t base = smem_u32(ring + s * F_STAGE);
+#pragma unroll
+                for (int k = 0; k < FK / 16; ++k) {
+                    const uint32_t ko = k * 32;
+                    const uint64_t a_hi = smem_desc_sw64(base + ko);
+                    const uint64_t a_lo = smem_desc_sw64(base + F_ATILE + ko);
+                    const uint64_t b_hi = smem_desc_sw64(bh + kb * btile + ko);
+                    const uint64_t b_lo = smem_desc_sw64(bl + kb * btile + ko);
+                    umma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, (kb | k) ? 1u : 0u);
+                    umma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1u);
+                    umma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1u);
+                }
+                umma_commit_2sm(&empty_bar[s], 3);
+            }
+            umma_commit_2sm(&tmem_full[acc], 3);
+            ++tcount;
+        }
+    } else if (warp >= 2) {
+        // ---------------- epilogue warps
+        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
+        const int cwid = g.chunk_w;
+        const int n_chunks = (n_lim + cwid - 1) / cwid;
+        const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+        const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+        ChainWalk walk(sc, pair_in_slice, pairs_per_slice, grp);
+        ChainItem w;
+        uint32_t tcount = 0;
+        // the intermediate is read back within microseconds: keep it in L2; the final output is not read here
+        const uint64_t pol_last = sc.hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+        const uint64_t pol_first = sc.hints ? l2_policy_evict_first() : l2_policy_evict_normal();
+        // A finished pass-1 tile is published (fence + counter) only after the wait for the NEXT accumulator:
+        // by then its stores have drained, so the fence does not stall the epilogue.  The next tile must not
+        // depend on the pending publication (a pass-2 tile of the same or a later sub-batch would wait for it
+        // in the producer while we wait for its accumulator): then publish first.
+        int pending_sb = -1;
+        auto publish = [&]() {
+            if (pending_sb >= 0) {
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(sc.done + pending_sb, 1);
+                pending_sb = -1;
+            }
+        };
+        while (walk.next(w)) {
+            const FoldEpi& ep = w.pass ? ep2 : ep1;
+            const int rows_per_seg = sc.p[w.pass].rows_per_seg;
+            const int r = w.row0 + (int)rank * 128 + quarter * 32 + lane;   // stacked row
+            const bool row_ok = r < rows_per_seg;
+            const int item = r / ep.rows_per_item, rin = r - item * ep.rows_per_item;
+            const bool scoring = w.pass == 1 && g.score_groups > 0;
+            int64_t base;
+            ScoreCtx sctx{};
+            if (ep.mode == 2) {
+                const int img = item / ep.channels, ch = item - img * ep.channels;
+                const int tw = rin / ep.p, pj = rin - tw * ep.p;
+                const int64_t tok0 = ((int64_t)img * ep.tiles_h * ep.tiles_w + tw) * ep.channels + ch;
+                base = tok0 * (ep.p * ep.p) + pj;
+                sctx.smax = smax + quarter * 32 + lane;
+            } else {
+                base = (int64_t)w.seg * ep.seg_stride + (int64_t)item * ep.item_stride + rin;
+            }
+            const bool dc_slice = (ep.dc != nullptr) && grp == 0;
+            const float dcv = (dc_slice && row_ok && rin == 0) ? __ldg(ep.dc + item) : 0.0f;
+            const uint64_t p_hi = reinterpret_cast<uint64_t>(ep.out_hi + base);
+            const uint64_t p_lo = reinterpret_cast<uint64_t>(ep.out_lo + base);
+            const uint64_t p_f32 = reinterpret_cast<uint64_t>(ep.out_f32 + base);
+            const int acc = tcount & 1;
+            if (w.pass == 1 && w.sb >= pending_sb) publish();
+            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            tc_fence_after();
+            publish();
+            const uint32_t tmem_acc = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
+            int last = n_chunks - 1;
+            if ((last & 1) != chalf) --last;
+            if (last < chalf) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+            }
+            const int32_t* coff = col_off[w.pass];
+            const float* cscl = col_scale[w.pass];
+#pragma unroll 1
+            for (int c = chalf; c < n_chunks; c += 2) {
+                uint32_t rr[32];
+                tmem_ld32_nowait(tmem_acc + c * cwid, rr);
+                tmem_ld_wait();
+                if (c == last) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+                }
+                if (!row_ok) continue;
+                const float dcc = c == 0 ? dcv : 0.0f;
+                if (w.pass == 0) {
+                    if (c * cwid + cwid <= n_lim) store_chunk<0, false, false, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid, pol_last);
+                    else store_chunk<0, true, false, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid, pol_last);
+                } else if (scoring) {
+                    ScoreCtx sc2 = sctx;
+                    sc2.col_grp = &col_grp[c * cwid];
+                    store_chunk<1, true, true, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sc2, cwid, pol_first);
+                } else {
+                    if (c * cwid + cwid <= n_lim) store_chunk<1, false, false, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid, pol_first);
+                    else store_chunk<1, true, false, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid, pol_first);
+                }
+            }
+            if (w.pass == 0) {
+                // this warp's share of the tile: its stores must be visible device-wide (and to the async proxy
+                // of the consumer's TMA loads) before the count moves -- see publish()
+                pending_sb = w.sb;
+            } else if (scoring) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int R0 = w.row0 + (int)rank * 128;
+                const int Rend = min(R0 + 128, rows_per_seg);
+                if (Rend > R0) {
+                    const int s_first = R0 / ep.p, n_cols = (Rend - 1) / ep.p - s_first + 1;
+                    for (int i = (int)threadIdx.x - 64; i < g.score_groups * n_cols; i += 256) {
+                        const int th = i / n_cols, scol = s_first + (i - th * n_cols);
+                        const int lo = max(R0, scol * ep.p) - R0, hi = min(Rend, scol * ep.p + ep.p) - R0;
+                        unsigned m = 0;
+                        for (int rr_ = lo; rr_ < hi; ++rr_) {
+                            m = max(m, smax[th * 128 + rr_]);
+                            smax[th * 128 + rr_] = 0u;
+                        }
+                        if (m != 0u) {
+                            const int plane = scol / ep.tiles_w, tw = scol - plane * ep.tiles_w;
+                            const int img = plane / ep.channels, ch = plane - img * ep.channels;
+                            atomicMax(reinterpret_cast<unsigned*>(ep.maxabs) +
+                                          (((int64_t)img * ep.tiles_h + th) * ep.tiles_w + tw) * ep.channels + ch, m);
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            ++tcount;
+        }
+        publish();
     }
     __syncwarp();
     tc_fence_before();
@@ -397,7 +785,7 @@ struct FoldOperand {
 };
 
 // slice geometry for a basis of n_valid rows and K columns: (n_tile, n_ntiles, stages), or false if nothing fits
-static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0) {
+static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0, int extra_static = 0) {
     g.num_kb = (int)ceil_div(K, FK);
     g.n_valid = n_valid;
     g.score_groups = score_groups;
@@ -405,12 +793,14 @@ static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0)
     for (int nn = (int)ceil_div(n_valid, 256); nn <= 16; ++nn) {
         const int n_tile = (int)ceil_div(ceil_div(n_valid, nn), 16) * 16;
         const int64_t basis = (int64_t)g.num_kb * (n_tile / 2) * 64;
-        const int64_t stages = (F_SMEM_LIMIT - 1024 - 2 * basis - score_bytes) / F_STAGE;
+        const int64_t stages = (F_SMEM_LIMIT - extra_static - 1024 - 2 * basis - score_bytes) / F_STAGE;
         if (n_tile <= 256 && stages >= 3) {
             g.n_tile = n_tile;
             g.n_ntiles = nn;
             g.basis_bytes = (uint32_t)basis;
             g.stages = (int)(stages < F_MAX_STAGES ? stages : F_MAX_STAGES);
+            const int pairs_of_chunks = (int)ceil_div(n_tile, 64);
+            g.chunk_w = (int)ceil_div(ceil_div(n_tile, 2 * pairs_of_chunks), 4) * 4;
             return 4 * basis < (1 << 20);      // mbarrier transaction-count range
         }
     }
@@ -455,6 +845,80 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
     }
     if (e != cudaSuccess) { set_error("fold_gemm: %s", cudaGetErrorString(e)); return DCTA_ERR_LAUNCH; }
     return check_launch("fold_gemm");
+}
+
+// Both passes in one launch (see fold_chain_kernel).  Returns DCTA_ERR_UNSUPPORTED (without setting an error
+// the caller has to report) when the geometry does not allow it; the caller then launches the passes one by one.
+static int launch_fold_chain(const FoldOperand& A1, const FoldOperand& A2, const FoldOperand& Bas, int n_valid, int K,
+                             int64_t n_planes, ChainPass p1, ChainPass p2, int32_t* done, int done_len, FoldEpi ep1,
+                             FoldEpi ep2, void* stream) {
+    // Opt-in (DCTA_CHAIN=1).  Measured on B200 (profiles/r01_chain_experiment.txt): the chained launch does read
+    // most of the intermediate back from L2 (DRAM reads of the forward passes 762 -> 492 MB per 128 images) but the
+    // passes are no longer DRAM-bound at that point and the launch is 6-10 % SLOWER than the two separate launches,
+    // so the separate launches stay the default.
+    static const bool enabled = getenv("DCTA_CHAIN") != nullptr && atoi(getenv("DCTA_CHAIN")) != 0;
+    if (!enabled || done == nullptr) return DCTA_ERR_UNSUPPORTED;
+    FoldGemm g{};
+    const int score_groups = (ep2.mode == 2 && ep2.maxabs != nullptr) ? ep2.tiles_h : 0;
+    if (!fold_geometry(n_valid, K, g, score_groups, 2048) || g.n_ntiles != 1) return DCTA_ERR_UNSUPPORTED;
+    if (n_planes % 8 || p1.rpp % 32 || p2.rpp % 32 || n_planes * 4 * (int64_t)(p1.rpp > p2.rpp ? p1.rpp : p2.rpp) >= (1ll << 31))
+        return DCTA_ERR_UNSUPPORTED;
+    // sub-batch: about 20 MB of intermediate (pass-2 operand: hi + lo fp16), a multiple of 8 planes
+    static const int env_mb = getenv("DCTA_CHAIN_MB") ? atoi(getenv("DCTA_CHAIN_MB")) : 20;
+    static const int env_lag = getenv("DCTA_CHAIN_LAG") ? atoi(getenv("DCTA_CHAIN_LAG")) : 1;
+    const int64_t inter_per_plane = (int64_t)p2.units * p2.rpp * K * 4;
+    int ps = (int)(((int64_t)env_mb << 20) / (inter_per_plane > 0 ? inter_per_plane : 1)) / 8 * 8;
+    if (ps < 8) ps = 8;
+    if (ps > n_planes) ps = (int)n_planes;
+    ChainSched sc{};
+    sc.p[0] = p1;
+    sc.p[1] = p2;
+    sc.planes = (int)n_planes;
+    sc.ps = ps;
+    sc.ns = (int)ceil_div(n_planes, ps);
+    sc.lag = env_lag < 1 ? 1 : env_lag;
+    static const int env_hints = getenv("DCTA_CHAIN_HINTS") ? atoi(getenv("DCTA_CHAIN_HINTS")) : 1;
+    sc.hints = env_hints;
+    sc.done = done;
+    if (sc.ns > done_len) return DCTA_ERR_UNSUPPORTED;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int pps = (sms / 2) / 2;                     // pairs per basis group
+    if (pps < 1) return DCTA_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)(4 * pps);
+    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4;
+    if (cudaFuncSetAttribute(fold_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return DCTA_ERR_UNSUPPORTED;
+    }
+    // the pass-2 producers spin on the progress of other pairs: every pair must be resident at once
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(F_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, fold_chain_kernel, &cfg) != cudaSuccess || max_clusters < (int)(grid / 2)) {
+        cudaGetLastError();
+        return DCTA_ERR_UNSUPPORTED;
+    }
+    CUtensorMap m1h, m1l, m2h, m2l, mbh, mbl;
+    int rc;
+    if ((rc = make_map3(&m1h, A1.hi, K, p1.rows_per_seg, 2, A1.ld, A1.seg_stride, 128))) return rc;
+    if ((rc = make_map3(&m1l, A1.lo, K, p1.rows_per_seg, 2, A1.ld, A1.seg_stride, 128))) return rc;
+    const int segs2 = 2 * (p2.units / p2.blocks);
+    if ((rc = make_map3(&m2h, A2.hi, K, p2.rows_per_seg, segs2, A2.ld, A2.seg_stride, 128))) return rc;
+    if ((rc = make_map3(&m2l, A2.lo, K, p2.rows_per_seg, segs2, A2.ld, A2.seg_stride, 128))) return rc;
+    if ((rc = make_map3(&mbh, Bas.hi, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
+    if ((rc = make_map3(&mbl, Bas.lo, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
+    cudaMemsetAsync(done, 0, sizeof(int32_t) * sc.ns, as_stream(stream));
+    fold_chain_kernel<<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(m1h, m1l, m2h, m2l, mbh, mbl, g, sc, ep1, ep2);
+    return check_launch("fold_chain");
 }
 
 // ------------------------------------------------------------------------------ fold / unfold kernels
@@ -880,7 +1344,8 @@ extern "C" int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float*
 extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
                                   const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
                                   const float* rs_h, void* work_hi, void* work_lo, float* y, float* maxabs,
-                                  int64_t n_planes, int h, int w, int kh, int kw, int tile_p, int channels, void* stream) {
+                                  int32_t* chain_scratch, int64_t n_planes, int h, int w, int kh, int kw, int tile_p,
+                                  int channels, void* stream) {
     DCTA_REQUIRE(xq_hi && xq_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && y,
                  "dct2_fwd_fold: null pointer");
     DCTA_REQUIRE(maxabs == nullptr || tile_p > 0, "dct2_fwd_fold: maxabs needs the token-grid output");
@@ -898,8 +1363,6 @@ extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const fl
     e1.rows_per_item = h2; e1.seg_stride = 0; e1.item_stride = (int64_t)kw * h2;
     e1.col_mul = 2; e1.col_add = 1; e1.col_stride = h2;
     e1.alpha = kFScaleP / kFScaleX; e1.basis_scale = rs_w;
-    int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)h2, 2, B1, kw / 2, w2, e1, stream);
-    if (rc) return rc;
     // pass 2: Y[2i+a, kw] = sum_h' CH[2i+a, h'] P^T[a][plane][kw][h']   (+ the removed constant's DC at [0,0])
     FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, h2, n_planes * (int64_t)kw * h2};
     FoldOperand B2{(const __half*)bh_hi, (const __half*)bh_lo, h2, (int64_t)(kh / 2) * h2};
@@ -915,6 +1378,15 @@ extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const fl
     } else {
         e2.mode = 1; e2.seg_stride = 0; e2.item_stride = (int64_t)kh * kw; e2.col_stride = kw;
     }
+    if (h == w && kh == kw && bw_hi == bh_hi && bw_lo == bh_lo && rs_w == rs_h) {
+        // square planes: one resident basis serves both passes; the intermediate stays in L2
+        ChainPass p1{2, 2, h2, (int)(2 * n_planes * h2)}, p2{1, 1, kw, (int)(n_planes * kw)};
+        const int rc = launch_fold_chain(A1, A2, B1, kw / 2, w2, n_planes, p1, p2, chain_scratch, DCTA_CHAIN_SCRATCH,
+                                         e1, e2, stream);
+        if (rc != DCTA_ERR_UNSUPPORTED) return rc;
+    }
+    int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)h2, 2, B1, kw / 2, w2, e1, stream);
+    if (rc) return rc;
     return launch_fold_gemm(A2, n_planes * (int64_t)kw, 2, B2, kh / 2, h2, e2, stream);
 }
 
@@ -922,7 +1394,7 @@ extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const fl
 //   bwt: (2, w/2, ldq) = CW[2j+b, w']^T, bht: (2, h/2, ldi) = CH[2i+a, h']^T; work: (2, 2, n_planes, w/2, ldi) hi/lo
 extern "C" int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const void* bwt_hi, const void* bwt_lo,
                                   const void* bht_hi, const void* bht_lo, void* work_hi, void* work_lo, float* z,
-                                  int64_t n_planes, int h, int w, int kh, int kw, void* stream) {
+                                  int32_t* chain_scratch, int64_t n_planes, int h, int w, int kh, int kw, void* stream) {
     DCTA_REQUIRE(yq_hi && yq_lo && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && z,
                  "dct2_inv_fold: null pointer");
     DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_inv_fold: needs h, w multiples of 16 and even kh <= h, kw <= w");
@@ -937,8 +1409,6 @@ extern "C" int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const vo
     e1.rows_per_item = kh2; e1.seg_stride = 2 * n_planes * (int64_t)w2 * ldi; e1.item_stride = (int64_t)w2 * ldi;
     e1.col_mul = 1; e1.col_add = 0; e1.col_stride = (int)ldi;
     e1.alpha = kFScaleQ / (kFScaleBasis * kFScaleY);
-    int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)kh2, 2, B1, w2, kw2, e1, stream);
-    if (rc) return rc;
     // pass 2: Z[(b, a)][plane][h', w'] = sum_i CH[2i+a, h'] Q^T[b][a][plane][w'][i]
     FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, ldi, n_planes * (int64_t)w2 * ldi};
     FoldOperand B2{(const __half*)bht_hi, (const __half*)bht_lo, ldi, (int64_t)h2 * ldi};
@@ -947,6 +1417,14 @@ extern "C" int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const vo
     e2.seg_stride = n_planes * (int64_t)h2 * w2; e2.item_stride = (int64_t)h2 * w2;
     e2.col_mul = 1; e2.col_add = 0; e2.col_stride = w2;
     e2.alpha = 1.0f / (kFScaleBasis * kFScaleQ);
+    if (h == w && kh == kw && bwt_hi == bht_hi && bwt_lo == bht_lo) {
+        ChainPass p1{2, 2, kh2, (int)(2 * n_planes * kh2)}, p2{2, 1, w2, (int)(n_planes * w2)};
+        const int rc = launch_fold_chain(A1, A2, B1, w2, kw2, n_planes, p1, p2, chain_scratch, DCTA_CHAIN_SCRATCH, e1, e2,
+                                         stream);
+        if (rc != DCTA_ERR_UNSUPPORTED) return rc;
+    }
+    int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)kh2, 2, B1, w2, kw2, e1, stream);
+    if (rc) return rc;
     return launch_fold_gemm(A2, n_planes * (int64_t)w2, 4, B2, h2, kh2, e2, stream);
 }
 

@@ -814,7 +814,7 @@ using namespace dcta;
 // Scales of the split operands (powers of two, exact): images/IPT 2^8, forward intermediate 2^6,
 // coefficient planes 2^4, inverse intermediate 2^6; basis 2^10 (folded into row_scale / alpha).
 static const float kScaleX = 256.f, kScaleP = 64.f, kScaleY = 16.f, kScaleQ = 64.f, kScaleBasis = 1024.f;
-static const int kSumStride = 4;   // plane-mean estimate from every 4th quad
+static const int kSumStride = 16;  // plane-mean estimate from every 16th run of 128 quads (any estimate is exact: it is added back)
 
 extern "C" int dcta_gemm_split(const void* a_hi, const void* a_lo, int a_rows, int64_t a_ld, int64_t a_batch_stride,
                                const void* b_hi, const void* b_lo, int b_rows, int64_t b_ld, int64_t b_batch_stride,

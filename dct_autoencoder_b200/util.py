@@ -465,11 +465,12 @@ def dct2_fwd_fold(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: Optional[torch.T
     if with_maxabs:
         assert tile_p > 0
         maxabs = torch.empty(y.shape[:4], dtype=torch.float32, device=dev)
+    chain = torch.empty(_lib.CHAIN_SCRATCH, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dcta_dct2_fwd_fold", _lib.ptr(xq_hi), _lib.ptr(xq_lo), _lib.ptr(dc), _lib.ptr(bw_hi),
                   _lib.ptr(bw_lo), _lib.ptr(rs_w), _lib.ptr(bh_hi), _lib.ptr(bh_lo), _lib.ptr(rs_h), _lib.ptr(work_hi),
-                  _lib.ptr(work_lo), _lib.ptr(y), _lib.ptr(maxabs), n_planes, h, w, kh, kw, tile_p, channels,
-                  _lib.stream_ptr(dev))
+                  _lib.ptr(work_lo), _lib.ptr(y), _lib.ptr(maxabs), _lib.ptr(chain), n_planes, h, w, kh, kw, tile_p,
+                  channels, _lib.stream_ptr(dev))
     return (y, maxabs) if with_maxabs else y
 
 
@@ -484,9 +485,10 @@ def dct2_inv_fold(yq_hi: torch.Tensor, yq_lo: torch.Tensor, kh: int, kw: int, h:
     work_hi = torch.empty((2, 2, n_planes, w // 2, ldi), dtype=torch.float16, device=dev)
     work_lo = torch.empty_like(work_hi)
     z = torch.empty((4, n_planes, h // 2, w // 2), dtype=torch.float32, device=dev)
+    chain = torch.empty(_lib.CHAIN_SCRATCH, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dcta_dct2_inv_fold", _lib.ptr(yq_hi), _lib.ptr(yq_lo), _lib.ptr(bwt_hi), _lib.ptr(bwt_lo),
-                  _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z),
+                  _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z), _lib.ptr(chain),
                   n_planes, h, w, kh, kw, _lib.stream_ptr(dev))
     return z
 

@@ -30,6 +30,8 @@ extern "C" {
 #define DCTA_ERR_INVALID_ARG (-1)
 #define DCTA_ERR_LAUNCH (-2)
 #define DCTA_ERR_UNSUPPORTED (-3)
+/* int32 elements of the chain_scratch argument of dcta_dct2_fwd_fold / dcta_dct2_inv_fold */
+#define DCTA_CHAIN_SCRATCH 4096
 
 const char* dcta_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
@@ -139,11 +141,14 @@ int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float* dc, float*
  *   rs_w (2, kw/2) the factors undoing those scales;  bh_hi/lo (2, kh/2, h/2), rs_h likewise (group a);
  *   work_hi/lo (2, n_planes, kw, h/2) scratch;
  *   maxabs [nullable, token grid only] (n_planes/channels, kh/p, kw/p, channels): amax|tile| of every token
- *   (FE:409), reduced in the GEMM epilogue (input of dcta_sort_tokens_maxabs). */
+ *   (FE:409), reduced in the GEMM epilogue (input of dcta_sort_tokens_maxabs);
+ *   chain_scratch [nullable]: DCTA_CHAIN_SCRATCH int32 of device scratch.  When given, and the planes are square
+ *   with bw == bh (same pointers), both passes run in ONE launch and the intermediate is read back from L2. */
 int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
                        const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
-                       const float* rs_h, void* work_hi, void* work_lo, float* y, float* maxabs, int64_t n_planes,
-                       int h, int w, int kh, int kw, int tile_p, int channels, void* stream);
+                       const float* rs_h, void* work_hi, void* work_lo, float* y, float* maxabs,
+                       int32_t* chain_scratch, int64_t n_planes, int h, int w, int kh, int kw, int tile_p,
+                       int channels, void* stream);
 /* FE:635-653 un-patchify into folded coefficient quadrants yq_hi/lo (2, 2, n_img*channels, rows/2, ldq)
  * [b][a][plane][i][j] = Y[2i+a, 2j+b] * 2^4, ldq = round8(cols/2); DC moved to dc as in dcta_unpatchify_split. */
 int dcta_unpatchify_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
@@ -162,7 +167,7 @@ int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, float* dc, i
  *   work_hi/lo (2, 2, n_planes, w/2, ldi) scratch. */
 int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const void* bwt_hi, const void* bwt_lo,
                        const void* bht_hi, const void* bht_lo, void* work_hi, void* work_lo, float* z,
-                       int64_t n_planes, int h, int w, int kh, int kw, void* stream);
+                       int32_t* chain_scratch, int64_t n_planes, int h, int w, int kh, int kw, void* stream);
 /* Final butterfly (+ the DC constant dc[plane], nullable) fused with UT:85-97 ipt_to_rgb: rgb (n_img, 3, h, w). */
 int dcta_unfold_ipt_to_rgb(const float* z, const float* dc, float* rgb, int64_t n_img, int h, int w,
                            const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream);
