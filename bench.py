@@ -304,7 +304,10 @@ def run_ours(a):
         roofline = dict(bound="hbm", kernel="fold_gemm_kernel (4 launches per step: forward passes 1-2, inverse passes 1-2; "
                         "cta_group::2 tcgen05 fp16x3 split precision, folded basis resident in shared memory)",
                         achieved=achieved_gbs, peak=hbm, unit="GB/s", frac=achieved_gbs / hbm,
-                        traffic=None, launches_per_step=4, avg_launch_ms=gemm_ms / 4,
+                        # dram__bytes_read + write per launch, ncu --set full of this workload
+                        # (profiles/r01x_kernels_ncu_full_b256.txt: 1274 / 1459 / 1465 / 1414 MB for the 4 launches)
+                        traffic=(1.403e9 if (B == 256 and S == 512) else None),
+                        launches_per_step=4, avg_launch_ms=gemm_ms / 4,
                         algorithmic_bytes_per_launch=sum(alg) * B / 4,
                         peak_source=("measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"),
                         tensor=dict(achieved=tens, peak=peak_tf, unit="TFLOP/s", frac=tens / peak_tf,

@@ -1,7 +1,7 @@
 """Turns ncu outputs brought back in gpurun_out/ into the text summaries committed here.
 
-    python profiles/summarize.py launches gpurun_out/launches_X.csv  > profiles/rNN_launches.txt
-    python profiles/summarize.py kernel   gpurun_out/prof_X.ncu-rep  > profiles/rNN_kernel.txt
+    python profiles/summarize.py launches gpurun_out/launches_X.csv [N]  > profiles/rNN_launches.txt
+    python profiles/summarize.py kernel   gpurun_out/prof_X.ncu-rep      > profiles/rNN_kernel.txt
 """
 import collections
 import csv
@@ -9,30 +9,39 @@ import subprocess
 import sys
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__t_sector_hit_rate.pct",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
-        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.ratio",
+        "smsp__sass_average_data_bytes_per_sector_mem_global_op_st.ratio",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
-        "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
-        "sm__maximum_warps_per_active_cycle_pct", "smsp__cycles_active.avg"]
+        "launch__occupancy_limit_shared_mem", "launch__shared_mem_per_block_dynamic"]
 
 
-def launches(path):
+def launches(path, last=0):
     rows = list(csv.reader(open(path)))
     hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr, data = rows[hi], rows[hi + 1:]
     kn, mv, mn = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+    seq = [(r[kn].split("(")[0], float(r[mv].replace(",", ""))) for r in data
+           if len(r) > mv and r[mn] == "gpu__time_duration.sum"]
+    if last:
+        seq = seq[-last:]
+        tot = sum(v for _, v in seq)
+        print(f"# {path}: the last {last} launches = one warm step, {tot / 1e6:.3f} ms in total "
+              "(ncu per-launch times are cold-cache and serialised: compare SHARES)")
+        for k, v in seq:
+            print(f"{v / 1e3:10.1f} us {100 * v / tot:5.1f}%  {k}")
+        return
     agg = collections.OrderedDict()
-    for r in data:
-        if len(r) <= mv or r[mn] != "gpu__time_duration.sum":
-            continue
-        a = agg.setdefault(r[kn].split("(")[0], [0, 0.0])
+    for k, v in seq:
+        a = agg.setdefault(k, [0, 0.0])
         a[0] += 1
-        a[1] += float(r[mv].replace(",", ""))
+        a[1] += v
     tot = sum(v[1] for v in agg.values())
     print(f"# {path}: {sum(v[0] for v in agg.values())} launches, {tot / 1e6:.3f} ms total "
           "(ncu per-launch times are cold-cache and serialised: compare SHARES)")
@@ -46,7 +55,7 @@ def kernel(path):
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
-        print("kernel:", r[hdr.index("Kernel Name")])
+        print("kernel:", r[hdr.index("Kernel Name")][:110])
         for k in KEYS:
             if k in hdr:
                 i = hdr.index(k)
@@ -54,4 +63,7 @@ def kernel(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+    else:
+        kernel(sys.argv[2])
