@@ -31,7 +31,7 @@ constexpr int F_ATILE = 128 * FK * 2;     // one 128-row operand tile (hi or lo)
 constexpr int F_STAGE = 2 * F_ATILE;      // a ring stage: this CTA's A_hi, A_lo
 constexpr int F_THREADS = 320;
 constexpr int F_MAX_STAGES = 8;
-constexpr int F_SMEM_LIMIT = 227 * 1024 - 4096;   // dynamic shared memory we allow ourselves (static: ~2.3 KB)
+constexpr int F_SMEM_LIMIT = 227 * 1024 - 5120;   // dynamic shared memory we allow ourselves (static: ~2.3 KB)
 
 struct FoldGemm {
     int n_seg;            // data segments (3rd tensor-map coordinate); basis group of a segment = seg & 1
@@ -44,6 +44,7 @@ struct FoldGemm {
     int stages;
     uint32_t basis_bytes; // one CTA's resident basis plane (hi or lo): num_kb * (n_tile/2) * 64
     int score_groups;     // > 0: tile rows of the token grid; a [score_groups][128] max|value| image follows the ring
+    int code_cols;        // > 0: token columns a CTA's 128 rows can touch; a [n_tile][code_cols] code-word image follows
     int chunk_w;          // accumulator columns an epilogue warp takes at a time (multiple of 4, <= 32; an even
                           // number of chunks covers n_tile so that the two warps of a lane quarter get equal shares)
 };
@@ -62,6 +63,13 @@ struct FoldEpi {
     const float* basis_scale;    // optional (2, n_valid) per-basis-row factors
     const float* dc;             // optional per-item constant added to (group 0, basis row 0, row-in-item 0)
     int p, channels, tiles_h, tiles_w;   // mode 2
+    int32_t* code_grid;          // mode 2, optional: (n_img, tiles_h, tiles_w, channels, p) LFQ code words of the
+                                 // PatchNorm-normalised coefficients INSTEAD of the token grid (needs maxabs too)
+    const float* med;            //   PatchNorm median / b tables (channels, stat_h, stat_w, p*p), clamp and eps
+    const float* bstat;
+    int stat_h, stat_w;
+    float eps, clamp_lo, clamp_hi;
+    const int32_t* tame;         //   device flag: every b is a tame divisor (launch_b_tame)
     float* maxabs;               // mode 2, optional: (n_img, tiles_h, tiles_w, channels) max |coefficient| of every token,
                                  // accumulated with atomicMax on the bit pattern (the buffer must start at zero)
 };
@@ -156,6 +164,71 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&rr)[32], const int3
     }
 }
 
+// Forward pass 2 producing LFQ code words directly (one codebook per patch row, d == p): the value of column n
+// and row r is coefficient (kh = line(n), kw = r); its sign bit after PatchNorm is the sign of value - median
+// (exactly: see norm_sign_bit / the tame-divisor argument in fused_lfq.cu).  The 14 bits of one code word are
+// held by 14 consecutive lanes: one ballot per column, every lane cuts out the field of ITS token and the first
+// lane of the token ORs it into the shared code-word image (tokens can straddle warps and CTAs).
+struct SignCtx {
+    const float* med;          // + this row's base offset
+    const float* bst;
+    const int32_t* col_moff;   // per column: offset of (tile row, row-in-tile) in the statistics, < 0 past the end
+    const int32_t* col_grp;
+    unsigned* smax;            // as ScoreCtx
+    unsigned* codes_s;         // shared code-word image + this row's token column
+    int code_cols;
+    int l0, cnt, sh;           // lanes [l0, l0+cnt) hold this row's token; left shift of the field inside the word
+    unsigned cmask;
+    bool leader, row_ok, tame;
+    LfqNormParams q;
+};
+
+__device__ __forceinline__ void sign_chunk(const uint32_t (&rr)[32], const float* col_scale, float dcv, const SignCtx& sx,
+                                           int n0, int width) {
+    // all medians of the chunk first (independent loads, one L2 latency for the lot)
+    float mv[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        if (j >= width) break;
+        const int4 moff = *reinterpret_cast<const int4*>(sx.col_moff + j);
+        const int mo[4] = {moff.x, moff.y, moff.z, moff.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mv[j + u] = (sx.row_ok && mo[u] >= 0) ? __ldg(sx.med + mo[u]) : 0.0f;
+    }
+    float m = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        if (j >= width) break;
+        const int4 moff = *reinterpret_cast<const int4*>(sx.col_moff + j);
+        const int4 grp = *reinterpret_cast<const int4*>(sx.col_grp + j);
+        const float4 sc = *reinterpret_cast<const float4*>(col_scale + j);
+        float vv[4] = {__uint_as_float(rr[j]) * sc.x, __uint_as_float(rr[j + 1]) * sc.y,
+                       __uint_as_float(rr[j + 2]) * sc.z, __uint_as_float(rr[j + 3]) * sc.w};
+        if (j == 0) vv[0] += dcv;
+        const int mo[4] = {moff.x, moff.y, moff.z, moff.w};
+        const int gg[4] = {grp.x, grp.y, grp.z, grp.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (mo[u] >= 0) {                    // warp-uniform
+                bool bit = false;
+                if (sx.row_ok) {
+                    const float diff = __fsub_rn(vv[u], mv[j + u]);
+                    if (sx.tame && fabsf(diff) > 1e-20f) bit = diff > 0.0f;
+                    else bit = norm_sign_bit(vv[u], mv[j + u], __ldg(sx.bst + mo[u]), sx.q);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, bit);
+                const unsigned part = (__brev((bal >> sx.l0) & sx.cmask) >> (32 - sx.cnt)) << sx.sh;
+                if (sx.leader && part) atomicOr(sx.codes_s + (n0 + j + u) * sx.code_cols, part);
+            }
+            m = fmaxf(m, fabsf(vv[u]));
+            if (gg[u] < 0) {
+                if (sx.row_ok) atomicMax(sx.smax + (gg[u] & 0x7fffffff) * 128, __float_as_uint(m));
+                m = 0.0f;
+            }
+        }
+    }
+}
+
 template <int MODE>   // 0: fp16 hi/lo output, 1: fp32 output (plain or token grid)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
 fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -171,12 +244,14 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __shared__ __align__(16) int32_t col_off[288];     // n_tile + one chunk of slack (guarded reads past the end)
     __shared__ __align__(16) float col_scale[288];
     __shared__ __align__(16) int32_t col_grp[288];
+    __shared__ __align__(16) int32_t col_moff[288];
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* basis_hi = smem;
     uint8_t* basis_lo = smem + g.basis_bytes;
     uint8_t* ring = smem + 2 * g.basis_bytes;
     unsigned* smax = reinterpret_cast<unsigned*>(ring + g.stages * F_STAGE);
+    unsigned* codes_s = smax + g.score_groups * 128;            // [n_tile][code_cols]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -229,8 +304,15 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             grp_v = th | (ends ? (int32_t)0x80000000 : 0);
         }
         col_grp[n] = grp_v;
+        int32_t mo = -1;
+        if (ep.mode == 2 && ep.code_grid != nullptr && n < n_lim) {
+            const int line = (nt * g.n_tile + n) * ep.col_mul + grp * ep.col_add;
+            const int th = line / ep.p, pi = line - th * ep.p;
+            mo = th * ep.stat_w * ep.p * ep.p + pi * ep.p;
+        }
+        col_moff[n] = mo;
     }
-    for (int i = threadIdx.x; i < g.score_groups * 128; i += blockDim.x) smax[i] = 0u;
+    for (int i = threadIdx.x; i < g.score_groups * 128 + g.n_tile * g.code_cols; i += blockDim.x) smax[i] = 0u;
     if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
     tc_fence_before();
     __syncthreads();
@@ -305,6 +387,9 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
         const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
         const bool dc_slice = (ep.dc != nullptr) && grp == 0 && nt == 0;
+        const bool signs = MODE == 1 && g.code_cols > 0;
+        const bool tame = signs && ep.tame != nullptr && __ldg(ep.tame) != 0 && ep.eps > 1e-12f && ep.clamp_lo < 0.0f &&
+                          ep.clamp_hi > 0.0f;
         uint32_t tcount = 0;
         for (int w = pair_in_slice; w < n_work; w += pairs_per_slice, ++tcount) {
             const int seg = (w / g.tiles_per_seg) * 2 + grp;
@@ -313,12 +398,32 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const int item = r / ep.rows_per_item, rin = r - item * ep.rows_per_item;
             int64_t base;
             ScoreCtx sctx{};
+            SignCtx sx{};
             if (ep.mode == 2) {
                 const int img = item / ep.channels, ch = item - img * ep.channels;
                 const int tw = rin / ep.p, pj = rin - tw * ep.p;
                 const int64_t tok0 = ((int64_t)img * ep.tiles_h * ep.tiles_w + tw) * ep.channels + ch;   // token at tile row 0
                 base = tok0 * (ep.p * ep.p) + pj;
                 sctx.smax = smax + quarter * 32 + lane;
+                if (signs) {
+                    const int64_t mbase = ((int64_t)ch * ep.stat_h * ep.stat_w + tw) * (ep.p * ep.p) + pj;
+                    sx.med = ep.med + mbase;
+                    sx.bst = ep.bstat + mbase;
+                    sx.col_grp = col_grp;
+                    sx.smax = sctx.smax;
+                    sx.code_cols = g.code_cols;
+                    const int R0 = (w % g.tiles_per_seg) * 256 + (int)rank * 128;
+                    sx.codes_s = codes_s + (r / ep.p - R0 / ep.p);
+                    sx.l0 = max(0, lane - pj);
+                    const int px0 = pj - (lane - sx.l0);
+                    sx.cnt = min(32 - sx.l0, ep.p - px0);
+                    sx.sh = ep.p - px0 - sx.cnt;
+                    sx.cmask = sx.cnt >= 32 ? 0xffffffffu : ((1u << sx.cnt) - 1u);
+                    sx.row_ok = row_ok;
+                    sx.leader = row_ok && lane == sx.l0;
+                    sx.tame = tame;
+                    sx.q = LfqNormParams{nullptr, nullptr, 0, 0, 0, 0, ep.eps, ep.clamp_lo, ep.clamp_hi, 0, 0, 0.f};
+                }
             } else {
                 base = (int64_t)seg * ep.seg_stride + (int64_t)item * ep.item_stride + rin;
             }
@@ -348,6 +453,14 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
                 }
                 const float dcc = c == 0 ? dcv : 0.0f;
+                if (signs) {
+                    // every lane takes part in the ballots; rows past the end contribute zero bits
+                    SignCtx sx2 = sx;
+                    sx2.col_moff = &col_moff[c * cwid];
+                    sx2.col_grp = &col_grp[c * cwid];
+                    sign_chunk(rr, &col_scale[c * cwid], dcc, sx2, c * cwid, cwid);
+                    continue;
+                }
                 if (MODE == 1 && g.score_groups > 0) {
                     if (row_ok) {
                         ScoreCtx sc2 = sctx;
@@ -383,8 +496,286 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                                           (((int64_t)img * ep.tiles_h + th) * ep.tiles_w + tw) * ep.channels + ch, m);
                         }
                     }
+                    if (signs) {
+                        // code words: one per (column = (tile row, row in tile), token column); tokens that lie entirely
+                        // inside this CTA's rows are stored, the others are OR-ed (the grid starts at zero)
+                        for (int i = (int)threadIdx.x - 64; i < n_lim * n_cols; i += 256) {
+                            const int n = i / n_cols, tcl = i - n * n_cols;
+                            const unsigned word = codes_s[n * g.code_cols + tcl];
+                            if (word == 0u) continue;
+                            codes_s[n * g.code_cols + tcl] = 0u;
+                            const int line = (nt * g.n_tile + n) * ep.col_mul + grp * ep.col_add;
+                            const int th = line / ep.p, pi = line - th * ep.p;
+                            const int sc = s_first + tcl;
+                            const int plane = sc / ep.tiles_w, tw = sc - plane * ep.tiles_w;
+                            const int img = plane / ep.channels, ch = plane - img * ep.channels;
+                            int32_t* dst = ep.code_grid +
+                                           ((((int64_t)img * ep.tiles_h + th) * ep.tiles_w + tw) * ep.channels + ch) * ep.p + pi;
+                            if (sc * ep.p >= R0 && sc * ep.p + ep.p <= Rend) *dst = (int32_t)word;
+                            else atomicOr(reinterpret_cast<unsigned*>(dst), word);
+                        }
+                    }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------ forward pass 2 -> code words
+// The forward pass 2 with the operand roles swapped: M = basis rows (the coefficient rows kh = 2i + a of one
+// parity group, 128 per CTA of the pair, resident in shared memory), N = data rows (kw of a token-aligned run of
+// `tokens_per_tile` token columns, streamed by TMA).  A thread then owns one coefficient row (tile row th, row in
+// tile pi) and sees the p columns of a token as p CONSECUTIVE accumulator columns: the sign bits of
+// clamp((Y - median) / (b*sqrt2 + eps)) (patchnorm.py:157-165 + lfq.py:175-187, one LFQ codebook per patch row)
+// are packed into the code word in registers and stored once -- no ballots, no shared image, no token grid.
+// The per-token max |Y| (feature_extraction_dct_autoencoder.py:409) is reduced over the p/2 lanes of a tile row
+// with shuffles and one atomicMax per tile row, token and parity.
+struct CodesArgs {
+    int rows_per_seg;       // stacked data rows (planes * kw) in each of the 2 segments (= parity groups)
+    int tiles_per_seg;      // pair tiles per segment
+    int num_kb, stages;
+    int n_valid;            // basis rows per group (kh / 2)
+    int n_data;             // data rows per pair tile = tokens_per_tile * p  (MMA N, multiple of 16, <= 256)
+    int tokens_per_tile;
+    uint32_t basis_bytes;   // one CTA's resident basis plane (hi or lo): num_kb * 128 * 64
+    uint32_t stage_bytes;   // one ring stage: this CTA's n_data/2 data rows, hi then lo
+    int p, channels, tiles_h, tiles_w;
+    float alpha;
+    const float* basis_scale;   // (2, n_valid)
+    const float* dc;            // per plane constant added to coefficient (0, 0)
+    const float* med;           // PatchNorm tables (channels, stat_h, stat_w, p*p)
+    const float* bstat;
+    int stat_h, stat_w;
+    float eps, clamp_lo, clamp_hi;
+    const int32_t* tame;
+    float* maxabs;              // (n_img, tiles_h, tiles_w, channels), zeroed
+    int32_t* code_grid;         // (n_img, tiles_h, tiles_w, channels, p)
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
+fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo,
+                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                  CodesArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[F_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[F_MAX_STAGES];
+    __shared__ __align__(8) uint64_t tmem_full[2];
+    __shared__ __align__(8) uint64_t tmem_empty[2];
+    __shared__ __align__(8) uint64_t basis_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* basis_hi = smem;
+    uint8_t* basis_lo = smem + g.basis_bytes;
+    uint8_t* ring = smem + 2 * g.basis_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int grp = pair & 1;
+    const int pair_in_grp = pair >> 1, pairs_per_grp = n_pairs >> 1;
+    const int half_data = g.n_data >> 1;
+    const uint32_t dtile = (uint32_t)half_data * 64;          // one data operand tile (hi or lo) of a stage
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&map_d_hi);
+        tma_prefetch_desc(&map_d_lo);
+        tma_prefetch_desc(&map_b_hi);
+        tma_prefetch_desc(&map_b_lo);
+        for (int s = 0; s < F_MAX_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 16);
+        }
+        mbar_init(&basis_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer
+        const uint32_t basis_bar_leader = mapa_u32(smem_u32(&basis_bar), 0);
+        if (rank == 0) mbar_expect_tx(&basis_bar, 4 * g.basis_bytes);
+        for (int kb = 0; kb < g.num_kb; ++kb) {          // this CTA's 128 basis rows (rows past n_valid are zero-filled)
+            tma_load_3d_2sm(&map_b_hi, basis_bar_leader, basis_hi + kb * F_ATILE, kb * FK, (int)rank * 128, grp);
+            tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * F_ATILE, kb * FK, (int)rank * 128, grp);
+        }
+        uint32_t it = 0;
+        for (int w = pair_in_grp; w < g.tiles_per_seg; w += pairs_per_grp) {
+            const int row0 = w * g.n_data + (int)rank * half_data;
+            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+                const int s = it % g.stages;
+                mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
+                uint8_t* st = ring + s * g.stage_bytes;
+                const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 4 * dtile);
+                tma_load_3d_2sm(&map_d_hi, full_leader, st, kb * FK, row0, grp);
+                tma_load_3d_2sm(&map_d_lo, full_leader, st + dtile, kb * FK, row0, grp);
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ---------------- MMA issuer: A = resident basis (M = 256 over the pair), B = data stage (N = n_data)
+        const uint32_t idesc = fold_idesc(g.n_data);
+        const uint32_t bh = smem_u32(basis_hi), bl = smem_u32(basis_lo);
+        mbar_wait_cluster(&basis_bar, 0);
+        tc_fence_after();
+        uint32_t it = 0, tcount = 0;
+        for (int w = pair_in_grp; w < g.tiles_per_seg; w += pairs_per_grp, ++tcount) {
+            const int acc = tcount & 1;
+            mbar_wait_cluster(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc * 256;
+            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
+                const int s = it % g.stages;
+                mbar_wait_cluster(&full_bar[s], (it / g.stages) & 1);
+                tc_fence_after();
+                const uint32_t base = smem_u32(ring + s * g.stage_bytes);
+#pragma unroll
+                for (int k = 0; k < FK / 16; ++k) {
+                    const uint32_t ko = k * 32;
+                    const uint64_t a_hi = smem_desc_sw64(bh + kb * F_ATILE + ko);
+                    const uint64_t a_lo = smem_desc_sw64(bl + kb * F_ATILE + ko);
+                    const uint64_t b_hi = smem_desc_sw64(base + ko);
+                    const uint64_t b_lo = smem_desc_sw64(base + dtile + ko);
+                    umma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, (kb | k) ? 1u : 0u);   // small terms first
+                    umma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1u);
+                    umma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1u);
+                }
+                umma_commit_2sm(&empty_bar[s], 3);
+            }
+            umma_commit_2sm(&tmem_full[acc], 3);
+        }
+    } else if (warp >= 2) {
+        // ---------------- epilogue: lane quarter = warp & 3 (coefficient rows), the two warps of a quarter take
+        // half of the tile's token columns each
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+        const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+        const int p = g.p, z = p * p, p2 = p >> 1;
+        const int i = (int)rank * 128 + quarter * 32 + lane;         // basis row of this thread
+        const bool i_ok = i < g.n_valid;
+        const int kh = 2 * i + grp;
+        const int th = kh / p, pi = kh - th * p;
+        const float scale = i_ok ? g.alpha * (g.basis_scale ? __ldg(g.basis_scale + grp * g.n_valid + i) : 1.0f) : 0.0f;
+        const bool tame = g.tame != nullptr && __ldg(g.tame) != 0 && g.eps > 1e-12f && g.clamp_lo < 0.0f && g.clamp_hi > 0.0f;
+        const LfqNormParams q{nullptr, nullptr, 0, 0, 0, 0, g.eps, g.clamp_lo, g.clamp_hi, 0, 0, 0.f};
+        // lanes of the same tile row th are contiguous: the first of each run publishes the row's maximum
+        const int th_prev = __shfl_up_sync(0xffffffffu, th, 1);
+        const bool th_leader = i_ok && (lane == 0 || th_prev != th);
+        bool take[3];                                             // does lane + 1 / 2 / 4 belong to the same tile row?
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            const int oth = __shfl_down_sync(0xffffffffu, th, 1 << o);
+            take[o] = (lane + (1 << o) < 32) && oth == th;
+        }
+        const int t_lo = half * ((g.tokens_per_tile + 1) >> 1);
+        const int t_hi = half ? g.tokens_per_tile : ((g.tokens_per_tile + 1) >> 1);
+        const int64_t stat_row = (int64_t)th * g.stat_w * z + pi * p;        // + (ch * stat_h * stat_w + tw) * z
+        const int64_t stat_ch = (int64_t)g.stat_h * g.stat_w * z;
+        const int64_t tok_row = (int64_t)th * g.tiles_w * g.channels;        // token index = (img*tiles_h*tiles_w + tw) * C + ch + tok_row
+        uint32_t tcount = 0;
+        for (int w = pair_in_grp; w < g.tiles_per_seg; w += pairs_per_grp, ++tcount) {
+            const int acc = tcount & 1;
+            // token column counters of this warp's first token (global column = plane * tiles_w + tw)
+            int tc = w * g.tokens_per_tile + t_lo;
+            int plane = tc / g.tiles_w, tw = tc - plane * g.tiles_w;
+            int img = plane / g.channels, ch = plane - img * g.channels;
+            int tc_n = tc, plane_n = plane, tw_n = tw, ch_n = ch;      // the same for the token whose medians are in flight
+            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
+            float2 mcur[8], mnext[8];
+            auto load_medians = [&](bool in_range, float2 (&dst)[8]) {
+                const bool ok = i_ok && in_range && (int64_t)tc_n * p < g.rows_per_seg;
+                const float2* src = reinterpret_cast<const float2*>(g.med + ch_n * stat_ch + (int64_t)tw_n * z + stat_row);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = (ok && j < p2) ? __ldg(src + j) : make_float2(0.f, 0.f);
+            };
+            auto advance_n = [&]() {
+                ++tc_n;
+                if (++tw_n == g.tiles_w) { tw_n = 0; ++plane_n; if (++ch_n == g.channels) ch_n = 0; }
+            };
+            load_medians(t_lo < t_hi, mcur);
+            for (int tk = t_lo; tk < t_hi; ++tk) {
+                uint32_t rr[16];
+                tmem_ld16_nowait(tmem_acc + tk * p, rr);
+                advance_n();
+                load_medians(tk + 1 < t_hi, mnext);
+                tmem_ld_wait();
+                if (tk == t_hi - 1) {                          // accumulator read out by this warp: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+                }
+                const bool tok_ok = (int64_t)tc * p < g.rows_per_seg;           // warp-uniform
+                const int64_t tok = ((int64_t)img * g.tiles_h * g.tiles_w + tw) * g.channels + ch + tok_row;
+                const float mvals[16] = {mcur[0].x, mcur[0].y, mcur[1].x, mcur[1].y, mcur[2].x, mcur[2].y, mcur[3].x, mcur[3].y,
+                                         mcur[4].x, mcur[4].y, mcur[5].x, mcur[5].y, mcur[6].x, mcur[6].y, mcur[7].x, mcur[7].y};
+                float mx = 0.0f;
+                if (tok_ok && i_ok) {
+                    // fast path: bit = sign of (median - Y) (Y > median <=> the difference is negative), valid when the
+                    // divisor is tame and no |difference| is tiny; one funnel shift per element builds the word MSB first
+                    const float dcv = (kh == 0 && tw == 0 && g.dc != nullptr) ? __ldg(g.dc + plane) : 0.0f;
+                    unsigned word = 0;
+                    float dmin = 1.0f;
+                    float vals[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < p) {
+                            float v = __uint_as_float(rr[j]) * scale;
+                            if (j == 0) v += dcv;
+                            vals[j] = v;
+                            const float nd = __fsub_rn(mvals[j], v);
+                            word = __funnelshift_l(__float_as_uint(nd), word, 1);
+                            dmin = fminf(dmin, fabsf(nd));
+                            mx = fmaxf(mx, fabsf(v));
+                        }
+                    }
+                    if (!tame || !(dmin > 1e-20f)) {          // rare: exact sign of the clamped quotient
+                        const float* bsrc = g.bstat + ch * stat_ch + (int64_t)tw * z + stat_row;
+                        word = 0;
+                        for (int j = 0; j < p; ++j) {
+                            float v = __uint_as_float(rr[0]);
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) if (u == j) v = vals[u];
+                            float mvj = mvals[0];
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) if (u == j) mvj = mvals[u];
+                            word = (word << 1) | norm_sign_bit(v, mvj, __ldg(bsrc + j), q);
+                        }
+                    }
+                    g.code_grid[tok * p + pi] = (int32_t)word;
+                }
+                // max over the lanes of one tile row (runs of p/2 <= 8 lanes)
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                    const float other = __shfl_down_sync(0xffffffffu, mx, 1 << o);
+                    if (take[o]) mx = fmaxf(mx, other);
+                }
+                if (tok_ok && th_leader && mx > 0.0f) atomicMax(reinterpret_cast<unsigned*>(g.maxabs) + tok, __float_as_uint(mx));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mcur[j] = mnext[j];
+                ++tc;
+                if (++tw == g.tiles_w) { tw = 0; ++plane; if (++ch == g.channels) { ch = 0; ++img; } }
+            }
+            if (t_hi <= t_lo) {                                  // nothing to read: release immediately
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
             }
         }
     }
@@ -785,11 +1176,12 @@ struct FoldOperand {
 };
 
 // slice geometry for a basis of n_valid rows and K columns: (n_tile, n_ntiles, stages), or false if nothing fits
-static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0, int extra_static = 0) {
+static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0, int extra_static = 0, int code_cols = 0) {
     g.num_kb = (int)ceil_div(K, FK);
     g.n_valid = n_valid;
     g.score_groups = score_groups;
-    const int64_t score_bytes = (int64_t)score_groups * 128 * 4;
+    g.code_cols = code_cols;
+    const int64_t score_bytes = (int64_t)score_groups * 128 * 4 + (int64_t)code_cols * 256 * 4;
     for (int nn = (int)ceil_div(n_valid, 256); nn <= 16; ++nn) {
         const int n_tile = (int)ceil_div(ceil_div(n_valid, nn), 16) * 16;
         const int64_t basis = (int64_t)g.num_kb * (n_tile / 2) * 64;
@@ -812,7 +1204,8 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
     if (rows_per_seg == 0 || n_seg == 0) return DCTA_OK;
     FoldGemm g{};
     const int score_groups = (ep.mode == 2 && ep.maxabs != nullptr) ? ep.tiles_h : 0;
-    if (!fold_geometry(n_valid, K, g, score_groups)) { set_error("fold_gemm: basis %d x %d does not fit in shared memory", n_valid, K); return DCTA_ERR_UNSUPPORTED; }
+    const int code_cols = (ep.mode == 2 && ep.code_grid != nullptr) ? 128 / ep.p + 2 : 0;
+    if (!fold_geometry(n_valid, K, g, score_groups, 0, code_cols)) { set_error("fold_gemm: basis %d x %d does not fit in shared memory", n_valid, K); return DCTA_ERR_UNSUPPORTED; }
     if (rows_per_seg >= (1ll << 31) - 256 || (n_seg & 1)) { set_error("fold_gemm: bad segment geometry"); return DCTA_ERR_INVALID_ARG; }
     g.n_seg = n_seg;
     g.rows_per_seg = (int)rows_per_seg;
@@ -823,7 +1216,7 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
     if ((rc = make_map3(&ma_lo, A.lo, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
     if ((rc = make_map3(&mb_hi, Bas.hi, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
     if ((rc = make_map3(&mb_lo, Bas.lo, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
-    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4;
+    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4 + g.code_cols * 256 * 4;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -919,6 +1312,46 @@ static int launch_fold_chain(const FoldOperand& A1, const FoldOperand& A2, const
     cudaMemsetAsync(done, 0, sizeof(int32_t) * sc.ns, as_stream(stream));
     fold_chain_kernel<<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(m1h, m1l, m2h, m2l, mbh, mbl, g, sc, ep1, ep2);
     return check_launch("fold_chain");
+}
+
+// forward pass 2 straight to code words (fold_codes_kernel); DCTA_ERR_UNSUPPORTED when the geometry does not fit
+static int launch_fold_codes(const FoldOperand& Data, int64_t rows_per_seg, const FoldOperand& Bas, int n_valid, int K,
+                             CodesArgs g, void* stream) {
+    if (rows_per_seg == 0) return DCTA_OK;
+    const int p = g.p;
+    if (n_valid > 256 || p < 8 || p > 16 || (p & 1) || rows_per_seg % p) return DCTA_ERR_UNSUPPORTED;
+    // token-aligned data tiles: the largest multiple of p that is a multiple of 16 and at most 256 rows
+    int tokens = 256 / p;
+    while (tokens > 0 && (tokens * p) % 16) --tokens;
+    if (tokens < 2) return DCTA_ERR_UNSUPPORTED;
+    g.tokens_per_tile = tokens;
+    g.n_data = tokens * p;
+    g.rows_per_seg = (int)rows_per_seg;
+    g.tiles_per_seg = (int)ceil_div(rows_per_seg, g.n_data);
+    g.n_valid = n_valid;
+    g.num_kb = (int)ceil_div(K, FK);
+    g.basis_bytes = (uint32_t)g.num_kb * F_ATILE;
+    g.stage_bytes = (uint32_t)ceil_div((int64_t)g.n_data * 64, 1024) * 1024;      // hi + lo halves of n_data/2 rows each
+    const int64_t stages = (F_SMEM_LIMIT - 1024 - 2 * (int64_t)g.basis_bytes) / g.stage_bytes;
+    if (stages < 3 || 4ll * g.basis_bytes >= (1 << 20) || rows_per_seg >= (1ll << 31) - 256) return DCTA_ERR_UNSUPPORTED;
+    g.stages = (int)(stages < F_MAX_STAGES ? stages : F_MAX_STAGES);
+    CUtensorMap md_hi, md_lo, mb_hi, mb_lo;
+    int rc;
+    if ((rc = make_map3(&md_hi, Data.hi, K, rows_per_seg, 2, Data.ld, Data.seg_stride, g.n_data / 2))) return rc;
+    if ((rc = make_map3(&md_lo, Data.lo, K, rows_per_seg, 2, Data.ld, Data.seg_stride, g.n_data / 2))) return rc;
+    if ((rc = make_map3(&mb_hi, Bas.hi, K, n_valid, 2, Bas.ld, Bas.seg_stride, 128))) return rc;
+    if ((rc = make_map3(&mb_lo, Bas.lo, K, n_valid, 2, Bas.ld, Bas.seg_stride, 128))) return rc;
+    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * (int)g.stage_bytes;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t ppg = (sms / 2) / 2;                     // pairs per parity group
+    if (ppg < 1) ppg = 1;
+    if (ppg > g.tiles_per_seg) ppg = g.tiles_per_seg;
+    cudaError_t e = cudaFuncSetAttribute(fold_codes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { set_error("fold_codes: %s", cudaGetErrorString(e)); return DCTA_ERR_LAUNCH; }
+    fold_codes_kernel<<<(unsigned)(4 * ppg), F_THREADS, smem_bytes, as_stream(stream)>>>(md_hi, md_lo, mb_hi, mb_lo, g);
+    return check_launch("fold_codes");
 }
 
 // ------------------------------------------------------------------------------ fold / unfold kernels
@@ -1387,6 +1820,59 @@ extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const fl
     }
     int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)h2, 2, B1, kw / 2, w2, e1, stream);
     if (rc) return rc;
+    return launch_fold_gemm(A2, n_planes * (int64_t)kw, 2, B2, kh / 2, h2, e2, stream);
+}
+
+// forward straight to LFQ code words (one codebook per patch row: c == d == tile_p): the pass-2 epilogue forms
+// sign(clamp((Y - median) / (b*sqrt2 + eps))) of every coefficient and never writes the token grid.
+//   code_grid (n_planes/channels, kh/p, kw/p, channels, p) int32, maxabs as in dcta_dct2_fwd_fold.
+extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
+                                        const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
+                                        const float* rs_h, void* work_hi, void* work_lo, float* maxabs,
+                                        int32_t* code_grid, const float* median, const float* b, int H, int W,
+                                        float eps, float lo, float hi, int32_t* tame_scratch, int64_t n_planes, int h,
+                                        int w, int kh, int kw, int tile_p, int channels, void* stream) {
+    DCTA_REQUIRE(xq_hi && xq_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && maxabs &&
+                 code_grid && median && b && tame_scratch, "dct2_fwd_fold_codes: null pointer");
+    DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_fwd_fold_codes: needs h, w multiples of 16 and even kh <= h, kw <= w");
+    DCTA_REQUIRE(tile_p >= 8 && tile_p <= 32 && channels > 0 && kh % tile_p == 0 && kw % tile_p == 0 &&
+                 n_planes % channels == 0 && kh / tile_p <= H && kw / tile_p <= W && kh / tile_p <= 64,
+                 "dct2_fwd_fold_codes: needs 8 <= p <= 32, kh/kw multiples of p and a token grid inside the PatchNorm tables");
+    if (n_planes == 0) return DCTA_OK;
+    const int h2 = h / 2, w2 = w / 2;
+    cudaStream_t st = as_stream(stream);
+    int rc = launch_b_tame(b, (int64_t)channels * H * W * tile_p * tile_p, tame_scratch, st);
+    if (rc) return rc;
+    FoldOperand A1{(const __half*)xq_hi, (const __half*)xq_lo, w2, 2 * n_planes * (int64_t)h2 * w2};
+    FoldOperand B1{(const __half*)bw_hi, (const __half*)bw_lo, w2, (int64_t)(kw / 2) * w2};
+    FoldEpi e1{};
+    e1.mode = 0; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
+    e1.rows_per_item = h2; e1.seg_stride = 0; e1.item_stride = (int64_t)kw * h2;
+    e1.col_mul = 2; e1.col_add = 1; e1.col_stride = h2;
+    e1.alpha = kFScaleP / kFScaleX; e1.basis_scale = rs_w;
+    rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)h2, 2, B1, kw / 2, w2, e1, stream);
+    if (rc) return rc;
+    FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, h2, n_planes * (int64_t)kw * h2};
+    FoldOperand B2{(const __half*)bh_hi, (const __half*)bh_lo, h2, (int64_t)(kh / 2) * h2};
+    const int64_t n_tok = (n_planes / channels) * (kh / tile_p) * (kw / tile_p) * channels;
+    cudaMemsetAsync(maxabs, 0, sizeof(float) * n_tok, st);
+    {
+        // preferred: the transposed pass (a thread owns one coefficient row and packs the code words in registers)
+        CodesArgs cg{};
+        cg.p = tile_p; cg.channels = channels; cg.tiles_h = kh / tile_p; cg.tiles_w = kw / tile_p;
+        cg.alpha = 1.0f / kFScaleP; cg.basis_scale = rs_h; cg.dc = dc; cg.med = median; cg.bstat = b;
+        cg.stat_h = H; cg.stat_w = W; cg.eps = eps; cg.clamp_lo = lo; cg.clamp_hi = hi; cg.tame = tame_scratch;
+        cg.maxabs = maxabs; cg.code_grid = code_grid;
+        rc = launch_fold_codes(A2, n_planes * (int64_t)kw, B2, kh / 2, h2, cg, stream);
+        if (rc != DCTA_ERR_UNSUPPORTED) return rc;
+    }
+    FoldEpi e2{};
+    e2.rows_per_item = kw; e2.col_mul = 2; e2.col_add = 1;
+    e2.alpha = 1.0f / kFScaleP; e2.basis_scale = rs_h; e2.dc = dc;
+    e2.mode = 2; e2.p = tile_p; e2.channels = channels; e2.tiles_h = kh / tile_p; e2.tiles_w = kw / tile_p;
+    e2.maxabs = maxabs; e2.code_grid = code_grid; e2.med = median; e2.bstat = b; e2.stat_h = H; e2.stat_w = W;
+    e2.eps = eps; e2.clamp_lo = lo; e2.clamp_hi = hi; e2.tame = tame_scratch;
+    cudaMemsetAsync(code_grid, 0, sizeof(int32_t) * n_tok * tile_p, st);
     return launch_fold_gemm(A2, n_planes * (int64_t)kw, 2, B2, kh / 2, h2, e2, stream);
 }
 

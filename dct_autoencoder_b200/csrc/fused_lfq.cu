@@ -102,16 +102,6 @@ __global__ void __launch_bounds__(256) pack_codes_kernel(
     }
 }
 
-// sign of clamp((x - m) / (b*sqrt2 + eps)): decided by the numerator whenever that is safe (see above)
-__device__ __forceinline__ unsigned norm_sign_bit(float xv, float mv, float bv, const LfqNormParams& q) {
-    const float sd = __fadd_rn(__fmul_rn(bv, kSqrt2f), q.eps);
-    const float diff = __fsub_rn(xv, mv);
-    if (sd > 0.0f && sd < 1e30f && fabsf(diff) > 1e-30f && q.lo < 0.0f && q.hi > 0.0f) return diff > 0.0f;
-    float y = __fdiv_rn(diff, sd);
-    y = y < q.lo ? q.lo : (y > q.hi ? q.hi : y);
-    return y > 0.0f;
-}
-
 // Vectorised variant (z % 4 == 0, z <= 256, d <= 32).  A warp takes 32 consecutive slots: the per-slot
 // metadata chain (segment search -> order -> token address; three dependent global loads) runs ONCE,
 // lane-parallel, and the bookkeeping outputs are written coalesced; then the 32 tokens are streamed two at
@@ -271,6 +261,73 @@ __global__ void __launch_bounds__(256, 4) pack_codes_vec_kernel(
     }
 }
 
+int launch_b_tame(const float* b, int64_t n, int32_t* flag, cudaStream_t st) {
+    cudaMemsetAsync(flag, 1, sizeof(int32_t), st);
+    b_tame_kernel<<<grid_for(n, 1024, 1), 256, 0, st>>>(b, n, flag);
+    return check_launch("b_tame");
+}
+
+// Code words of a padding slot: zeros normalised with the statistics at (0, 0, 0) like the reference does
+// (patchnorm.py:157-161 runs on padding rows too).  One warp; pad_codes (c) int64.
+__global__ void pad_codes_kernel(LfqNormParams q, int64_t* __restrict__ pad_codes) {
+    for (int cb = threadIdx.x; cb < q.c; cb += blockDim.x) {
+        unsigned long long code = 0;
+        for (int i = 0; i < q.d; ++i) {
+            const int e = cb * q.d + i;
+            code = (code << 1) | norm_sign_bit(0.0f, q.median[e], q.b[e], q);
+        }
+        pad_codes[cb] = (int64_t)code;
+    }
+}
+
+// Gather of the code words computed by the forward DCT epilogue (dct_fold.cu): code_grid (n_img, th, tw, C, c)
+// int32 in token-grid order -> codes (rows, s, c) int64 in packed, sorted order, + the bookkeeping outputs.
+// One thread per slot: the metadata chain runs lane-parallel, every lane copies its own c words.
+__global__ void __launch_bounds__(256) pack_codes_grid_kernel(
+    const int32_t* __restrict__ code_grid, const int32_t* __restrict__ order, const dcta_segment* __restrict__ segs,
+    const int32_t* __restrict__ row_seg_start, int n_rows, int s, int tw, int channels, int n_tok_img,
+    float inv_channels, float inv_tw, int c, const int64_t* __restrict__ pad_codes, int64_t* __restrict__ codes,
+    int64_t* __restrict__ positions, int64_t* __restrict__ channels_out, int64_t* __restrict__ image_ids,
+    uint8_t* __restrict__ key_pad_mask) {
+    const int64_t total = (int64_t)n_rows * s;
+    for (int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(slot / s);
+        const int off = (int)(slot - (int64_t)row * s);
+        int lo = row_seg_start[row], hi = row_seg_start[row + 1];
+        int seg = -1;
+        if (hi - lo == 1) {
+            seg = (off >= segs[lo].offset && off < segs[lo].offset + segs[lo].k) ? lo : -1;
+        } else {
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const int so = segs[mid].offset;
+                if (off < so) hi = mid;
+                else if (off >= so + segs[mid].k) lo = mid + 1;
+                else { seg = mid; break; }
+            }
+        }
+        int ph = 0, pw = 0, pc = 0, image_id = 0;
+        int64_t* dst = codes + slot * c;
+        if (seg >= 0) {
+            const dcta_segment sg = segs[seg];
+            const int tok = order[sg.img * n_tok_img + (off - sg.offset)];
+            const int tile = (int)(((float)tok + 0.5f) * inv_channels);   // exact for tok < 2^22
+            pc = tok - tile * channels;
+            ph = (int)(((float)tile + 0.5f) * inv_tw);
+            pw = tile - ph * tw;
+            image_id = sg.image_id;
+            const int32_t* src = code_grid + (sg.img * n_tok_img + tok) * (int64_t)c;
+            for (int i = 0; i < c; ++i) dst[i] = (int64_t)__ldg(src + i);
+        } else {
+            for (int i = 0; i < c; ++i) dst[i] = __ldg(pad_codes + i);
+        }
+        reinterpret_cast<longlong2*>(positions)[slot] = make_longlong2(ph, pw);
+        channels_out[slot] = pc;
+        if (image_ids) image_ids[slot] = image_id;
+        if (key_pad_mask) key_pad_mask[slot] = seg < 0;
+    }
+}
+
 __device__ __forceinline__ void split16f(float v, float scale, __half& h, __half& l) {
     const float s = v * scale;
     h = __float2half_rn(s);
@@ -372,11 +429,8 @@ extern "C" int dcta_pack_codes_lfq(const float* tiles, const int32_t* order, con
     const bool aligned = ((reinterpret_cast<uintptr_t>(tiles) | reinterpret_cast<uintptr_t>(median) |
                            reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(positions)) & 15) == 0;
     if (z % 4 == 0 && d <= 32 && aligned && th * tw * channels < (1 << 22)) {
-        if (tame_scratch) {     // is every b a tame divisor?  (2.4 MB table, L2 resident: a few microseconds)
-            cudaMemsetAsync(tame_scratch, 1, sizeof(int32_t), as_stream(stream));
-            const int64_t nb = (int64_t)channels * H * W * z;
-            b_tame_kernel<<<grid_for(nb, 1024, 1), 256, 0, as_stream(stream)>>>(b, nb, tame_scratch);
-        }
+        if (tame_scratch)       // is every b a tame divisor?  (2.4 MB table, L2 resident: a few microseconds)
+            launch_b_tame(b, (int64_t)channels * H * W * z, tame_scratch, as_stream(stream));
         pack_codes_vec_kernel<<<grid_for((int64_t)n_rows * s, 256), 256, 0, as_stream(stream)>>>(
             tiles, order, segs, row_seg_start, n_rows, s, tw, channels, th * tw * channels, 1.0f / (float)channels,
             1.0f / (float)tw, q, tame_scratch, codes, positions, channels_out, image_ids, key_pad_mask);
@@ -407,4 +461,24 @@ extern "C" int dcta_decode_codes_split(const int64_t* codes, const int32_t* slot
         codes, slot_map, img_sel, th, tw, p, rows, cols, (int)ld, q, (__half*)y_hi, (__half*)y_lo, dc,
         1.0f / sqrtf((float)out_h * (float)out_w), 16.0f);
     return check_launch("decode_codes_split");
+}
+
+extern "C" int dcta_pack_codes_grid(const int32_t* code_grid, const int32_t* order, const dcta_segment* segs,
+                                    const int32_t* row_seg_start, int n_rows, int s, int th, int tw, int channels,
+                                    const float* median, const float* b, int H, int W, float eps, float lo, float hi,
+                                    int c, int d, int64_t* pad_scratch, int64_t* codes, int64_t* positions,
+                                    int64_t* channels_out, int64_t* image_ids, uint8_t* key_pad_mask, void* stream) {
+    DCTA_REQUIRE(code_grid && order && segs && row_seg_start && pad_scratch && codes && positions && channels_out,
+                 "pack_codes_grid: null pointer");
+    DCTA_REQUIRE(n_rows >= 0 && s > 0 && th > 0 && tw > 0 && channels > 0 && th * tw * channels < (1 << 22),
+                 "pack_codes_grid: bad sizes");
+    int rc = check_params("pack_codes_grid", median, b, channels, H, W, c * d, c, d);
+    if (rc) return rc;
+    if (n_rows == 0) return DCTA_OK;
+    LfqNormParams q{median, b, channels, H, W, c * d, eps, lo, hi, c, d, 1.0f};
+    pad_codes_kernel<<<1, 32, 0, as_stream(stream)>>>(q, pad_scratch);
+    pack_codes_grid_kernel<<<grid_for((int64_t)n_rows * s, 256), 256, 0, as_stream(stream)>>>(
+        code_grid, order, segs, row_seg_start, n_rows, s, tw, channels, th * tw * channels, 1.0f / (float)channels,
+        1.0f / (float)tw, c, pad_scratch, codes, positions, channels_out, image_ids, key_pad_mask);
+    return check_launch("pack_codes_grid");
 }

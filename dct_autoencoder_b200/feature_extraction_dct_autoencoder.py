@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .dct_patches import DCTPatches
-from .util import (_round8, dct2, dct2_fwd_fold, dct2_fwd_tc, dct2_inv_fold, dct2_inv_tc, dct2_truncated,
+from .util import (_round8, dct2, dct2_fwd_fold, dct2_fwd_fold_codes, dct2_fwd_tc, dct2_inv_fold, dct2_inv_tc, dct2_truncated,
                    exp_trunc_dist, fold_ok, idct2, idct2_truncated, ipt_to_rgb, rgb_to_ipt, rgb_to_ipt_fold,
                    rgb_to_ipt_split, tc_forward_ok, to_device_f32, unfold_ipt_to_rgb)
 
@@ -320,9 +320,24 @@ class DCTAutoencoderFeatureExtractor:
         x = to_device_f32(images, self._dev(images))
         b, c, h, w = x.shape
         ph, pw, th, tw = self._geometry(h, w)
-        tiles, maxabs = self._token_grid(x, want_maxabs=True)
-        order = self._sorted_order(tiles, maxabs)
+        p = self.patch_size
         n_tok = th * tw * c
+        # one codebook per patch row on the folded tensor-core path: the DCT epilogue emits the code words itself
+        in_epilogue = (self.dct_impl == "tc" and c == 3 and not self._hooks_overridden("_transform_image_in")
+                       and lfq.num_codebooks == p and lfq.codebook_dim == p and 8 <= p <= 32 and th <= 64
+                       and th <= norm.max_patch_h and tw <= norm.max_patch_w and fold_ok(h, w, th * p, tw * p))
+        if in_epilogue:
+            hi, lo, dc = rgb_to_ipt_fold(x)
+            maxabs, code_grid = dct2_fwd_fold_codes(hi, lo, dc, th * p, tw * p, p, c, norm)
+            del hi, lo
+            order = torch.empty((b, n_tok), dtype=torch.int32, device=x.device)
+            imp = _lib.host_floats(self.channel_importances.tolist()[:c] + [1.0] * max(0, c - len(self.channel_importances)))
+            with torch.cuda.device(x.device):
+                _lib.call("dcta_sort_tokens_maxabs", _lib.ptr(maxabs), None, _lib.ptr(order), b, th, tw, c,
+                          float(self.patch_sample_magnitude_weight), imp, _lib.stream_ptr(x.device))
+        else:
+            tiles, maxabs = self._token_grid(x, want_maxabs=True)
+            order = self._sorted_order(tiles, maxabs)
         if ks is None:
             ks = [self._choose_k(n_tok) for _ in range(b)]
         state = self._next_fit(ks)
@@ -334,14 +349,22 @@ class DCTAutoencoderFeatureExtractor:
         chan = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
         ids = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
         pad = torch.empty((n_rows, s), dtype=torch.bool, device=x.device)
-        tame = torch.empty(1, dtype=torch.int32, device=x.device)
         with torch.cuda.device(x.device):
-            _lib.call("dcta_pack_codes_lfq", _lib.ptr(tiles), _lib.ptr(order), tab.data_ptr() + offs[0],
-                      tab.data_ptr() + offs[1], n_rows, s, th, tw, c, self.patch_size ** 2,
-                      _lib.ptr(norm.median.data), _lib.ptr(norm.b.data), norm.max_patch_h, norm.max_patch_w,
-                      float(norm.eps), float(norm.min_val), float(norm.max_val), lfq.num_codebooks,
-                      lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(tame), _lib.ptr(codes), _lib.ptr(pos),
-                      _lib.ptr(chan), _lib.ptr(ids), _lib.ptr(pad), _lib.stream_ptr(x.device))
+            if in_epilogue:
+                pad_codes = torch.empty(lfq.num_codebooks, dtype=torch.int64, device=x.device)
+                _lib.call("dcta_pack_codes_grid", _lib.ptr(code_grid), _lib.ptr(order), tab.data_ptr() + offs[0],
+                          tab.data_ptr() + offs[1], n_rows, s, th, tw, c, _lib.ptr(norm.median.data), _lib.ptr(norm.b.data),
+                          norm.max_patch_h, norm.max_patch_w, float(norm.eps), float(norm.min_val), float(norm.max_val),
+                          lfq.num_codebooks, lfq.codebook_dim, _lib.ptr(pad_codes), _lib.ptr(codes), _lib.ptr(pos),
+                          _lib.ptr(chan), _lib.ptr(ids), _lib.ptr(pad), _lib.stream_ptr(x.device))
+            else:
+                tame = torch.empty(1, dtype=torch.int32, device=x.device)
+                _lib.call("dcta_pack_codes_lfq", _lib.ptr(tiles), _lib.ptr(order), tab.data_ptr() + offs[0],
+                          tab.data_ptr() + offs[1], n_rows, s, th, tw, c, self.patch_size ** 2,
+                          _lib.ptr(norm.median.data), _lib.ptr(norm.b.data), norm.max_patch_h, norm.max_patch_w,
+                          float(norm.eps), float(norm.min_val), float(norm.max_val), lfq.num_codebooks,
+                          lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(tame), _lib.ptr(codes), _lib.ptr(pos),
+                          _lib.ptr(chan), _lib.ptr(ids), _lib.ptr(pad), _lib.stream_ptr(x.device))
         batch = DCTPatches(patches=None, key_pad_mask=pad, batched_image_ids=ids, patch_channels=chan,
                            patch_positions=pos, patch_sizes=[(ph, pw)] * b, original_sizes=[(h, w)] * b,
                            _data={}, _row_num_images=[len(r) for r in rows])

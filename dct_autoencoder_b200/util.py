@@ -474,6 +474,31 @@ def dct2_fwd_fold(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: Optional[torch.T
     return (y, maxabs) if with_maxabs else y
 
 
+def dct2_fwd_fold_codes(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: torch.Tensor, kh: int, kw: int, tile_p: int,
+                        channels: int, norm):
+    """Forward DCT from folded quadrants straight to LFQ code words (one codebook per patch row) of the
+    PatchNorm-normalised coefficients: returns (maxabs (n_img, kh/p, kw/p, channels),
+    code_grid (n_img, kh/p, kw/p, channels, p) int32) -- the token grid itself is never written."""
+    n_planes, h2, w2 = xq_hi.shape[-3:]
+    h, w = 2 * h2, 2 * w2
+    dev = xq_hi.device
+    bw_hi, bw_lo, rs_w = fold_basis(w, kw, dev, False)
+    bh_hi, bh_lo, rs_h = fold_basis(h, kh, dev, False)
+    work_hi = torch.empty((2, n_planes, kw, h2), dtype=torch.float16, device=dev)
+    work_lo = torch.empty_like(work_hi)
+    shape = (n_planes // channels, kh // tile_p, kw // tile_p, channels)
+    maxabs = torch.empty(shape, dtype=torch.float32, device=dev)
+    code_grid = torch.empty(shape + (tile_p,), dtype=torch.int32, device=dev)
+    tame = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_dct2_fwd_fold_codes", _lib.ptr(xq_hi), _lib.ptr(xq_lo), _lib.ptr(dc), _lib.ptr(bw_hi),
+                  _lib.ptr(bw_lo), _lib.ptr(rs_w), _lib.ptr(bh_hi), _lib.ptr(bh_lo), _lib.ptr(rs_h), _lib.ptr(work_hi),
+                  _lib.ptr(work_lo), _lib.ptr(maxabs), _lib.ptr(code_grid), _lib.ptr(norm.median.data),
+                  _lib.ptr(norm.b.data), norm.max_patch_h, norm.max_patch_w, float(norm.eps), float(norm.min_val),
+                  float(norm.max_val), _lib.ptr(tame), n_planes, h, w, kh, kw, tile_p, channels, _lib.stream_ptr(dev))
+    return maxabs, code_grid
+
+
 def dct2_inv_fold(yq_hi: torch.Tensor, yq_lo: torch.Tensor, kh: int, kw: int, h: int, w: int) -> torch.Tensor:
     """Folded coefficient quadrants (2, 2, n_planes, kh/2, round8(kw/2)) -> quadrant transforms
     z (4, n_planes, h/2, w/2) fp32 (to be un-folded by ``unfold_ipt_to_rgb`` / ``unfold_planes``)."""

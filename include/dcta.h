@@ -149,6 +149,18 @@ int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, co
                        const float* rs_h, void* work_hi, void* work_lo, float* y, float* maxabs,
                        int32_t* chain_scratch, int64_t n_planes, int h, int w, int kh, int kw, int tile_p,
                        int channels, void* stream);
+/* The forward transform straight to LFQ code words, for a projection-free LFQ with one codebook per patch row
+ * (c == d == tile_p) on frozen PatchNorm tables: the pass-2 epilogue forms the sign bit of
+ * clamp((Y - median) / (b*sqrt2 + eps)) (PN:157-165, LFQ:175-187) of every coefficient and never writes the token grid.
+ *   code_grid (n_planes/channels, kh/p, kw/p, channels, p) int32: code word of patch row r of every token, in
+ *   token-grid order (dcta_pack_codes_grid gathers them into sorted, packed order);  maxabs as above;
+ *   median, b (channels, H, W, p*p);  tame_scratch: one device int32. */
+int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
+                             const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
+                             const float* rs_h, void* work_hi, void* work_lo, float* maxabs, int32_t* code_grid,
+                             const float* median, const float* b, int H, int W, float eps, float lo, float hi,
+                             int32_t* tame_scratch, int64_t n_planes, int h, int w, int kh, int kw, int tile_p,
+                             int channels, void* stream);
 /* FE:635-653 un-patchify into folded coefficient quadrants yq_hi/lo (2, 2, n_img*channels, rows/2, ldq)
  * [b][a][plane][i][j] = Y[2i+a, 2j+b] * 2^4, ldq = round8(cols/2); DC moved to dc as in dcta_unpatchify_split. */
 int dcta_unpatchify_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
@@ -296,6 +308,14 @@ int dcta_pack_codes_lfq(const float* tiles, const int32_t* order, const dcta_seg
                         int z, const float* median, const float* b, int H, int W, float eps, float lo,
                         float hi, int c, int d, float scale, int32_t* tame_scratch, int64_t* codes, int64_t* positions,
                         int64_t* channels_out, int64_t* image_ids, uint8_t* key_pad_mask, void* stream);
+/* FE:437-452 / 516-605 gather of those code words: codes (n_rows, s, c) i64 + the bookkeeping outputs of
+ * dcta_pack_codes_lfq.  Padding slots get the code words of an all-zero token at position (0,0,0), as in the
+ * reference.  pad_scratch: c device int64. */
+int dcta_pack_codes_grid(const int32_t* code_grid, const int32_t* order, const dcta_segment* segs,
+                         const int32_t* row_seg_start, int n_rows, int s, int th, int tw, int channels,
+                         const float* median, const float* b, int H, int W, float eps, float lo, float hi, int c,
+                         int d, int64_t* pad_scratch, int64_t* codes, int64_t* positions, int64_t* channels_out,
+                         int64_t* image_ids, uint8_t* key_pad_mask, void* stream);
 /* Decode from codes straight into the inverse GEMM's operand planes: lfq.py:105-134 unpack +
  * PN:167-177 de-normalise + FE:635-653 un-patchify + fp16 hi/lo split (scale 2^4, DC to dc[]).
  * Bit-identical to dcta_lfq_indices_to_codes -> dcta_patchnorm_apply(inverse) -> dcta_unpatchify_split. */
