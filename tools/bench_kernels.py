@@ -40,6 +40,8 @@ def main():
     t("fwd fold -> token grid + maxabs", lambda: U.dct2_fwd_fold(hi, lo, dc, 448, 448, tile_p=14, channels=3, with_maxabs=True))
     t("fwd fold -> token grid", lambda: U.dct2_fwd_fold(hi, lo, dc, 448, 448, tile_p=14, channels=3))
     y = t("fwd fold -> planes", lambda: U.dct2_fwd_fold(hi, lo, dc, 448, 448, out_shape=(B, 3)))
+    pn = D.PatchNorm(32, 32, 14, 3).to(dev)
+    t("fwd fold -> code grid + maxabs", lambda: U.dct2_fwd_fold_codes(hi, lo, dc, 448, 448, 14, 3, pn))
     del hi, lo
     t("idct fold (fold_coef + 2 passes + unfold planes)", lambda: U.idct2_truncated_fold(y, 512, 512))
 
