@@ -651,8 +651,10 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
                     const uint64_t a_lo = smem_desc_sw64(bl + kb * F_ATILE + ko);
                     const uint64_t b_hi = smem_desc_sw64(base + ko);
                     const uint64_t b_lo = smem_desc_sw64(base + dtile + ko);
-                    umma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, (kb | k) ? 1u : 0u);   // small terms first
-                    umma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1u);
+                    // the same sequence of partial sums as fold_gemm_kernel (data_lo*basis_hi, data_hi*basis_lo,
+                    // data_hi*basis_hi) so that both kernels produce bit-identical coefficients
+                    umma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, (kb | k) ? 1u : 0u);
+                    umma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, 1u);
                     umma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1u);
                 }
                 umma_commit_2sm(&empty_bar[s], 3);

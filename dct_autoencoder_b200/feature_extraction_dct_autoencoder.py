@@ -13,6 +13,7 @@ Additions that the reference does not have (its API is per-image):
 ``postprocess_batch``.  They produce exactly what the per-image path followed by
 ``iter_batches(batch_size=None)`` / ``postprocess`` produces.
 """
+import os
 from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -323,7 +324,7 @@ class DCTAutoencoderFeatureExtractor:
         p = self.patch_size
         n_tok = th * tw * c
         # one codebook per patch row on the folded tensor-core path: the DCT epilogue emits the code words itself
-        in_epilogue = (self.dct_impl == "tc" and c == 3 and not self._hooks_overridden("_transform_image_in")
+        in_epilogue = (os.environ.get("DCTA_NO_EPILOGUE_CODES") is None and self.dct_impl == "tc" and c == 3 and not self._hooks_overridden("_transform_image_in")
                        and lfq.num_codebooks == p and lfq.codebook_dim == p and 8 <= p <= 32 and th <= 64
                        and th <= norm.max_patch_h and tw <= norm.max_patch_w and fold_ok(h, w, th * p, tw * p))
         if in_epilogue:

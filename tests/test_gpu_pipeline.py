@@ -123,3 +123,22 @@ def test_fused_roundtrip_is_bit_identical_to_staged(D, beta, max_seq_len, size, 
     # not fusable -> staged path is used transparently
     lfq2 = D.LFQ(dim=patch * patch, codebook_size=8192, num_codebooks=16).cuda().eval()
     assert not D.TransformPipeline(fe, pn, lfq2).fusable()
+
+
+def test_fused_codes_match_staged_when_values_tie_with_the_median(D):
+    """PatchNorm fitted on the very images that are encoded: a quarter of the coefficients EQUAL their median, so any
+    last-bit difference between the kernel that wrote the fitted coefficients (token grid) and the one that forms the
+    code words in its epilogue would flip sign bits.  Both must produce bit-identical coefficients."""
+    torch.manual_seed(0)
+    for shape in [(4, 3, 128, 112), (8, 3, 512, 512)]:
+        x = torch.rand(*shape).cuda()
+        fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+        pn = D.PatchNorm(32, 32, 14, 3).cuda()
+        lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).cuda().eval()
+        pipe = D.TransformPipeline(fe, pn, lfq)
+        pipe.fit_norm(x)
+        assert pipe.fusable()
+        rec_s, codes_s = pipe.roundtrip(x, fused=False)
+        rec_f, codes_f = pipe.roundtrip(x)
+        assert torch.equal(codes_f, codes_s)
+        assert torch.equal(rec_f, rec_s)
