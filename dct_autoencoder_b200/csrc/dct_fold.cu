@@ -44,7 +44,6 @@ struct FoldGemm {
     int stages;
     uint32_t basis_bytes; // one CTA's resident basis plane (hi or lo): num_kb * (n_tile/2) * 64
     int score_groups;     // > 0: tile rows of the token grid; a [score_groups][128] max|value| image follows the ring
-    int code_cols;        // > 0: token columns a CTA's 128 rows can touch; a [n_tile][code_cols] code-word image follows
     int chunk_w;          // accumulator columns an epilogue warp takes at a time (multiple of 4, <= 32; an even
                           // number of chunks covers n_tile so that the two warps of a lane quarter get equal shares)
 };
@@ -63,13 +62,6 @@ struct FoldEpi {
     const float* basis_scale;    // optional (2, n_valid) per-basis-row factors
     const float* dc;             // optional per-item constant added to (group 0, basis row 0, row-in-item 0)
     int p, channels, tiles_h, tiles_w;   // mode 2
-    int32_t* code_grid;          // mode 2, optional: (n_img, tiles_h, tiles_w, channels, p) LFQ code words of the
-                                 // PatchNorm-normalised coefficients INSTEAD of the token grid (needs maxabs too)
-    const float* med;            //   PatchNorm median / b tables (channels, stat_h, stat_w, p*p), clamp and eps
-    const float* bstat;
-    int stat_h, stat_w;
-    float eps, clamp_lo, clamp_hi;
-    const int32_t* tame;         //   device flag: every b is a tame divisor (launch_b_tame)
     float* maxabs;               // mode 2, optional: (n_img, tiles_h, tiles_w, channels) max |coefficient| of every token,
                                  // accumulated with atomicMax on the bit pattern (the buffer must start at zero)
 };
@@ -164,71 +156,6 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&rr)[32], const int3
     }
 }
 
-// Forward pass 2 producing LFQ code words directly (one codebook per patch row, d == p): the value of column n
-// and row r is coefficient (kh = line(n), kw = r); its sign bit after PatchNorm is the sign of value - median
-// (exactly: see norm_sign_bit / the tame-divisor argument in fused_lfq.cu).  The 14 bits of one code word are
-// held by 14 consecutive lanes: one ballot per column, every lane cuts out the field of ITS token and the first
-// lane of the token ORs it into the shared code-word image (tokens can straddle warps and CTAs).
-struct SignCtx {
-    const float* med;          // + this row's base offset
-    const float* bst;
-    const int32_t* col_moff;   // per column: offset of (tile row, row-in-tile) in the statistics, < 0 past the end
-    const int32_t* col_grp;
-    unsigned* smax;            // as ScoreCtx
-    unsigned* codes_s;         // shared code-word image + this row's token column
-    int code_cols;
-    int l0, cnt, sh;           // lanes [l0, l0+cnt) hold this row's token; left shift of the field inside the word
-    unsigned cmask;
-    bool leader, row_ok, tame;
-    LfqNormParams q;
-};
-
-__device__ __forceinline__ void sign_chunk(const uint32_t (&rr)[32], const float* col_scale, float dcv, const SignCtx& sx,
-                                           int n0, int width) {
-    // all medians of the chunk first (independent loads, one L2 latency for the lot)
-    float mv[32];
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        if (j >= width) break;
-        const int4 moff = *reinterpret_cast<const int4*>(sx.col_moff + j);
-        const int mo[4] = {moff.x, moff.y, moff.z, moff.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) mv[j + u] = (sx.row_ok && mo[u] >= 0) ? __ldg(sx.med + mo[u]) : 0.0f;
-    }
-    float m = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        if (j >= width) break;
-        const int4 moff = *reinterpret_cast<const int4*>(sx.col_moff + j);
-        const int4 grp = *reinterpret_cast<const int4*>(sx.col_grp + j);
-        const float4 sc = *reinterpret_cast<const float4*>(col_scale + j);
-        float vv[4] = {__uint_as_float(rr[j]) * sc.x, __uint_as_float(rr[j + 1]) * sc.y,
-                       __uint_as_float(rr[j + 2]) * sc.z, __uint_as_float(rr[j + 3]) * sc.w};
-        if (j == 0) vv[0] += dcv;
-        const int mo[4] = {moff.x, moff.y, moff.z, moff.w};
-        const int gg[4] = {grp.x, grp.y, grp.z, grp.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (mo[u] >= 0) {                    // warp-uniform
-                bool bit = false;
-                if (sx.row_ok) {
-                    const float diff = __fsub_rn(vv[u], mv[j + u]);
-                    if (sx.tame && fabsf(diff) > 1e-20f) bit = diff > 0.0f;
-                    else bit = norm_sign_bit(vv[u], mv[j + u], __ldg(sx.bst + mo[u]), sx.q);
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, bit);
-                const unsigned part = (__brev((bal >> sx.l0) & sx.cmask) >> (32 - sx.cnt)) << sx.sh;
-                if (sx.leader && part) atomicOr(sx.codes_s + (n0 + j + u) * sx.code_cols, part);
-            }
-            m = fmaxf(m, fabsf(vv[u]));
-            if (gg[u] < 0) {
-                if (sx.row_ok) atomicMax(sx.smax + (gg[u] & 0x7fffffff) * 128, __float_as_uint(m));
-                m = 0.0f;
-            }
-        }
-    }
-}
-
 template <int MODE>   // 0: fp16 hi/lo output, 1: fp32 output (plain or token grid)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
 fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -244,14 +171,12 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __shared__ __align__(16) int32_t col_off[288];     // n_tile + one chunk of slack (guarded reads past the end)
     __shared__ __align__(16) float col_scale[288];
     __shared__ __align__(16) int32_t col_grp[288];
-    __shared__ __align__(16) int32_t col_moff[288];
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* basis_hi = smem;
     uint8_t* basis_lo = smem + g.basis_bytes;
     uint8_t* ring = smem + 2 * g.basis_bytes;
     unsigned* smax = reinterpret_cast<unsigned*>(ring + g.stages * F_STAGE);
-    unsigned* codes_s = smax + g.score_groups * 128;            // [n_tile][code_cols]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -304,15 +229,8 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             grp_v = th | (ends ? (int32_t)0x80000000 : 0);
         }
         col_grp[n] = grp_v;
-        int32_t mo = -1;
-        if (ep.mode == 2 && ep.code_grid != nullptr && n < n_lim) {
-            const int line = (nt * g.n_tile + n) * ep.col_mul + grp * ep.col_add;
-            const int th = line / ep.p, pi = line - th * ep.p;
-            mo = th * ep.stat_w * ep.p * ep.p + pi * ep.p;
-        }
-        col_moff[n] = mo;
     }
-    for (int i = threadIdx.x; i < g.score_groups * 128 + g.n_tile * g.code_cols; i += blockDim.x) smax[i] = 0u;
+    for (int i = threadIdx.x; i < g.score_groups * 128; i += blockDim.x) smax[i] = 0u;
     if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
     tc_fence_before();
     __syncthreads();
@@ -387,9 +305,6 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
         const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
         const bool dc_slice = (ep.dc != nullptr) && grp == 0 && nt == 0;
-        const bool signs = MODE == 1 && g.code_cols > 0;
-        const bool tame = signs && ep.tame != nullptr && __ldg(ep.tame) != 0 && ep.eps > 1e-12f && ep.clamp_lo < 0.0f &&
-                          ep.clamp_hi > 0.0f;
         uint32_t tcount = 0;
         for (int w = pair_in_slice; w < n_work; w += pairs_per_slice, ++tcount) {
             const int seg = (w / g.tiles_per_seg) * 2 + grp;
@@ -398,32 +313,12 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const int item = r / ep.rows_per_item, rin = r - item * ep.rows_per_item;
             int64_t base;
             ScoreCtx sctx{};
-            SignCtx sx{};
             if (ep.mode == 2) {
                 const int img = item / ep.channels, ch = item - img * ep.channels;
                 const int tw = rin / ep.p, pj = rin - tw * ep.p;
                 const int64_t tok0 = ((int64_t)img * ep.tiles_h * ep.tiles_w + tw) * ep.channels + ch;   // token at tile row 0
                 base = tok0 * (ep.p * ep.p) + pj;
                 sctx.smax = smax + quarter * 32 + lane;
-                if (signs) {
-                    const int64_t mbase = ((int64_t)ch * ep.stat_h * ep.stat_w + tw) * (ep.p * ep.p) + pj;
-                    sx.med = ep.med + mbase;
-                    sx.bst = ep.bstat + mbase;
-                    sx.col_grp = col_grp;
-                    sx.smax = sctx.smax;
-                    sx.code_cols = g.code_cols;
-                    const int R0 = (w % g.tiles_per_seg) * 256 + (int)rank * 128;
-                    sx.codes_s = codes_s + (r / ep.p - R0 / ep.p);
-                    sx.l0 = max(0, lane - pj);
-                    const int px0 = pj - (lane - sx.l0);
-                    sx.cnt = min(32 - sx.l0, ep.p - px0);
-                    sx.sh = ep.p - px0 - sx.cnt;
-                    sx.cmask = sx.cnt >= 32 ? 0xffffffffu : ((1u << sx.cnt) - 1u);
-                    sx.row_ok = row_ok;
-                    sx.leader = row_ok && lane == sx.l0;
-                    sx.tame = tame;
-                    sx.q = LfqNormParams{nullptr, nullptr, 0, 0, 0, 0, ep.eps, ep.clamp_lo, ep.clamp_hi, 0, 0, 0.f};
-                }
             } else {
                 base = (int64_t)seg * ep.seg_stride + (int64_t)item * ep.item_stride + rin;
             }
@@ -453,14 +348,6 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
                 }
                 const float dcc = c == 0 ? dcv : 0.0f;
-                if (signs) {
-                    // every lane takes part in the ballots; rows past the end contribute zero bits
-                    SignCtx sx2 = sx;
-                    sx2.col_moff = &col_moff[c * cwid];
-                    sx2.col_grp = &col_grp[c * cwid];
-                    sign_chunk(rr, &col_scale[c * cwid], dcc, sx2, c * cwid, cwid);
-                    continue;
-                }
                 if (MODE == 1 && g.score_groups > 0) {
                     if (row_ok) {
                         ScoreCtx sc2 = sctx;
@@ -494,25 +381,6 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                             const int img = plane / ep.channels, ch = plane - img * ep.channels;
                             atomicMax(reinterpret_cast<unsigned*>(ep.maxabs) +
                                           (((int64_t)img * ep.tiles_h + th) * ep.tiles_w + tw) * ep.channels + ch, m);
-                        }
-                    }
-                    if (signs) {
-                        // code words: one per (column = (tile row, row in tile), token column); tokens that lie entirely
-                        // inside this CTA's rows are stored, the others are OR-ed (the grid starts at zero)
-                        for (int i = (int)threadIdx.x - 64; i < n_lim * n_cols; i += 256) {
-                            const int n = i / n_cols, tcl = i - n * n_cols;
-                            const unsigned word = codes_s[n * g.code_cols + tcl];
-                            if (word == 0u) continue;
-                            codes_s[n * g.code_cols + tcl] = 0u;
-                            const int line = (nt * g.n_tile + n) * ep.col_mul + grp * ep.col_add;
-                            const int th = line / ep.p, pi = line - th * ep.p;
-                            const int sc = s_first + tcl;
-                            const int plane = sc / ep.tiles_w, tw = sc - plane * ep.tiles_w;
-                            const int img = plane / ep.channels, ch = plane - img * ep.channels;
-                            int32_t* dst = ep.code_grid +
-                                           ((((int64_t)img * ep.tiles_h + th) * ep.tiles_w + tw) * ep.channels + ch) * ep.p + pi;
-                            if (sc * ep.p >= R0 && sc * ep.p + ep.p <= Rend) *dst = (int32_t)word;
-                            else atomicOr(reinterpret_cast<unsigned*>(dst), word);
                         }
                     }
                 }
@@ -1178,12 +1046,11 @@ struct FoldOperand {
 };
 
 // slice geometry for a basis of n_valid rows and K columns: (n_tile, n_ntiles, stages), or false if nothing fits
-static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0, int extra_static = 0, int code_cols = 0) {
+static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0, int extra_static = 0) {
     g.num_kb = (int)ceil_div(K, FK);
     g.n_valid = n_valid;
     g.score_groups = score_groups;
-    g.code_cols = code_cols;
-    const int64_t score_bytes = (int64_t)score_groups * 128 * 4 + (int64_t)code_cols * 256 * 4;
+    const int64_t score_bytes = (int64_t)score_groups * 128 * 4;
     for (int nn = (int)ceil_div(n_valid, 256); nn <= 16; ++nn) {
         const int n_tile = (int)ceil_div(ceil_div(n_valid, nn), 16) * 16;
         const int64_t basis = (int64_t)g.num_kb * (n_tile / 2) * 64;
@@ -1206,8 +1073,7 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
     if (rows_per_seg == 0 || n_seg == 0) return DCTA_OK;
     FoldGemm g{};
     const int score_groups = (ep.mode == 2 && ep.maxabs != nullptr) ? ep.tiles_h : 0;
-    const int code_cols = (ep.mode == 2 && ep.code_grid != nullptr) ? 128 / ep.p + 2 : 0;
-    if (!fold_geometry(n_valid, K, g, score_groups, 0, code_cols)) { set_error("fold_gemm: basis %d x %d does not fit in shared memory", n_valid, K); return DCTA_ERR_UNSUPPORTED; }
+    if (!fold_geometry(n_valid, K, g, score_groups)) { set_error("fold_gemm: basis %d x %d does not fit in shared memory", n_valid, K); return DCTA_ERR_UNSUPPORTED; }
     if (rows_per_seg >= (1ll << 31) - 256 || (n_seg & 1)) { set_error("fold_gemm: bad segment geometry"); return DCTA_ERR_INVALID_ARG; }
     g.n_seg = n_seg;
     g.rows_per_seg = (int)rows_per_seg;
@@ -1218,7 +1084,7 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
     if ((rc = make_map3(&ma_lo, A.lo, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
     if ((rc = make_map3(&mb_hi, Bas.hi, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
     if ((rc = make_map3(&mb_lo, Bas.lo, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
-    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4 + g.code_cols * 256 * 4;
+    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1825,6 +1691,17 @@ extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const fl
     return launch_fold_gemm(A2, n_planes * (int64_t)kw, 2, B2, kh / 2, h2, e2, stream);
 }
 
+extern "C" int dcta_fold_codes_supported(int h, int w, int kh, int kw, int tile_p) {
+    if (!dcta_fold_supported(h, w, kh, kw)) return 0;
+    if (tile_p < 8 || tile_p > 16 || (tile_p & 1) || kh % tile_p || kw % tile_p || kh / 2 > 256) return 0;
+    int tokens = 256 / tile_p;
+    while (tokens > 0 && (tokens * tile_p) % 16) --tokens;
+    if (tokens < 2) return 0;
+    const int64_t basis = ceil_div(h / 2, FK) * (int64_t)F_ATILE;
+    const int64_t stage = ceil_div((int64_t)tokens * tile_p * 64, 1024) * 1024;
+    return (F_SMEM_LIMIT - 1024 - 2 * basis) / stage >= 3 && 4 * basis < (1 << 20);
+}
+
 // forward straight to LFQ code words (one codebook per patch row: c == d == tile_p): the pass-2 epilogue forms
 // sign(clamp((Y - median) / (b*sqrt2 + eps))) of every coefficient and never writes the token grid.
 //   code_grid (n_planes/channels, kh/p, kw/p, channels, p) int32, maxabs as in dcta_dct2_fwd_fold.
@@ -1837,9 +1714,9 @@ extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, co
     DCTA_REQUIRE(xq_hi && xq_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && maxabs &&
                  code_grid && median && b && tame_scratch, "dct2_fwd_fold_codes: null pointer");
     DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_fwd_fold_codes: needs h, w multiples of 16 and even kh <= h, kw <= w");
-    DCTA_REQUIRE(tile_p >= 8 && tile_p <= 32 && channels > 0 && kh % tile_p == 0 && kw % tile_p == 0 &&
-                 n_planes % channels == 0 && kh / tile_p <= H && kw / tile_p <= W && kh / tile_p <= 64,
-                 "dct2_fwd_fold_codes: needs 8 <= p <= 32, kh/kw multiples of p and a token grid inside the PatchNorm tables");
+    DCTA_REQUIRE(dcta_fold_codes_supported(h, w, kh, kw, tile_p), "dct2_fwd_fold_codes: geometry not supported");
+    DCTA_REQUIRE(channels > 0 && n_planes % channels == 0 && kh / tile_p <= H && kw / tile_p <= W,
+                 "dct2_fwd_fold_codes: needs a token grid inside the PatchNorm tables");
     if (n_planes == 0) return DCTA_OK;
     const int h2 = h / 2, w2 = w / 2;
     cudaStream_t st = as_stream(stream);
@@ -1858,24 +1735,14 @@ extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, co
     FoldOperand B2{(const __half*)bh_hi, (const __half*)bh_lo, h2, (int64_t)(kh / 2) * h2};
     const int64_t n_tok = (n_planes / channels) * (kh / tile_p) * (kw / tile_p) * channels;
     cudaMemsetAsync(maxabs, 0, sizeof(float) * n_tok, st);
-    {
-        // preferred: the transposed pass (a thread owns one coefficient row and packs the code words in registers)
-        CodesArgs cg{};
-        cg.p = tile_p; cg.channels = channels; cg.tiles_h = kh / tile_p; cg.tiles_w = kw / tile_p;
-        cg.alpha = 1.0f / kFScaleP; cg.basis_scale = rs_h; cg.dc = dc; cg.med = median; cg.bstat = b;
-        cg.stat_h = H; cg.stat_w = W; cg.eps = eps; cg.clamp_lo = lo; cg.clamp_hi = hi; cg.tame = tame_scratch;
-        cg.maxabs = maxabs; cg.code_grid = code_grid;
-        rc = launch_fold_codes(A2, n_planes * (int64_t)kw, B2, kh / 2, h2, cg, stream);
-        if (rc != DCTA_ERR_UNSUPPORTED) return rc;
-    }
-    FoldEpi e2{};
-    e2.rows_per_item = kw; e2.col_mul = 2; e2.col_add = 1;
-    e2.alpha = 1.0f / kFScaleP; e2.basis_scale = rs_h; e2.dc = dc;
-    e2.mode = 2; e2.p = tile_p; e2.channels = channels; e2.tiles_h = kh / tile_p; e2.tiles_w = kw / tile_p;
-    e2.maxabs = maxabs; e2.code_grid = code_grid; e2.med = median; e2.bstat = b; e2.stat_h = H; e2.stat_w = W;
-    e2.eps = eps; e2.clamp_lo = lo; e2.clamp_hi = hi; e2.tame = tame_scratch;
-    cudaMemsetAsync(code_grid, 0, sizeof(int32_t) * n_tok * tile_p, st);
-    return launch_fold_gemm(A2, n_planes * (int64_t)kw, 2, B2, kh / 2, h2, e2, stream);
+    CodesArgs cg{};
+    cg.p = tile_p; cg.channels = channels; cg.tiles_h = kh / tile_p; cg.tiles_w = kw / tile_p;
+    cg.alpha = 1.0f / kFScaleP; cg.basis_scale = rs_h; cg.dc = dc; cg.med = median; cg.bstat = b;
+    cg.stat_h = H; cg.stat_w = W; cg.eps = eps; cg.clamp_lo = lo; cg.clamp_hi = hi; cg.tame = tame_scratch;
+    cg.maxabs = maxabs; cg.code_grid = code_grid;
+    rc = launch_fold_codes(A2, n_planes * (int64_t)kw, B2, kh / 2, h2, cg, stream);
+    if (rc == DCTA_ERR_UNSUPPORTED) set_error("dct2_fwd_fold_codes: geometry not supported (see dcta_fold_codes_supported)");
+    return rc;
 }
 
 // inverse: yq[b][a][plane][kh/2][ldq] (scale 2^4, DC removed) -> z[b*2+a][plane][h/2][w/2] fp32 quadrant transforms

@@ -325,8 +325,9 @@ class DCTAutoencoderFeatureExtractor:
         n_tok = th * tw * c
         # one codebook per patch row on the folded tensor-core path: the DCT epilogue emits the code words itself
         in_epilogue = (os.environ.get("DCTA_NO_EPILOGUE_CODES") is None and self.dct_impl == "tc" and c == 3 and not self._hooks_overridden("_transform_image_in")
-                       and lfq.num_codebooks == p and lfq.codebook_dim == p and 8 <= p <= 32 and th <= 64
-                       and th <= norm.max_patch_h and tw <= norm.max_patch_w and fold_ok(h, w, th * p, tw * p))
+                       and lfq.num_codebooks == p and lfq.codebook_dim == p
+                       and th <= norm.max_patch_h and tw <= norm.max_patch_w
+                       and bool(_lib.load().dcta_fold_codes_supported(h, w, th * p, tw * p, p)))
         if in_epilogue:
             hi, lo, dc = rgb_to_ipt_fold(x)
             maxabs, code_grid = dct2_fwd_fold_codes(hi, lo, dc, th * p, tw * p, p, c, norm)

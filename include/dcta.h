@@ -155,6 +155,7 @@ int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, co
  *   code_grid (n_planes/channels, kh/p, kw/p, channels, p) int32: code word of patch row r of every token, in
  *   token-grid order (dcta_pack_codes_grid gathers them into sorted, packed order);  maxabs as above;
  *   median, b (channels, H, W, p*p);  tame_scratch: one device int32. */
+int dcta_fold_codes_supported(int h, int w, int kh, int kw, int tile_p);   /* 1 if the next entry point takes these sizes */
 int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
                              const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
                              const float* rs_h, void* work_hi, void* work_lo, float* maxabs, int32_t* code_grid,
