@@ -110,6 +110,88 @@ __global__ void __launch_bounds__(1024) sort_tokens_kernel(const float* __restri
         order[img * n_tok + i] = (int32_t)(keys[i] & 0xffffffffu);
 }
 
+// Faster variant for 128 <= n_pad <= 4096: four consecutive keys per thread.  Compare-exchange distances 1 and 2
+// stay in registers, distances 4..64 are partner lanes of the same warp (shuffles, no barrier), only distances
+// >= 128 go through (double-buffered) shared memory: 15 block barriers for 4096 keys instead of 78.
+__device__ __forceinline__ void cmp_swap(unsigned long long& a, unsigned long long& b, bool up) {
+    if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
+}
+
+template <bool kFromMax>
+__global__ void __launch_bounds__(1024) sort_tokens_fast_kernel(const float* __restrict__ scores,
+                                                                int32_t* __restrict__ order, int n_tok, int n_pad,
+                                                                ScoreParams sp) {
+    extern __shared__ unsigned long long keys[];          // [2][n_pad]
+    const int64_t img = blockIdx.x;
+    const float* s = scores + img * n_tok;
+    const int t = threadIdx.x, lane = t & 31;
+    unsigned long long k[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = 4 * t + e;
+        k[e] = ~0ull;
+        if (i < n_tok) {
+            float sc = s[i];
+            if (kFromMax) {
+                const int c = i % sp.channels;
+                const int tile = i / sp.channels;
+                const int h = tile / sp.tw, w = tile - h * sp.tw;
+                const float mags = __fmul_rn(sc, sp.mag_weight);
+                const float dist = __fdiv_rn((float)(-(h + w)), sp.imp.v[c]);
+                sc = __fadd_rn(mags, dist);
+                if (sp.scores_out) sp.scores_out[img * n_tok + i] = sc;
+            }
+            k[e] = ((unsigned long long)(~orderable(sc)) << 32) | (unsigned)i;
+        }
+    }
+    int buf = 0;
+    for (int size = 2; size <= n_pad; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 128) {
+                unsigned long long* kb = keys + buf * n_pad;
+                buf ^= 1;
+                reinterpret_cast<ulonglong2*>(kb)[2 * t] = make_ulonglong2(k[0], k[1]);
+                reinterpret_cast<ulonglong2*>(kb)[2 * t + 1] = make_ulonglong2(k[2], k[3]);
+                __syncthreads();
+                const int pt = t ^ (stride >> 2);                     // the partner thread holds the 4 partner keys
+                const ulonglong2 o01 = reinterpret_cast<const ulonglong2*>(kb)[2 * pt];
+                const ulonglong2 o23 = reinterpret_cast<const ulonglong2*>(kb)[2 * pt + 1];
+                const unsigned long long o[4] = {o01.x, o01.y, o23.x, o23.y};
+                const bool take_min = (((4 * t) & stride) == 0) == (((4 * t) & size) == 0);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) k[e] = take_min ? (k[e] < o[e] ? k[e] : o[e]) : (k[e] > o[e] ? k[e] : o[e]);
+            } else if (stride >= 4) {
+                const int d = stride >> 2;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 4 * t + e;
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[e], d);
+                    const bool up = (i & size) == 0, low = (lane & d) == 0;
+                    const bool take_min = (low == up);
+                    k[e] = take_min ? (k[e] < o ? k[e] : o) : (k[e] > o ? k[e] : o);
+                }
+            } else {
+                const bool up = ((4 * t) & size) == 0;       // size >= 4: the same direction for the 4 keys of a thread
+                if (stride == 2) {
+                    cmp_swap(k[0], k[2], up);
+                    cmp_swap(k[1], k[3], up);
+                } else if (size == 2) {                       // directions alternate between the two pairs
+                    cmp_swap(k[0], k[1], true);
+                    cmp_swap(k[2], k[3], false);
+                } else {
+                    cmp_swap(k[0], k[1], up);
+                    cmp_swap(k[2], k[3], up);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = 4 * t + e;
+        if (i < n_tok) order[img * n_tok + i] = (int32_t)(k[e] & 0xffffffffu);
+    }
+}
+
 // ------------------------------------------------------------------------------ pack
 // One warp per output slot (row, s).  kTiles: source is the token grid + sort order;
 // otherwise per-image token lists through pointer tables.
@@ -228,6 +310,18 @@ static int launch_sort(const float* scores, int32_t* order, int64_t n_img, int n
     if (smem > 48 * 1024) {  // per-device attribute: set on every call that needs it (cheap)
         cudaFuncSetAttribute(sort_tokens_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
         cudaFuncSetAttribute(sort_tokens_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    }
+    if (n_pad >= 128 && n_pad <= 4096) {
+        const size_t smem_fast = 2 * smem;
+        if (smem_fast > 48 * 1024) {
+            cudaFuncSetAttribute(sort_tokens_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 8);
+            cudaFuncSetAttribute(sort_tokens_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 8);
+        }
+        if (from_max)
+            sort_tokens_fast_kernel<true><<<(unsigned)n_img, n_pad / 4, smem_fast, as_stream(stream)>>>(scores, order, n_tok, n_pad, sp);
+        else
+            sort_tokens_fast_kernel<false><<<(unsigned)n_img, n_pad / 4, smem_fast, as_stream(stream)>>>(scores, order, n_tok, n_pad, sp);
+        return check_launch("sort_tokens");
     }
     int threads = n_pad / 2;
     if (threads > 1024) threads = 1024;

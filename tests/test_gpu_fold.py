@@ -159,3 +159,17 @@ torch.save(dict(tiles=tiles.cpu(), maxabs=maxabs.cpu(), planes=planes.cpu(), bac
     assert torch.equal(maxabs.cpu(), ref["maxabs"])
     assert torch.equal(planes.cpu(), ref["planes"])
     assert torch.equal(back.cpu(), ref["back"])
+
+
+@pytest.mark.parametrize("n_tok", [100, 128, 500, 3072, 4096, 5000])
+def test_sort_tokens_matches_torch_sort(D, n_tok):
+    """Per-image descending sort (ties: ascending index), both kernels (register/shuffle variant up to 4096 keys)."""
+    from dct_autoencoder_b200 import _lib
+    torch.manual_seed(n_tok)
+    scores = torch.randn(7, n_tok, device="cuda")
+    idx = torch.arange(0, n_tok - 1, 5, device="cuda")
+    scores[:, idx] = scores[:, idx + 1]                                    # exact ties
+    order = torch.empty((7, n_tok), dtype=torch.int32, device="cuda")
+    _lib.call("dcta_sort_tokens", _lib.ptr(scores), _lib.ptr(order), 7, n_tok, _lib.stream_ptr())
+    ref = torch.sort(scores, dim=1, descending=True, stable=True).indices
+    assert torch.equal(order.long(), ref)
