@@ -298,15 +298,23 @@ def run_ours(a):
         qt = 3 * 4 * Sq * Kq * 4            # inverse intermediate Q^T, hi + lo
         zq = 3 * 4 * Sq * Sq * 4            # fp32 quadrant transforms
         alg = [xq + pt, pt + yt, yt + qt, qt + zq]
-        gemm_ms = stages["dct_fwd"] + stages["dct_inv"]
+        fwd_key = "dct_fwd"
+        if "dct_fwd_codes" in stages:
+            # the timed (fused) step runs forward pass 2 as fold_codes_kernel: P^T in, 14 code words (int32) + the
+            # maximum per token out instead of the fp32 token grid
+            n_tok = 3 * (K // 14) * (K // 14)
+            alg[1] = pt + n_tok * (14 * 4 + 4)
+            fwd_key = "dct_fwd_codes"
+        gemm_ms = stages[fwd_key] + stages["dct_inv"]
         achieved_gbs = sum(alg) * B / (gemm_ms / 1e3) / 1e9
-        tens = (flops_fwd / (stages["dct_fwd"] / 1e3) / 1e12)
-        roofline = dict(bound="hbm", kernel="fold_gemm_kernel (4 launches per step: forward passes 1-2, inverse passes 1-2; "
+        tens = (flops_fwd / (stages[fwd_key] / 1e3) / 1e12)
+        roofline = dict(bound="hbm", kernel="fold_gemm_kernel x3 + fold_codes_kernel (the 4 DCT GEMM launches of the timed step: "
+                        "forward pass 1, forward pass 2 -> code words, inverse passes 1-2; "
                         "cta_group::2 tcgen05 fp16x3 split precision, folded basis resident in shared memory)",
                         achieved=achieved_gbs, peak=hbm, unit="GB/s", frac=achieved_gbs / hbm,
-                        # dram__bytes_read + write per launch, ncu --set full of this workload
-                        # (profiles/r01x_kernels_ncu_full_b256.txt: 1274 / 1459 / 1465 / 1414 MB for the 4 launches)
-                        traffic=(1.403e9 if (B == 256 and S == 512) else None),
+                        # dram__bytes_read + write per launch, ncu --set full of this workload (profiles/: 1465 MB forward
+                        # pass 1, 758 MB fold_codes_kernel, 1274 / 1459 MB inverse passes)
+                        traffic=(1.24e9 if (B == 256 and S == 512 and "dct_fwd_codes" in stages) else None),
                         launches_per_step=4, avg_launch_ms=gemm_ms / 4,
                         algorithmic_bytes_per_launch=sum(alg) * B / 4,
                         peak_source=("measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"),
@@ -394,6 +402,10 @@ def stage_times(torch, D, pipe, x, dev, reps=3):
     if fold:
         hi, lo, dc = t("rgb_to_ipt_fold", lambda: U.rgb_to_ipt_fold(x))
         tiles = t("dct_fwd", lambda: U.dct2_fwd_fold(hi, lo, dc, KH, KW, tile_p=p, channels=3))
+        if (pipe.fusable() and lfq.num_codebooks == p and lfq.codebook_dim == p
+                and _lib.load().dcta_fold_codes_supported(H, W, KH, KW, p)):
+            # what the fused step runs: pass 1 + pass 2 straight to code words (no token grid)
+            t("dct_fwd_codes", lambda: U.dct2_fwd_fold_codes(hi, lo, dc, KH, KW, p, 3, pn))
         del hi, lo
     elif tc:
         hi, lo, dc = t("rgb_to_ipt_split", lambda: U.rgb_to_ipt_split(x))

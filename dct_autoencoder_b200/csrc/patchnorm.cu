@@ -12,6 +12,30 @@ namespace dcta {
 constexpr float kSqrt2 = 1.41421356237309504880f;  // float32(2 ** 0.5), PN:158
 
 // ------------------------------------------------------------------------------ apply
+__device__ __forceinline__ int clamped_position(const int64_t* channels, const int64_t* positions, int64_t tok, int C,
+                                                int H, int W) {
+    int64_t c = channels[tok], h = positions[2 * tok], w = positions[2 * tok + 1];
+    // torch indexing wraps negative indices; out-of-range indices raise in the reference.
+    if (c < 0) c += C;
+    if (h < 0) h += H;
+    if (w < 0) w += W;
+    c = min(max(c, (int64_t)0), (int64_t)C - 1);
+    h = min(max(h, (int64_t)0), (int64_t)H - 1);
+    w = min(max(w, (int64_t)0), (int64_t)W - 1);
+    return (int)((c * H + h) * W + w);
+}
+
+template <bool kInverse>
+__device__ __forceinline__ float patchnorm_value(float xv, float mv, float bv, float eps, float lo, float hi) {
+    const float sd = __fadd_rn(__fmul_rn(bv, kSqrt2), eps);
+    if (kInverse) return __fadd_rn(__fmul_rn(xv, sd), mv);          // PN:177
+    const float y = __fdiv_rn(__fsub_rn(xv, mv), sd);                // PN:161
+    return y < lo ? lo : (y > hi ? hi : y);                          // PN:163 (NaN propagates, as torch.clamp)
+}
+
+// kVec == 4 (z % 4 == 0, z <= 256): a warp takes 32 consecutive tokens, the position lookups (three dependent
+// 8-byte loads per token) run once, lane-parallel, and the tokens are then streamed two at a time with 128-bit
+// accesses, i.e. up to 12 independent loads in flight per lane.  kVec == 1: one warp per token, scalar.
 template <bool kInverse, int kVec>
 __global__ void __launch_bounds__(256) patchnorm_apply_kernel(
     const float* __restrict__ x, const int64_t* __restrict__ channels,
@@ -21,40 +45,75 @@ __global__ void __launch_bounds__(256) patchnorm_apply_kernel(
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    if (kVec == 4 && z <= 256) {
+        const int z4 = z >> 2;
+        for (int64_t tok0 = warp0 * 32; tok0 < n_tok; tok0 += n_warps * 32) {
+            const int pid_mine = tok0 + lane < n_tok ? clamped_position(channels, positions, tok0 + lane, C, H, W) : 0;
+            const int n_here = (int)min((int64_t)32, n_tok - tok0);
+            for (int t = 0; t < n_here; t += 2) {
+                float4 xv[2][2], mv[2][2], bv[2][2];
+                const bool second = t + 1 < n_here;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int pid = __shfl_sync(0xffffffffu, pid_mine, t + u);
+                    if (u == 0 || second) {
+                        const float4* xs = reinterpret_cast<const float4*>(x + (tok0 + t + u) * z);
+                        const float4* ms = reinterpret_cast<const float4*>(median + (int64_t)pid * z);
+                        const float4* bs = reinterpret_cast<const float4*>(b + (int64_t)pid * z);
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int i = lane + 32 * pass;
+                            if (i < z4) {
+                                xv[u][pass] = ld_stream(xs + i);
+                                mv[u][pass] = __ldg(ms + i);
+                                bv[u][pass] = __ldg(bs + i);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (u == 0 || second) {
+                        float4* os = reinterpret_cast<float4*>(out + (tok0 + t + u) * z);
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int i = lane + 32 * pass;
+                            if (i < z4) {
+                                float4 o;
+                                o.x = patchnorm_value<kInverse>(xv[u][pass].x, mv[u][pass].x, bv[u][pass].x, eps, lo, hi);
+                                o.y = patchnorm_value<kInverse>(xv[u][pass].y, mv[u][pass].y, bv[u][pass].y, eps, lo, hi);
+                                o.z = patchnorm_value<kInverse>(xv[u][pass].z, mv[u][pass].z, bv[u][pass].z, eps, lo, hi);
+                                o.w = patchnorm_value<kInverse>(xv[u][pass].w, mv[u][pass].w, bv[u][pass].w, eps, lo, hi);
+                                st_stream(os + i, o);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (int64_t tok = warp0; tok < n_tok; tok += n_warps) {
-        int64_t c = channels[tok], h = positions[2 * tok], w = positions[2 * tok + 1];
-        // torch indexing wraps negative indices; out-of-range indices raise in the reference.
-        if (c < 0) c += C;
-        if (h < 0) h += H;
-        if (w < 0) w += W;
-        c = min(max(c, (int64_t)0), (int64_t)C - 1);
-        h = min(max(h, (int64_t)0), (int64_t)H - 1);
-        w = min(max(w, (int64_t)0), (int64_t)W - 1);
-        const int64_t pid = (c * H + h) * W + w;
+        const int64_t pid = clamped_position(channels, positions, tok, C, H, W);
         const float* xs = x + tok * z;
         const float* ms = median + pid * z;
         const float* bs = b + pid * z;
         float* os = out + tok * z;
-        auto f = [&](float xv, float mv, float bv) -> float {
-            const float sd = __fadd_rn(__fmul_rn(bv, kSqrt2), eps);
-            if (kInverse) return __fadd_rn(__fmul_rn(xv, sd), mv);          // PN:177
-            const float y = __fdiv_rn(__fsub_rn(xv, mv), sd);                // PN:161
-            return y < lo ? lo : (y > hi ? hi : y);                          // PN:163 (NaN propagates, as torch.clamp)
-        };
         if (kVec == 4) {
             for (int i = lane; i < z / 4; i += 32) {
                 const float4 xv = ld_stream(reinterpret_cast<const float4*>(xs) + i);
                 const float4 mv = __ldg(reinterpret_cast<const float4*>(ms) + i);
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(bs) + i);
                 float4 o;
-                o.x = f(xv.x, mv.x, bv.x);
-                o.y = f(xv.y, mv.y, bv.y);
-                o.z = f(xv.z, mv.z, bv.z);
-                o.w = f(xv.w, mv.w, bv.w);
+                o.x = patchnorm_value<kInverse>(xv.x, mv.x, bv.x, eps, lo, hi);
+                o.y = patchnorm_value<kInverse>(xv.y, mv.y, bv.y, eps, lo, hi);
+                o.z = patchnorm_value<kInverse>(xv.z, mv.z, bv.z, eps, lo, hi);
+                o.w = patchnorm_value<kInverse>(xv.w, mv.w, bv.w, eps, lo, hi);
                 st_stream(reinterpret_cast<float4*>(os) + i, o);
             }
         } else {
-            for (int i = lane; i < z; i += 32) os[i] = f(__ldg(xs + i), __ldg(ms + i), __ldg(bs + i));
+            for (int i = lane; i < z; i += 32)
+                os[i] = patchnorm_value<kInverse>(__ldg(xs + i), __ldg(ms + i), __ldg(bs + i), eps, lo, hi);
         }
     }
 }
@@ -276,8 +335,8 @@ extern "C" int dcta_patchnorm_apply(const float* x, const int64_t* channels,
     DCTA_REQUIRE(x && channels && positions && median && b && out, "patchnorm_apply: null pointer");
     DCTA_REQUIRE(n_tok >= 0 && z > 0 && C > 0 && H > 0 && W > 0, "patchnorm_apply: bad sizes");
     if (n_tok == 0) return DCTA_OK;
-    const int grid = grid_for(n_tok, 8);
     const bool vec = (z % 4 == 0) && al16(x) && al16(out) && al16(median) && al16(b);
+    const int grid = (vec && z <= 256) ? grid_for(n_tok, 256) : grid_for(n_tok, 8);
     cudaStream_t st = as_stream(stream);
 #define LAUNCH(INV, VEC) patchnorm_apply_kernel<INV, VEC><<<grid, 256, 0, st>>>(x, channels, positions, median, b, out, n_tok, z, C, H, W, eps, lo, hi)
     if (inverse) { if (vec) LAUNCH(true, 4); else LAUNCH(true, 1); }
