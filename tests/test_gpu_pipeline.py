@@ -142,3 +142,41 @@ def test_fused_codes_match_staged_when_values_tie_with_the_median(D):
         rec_f, codes_f = pipe.roundtrip(x)
         assert torch.equal(codes_f, codes_s)
         assert torch.equal(rec_f, rec_s)
+
+
+@pytest.mark.parametrize("patch,size,max_seq_len,beta", [
+    (16, (256, 256), 1024, 0.0),       # 16-column tiles: 16 token columns per 256-row data tile
+    (8, (128, 192), 3072, 0.0),        # 8-column tiles: 32 token columns per tile
+    (14, (512, 512), 3072, 0.0),       # config 2
+    (14, (1024, 1024), 1024, 0.004),   # config 3b: top-k cap, variable k, several images per row (the 512-wide basis does
+                                       # not fit next to the ring: token grid + pack_codes_vec_kernel is used instead)
+    (12, (192, 240), 700, 0.0),        # 12-column tiles: 20 token columns = 240 rows per tile
+])
+def test_codes_in_the_dct_epilogue_for_other_tile_sizes(D, patch, size, max_seq_len, beta):
+    """fold_codes_kernel (forward pass 2 straight to code words) for every tile size it accepts: same codes,
+    metadata and reconstructions, bit for bit, as the staged modules."""
+    import random
+    from dct_autoencoder_b200 import _lib
+    torch.manual_seed(patch)
+    h, w = size
+    n = 3 if h >= 1024 else 6
+    x = torch.rand(n, 3, h, w).cuda()
+    fe = D.DCTAutoencoderFeatureExtractor(3, patch, beta, 32, 32, max_seq_len)
+    _, _, th, tw = fe._geometry(h, w)
+    assert bool(_lib.load().dcta_fold_codes_supported(h, w, th * patch, tw * patch, patch)) == (h < 1024)
+    pn = D.PatchNorm(32, 32, patch, 3).cuda()
+    lfq = D.LFQ(codebook_size=2 ** patch, num_codebooks=patch).cuda().eval()
+    pipe = D.TransformPipeline(fe, pn, lfq)
+    random.seed(1)
+    pipe.fit_norm(torch.rand(4, 3, h, w).cuda())
+    assert pipe.fusable()
+    random.seed(5)
+    rec_s, codes_s = pipe.roundtrip(x, fused=False)
+    random.seed(5)
+    batch_s, _, _ = pipe.encode(x)
+    random.seed(5)
+    batch_f, codes_f = pipe.encode_codes(x)
+    for f in ("key_pad_mask", "batched_image_ids", "patch_channels", "patch_positions"):
+        assert torch.equal(getattr(batch_f, f), getattr(batch_s, f)), f
+    assert torch.equal(codes_f, codes_s)
+    assert torch.equal(pipe.decode_codes(batch_f, codes_f), rec_s)
