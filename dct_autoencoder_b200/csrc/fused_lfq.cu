@@ -282,49 +282,62 @@ __global__ void pad_codes_kernel(LfqNormParams q, int64_t* __restrict__ pad_code
 
 // Gather of the code words computed by the forward DCT epilogue (dct_fold.cu): code_grid (n_img, th, tw, C, c)
 // int32 in token-grid order -> codes (rows, s, c) int64 in packed, sorted order, + the bookkeeping outputs.
-// One thread per slot: the metadata chain runs lane-parallel, every lane copies its own c words.
+// A warp takes 32 consecutive slots: the metadata chain runs once, lane-parallel; the 32 * c code words are
+// then copied with the lanes on consecutive OUTPUT words (fully coalesced 256-byte stores, independent loads).
 __global__ void __launch_bounds__(256) pack_codes_grid_kernel(
     const int32_t* __restrict__ code_grid, const int32_t* __restrict__ order, const dcta_segment* __restrict__ segs,
     const int32_t* __restrict__ row_seg_start, int n_rows, int s, int tw, int channels, int n_tok_img,
-    float inv_channels, float inv_tw, int c, const int64_t* __restrict__ pad_codes, int64_t* __restrict__ codes,
-    int64_t* __restrict__ positions, int64_t* __restrict__ channels_out, int64_t* __restrict__ image_ids,
-    uint8_t* __restrict__ key_pad_mask) {
+    float inv_channels, float inv_tw, int c, float inv_c, const int64_t* __restrict__ pad_codes,
+    int64_t* __restrict__ codes, int64_t* __restrict__ positions, int64_t* __restrict__ channels_out,
+    int64_t* __restrict__ image_ids, uint8_t* __restrict__ key_pad_mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t total = (int64_t)n_rows * s;
-    for (int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += (int64_t)gridDim.x * blockDim.x) {
-        const int row = (int)(slot / s);
-        const int off = (int)(slot - (int64_t)row * s);
-        int lo = row_seg_start[row], hi = row_seg_start[row + 1];
-        int seg = -1;
-        if (hi - lo == 1) {
-            seg = (off >= segs[lo].offset && off < segs[lo].offset + segs[lo].k) ? lo : -1;
-        } else {
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                const int so = segs[mid].offset;
-                if (off < so) hi = mid;
-                else if (off >= so + segs[mid].k) lo = mid + 1;
-                else { seg = mid; break; }
+    for (int64_t slot0 = warp0 * 32; slot0 < total; slot0 += n_warps * 32) {
+        const int64_t slot = slot0 + lane;
+        int64_t src_off = -1;                  // first code word of the token in code_grid, -1 = padding slot
+        if (slot < total) {
+            const int row = (int)(slot / s);
+            const int off = (int)(slot - (int64_t)row * s);
+            int lo = row_seg_start[row], hi = row_seg_start[row + 1];
+            int seg = -1;
+            if (hi - lo == 1) {
+                seg = (off >= segs[lo].offset && off < segs[lo].offset + segs[lo].k) ? lo : -1;
+            } else {
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int so = segs[mid].offset;
+                    if (off < so) hi = mid;
+                    else if (off >= so + segs[mid].k) lo = mid + 1;
+                    else { seg = mid; break; }
+                }
             }
+            int ph = 0, pw = 0, pc = 0, image_id = 0;
+            if (seg >= 0) {
+                const dcta_segment sg = segs[seg];
+                const int tok = order[sg.img * n_tok_img + (off - sg.offset)];
+                const int tile = (int)(((float)tok + 0.5f) * inv_channels);   // exact for tok < 2^22
+                pc = tok - tile * channels;
+                ph = (int)(((float)tile + 0.5f) * inv_tw);
+                pw = tile - ph * tw;
+                image_id = sg.image_id;
+                src_off = (sg.img * n_tok_img + tok) * (int64_t)c;
+            }
+            reinterpret_cast<longlong2*>(positions)[slot] = make_longlong2(ph, pw);
+            channels_out[slot] = pc;
+            if (image_ids) image_ids[slot] = image_id;
+            if (key_pad_mask) key_pad_mask[slot] = seg < 0;
         }
-        int ph = 0, pw = 0, pc = 0, image_id = 0;
-        int64_t* dst = codes + slot * c;
-        if (seg >= 0) {
-            const dcta_segment sg = segs[seg];
-            const int tok = order[sg.img * n_tok_img + (off - sg.offset)];
-            const int tile = (int)(((float)tok + 0.5f) * inv_channels);   // exact for tok < 2^22
-            pc = tok - tile * channels;
-            ph = (int)(((float)tile + 0.5f) * inv_tw);
-            pw = tile - ph * tw;
-            image_id = sg.image_id;
-            const int32_t* src = code_grid + (sg.img * n_tok_img + tok) * (int64_t)c;
-            for (int i = 0; i < c; ++i) dst[i] = (int64_t)__ldg(src + i);
-        } else {
-            for (int i = 0; i < c; ++i) dst[i] = __ldg(pad_codes + i);
+        const int n_words = (int)min((int64_t)32, total - slot0) * c;
+        int64_t* dst = codes + slot0 * c;
+#pragma unroll 4
+        for (int it = 0; it < c; ++it) {
+            const int idx = it * 32 + lane;
+            const int sl = min((int)(((float)idx + 0.5f) * inv_c), 31), wd = idx - sl * c;
+            const int64_t so = __shfl_sync(0xffffffffu, src_off, sl);
+            if (idx < n_words) dst[idx] = so >= 0 ? (int64_t)__ldg(code_grid + so + wd) : __ldg(pad_codes + wd);
         }
-        reinterpret_cast<longlong2*>(positions)[slot] = make_longlong2(ph, pw);
-        channels_out[slot] = pc;
-        if (image_ids) image_ids[slot] = image_id;
-        if (key_pad_mask) key_pad_mask[slot] = seg < 0;
     }
 }
 
@@ -479,6 +492,6 @@ extern "C" int dcta_pack_codes_grid(const int32_t* code_grid, const int32_t* ord
     pad_codes_kernel<<<1, 32, 0, as_stream(stream)>>>(q, pad_scratch);
     pack_codes_grid_kernel<<<grid_for((int64_t)n_rows * s, 256), 256, 0, as_stream(stream)>>>(
         code_grid, order, segs, row_seg_start, n_rows, s, tw, channels, th * tw * channels, 1.0f / (float)channels,
-        1.0f / (float)tw, c, pad_scratch, codes, positions, channels_out, image_ids, key_pad_mask);
+        1.0f / (float)tw, c, 1.0f / (float)c, pad_scratch, codes, positions, channels_out, image_ids, key_pad_mask);
     return check_launch("pack_codes_grid");
 }
