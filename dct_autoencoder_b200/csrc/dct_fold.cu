@@ -49,7 +49,9 @@ struct FoldGemm {
 };
 
 struct FoldEpi {
-    int mode;                    // 0: fp16 hi/lo, 1: fp32, 2: fp32 token grid (forward pass 2)
+    int mode;                    // 0: fp16 hi/lo, 1: fp32, 2: fp32 token grid (forward pass 2),
+                                 // 3: fp16 hi/lo with the output lines regrouped as [channel][token column][image][pj]
+                                 //    (forward pass 1 feeding fold_codes_kernel; uses p, channels, tiles_w, batch)
     __half* out_hi;
     __half* out_lo;
     float* out_f32;
@@ -61,7 +63,8 @@ struct FoldEpi {
     float alpha;
     const float* basis_scale;    // optional (2, n_valid) per-basis-row factors
     const float* dc;             // optional per-item constant added to (group 0, basis row 0, row-in-item 0)
-    int p, channels, tiles_h, tiles_w;   // mode 2
+    int p, channels, tiles_h, tiles_w;   // modes 2, 3
+    int batch;                           // mode 3: images
     float* maxabs;               // mode 2, optional: (n_img, tiles_h, tiles_w, channels) max |coefficient| of every token,
                                  // accumulated with atomicMax on the bit pattern (the buffer must start at zero)
 };
@@ -214,6 +217,9 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             if (ep.mode == 2) {
                 const int th = line / ep.p, pi = line - th * ep.p;
                 off = th * ep.tiles_w * ep.channels * ep.p * ep.p + pi * ep.p;
+            } else if (ep.mode == 3) {
+                const int tw = line / ep.p, pj = line - tw * ep.p;
+                off = (tw * ep.batch * ep.p + pj) * ep.col_stride;
             } else {
                 off = line * ep.col_stride;
             }
@@ -319,6 +325,13 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 const int64_t tok0 = ((int64_t)img * ep.tiles_h * ep.tiles_w + tw) * ep.channels + ch;   // token at tile row 0
                 base = tok0 * (ep.p * ep.p) + pj;
                 sctx.smax = smax + quarter * 32 + lane;
+            } else if (ep.mode == 3) {
+                // item = a * planes + plane: the line block of (a, channel) starts at ((a*C + ch) * tiles_w * batch) * p,
+                // inside it image img adds img * p lines (the token column adds tw * batch * p + pj: col_off)
+                const int planes = ep.batch * ep.channels;
+                const int a = item / planes, plane = item - a * planes;
+                const int img = plane / ep.channels, ch = plane - img * ep.channels;
+                base = (((int64_t)(a * ep.channels + ch) * ep.tiles_w * ep.batch + img) * ep.p) * ep.col_stride + rin;
             } else {
                 base = (int64_t)seg * ep.seg_stride + (int64_t)item * ep.item_stride + rin;
             }
@@ -414,6 +427,7 @@ struct CodesArgs {
     uint32_t basis_bytes;   // one CTA's resident basis plane (hi or lo): num_kb * 128 * 64
     uint32_t stage_bytes;   // one ring stage: this CTA's n_data/2 data rows, hi then lo
     int p, channels, tiles_h, tiles_w;
+    int batch;                  // images: the data rows are ordered [channel][token column tw][image][pj]
     float alpha;
     const float* basis_scale;   // (2, n_valid)
     const float* dc;            // per plane constant added to coefficient (0, 0)
@@ -560,38 +574,34 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
         uint32_t tcount = 0;
         for (int w = pair_in_grp; w < g.tiles_per_seg; w += pairs_per_grp, ++tcount) {
             const int acc = tcount & 1;
-            // token column counters of this warp's first token (global column = plane * tiles_w + tw)
+            // token of this warp's first data column: the data rows run [channel][tw][image][pj]
             int tc = w * g.tokens_per_tile + t_lo;
-            int plane = tc / g.tiles_w, tw = tc - plane * g.tiles_w;
-            int img = plane / g.channels, ch = plane - img * g.channels;
-            int tc_n = tc, plane_n = plane, tw_n = tw, ch_n = ch;      // the same for the token whose medians are in flight
+            int img = tc % g.batch;
+            int tw = (tc / g.batch) % g.tiles_w, ch = tc / (g.batch * g.tiles_w);
             mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
-            float2 mcur[8], mnext[8];
-            auto load_medians = [&](bool in_range, float2 (&dst)[8]) {
-                const bool ok = i_ok && in_range && (int64_t)tc_n * p < g.rows_per_seg;
-                const float2* src = reinterpret_cast<const float2*>(g.med + ch_n * stat_ch + (int64_t)tw_n * z + stat_row);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = (ok && j < p2) ? __ldg(src + j) : make_float2(0.f, 0.f);
-            };
-            auto advance_n = [&]() {
-                ++tc_n;
-                if (++tw_n == g.tiles_w) { tw_n = 0; ++plane_n; if (++ch_n == g.channels) ch_n = 0; }
-            };
-            load_medians(t_lo < t_hi, mcur);
+            // the medians of this coefficient row depend on (channel, tw) only: one load per run of images
+            float2 mcur[8];
+            int m_tw = -1, m_ch = -1;
             for (int tk = t_lo; tk < t_hi; ++tk) {
                 uint32_t rr[16];
                 tmem_ld16_nowait(tmem_acc + tk * p, rr);
-                advance_n();
-                load_medians(tk + 1 < t_hi, mnext);
+                const bool tok_ok = (int64_t)tc * p < g.rows_per_seg;           // warp-uniform
+                if (tok_ok && (tw != m_tw || ch != m_ch)) {
+                    const float2* src = reinterpret_cast<const float2*>(g.med + ch * stat_ch + (int64_t)tw * z + stat_row);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) mcur[j] = (i_ok && j < p2) ? __ldg(src + j) : make_float2(0.f, 0.f);
+                    m_tw = tw;
+                    m_ch = ch;
+                }
                 tmem_ld_wait();
                 if (tk == t_hi - 1) {                          // accumulator read out by this warp: hand it back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
                 }
-                const bool tok_ok = (int64_t)tc * p < g.rows_per_seg;           // warp-uniform
+                const int plane = img * g.channels + ch;
                 const int64_t tok = ((int64_t)img * g.tiles_h * g.tiles_w + tw) * g.channels + ch + tok_row;
                 const float mvals[16] = {mcur[0].x, mcur[0].y, mcur[1].x, mcur[1].y, mcur[2].x, mcur[2].y, mcur[3].x, mcur[3].y,
                                          mcur[4].x, mcur[4].y, mcur[5].x, mcur[5].y, mcur[6].x, mcur[6].y, mcur[7].x, mcur[7].y};
@@ -637,10 +647,8 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
                     if (take[o]) mx = fmaxf(mx, other);
                 }
                 if (tok_ok && th_leader && mx > 0.0f) atomicMax(reinterpret_cast<unsigned*>(g.maxabs) + tok, __float_as_uint(mx));
-#pragma unroll
-                for (int j = 0; j < 8; ++j) mcur[j] = mnext[j];
                 ++tc;
-                if (++tw == g.tiles_w) { tw = 0; ++plane; if (++ch == g.channels) { ch = 0; ++img; } }
+                if (++img == g.batch) { img = 0; if (++tw == g.tiles_w) { tw = 0; ++ch; } }
             }
             if (t_hi <= t_lo) {                                  // nothing to read: release immediately
                 tc_fence_before();
@@ -1095,7 +1103,7 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
     if (pps > work_per_slice) pps = work_per_slice;
     const unsigned grid = (unsigned)(2 * pps * n_slices);
     cudaError_t e;
-    if (ep.mode == 0) {
+    if (ep.mode == 0 || ep.mode == 3) {          // fp16 hi/lo outputs
         e = cudaFuncSetAttribute(fold_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e == cudaSuccess)
             fold_gemm_kernel<0><<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, g, ep);
@@ -1725,9 +1733,11 @@ extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, co
     FoldOperand A1{(const __half*)xq_hi, (const __half*)xq_lo, w2, 2 * n_planes * (int64_t)h2 * w2};
     FoldOperand B1{(const __half*)bw_hi, (const __half*)bw_lo, w2, (int64_t)(kw / 2) * w2};
     FoldEpi e1{};
-    e1.mode = 0; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
-    e1.rows_per_item = h2; e1.seg_stride = 0; e1.item_stride = (int64_t)kw * h2;
-    e1.col_mul = 2; e1.col_add = 1; e1.col_stride = h2;
+    // pass 1 writes P^T with its lines regrouped as [a][channel][token column][image][pj]: the 16 token columns of a
+    // fold_codes_kernel tile are then 16 images at the SAME (channel, tw), i.e. they share their PatchNorm medians
+    e1.mode = 3; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
+    e1.rows_per_item = h2; e1.col_mul = 2; e1.col_add = 1; e1.col_stride = h2;
+    e1.p = tile_p; e1.channels = channels; e1.tiles_w = kw / tile_p; e1.batch = (int)(n_planes / channels);
     e1.alpha = kFScaleP / kFScaleX; e1.basis_scale = rs_w;
     rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)h2, 2, B1, kw / 2, w2, e1, stream);
     if (rc) return rc;
@@ -1737,6 +1747,7 @@ extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, co
     cudaMemsetAsync(maxabs, 0, sizeof(float) * n_tok, st);
     CodesArgs cg{};
     cg.p = tile_p; cg.channels = channels; cg.tiles_h = kh / tile_p; cg.tiles_w = kw / tile_p;
+    cg.batch = (int)(n_planes / channels);
     cg.alpha = 1.0f / kFScaleP; cg.basis_scale = rs_h; cg.dc = dc; cg.med = median; cg.bstat = b;
     cg.stat_h = H; cg.stat_w = W; cg.eps = eps; cg.clamp_lo = lo; cg.clamp_hi = hi; cg.tame = tame_scratch;
     cg.maxabs = maxabs; cg.code_grid = code_grid;
