@@ -1093,8 +1093,12 @@ extern "C" int dcta_vq_nearest_tc(const float* x, const void* x_hi, const void* 
     DCTA_REQUIRE(n_tok >= 0 && n_codes > 0 && d > 0 && ld >= d && ld % 8 == 0, "vq_nearest_tc: bad sizes");
     if (n_tok == 0) return DCTA_OK;
     const int n_tiles = (int)ceil_div(n_codes, TN);
+    // preferred: CTA pairs with the token operand resident in shared memory (vq_tc.cu)
+    int rc_pair = launch_vq_pair(x_hi, x_lo, e_hi, e_lo, e2, alpha_dev, part_val, part_idx, n_tok, n_codes, d, ld,
+                                 as_stream(stream));
+    if (rc_pair != DCTA_OK && rc_pair != DCTA_ERR_UNSUPPORTED) return rc_pair;
     const int64_t max_rows = 65535ll * TM;   // grid.y limit
-    for (int64_t r0 = 0; r0 < n_tok; r0 += max_rows) {
+    for (int64_t r0 = 0; rc_pair == DCTA_ERR_UNSUPPORTED && r0 < n_tok; r0 += max_rows) {
         const int64_t rows = n_tok - r0 < max_rows ? n_tok - r0 : max_rows;
         Operand A{(const __half*)x_hi + r0 * ld, (const __half*)x_lo + r0 * ld, (int)rows, ld, 0};
         Operand B{(const __half*)e_hi, (const __half*)e_lo, n_codes, ld, 0};
