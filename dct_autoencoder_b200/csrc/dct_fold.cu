@@ -1573,6 +1573,206 @@ __global__ void __launch_bounds__(256, 4) unpatchify_fold_kernel(const float* __
     }
 }
 
+// The same for one LFQ codebook per patch row (c == d == p <= 16), the configuration of the headline benchmark.
+// A de-quantised, de-normalised coefficient can only be one of TWO values per position: median + s*sd or
+// median - s*sd (lfq.py:118-120, patchnorm.py:177).  Both are computed once per CTA, already scaled and split into
+// their fp16 hi/lo halves (packed in one 32-bit word: hi in the low half), and staged in shared memory as
+// [row][column group][8] (16-byte halves swizzled: conflict-free 128-bit reads).  The main loop is then one select
+// per element on the sign bit and one byte-permute per pair of elements to assemble the 8-byte hi and lo groups
+// of each column parity: about a quarter of the instructions of the generic kernel, bit-identical results.
+__device__ __forceinline__ uint32_t pack_split16(float v, float scale) {
+    const float sv = v * scale;
+    const __half h = __float2half_rn(sv);
+    const __half l = __float2half_rn(sv - __half2float(h));
+    return (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+}
+
+// The two-value tables of EVERY (channel, tile row) of the PatchNorm statistics, in the shared-memory layout of
+// decode_codes_rows_kernel ([channel][tile row][row][column group of the full statistics width][8], swizzled): a CTA
+// then stages its rows with plain 128-bit copies.  tab: pos then neg, each C*H*p*nxv_tab*8 words.
+__global__ void __launch_bounds__(256) decode_tables_kernel(LfqNormParams q, int p, int nxv_tab, float scale,
+                                                            uint32_t* __restrict__ pos_tab, uint32_t* __restrict__ neg_tab) {
+    const int z = p * p;
+    const int64_t total = (int64_t)q.C * q.H * p * nxv_tab * 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k4 = (int)(i & 3);
+        int64_t r = i >> 2;
+        const int hs = (int)(r & 1);             // stored 16-byte half
+        r >>= 1;
+        const int xv = (int)(r % nxv_tab);
+        r /= nxv_tab;
+        const int py = (int)(r % p);
+        r /= p;
+        const int ty = (int)(r % q.H);
+        const int c = (int)(r / q.H);
+        const int k = ((hs ^ ((xv >> 2) & 1)) << 2) | k4;        // column inside the group of 8 (un-swizzled)
+        const int x = xv * 8 + k;
+        const int tx = x / p, px = x - tx * p;
+        uint32_t vp = 0u, vn = 0u;
+        if (tx < q.W && !(ty == 0 && tx == 0 && py == 0 && px == 0)) {
+            const int64_t e = (((int64_t)c * q.H + ty) * q.W + tx) * z + py * p + px;
+            const float sd = __fadd_rn(__fmul_rn(__ldg(q.b + e), kSqrt2f), q.eps);
+            const float md = __ldg(q.median + e);
+            vp = pack_split16(__fadd_rn(__fmul_rn(q.scale, sd), md), scale);
+            vn = pack_split16(__fadd_rn(__fmul_rn(-q.scale, sd), md), scale);
+        }
+        pos_tab[i] = vp;
+        neg_tab[i] = vn;
+    }
+}
+
+template <bool PRE>      // PRE: the tables come from decode_tables_kernel (tab / nxv_tab), else they are built here
+__global__ void __launch_bounds__(256, 3) decode_codes_rows_kernel(const int64_t* __restrict__ codes,
+                                                                   const int32_t* __restrict__ slot_map,
+                                                                   const int32_t* __restrict__ img_sel, int64_t n_img,
+                                                                   int imgs_per_cta, int C, int th, int tw, int p, int rows,
+                                                                   int cols, int ldq, LfqNormParams q,
+                                                                   const uint32_t* __restrict__ pos_tab,
+                                                                   const uint32_t* __restrict__ neg_tab, int nxv_tab,
+                                                                   __half* __restrict__ hi, __half* __restrict__ lo,
+                                                                   float* __restrict__ dc, float dc_factor, float scale) {
+    extern __shared__ __align__(16) float smem_f[];
+    const int z = p * p;
+    const int nxv = ldq >> 2;
+    const int tile_rows = rows / p;
+    const unsigned id = blockIdx.x;
+    const int ty = (int)(id % (unsigned)tile_rows);
+    const unsigned t = id / (unsigned)tile_rows;
+    const int c = (int)(t % (unsigned)C);
+    const int64_t sel0 = (int64_t)(t / (unsigned)C) * imgs_per_cta;
+    const int n_here = (int)min((int64_t)imgs_per_cta, n_img - sel0);
+    const bool row_in = ty < th;
+    const int n_tx = row_in ? min(tw, cols / p) : 0;
+    uint4* pos_t = reinterpret_cast<uint4*>(smem_f);          // [p][nxv][2] words of 4: value when the bit is 1
+    uint4* neg_t = pos_t + p * nxv * 2;                       //                            value when the bit is 0
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, n_thr = blockDim.x * blockDim.y;
+    const float* med_row = q.median + (((int64_t)c * q.H + ty) * q.W) * q.z;
+    const float* b_row = q.b + (((int64_t)c * q.H + ty) * q.W) * q.z;
+    if (PRE) {
+        const uint4* ps = reinterpret_cast<const uint4*>(pos_tab) + ((int64_t)c * q.H + ty) * p * nxv_tab * 2;
+        const uint4* ns = reinterpret_cast<const uint4*>(neg_tab) + ((int64_t)c * q.H + ty) * p * nxv_tab * 2;
+        for (int i = tid; i < p * nxv * 2; i += n_thr) {
+            const int py = i / (nxv * 2), r = i - py * (nxv * 2);
+            pos_t[i] = __ldg(ps + py * nxv_tab * 2 + r);
+            neg_t[i] = __ldg(ns + py * nxv_tab * 2 + r);
+        }
+        __syncthreads();
+    } else {
+        uint32_t* pos_w = reinterpret_cast<uint32_t*>(pos_t);
+        uint32_t* neg_w = reinterpret_cast<uint32_t*>(neg_t);
+        for (int i = tid; i < p * nxv * 8; i += n_thr) { pos_w[i] = 0u; neg_w[i] = 0u; }
+        __syncthreads();
+        for (int e = tid; e < n_tx * z; e += n_thr) {
+            const int tx = e / z, r = e - tx * z;
+            const int py = r / p, px = r - py * p;
+            const int x = tx * p + px, xv = x >> 3, k = x & 7;
+            const int idx = ((py * nxv + xv) * 2 + ((k >> 2) ^ ((xv >> 2) & 1))) * 4 + (k & 3);
+            const float sd = __fadd_rn(__fmul_rn(__ldg(b_row + e), kSqrt2f), q.eps);
+            const float md = __ldg(med_row + e);
+            float vp = __fadd_rn(__fmul_rn(q.scale, sd), md);                               // patchnorm.py:177
+            float vn = __fadd_rn(__fmul_rn(-q.scale, sd), md);
+            if (ty == 0 && e == 0) { vp = 0.0f; vn = 0.0f; }                                // the DC goes to dc[]
+            pos_w[idx] = pack_split16(vp, scale);
+            neg_w[idx] = pack_split16(vn, scale);
+        }
+        __syncthreads();
+    }
+    const int rows2 = rows >> 1;
+    const int64_t n_planes = n_img * C;
+    const int64_t quad = n_planes * rows2 * (int64_t)ldq;
+    // a token's p code words are 16-byte aligned pairs when p is even (p int64 words per token)
+    const bool vec_codes = (p & 1) == 0 && (reinterpret_cast<uintptr_t>(codes) & 15) == 0;
+    for (int k = threadIdx.y; k < n_here; k += blockDim.y) {
+        const int64_t img = img_sel ? img_sel[sel0 + k] : sel0 + k;
+        const int64_t plane = (sel0 + k) * C + c;
+        const int32_t* smap = slot_map + ((img * C + c) * th + (row_in ? ty : 0)) * tw;
+        for (int xv = threadIdx.x; xv < nxv; xv += blockDim.x) {
+            const int x0 = xv * 8;
+            const int tx0 = x0 / p, px0 = x0 - tx0 * p;
+            const int n_first = min(8, p - px0);
+            const int32_t slot0 = tx0 < n_tx ? __ldg(smap + tx0) : -1;
+            const int32_t slot1 = (n_first < 8 && tx0 + 1 < n_tx) ? __ldg(smap + tx0 + 1) : -1;
+            const int64_t* cw0 = slot0 >= 0 ? codes + (int64_t)slot0 * q.c : nullptr;
+            const int64_t* cw1 = slot1 >= 0 ? codes + (int64_t)slot1 * q.c : nullptr;
+            const unsigned m_first = (0xffu << (8 - n_first)) & 0xffu;
+            const unsigned valid8 = (slot0 >= 0 ? m_first : 0u) | (slot1 >= 0 ? (0xffu & ~m_first) : 0u);
+            unsigned bpack[4] = {0u, 0u, 0u, 0u};                    // sign byte of row py in byte py
+            const int sh0 = q.d - px0 - n_first, sh1 = q.d - (8 - n_first);
+            // all code words of the two tokens first (independent 128-bit loads: two int64 words each), then the bits
+            const longlong2* c0 = reinterpret_cast<const longlong2*>(cw0 ? cw0 : codes);
+            const longlong2* c1 = reinterpret_cast<const longlong2*>(cw1 ? cw1 : codes);
+            longlong2 w0v[8], w1v[8];
+            if (vec_codes) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (2 * j < p) {
+                        w0v[j] = __ldg(c0 + j);
+                        w1v[j] = __ldg(c1 + j);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (2 * j < p) {
+                        w0v[j].x = __ldg((cw0 ? cw0 : codes) + 2 * j);
+                        w1v[j].x = __ldg((cw1 ? cw1 : codes) + 2 * j);
+                        w0v[j].y = 2 * j + 1 < p ? __ldg((cw0 ? cw0 : codes) + 2 * j + 1) : 0;
+                        w1v[j].y = 2 * j + 1 < p ? __ldg((cw1 ? cw1 : codes) + 2 * j + 1) : 0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int py = 0; py < 16; ++py) {
+                if (py < p) {
+                    const unsigned w0 = cw0 ? (unsigned)((py & 1) ? w0v[py >> 1].y : w0v[py >> 1].x) : 0u;
+                    const unsigned w1 = cw1 ? (unsigned)((py & 1) ? w1v[py >> 1].y : w1v[py >> 1].x) : 0u;
+                    const unsigned f0 = (w0 >> sh0) << (8 - n_first);
+                    const unsigned f1 = n_first < 8 ? (w1 >> sh1) & (0xffu >> n_first) : 0u;
+                    bpack[py >> 2] |= ((f0 | f1) & 0xffu) << (8 * (py & 3));
+                }
+            }
+            if (ty == 0 && xv == 0) {
+                // the DC coefficient (row 0, column 0 of tile row 0) is carried separately
+                float dcval = 0.0f;
+                if (slot0 >= 0) {
+                    const float sd = __fadd_rn(__fmul_rn(__ldg(b_row), kSqrt2f), q.eps);
+                    const float qv = (bpack[0] & 0x80u) ? q.scale : -q.scale;
+                    dcval = __fadd_rn(__fmul_rn(qv, sd), __ldg(med_row)) * dc_factor;
+                }
+                dc[plane] = dcval;
+            }
+            const int sw = (xv >> 2) & 1;
+#pragma unroll 2
+            for (int py = 0; py < p; ++py) {
+                const int ti = (py * nxv + xv) * 2;
+                const uint4 p0 = pos_t[ti + sw], p1 = pos_t[ti + (sw ^ 1)];
+                const uint4 n0 = neg_t[ti + sw], n1 = neg_t[ti + (sw ^ 1)];
+                const unsigned bits8 = ((bpack[(py >> 2) & 3] >> (8 * (py & 3))) & 0xffu) ;
+                const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                const uint32_t nw[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t v = (bits8 & (0x80u >> j)) ? pw[j] : nw[j];
+                    w[j] = (valid8 & (0x80u >> j)) ? v : 0u;
+                }
+                // hi halves are the low 16 bits, lo halves the high 16 bits of each word; even columns -> parity b = 0
+                const uint2 eh = make_uint2(__byte_perm(w[0], w[2], 0x5410), __byte_perm(w[4], w[6], 0x5410));
+                const uint2 el = make_uint2(__byte_perm(w[0], w[2], 0x7632), __byte_perm(w[4], w[6], 0x7632));
+                const uint2 oh = make_uint2(__byte_perm(w[1], w[3], 0x5410), __byte_perm(w[5], w[7], 0x5410));
+                const uint2 ol = make_uint2(__byte_perm(w[1], w[3], 0x7632), __byte_perm(w[5], w[7], 0x7632));
+                const int kh = ty * p + py;
+                const int a = kh & 1, ii = kh >> 1;
+                const int64_t o = ((a * n_planes + plane) * rows2 + ii) * (int64_t)ldq + xv * 4;   // + b * 2 * quad
+                *reinterpret_cast<uint2*>(hi + o) = eh;
+                *reinterpret_cast<uint2*>(lo + o) = el;
+                *reinterpret_cast<uint2*>(hi + 2 * quad + o) = oh;
+                *reinterpret_cast<uint2*>(lo + 2 * quad + o) = ol;
+            }
+        }
+    }
+}
+
 // fp32 coefficient planes (n_planes, kh, kw) -> folded split quadrants (DC moved to dc[])
 __global__ void __launch_bounds__(256) fold_coef_kernel(const float* __restrict__ y, __half* __restrict__ hi,
                                                         __half* __restrict__ lo, float* __restrict__ dc,
@@ -1827,7 +2027,7 @@ extern "C" int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, f
 static int launch_unpatchify_fold(bool with_codes, const float* patches, const int64_t* codes, const int32_t* slot_map,
                                   const int32_t* img_sel, int64_t n_img, int C, int th, int tw, int p, int rows, int cols,
                                   int out_h, int out_w, const LfqNormParams& q, void* yq_hi, void* yq_lo, float* dc,
-                                  void* stream, const char* who) {
+                                  void* stream, const char* who, uint32_t* tab_scratch = nullptr) {
     DCTA_REQUIRE(slot_map && yq_hi && yq_lo && dc, "%s: null pointer", who);
     DCTA_REQUIRE(rows > 0 && cols > 0 && p > 0 && out_h > 0 && out_w > 0 && rows % 2 == 0 && cols % 2 == 0 && rows % p == 0,
                  "%s: needs even plane sizes and rows %% patch == 0", who);
@@ -1850,11 +2050,23 @@ static int launch_unpatchify_fold(bool with_codes, const float* patches, const i
     const dim3 block((unsigned)bx, (unsigned)by);
     cudaError_t e = cudaSuccess;
     if (with_codes && fast) {
-        e = cudaFuncSetAttribute(unpatchify_fold_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        if (e == cudaSuccess)
-            unpatchify_fold_kernel<true, true><<<(unsigned)n_ctas, block, smem_bytes, as_stream(stream)>>>(
-                patches, codes, slot_map, img_sel, n_img, imgs_per_cta, C, th, tw, p, rows, cols, ldq, q, (__half*)yq_hi,
-                (__half*)yq_lo, dc, dcf, kFScaleY);
+        const int nxv_tab = (int)ceil_div((int64_t)q.W * p, 8);
+        if (tab_scratch != nullptr && nxv <= nxv_tab) {
+            const int64_t n_tab = (int64_t)q.C * q.H * p * nxv_tab * 8;
+            decode_tables_kernel<<<grid_for(n_tab, 256), 256, 0, as_stream(stream)>>>(q, p, nxv_tab, kFScaleY, tab_scratch,
+                                                                                      tab_scratch + n_tab);
+            e = cudaFuncSetAttribute(decode_codes_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+            if (e == cudaSuccess)
+                decode_codes_rows_kernel<true><<<(unsigned)n_ctas, block, smem_bytes, as_stream(stream)>>>(
+                    codes, slot_map, img_sel, n_img, imgs_per_cta, C, th, tw, p, rows, cols, ldq, q, tab_scratch,
+                    tab_scratch + n_tab, nxv_tab, (__half*)yq_hi, (__half*)yq_lo, dc, dcf, kFScaleY);
+        } else {
+            e = cudaFuncSetAttribute(decode_codes_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+            if (e == cudaSuccess)
+                decode_codes_rows_kernel<false><<<(unsigned)n_ctas, block, smem_bytes, as_stream(stream)>>>(
+                    codes, slot_map, img_sel, n_img, imgs_per_cta, C, th, tw, p, rows, cols, ldq, q, nullptr, nullptr, 0,
+                    (__half*)yq_hi, (__half*)yq_lo, dc, dcf, kFScaleY);
+        }
     } else if (with_codes) {
         e = cudaFuncSetAttribute(unpatchify_fold_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e == cudaSuccess)
@@ -1882,11 +2094,12 @@ extern "C" int dcta_unpatchify_fold(const float* patches, const int32_t* slot_ma
 extern "C" int dcta_decode_codes_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel,
                                       int64_t n_img, int channels_n, int th, int tw, int p, int rows, int cols, int out_h,
                                       int out_w, const float* median, const float* b, int H, int W, float eps, int c,
-                                      int d, float scale, void* yq_hi, void* yq_lo, float* dc, void* stream) {
+                                      int d, float scale, void* yq_hi, void* yq_lo, float* dc, void* tab_scratch,
+                                      void* stream) {
     DCTA_REQUIRE(codes && median && b, "decode_codes_fold: null pointer");
     DCTA_REQUIRE(th <= H && tw <= W && c > 0 && d > 0 && d <= 62 && c * d == p * p && rows / p <= H,
                  "decode_codes_fold: needs a projection-free LFQ (c*d == p*p) and a token grid inside the PatchNorm tables");
     LfqNormParams q{median, b, channels_n, H, W, p * p, eps, 0.f, 0.f, c, d, scale};
     return launch_unpatchify_fold(true, nullptr, codes, slot_map, img_sel, n_img, channels_n, th, tw, p, rows, cols,
-                                  out_h, out_w, q, yq_hi, yq_lo, dc, stream, "decode_codes_fold");
+                                  out_h, out_w, q, yq_hi, yq_lo, dc, stream, "decode_codes_fold", (uint32_t*)tab_scratch);
 }

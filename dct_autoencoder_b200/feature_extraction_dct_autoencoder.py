@@ -582,11 +582,13 @@ class DCTAutoencoderFeatureExtractor:
                     y_lo = torch.empty_like(y_hi)
                     dc = torch.empty(n * C, dtype=torch.float32, device=dev)
                     if codes is not None:
+                        n_tab = C * norm.max_patch_h * p * ((norm.max_patch_w * p + 7) // 8) * 8
+                        tab = torch.empty(2 * n_tab, dtype=torch.int32, device=dev)
                         _lib.call("dcta_decode_codes_fold", _lib.ptr(codes), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
                                   th, tw, p, kh, kw, h, w, _lib.ptr(norm.median.data), _lib.ptr(norm.b.data),
                                   norm.max_patch_h, norm.max_patch_w, float(norm.eps), lfq.num_codebooks,
                                   lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(y_hi), _lib.ptr(y_lo),
-                                  _lib.ptr(dc), st)
+                                  _lib.ptr(dc), _lib.ptr(tab), st)
                     else:
                         _lib.call("dcta_unpatchify_fold", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
                                   th, tw, p, kh, kw, h, w, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc), st)

@@ -167,11 +167,13 @@ int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, const float* 
 int dcta_unpatchify_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
                          int channels_n, int th, int tw, int p, int rows, int cols, int out_h, int out_w,
                          void* yq_hi, void* yq_lo, float* dc, void* stream);
-/* The same from LFQ codes (contract of dcta_decode_codes_split). */
+/* The same from LFQ codes (contract of dcta_decode_codes_split).
+ *   tab_scratch [nullable]: 2 * channels*H*p*ceil(W*p/8)*8 device uint32.  When given (and c == d == p <= 16) the two
+ *   values a de-quantised coefficient can take at every position are tabulated once per call instead of once per CTA. */
 int dcta_decode_codes_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel,
                            int64_t n_img, int channels_n, int th, int tw, int p, int rows, int cols, int out_h,
                            int out_w, const float* median, const float* b, int H, int W, float eps, int c,
-                           int d, float scale, void* yq_hi, void* yq_lo, float* dc, void* stream);
+                           int d, float scale, void* yq_hi, void* yq_lo, float* dc, void* tab_scratch, void* stream);
 /* fp32 coefficient planes y (n_planes, kh, kw) -> folded quadrants. */
 int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, float* dc, int64_t n_planes, int kh,
                           int kw, int out_h, int out_w, void* stream);
