@@ -88,6 +88,8 @@ SIGNATURES = {
     "dcta_vq_nearest_tc": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int64, P],
     "dcta_build_slot_map": [P, P, P, P, P, c_int, c_int, c_int64, c_int, c_int, c_int, P, P],
     "dcta_unpatchify": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P],
+    "dcta_wire_pack": [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P],
+    "dcta_wire_unpack": [P, c_int64, c_int, c_int, c_int, P, P, P, P],
 }
 _RESTYPES = {"dcta_last_error": c_char_p}
 REDUCE_SCRATCH = 2048  # DCTA_REDUCE_SCRATCH
@@ -101,7 +103,7 @@ KERNELS_PER_CALL = {
     "dcta_patchnorm_update_median": 1, "dcta_patchnorm_abs_dev": 1, "dcta_patchnorm_update_b": 2,
     "dcta_zero_padding": 1, "dcta_lfq_quantize": 1, "dcta_lfq_indices_to_codes": 1, "dcta_lfq_commit_loss": 2,
     "dcta_lfq_distance": 1, "dcta_entropy_loss": 2, "dcta_perplexity": 2, "dcta_vq_nearest": 2,
-    "dcta_build_slot_map": 1, "dcta_unpatchify": 1,
+    "dcta_build_slot_map": 1, "dcta_unpatchify": 1, "dcta_wire_pack": 1, "dcta_wire_unpack": 1,
     "dcta_gemm_split": 1, "dcta_split_f32": 1, "dcta_rgb_to_ipt_split": 2, "dcta_unpatchify_split": 1,
     "dcta_split_planes_centered": 2, "dcta_split_coef_planes": 1,
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,

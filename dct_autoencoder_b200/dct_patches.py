@@ -140,3 +140,94 @@ def from_dict(obj: dict, device=None):
     )
     codes = torch.tensor([e["data"] for e in entries], dtype=torch.long, device=device)
     return dp, codes
+
+
+# ----------------------------------------------------------------------------------------------
+# compact wire format (csrc/wire.cu): the binary counterpart of to_dict / from_dict
+# ----------------------------------------------------------------------------------------------
+_WIRE_MAGIC = b"DCTW"
+_WIRE_HEADER = "<4sBBBBHHIII"      # magic, version, c, d, reserved, ph, pw, H, W, n_tokens
+WIRE_HEADER_BYTES = 24
+
+
+def wire_record_bytes(num_codebooks: int, bits: int) -> int:
+    return 2 + (num_codebooks * bits + 7) // 8
+
+
+def to_bytes(dct_patches: DCTPatches, codes: torch.Tensor, codebook_size: int) -> List[bytes]:
+    """One byte string per image: a 24-byte header (magic ``DCTW``, version, codebooks, bits per code,
+    patch grid (ph, pw), original size (H, W), token count) followed by one fixed-size record per
+    token, ``u16 c<<12|h<<6|w`` + the code words bit-packed MSB first (include/dcta.h
+    ``dcta_wire_pack``).  Carries exactly what ``to_dict`` (dct_patches.py:54-87) carries, in
+    27 instead of ~400 bytes per token for the 14x14-bit quantiser, and is produced by one kernel and
+    one device->host copy instead of one ``.item()`` per field."""
+    import struct
+
+    from . import _lib
+    _lib.require_cuda(codes)
+    b, s, c = codes.shape
+    assert (b, s) == tuple(dct_patches.key_pad_mask.shape)
+    d = max(1, (int(codebook_size) - 1).bit_length())
+    assert 2 ** d == codebook_size, "codebook_size must be a power of two"
+    if int(dct_patches.patch_channels.max()) >= 16 or int(dct_patches.patch_positions.max()) >= 64:
+        raise ValueError("wire format holds channel < 16 and h, w < 64")
+    rec = wire_record_bytes(c, d)
+    dev = codes.device
+    codes = codes.to(torch.int64).contiguous()
+    pos = dct_patches.patch_positions.to(dev, torch.int64).contiguous()
+    ch = dct_patches.patch_channels.to(dev, torch.int64).contiguous()
+    ids = dct_patches.batched_image_ids.to(dev, torch.int64).contiguous()
+    pad = dct_patches.key_pad_mask.to(dev).contiguous()
+    out = torch.empty((b, s, rec), dtype=torch.uint8, device=dev)
+    counts = torch.empty((b, s), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_wire_pack", _lib.ptr(codes), _lib.ptr(pos), _lib.ptr(ch), _lib.ptr(ids),
+                  pad.data_ptr(), b, s, c, d, rec, _lib.ptr(out), _lib.ptr(counts), _lib.stream_ptr(dev))
+    n_img = dct_patches.row_num_images()
+    h_out = out.cpu().numpy()
+    h_counts = counts[:, :max(n_img)].cpu().numpy()
+    blobs = []
+    for r in range(b):
+        off = 0
+        for i in range(n_img[r]):
+            k = int(h_counts[r, i])
+            ph, pw = dct_patches.patch_sizes[len(blobs)]
+            oh, ow = dct_patches.original_sizes[len(blobs)]
+            head = struct.pack(_WIRE_HEADER, _WIRE_MAGIC, 1, c, d, 0, ph, pw, oh, ow, k)
+            blobs.append(head + h_out[r, off:off + k].tobytes())
+            off += k
+    return blobs
+
+
+def from_bytes(blob: bytes, device=None):
+    """Inverse of ``to_bytes`` for one image -> (DCTPatches, codes (n, c) int64), the pair
+    ``from_dict`` (dct_patches.py:90-122) returns."""
+    import struct
+
+    import numpy as np
+
+    from . import _lib
+    from .util import default_device
+    magic, version, c, d, _, ph, pw, oh, ow, n = struct.unpack_from(_WIRE_HEADER, blob, 0)
+    if magic != _WIRE_MAGIC or version != 1:
+        raise ValueError("not a DCTW version-1 record")
+    rec = wire_record_bytes(c, d)
+    if len(blob) != WIRE_HEADER_BYTES + n * rec:
+        raise ValueError(f"truncated record: {len(blob)} bytes for {n} tokens of {rec} bytes")
+    dev = torch.device(device) if device is not None else default_device()
+    body = torch.from_numpy(np.frombuffer(blob, dtype=np.uint8, offset=WIRE_HEADER_BYTES).copy()).to(dev)
+    codes = torch.empty((n, c), dtype=torch.int64, device=dev)
+    pos = torch.empty((1, n, 2), dtype=torch.int64, device=dev)
+    ch = torch.empty((1, n), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_wire_unpack", _lib.ptr(body), n, c, d, rec, _lib.ptr(codes), _lib.ptr(pos), _lib.ptr(ch),
+                  _lib.stream_ptr(dev))
+    dp = DCTPatches(
+        patches=torch.zeros(1, device=dev),
+        key_pad_mask=torch.zeros(1, n, dtype=torch.bool, device=dev),
+        attn_mask=torch.ones(1, n, n, dtype=torch.bool, device=dev),
+        batched_image_ids=torch.zeros(1, n, dtype=torch.long, device=dev),
+        patch_channels=ch, patch_positions=pos,
+        patch_sizes=[(ph, pw)], original_sizes=[(oh, ow)], _row_num_images=[1],
+    )
+    return dp, codes

@@ -276,6 +276,42 @@ class DCTAutoencoderFeatureExtractor:
                     original_sizes=(h, w), patch_sizes=(ph, pw))
 
     @torch.no_grad()
+    def _preprocess_batch_raw(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None):
+        """Tokens of b same-size images, one image per row of (b, max k, .) buffers.
+        -> (patches fp32, positions, channels, ks, (h, w), (ph, pw))."""
+        x = to_device_f32(images, self._dev(images))
+        b, c, h, w = x.shape
+        ph, pw, th, tw = self._geometry(h, w)
+        tiles, maxabs = self._token_grid(x, want_maxabs=True)
+        order = self._sorted_order(tiles, maxabs)
+        n_tok = th * tw * c
+        if ks is None:
+            ks = [self._choose_k(n_tok) for _ in range(b)]
+        ks = [int(k) for k in ks]
+        assert len(ks) == b and all(1 <= k <= min(n_tok, self.max_seq_len) for k in ks)
+        kmax, z = max(ks), self.patch_size ** 2
+        patches = torch.empty((b, kmax, z), dtype=torch.float32, device=x.device)
+        pos = torch.empty((b, kmax, 2), dtype=torch.int64, device=x.device)
+        chan = torch.empty((b, kmax), dtype=torch.int64, device=x.device)
+        tab, offs = self._tables([[i] for i in range(b)], dict(enumerate(ks)), x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("dcta_pack_tiles", _lib.ptr(tiles), _lib.ptr(order), tab.data_ptr() + offs[0],
+                      tab.data_ptr() + offs[1], b, kmax, th, tw, c, z, _lib.ptr(patches), _lib.ptr(pos),
+                      _lib.ptr(chan), None, None, _lib.stream_ptr(x.device))
+        return patches, pos, chan, ks, (h, w), (ph, pw)
+
+    @torch.no_grad()
+    def preprocess_batch(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None) -> List[dict]:
+        """``[preprocess(im) for im in images]`` for (b, c, h, w) same-size images in one set of
+        launches (the batched multi-image preprocess the offline shard writer needs,
+        preproc_dataset.py:62-84).  The per-image tensors are views of one (b, max k, .) buffer."""
+        patches, pos, chan, ks, osz, psz = self._preprocess_batch_raw(images, ks)
+        if images.dtype != torch.float32:
+            patches = patches.to(images.dtype)
+        return [dict(patches=patches[i, :k], positions=pos[i, :k], channels=chan[i, :k],
+                     original_sizes=osz, patch_sizes=psz) for i, k in enumerate(ks)]
+
+    @torch.no_grad()
     def process_batch(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None) -> DCTPatches:
         """Whole-batch encode of (b, c, h, w) same-size images: equals
         ``next(iter_batches(iter([dict_collate([preprocess(im) for im in images])]), None))``."""

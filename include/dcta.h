@@ -297,6 +297,22 @@ int dcta_entropy_loss(const float* affinity, const uint8_t* mask, float* scratch
 int dcta_perplexity(const int64_t* codes, int64_t n, int codebook_size, int64_t null_index,
                     int64_t* counts, float* result, void* stream);
 
+/* ------------------------------------------------------------------ code wire format ------ */
+/* Compact replacement of DP:54-87 to_dict's per-token {c, h, w, data} dicts (consumer:
+ * prepare_autoregressive_dataset.py:51-66).  One record of rec = 2 + ceil(c*d/8) bytes per slot of the
+ * (n_rows, s) batch: little-endian u16 channel<<12 | h<<6 | w, then the token's c code words of d bits each,
+ * most significant bit first, concatenated (last byte zero-padded).  Needs channel < 16 and h, w < 64.
+ * counts [nullable]: (n_rows, s) int32, zeroed by the call; counts[r, i] = number of non-padding tokens of
+ * the i-th image of row r (tokens of one image are adjacent, FE:516-605), which is all the host needs to
+ * cut out[r] into per-image byte strings. */
+int dcta_wire_pack(const int64_t* codes, const int64_t* positions, const int64_t* channels,
+                   const int64_t* image_ids, const uint8_t* key_pad_mask, int64_t n_rows, int s, int c, int d,
+                   int rec, uint8_t* out, int32_t* counts, void* stream);
+/* Inverse (DP:90-122 from_dict): n_tok records -> codes (n_tok, c) i64, positions (n_tok, 2) i64 [h, w],
+ * channels (n_tok) i64.  `in` must be 4-byte aligned. */
+int dcta_wire_unpack(const uint8_t* in, int64_t n_tok, int c, int d, int rec, int64_t* codes,
+                     int64_t* positions, int64_t* channels, void* stream);
+
 /* ------------------------------------------------------------------ fused PatchNorm + LFQ -- */
 /* Encode to codes without materialising the gathered / normalised / quantised patches:
  * dcta_pack_tiles' gather (FE:437-452, FE:516-605) + PN:157-165 + lfq.py:168-187 in registers.
