@@ -34,8 +34,8 @@ __device__ __forceinline__ float patchnorm_value(float xv, float mv, float bv, f
 }
 
 // kVec == 4 (z % 4 == 0, z <= 256): a warp takes 32 consecutive tokens, the position lookups (three dependent
-// 8-byte loads per token) run once, lane-parallel, and the tokens are then streamed two at a time with 128-bit
-// accesses, i.e. up to 12 independent loads in flight per lane.  kVec == 1: one warp per token, scalar.
+// 8-byte loads per token) run once, lane-parallel, and the tokens' words are then streamed with 128-bit
+// accesses, 12 independent loads in flight per lane.  kVec == 1: one warp per token, scalar.
 template <bool kInverse, int kVec>
 __global__ void __launch_bounds__(256) patchnorm_apply_kernel(
     const float* __restrict__ x, const int64_t* __restrict__ channels,
@@ -46,47 +46,41 @@ __global__ void __launch_bounds__(256) patchnorm_apply_kernel(
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     if (kVec == 4 && z <= 256) {
+        // the 32 * z/4 float4s of the warp's tokens are contiguous in x and out: lanes run over consecutive
+        // words (all 32 lanes busy whatever z is), the statistics row of a word's token comes from a shuffle
+        constexpr int kUnroll = 4;
         const int z4 = z >> 2;
+        const float inv_z4 = 1.0f / (float)z4;
+        const float4* m4 = reinterpret_cast<const float4*>(median);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
         for (int64_t tok0 = warp0 * 32; tok0 < n_tok; tok0 += n_warps * 32) {
-            const int pid_mine = tok0 + lane < n_tok ? clamped_position(channels, positions, tok0 + lane, C, H, W) : 0;
-            const int n_here = (int)min((int64_t)32, n_tok - tok0);
-            for (int t = 0; t < n_here; t += 2) {
-                float4 xv[2][2], mv[2][2], bv[2][2];
-                const bool second = t + 1 < n_here;
+            const int row_mine = (tok0 + lane < n_tok ? clamped_position(channels, positions, tok0 + lane, C, H, W) : 0) * z4;
+            const int n4 = (int)min((int64_t)32, n_tok - tok0) * z4;
+            const float4* xs = reinterpret_cast<const float4*>(x + tok0 * z);
+            float4* os = reinterpret_cast<float4*>(out + tok0 * z);
+            for (int it = 0; it < z4; it += kUnroll) {
+                float4 xv[kUnroll], mv[kUnroll], bv[kUnroll];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int pid = __shfl_sync(0xffffffffu, pid_mine, t + u);
-                    if (u == 0 || second) {
-                        const float4* xs = reinterpret_cast<const float4*>(x + (tok0 + t + u) * z);
-                        const float4* ms = reinterpret_cast<const float4*>(median + (int64_t)pid * z);
-                        const float4* bs = reinterpret_cast<const float4*>(b + (int64_t)pid * z);
-#pragma unroll
-                        for (int pass = 0; pass < 2; ++pass) {
-                            const int i = lane + 32 * pass;
-                            if (i < z4) {
-                                xv[u][pass] = ld_stream(xs + i);
-                                mv[u][pass] = __ldg(ms + i);
-                                bv[u][pass] = __ldg(bs + i);
-                            }
-                        }
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int idx = (it + u) * 32 + lane;
+                    const int sl = min((int)(((float)idx + 0.5f) * inv_z4), 31), wd = idx - sl * z4;   // exact: idx < 2^11
+                    const int row = __shfl_sync(0xffffffffu, row_mine, sl);
+                    if (it + u < z4 && idx < n4) {
+                        xv[u] = ld_stream(xs + idx);
+                        mv[u] = __ldg(m4 + row + wd);
+                        bv[u] = __ldg(b4 + row + wd);
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (u == 0 || second) {
-                        float4* os = reinterpret_cast<float4*>(out + (tok0 + t + u) * z);
-#pragma unroll
-                        for (int pass = 0; pass < 2; ++pass) {
-                            const int i = lane + 32 * pass;
-                            if (i < z4) {
-                                float4 o;
-                                o.x = patchnorm_value<kInverse>(xv[u][pass].x, mv[u][pass].x, bv[u][pass].x, eps, lo, hi);
-                                o.y = patchnorm_value<kInverse>(xv[u][pass].y, mv[u][pass].y, bv[u][pass].y, eps, lo, hi);
-                                o.z = patchnorm_value<kInverse>(xv[u][pass].z, mv[u][pass].z, bv[u][pass].z, eps, lo, hi);
-                                o.w = patchnorm_value<kInverse>(xv[u][pass].w, mv[u][pass].w, bv[u][pass].w, eps, lo, hi);
-                                st_stream(os + i, o);
-                            }
-                        }
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int idx = (it + u) * 32 + lane;
+                    if (it + u < z4 && idx < n4) {
+                        float4 o;
+                        o.x = patchnorm_value<kInverse>(xv[u].x, mv[u].x, bv[u].x, eps, lo, hi);
+                        o.y = patchnorm_value<kInverse>(xv[u].y, mv[u].y, bv[u].y, eps, lo, hi);
+                        o.z = patchnorm_value<kInverse>(xv[u].z, mv[u].z, bv[u].z, eps, lo, hi);
+                        o.w = patchnorm_value<kInverse>(xv[u].w, mv[u].w, bv[u].w, eps, lo, hi);
+                        st_stream(os + idx, o);
                     }
                 }
             }

@@ -275,6 +275,93 @@ __global__ void __launch_bounds__(256) pack_kernel(
     }
 }
 
+// 128-bit variant (z % 4 == 0, z <= 1024, aligned bases): a warp takes 32 consecutive output slots.  The
+// metadata chain (segment search -> sort order -> source address) runs once, lane-parallel; the 32 * z/4
+// output float4s, which are contiguous, are then copied with the lanes on consecutive OUTPUT words: every
+// store instruction writes 512 contiguous bytes, every load reads at most two tokens' contiguous bytes, and
+// kUnroll independent loads are in flight per lane.
+template <bool kTiles>
+__global__ void __launch_bounds__(256) pack_rows_kernel(
+    const float* __restrict__ tiles, const int32_t* __restrict__ order,
+    const float* const* __restrict__ src_patches, const int64_t* const* __restrict__ src_positions,
+    const int64_t* const* __restrict__ src_channels, const dcta_segment* __restrict__ segs,
+    const int32_t* __restrict__ row_seg_start, int n_rows, int s, int tw, int channels,
+    int n_tok_img, int z, float* __restrict__ patches, int64_t* __restrict__ positions,
+    int64_t* __restrict__ channels_out, int64_t* __restrict__ image_ids,
+    uint8_t* __restrict__ key_pad_mask) {
+    constexpr int kUnroll = 7;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t total = (int64_t)n_rows * s;
+    const int z4 = z >> 2;
+    const float inv_z4 = 1.0f / (float)z4;
+    for (int64_t slot0 = warp0 * 32; slot0 < total; slot0 += n_warps * 32) {
+        const int64_t slot = slot0 + lane;
+        const float4* src = nullptr;             // nullptr = padding slot (UT:155-157 zeros; FE:574-576 mask = True)
+        if (slot < total) {
+            const int row = (int)(slot / s);
+            const int off = (int)(slot - (int64_t)row * s);
+            int lo = row_seg_start[row], hi = row_seg_start[row + 1];
+            int seg = -1;
+            if (hi - lo == 1) {
+                seg = (off >= segs[lo].offset && off < segs[lo].offset + segs[lo].k) ? lo : -1;
+            } else {
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int so = segs[mid].offset;
+                    if (off < so) hi = mid;
+                    else if (off >= so + segs[mid].k) lo = mid + 1;
+                    else { seg = mid; break; }
+                }
+            }
+            int64_t ph = 0, pw = 0, pc = 0, image_id = 0;
+            if (seg >= 0) {
+                const dcta_segment sg = segs[seg];
+                const int j = off - sg.offset;
+                image_id = sg.image_id;
+                if (kTiles) {
+                    const int tok = order[sg.img * n_tok_img + j];
+                    src = reinterpret_cast<const float4*>(tiles + (sg.img * n_tok_img + tok) * z);
+                    const int tile = tok / channels;
+                    pc = tok - tile * channels;
+                    ph = tile / tw;
+                    pw = tile - (int)ph * tw;
+                } else {
+                    src = reinterpret_cast<const float4*>(src_patches[sg.img] + (int64_t)j * z);
+                    const longlong2 hw = *reinterpret_cast<const longlong2*>(src_positions[sg.img] + 2 * j);
+                    ph = hw.x;
+                    pw = hw.y;
+                    pc = src_channels[sg.img][j];
+                }
+            }
+            reinterpret_cast<longlong2*>(positions)[slot] = make_longlong2(ph, pw);
+            channels_out[slot] = pc;
+            if (image_ids) image_ids[slot] = image_id;
+            if (key_pad_mask) key_pad_mask[slot] = seg < 0;
+        }
+        const int n4 = (int)min((int64_t)32, total - slot0) * z4;
+        float4* dst = reinterpret_cast<float4*>(patches + slot0 * z);
+        const unsigned long long src_bits = (unsigned long long)src;
+        for (int it = 0; it < z4; it += kUnroll) {
+            float4 v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int idx = (it + u) * 32 + lane;
+                const int sl = min((int)(((float)idx + 0.5f) * inv_z4), 31), wd = idx - sl * z4;   // exact: idx < 2^13
+                const float4* sp = (const float4*)__shfl_sync(0xffffffffu, src_bits, sl);
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (it + u < z4 && idx < n4 && sp != nullptr) v[u] = ld_stream(sp + wd);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int idx = (it + u) * 32 + lane;
+                if (it + u < z4 && idx < n4) st_stream(dst + idx, v[u]);
+            }
+        }
+    }
+}
+
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace dcta
@@ -361,7 +448,9 @@ extern "C" int dcta_pack_tiles(const float* tiles, const int32_t* order, const d
     if (n_rows == 0) return DCTA_OK;
     const int grid = grid_for((int64_t)n_rows * s, 8);
     const int n_tok_img = th * tw * channels;
-    if (z % 4 == 0 && al16(tiles) && al16(patches))
+    if (z % 4 == 0 && z <= 1024 && al16(tiles) && al16(patches))
+        pack_rows_kernel<true><<<grid_for((int64_t)n_rows * s, 256), 256, 0, as_stream(stream)>>>(tiles, order, nullptr, nullptr, nullptr, segs, row_seg_start, n_rows, s, tw, channels, n_tok_img, z, patches, positions, channels_out, image_ids, key_pad_mask);
+    else if (z % 4 == 0 && al16(tiles) && al16(patches))
         pack_kernel<true, 4><<<grid, 256, 0, as_stream(stream)>>>(tiles, order, nullptr, nullptr, nullptr, segs, row_seg_start, n_rows, s, tw, channels, n_tok_img, z, patches, positions, channels_out, image_ids, key_pad_mask);
     else
         pack_kernel<true, 1><<<grid, 256, 0, as_stream(stream)>>>(tiles, order, nullptr, nullptr, nullptr, segs, row_seg_start, n_rows, s, tw, channels, n_tok_img, z, patches, positions, channels_out, image_ids, key_pad_mask);
@@ -381,7 +470,9 @@ extern "C" int dcta_pack_lists(const float* const* src_patches, const int64_t* c
     // per-image sources are torch allocations (>= 16-byte aligned at offset 0) but may be views:
     // the 128-bit path needs z*4 % 16 == 0 AND every base aligned; the host shim guarantees the
     // latter by passing contiguous tensors, else it asks for the scalar path via z's alignment.
-    if (z % 4 == 0 && al16(patches))
+    if (z % 4 == 0 && z <= 1024 && al16(patches))
+        pack_rows_kernel<false><<<grid_for((int64_t)n_rows * s, 256), 256, 0, as_stream(stream)>>>(nullptr, nullptr, src_patches, src_positions, src_channels, segs, row_seg_start, n_rows, s, 0, 0, 0, z, patches, positions, channels_out, image_ids, key_pad_mask);
+    else if (z % 4 == 0 && al16(patches))
         pack_kernel<false, 4><<<grid, 256, 0, as_stream(stream)>>>(nullptr, nullptr, src_patches, src_positions, src_channels, segs, row_seg_start, n_rows, s, 0, 0, 0, z, patches, positions, channels_out, image_ids, key_pad_mask);
     else
         pack_kernel<false, 1><<<grid, 256, 0, as_stream(stream)>>>(nullptr, nullptr, src_patches, src_positions, src_channels, segs, row_seg_start, n_rows, s, 0, 0, 0, z, patches, positions, channels_out, image_ids, key_pad_mask);

@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--dct-impl", default="tc")
+    ap.add_argument("--staged", action="store_true", help="the drop-in modules one by one instead of the fused step")
     a = ap.parse_args()
     import torch
     import dct_autoencoder_b200 as D
@@ -28,14 +29,15 @@ def main():
     g.manual_seed(1)
     pipe.fit_norm(torch.rand(min(a.batch, 16), 3, a.size, a.size, device=dev, generator=g))
     x = torch.rand(a.batch, 3, a.size, a.size, device=dev, generator=g)
+    step = (lambda: pipe.roundtrip_staged(x)) if a.staged else (lambda: pipe.roundtrip(x))
     for _ in range(a.warmup):
-        pipe.roundtrip(x)
+        step()
     torch.cuda.synchronize()
     l0 = D._lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        pipe.roundtrip(x)
+        step()
     e1.record()
     torch.cuda.synchronize()
     print(f"batch {a.batch} size {a.size}: {e0.elapsed_time(e1) / a.steps:.3f} ms/step, "
