@@ -1484,6 +1484,7 @@ __global__ void __launch_bounds__(256, 4) unpatchify_fold_kernel(const float* __
     const int rows2 = rows >> 1;
     const int64_t n_planes = n_img * C;
     const int64_t quad = n_planes * rows2 * (int64_t)ldq;          // elements of one quadrant array
+    const bool pairs = !CODES && (p & 1) == 0 && (reinterpret_cast<uintptr_t>(patches) & 7) == 0;
     for (int k = threadIdx.y; k < n_here; k += blockDim.y) {
         const int64_t img = img_sel ? img_sel[sel0 + k] : sel0 + k;
         const int64_t plane = (sel0 + k) * C + c;
@@ -1545,6 +1546,15 @@ __global__ void __launch_bounds__(256, 4) unpatchify_fold_kernel(const float* __
                         const float qv = (bits8 & (0x80u >> j)) ? q.scale : -q.scale;             // lfq.py:118-120
                         const float val = __fadd_rn(__fmul_rn(qv, sv[j]), mv[j]);                 // patchnorm.py:177
                         v[j] = (valid8 & (0x80u >> j)) ? val : 0.0f;
+                    }
+                } else if (pairs) {
+                    // even tile width: px0 and n_first are even, so column pairs are 8-byte aligned in the token
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const float* src = j < n_first ? src0 : src1;
+                        const float2 t = src ? __ldg(reinterpret_cast<const float2*>(src + py * p + j)) : make_float2(0.0f, 0.0f);
+                        v[j] = t.x;
+                        v[j + 1] = t.y;
                     }
                 } else {
 #pragma unroll

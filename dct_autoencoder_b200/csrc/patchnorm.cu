@@ -35,9 +35,9 @@ __device__ __forceinline__ float patchnorm_value(float xv, float mv, float bv, f
 
 // kVec == 4 (z % 4 == 0, z <= 256): a warp takes 32 consecutive tokens, the position lookups (three dependent
 // 8-byte loads per token) run once, lane-parallel, and the tokens' words are then streamed with 128-bit
-// accesses, 12 independent loads in flight per lane.  kVec == 1: one warp per token, scalar.
+// accesses, 9 independent loads in flight per lane at 32 resident warps per SM.  kVec == 1: one warp per token, scalar.
 template <bool kInverse, int kVec>
-__global__ void __launch_bounds__(256) patchnorm_apply_kernel(
+__global__ void __launch_bounds__(256, 4) patchnorm_apply_kernel(
     const float* __restrict__ x, const int64_t* __restrict__ channels,
     const int64_t* __restrict__ positions, const float* __restrict__ median,
     const float* __restrict__ b, float* __restrict__ out, int64_t n_tok, int z, int C, int H, int W,
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) patchnorm_apply_kernel(
     if (kVec == 4 && z <= 256) {
         // the 32 * z/4 float4s of the warp's tokens are contiguous in x and out: lanes run over consecutive
         // words (all 32 lanes busy whatever z is), the statistics row of a word's token comes from a shuffle
-        constexpr int kUnroll = 4;
+        constexpr int kUnroll = 3;
         const int z4 = z >> 2;
         const float inv_z4 = 1.0f / (float)z4;
         const float4* m4 = reinterpret_cast<const float4*>(median);
