@@ -10,10 +10,10 @@ from .dct_patches import DCTPatches, from_bytes, from_dict, to_bytes, to_dict
 from .feature_extraction_dct_autoencoder import DCTAutoencoderFeatureExtractor
 from .lfq import LFQ
 from .patchnorm import PatchNorm
-from .pipeline import TransformPipeline, dict_collate, get_max_seq_length
+from .pipeline import GraphedRoundtrip, TransformPipeline, dict_collate, get_max_seq_length
 from .vector_quantize import VectorQuantize
 
 __all__ = [
     "DCTAutoencoderFeatureExtractor", "DCTPatches", "PatchNorm", "LFQ", "VectorQuantize",
-    "TransformPipeline", "dict_collate", "get_max_seq_length", "to_dict", "from_dict", "to_bytes", "from_bytes", "util", "shards",
+    "TransformPipeline", "GraphedRoundtrip", "dict_collate", "get_max_seq_length", "to_dict", "from_dict", "to_bytes", "from_bytes", "util", "shards",
 ]

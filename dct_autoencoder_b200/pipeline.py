@@ -110,6 +110,10 @@ class TransformPipeline:
         batch, codes = self.encode_codes(images, ks)
         return self.decode_codes(batch, codes), codes
 
+    def graphed(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None, fused: Optional[bool] = None):
+        """``roundtrip`` of a fixed-shape device batch captured once in a CUDA graph; see GraphedRoundtrip."""
+        return GraphedRoundtrip(self, images, ks, fused)
+
     @torch.no_grad()
     def roundtrip_host(self, images: torch.Tensor, out_images: Optional[torch.Tensor] = None,
                        out_codes: Optional[torch.Tensor] = None, chunk: int = 32, device=None):
@@ -150,3 +154,44 @@ class TransformPipeline:
             codes.record_stream(s_out)
         main.wait_stream(s_out)
         return out_images, out_codes
+
+
+class GraphedRoundtrip:
+    """The launch sequence of ``TransformPipeline.roundtrip`` for one batch shape, captured in a CUDA graph.
+
+    The step is ~15 short kernels; launched from Python it costs about a millisecond of host time per
+    call, which a graph replay removes (one driver call per step, no allocator traffic, launch gaps of a
+    microsecond).  The graph reads ``images`` in place (the tensor given at capture time) and writes the
+    same two output tensors on every replay; call it with another tensor of the same shape to have it
+    copied in first.  PatchNorm tables and the quantiser are read through their device pointers, so
+    in-place updates of their values are seen by later replays.  Only for a fixed token count per image
+    (``sample_patches_beta == 0`` or explicit ``ks``): the packing tables are part of the capture."""
+
+    def __init__(self, pipe: "TransformPipeline", images: torch.Tensor, ks: Optional[Sequence[int]] = None,
+                 fused: Optional[bool] = None, warmup: int = 2):
+        from . import _lib
+        assert images.is_cuda, "GraphedRoundtrip captures device work; use roundtrip_host for host tensors"
+        assert ks is not None or pipe.extractor.sample_patches_beta <= 0.0, \
+            "a captured step cannot redraw k: pass ks or use sample_patches_beta = 0"
+        self.pipe, self.images = pipe, images
+        cur = torch.cuda.current_stream(images.device)
+        side = torch.cuda.Stream(images.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):              # warm caches (tables, tensor maps, function attributes)
+            for _ in range(warmup):
+                pipe.roundtrip(images, ks, fused)
+        cur.wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count
+        with torch.cuda.graph(self.graph):
+            self.rec, self.codes = pipe.roundtrip(images, ks, fused)
+        self.launches = _lib.launch_count - l0     # kernels per replay
+        self._lib = _lib
+
+    def __call__(self, images: Optional[torch.Tensor] = None):
+        if images is not None and images.data_ptr() != self.images.data_ptr():
+            assert images.shape == self.images.shape
+            self.images.copy_(images)
+        self.graph.replay()
+        self._lib.launch_count += self.launches
+        return self.rec, self.codes

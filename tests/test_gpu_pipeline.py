@@ -180,3 +180,26 @@ def test_codes_in_the_dct_epilogue_for_other_tile_sizes(D, patch, size, max_seq_
         assert torch.equal(getattr(batch_f, f), getattr(batch_s, f)), f
     assert torch.equal(codes_f, codes_s)
     assert torch.equal(pipe.decode_codes(batch_f, codes_f), rec_s)
+
+
+def test_graphed_roundtrip_replays_the_eager_step(D):
+    torch.manual_seed(4)
+    pipe = _pipe(D, "tc")
+    x = torch.rand(6, 3, 256, 256).cuda()
+    pipe.fit_norm(torch.rand(4, 3, 256, 256).cuda())
+    rec, codes = pipe.roundtrip(x)
+    g = pipe.graphed(x)
+    assert g.launches > 0
+    for _ in range(3):
+        r2, c2 = g()
+        torch.cuda.synchronize()
+        assert torch.equal(r2, rec) and torch.equal(c2, codes)
+    y = torch.rand(6, 3, 256, 256).cuda()
+    want_rec, want_codes = pipe.roundtrip(y)
+    r3, c3 = g(y)                                    # another tensor of the same shape is copied in first
+    assert torch.equal(r3, want_rec) and torch.equal(c3, want_codes)
+    # staged modules under capture as well (x now holds y's values: the graph reads its input in place)
+    assert torch.equal(x, y)
+    gs = pipe.graphed(x, fused=False)
+    r4, c4 = gs()
+    assert torch.equal(r4, want_rec) and torch.equal(c4, want_codes)
