@@ -440,6 +440,168 @@ struct CodesArgs {
     int32_t* code_grid;         // (n_img, tiles_h, tiles_w, channels, p)
 };
 
+template <int N>
+__device__ __forceinline__ float tree_max(float (&x)[N]) {
+#pragma unroll
+    for (int s = 1; s < N; s *= 2)
+#pragma unroll
+        for (int j = 0; j + s < N; j += 2 * s) x[j] = fmaxf(x[j], x[j + s]);
+    return x[0];
+}
+template <int N>
+__device__ __forceinline__ float tree_min(float (&x)[N]) {
+#pragma unroll
+    for (int s = 1; s < N; s *= 2)
+#pragma unroll
+        for (int j = 0; j + s < N; j += 2 * s) x[j] = fminf(x[j], x[j + s]);
+    return x[0];
+}
+
+// Epilogue of fold_codes_kernel for tile width P (8 warps per CTA: lane quarter = warp & 3 picks the coefficient
+// rows, the two warps of a quarter take half of the tile's token columns each).  The epilogue warps are only two
+// per scheduler, so the code is written for instruction-level parallelism: two tokens are read out of TMEM and
+// processed together, the per-token maxima / minima are reduction trees and the code word is assembled as two
+// half chains, instead of three 14-step dependent chains per token.
+template <int P>
+__device__ __forceinline__ void codes_epilogue(const CodesArgs& g, uint32_t tmem_base, uint64_t* tmem_full,
+                                               uint32_t tmem_empty_leader0, uint32_t tmem_empty_leader1, int warp,
+                                               int lane, uint32_t rank, int grp, int pair_in_grp, int pairs_per_grp) {
+    constexpr int Z = P * P, P2 = P / 2;
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int i = (int)rank * 128 + quarter * 32 + lane;         // basis row of this thread
+    const bool i_ok = i < g.n_valid;
+    const int kh = 2 * i + grp;
+    const int th = kh / P, pi = kh - th * P;
+    const float scale = i_ok ? g.alpha * (g.basis_scale ? __ldg(g.basis_scale + grp * g.n_valid + i) : 1.0f) : 0.0f;
+    const bool tame = g.tame != nullptr && __ldg(g.tame) != 0 && g.eps > 1e-12f && g.clamp_lo < 0.0f && g.clamp_hi > 0.0f;
+    const LfqNormParams q{nullptr, nullptr, 0, 0, 0, 0, g.eps, g.clamp_lo, g.clamp_hi, 0, 0, 0.f};
+    // lanes of the same tile row th are contiguous: the first of each run publishes the row's maximum
+    const int th_prev = __shfl_up_sync(0xffffffffu, th, 1);
+    const bool th_leader = i_ok && (lane == 0 || th_prev != th);
+    bool take[3];                                             // does lane + 1 / 2 / 4 belong to the same tile row?
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        const int oth = __shfl_down_sync(0xffffffffu, th, 1 << o);
+        take[o] = (lane + (1 << o) < 32) && oth == th;
+    }
+    const int t_lo = half * ((g.tokens_per_tile + 1) >> 1);
+    const int t_hi = half ? g.tokens_per_tile : ((g.tokens_per_tile + 1) >> 1);
+    const int64_t stat_row = (int64_t)th * g.stat_w * Z + pi * P;        // + (ch * stat_h * stat_w + tw) * Z
+    const int64_t stat_ch = (int64_t)g.stat_h * g.stat_w * Z;
+    const int64_t tok_row = (int64_t)th * g.tiles_w * g.channels;        // token = (img*tiles_h*tiles_w + tw) * C + ch + tok_row
+    const int64_t tok_img = (int64_t)g.tiles_h * g.tiles_w * g.channels; // token index step from one image to the next
+    const bool dc_lane = kh == 0 && g.dc != nullptr;
+    uint32_t tcount = 0;
+    for (int w = pair_in_grp; w < g.tiles_per_seg; w += pairs_per_grp, ++tcount) {
+        const int acc = tcount & 1;
+        // token of this warp's first data column: the data rows run [channel][tw][image][pj]
+        int tc = w * g.tokens_per_tile + t_lo;
+        int img = tc % g.batch;
+        int tw = (tc / g.batch) % g.tiles_w, ch = tc / (g.batch * g.tiles_w);
+        mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
+        // the medians of this coefficient row depend on (channel, tw) only: one load per run of images
+        float mv[P];
+        int m_tw = -1, m_ch = -1;
+        int tk = t_lo;
+        if (t_hi <= t_lo) {                                  // nothing to read: release immediately
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+        }
+        while (tk < t_hi) {
+            // a pair of tokens shares its medians unless the image index wraps between them (warp-uniform)
+            const bool two = tk + 1 < t_hi && img + 1 < g.batch;
+            uint32_t rr[2][16];
+            tmem_ld16_nowait(tmem_acc + tk * P, rr[0]);
+            if (two) tmem_ld16_nowait(tmem_acc + (tk + 1) * P, rr[1]);
+            const bool ok[2] = {(int64_t)tc * P < g.rows_per_seg, two && (int64_t)(tc + 1) * P < g.rows_per_seg};
+            if (ok[0] && (tw != m_tw || ch != m_ch)) {
+                const float2* src = reinterpret_cast<const float2*>(g.med + ch * stat_ch + (int64_t)tw * Z + stat_row);
+#pragma unroll
+                for (int j = 0; j < P2; ++j) {
+                    const float2 t = i_ok ? __ldg(src + j) : make_float2(0.f, 0.f);
+                    mv[2 * j] = t.x;
+                    mv[2 * j + 1] = t.y;
+                }
+                m_tw = tw;
+                m_ch = ch;
+            }
+            float dcv[2] = {0.0f, 0.0f};
+            if (dc_lane && tw == 0) {
+                if (ok[0]) dcv[0] = __ldg(g.dc + img * g.channels + ch);
+                if (ok[1]) dcv[1] = __ldg(g.dc + (img + 1) * g.channels + ch);
+            }
+            tmem_ld_wait();
+            if (tk + (two ? 2 : 1) >= t_hi) {                  // accumulator read out by this warp: hand it back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+            }
+            if (!two) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) rr[1][j] = rr[0][j];
+            }
+            const int64_t tok0 = ((int64_t)img * g.tiles_h * g.tiles_w + tw) * g.channels + ch + tok_row;
+            unsigned word[2];
+            float mx[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                // fast path: bit = sign of (median - Y) (Y > median <=> the difference is negative), valid when the
+                // divisor is tame and no |difference| is tiny; funnel shifts build the word MSB first
+                float v[P], nd[P], av[P], ad[P];
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    v[j] = __uint_as_float(rr[u][j]) * scale;
+                    if (j == 0) v[j] += dcv[u];
+                    nd[j] = __fsub_rn(mv[j], v[j]);
+                    av[j] = fabsf(v[j]);
+                    ad[j] = fabsf(nd[j]);
+                }
+                unsigned wa = 0, wb = 0;
+#pragma unroll
+                for (int j = 0; j < P2; ++j) {
+                    wa = __funnelshift_l(__float_as_uint(nd[j]), wa, 1);
+                    wb = __funnelshift_l(__float_as_uint(nd[P2 + j]), wb, 1);
+                }
+                word[u] = (wa << P2) | wb;
+                const float dmin = tree_min<P>(ad);
+                mx[u] = (ok[u] && i_ok) ? tree_max<P>(av) : 0.0f;
+                if (ok[u] && i_ok && (!tame || !(dmin > 1e-20f))) {          // rare: exact sign of the clamped quotient
+                    const float* bsrc = g.bstat + ch * stat_ch + (int64_t)tw * Z + stat_row;
+                    unsigned wd = 0;
+#pragma unroll
+                    for (int j = 0; j < P; ++j) wd = (wd << 1) | norm_sign_bit(v[j], mv[j], __ldg(bsrc + j), q);
+                    word[u] = wd;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (ok[u] && i_ok) g.code_grid[(tok0 + u * tok_img) * P + pi] = (int32_t)word[u];
+            // max over the lanes of one tile row (runs of P/2 <= 8 lanes)
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                const float o0 = __shfl_down_sync(0xffffffffu, mx[0], 1 << o);
+                const float o1 = __shfl_down_sync(0xffffffffu, mx[1], 1 << o);
+                if (take[o]) {
+                    mx[0] = fmaxf(mx[0], o0);
+                    mx[1] = fmaxf(mx[1], o1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (ok[u] && th_leader && mx[u] > 0.0f)
+                    atomicMax(reinterpret_cast<unsigned*>(g.maxabs) + tok0 + u * tok_img, __float_as_uint(mx[u]));
+            const int n = two ? 2 : 1;
+            tk += n;
+            tc += n;
+            img += n;
+            if (img >= g.batch) { img = 0; if (++tw == g.tiles_w) { tw = 0; ++ch; } }
+        }
+    }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
 fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_constant__ CUtensorMap map_d_lo,
                   const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -544,117 +706,14 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
             umma_commit_2sm(&tmem_full[acc], 3);
         }
     } else if (warp >= 2) {
-        // ---------------- epilogue: lane quarter = warp & 3 (coefficient rows), the two warps of a quarter take
-        // half of the tile's token columns each
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
-        const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
-        const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
-        const int p = g.p, z = p * p, p2 = p >> 1;
-        const int i = (int)rank * 128 + quarter * 32 + lane;         // basis row of this thread
-        const bool i_ok = i < g.n_valid;
-        const int kh = 2 * i + grp;
-        const int th = kh / p, pi = kh - th * p;
-        const float scale = i_ok ? g.alpha * (g.basis_scale ? __ldg(g.basis_scale + grp * g.n_valid + i) : 1.0f) : 0.0f;
-        const bool tame = g.tame != nullptr && __ldg(g.tame) != 0 && g.eps > 1e-12f && g.clamp_lo < 0.0f && g.clamp_hi > 0.0f;
-        const LfqNormParams q{nullptr, nullptr, 0, 0, 0, 0, g.eps, g.clamp_lo, g.clamp_hi, 0, 0, 0.f};
-        // lanes of the same tile row th are contiguous: the first of each run publishes the row's maximum
-        const int th_prev = __shfl_up_sync(0xffffffffu, th, 1);
-        const bool th_leader = i_ok && (lane == 0 || th_prev != th);
-        bool take[3];                                             // does lane + 1 / 2 / 4 belong to the same tile row?
-#pragma unroll
-        for (int o = 0; o < 3; ++o) {
-            const int oth = __shfl_down_sync(0xffffffffu, th, 1 << o);
-            take[o] = (lane + (1 << o) < 32) && oth == th;
-        }
-        const int t_lo = half * ((g.tokens_per_tile + 1) >> 1);
-        const int t_hi = half ? g.tokens_per_tile : ((g.tokens_per_tile + 1) >> 1);
-        const int64_t stat_row = (int64_t)th * g.stat_w * z + pi * p;        // + (ch * stat_h * stat_w + tw) * z
-        const int64_t stat_ch = (int64_t)g.stat_h * g.stat_w * z;
-        const int64_t tok_row = (int64_t)th * g.tiles_w * g.channels;        // token index = (img*tiles_h*tiles_w + tw) * C + ch + tok_row
-        uint32_t tcount = 0;
-        for (int w = pair_in_grp; w < g.tiles_per_seg; w += pairs_per_grp, ++tcount) {
-            const int acc = tcount & 1;
-            // token of this warp's first data column: the data rows run [channel][tw][image][pj]
-            int tc = w * g.tokens_per_tile + t_lo;
-            int img = tc % g.batch;
-            int tw = (tc / g.batch) % g.tiles_w, ch = tc / (g.batch * g.tiles_w);
-            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
-            tc_fence_after();
-            const uint32_t tmem_acc = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
-            // the medians of this coefficient row depend on (channel, tw) only: one load per run of images
-            float2 mcur[8];
-            int m_tw = -1, m_ch = -1;
-            for (int tk = t_lo; tk < t_hi; ++tk) {
-                uint32_t rr[16];
-                tmem_ld16_nowait(tmem_acc + tk * p, rr);
-                const bool tok_ok = (int64_t)tc * p < g.rows_per_seg;           // warp-uniform
-                if (tok_ok && (tw != m_tw || ch != m_ch)) {
-                    const float2* src = reinterpret_cast<const float2*>(g.med + ch * stat_ch + (int64_t)tw * z + stat_row);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) mcur[j] = (i_ok && j < p2) ? __ldg(src + j) : make_float2(0.f, 0.f);
-                    m_tw = tw;
-                    m_ch = ch;
-                }
-                tmem_ld_wait();
-                if (tk == t_hi - 1) {                          // accumulator read out by this warp: hand it back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
-                }
-                const int plane = img * g.channels + ch;
-                const int64_t tok = ((int64_t)img * g.tiles_h * g.tiles_w + tw) * g.channels + ch + tok_row;
-                const float mvals[16] = {mcur[0].x, mcur[0].y, mcur[1].x, mcur[1].y, mcur[2].x, mcur[2].y, mcur[3].x, mcur[3].y,
-                                         mcur[4].x, mcur[4].y, mcur[5].x, mcur[5].y, mcur[6].x, mcur[6].y, mcur[7].x, mcur[7].y};
-                float mx = 0.0f;
-                if (tok_ok && i_ok) {
-                    // fast path: bit = sign of (median - Y) (Y > median <=> the difference is negative), valid when the
-                    // divisor is tame and no |difference| is tiny; one funnel shift per element builds the word MSB first
-                    const float dcv = (kh == 0 && tw == 0 && g.dc != nullptr) ? __ldg(g.dc + plane) : 0.0f;
-                    unsigned word = 0;
-                    float dmin = 1.0f;
-                    float vals[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (j < p) {
-                            float v = __uint_as_float(rr[j]) * scale;
-                            if (j == 0) v += dcv;
-                            vals[j] = v;
-                            const float nd = __fsub_rn(mvals[j], v);
-                            word = __funnelshift_l(__float_as_uint(nd), word, 1);
-                            dmin = fminf(dmin, fabsf(nd));
-                            mx = fmaxf(mx, fabsf(v));
-                        }
-                    }
-                    if (!tame || !(dmin > 1e-20f)) {          // rare: exact sign of the clamped quotient
-                        const float* bsrc = g.bstat + ch * stat_ch + (int64_t)tw * z + stat_row;
-                        word = 0;
-                        for (int j = 0; j < p; ++j) {
-                            float v = __uint_as_float(rr[0]);
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) if (u == j) v = vals[u];
-                            float mvj = mvals[0];
-#pragma unroll
-                            for (int u = 0; u < 16; ++u) if (u == j) mvj = mvals[u];
-                            word = (word << 1) | norm_sign_bit(v, mvj, __ldg(bsrc + j), q);
-                        }
-                    }
-                    g.code_grid[tok * p + pi] = (int32_t)word;
-                }
-                // max over the lanes of one tile row (runs of p/2 <= 8 lanes)
-#pragma unroll
-                for (int o = 0; o < 3; ++o) {
-                    const float other = __shfl_down_sync(0xffffffffu, mx, 1 << o);
-                    if (take[o]) mx = fmaxf(mx, other);
-                }
-                if (tok_ok && th_leader && mx > 0.0f) atomicMax(reinterpret_cast<unsigned*>(g.maxabs) + tok, __float_as_uint(mx));
-                ++tc;
-                if (++img == g.batch) { img = 0; if (++tw == g.tiles_w) { tw = 0; ++ch; } }
-            }
-            if (t_hi <= t_lo) {                                  // nothing to read: release immediately
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
-            }
+        // ---------------- epilogue (codes_epilogue<P> above), one instantiation per supported tile width
+        const uint32_t e0 = mapa_u32(smem_u32(&tmem_empty[0]), 0), e1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+        switch (g.p) {
+            case 8: codes_epilogue<8>(g, tmem_base, tmem_full, e0, e1, warp, lane, rank, grp, pair_in_grp, pairs_per_grp); break;
+            case 10: codes_epilogue<10>(g, tmem_base, tmem_full, e0, e1, warp, lane, rank, grp, pair_in_grp, pairs_per_grp); break;
+            case 12: codes_epilogue<12>(g, tmem_base, tmem_full, e0, e1, warp, lane, rank, grp, pair_in_grp, pairs_per_grp); break;
+            case 14: codes_epilogue<14>(g, tmem_base, tmem_full, e0, e1, warp, lane, rank, grp, pair_in_grp, pairs_per_grp); break;
+            default: codes_epilogue<16>(g, tmem_base, tmem_full, e0, e1, warp, lane, rank, grp, pair_in_grp, pairs_per_grp); break;
         }
     }
     __syncwarp();
