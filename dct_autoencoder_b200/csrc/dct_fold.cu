@@ -255,50 +255,55 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             tma_load_3d_2sm(&map_b_hi, basis_bar_leader, basis_hi + kb * btile, kb * FK, row, grp);
             tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * btile, kb * FK, row, grp);
         }
-        uint32_t it = 0;
+        const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
+        int s = 0;
+        uint32_t ph = 1;                                 // parity of a free slot
         for (int w = pair_in_slice; w < n_work; w += pairs_per_slice) {
             const int seg = (w / g.tiles_per_seg) * 2 + grp;
             const int row0 = (w % g.tiles_per_seg) * 256 + (int)rank * 128;
-            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
-                const int s = it % g.stages;
-                mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                mbar_wait(&empty_bar[s], ph);
                 uint8_t* st = ring + s * F_STAGE;
-                const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
+                const uint32_t full_leader = full_leader0 + 8u * s;
                 if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * F_STAGE);
                 tma_load_3d_2sm(&map_a_hi, full_leader, st, kb * FK, row0, seg);
                 tma_load_3d_2sm(&map_a_lo, full_leader, st + F_ATILE, kb * FK, row0, seg);
+                if (++s == g.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
-        // ---------------- MMA issuer (leader CTA only)
+        // ---------------- MMA issuer (leader CTA only): one thread, so the loop is kept to a wait, one add per
+        // descriptor and the MMAs (no division for the ring slot, no descriptor rebuild)
         const uint32_t idesc = fold_idesc(g.n_tile);
-        const uint32_t btile = (uint32_t)(g.n_tile >> 1) * 64;
-        const uint32_t bh = smem_u32(basis_hi), bl = smem_u32(basis_lo);
+        const uint32_t btile16 = ((uint32_t)(g.n_tile >> 1) * 64) >> 4;
+        const uint32_t bh = smem_desc_lo(smem_u32(basis_hi)), bl = smem_desc_lo(smem_u32(basis_lo));
+        const uint32_t ring16 = smem_desc_lo(smem_u32(ring));
         mbar_wait_cluster(&basis_bar, 0);
         tc_fence_after();
-        uint32_t it = 0, tcount = 0;
+        uint32_t tcount = 0, ph = 0;
+        int s = 0;
         for (int w = pair_in_slice; w < n_work; w += pairs_per_slice, ++tcount) {
             const int acc = tcount & 1;
             mbar_wait_cluster(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + acc * 256;
-            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
-                const int s = it % g.stages;
-                mbar_wait_cluster(&full_bar[s], (it / g.stages) & 1);
+            uint32_t b16 = 0;
+            for (int kb = 0; kb < g.num_kb; ++kb, b16 += btile16) {
+                mbar_wait_cluster(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t base = smem_u32(ring + s * F_STAGE);
+                const uint32_t a16 = ring16 + (uint32_t)s * (F_STAGE >> 4);
 #pragma unroll
                 for (int k = 0; k < FK / 16; ++k) {
-                    const uint32_t ko = k * 32;
-                    const uint64_t a_hi = smem_desc_sw64(base + ko);
-                    const uint64_t a_lo = smem_desc_sw64(base + F_ATILE + ko);
-                    const uint64_t b_hi = smem_desc_sw64(bh + kb * btile + ko);
-                    const uint64_t b_lo = smem_desc_sw64(bl + kb * btile + ko);
+                    const uint64_t a_hi = smem_desc_sw64_from_lo(a16 + 2 * k);
+                    const uint64_t a_lo = smem_desc_sw64_from_lo(a16 + (F_ATILE >> 4) + 2 * k);
+                    const uint64_t b_hi = smem_desc_sw64_from_lo(bh + b16 + 2 * k);
+                    const uint64_t b_lo = smem_desc_sw64_from_lo(bl + b16 + 2 * k);
                     umma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, (kb | k) ? 1u : 0u);   // small terms first
                     umma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1u);
                     umma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1u);
                 }
                 umma_commit_2sm(&empty_bar[s], 3);       // frees the stage in both CTAs
+                if (++s == g.stages) { s = 0; ph ^= 1u; }
             }
             umma_commit_2sm(&tmem_full[acc], 3);         // accumulator complete in both CTAs
         }
@@ -658,43 +663,47 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
             tma_load_3d_2sm(&map_b_hi, basis_bar_leader, basis_hi + kb * F_ATILE, kb * FK, (int)rank * 128, grp);
             tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * F_ATILE, kb * FK, (int)rank * 128, grp);
         }
-        uint32_t it = 0;
+        const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
+        int s = 0;
+        uint32_t ph = 1;                                 // parity of a free slot
         for (int w = pair_in_grp; w < g.tiles_per_seg; w += pairs_per_grp) {
             const int row0 = w * g.n_data + (int)rank * half_data;
-            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
-                const int s = it % g.stages;
-                mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                mbar_wait(&empty_bar[s], ph);
                 uint8_t* st = ring + s * g.stage_bytes;
-                const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
+                const uint32_t full_leader = full_leader0 + 8u * s;
                 if (rank == 0) mbar_expect_tx(&full_bar[s], 4 * dtile);
                 tma_load_3d_2sm(&map_d_hi, full_leader, st, kb * FK, row0, grp);
                 tma_load_3d_2sm(&map_d_lo, full_leader, st + dtile, kb * FK, row0, grp);
+                if (++s == g.stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
-        // ---------------- MMA issuer: A = resident basis (M = 256 over the pair), B = data stage (N = n_data)
+        // ---------------- MMA issuer: A = resident basis (M = 256 over the pair), B = data stage (N = n_data);
+        // a single thread, kept to a wait, one add per descriptor and the MMAs (see fold_gemm_kernel)
         const uint32_t idesc = fold_idesc(g.n_data);
-        const uint32_t bh = smem_u32(basis_hi), bl = smem_u32(basis_lo);
+        const uint32_t bh = smem_desc_lo(smem_u32(basis_hi)), bl = smem_desc_lo(smem_u32(basis_lo));
+        const uint32_t ring16 = smem_desc_lo(smem_u32(ring)), stage16 = g.stage_bytes >> 4, dtile16 = dtile >> 4;
         mbar_wait_cluster(&basis_bar, 0);
         tc_fence_after();
-        uint32_t it = 0, tcount = 0;
+        uint32_t tcount = 0, ph = 0;
+        int s = 0;
         for (int w = pair_in_grp; w < g.tiles_per_seg; w += pairs_per_grp, ++tcount) {
             const int acc = tcount & 1;
             mbar_wait_cluster(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + acc * 256;
-            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
-                const int s = it % g.stages;
-                mbar_wait_cluster(&full_bar[s], (it / g.stages) & 1);
+            uint32_t a16 = 0;
+            for (int kb = 0; kb < g.num_kb; ++kb, a16 += F_ATILE >> 4) {
+                mbar_wait_cluster(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t base = smem_u32(ring + s * g.stage_bytes);
+                const uint32_t d16 = ring16 + (uint32_t)s * stage16;
 #pragma unroll
                 for (int k = 0; k < FK / 16; ++k) {
-                    const uint32_t ko = k * 32;
-                    const uint64_t a_hi = smem_desc_sw64(bh + kb * F_ATILE + ko);
-                    const uint64_t a_lo = smem_desc_sw64(bl + kb * F_ATILE + ko);
-                    const uint64_t b_hi = smem_desc_sw64(base + ko);
-                    const uint64_t b_lo = smem_desc_sw64(base + dtile + ko);
+                    const uint64_t a_hi = smem_desc_sw64_from_lo(bh + a16 + 2 * k);
+                    const uint64_t a_lo = smem_desc_sw64_from_lo(bl + a16 + 2 * k);
+                    const uint64_t b_hi = smem_desc_sw64_from_lo(d16 + 2 * k);
+                    const uint64_t b_lo = smem_desc_sw64_from_lo(d16 + dtile16 + 2 * k);
                     // the same sequence of partial sums as fold_gemm_kernel (data_lo*basis_hi, data_hi*basis_lo,
                     // data_hi*basis_hi) so that both kernels produce bit-identical coefficients
                     umma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, (kb | k) ? 1u : 0u);
@@ -702,6 +711,7 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
                     umma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1u);
                 }
                 umma_commit_2sm(&empty_bar[s], 3);
+                if (++s == g.stages) { s = 0; ph ^= 1u; }
             }
             umma_commit_2sm(&tmem_full[acc], 3);
         }

@@ -85,6 +85,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
     return d;
 }
 
+// The MMA issuer is ONE thread: every instruction it spends between two tcgen05.mma is serial latency, so the
+// descriptors of a k-step are formed from a precomputed low word (start address >> 4) with one add each.
+constexpr uint32_t kDescSw64Hi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);    // SBO 512 B, version 1, SWIZZLE_64B
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return (saddr & 0x3ffff) >> 4; }
+__device__ __forceinline__ uint64_t smem_desc_sw64_from_lo(uint32_t lo) { return ((uint64_t)kDescSw64Hi << 32) | lo; }
+
 
 // ------------------------------------------------------------------------------ CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
