@@ -259,6 +259,9 @@ def run_ours(a):
     staged_value = world * B * staged_steps / (ms_staged / 1e3)
 
     # ---- end to end through the public API with HOST buffers (pinned in, pinned out)
+    # pinned buffers live on the NUMA node of the allocating thread: allocate next to the GPU (no-op on one node)
+    old_affinity = os.sched_getaffinity(0)
+    numa_bound = D.util.bind_to_gpu_numa(dev)
     hx = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
     hx.copy_(x)
     h_rec = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
@@ -272,6 +275,8 @@ def run_ours(a):
     e2e_steps = max(2, min(a.steps, 8))
     ms_e2e = timed(step_e2e, e2e_steps, 2)
     e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
+    if numa_bound:
+        os.sched_setaffinity(0, old_affinity)
 
     # ---- per-stage device times (CUDA events around each public call) for the roofline object
     stages = stage_times(torch, D, pipe, x, dev, reps=3)

@@ -18,11 +18,19 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--chunks", default="8,16,32,64")
     ap.add_argument("--reps", type=int, default=6)
+    ap.add_argument("--bind", action="store_true", help="bind to the CPUs of the GPU's NUMA node before allocating")
     a = ap.parse_args()
     import torch
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     B, S = a.batch, 512
+    import os
+    from dct_autoencoder_b200 import util
+    cpus = util.gpu_numa_cpus(dev)
+    print(f"affinity {len(os.sched_getaffinity(0))} cpus; GPU NUMA cpus: {None if cpus is None else len(cpus)}; "
+          f"nodes: {[d for d in os.listdir('/sys/devices/system/node') if d.startswith('node')]}")
+    if a.bind:
+        print("bound:", util.bind_to_gpu_numa(dev))
 
     # ---- the link
     n = 512 << 20
