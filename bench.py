@@ -317,9 +317,9 @@ def run_ours(a):
                         "forward pass 1, forward pass 2 -> code words, inverse passes 1-2; "
                         "cta_group::2 tcgen05 fp16x3 split precision, folded basis resident in shared memory)",
                         achieved=achieved_gbs, peak=hbm, unit="GB/s", frac=achieved_gbs / hbm,
-                        # dram__bytes_read + write per launch, ncu --set full of this workload (profiles/r02n_kernels_ncu_full_b256.txt:
-                        # 1465 MB forward pass 1, 819 MB fold_codes_kernel, 1271 / 1457 MB inverse passes)
-                        traffic=(1.253e9 if (B == 256 and S == 512 and "dct_fwd_codes" in stages) else None),
+                        # dram__bytes_read + write per launch, ncu --set full of this workload (profiles/r02v_kernels_ncu_full_b256.txt:
+                        # 1470 MB forward pass 1, 821 MB fold_codes_kernel, 1272 / 1459 MB inverse passes)
+                        traffic=(1.256e9 if (B == 256 and S == 512 and "dct_fwd_codes" in stages) else None),
                         launches_per_step=4, avg_launch_ms=gemm_ms / 4,
                         algorithmic_bytes_per_launch=sum(alg) * B / 4,
                         peak_source=("measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"),
