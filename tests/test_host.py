@@ -284,3 +284,22 @@ def test_shard_rollover_reader_and_collate(D, tmp_path):
         w3.write(bad)
         w3.write(_sample(2))
     assert len(list(D.shards.load_preprocessed_dataset(w3.paths))) == 2
+
+
+def test_fast_pth_writer_is_a_valid_torch_archive(D):
+    """The shard writer's own .pth encoder: readable by torch.load(weights_only=True) and by zipfile (CRCs), stores
+    exactly the slice it was given, and falls back to torch.save where it does not apply."""
+    import io, zipfile
+    big = torch.arange(6 * 40, dtype=torch.float32).reshape(6, 40)
+    for dt in (torch.float16, torch.float32, torch.bfloat16, torch.int64, torch.uint8, torch.bool):
+        x = big.to(dt)[2:5]                                   # a slice of a larger buffer, as in preprocess_to_shards
+        blob = D.shards._save_tensor(x)
+        assert D.shards._FAST_SAVE_OK[dt]
+        y = torch.load(io.BytesIO(blob), weights_only=True)
+        assert y.dtype == dt and torch.equal(y, x)
+        assert y.untyped_storage().nbytes() == x.numel() * x.element_size()      # not the whole parent buffer
+        z = zipfile.ZipFile(io.BytesIO(blob))
+        assert z.testzip() is None and "archive/data.pkl" in z.namelist() and "archive/data/0" in z.namelist()
+    for odd in (big.t(), torch.empty(0, 3)):                  # non-contiguous / empty: plain torch.save
+        y = torch.load(io.BytesIO(D.shards._save_tensor(odd)), weights_only=True)
+        assert y.shape == odd.shape and torch.equal(y, odd)
