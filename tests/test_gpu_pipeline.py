@@ -203,3 +203,34 @@ def test_graphed_roundtrip_replays_the_eager_step(D):
     gs = pipe.graphed(x, fused=False)
     r4, c4 = gs()
     assert torch.equal(r4, want_rec) and torch.equal(c4, want_codes)
+
+
+def test_config2_full_batch_properties(D):
+    """BASELINE config 2 at its full size (256 x 512^2, patch 14, 14 x 14-bit LFQ), checked through properties
+    that do not need the CPU oracle: every image's codes and reconstruction are independent of the batch it is
+    processed in (bit for bit, full batch vs chunks of 32 vs the staged modules), every (channel, h, w) token
+    appears exactly once per image, code words are 14-bit, and the reconstruction error is that of the
+    quantiser, not of the transform."""
+    torch.manual_seed(0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(256, 3, 512, 512, device="cuda", generator=g)
+    pipe = _pipe(D, "tc")
+    pipe.fit_norm(torch.rand(32, 3, 512, 512, device="cuda", generator=g))
+    batch, codes = pipe.encode_codes(x)
+    rec = pipe.decode_codes(batch, codes)
+    assert tuple(codes.shape) == (256, 3072, 14) and codes.dtype == torch.int64
+    assert int(codes.min()) >= 0 and int(codes.max()) < 2 ** 14
+    assert not bool(batch.key_pad_mask.any())
+    key = (batch.patch_channels * 32 + batch.patch_positions[..., 0]) * 32 + batch.patch_positions[..., 1]
+    assert bool((torch.sort(key, dim=1).values == torch.arange(3072, device="cuda")).all())
+    # checksum of checksums: chunks of 32 images reproduce the full batch exactly
+    for lo in range(0, 256, 32):
+        r2, c2 = pipe.roundtrip(x[lo:lo + 32])
+        assert torch.equal(c2, codes[lo:lo + 32]) and torch.equal(r2, rec[lo:lo + 32]), lo
+    # ... and so do the staged drop-in modules (on a slice, they materialise every intermediate)
+    r3, c3 = pipe.roundtrip_staged(x[64:96])
+    assert torch.equal(c3, codes[64:96]) and torch.equal(r3, rec[64:96])
+    # un-quantised round trip = low-pass of the image; quantised one is bounded by the clamp of PatchNorm
+    plain = pipe.extractor.postprocess_batch(pipe.extractor.process_batch(x[:8]))
+    assert float((plain - x[:8]).abs().mean()) < float((rec[:8] - x[:8]).abs().mean())
+    assert bool(torch.isfinite(rec).all())

@@ -1,5 +1,13 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+"""Eager launches vs CUDA-graph replay of the fused round trip at several batch sizes.
+
+    python tools/bench_graph.py
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dct_autoencoder_b200 as D
 dev = torch.device('cuda', 0)
 fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
