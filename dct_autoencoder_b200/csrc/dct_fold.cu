@@ -355,16 +355,8 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
             }
-#pragma unroll 1
-            for (int c = chalf; c < n_chunks; c += 2) {
-                uint32_t rr[32];
-                tmem_ld32_nowait(tmem_acc + c * cwid, rr);
-                tmem_ld_wait();
-                if (c == last) {                             // accumulator read out by this warp: hand it back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
-                }
+            // software-pipelined read-out: the next chunk's tcgen05.ld is in flight while this one is stored
+            auto process = [&](const uint32_t (&rr)[32], int c) {
                 const float dcc = c == 0 ? dcv : 0.0f;
                 if (MODE == 1 && g.score_groups > 0) {
                     if (row_ok) {
@@ -372,11 +364,33 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                         sc2.col_grp = &col_grp[c * cwid];
                         store_chunk<MODE, true, true>(rr, &col_off[c * cwid], &col_scale[c * cwid], p_hi, p_lo, p_f32, dcc, sc2, cwid);
                     }
-                    continue;
+                    return;
                 }
-                if (!row_ok) continue;
+                if (!row_ok) return;
                 if (c * cwid + cwid <= n_lim) store_chunk<MODE, false, false>(rr, &col_off[c * cwid], &col_scale[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid);
                 else store_chunk<MODE, true, false>(rr, &col_off[c * cwid], &col_scale[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid);
+            };
+            auto hand_back = [&]() {                         // accumulator read out by this warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
+            };
+            uint32_t ra[32], rb[32];
+            int c = chalf;
+            if (c < n_chunks) tmem_ld32_nowait(tmem_acc + c * cwid, ra);
+#pragma unroll 1
+            while (c < n_chunks) {
+                tmem_ld_wait();
+                if (c + 2 < n_chunks) tmem_ld32_nowait(tmem_acc + (c + 2) * cwid, rb);
+                if (c == last) hand_back();
+                process(ra, c);
+                c += 2;
+                if (c >= n_chunks) break;
+                tmem_ld_wait();
+                if (c + 2 < n_chunks) tmem_ld32_nowait(tmem_acc + (c + 2) * cwid, ra);
+                if (c == last) hand_back();
+                process(rb, c);
+                c += 2;
             }
             if (MODE == 1 && g.score_groups > 0) {
                 // max |value| of every token touched by this CTA's 128 accumulator rows: the rows of a token are
