@@ -1835,11 +1835,16 @@ __global__ void __launch_bounds__(256, 3) decode_codes_rows_kernel(const int64_t
                 dc[plane] = dcval;
             }
             const int sw = (xv >> 2) & 1;
+            // output rows alternate between the two row parities a = kh & 1: one running offset per parity
+            const int kh0 = ty * p, par0 = kh0 & 1;
+            int64_t o_even = ((int64_t)plane * rows2 + ((kh0 + par0) >> 1)) * (int64_t)ldq + xv * 4;
+            int64_t o_odd = ((n_planes + plane) * rows2 + ((kh0 + 1 - par0) >> 1)) * (int64_t)ldq + xv * 4;
+            const uint4* pt_row = pos_t + xv * 2;
+            const uint4* nt_row = neg_t + xv * 2;
 #pragma unroll 2
-            for (int py = 0; py < p; ++py) {
-                const int ti = (py * nxv + xv) * 2;
-                const uint4 p0 = pos_t[ti + sw], p1 = pos_t[ti + (sw ^ 1)];
-                const uint4 n0 = neg_t[ti + sw], n1 = neg_t[ti + (sw ^ 1)];
+            for (int py = 0; py < p; ++py, pt_row += nxv * 2, nt_row += nxv * 2) {
+                const uint4 p0 = pt_row[sw], p1 = pt_row[sw ^ 1];
+                const uint4 n0 = nt_row[sw], n1 = nt_row[sw ^ 1];
                 const unsigned bits8 = ((bpack[(py >> 2) & 3] >> (8 * (py & 3))) & 0xffu) ;
                 const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
                 const uint32_t nw[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
@@ -1854,9 +1859,9 @@ __global__ void __launch_bounds__(256, 3) decode_codes_rows_kernel(const int64_t
                 const uint2 el = make_uint2(__byte_perm(w[0], w[2], 0x7632), __byte_perm(w[4], w[6], 0x7632));
                 const uint2 oh = make_uint2(__byte_perm(w[1], w[3], 0x5410), __byte_perm(w[5], w[7], 0x5410));
                 const uint2 ol = make_uint2(__byte_perm(w[1], w[3], 0x7632), __byte_perm(w[5], w[7], 0x7632));
-                const int kh = ty * p + py;
-                const int a = kh & 1, ii = kh >> 1;
-                const int64_t o = ((a * n_planes + plane) * rows2 + ii) * (int64_t)ldq + xv * 4;   // + b * 2 * quad
+                const bool odd = (kh0 + py) & 1;
+                const int64_t o = odd ? o_odd : o_even;              // (a, plane, kh >> 1, xv * 4); + b * 2 * quad
+                if (odd) o_odd += ldq; else o_even += ldq;
                 *reinterpret_cast<uint2*>(hi + o) = eh;
                 *reinterpret_cast<uint2*>(lo + o) = el;
                 *reinterpret_cast<uint2*>(hi + 2 * quad + o) = oh;
