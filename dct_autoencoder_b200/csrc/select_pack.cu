@@ -192,6 +192,137 @@ __global__ void __launch_bounds__(1024) sort_tokens_fast_kernel(const float* __r
     }
 }
 
+// Block radix sort for 1024 < n_tok <= 4096 (the 3072 tokens of a 512^2 image): the order is decided by the 32-bit
+// key ~orderable(score) alone, ties by ascending index, i.e. a STABLE sort of the keys in index order -- which is
+// what least-significant-digit radix sort delivers.  Four passes of 8 bits; 1024 threads hold 4 elements each
+// (warp w owns elements 128w .. 128w+127, slot e of lane l is element 128w + 32e + l, so rank order inside a warp
+// is index order).  Per pass: every warp ranks its elements per digit with ballots (no atomics), an exclusive
+// scan over (digit, warp) turns the counts into offsets, elements move to their place in shared memory.
+// ~1/4 of the instructions of the 4096-slot bitonic network on 64-bit keys.
+constexpr int kRadixThreads = 1024, kRadixSlots = 4;
+
+template <bool kFromMax>
+__global__ void __launch_bounds__(kRadixThreads, 2) sort_tokens_radix_kernel(const float* __restrict__ scores,
+                                                                             int32_t* __restrict__ order, int n_tok,
+                                                                             ScoreParams sp) {
+    extern __shared__ __align__(16) uint32_t radix_smem[];
+    uint32_t* keys0 = radix_smem;                                     // [4096]
+    uint32_t* keys1 = keys0 + 4096;
+    uint16_t* idx0 = reinterpret_cast<uint16_t*>(keys1 + 4096);       // [4096]
+    uint16_t* idx1 = idx0 + 4096;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(idx1 + 4096);        // [32 warps][256 digits]
+    uint32_t* warp_tot = hist + 32 * 256;                             // [32]
+    const int64_t img = blockIdx.x;
+    const float* s = scores + img * n_tok;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t key[kRadixSlots];
+    uint32_t idx[kRadixSlots];
+#pragma unroll
+    for (int e = 0; e < kRadixSlots; ++e) {
+        const int i = warp * 128 + e * 32 + lane;
+        key[e] = 0xffffffffu;                                         // padding sorts last (stable: after every token)
+        idx[e] = (uint32_t)i;
+        if (i < n_tok) {
+            float sc = s[i];
+            if (kFromMax) {
+                const int c = i % sp.channels;
+                const int tile = i / sp.channels;
+                const int h = tile / sp.tw, w = tile - h * sp.tw;
+                const float mags = __fmul_rn(sc, sp.mag_weight);
+                const float dist = __fdiv_rn((float)(-(h + w)), sp.imp.v[c]);
+                sc = __fadd_rn(mags, dist);
+                if (sp.scores_out) sp.scores_out[img * n_tok + i] = sc;
+            }
+            key[e] = ~orderable(sc);
+        }
+    }
+    uint32_t* kin = keys0;
+    uint32_t* kout = keys1;
+    uint16_t* iin = idx0;
+    uint16_t* iout = idx1;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        for (int i = t; i < 32 * 256; i += kRadixThreads) hist[i] = 0u;
+        __syncthreads();
+        // rank of every element among the elements of its warp with the same digit, in index order
+        uint32_t rank[kRadixSlots], dig[kRadixSlots];
+        uint32_t* my_hist = hist + warp * 256;
+#pragma unroll
+        for (int e = 0; e < kRadixSlots; ++e) {
+            dig[e] = (key[e] >> shift) & 0xffu;
+            // lanes holding the same digit: eight ballots (match.any costs one round per distinct value, ~30 here)
+            unsigned peers = 0xffffffffu;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const unsigned bal = __ballot_sync(0xffffffffu, (dig[e] >> b) & 1u);
+                peers &= ((dig[e] >> b) & 1u) ? bal : ~bal;
+            }
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) {
+                base = my_hist[dig[e]];
+                my_hist[dig[e]] = base + __popc(peers);
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            rank[e] = base + __popc(peers & lt_mask);
+            __syncwarp();
+        }
+        __syncthreads();
+        // exclusive scan of the counts in (digit, warp) order: thread t owns digit t/4, warps 8(t%4) .. 8(t%4)+7
+        {
+            const int d = t >> 2, w0 = (t & 3) * 8;
+            uint32_t sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += hist[(w0 + j) * 256 + d];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t v = warp_tot[lane], inc2 = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if (lane >= o) inc2 += u;
+                }
+                warp_tot[lane] = inc2 - v;                            // exclusive
+            }
+            __syncthreads();
+            uint32_t run = warp_tot[warp] + incl - sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t cnt = hist[(w0 + j) * 256 + d];
+                hist[(w0 + j) * 256 + d] = run;
+                run += cnt;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < kRadixSlots; ++e) {
+            const uint32_t pos = my_hist[dig[e]] + rank[e];
+            kout[pos] = key[e];
+            iout[pos] = (uint16_t)idx[e];
+        }
+        __syncthreads();
+        if (pass < 3) {
+#pragma unroll
+            for (int e = 0; e < kRadixSlots; ++e) {
+                const int i = warp * 128 + e * 32 + lane;
+                key[e] = kout[i];
+                idx[e] = iout[i];
+            }
+        }
+        uint32_t* tk = kin; kin = kout; kout = tk;
+        uint16_t* ti = iin; iin = iout; iout = ti;
+    }
+    for (int i = t; i < n_tok; i += kRadixThreads) order[img * n_tok + i] = (int32_t)iin[i];
+}
+
 // ------------------------------------------------------------------------------ pack
 // One warp per output slot (row, s).  kTiles: source is the token grid + sort order;
 // otherwise per-image token lists through pointer tables.
@@ -397,6 +528,17 @@ static int launch_sort(const float* scores, int32_t* order, int64_t n_img, int n
     if (smem > 48 * 1024) {  // per-device attribute: set on every call that needs it (cheap)
         cudaFuncSetAttribute(sort_tokens_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
         cudaFuncSetAttribute(sort_tokens_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    }
+    if (n_tok > 1024 && n_tok <= 4096) {
+        const size_t smem_radix = 2 * 4096 * 4 + 2 * 4096 * 2 + 32 * 256 * 4 + 32 * 4;
+        if (from_max) {
+            cudaFuncSetAttribute(sort_tokens_radix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_radix);
+            sort_tokens_radix_kernel<true><<<(unsigned)n_img, kRadixThreads, smem_radix, as_stream(stream)>>>(scores, order, n_tok, sp);
+        } else {
+            cudaFuncSetAttribute(sort_tokens_radix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_radix);
+            sort_tokens_radix_kernel<false><<<(unsigned)n_img, kRadixThreads, smem_radix, as_stream(stream)>>>(scores, order, n_tok, sp);
+        }
+        return check_launch("sort_tokens");
     }
     if (n_pad >= 128 && n_pad <= 4096) {
         const size_t smem_fast = 2 * smem;

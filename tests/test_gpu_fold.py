@@ -161,7 +161,7 @@ torch.save(dict(tiles=tiles.cpu(), maxabs=maxabs.cpu(), planes=planes.cpu(), bac
     assert torch.equal(back.cpu(), ref["back"])
 
 
-@pytest.mark.parametrize("n_tok", [100, 128, 500, 3072, 4096, 5000])
+@pytest.mark.parametrize("n_tok", [100, 128, 500, 1024, 1025, 2000, 3072, 4096, 5000])
 def test_sort_tokens_matches_torch_sort(D, n_tok):
     """Per-image descending sort (ties: ascending index), both kernels (register/shuffle variant up to 4096 keys)."""
     from dct_autoencoder_b200 import _lib
