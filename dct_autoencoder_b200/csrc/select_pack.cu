@@ -194,14 +194,14 @@ __global__ void __launch_bounds__(1024) sort_tokens_fast_kernel(const float* __r
 
 // Block radix sort for 1024 < n_tok <= 4096 (the 3072 tokens of a 512^2 image): the order is decided by the 32-bit
 // key ~orderable(score) alone, ties by ascending index, i.e. a STABLE sort of the keys in index order -- which is
-// what least-significant-digit radix sort delivers.  Four passes of 8 bits; 1024 threads hold 4 elements each
-// (warp w owns elements 128w .. 128w+127, slot e of lane l is element 128w + 32e + l, so rank order inside a warp
-// is index order).  Per pass: every warp ranks its elements per digit with ballots (no atomics), an exclusive
+// what least-significant-digit radix sort delivers.  Four passes of 8 bits; 16, 24 or 32 warps hold 128 elements
+// each (768 threads for 3072 tokens: no padding; warp w owns elements 128w .. 128w+127, slot e of lane l is element
+// 128w + 32e + l, so rank order inside a warp is index order).  Per pass: every warp ranks its elements per digit with ballots (no atomics), an exclusive
 // scan over (digit, warp) turns the counts into offsets, elements move to their place in shared memory.
 // ~1/4 of the instructions of the 4096-slot bitonic network on 64-bit keys.
 constexpr int kRadixThreads = 1024, kRadixSlots = 4;
 
-template <bool kFromMax>
+template <bool kFromMax>      // blockDim.x = 512, 768 or 1024
 __global__ void __launch_bounds__(kRadixThreads, 2) sort_tokens_radix_kernel(const float* __restrict__ scores,
                                                                              int32_t* __restrict__ order, int n_tok,
                                                                              ScoreParams sp) {
@@ -210,8 +210,9 @@ __global__ void __launch_bounds__(kRadixThreads, 2) sort_tokens_radix_kernel(con
     uint32_t* keys1 = keys0 + 4096;
     uint16_t* idx0 = reinterpret_cast<uint16_t*>(keys1 + 4096);       // [4096]
     uint16_t* idx1 = idx0 + 4096;
-    uint32_t* hist = reinterpret_cast<uint32_t*>(idx1 + 4096);        // [32 warps][256 digits]
+    uint32_t* hist = reinterpret_cast<uint32_t*>(idx1 + 4096);        // [n_warps][256 digits]
     uint32_t* warp_tot = hist + 32 * 256;                             // [32]
+    const int n_thr = blockDim.x, n_warps = n_thr >> 5;               // n_warps is a multiple of 8
     const int64_t img = blockIdx.x;
     const float* s = scores + img * n_tok;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kRadixThreads, 2) sort_tokens_radix_kernel(con
     uint16_t* iout = idx1;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 8 * pass;
-        for (int i = t; i < 32 * 256; i += kRadixThreads) hist[i] = 0u;
+        for (int i = t; i < n_warps * 256; i += n_thr) hist[i] = 0u;
         __syncthreads();
         // rank of every element among the elements of its warp with the same digit, in index order
         uint32_t rank[kRadixSlots], dig[kRadixSlots];
@@ -269,9 +270,10 @@ __global__ void __launch_bounds__(kRadixThreads, 2) sort_tokens_radix_kernel(con
             __syncwarp();
         }
         __syncthreads();
-        // exclusive scan of the counts in (digit, warp) order: thread t owns digit t/4, warps 8(t%4) .. 8(t%4)+7
+        // exclusive scan of the counts in (digit, warp) order: thread t owns the 8 consecutive entries 8t .. 8t+7 of
+        // that order (256 * n_warps = 8 * n_thr of them), which share their digit because 8 divides n_warps
         {
-            const int d = t >> 2, w0 = (t & 3) * 8;
+            const int d = (8 * t) / n_warps, w0 = 8 * t - d * n_warps;
             uint32_t sum = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) sum += hist[(w0 + j) * 256 + d];
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(kRadixThreads, 2) sort_tokens_radix_kernel(con
             if (lane == 31) warp_tot[warp] = incl;
             __syncthreads();
             if (warp == 0) {
-                uint32_t v = warp_tot[lane], inc2 = v;
+                uint32_t v = lane < n_warps ? warp_tot[lane] : 0u, inc2 = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t u = __shfl_up_sync(0xffffffffu, inc2, o);
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(kRadixThreads, 2) sort_tokens_radix_kernel(con
         uint32_t* tk = kin; kin = kout; kout = tk;
         uint16_t* ti = iin; iin = iout; iout = ti;
     }
-    for (int i = t; i < n_tok; i += kRadixThreads) order[img * n_tok + i] = (int32_t)iin[i];
+    for (int i = t; i < n_tok; i += n_thr) order[img * n_tok + i] = (int32_t)iin[i];
 }
 
 // ------------------------------------------------------------------------------ pack
@@ -531,12 +533,13 @@ static int launch_sort(const float* scores, int32_t* order, int64_t n_img, int n
     }
     if (n_tok > 1024 && n_tok <= 4096) {
         const size_t smem_radix = 2 * 4096 * 4 + 2 * 4096 * 2 + 32 * 256 * 4 + 32 * 4;
+        const int threads = (int)ceil_div(n_tok, 1024) * 256;          // 128 elements per warp, a multiple of 8 warps
         if (from_max) {
             cudaFuncSetAttribute(sort_tokens_radix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_radix);
-            sort_tokens_radix_kernel<true><<<(unsigned)n_img, kRadixThreads, smem_radix, as_stream(stream)>>>(scores, order, n_tok, sp);
+            sort_tokens_radix_kernel<true><<<(unsigned)n_img, threads, smem_radix, as_stream(stream)>>>(scores, order, n_tok, sp);
         } else {
             cudaFuncSetAttribute(sort_tokens_radix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_radix);
-            sort_tokens_radix_kernel<false><<<(unsigned)n_img, kRadixThreads, smem_radix, as_stream(stream)>>>(scores, order, n_tok, sp);
+            sort_tokens_radix_kernel<false><<<(unsigned)n_img, threads, smem_radix, as_stream(stream)>>>(scores, order, n_tok, sp);
         }
         return check_launch("sort_tokens");
     }
