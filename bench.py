@@ -251,7 +251,8 @@ def run_ours(a):
         torch.cuda.synchronize()
     clocks = sampler.stop(skip) if sampler else None
     value = world * B * a.steps / (ms / 1e3)
-    mode = "fused PatchNorm+LFQ inside pack/un-patchify (bit-identical to staged)" if pipe.fusable() else "staged"
+    mode = ("fused: PatchNorm + LFQ code words formed in the forward DCT epilogue, decode straight from code words "
+            "(bit-identical to staged)") if pipe.fusable() else "staged"
 
     # ---- the same job through the drop-in modules one by one (every intermediate materialised)
     staged_steps = max(2, min(a.steps, 5))
