@@ -109,7 +109,7 @@ KERNELS_PER_CALL = {
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,
     "dcta_row_sumsq": 1, "dcta_split_rows": 1, "dcta_vq_nearest_tc": 2,
     "dcta_pack_codes_lfq": 2, "dcta_decode_codes_split": 1,
-    "dcta_fold_supported": 0, "dcta_fold_codes_supported": 0, "dcta_rgb_to_ipt_fold": 3, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
+    "dcta_fold_supported": 0, "dcta_fold_codes_supported": 0, "dcta_rgb_to_ipt_fold": 2, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
     "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 2, "dcta_fold_coef_planes": 1, "dcta_dct2_inv_fold": 2,
     "dcta_unfold_ipt_to_rgb": 1, "dcta_unfold_planes": 1, "dcta_sort_tokens_maxabs": 1, "dcta_dct2_fwd_fold_codes": 3, "dcta_pack_codes_grid": 2,
 }

@@ -609,10 +609,10 @@ __global__ void __launch_bounds__(256) split_f32_kernel(const float* __restrict_
         split16(x[i], scale, hi[i], lo[i]);
 }
 
-// Sub-sampling pattern of the plane-mean estimate: runs of kRun consecutive quads (2 KB, so DRAM
+// Sub-sampling pattern of the plane-mean estimate: runs of kRun consecutive quads (512 B, so DRAM
 // sectors are fully used) out of every `stride` runs.  The k-th sampled quad of a chunk sits at
 // (k / kRun) * kRun * stride + k % kRun.
-constexpr int kRun = 128;
+constexpr int kRun = 32;
 __host__ __device__ __forceinline__ int64_t sample_index(int64_t k, int stride) {
     return (k / kRun) * kRun * stride + (k % kRun);
 }
@@ -729,6 +729,47 @@ __global__ void __launch_bounds__(256) ipt_sums_kernel(const float* __restrict__
     }
 }
 
+// The same estimate in one launch for the folded path: one CTA per image visits the sampled quads of all chunks
+// (warp w takes chunks w, w+8, ...), reduces the three plane sums and writes mu / dc itself.  8192 tiny CTAs plus a
+// finalising launch cost more than the arithmetic.
+__global__ void __launch_bounds__(256) ipt_means_kernel(const float* __restrict__ rgb, float* __restrict__ mu,
+                                                        float* __restrict__ dc, int64_t plane4, int stride, Mat3 A, Mat3 B,
+                                                        float inv_count, float dc_factor) {
+    __shared__ float red[8];
+    const int64_t img = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per = (plane4 + kSumChunks - 1) / kSumChunks;
+    const float4* src = reinterpret_cast<const float4*>(rgb) + img * 3 * plane4;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int c = warp; c < kSumChunks; c += 8) {
+        const int64_t beg = c * per, len = min(plane4, beg + per) - beg;
+        for (int64_t k = lane;; k += 32) {
+            const int64_t i = sample_index(k, stride);
+            if (i >= len) break;
+            const float4 c0 = ld_stream(src + beg + i), c1 = ld_stream(src + plane4 + beg + i),
+                         c2 = ld_stream(src + 2 * plane4 + beg + i);
+            const float r[4] = {c0.x, c0.y, c0.z, c0.w}, g[4] = {c1.x, c1.y, c1.z, c1.w}, b[4] = {c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o0, o1, o2;
+                rgb_px_to_ipt(r[j], g[j], b[j], A, B, o0, o1, o2);
+                s0 += o0; s1 += o1; s2 += o2;
+            }
+        }
+    }
+    s0 = block_sum_256(s0, red);
+    s1 = block_sum_256(s1, red);
+    s2 = block_sum_256(s2, red);
+    if (threadIdx.x == 0) {
+        const float m[3] = {s0 * inv_count, s1 * inv_count, s2 * inv_count};
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            mu[img * 3 + p] = m[p];
+            dc[img * 3 + p] = m[p] * dc_factor;
+        }
+    }
+}
+
 // util.py:70-82 rgb_to_ipt, writing the centred, scaled fp16 hi/lo operand planes of the forward GEMM
 __global__ void __launch_bounds__(256) rgb_to_ipt_split_kernel(const float* __restrict__ rgb, const float* __restrict__ mus,
                                                                __half* __restrict__ hi, __half* __restrict__ lo,
@@ -814,7 +855,7 @@ using namespace dcta;
 // Scales of the split operands (powers of two, exact): images/IPT 2^8, forward intermediate 2^6,
 // coefficient planes 2^4, inverse intermediate 2^6; basis 2^10 (folded into row_scale / alpha).
 static const float kScaleX = 256.f, kScaleP = 64.f, kScaleY = 16.f, kScaleQ = 64.f, kScaleBasis = 1024.f;
-static const int kSumStride = 16;  // plane-mean estimate from every 16th run of 128 quads (any estimate is exact: it is added back)
+static const int kSumStride = 64;  // plane-mean estimate from every 64th run of 32 quads: 4096 pixels of a 512^2 plane (any estimate is exact: it is added back)
 
 extern "C" int dcta_gemm_split(const void* a_hi, const void* a_lo, int a_rows, int64_t a_ld, int64_t a_batch_stride,
                                const void* b_hi, const void* b_lo, int b_rows, int64_t b_ld, int64_t b_batch_stride,
@@ -883,11 +924,10 @@ namespace dcta {
 const float* launch_ipt_plane_means(const float* rgb, float* sums_scratch, float* dc, int64_t n_img, int h, int w,
                                     const Mat3& A, const Mat3& B, cudaStream_t st) {
     const int64_t plane = (int64_t)h * w;
-    ipt_sums_kernel<<<dim3(kSumChunks, (unsigned)n_img), 256, 0, st>>>(rgb, sums_scratch, plane / 4, kSumStride, A, B);
     const float inv_count = 1.0f / (4.0f * (float)sampled_quads(plane / 4, kSumStride));
     float* mus = sums_scratch + n_img * 3 * kSumChunks;
-    finalize_means_kernel<<<(unsigned)ceil_div(n_img * 3, 128), 128, 0, st>>>(sums_scratch, mus, dc, n_img * 3, inv_count,
-                                                                              sqrtf((float)h * (float)w));
+    ipt_means_kernel<<<(unsigned)n_img, 256, 0, st>>>(rgb, mus, dc, plane / 4, kSumStride, A, B, inv_count,
+                                                      sqrtf((float)h * (float)w));
     return mus;
 }
 const float* launch_plane_means(const float* x, float* sums_scratch, float* dc, int64_t n_planes, int h, int w,
