@@ -303,3 +303,13 @@ def test_fast_pth_writer_is_a_valid_torch_archive(D):
     for odd in (big.t(), torch.empty(0, 3)):                  # non-contiguous / empty: plain torch.save
         y = torch.load(io.BytesIO(D.shards._save_tensor(odd)), weights_only=True)
         assert y.shape == odd.shape and torch.equal(y, odd)
+
+
+def test_numa_binding_is_a_noop_without_a_gpu(D):
+    """util.bind_to_gpu_numa must never raise or change the affinity when the topology cannot be read."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a host without CUDA")
+    before = os.sched_getaffinity(0)
+    assert D.util.gpu_numa_cpus() is None
+    assert D.util.bind_to_gpu_numa() is False
+    assert os.sched_getaffinity(0) == before
