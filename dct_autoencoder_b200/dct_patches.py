@@ -74,7 +74,8 @@ class DCTPatches:
     def to(self, what) -> "DCTPatches":
         """In place, returns self (dct_patches.py:44-51).  A dtype only applies to ``patches``
         semantics-wise in the reference too (bool/int tensors follow torch's .to rules)."""
-        self.patches = self.patches.to(what)
+        if self.patches is not None:            # None on the fused encode path (codes only)
+            self.patches = self.patches.to(what)
         self.key_pad_mask = self.key_pad_mask.to(what)
         if self._attn_mask is not None:
             self._attn_mask = self._attn_mask.to(what)
@@ -92,16 +93,18 @@ class DCTPatches:
         return self._row_num_images
 
     def __repr__(self):
-        return (f"DCTPatches(patches={tuple(self.patches.shape)}, images={len(self.patch_sizes or [])}, "
-                f"device={self.patches.device})")
+        shape = tuple(self.patches.shape) if self.patches is not None else None
+        return (f"DCTPatches(patches={shape}, rows x slots={tuple(self.key_pad_mask.shape)}, "
+                f"images={len(self.patch_sizes or [])}, device={self.key_pad_mask.device})")
 
 
 def to_dict(dct_patches: DCTPatches, codes: torch.Tensor):
     """dct_patches.py:54-87: per image ``{size, original_size, codes: [{c, h, w, data}]}``.
     One bulk device->host copy instead of ``.item()`` per token."""
     b, s, _ = codes.shape
-    assert b == dct_patches.patches.shape[0]
-    assert s == dct_patches.patches.shape[1]
+    # the reference asserts against patches.shape[:2]; key_pad_mask has the same (rows, slots) and is
+    # also there for the code-only batches of the fused encode path (patches is None)
+    assert (b, s) == tuple(dct_patches.key_pad_mask.shape)
     ids = dct_patches.batched_image_ids.cpu()
     pad = dct_patches.key_pad_mask.cpu()
     ch = dct_patches.patch_channels.cpu()

@@ -13,7 +13,7 @@ Additions that the reference does not have (its API is per-image):
 ``postprocess_batch``.  They produce exactly what the per-image path followed by
 ``iter_batches(batch_size=None)`` / ``postprocess`` produces.
 """
-import os
+from collections import OrderedDict
 from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -70,7 +70,12 @@ class DCTAutoencoderFeatureExtractor:
         self.channel_importances = torch.Tensor(channel_importances)
         self.patch_sample_magnitude_weight = patch_sample_magnitude_weight
         self.device = torch.device(device) if device is not None else None
-        self._table_cache: Dict[bytes, torch.Tensor] = {}
+        # small device tables (segment lists, row bases) keyed by (device, contents), least recently used
+        # evicted first; `_keepalive`, when a list, collects every table handed out (GraphedRoundtrip keeps
+        # the ones its captured kernels point at alive for as long as the graph exists)
+        self._table_cache: "OrderedDict[Tuple[str, bytes], torch.Tensor]" = OrderedDict()
+        self._table_cache_size = 64
+        self._keepalive: Optional[List[torch.Tensor]] = None
         self._maxabs: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ helpers
@@ -231,15 +236,32 @@ class DCTAutoencoderFeatureExtractor:
                 blobs.append(np.zeros(pad, np.uint8))
             cur += len(part) + pad
         blob = np.concatenate(blobs) if cur else np.zeros(16, np.uint8)
-        key = blob.tobytes() if extra is None else None
-        if key is not None and key in self._table_cache:
-            return self._table_cache[key], offs
-        dev = torch.from_numpy(blob).pin_memory().to(device, non_blocking=True)
-        if key is not None:
-            if len(self._table_cache) > 16:
-                self._table_cache.clear()
-            self._table_cache[key] = dev
-        return dev, offs
+        key = (str(torch.device(device)), blob.tobytes()) if extra is None else None
+        return self._cached_table(key, blob, device), offs
+
+    def _cached_table(self, key, host: np.ndarray, device) -> torch.Tensor:
+        """Device copy of a small host table, cached per (device, contents) with LRU eviction."""
+        dev = self._table_cache.get(key) if key is not None else None
+        if dev is None:
+            dev = torch.from_numpy(host).pin_memory().to(device, non_blocking=True)
+            if key is not None:
+                self._table_cache[key] = dev
+                while len(self._table_cache) > self._table_cache_size:
+                    self._table_cache.popitem(last=False)
+        else:
+            self._table_cache.move_to_end(key)
+        if self._keepalive is not None:
+            self._keepalive.append(dev)
+        return dev
+
+    def _check_ks(self, ks: Sequence[int], b: int, n_tok: int) -> List[int]:
+        """Caller-supplied token counts: one per image, 1 <= k <= min(tokens of the image, max_seq_len)
+        (FE:429-435 never produces anything else; the pack kernels index `order[img, :k]`)."""
+        ks = [int(k) for k in ks]
+        assert len(ks) == b, f"{len(ks)} token counts for {b} images"
+        lim = min(n_tok, self.max_seq_len)
+        assert all(1 <= k <= lim for k in ks), f"token counts must lie in [1, {lim}]"
+        return ks
 
     def _alloc_batch(self, n_rows: int, device):
         s, z = self.max_seq_len, self.patch_size ** 2
@@ -287,8 +309,7 @@ class DCTAutoencoderFeatureExtractor:
         n_tok = th * tw * c
         if ks is None:
             ks = [self._choose_k(n_tok) for _ in range(b)]
-        ks = [int(k) for k in ks]
-        assert len(ks) == b and all(1 <= k <= min(n_tok, self.max_seq_len) for k in ks)
+        ks = self._check_ks(ks, b, n_tok)
         kmax, z = max(ks), self.patch_size ** 2
         patches = torch.empty((b, kmax, z), dtype=torch.float32, device=x.device)
         pos = torch.empty((b, kmax, 2), dtype=torch.int64, device=x.device)
@@ -323,6 +344,7 @@ class DCTAutoencoderFeatureExtractor:
         n_tok = th * tw * c
         if ks is None:
             ks = [self._choose_k(n_tok) for _ in range(b)]
+        ks = self._check_ks(ks, b, n_tok)
         state = self._next_fit(ks)
         rows = state.rows + ([state.row] if state.row else [])
         tab, offs = self._tables(rows, dict(enumerate(ks)), x.device)
@@ -340,13 +362,15 @@ class DCTAutoencoderFeatureExtractor:
                           _data={}, _row_num_images=[len(r) for r in rows])
 
     # ------------------------------------------------------------------ fused PatchNorm + LFQ path
-    @staticmethod
-    def _lfq_fusable(norm, lfq) -> bool:
-        """Projection-free LFQ in eval mode on frozen (or eval) fp32 PatchNorm tables."""
+    def _lfq_fusable(self, norm, lfq) -> bool:
+        """Projection-free LFQ in eval mode on frozen (or eval) fp32 PatchNorm tables that were built for
+        this extractor's token geometry."""
         return (getattr(lfq, "has_projections", True) is False and not lfq.training
                 and (norm.frozen or not norm.training)
+                and norm.channels == self.channels and norm.patch_size == self.patch_size
                 and lfq.num_codebooks * lfq.codebook_dim == norm.patch_size ** 2 <= 256
-                and norm.median.dtype == torch.float32 and norm.median.is_cuda)
+                and norm.median.dtype == torch.float32 and norm.median.is_cuda
+                and norm.b.dtype == torch.float32 and norm.b.device == norm.median.device)
 
     @torch.no_grad()
     def process_batch_to_codes(self, images: torch.Tensor, norm, lfq, ks: Optional[Sequence[int]] = None):
@@ -355,12 +379,14 @@ class DCTAutoencoderFeatureExtractor:
         codes (rows, s, codebooks) int64), bit-identical to the staged calls."""
         assert self._lfq_fusable(norm, lfq)
         x = to_device_f32(images, self._dev(images))
+        if norm.median.device != x.device:
+            raise _lib.DctaError(f"PatchNorm tables live on {norm.median.device}, the images on {x.device}")
         b, c, h, w = x.shape
         ph, pw, th, tw = self._geometry(h, w)
         p = self.patch_size
         n_tok = th * tw * c
         # one codebook per patch row on the folded tensor-core path: the DCT epilogue emits the code words itself
-        in_epilogue = (os.environ.get("DCTA_NO_EPILOGUE_CODES") is None and self.dct_impl == "tc" and c == 3 and not self._hooks_overridden("_transform_image_in")
+        in_epilogue = (self.dct_impl == "tc" and c == 3 and not self._hooks_overridden("_transform_image_in")
                        and lfq.num_codebooks == p and lfq.codebook_dim == p
                        and th <= norm.max_patch_h and tw <= norm.max_patch_w
                        and bool(_lib.load().dcta_fold_codes_supported(h, w, th * p, tw * p, p)))
@@ -378,6 +404,7 @@ class DCTAutoencoderFeatureExtractor:
             order = self._sorted_order(tiles, maxabs)
         if ks is None:
             ks = [self._choose_k(n_tok) for _ in range(b)]
+        ks = self._check_ks(ks, b, n_tok)
         state = self._next_fit(ks)
         rows = state.rows + ([state.row] if state.row else [])
         tab, offs = self._tables(rows, dict(enumerate(ks)), x.device)
@@ -406,6 +433,8 @@ class DCTAutoencoderFeatureExtractor:
         batch = DCTPatches(patches=None, key_pad_mask=pad, batched_image_ids=ids, patch_channels=chan,
                            patch_positions=pos, patch_sizes=[(ph, pw)] * b, original_sizes=[(h, w)] * b,
                            _data={}, _row_num_images=[len(r) for r in rows])
+        if not lfq.keep_num_codebooks_dim:       # lfq.py:224-225: a single codebook loses its axis
+            codes = codes[..., 0]
         return batch, codes
 
     @torch.no_grad()
@@ -414,6 +443,10 @@ class DCTAutoencoderFeatureExtractor:
         de-quantised patches kept in registers; same-size batches, tensor-core DCT path."""
         assert self._lfq_fusable(norm, lfq) and self.dct_impl in ("tc", "tc_plain")
         assert len(set(map(tuple, x.original_sizes))) == 1 and len(set(map(tuple, x.patch_sizes))) == 1
+        if not lfq.keep_num_codebooks_dim:       # lfq.py:106-107
+            codes = codes[..., None]
+        if norm.median.device != codes.device:
+            raise _lib.DctaError(f"PatchNorm tables live on {norm.median.device}, the codes on {codes.device}")
         (idx, rgb), = self._decode_groups(x, codes=codes.contiguous(), norm=norm, lfq=lfq)
         return rgb
 
@@ -517,11 +550,7 @@ class DCTAutoencoderFeatureExtractor:
         if b > 1:
             base[1:] = np.cumsum(counts[:-1])
         dev = x.key_pad_mask.device
-        key = b"base" + base.tobytes()
-        base_dev = self._table_cache.get(key)
-        if base_dev is None or base_dev.device != dev:
-            base_dev = torch.from_numpy(base).pin_memory().to(dev, non_blocking=True)
-            self._table_cache[key] = base_dev
+        base_dev = self._cached_table((str(dev), b"base" + base.tobytes()), base, dev)
         slot_map = torch.empty((n_img, self.channels, th, tw), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.call("dcta_build_slot_map", _lib.ptr(x.patch_channels), _lib.ptr(x.patch_positions),

@@ -177,14 +177,23 @@ class GraphedRoundtrip:
         cur = torch.cuda.current_stream(images.device)
         side = torch.cuda.Stream(images.device)
         side.wait_stream(cur)
-        with torch.cuda.stream(side):              # warm caches (tables, tensor maps, function attributes)
-            for _ in range(warmup):
-                pipe.roundtrip(images, ks, fused)
-        cur.wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        l0 = _lib.launch_count
-        with torch.cuda.graph(self.graph):
-            self.rec, self.codes = pipe.roundtrip(images, ks, fused)
+        # The captured kernels hold raw pointers to the extractor's cached packing tables, which are created
+        # outside the capture's private pool: keep a strong reference to every table handed out while warming
+        # up and capturing, so that a later cache eviction cannot free memory the graph still reads.
+        fe = pipe.extractor
+        saved, fe._keepalive = fe._keepalive, []
+        try:
+            with torch.cuda.stream(side):          # warm caches (tables, tensor maps, function attributes)
+                for _ in range(warmup):
+                    pipe.roundtrip(images, ks, fused)
+            cur.wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count
+            with torch.cuda.graph(self.graph):
+                self.rec, self.codes = pipe.roundtrip(images, ks, fused)
+            self._tables = list(fe._keepalive)
+        finally:
+            fe._keepalive = saved
         self.launches = _lib.launch_count - l0     # kernels per replay
         self._lib = _lib
 

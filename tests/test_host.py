@@ -313,3 +313,67 @@ def test_numa_binding_is_a_noop_without_a_gpu(D):
     assert D.util.gpu_numa_cpus() is None
     assert D.util.bind_to_gpu_numa() is False
     assert os.sched_getaffinity(0) == before
+
+
+def test_to_dict_from_dict_match_the_reference_fixture(D, golden):
+    """to_dict / from_dict (DP:54-122) against the UNMODIFIED reference's output on a packed 3-image batch
+    (tests/golden/make_golden_configs.py).  Host tensors: these two functions are plain serialisation.  Also covers
+    the code-only batches of the fused encode path (patches=None), which `to`, `repr` and `to_dict` must accept."""
+    import json
+    g = golden("to_dict")
+    want = json.load(open(os.path.join(ROOT, "tests", "golden", "to_dict.json")))
+    t = torch.from_numpy
+    for patches in (torch.zeros(tuple(g["patches_shape"])), None):
+        dp = D.DCTPatches(patches=patches, key_pad_mask=t(g["key_pad_mask"]), batched_image_ids=t(g["image_ids"]),
+                          patch_channels=t(g["channels"]), patch_positions=t(g["positions"]),
+                          patch_sizes=[tuple(x) for x in g["patch_sizes"].tolist()],
+                          original_sizes=[tuple(x) for x in g["original_sizes"].tolist()])
+        got = D.to_dict(dp, t(g["codes"]))
+        assert json.loads(json.dumps(got)) == want
+        assert "DCTPatches(" in repr(dp)
+        assert dp.to("cpu") is dp
+    dp1, codes1 = D.from_dict(want[1])
+    assert torch.equal(codes1, t(g["fd_codes"])) and codes1.dtype == torch.int64
+    for ours, key in ((dp1.patch_channels, "fd_channels"), (dp1.patch_positions, "fd_positions"),
+                      (dp1.key_pad_mask, "fd_key_pad_mask"), (dp1.batched_image_ids, "fd_image_ids"),
+                      (dp1.attn_mask, "fd_attn_mask"), (dp1.patches, "fd_patches")):
+        assert ours.dtype == t(g[key]).dtype and torch.equal(ours, t(g[key])), key
+    assert dp1.patch_sizes == [want[1]["size"]] and dp1.original_sizes == [want[1]["original_size"]]
+    # round trip through our own pair
+    assert D.to_dict(dp1, codes1[None])[0]["codes"] == want[1]["codes"]
+
+
+def test_caller_supplied_token_counts_are_validated(D):
+    """process_batch / process_batch_to_codes index order[img, :k]: k beyond the image's own token count (or a wrong
+    number of ks) must be refused on the host, before any kernel sees it."""
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+    n_tok = 9 * 8 * 3
+    assert fe._check_ks([1, n_tok], 2, n_tok) == [1, n_tok]
+    for bad in ([n_tok + 1, 5], [0, 5], [5], [5, 5, 5]):
+        with pytest.raises(AssertionError):
+            fe._check_ks(bad, 2, n_tok)
+    with pytest.raises(AssertionError):
+        D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 100)._check_ks([101], 1, n_tok)
+
+
+def test_table_cache_is_keyed_by_device_and_evicts_lru(D):
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072)
+    fe._table_cache_size = 3
+    made = []
+    orig = torch.Tensor.pin_memory
+    # no GPU here: exercise the cache logic with CPU "device" copies
+    torch.Tensor.pin_memory = lambda self: self
+    try:
+        for i in range(5):
+            fe._cached_table(("cpu", bytes([i])), np.full(4, i, np.uint8), "cpu")
+        assert list(k[1] for k in fe._table_cache) == [bytes([2]), bytes([3]), bytes([4])]
+        a = fe._cached_table(("cpu", bytes([2])), np.full(4, 2, np.uint8), "cpu")      # hit: becomes most recent
+        fe._cached_table(("cpu", bytes([9])), np.full(4, 9, np.uint8), "cpu")
+        assert bytes([2]) in [k[1] for k in fe._table_cache] and bytes([3]) not in [k[1] for k in fe._table_cache]
+        b = fe._cached_table(("other", bytes([2])), np.full(4, 2, np.uint8), "cpu")     # same bytes, other device
+        assert a is not b
+        fe._keepalive = []
+        c = fe._cached_table(("cpu", bytes([2])), np.full(4, 2, np.uint8), "cpu")
+        assert fe._keepalive == [c] and c is a
+    finally:
+        torch.Tensor.pin_memory = orig
