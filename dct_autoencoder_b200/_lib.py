@@ -9,7 +9,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcta.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class DctaError(RuntimeError):
@@ -30,6 +30,8 @@ SIGNATURES = {
     "dcta_compiled_arch": [],
     "dcta_rgb_to_ipt": [P, P, c_int64, c_int64, P, P, P],
     "dcta_ipt_to_rgb": [P, P, c_int64, c_int64, P, P, P],
+    "dcta_u8_to_unit_f32": [P, P, c_int64, P],
+    "dcta_unit_f32_to_u8": [P, P, c_int64, P],
     "dcta_dct2_fwd": [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "dcta_dct2_inv": [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_gemm_split": [P, P, c_int, c_int64, c_int64, P, P, c_int, c_int64, c_int64, c_int, c_int64, P, c_float,
@@ -46,8 +48,9 @@ SIGNATURES = {
     "dcta_fold_supported": [c_int, c_int, c_int, c_int],
     "dcta_fold_codes_supported": [c_int, c_int, c_int, c_int, c_int],
     "dcta_rgb_to_ipt_fold": [P, P, P, P, P, c_int64, c_int, c_int, P, P, P],
+    "dcta_rgb_u8_to_ipt_fold": [P, P, P, P, P, c_int64, c_int, c_int, P, P, P],
     "dcta_fold_planes": [P, P, P, P, P, c_int64, c_int, c_int, P],
-    "dcta_dct2_fwd_fold": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "dcta_dct2_fwd_fold": [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "dcta_dct2_fwd_fold_codes": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_float, c_float, c_float, P,
                                  c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "dcta_pack_codes_grid": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float,
@@ -57,8 +60,9 @@ SIGNATURES = {
     "dcta_decode_codes_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P, P],
     "dcta_fold_coef_planes": [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
-    "dcta_dct2_inv_fold": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
+    "dcta_dct2_inv_fold": [P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_unfold_ipt_to_rgb": [P, P, P, c_int64, c_int, c_int, P, P, P],
+    "dcta_unfold_ipt_to_rgb_u8": [P, P, P, c_int64, c_int, c_int, P, P, P],
     "dcta_unfold_planes": [P, P, P, c_int64, c_int, c_int, P],
     "dcta_patchify": [P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "dcta_tile_scores": [P, P, c_int64, c_int, c_int, c_int, c_int, c_float, P, P],
@@ -93,11 +97,10 @@ SIGNATURES = {
 }
 _RESTYPES = {"dcta_last_error": c_char_p}
 REDUCE_SCRATCH = 2048  # DCTA_REDUCE_SCRATCH
-CHAIN_SCRATCH = 4096   # DCTA_CHAIN_SCRATCH
 
 # kernels launched by one call of each entry point (memsets not counted)
 KERNELS_PER_CALL = {
-    "dcta_rgb_to_ipt": 1, "dcta_ipt_to_rgb": 1, "dcta_dct2_fwd": 2, "dcta_dct2_inv": 2, "dcta_patchify": 1,
+    "dcta_rgb_to_ipt": 1, "dcta_ipt_to_rgb": 1, "dcta_u8_to_unit_f32": 1, "dcta_unit_f32_to_u8": 1, "dcta_dct2_fwd": 2, "dcta_dct2_inv": 2, "dcta_patchify": 1,
     "dcta_tile_scores": 1, "dcta_sort_tokens": 1, "dcta_pack_tiles": 1, "dcta_pack_lists": 1,
     "dcta_patchnorm_apply": 1, "dcta_patchnorm_build_lists": 4, "dcta_patchnorm_batch_median": 1,
     "dcta_patchnorm_update_median": 1, "dcta_patchnorm_abs_dev": 1, "dcta_patchnorm_update_b": 2,
@@ -109,7 +112,7 @@ KERNELS_PER_CALL = {
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,
     "dcta_row_sumsq": 1, "dcta_split_rows": 1, "dcta_vq_nearest_tc": 2,
     "dcta_pack_codes_lfq": 2, "dcta_decode_codes_split": 1,
-    "dcta_fold_supported": 0, "dcta_fold_codes_supported": 0, "dcta_rgb_to_ipt_fold": 2, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
+    "dcta_fold_supported": 0, "dcta_fold_codes_supported": 0, "dcta_rgb_to_ipt_fold": 2, "dcta_rgb_u8_to_ipt_fold": 2, "dcta_unfold_ipt_to_rgb_u8": 1, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
     "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 2, "dcta_fold_coef_planes": 1, "dcta_dct2_inv_fold": 2,
     "dcta_unfold_ipt_to_rgb": 1, "dcta_unfold_planes": 1, "dcta_sort_tokens_maxabs": 1, "dcta_dct2_fwd_fold_codes": 3, "dcta_pack_codes_grid": 2,
 }

@@ -17,5 +17,5 @@ void set_error(const char* fmt, ...) {
 }  // namespace dcta
 
 extern "C" const char* dcta_last_error(void) { return dcta::g_err; }
-extern "C" int dcta_abi_version(void) { return 1; }
+extern "C" int dcta_abi_version(void) { return 2; }
 extern "C" int dcta_compiled_arch(void) { return 100; }

@@ -15,9 +15,15 @@ __device__ __forceinline__ void convert_px(float r, float g, float b, const Mat3
     float m = fmaf(A.m[5], b, fmaf(A.m[4], g, A.m[3] * r));
     float s = fmaf(A.m[8], b, fmaf(A.m[7], g, A.m[6] * r));
     const float gamma = kToIpt ? 0.43f : (float)(1.0 / 0.43);
-    l = signed_pow(l, gamma);
-    m = signed_pow(m, gamma);
-    s = signed_pow(s, gamma);
+    if (kToIpt) {      // forward: accurate exp2 (errors here are summed coherently by the whole-image DCT)
+        l = signed_pow_fwd(l, gamma);
+        m = signed_pow_fwd(m, gamma);
+        s = signed_pow_fwd(s, gamma);
+    } else {
+        l = signed_pow(l, gamma);
+        m = signed_pow(m, gamma);
+        s = signed_pow(s, gamma);
+    }
     o0 = fmaf(B.m[2], s, fmaf(B.m[1], m, B.m[0] * l));
     o1 = fmaf(B.m[5], s, fmaf(B.m[4], m, B.m[3] * l));
     o2 = fmaf(B.m[8], s, fmaf(B.m[7], m, B.m[6] * l));
@@ -87,7 +93,39 @@ int launch_colorspace(const float* in, float* out, int64_t n_img, int64_t plane,
     return check_launch("colorspace");
 }
 
+// 8-bit pixels <-> unit-range floats (the conversions the reference's callers do around the path; common.cuh)
+__global__ void __launch_bounds__(256) u8_to_unit_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+        st_stream(reinterpret_cast<float4*>(out) + i, ld_px4(in, i));
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[n4 * 4 + threadIdx.x] = u8_to_unit(in[n4 * 4 + threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) unit_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int64_t n) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+        st_px4(out, i, ld_stream(reinterpret_cast<const float4*>(in) + i));
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[n4 * 4 + threadIdx.x] = (uint8_t)unit_to_u8(in[n4 * 4 + threadIdx.x]);
+}
+
 }  // namespace dcta
+
+extern "C" int dcta_u8_to_unit_f32(const uint8_t* in, float* out, int64_t n, void* stream) {
+    DCTA_REQUIRE(in && out && n >= 0, "u8_to_unit_f32: bad arguments");
+    DCTA_REQUIRE((reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "u8_to_unit_f32: needs a 4-byte aligned input and a 16-byte aligned output");
+    if (n == 0) return DCTA_OK;
+    dcta::u8_to_unit_kernel<<<dcta::grid_for(n / 4 + 1, 256), 256, 0, dcta::as_stream(stream)>>>(in, out, n);
+    return dcta::check_launch("u8_to_unit_f32");
+}
+
+extern "C" int dcta_unit_f32_to_u8(const float* in, uint8_t* out, int64_t n, void* stream) {
+    DCTA_REQUIRE(in && out && n >= 0, "unit_f32_to_u8: bad arguments");
+    DCTA_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+                 "unit_f32_to_u8: needs a 16-byte aligned input and a 4-byte aligned output");
+    if (n == 0) return DCTA_OK;
+    dcta::unit_to_u8_kernel<<<dcta::grid_for(n / 4 + 1, 256), 256, 0, dcta::as_stream(stream)>>>(in, out, n);
+    return dcta::check_launch("unit_f32_to_u8");
+}
 
 extern "C" int dcta_rgb_to_ipt(const float* rgb, float* ipt, int64_t n_img, int64_t plane,
                                const float* m_rgb2lms_host, const float* m_ipt_host, void* stream) {

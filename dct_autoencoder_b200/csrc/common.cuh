@@ -61,6 +61,35 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                  : "memory");
 }
 
+// uint8 pixel -> float in [0, 1], bit-identical to torch's `u8_tensor / 255` (an IEEE fp32 division; what the
+// reference's callers do with torchvision.io.read_image, decode_gif.py:22, testpipe.py:17): q = u * fl(1/255) is off
+// by one ulp for 126 of the 256 values; one FMA residual + one FMA correction rounds all 256 correctly.
+__device__ __forceinline__ float u8_to_unit(uint32_t u) {
+    const float uf = (float)u, r = 1.0f / 255.0f;
+    const float q = uf * r;
+    return fmaf(fmaf(-q, 255.0f, uf), r, q);
+}
+// float -> uint8 as torchvision.utils.save_image stores it (what the reference's callers do with a reconstruction,
+// testpipe.py:74-75): clamp(0, 1) * 255 + 0.5, clamp to [0, 255], truncate.  NaN -> 0.
+__device__ __forceinline__ uint32_t unit_to_u8(float v) {
+    const float c = fminf(fmaxf(v, 0.0f), 1.0f);
+    return (uint32_t)__float2int_rz(__fadd_rn(__fmul_rn(c, 255.0f), 0.5f));
+}
+// four consecutive pixels of one channel plane, in units of 4 pixels (float4 for fp32 planes, one 32-bit word for uint8)
+__device__ __forceinline__ float4 ld_px4(const float* plane, int64_t i4) {
+    return ld_stream(reinterpret_cast<const float4*>(plane) + i4);
+}
+__device__ __forceinline__ float4 ld_px4(const uint8_t* plane, int64_t i4) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(plane) + i4);
+    return make_float4(u8_to_unit(v & 255u), u8_to_unit((v >> 8) & 255u), u8_to_unit((v >> 16) & 255u), u8_to_unit(v >> 24));
+}
+__device__ __forceinline__ void st_px4(float* plane, int64_t i4, const float4& v) {
+    st_stream(reinterpret_cast<float4*>(plane) + i4, v);
+}
+__device__ __forceinline__ void st_px4(uint8_t* plane, int64_t i4, const float4& v) {
+    reinterpret_cast<uint32_t*>(plane)[i4] = unit_to_u8(v.x) | (unit_to_u8(v.y) << 8) | (unit_to_u8(v.z) << 16) | (unit_to_u8(v.w) << 24);
+}
+
 // sign(v) * |v|^g as exp2(g * log2|v|) on the special-function unit (MUFU.LG2 / MUFU.EX2):
 // |log2 error| <= 2^-21.4 on [0.5, 2] and 2 ulp elsewhere, exp2 2 ulp, i.e. <= ~4e-7 relative for the
 // exponents used here (0.43 and 1/0.43) at a tenth of the instructions of powf(), which keeps the colour
@@ -70,6 +99,33 @@ __device__ __forceinline__ float signed_pow(float v, float g) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fabsf(v)));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(g * l));
     return v < 0.0f ? -a : a;
+}
+
+// The same with the exp2 evaluated by a degree-6 polynomial on the FMA pipe (truncation 2e-9, fp32 Horner rounding
+// <= 1e-7, pseudo-random) and the product g * log2|v| carried with its FMA residual.  MUFU.EX2's 2^-22 relative error
+// is a smooth function of its argument: over a natural image it is spatially correlated, and the whole-image DCT sums
+// correlated input errors coherently into the low-frequency coefficients (measured: 4.4e-7 * max|Y| on the
+// reference's images/ at 256^2 with MUFU.EX2, against 4e-7 stated).  Used by the FORWARD colour transform only; the
+// decode side ends at the pixels, where nothing accumulates.
+__device__ __forceinline__ float signed_pow_fwd(float v, float g) {
+    float l;
+    const float av = fabsf(v);
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(av));
+    float t_hi = g * l;
+    const float t_lo = fmaf(g, l, -t_hi);
+    t_hi = fminf(fmaxf(t_hi, -126.0f), 126.0f);
+    const float magic = 12582912.0f;                  // 1.5 * 2^23: the sum holds round(t_hi) in its low mantissa bits
+    const float nm = t_hi + magic;
+    const float r = (t_hi - (nm - magic)) + t_lo;     // [-0.5, 0.5]
+    float p = 1.5370705e-4f;
+    p = fmaf(p, r, 1.3399848e-3f);
+    p = fmaf(p, r, 9.6183736e-3f);
+    p = fmaf(p, r, 5.5503290e-2f);
+    p = fmaf(p, r, 2.4022648e-1f);
+    p = fmaf(p, r, 6.9314718e-1f);
+    p = fmaf(p, r, 1.0f);
+    const float a = __int_as_float(__float_as_int(p) + (__float_as_int(nm) << 23));
+    return l < -125.0f ? 0.0f : (v < 0.0f ? -a : a);   // |v| = 0 (or subnormal): log2 = -inf -> 0, as pow does
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -747,367 +747,6 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
     if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------ chained passes
-// Both passes of a transform in ONE persistent launch, so that the intermediate operand (P^T / Q^T) is read
-// back out of L2 instead of HBM.  Possible when the two passes use the same basis (square planes, kh == kw):
-// a CTA pair keeps its basis slice resident and alternates between pass-1 tiles of sub-batch s and pass-2
-// tiles of sub-batch s-1 (a sub-batch is `ps` planes, ~20 MB of intermediate).  A pass-2 tile may only start
-// when every pass-1 tile of its sub-batch has been stored: the epilogue warps publish their tiles in a global
-// counter per sub-batch, the TMA producer of a pass-2 tile polls it.  All pairs are co-resident (grid <= SMs,
-// one CTA per SM; the launcher checks it), and every pair finishes its pass-1 tiles of sub-batch s before it
-// waits for anything of sub-batch s, so the wait cannot deadlock.
-struct ChainPass {
-    int units;          // (segment of the group, block) combinations per basis group
-    int blocks;         // blocks of `planes` planes inside one segment
-    int rpp;            // stacked rows per plane
-    int rows_per_seg;   // blocks * planes * rpp
-};
-
-struct ChainSched {
-    ChainPass p[2];
-    int planes;         // planes per block
-    int ps;             // planes per sub-batch
-    int ns;             // sub-batches
-    int lag;            // pass-2 tiles of sub-batch s are scheduled together with the pass-1 tiles of sub-batch s + lag
-    int hints;          // 1: L2 eviction priorities (operands evict-first, intermediate evict-last); 0: none
-    int32_t* done;      // [ns] pass-1 warp completions per sub-batch (zeroed by the launcher)
-};
-
-struct ChainItem {
-    int pass, sb, seg, row0;
-};
-
-struct ChainWalk {
-    const ChainSched& sc;
-    int q, P, grp;
-    int l = -1;            // current list: even l = (pass 1, sb l/2); odd l = (pass 2, sb l/2 - lag)
-    int64_t pos = 0;       // global index of the first item of the current list
-    int j = 0, cnt = 0;    // next local index / size of the current list
-    int pass = 0, sb = 0, np = 0, tpu = 1;
-    __device__ ChainWalk(const ChainSched& s, int q_, int P_, int g_) : sc(s), q(q_), P(P_), grp(g_) {}
-    __device__ int planes_in(int sb_) const { return min(sc.ps, sc.planes - sb_ * sc.ps); }
-    __device__ int list_size(int pass_, int sb_) const {
-        if (sb_ < 0 || sb_ >= sc.ns) return 0;
-        return sc.p[pass_].units * (planes_in(sb_) * sc.p[pass_].rpp / 256);
-    }
-    __device__ bool next(ChainItem& w) {
-        while (true) {
-            if (l >= 0 && j < cnt) {
-                const int u = j / tpu, i = j - u * tpu;
-                const ChainPass& cp = sc.p[pass];
-                const int sg = u / cp.blocks, blk = u - sg * cp.blocks;
-                w.pass = pass;
-                w.sb = sb;
-                w.seg = sg * 2 + grp;
-                w.row0 = (blk * sc.planes + sb * sc.ps) * cp.rpp + i * 256;
-                j += P;
-                return true;
-            }
-            if (l >= 0) pos += cnt;
-            ++l;
-            if (l >= 2 * (sc.ns + sc.lag)) return false;
-            if (l & 1) { pass = 1; sb = (l >> 1) - sc.lag; }
-            else { pass = 0; sb = l >> 1; }
-            cnt = list_size(pass, sb);
-            if (cnt > 0) {
-                np = planes_in(sb);
-                tpu = np * sc.p[pass].rpp / 256;
-            }
-            const int64_t first = ((q - pos) % P + P) % P;       // smallest local index with (pos + j) % P == q
-            j = (int)first;
-        }
-    }
-};
-
-__device__ __forceinline__ void wait_counter(const int32_t* ptr, int expected) {
-    const long long t0 = clock64();
-    while (true) {
-        int v;
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-        if (v >= expected) break;
-        if (clock64() - t0 > 4000000000ll) __trap();
-        __nanosleep(100);
-    }
-    // the tiles were written through the generic proxy by other SMs and are about to be read by TMA
-    asm volatile("fence.proxy.async.global;" ::: "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
-fold_chain_kernel(const __grid_constant__ CUtensorMap map_a1_hi, const __grid_constant__ CUtensorMap map_a1_lo,
-                  const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
-                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                  FoldGemm g, ChainSched sc, FoldEpi ep1, FoldEpi ep2) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[F_MAX_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[F_MAX_STAGES];
-    __shared__ __align__(8) uint64_t tmem_full[2];
-    __shared__ __align__(8) uint64_t tmem_empty[2];
-    __shared__ __align__(8) uint64_t basis_bar;
-    __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) int32_t col_off[2][288];
-    __shared__ __align__(16) float col_scale[2][288];
-    __shared__ __align__(16) int32_t col_grp[288];
-
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* basis_hi = smem;
-    uint8_t* basis_lo = smem + g.basis_bytes;
-    uint8_t* ring = smem + 2 * g.basis_bytes;
-    unsigned* smax = reinterpret_cast<unsigned*>(ring + g.stages * F_STAGE);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const int grp = pair & 1;                                   // one N tile per group (checked by the launcher)
-    const int pair_in_slice = pair >> 1, pairs_per_slice = n_pairs >> 1;
-    const int n_lim = g.n_valid;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&map_a1_hi);
-        tma_prefetch_desc(&map_a1_lo);
-        tma_prefetch_desc(&map_a2_hi);
-        tma_prefetch_desc(&map_a2_lo);
-        tma_prefetch_desc(&map_b_hi);
-        tma_prefetch_desc(&map_b_lo);
-        for (int s = 0; s < F_MAX_STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 16);
-        }
-        mbar_init(&basis_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = threadIdx.x; i < 2 * 288; i += blockDim.x) {
-        const int ps = i / 288, n = i - ps * 288;
-        const FoldEpi& ep = ps ? ep2 : ep1;
-        int32_t off = -1;
-        float scl = 0.f;
-        int32_t grp_v = 0;
-        if (n < n_lim) {
-            const int line = n * ep.col_mul + grp * ep.col_add;
-            if (ep.mode == 2) {
-                const int th = line / ep.p, pi = line - th * ep.p;
-                off = th * ep.tiles_w * ep.channels * ep.p * ep.p + pi * ep.p;
-                const bool ends = (n == n_lim - 1) || ((n % g.chunk_w) == g.chunk_w - 1) || ((line + ep.col_mul) / ep.p != th);
-                grp_v = th | (ends ? (int32_t)0x80000000 : 0);
-            } else {
-                off = line * ep.col_stride;
-            }
-            scl = ep.alpha * (ep.basis_scale ? __ldg(ep.basis_scale + grp * g.n_valid + n) : 1.0f);
-        }
-        col_off[ps][n] = off;
-        col_scale[ps][n] = scl;
-        if (ps) col_grp[n] = grp_v;
-    }
-    for (int i = threadIdx.x; i < g.score_groups * 128; i += blockDim.x) smax[i] = 0u;
-    if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_slot;
-
-    if (warp == 0 && lane == 0) {
-        // ---------------- TMA producer
-        const uint32_t basis_bar_leader = mapa_u32(smem_u32(&basis_bar), 0);
-        const int half_rows = g.n_tile >> 1;
-        const uint32_t btile = (uint32_t)half_rows * 64;
-        if (rank == 0) mbar_expect_tx(&basis_bar, 4 * g.basis_bytes);
-        for (int kb = 0; kb < g.num_kb; ++kb) {
-            const int row = (int)rank * half_rows;
-            tma_load_3d_2sm(&map_b_hi, basis_bar_leader, basis_hi + kb * btile, kb * FK, row, grp);
-            tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * btile, kb * FK, row, grp);
-        }
-        ChainWalk walk(sc, pair_in_slice, pairs_per_slice, grp);
-        ChainItem w;
-        uint32_t it = 0;
-        int waited_sb = -1;
-        const uint64_t pol_first = sc.hints ? l2_policy_evict_first() : l2_policy_evict_normal();   // operands are read once
-        while (walk.next(w)) {
-            if (w.pass == 1 && w.sb > waited_sb) {
-                // every pass-1 tile of this sub-batch, from both basis groups: 2 groups x tiles x 2 CTAs x 8 warps
-                wait_counter(sc.done + w.sb, 2 * walk.list_size(0, w.sb) * 16);
-                waited_sb = w.sb;
-            }
-            const CUtensorMap* mh = w.pass ? &map_a2_hi : &map_a1_hi;
-            const CUtensorMap* ml = w.pass ? &map_a2_lo : &map_a1_lo;
-            const int row0 = w.row0 + (int)rank * 128;
-            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
-                const int s = it % g.stages;
-                mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
-                uint8_t* st = ring + s * F_STAGE;
-                const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
-                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * F_STAGE);
-                tma_load_3d_2sm_hint(mh, full_leader, st, kb * FK, row0, w.seg, pol_first);
-                tma_load_3d_2sm_hint(ml, full_leader, st + F_ATILE, kb * FK, row0, w.seg, pol_first);
-            }
-        }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
-        // ---------------- MMA issuer (leader CTA only): the same basis serves both passes
-        const uint32_t idesc = fold_idesc(g.n_tile);
-        const uint32_t btile = (uint32_t)(g.n_tile >> 1) * 64;
-        const uint32_t bh = smem_u32(basis_hi), bl = smem_u32(basis_lo);
-        mbar_wait_cluster(&basis_bar, 0);
-        tc_fence_after();
-        ChainWalk walk(sc, pair_in_slice, pairs_per_slice, grp);
-        ChainItem w;
-        uint32_t it = 0, tcount = 0;
-        while (walk.next(w)) {
-            const int acc = tcount & 1;
-            mbar_wait_cluster(&tmem_empty[acc], ((tcount >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_acc = tmem_base + acc * 256;
-            for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
-                const int s = it % g.stages;
-                mbar_wait_cluster(&full_bar[s], (it / g.stages) & 1);
-                tc_fence_after();
-                const uint32_t base = smem_u32(ring + s * F_STAGE);
-#pragma unroll
-                for (int k = 0; k < FK / 16; ++k) {
-                    const uint32_t ko = k * 32;
-                    const uint64_t a_hi = smem_desc_sw64(base + ko);
-                    const uint64_t a_lo = smem_desc_sw64(base + F_ATILE + ko);
-                    const uint64_t b_hi = smem_desc_sw64(bh + kb * btile + ko);
-                    const uint64_t b_lo = smem_desc_sw64(bl + kb * btile + ko);
-                    umma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, (kb | k) ? 1u : 0u);
-                    umma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1u);
-                    umma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1u);
-                }
-                umma_commit_2sm(&empty_bar[s], 3);
-            }
-            umma_commit_2sm(&tmem_full[acc], 3);
-            ++tcount;
-        }
-    } else if (warp >= 2) {
-        // ---------------- epilogue warps
-        const int quarter = warp & 3, chalf = (warp - 2) >> 2;
-        const int cwid = g.chunk_w;
-        const int n_chunks = (n_lim + cwid - 1) / cwid;
-        const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
-        const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
-        ChainWalk walk(sc, pair_in_slice, pairs_per_slice, grp);
-        ChainItem w;
-        uint32_t tcount = 0;
-        // the intermediate is read back within microseconds: keep it in L2; the final output is not read here
-        const uint64_t pol_last = sc.hints ? l2_policy_evict_last() : l2_policy_evict_normal();
-        const uint64_t pol_first = sc.hints ? l2_policy_evict_first() : l2_policy_evict_normal();
-        // A finished pass-1 tile is published (fence + counter) only after the wait for the NEXT accumulator:
-        // by then its stores have drained, so the fence does not stall the epilogue.  The next tile must not
-        // depend on the pending publication (a pass-2 tile of the same or a later sub-batch would wait for it
-        // in the producer while we wait for its accumulator): then publish first.
-        int pending_sb = -1;
-        auto publish = [&]() {
-            if (pending_sb >= 0) {
-                asm volatile("fence.proxy.async.global;" ::: "memory");
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(sc.done + pending_sb, 1);
-                pending_sb = -1;
-            }
-        };
-        while (walk.next(w)) {
-            const FoldEpi& ep = w.pass ? ep2 : ep1;
-            const int rows_per_seg = sc.p[w.pass].rows_per_seg;
-            const int r = w.row0 + (int)rank * 128 + quarter * 32 + lane;   // stacked row
-            const bool row_ok = r < rows_per_seg;
-            const int item = r / ep.rows_per_item, rin = r - item * ep.rows_per_item;
-            const bool scoring = w.pass == 1 && g.score_groups > 0;
-            int64_t base;
-            ScoreCtx sctx{};
-            if (ep.mode == 2) {
-                const int img = item / ep.channels, ch = item - img * ep.channels;
-                const int tw = rin / ep.p, pj = rin - tw * ep.p;
-                const int64_t tok0 = ((int64_t)img * ep.tiles_h * ep.tiles_w + tw) * ep.channels + ch;
-                base = tok0 * (ep.p * ep.p) + pj;
-                sctx.smax = smax + quarter * 32 + lane;
-            } else {
-                base = (int64_t)w.seg * ep.seg_stride + (int64_t)item * ep.item_stride + rin;
-            }
-            const bool dc_slice = (ep.dc != nullptr) && grp == 0;
-            const float dcv = (dc_slice && row_ok && rin == 0) ? __ldg(ep.dc + item) : 0.0f;
-            const uint64_t p_hi = reinterpret_cast<uint64_t>(ep.out_hi + base);
-            const uint64_t p_lo = reinterpret_cast<uint64_t>(ep.out_lo + base);
-            const uint64_t p_f32 = reinterpret_cast<uint64_t>(ep.out_f32 + base);
-            const int acc = tcount & 1;
-            if (w.pass == 1 && w.sb >= pending_sb) publish();
-            mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
-            tc_fence_after();
-            publish();
-            const uint32_t tmem_acc = tmem_base + acc * 256 + ((uint32_t)(quarter * 32) << 16);
-            int last = n_chunks - 1;
-            if ((last & 1) != chalf) --last;
-            if (last < chalf) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
-            }
-            const int32_t* coff = col_off[w.pass];
-            const float* cscl = col_scale[w.pass];
-#pragma unroll 1
-            for (int c = chalf; c < n_chunks; c += 2) {
-                uint32_t rr[32];
-                tmem_ld32_nowait(tmem_acc + c * cwid, rr);
-                tmem_ld_wait();
-                if (c == last) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
-                }
-                if (!row_ok) continue;
-                const float dcc = c == 0 ? dcv : 0.0f;
-                if (w.pass == 0) {
-                    if (c * cwid + cwid <= n_lim) store_chunk<0, false, false, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid, pol_last);
-                    else store_chunk<0, true, false, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid, pol_last);
-                } else if (scoring) {
-                    ScoreCtx sc2 = sctx;
-                    sc2.col_grp = &col_grp[c * cwid];
-                    store_chunk<1, true, true, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sc2, cwid, pol_first);
-                } else {
-                    if (c * cwid + cwid <= n_lim) store_chunk<1, false, false, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid, pol_first);
-                    else store_chunk<1, true, false, true>(rr, &coff[c * cwid], &cscl[c * cwid], p_hi, p_lo, p_f32, dcc, sctx, cwid, pol_first);
-                }
-            }
-            if (w.pass == 0) {
-                // this warp's share of the tile: its stores must be visible device-wide (and to the async proxy
-                // of the consumer's TMA loads) before the count moves -- see publish()
-                pending_sb = w.sb;
-            } else if (scoring) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const int R0 = w.row0 + (int)rank * 128;
-                const int Rend = min(R0 + 128, rows_per_seg);
-                if (Rend > R0) {
-                    const int s_first = R0 / ep.p, n_cols = (Rend - 1) / ep.p - s_first + 1;
-                    for (int i = (int)threadIdx.x - 64; i < g.score_groups * n_cols; i += 256) {
-                        const int th = i / n_cols, scol = s_first + (i - th * n_cols);
-                        const int lo = max(R0, scol * ep.p) - R0, hi = min(Rend, scol * ep.p + ep.p) - R0;
-                        unsigned m = 0;
-                        for (int rr_ = lo; rr_ < hi; ++rr_) {
-                            m = max(m, smax[th * 128 + rr_]);
-                            smax[th * 128 + rr_] = 0u;
-                        }
-                        if (m != 0u) {
-                            const int plane = scol / ep.tiles_w, tw = scol - plane * ep.tiles_w;
-                            const int img = plane / ep.channels, ch = plane - img * ep.channels;
-                            atomicMax(reinterpret_cast<unsigned*>(ep.maxabs) +
-                                          (((int64_t)img * ep.tiles_h + th) * ep.tiles_w + tw) * ep.channels + ch, m);
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            ++tcount;
-        }
-        publish();
-    }
-    __syncwarp();
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
-}
-
 // ------------------------------------------------------------------------------ host: launch
 // 3-D fp16 tensor map (k, rows, segments) with a (32, box_rows, 1) box, SWIZZLE_64B
 static int make_map3(CUtensorMap* map, const void* ptr, int64_t k, int64_t rows, int64_t segs, int64_t ld,
@@ -1199,80 +838,6 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
     return check_launch("fold_gemm");
 }
 
-// Both passes in one launch (see fold_chain_kernel).  Returns DCTA_ERR_UNSUPPORTED (without setting an error
-// the caller has to report) when the geometry does not allow it; the caller then launches the passes one by one.
-static int launch_fold_chain(const FoldOperand& A1, const FoldOperand& A2, const FoldOperand& Bas, int n_valid, int K,
-                             int64_t n_planes, ChainPass p1, ChainPass p2, int32_t* done, int done_len, FoldEpi ep1,
-                             FoldEpi ep2, void* stream) {
-    // Opt-in (DCTA_CHAIN=1).  Measured on B200 (profiles/r01_chain_experiment.txt): the chained launch does read
-    // most of the intermediate back from L2 (DRAM reads of the forward passes 762 -> 492 MB per 128 images) but the
-    // passes are no longer DRAM-bound at that point and the launch is 6-10 % SLOWER than the two separate launches,
-    // so the separate launches stay the default.
-    static const bool enabled = getenv("DCTA_CHAIN") != nullptr && atoi(getenv("DCTA_CHAIN")) != 0;
-    if (!enabled || done == nullptr) return DCTA_ERR_UNSUPPORTED;
-    FoldGemm g{};
-    const int score_groups = (ep2.mode == 2 && ep2.maxabs != nullptr) ? ep2.tiles_h : 0;
-    if (!fold_geometry(n_valid, K, g, score_groups, 2048) || g.n_ntiles != 1) return DCTA_ERR_UNSUPPORTED;
-    if (n_planes % 8 || p1.rpp % 32 || p2.rpp % 32 || n_planes * 4 * (int64_t)(p1.rpp > p2.rpp ? p1.rpp : p2.rpp) >= (1ll << 31))
-        return DCTA_ERR_UNSUPPORTED;
-    // sub-batch: about 20 MB of intermediate (pass-2 operand: hi + lo fp16), a multiple of 8 planes
-    static const int env_mb = getenv("DCTA_CHAIN_MB") ? atoi(getenv("DCTA_CHAIN_MB")) : 20;
-    static const int env_lag = getenv("DCTA_CHAIN_LAG") ? atoi(getenv("DCTA_CHAIN_LAG")) : 1;
-    const int64_t inter_per_plane = (int64_t)p2.units * p2.rpp * K * 4;
-    int ps = (int)(((int64_t)env_mb << 20) / (inter_per_plane > 0 ? inter_per_plane : 1)) / 8 * 8;
-    if (ps < 8) ps = 8;
-    if (ps > n_planes) ps = (int)n_planes;
-    ChainSched sc{};
-    sc.p[0] = p1;
-    sc.p[1] = p2;
-    sc.planes = (int)n_planes;
-    sc.ps = ps;
-    sc.ns = (int)ceil_div(n_planes, ps);
-    sc.lag = env_lag < 1 ? 1 : env_lag;
-    static const int env_hints = getenv("DCTA_CHAIN_HINTS") ? atoi(getenv("DCTA_CHAIN_HINTS")) : 1;
-    sc.hints = env_hints;
-    sc.done = done;
-    if (sc.ns > done_len) return DCTA_ERR_UNSUPPORTED;
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int pps = (sms / 2) / 2;                     // pairs per basis group
-    if (pps < 1) return DCTA_ERR_UNSUPPORTED;
-    const unsigned grid = (unsigned)(4 * pps);
-    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4;
-    if (cudaFuncSetAttribute(fold_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) {
-        cudaGetLastError();
-        return DCTA_ERR_UNSUPPORTED;
-    }
-    // the pass-2 producers spin on the progress of other pairs: every pair must be resident at once
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(F_THREADS);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, fold_chain_kernel, &cfg) != cudaSuccess || max_clusters < (int)(grid / 2)) {
-        cudaGetLastError();
-        return DCTA_ERR_UNSUPPORTED;
-    }
-    CUtensorMap m1h, m1l, m2h, m2l, mbh, mbl;
-    int rc;
-    if ((rc = make_map3(&m1h, A1.hi, K, p1.rows_per_seg, 2, A1.ld, A1.seg_stride, 128))) return rc;
-    if ((rc = make_map3(&m1l, A1.lo, K, p1.rows_per_seg, 2, A1.ld, A1.seg_stride, 128))) return rc;
-    const int segs2 = 2 * (p2.units / p2.blocks);
-    if ((rc = make_map3(&m2h, A2.hi, K, p2.rows_per_seg, segs2, A2.ld, A2.seg_stride, 128))) return rc;
-    if ((rc = make_map3(&m2l, A2.lo, K, p2.rows_per_seg, segs2, A2.ld, A2.seg_stride, 128))) return rc;
-    if ((rc = make_map3(&mbh, Bas.hi, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
-    if ((rc = make_map3(&mbl, Bas.lo, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
-    cudaMemsetAsync(done, 0, sizeof(int32_t) * sc.ns, as_stream(stream));
-    fold_chain_kernel<<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(m1h, m1l, m2h, m2l, mbh, mbl, g, sc, ep1, ep2);
-    return check_launch("fold_chain");
-}
-
 // forward pass 2 straight to code words (fold_codes_kernel); DCTA_ERR_UNSUPPORTED when the geometry does not fit
 static int launch_fold_codes(const FoldOperand& Data, int64_t rows_per_seg, const FoldOperand& Bas, int n_valid, int K,
                              CodesArgs g, void* stream) {
@@ -1328,9 +893,9 @@ __device__ __forceinline__ void rgb_px_to_ipt_f(float r, float g, float b, const
     float l = fmaf(A.m[2], b, fmaf(A.m[1], g, A.m[0] * r));
     float m = fmaf(A.m[5], b, fmaf(A.m[4], g, A.m[3] * r));
     float s = fmaf(A.m[8], b, fmaf(A.m[7], g, A.m[6] * r));
-    l = signed_pow(l, 0.43f);
-    m = signed_pow(m, 0.43f);
-    s = signed_pow(s, 0.43f);
+    l = signed_pow_fwd(l, 0.43f);
+    m = signed_pow_fwd(m, 0.43f);
+    s = signed_pow_fwd(s, 0.43f);
     o0 = fmaf(B.m[2], s, fmaf(B.m[1], m, B.m[0] * l));
     o1 = fmaf(B.m[5], s, fmaf(B.m[4], m, B.m[3] * l));
     o2 = fmaf(B.m[8], s, fmaf(B.m[7], m, B.m[6] * l));
@@ -1348,7 +913,8 @@ __device__ __forceinline__ void butterfly4(float p1, float p2, float p3, float p
 
 // util.py:70-82 rgb_to_ipt fused with centring, the 2-D fold and the fp16 hi/lo split:
 // xq[b][a][plane][h'][w'], plane = img * 3 + c.  One thread = 4 consecutive w' of one (img, h').
-__global__ void __launch_bounds__(256) rgb_to_ipt_fold_kernel(const float* __restrict__ rgb, const float* __restrict__ mus,
+template <typename TIn>       // float in [0, 1], or uint8 (read as u8 / 255)
+__global__ void __launch_bounds__(256) rgb_to_ipt_fold_kernel(const TIn* __restrict__ rgb, const float* __restrict__ mus,
                                                               __half* __restrict__ hi, __half* __restrict__ lo,
                                                               int64_t n_img, int h, int w, Mat3 A, Mat3 B, float scale) {
     const int h2 = h >> 1, w8 = w >> 3;                 // w8: float4 groups of the half row
@@ -1360,14 +926,14 @@ __global__ void __launch_bounds__(256) rgb_to_ipt_fold_kernel(const float* __res
         const int64_t t = i / w8;
         const int y = (int)(t % h2);
         const int64_t img = t / h2;
-        const float4* src = reinterpret_cast<const float4*>(rgb) + img * 3 * plane4;
+        const TIn* src = rgb + img * 3 * plane4 * 4;
         const int64_t top = (int64_t)y * (w >> 2), bot = (int64_t)(h - 1 - y) * (w >> 2);
         const int xl = xv, xr = (w >> 2) - 1 - xv;
         float ipt[4][3][4];          // [corner: top-left, top-right, bottom-left, bottom-right][channel][pixel]
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int64_t o = ((k & 2) ? bot : top) + ((k & 1) ? xr : xl);
-            const float4 c0 = ld_stream(src + o), c1 = ld_stream(src + plane4 + o), c2 = ld_stream(src + 2 * plane4 + o);
+            const float4 c0 = ld_px4(src, o), c1 = ld_px4(src, plane4 + o), c2 = ld_px4(src, 2 * plane4 + o);
             const float r[4] = {c0.x, c0.y, c0.z, c0.w}, gg[4] = {c1.x, c1.y, c1.z, c1.w}, bb[4] = {c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) rgb_px_to_ipt_f(r[j], gg[j], bb[j], A, B, ipt[k][0][j], ipt[k][1][j], ipt[k][2][j]);
@@ -1460,9 +1026,9 @@ __device__ __forceinline__ void unbutterfly4(const float (&z)[4], float dcv, flo
 }
 
 // quadrant planes z[s][plane][h'][w'] -> un-folded IPT -> RGB (util.py:85-97); COLOR = false: plain planes out
-template <bool COLOR>
+template <bool COLOR, typename TOut = float>     // TOut = uint8_t: 8-bit pixels as torchvision's save_image stores them
 __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ z, const float* __restrict__ dc,
-                                                     float* __restrict__ out, int64_t n_items, int h, int w, Mat3 A, Mat3 B) {
+                                                     TOut* __restrict__ out, int64_t n_items, int h, int w, Mat3 A, Mat3 B) {
     constexpr int CH = COLOR ? 3 : 1;
     const int h2 = h >> 1, w8 = w >> 3;
     const int64_t total = n_items * h2 * w8;
@@ -1490,7 +1056,7 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ z
                 unbutterfly4(zz, dcv, px[0][c][j], px[1][c][3 - j], px[2][c][j], px[3][c][3 - j]);
             }
         }
-        float4* dst = reinterpret_cast<float4*>(out) + item * CH * plane4;
+        TOut* dst = out + item * CH * plane4 * 4;
         const int64_t top = (int64_t)y * (w >> 2), bot = (int64_t)(h - 1 - y) * (w >> 2);
         const int xr = (w >> 2) - 1 - xv;
 #pragma unroll
@@ -1506,7 +1072,7 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ z
             const int64_t o = ((k & 2) ? bot : top) + ((k & 1) ? xr : xv);
 #pragma unroll
             for (int c = 0; c < CH; ++c)
-                st_stream(dst + c * plane4 + o, make_float4(px[k][c][0], px[k][c][1], px[k][c][2], px[k][c][3]));
+                st_px4(dst, c * plane4 + o, make_float4(px[k][c][0], px[k][c][1], px[k][c][2], px[k][c][3]));
         }
     }
 }
@@ -1927,9 +1493,25 @@ extern "C" int dcta_rgb_to_ipt_fold(const float* rgb, void* xq_hi, void* xq_lo, 
     for (int i = 0; i < 9; ++i) { A.m[i] = m_rgb2lms_host[i]; B.m[i] = m_ipt_host[i]; }
     cudaStream_t st = as_stream(stream);
     const float* mus = launch_ipt_plane_means(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
-    rgb_to_ipt_fold_kernel<<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, st>>>(
+    rgb_to_ipt_fold_kernel<float><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, st>>>(
         rgb, mus, (__half*)xq_hi, (__half*)xq_lo, n_img, h, w, A, B, kFScaleX);
     return check_launch("rgb_to_ipt_fold");
+}
+
+extern "C" int dcta_rgb_u8_to_ipt_fold(const uint8_t* rgb, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
+                                       int64_t n_img, int h, int w, const float* m_rgb2lms_host, const float* m_ipt_host,
+                                       void* stream) {
+    DCTA_REQUIRE(rgb && xq_hi && xq_lo && dc && sums_scratch && m_rgb2lms_host && m_ipt_host, "rgb_u8_to_ipt_fold: null pointer");
+    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 3) == 0 && n_img <= 65535,
+                 "rgb_u8_to_ipt_fold: needs h, w multiples of 16, 4-byte aligned input, at most 65535 images");
+    if (n_img == 0) return DCTA_OK;
+    Mat3 A, B;
+    for (int i = 0; i < 9; ++i) { A.m[i] = m_rgb2lms_host[i]; B.m[i] = m_ipt_host[i]; }
+    cudaStream_t st = as_stream(stream);
+    const float* mus = launch_ipt_plane_means_u8(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
+    rgb_to_ipt_fold_kernel<uint8_t><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, st>>>(
+        rgb, mus, (__half*)xq_hi, (__half*)xq_lo, n_img, h, w, A, B, kFScaleX);
+    return check_launch("rgb_u8_to_ipt_fold");
 }
 
 extern "C" int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
@@ -1951,7 +1533,7 @@ extern "C" int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float*
 extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
                                   const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
                                   const float* rs_h, void* work_hi, void* work_lo, float* y, float* maxabs,
-                                  int32_t* chain_scratch, int64_t n_planes, int h, int w, int kh, int kw, int tile_p,
+                                  int64_t n_planes, int h, int w, int kh, int kw, int tile_p,
                                   int channels, void* stream) {
     DCTA_REQUIRE(xq_hi && xq_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && y,
                  "dct2_fwd_fold: null pointer");
@@ -1984,13 +1566,6 @@ extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const fl
                             as_stream(stream));
     } else {
         e2.mode = 1; e2.seg_stride = 0; e2.item_stride = (int64_t)kh * kw; e2.col_stride = kw;
-    }
-    if (h == w && kh == kw && bw_hi == bh_hi && bw_lo == bh_lo && rs_w == rs_h) {
-        // square planes: one resident basis serves both passes; the intermediate stays in L2
-        ChainPass p1{2, 2, h2, (int)(2 * n_planes * h2)}, p2{1, 1, kw, (int)(n_planes * kw)};
-        const int rc = launch_fold_chain(A1, A2, B1, kw / 2, w2, n_planes, p1, p2, chain_scratch, DCTA_CHAIN_SCRATCH,
-                                         e1, e2, stream);
-        if (rc != DCTA_ERR_UNSUPPORTED) return rc;
     }
     int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)h2, 2, B1, kw / 2, w2, e1, stream);
     if (rc) return rc;
@@ -2058,7 +1633,7 @@ extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, co
 //   bwt: (2, w/2, ldq) = CW[2j+b, w']^T, bht: (2, h/2, ldi) = CH[2i+a, h']^T; work: (2, 2, n_planes, w/2, ldi) hi/lo
 extern "C" int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const void* bwt_hi, const void* bwt_lo,
                                   const void* bht_hi, const void* bht_lo, void* work_hi, void* work_lo, float* z,
-                                  int32_t* chain_scratch, int64_t n_planes, int h, int w, int kh, int kw, void* stream) {
+                                  int64_t n_planes, int h, int w, int kh, int kw, void* stream) {
     DCTA_REQUIRE(yq_hi && yq_lo && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && z,
                  "dct2_inv_fold: null pointer");
     DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_inv_fold: needs h, w multiples of 16 and even kh <= h, kw <= w");
@@ -2081,12 +1656,6 @@ extern "C" int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const vo
     e2.seg_stride = n_planes * (int64_t)h2 * w2; e2.item_stride = (int64_t)h2 * w2;
     e2.col_mul = 1; e2.col_add = 0; e2.col_stride = w2;
     e2.alpha = 1.0f / (kFScaleBasis * kFScaleQ);
-    if (h == w && kh == kw && bwt_hi == bht_hi && bwt_lo == bht_lo) {
-        ChainPass p1{2, 2, kh2, (int)(2 * n_planes * kh2)}, p2{2, 1, w2, (int)(n_planes * w2)};
-        const int rc = launch_fold_chain(A1, A2, B1, w2, kw2, n_planes, p1, p2, chain_scratch, DCTA_CHAIN_SCRATCH, e1, e2,
-                                         stream);
-        if (rc != DCTA_ERR_UNSUPPORTED) return rc;
-    }
     int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)kh2, 2, B1, w2, kw2, e1, stream);
     if (rc) return rc;
     return launch_fold_gemm(A2, n_planes * (int64_t)w2, 4, B2, h2, kh2, e2, stream);
@@ -2101,6 +1670,17 @@ extern "C" int dcta_unfold_ipt_to_rgb(const float* z, const float* dc, float* rg
     for (int i = 0; i < 9; ++i) { A.m[i] = m_ipt_inv_host[i]; B.m[i] = m_lms2rgb_host[i]; }
     unfold_kernel<true><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, rgb, n_img, h, w, A, B);
     return check_launch("unfold_ipt_to_rgb");
+}
+
+extern "C" int dcta_unfold_ipt_to_rgb_u8(const float* z, const float* dc, uint8_t* rgb, int64_t n_img, int h, int w,
+                                         const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream) {
+    DCTA_REQUIRE(z && rgb && m_ipt_inv_host && m_lms2rgb_host, "unfold_ipt_to_rgb_u8: null pointer");
+    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 3) == 0, "unfold_ipt_to_rgb_u8: bad sizes");
+    if (n_img == 0) return DCTA_OK;
+    Mat3 A, B;
+    for (int i = 0; i < 9; ++i) { A.m[i] = m_ipt_inv_host[i]; B.m[i] = m_lms2rgb_host[i]; }
+    unfold_kernel<true, uint8_t><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, rgb, n_img, h, w, A, B);
+    return check_launch("unfold_ipt_to_rgb_u8");
 }
 
 extern "C" int dcta_unfold_planes(const float* z, const float* dc, float* x, int64_t n_planes, int h, int w, void* stream) {

@@ -687,6 +687,20 @@ __global__ void __launch_bounds__(256) split_centered_kernel(const float* __rest
 
 __device__ __forceinline__ float signed_pow_tc(float v, float g) { return signed_pow(v, g); }
 
+// the operand producer uses the accurate exp2 (common.cuh: signed_pow_fwd); the plane-mean ESTIMATE below keeps MUFU
+__device__ __forceinline__ void rgb_px_to_ipt_acc(float r, float g, float b, const Mat3& A, const Mat3& B, float& o0,
+                                                  float& o1, float& o2) {
+    float l = fmaf(A.m[2], b, fmaf(A.m[1], g, A.m[0] * r));
+    float m = fmaf(A.m[5], b, fmaf(A.m[4], g, A.m[3] * r));
+    float s = fmaf(A.m[8], b, fmaf(A.m[7], g, A.m[6] * r));
+    l = signed_pow_fwd(l, 0.43f);
+    m = signed_pow_fwd(m, 0.43f);
+    s = signed_pow_fwd(s, 0.43f);
+    o0 = fmaf(B.m[2], s, fmaf(B.m[1], m, B.m[0] * l));
+    o1 = fmaf(B.m[5], s, fmaf(B.m[4], m, B.m[3] * l));
+    o2 = fmaf(B.m[8], s, fmaf(B.m[7], m, B.m[6] * l));
+}
+
 __device__ __forceinline__ void rgb_px_to_ipt(float r, float g, float b, const Mat3& A, const Mat3& B, float& o0,
                                               float& o1, float& o2) {
     float l = fmaf(A.m[2], b, fmaf(A.m[1], g, A.m[0] * r));
@@ -732,22 +746,22 @@ __global__ void __launch_bounds__(256) ipt_sums_kernel(const float* __restrict__
 // The same estimate in one launch for the folded path: one CTA per image visits the sampled quads of all chunks
 // (warp w takes chunks w, w+8, ...), reduces the three plane sums and writes mu / dc itself.  8192 tiny CTAs plus a
 // finalising launch cost more than the arithmetic.
-__global__ void __launch_bounds__(256) ipt_means_kernel(const float* __restrict__ rgb, float* __restrict__ mu,
+template <typename TIn>
+__global__ void __launch_bounds__(256) ipt_means_kernel(const TIn* __restrict__ rgb, float* __restrict__ mu,
                                                         float* __restrict__ dc, int64_t plane4, int stride, Mat3 A, Mat3 B,
                                                         float inv_count, float dc_factor) {
     __shared__ float red[8];
     const int64_t img = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t per = (plane4 + kSumChunks - 1) / kSumChunks;
-    const float4* src = reinterpret_cast<const float4*>(rgb) + img * 3 * plane4;
+    const TIn* src = rgb + img * 3 * plane4 * 4;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     for (int c = warp; c < kSumChunks; c += 8) {
         const int64_t beg = c * per, len = min(plane4, beg + per) - beg;
         for (int64_t k = lane;; k += 32) {
             const int64_t i = sample_index(k, stride);
             if (i >= len) break;
-            const float4 c0 = ld_stream(src + beg + i), c1 = ld_stream(src + plane4 + beg + i),
-                         c2 = ld_stream(src + 2 * plane4 + beg + i);
+            const float4 c0 = ld_px4(src, beg + i), c1 = ld_px4(src, plane4 + beg + i), c2 = ld_px4(src, 2 * plane4 + beg + i);
             const float r[4] = {c0.x, c0.y, c0.z, c0.w}, g[4] = {c1.x, c1.y, c1.z, c1.w}, b[4] = {c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -786,7 +800,7 @@ __global__ void __launch_bounds__(256) rgb_to_ipt_split_kernel(const float* __re
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float o0, o1, o2;
-            rgb_px_to_ipt(r[j], g[j], b[j], A, B, o0, o1, o2);
+            rgb_px_to_ipt_acc(r[j], g[j], b[j], A, B, o0, o1, o2);
             split16(o0 - mu[0], scale, oh[0][j], ol[0][j]);
             split16(o1 - mu[1], scale, oh[1][j], ol[1][j]);
             split16(o2 - mu[2], scale, oh[2][j], ol[2][j]);
@@ -921,14 +935,23 @@ extern "C" int dcta_rgb_to_ipt_split(const float* rgb, void* ipt_hi, void* ipt_l
 // plane means of the IPT image (sampled estimate) + the DC term they stand for; shared with dct_fold.cu.
 // scratch holds (kSumChunks + 1) floats per plane; returns the device pointer of the means.
 namespace dcta {
-const float* launch_ipt_plane_means(const float* rgb, float* sums_scratch, float* dc, int64_t n_img, int h, int w,
-                                    const Mat3& A, const Mat3& B, cudaStream_t st) {
+template <typename TIn>
+static const float* launch_ipt_plane_means_t(const TIn* rgb, float* sums_scratch, float* dc, int64_t n_img, int h, int w,
+                                             const Mat3& A, const Mat3& B, cudaStream_t st) {
     const int64_t plane = (int64_t)h * w;
     const float inv_count = 1.0f / (4.0f * (float)sampled_quads(plane / 4, kSumStride));
     float* mus = sums_scratch + n_img * 3 * kSumChunks;
-    ipt_means_kernel<<<(unsigned)n_img, 256, 0, st>>>(rgb, mus, dc, plane / 4, kSumStride, A, B, inv_count,
-                                                      sqrtf((float)h * (float)w));
+    ipt_means_kernel<TIn><<<(unsigned)n_img, 256, 0, st>>>(rgb, mus, dc, plane / 4, kSumStride, A, B, inv_count,
+                                                           sqrtf((float)h * (float)w));
     return mus;
+}
+const float* launch_ipt_plane_means(const float* rgb, float* sums_scratch, float* dc, int64_t n_img, int h, int w,
+                                    const Mat3& A, const Mat3& B, cudaStream_t st) {
+    return launch_ipt_plane_means_t(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
+}
+const float* launch_ipt_plane_means_u8(const uint8_t* rgb, float* sums_scratch, float* dc, int64_t n_img, int h, int w,
+                                       const Mat3& A, const Mat3& B, cudaStream_t st) {
+    return launch_ipt_plane_means_t(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
 }
 const float* launch_plane_means(const float* x, float* sums_scratch, float* dc, int64_t n_planes, int h, int w,
                                 cudaStream_t st) {

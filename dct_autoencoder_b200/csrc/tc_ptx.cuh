@@ -239,6 +239,8 @@ const float* launch_ipt_plane_means(const float* rgb, float* sums_scratch, float
 int launch_vq_pair(const void* x_hi, const void* x_lo, const void* e_hi, const void* e_lo, const float* e2,
                    const float* alpha_dev, float* part_val, int32_t* part_idx, int64_t n_tok, int n_codes, int d,
                    int64_t ld, cudaStream_t st);
+const float* launch_ipt_plane_means_u8(const uint8_t* rgb, float* sums_scratch, float* dc, int64_t n_img, int h, int w,
+                                       const Mat3& A, const Mat3& B, cudaStream_t st);
 const float* launch_plane_means(const float* x, float* sums_scratch, float* dc, int64_t n_planes, int h, int w,
                                 cudaStream_t st);
 

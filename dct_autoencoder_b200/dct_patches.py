@@ -165,27 +165,12 @@ def to_bytes(dct_patches: DCTPatches, codes: torch.Tensor, codebook_size: int) -
     27 instead of ~400 bytes per token for the 14x14-bit quantiser, and is produced by one kernel and
     one device->host copy instead of one ``.item()`` per field."""
     import struct
-
-    from . import _lib
-    _lib.require_cuda(codes)
     b, s, c = codes.shape
-    assert (b, s) == tuple(dct_patches.key_pad_mask.shape)
     d = max(1, (int(codebook_size) - 1).bit_length())
     assert 2 ** d == codebook_size, "codebook_size must be a power of two"
     if int(dct_patches.patch_channels.max()) >= 16 or int(dct_patches.patch_positions.max()) >= 64:
         raise ValueError("wire format holds channel < 16 and h, w < 64")
-    rec = wire_record_bytes(c, d)
-    dev = codes.device
-    codes = codes.to(torch.int64).contiguous()
-    pos = dct_patches.patch_positions.to(dev, torch.int64).contiguous()
-    ch = dct_patches.patch_channels.to(dev, torch.int64).contiguous()
-    ids = dct_patches.batched_image_ids.to(dev, torch.int64).contiguous()
-    pad = dct_patches.key_pad_mask.to(dev).contiguous()
-    out = torch.empty((b, s, rec), dtype=torch.uint8, device=dev)
-    counts = torch.empty((b, s), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.call("dcta_wire_pack", _lib.ptr(codes), _lib.ptr(pos), _lib.ptr(ch), _lib.ptr(ids),
-                  pad.data_ptr(), b, s, c, d, rec, _lib.ptr(out), _lib.ptr(counts), _lib.stream_ptr(dev))
+    out, counts = wire_records(dct_patches, codes, d)
     n_img = dct_patches.row_num_images()
     h_out = out.cpu().numpy()
     h_counts = counts[:, :max(n_img)].cpu().numpy()
@@ -200,6 +185,31 @@ def to_bytes(dct_patches: DCTPatches, codes: torch.Tensor, codebook_size: int) -
             blobs.append(head + h_out[r, off:off + k].tobytes())
             off += k
     return blobs
+
+
+def wire_records(dct_patches: DCTPatches, codes: torch.Tensor, bits: int):
+    """Device half of ``to_bytes``: (rows, s, codebooks) codes + the batch's positions / channels / ids / mask ->
+    records (rows, s, 2 + ceil(codebooks*bits/8)) uint8, one per slot (the images of a row follow each other and the
+    padding trails, FE:455-513, so image i of row r owns records [sum(counts[r, :i]), +counts[r, i])), and
+    counts (rows, s) int32 with counts[r, i] = tokens of image i of row r.  One kernel
+    (csrc/wire.cu); the caller must make sure channel < 16 and h, w < 64 (``to_bytes`` checks)."""
+    from . import _lib
+    _lib.require_cuda(codes)
+    b, s, c = codes.shape
+    assert (b, s) == tuple(dct_patches.key_pad_mask.shape)
+    rec = wire_record_bytes(c, bits)
+    dev = codes.device
+    codes = codes.to(torch.int64).contiguous()
+    pos = dct_patches.patch_positions.to(dev, torch.int64).contiguous()
+    ch = dct_patches.patch_channels.to(dev, torch.int64).contiguous()
+    ids = dct_patches.batched_image_ids.to(dev, torch.int64).contiguous()
+    pad = dct_patches.key_pad_mask.to(dev).contiguous()
+    out = torch.empty((b, s, rec), dtype=torch.uint8, device=dev)
+    counts = torch.empty((b, s), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_wire_pack", _lib.ptr(codes), _lib.ptr(pos), _lib.ptr(ch), _lib.ptr(ids),
+                  pad.data_ptr(), b, s, c, bits, rec, _lib.ptr(out), _lib.ptr(counts), _lib.stream_ptr(dev))
+    return out, counts
 
 
 def from_bytes(blob: bytes, device=None):

@@ -23,7 +23,7 @@ from . import _lib
 from .dct_patches import DCTPatches
 from .util import (_round8, dct2, dct2_fwd_fold, dct2_fwd_fold_codes, dct2_fwd_tc, dct2_inv_fold, dct2_inv_tc, dct2_truncated,
                    exp_trunc_dist, fold_ok, idct2, idct2_truncated, ipt_to_rgb, rgb_to_ipt, rgb_to_ipt_fold,
-                   rgb_to_ipt_split, tc_forward_ok, to_device_f32, unfold_ipt_to_rgb)
+                   rgb_to_ipt_split, tc_forward_ok, to_device_f32, to_device_pixels, unfold_ipt_to_rgb, unit_to_u8)
 
 _SEG_DTYPE = np.dtype([("row", "<i4"), ("offset", "<i4"), ("k", "<i4"), ("image_id", "<i4"), ("img", "<i8")])
 assert _SEG_DTYPE.itemsize == 24
@@ -276,8 +276,8 @@ class DCTAutoencoderFeatureExtractor:
     def preprocess(self, im: torch.Tensor):
         """FE:155-177: one (c, h, w) image -> dict(patches (k, p*p), positions (k, 2),
         channels (k,), original_sizes (h, w), patch_sizes (ph, pw))."""
-        og = im.dtype
-        x = to_device_f32(im, self._dev(im))[None]
+        og = im.dtype if im.dtype != torch.uint8 else torch.float32     # uint8 pixels stand for x / 255 (fp32)
+        x = to_device_pixels(im, self._dev(im))[None]
         _, c, h, w = x.shape
         ph, pw, th, tw = self._geometry(h, w)
         tiles, maxabs = self._token_grid(x, want_maxabs=True)
@@ -301,7 +301,7 @@ class DCTAutoencoderFeatureExtractor:
     def _preprocess_batch_raw(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None):
         """Tokens of b same-size images, one image per row of (b, max k, .) buffers.
         -> (patches fp32, positions, channels, ks, (h, w), (ph, pw))."""
-        x = to_device_f32(images, self._dev(images))
+        x = to_device_pixels(images, self._dev(images))
         b, c, h, w = x.shape
         ph, pw, th, tw = self._geometry(h, w)
         tiles, maxabs = self._token_grid(x, want_maxabs=True)
@@ -327,7 +327,7 @@ class DCTAutoencoderFeatureExtractor:
         launches (the batched multi-image preprocess the offline shard writer needs,
         preproc_dataset.py:62-84).  The per-image tensors are views of one (b, max k, .) buffer."""
         patches, pos, chan, ks, osz, psz = self._preprocess_batch_raw(images, ks)
-        if images.dtype != torch.float32:
+        if images.dtype not in (torch.float32, torch.uint8):
             patches = patches.to(images.dtype)
         return [dict(patches=patches[i, :k], positions=pos[i, :k], channels=chan[i, :k],
                      original_sizes=osz, patch_sizes=psz) for i, k in enumerate(ks)]
@@ -336,7 +336,7 @@ class DCTAutoencoderFeatureExtractor:
     def process_batch(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None) -> DCTPatches:
         """Whole-batch encode of (b, c, h, w) same-size images: equals
         ``next(iter_batches(iter([dict_collate([preprocess(im) for im in images])]), None))``."""
-        x = to_device_f32(images, self._dev(images))
+        x = to_device_pixels(images, self._dev(images))
         b, c, h, w = x.shape
         ph, pw, th, tw = self._geometry(h, w)
         tiles, maxabs = self._token_grid(x, want_maxabs=True)
@@ -354,7 +354,7 @@ class DCTAutoencoderFeatureExtractor:
                       tab.data_ptr() + offs[1], len(rows), self.max_seq_len, th, tw, c,
                       self.patch_size ** 2, _lib.ptr(patches), _lib.ptr(pos), _lib.ptr(chan),
                       _lib.ptr(ids), _lib.ptr(pad), _lib.stream_ptr(x.device))
-        if images.dtype != torch.float32:
+        if images.dtype not in (torch.float32, torch.uint8):
             patches = patches.to(images.dtype)
         return DCTPatches(patches=patches, key_pad_mask=pad, batched_image_ids=ids,
                           patch_channels=chan, patch_positions=pos,
@@ -378,7 +378,7 @@ class DCTAutoencoderFeatureExtractor:
         tensors kept in registers (csrc/fused_lfq.cu).  Returns (DCTPatches with ``patches=None``,
         codes (rows, s, codebooks) int64), bit-identical to the staged calls."""
         assert self._lfq_fusable(norm, lfq)
-        x = to_device_f32(images, self._dev(images))
+        x = to_device_pixels(images, self._dev(images), keep_u8=True)     # uint8 pixels stay bytes until the colour kernel
         if norm.median.device != x.device:
             raise _lib.DctaError(f"PatchNorm tables live on {norm.median.device}, the images on {x.device}")
         b, c, h, w = x.shape
@@ -400,6 +400,8 @@ class DCTAutoencoderFeatureExtractor:
                 _lib.call("dcta_sort_tokens_maxabs", _lib.ptr(maxabs), None, _lib.ptr(order), b, th, tw, c,
                           float(self.patch_sample_magnitude_weight), imp, _lib.stream_ptr(x.device))
         else:
+            if x.dtype == torch.uint8:
+                x = to_device_pixels(x)
             tiles, maxabs = self._token_grid(x, want_maxabs=True)
             order = self._sorted_order(tiles, maxabs)
         if ks is None:
@@ -438,16 +440,17 @@ class DCTAutoencoderFeatureExtractor:
         return batch, codes
 
     @torch.no_grad()
-    def postprocess_codes_batch(self, x: DCTPatches, codes: torch.Tensor, norm, lfq) -> torch.Tensor:
+    def postprocess_codes_batch(self, x: DCTPatches, codes: torch.Tensor, norm, lfq, out_dtype=torch.float32) -> torch.Tensor:
         """``lfq.indices_to_codes`` -> ``norm.inverse_norm`` -> ``postprocess_batch`` with the
-        de-quantised patches kept in registers; same-size batches, tensor-core DCT path."""
+        de-quantised patches kept in registers; same-size batches, tensor-core DCT path.
+        ``out_dtype=torch.uint8``: 8-bit pixels, quantised like torchvision's save_image (util.unit_to_u8)."""
         assert self._lfq_fusable(norm, lfq) and self.dct_impl in ("tc", "tc_plain")
         assert len(set(map(tuple, x.original_sizes))) == 1 and len(set(map(tuple, x.patch_sizes))) == 1
         if not lfq.keep_num_codebooks_dim:       # lfq.py:106-107
             codes = codes[..., None]
         if norm.median.device != codes.device:
             raise _lib.DctaError(f"PatchNorm tables live on {norm.median.device}, the codes on {codes.device}")
-        (idx, rgb), = self._decode_groups(x, codes=codes.contiguous(), norm=norm, lfq=lfq)
+        (idx, rgb), = self._decode_groups(x, codes=codes.contiguous(), norm=norm, lfq=lfq, out_dtype=out_dtype)
         return rgb
 
     def _group_patches_by_max_seq_len(self, batched_patches, batched_positions=None,
@@ -613,7 +616,8 @@ class DCTAutoencoderFeatureExtractor:
                 res[i] = rgb[n] if og == torch.float32 else rgb[n].to(og)
         return res
 
-    def _decode_groups(self, x: DCTPatches, codes: Optional[torch.Tensor] = None, norm=None, lfq=None):
+    def _decode_groups(self, x: DCTPatches, codes: Optional[torch.Tensor] = None, norm=None, lfq=None,
+                       out_dtype=torch.float32):
         """Token rows -> RGB, one kernel sequence per group of images that share (tile grid,
         original size).  Yields (image indices, rgb (n, c, h, w)).  The zero padding of FE:300-304
         is implicit in the truncated inverse basis.  With ``codes`` the tokens are de-quantised and
@@ -657,7 +661,7 @@ class DCTAutoencoderFeatureExtractor:
                     else:
                         _lib.call("dcta_unpatchify_fold", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
                                   th, tw, p, kh, kw, h, w, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc), st)
-                    yield idx, unfold_ipt_to_rgb(dct2_inv_fold(y_hi, y_lo, kh, kw, h, w), dc, h, w)
+                    yield idx, unfold_ipt_to_rgb(dct2_inv_fold(y_hi, y_lo, kh, kw, h, w), dc, h, w, out_dtype)
                     continue
                 if self.dct_impl in ("tc", "tc_plain"):
                     ld = _round8(kw)
@@ -679,11 +683,13 @@ class DCTAutoencoderFeatureExtractor:
                     _lib.call("dcta_unpatchify", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C, th, tw,
                               p, kh, kw, _lib.ptr(planes), st)
                     ipt = idct2_truncated(planes, h, w)
-            yield idx, ipt_to_rgb(ipt)
+            rgb = ipt_to_rgb(ipt)
+            yield idx, (unit_to_u8(rgb) if out_dtype == torch.uint8 else rgb)
 
     @torch.no_grad()
-    def postprocess_batch(self, x: DCTPatches) -> torch.Tensor:
-        """Same as ``torch.stack(postprocess(x))`` for batches whose images share one size."""
+    def postprocess_batch(self, x: DCTPatches, out_dtype=torch.float32) -> torch.Tensor:
+        """Same as ``torch.stack(postprocess(x))`` for batches whose images share one size.
+        ``out_dtype=torch.uint8``: 8-bit pixels, quantised like torchvision's save_image (util.unit_to_u8)."""
         assert len(set(map(tuple, x.original_sizes))) == 1 and len(set(map(tuple, x.patch_sizes))) == 1
-        (idx, rgb), = self._decode_groups(x)
+        (idx, rgb), = self._decode_groups(x, out_dtype=out_dtype)
         return rgb

@@ -7,10 +7,10 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from .dct_patches import DCTPatches
+from .dct_patches import DCTPatches, wire_records
 from .feature_extraction_dct_autoencoder import DCTAutoencoderFeatureExtractor
 from .patchnorm import PatchNorm
-from .util import power_of_two
+from .util import power_of_two, unit_to_u8
 
 
 def dict_collate(x: List[dict]) -> dict:
@@ -82,15 +82,16 @@ class TransformPipeline:
         return batch, codes
 
     @torch.no_grad()
-    def decode_codes(self, batch: DCTPatches, codes: torch.Tensor) -> torch.Tensor:
+    def decode_codes(self, batch: DCTPatches, codes: torch.Tensor, out_dtype=torch.float32) -> torch.Tensor:
         """(batch metadata, codes) -> (n, c, h, w) RGB (modeling_dct_autoencoder.py:157-163
-        decode_from_codes without the transformer); fused when ``fusable()``."""
+        decode_from_codes without the transformer); fused when ``fusable()``.
+        ``out_dtype=torch.uint8``: 8-bit pixels as torchvision's save_image would store the float result."""
         if self.fusable():
-            return self.extractor.postprocess_codes_batch(batch, codes, self.norm, self.quantizer)
+            return self.extractor.postprocess_codes_batch(batch, codes, self.norm, self.quantizer, out_dtype)
         b = batch.shallow_copy()
         b.patches = self.quantizer.indices_to_codes(codes)
         b.patches = self.norm.inverse_norm(b)
-        return self.extractor.postprocess_batch(b)
+        return self.extractor.postprocess_batch(b, out_dtype)
 
     @torch.no_grad()
     def roundtrip_staged(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None):
@@ -100,15 +101,18 @@ class TransformPipeline:
         return self.decode(batch, q), codes
 
     @torch.no_grad()
-    def roundtrip(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None, fused: Optional[bool] = None):
+    def roundtrip(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None, fused: Optional[bool] = None,
+                  out_dtype=torch.float32):
         """images -> (reconstructed images, codes).  ``fused=None`` picks the fused PatchNorm+LFQ
-        kernels when they apply; results are bit-identical to ``roundtrip_staged``."""
+        kernels when they apply; results are bit-identical to ``roundtrip_staged``.  uint8 ``images`` are 8-bit
+        pixels standing for ``x / 255``; ``out_dtype=torch.uint8`` returns 8-bit pixels (util.unit_to_u8)."""
         if fused is None:
             fused = self.fusable()
         if not fused:
-            return self.roundtrip_staged(images, ks)
+            rec, codes = self.roundtrip_staged(images, ks)
+            return (rec if out_dtype == torch.float32 else unit_to_u8(rec)), codes
         batch, codes = self.encode_codes(images, ks)
-        return self.decode_codes(batch, codes), codes
+        return self.decode_codes(batch, codes, out_dtype), codes
 
     def graphed(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None, fused: Optional[bool] = None):
         """``roundtrip`` of a fixed-shape device batch captured once in a CUDA graph; see GraphedRoundtrip."""
@@ -116,15 +120,26 @@ class TransformPipeline:
 
     @torch.no_grad()
     def roundtrip_host(self, images: torch.Tensor, out_images: Optional[torch.Tensor] = None,
-                       out_codes: Optional[torch.Tensor] = None, chunk: int = 32, device=None):
+                       out_codes: Optional[torch.Tensor] = None, chunk: int = 32, device=None,
+                       compact: bool = False, out_counts: Optional[torch.Tensor] = None):
         """Host-to-host round trip of a (n, c, h, w) HOST batch (pinned memory for full speed):
         the batch is streamed through the GPU in chunks so that the host->device copy of chunk i+1,
         the kernels of chunk i and the device->host copy of chunk i-1 overlap (three streams).
         Image-independent work only, so chunking does not change any result.
-        Returns (out_images (n, c, h, w) fp32, out_codes (n, s, codebooks) int64) on the host.
-        Codes are returned per IMAGE, so every image must fill its own row (k == max_seq_len, as in
-        the benchmark configuration); use roundtrip() per chunk for packed rows."""
+
+        Default (the reference's types): fp32 images in, fp32 images + int64 codes out --
+        (out_images (n, c, h, w) fp32, out_codes (n, s, codebooks) int64).
+        ``compact=True``: the same computation with 8-bit pixels on both sides of the link and the codes in the
+        wire format of ``to_bytes`` -- uint8 images in (read as ``x / 255``, what ``read_image(path) / 255`` gives the
+        reference), uint8 images out (what ``save_image`` writes) and, instead of int64 codes, one record
+        ``u16 c<<12|h<<6|w`` + bit-packed code words per token: returns (out_images (n, c, h, w) uint8,
+        records (n, s, record_bytes) uint8, counts (n,) int32 = valid records per image).  PCIe moves 1.65 MB per
+        512^2 image instead of 6.6 MB; codes, token order and pixels are those of the default mode (pixels after
+        the 8-bit quantisation).  Every image must fill its own row (k == max_seq_len, as in the benchmark
+        configuration); use roundtrip() per chunk for packed rows."""
         assert not images.is_cuda, "roundtrip_host takes host tensors; use roundtrip() for device tensors"
+        if compact:
+            assert images.dtype == torch.uint8, "compact mode takes 8-bit pixels"
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         n = images.shape[0]
         if not hasattr(self, "_copy_streams"):
@@ -133,6 +148,7 @@ class TransformPipeline:
         main = torch.cuda.current_stream(dev)
         s_in.wait_stream(main)
         s_out.wait_stream(main)
+        out_dtype = torch.uint8 if compact else torch.float32
         for i in range(0, n, chunk):
             sl = slice(i, min(n, i + chunk))
             with torch.cuda.stream(s_in):
@@ -140,20 +156,31 @@ class TransformPipeline:
                 ev_in = s_in.record_event()
             main.wait_event(ev_in)
             x.record_stream(main)
-            rec, codes = self.roundtrip(x)
+            batch, codes = self.encode_codes(x)
+            rec = self.decode_codes(batch, codes, out_dtype)
             assert codes.shape[0] == x.shape[0], "roundtrip_host needs one image per row (k == max_seq_len)"
+            counts = None
+            if compact:
+                codes, counts = wire_records(batch, codes, self.quantizer.codebook_dim)
+                counts = counts[:, 0].contiguous()
             if out_images is None:
                 out_images = torch.empty((n,) + tuple(rec.shape[1:]), dtype=rec.dtype).pin_memory()
+            if out_codes is None:
                 out_codes = torch.empty((n,) + tuple(codes.shape[1:]), dtype=codes.dtype).pin_memory()
+            if compact and out_counts is None:
+                out_counts = torch.empty(n, dtype=torch.int32).pin_memory()
             ev_done = main.record_event()
             s_out.wait_event(ev_done)
             with torch.cuda.stream(s_out):
                 out_images[sl].copy_(rec, non_blocking=True)
                 out_codes[sl].copy_(codes, non_blocking=True)
+                if compact:
+                    out_counts[sl].copy_(counts, non_blocking=True)
+                    counts.record_stream(s_out)
             rec.record_stream(s_out)
             codes.record_stream(s_out)
         main.wait_stream(s_out)
-        return out_images, out_codes
+        return (out_images, out_codes, out_counts) if compact else (out_images, out_codes)
 
 
 class GraphedRoundtrip:

@@ -93,6 +93,44 @@ def to_device_f32(x: torch.Tensor, device=None) -> torch.Tensor:
     return x.contiguous()
 
 
+def to_device_pixels(x: torch.Tensor, device=None, keep_u8: bool = False) -> torch.Tensor:
+    """Images for the encoder.  Floating tensors: ``to_device_f32``.  uint8 tensors are 8-bit pixels -- what
+    ``torchvision.io.read_image`` returns -- and stand for ``x / 255`` exactly as the reference's callers compute it
+    (decode_gif.py:22, testpipe.py:17): they cross PCIe as bytes and are converted on the device, either by the
+    consuming kernel (``keep_u8``: returned as a contiguous uint8 CUDA tensor) or by ``u8_to_unit``."""
+    if x.dtype != torch.uint8:
+        return to_device_f32(x, device)
+    if not x.is_cuda:
+        device = device or default_device()
+        x = x.contiguous()
+        if not x.is_pinned():
+            x = x.pin_memory()
+        x = x.to(device, non_blocking=True)
+    x = x.contiguous()
+    return x if keep_u8 else u8_to_unit(x)
+
+
+def u8_to_unit(x: torch.Tensor) -> torch.Tensor:
+    """uint8 CUDA tensor -> fp32 ``x / 255`` (IEEE division, bit-identical to torch's)."""
+    _lib.require_cuda(x)
+    assert x.dtype == torch.uint8
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dcta_u8_to_unit_f32", _lib.ptr(x), _lib.ptr(out), x.numel(), _lib.stream_ptr(x.device))
+    return out
+
+
+def unit_to_u8(x: torch.Tensor) -> torch.Tensor:
+    """fp32 CUDA image -> uint8 the way ``torchvision.utils.save_image`` stores it (testpipe.py:74-75):
+    ``floor(clamp(x, 0, 1) * 255 + 0.5)``."""
+    x = to_device_f32(x)
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("dcta_unit_f32_to_u8", _lib.ptr(x), _lib.ptr(out), x.numel(), _lib.stream_ptr(x.device))
+    return out
+
+
 def _colorspace(x: torch.Tensor, fn: str, a, b) -> torch.Tensor:
     og_dtype = x.dtype
     x = to_device_f32(x)
@@ -459,8 +497,9 @@ def rgb_to_ipt_fold(x: torch.Tensor):
     lo = torch.empty_like(hi)
     dc = torch.empty(b * 3, dtype=torch.float32, device=x.device)
     scratch = torch.empty(b * 3 * 33, dtype=torch.float32, device=x.device)
+    fn = "dcta_rgb_u8_to_ipt_fold" if x.dtype == torch.uint8 else "dcta_rgb_to_ipt_fold"   # uint8: read as x / 255
     with torch.cuda.device(x.device):
-        _lib.call("dcta_rgb_to_ipt_fold", _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc), _lib.ptr(scratch),
+        _lib.call(fn, _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(dc), _lib.ptr(scratch),
                   b, h, w, _M_RGB2LMS, _M_IPT, _lib.stream_ptr(x.device))
     return hi, lo, dc
 
@@ -500,11 +539,10 @@ def dct2_fwd_fold(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: Optional[torch.T
     if with_maxabs:
         assert tile_p > 0
         maxabs = torch.empty(y.shape[:4], dtype=torch.float32, device=dev)
-    chain = torch.empty(_lib.CHAIN_SCRATCH, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dcta_dct2_fwd_fold", _lib.ptr(xq_hi), _lib.ptr(xq_lo), _lib.ptr(dc), _lib.ptr(bw_hi),
                   _lib.ptr(bw_lo), _lib.ptr(rs_w), _lib.ptr(bh_hi), _lib.ptr(bh_lo), _lib.ptr(rs_h), _lib.ptr(work_hi),
-                  _lib.ptr(work_lo), _lib.ptr(y), _lib.ptr(maxabs), _lib.ptr(chain), n_planes, h, w, kh, kw, tile_p,
+                  _lib.ptr(work_lo), _lib.ptr(y), _lib.ptr(maxabs), n_planes, h, w, kh, kw, tile_p,
                   channels, _lib.stream_ptr(dev))
     return (y, maxabs) if with_maxabs else y
 
@@ -545,20 +583,22 @@ def dct2_inv_fold(yq_hi: torch.Tensor, yq_lo: torch.Tensor, kh: int, kw: int, h:
     work_hi = torch.empty((2, 2, n_planes, w // 2, ldi), dtype=torch.float16, device=dev)
     work_lo = torch.empty_like(work_hi)
     z = torch.empty((4, n_planes, h // 2, w // 2), dtype=torch.float32, device=dev)
-    chain = torch.empty(_lib.CHAIN_SCRATCH, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dcta_dct2_inv_fold", _lib.ptr(yq_hi), _lib.ptr(yq_lo), _lib.ptr(bwt_hi), _lib.ptr(bwt_lo),
-                  _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z), _lib.ptr(chain),
+                  _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z),
                   n_planes, h, w, kh, kw, _lib.stream_ptr(dev))
     return z
 
 
-def unfold_ipt_to_rgb(z: torch.Tensor, dc: Optional[torch.Tensor], h: int, w: int) -> torch.Tensor:
-    """Final butterfly of the folded inverse fused with util.py:85-97: z (4, n_img*3, h/2, w/2) -> RGB (n_img, 3, h, w)."""
+def unfold_ipt_to_rgb(z: torch.Tensor, dc: Optional[torch.Tensor], h: int, w: int, out_dtype=torch.float32) -> torch.Tensor:
+    """Final butterfly of the folded inverse fused with util.py:85-97: z (4, n_img*3, h/2, w/2) -> RGB (n_img, 3, h, w).
+    ``out_dtype=torch.uint8``: 8-bit pixels, quantised in the same kernel as ``unit_to_u8`` does."""
     n_img = z.shape[1] // 3
-    rgb = torch.empty((n_img, 3, h, w), dtype=torch.float32, device=z.device)
+    assert out_dtype in (torch.float32, torch.uint8)
+    rgb = torch.empty((n_img, 3, h, w), dtype=out_dtype, device=z.device)
+    fn = "dcta_unfold_ipt_to_rgb_u8" if out_dtype == torch.uint8 else "dcta_unfold_ipt_to_rgb"
     with torch.cuda.device(z.device):
-        _lib.call("dcta_unfold_ipt_to_rgb", _lib.ptr(z), _lib.ptr(dc), _lib.ptr(rgb), n_img, h, w, _M_IPT_INV,
+        _lib.call(fn, _lib.ptr(z), _lib.ptr(dc), _lib.ptr(rgb), n_img, h, w, _M_IPT_INV,
                   _M_LMS2RGB, _lib.stream_ptr(z.device))
     return rgb
 

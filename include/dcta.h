@@ -30,8 +30,6 @@ extern "C" {
 #define DCTA_ERR_INVALID_ARG (-1)
 #define DCTA_ERR_LAUNCH (-2)
 #define DCTA_ERR_UNSUPPORTED (-3)
-/* int32 elements of the chain_scratch argument of dcta_dct2_fwd_fold / dcta_dct2_inv_fold */
-#define DCTA_CHAIN_SCRATCH 4096
 
 const char* dcta_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
@@ -45,6 +43,11 @@ int dcta_compiled_arch(void);
  * (the reference's Trgb2lms UT:40 and Mipt UT:37-39).  rgb and ipt must not overlap. */
 int dcta_rgb_to_ipt(const float* rgb, float* ipt, int64_t n_img, int64_t plane,
                     const float* m_rgb2lms_host, const float* m_ipt_host, void* stream);
+/* 8-bit pixels -> floats in [0, 1]: out[i] = in[i] / 255 with torch's IEEE fp32 division, bit for bit (the callers'
+ * `torchvision.io.read_image(path) / 255`, decode_gif.py:22, testpipe.py:17), and back the way
+ * torchvision.utils.save_image stores a float image (testpipe.py:74-75): floor(clamp(x, 0, 1) * 255 + 0.5). */
+int dcta_u8_to_unit_f32(const uint8_t* in, float* out, int64_t n, void* stream);
+int dcta_unit_f32_to_u8(const float* in, uint8_t* out, int64_t n, void* stream);
 /* UT:85-97 ipt_to_rgb.  m_ipt_inv_host = Mipt.inverse() (UT:91), m_lms2rgb_host = Tlms2rgb (UT:41). */
 int dcta_ipt_to_rgb(const float* ipt, float* rgb, int64_t n_img, int64_t plane,
                     const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream);
@@ -133,6 +136,12 @@ int dcta_fold_supported(int h, int w, int kh, int kw);
 int dcta_rgb_to_ipt_fold(const float* rgb, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
                          int64_t n_img, int h, int w, const float* m_rgb2lms_host, const float* m_ipt_host,
                          void* stream);
+/* The same for 8-bit pixels: rgb (n_img, 3, h, w) uint8, read as u8 / 255 exactly as torch's IEEE fp32 division
+ * does (the callers' `torchvision.io.read_image(path) / 255`, decode_gif.py:22, testpipe.py:17).  4x fewer bytes
+ * over PCIe for host-resident images. */
+int dcta_rgb_u8_to_ipt_fold(const uint8_t* rgb, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
+                            int64_t n_img, int h, int w, const float* m_rgb2lms_host, const float* m_ipt_host,
+                            void* stream);
 /* The same for plain fp32 planes x (n_planes, h, w). */
 int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
                      int64_t n_planes, int h, int w, void* stream);
@@ -141,14 +150,11 @@ int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float* dc, float*
  *   rs_w (2, kw/2) the factors undoing those scales;  bh_hi/lo (2, kh/2, h/2), rs_h likewise (group a);
  *   work_hi/lo (2, n_planes, kw, h/2) scratch;
  *   maxabs [nullable, token grid only] (n_planes/channels, kh/p, kw/p, channels): amax|tile| of every token
- *   (FE:409), reduced in the GEMM epilogue (input of dcta_sort_tokens_maxabs);
- *   chain_scratch [nullable]: DCTA_CHAIN_SCRATCH int32 of device scratch.  When given, and the planes are square
- *   with bw == bh (same pointers), both passes run in ONE launch and the intermediate is read back from L2. */
+ *   (FE:409), reduced in the GEMM epilogue (input of dcta_sort_tokens_maxabs). */
 int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
                        const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
                        const float* rs_h, void* work_hi, void* work_lo, float* y, float* maxabs,
-                       int32_t* chain_scratch, int64_t n_planes, int h, int w, int kh, int kw, int tile_p,
-                       int channels, void* stream);
+                       int64_t n_planes, int h, int w, int kh, int kw, int tile_p, int channels, void* stream);
 /* The forward transform straight to LFQ code words, for a projection-free LFQ with one codebook per patch row
  * (c == d == tile_p) on frozen PatchNorm tables: the pass-2 epilogue forms the sign bit of
  * clamp((Y - median) / (b*sqrt2 + eps)) (PN:157-165, LFQ:175-187) of every coefficient and never writes the token grid.
@@ -182,10 +188,14 @@ int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, float* dc, i
  *   work_hi/lo (2, 2, n_planes, w/2, ldi) scratch. */
 int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const void* bwt_hi, const void* bwt_lo,
                        const void* bht_hi, const void* bht_lo, void* work_hi, void* work_lo, float* z,
-                       int32_t* chain_scratch, int64_t n_planes, int h, int w, int kh, int kw, void* stream);
+                       int64_t n_planes, int h, int w, int kh, int kw, void* stream);
 /* Final butterfly (+ the DC constant dc[plane], nullable) fused with UT:85-97 ipt_to_rgb: rgb (n_img, 3, h, w). */
 int dcta_unfold_ipt_to_rgb(const float* z, const float* dc, float* rgb, int64_t n_img, int h, int w,
                            const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream);
+/* The same with 8-bit output, rgb (n_img, 3, h, w) uint8 = floor(clamp(x, 0, 1) * 255 + 0.5): the quantisation of
+ * torchvision.utils.save_image, which is what the reference's callers apply to a reconstruction (testpipe.py:74-75). */
+int dcta_unfold_ipt_to_rgb_u8(const float* z, const float* dc, uint8_t* rgb, int64_t n_img, int h, int w,
+                              const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream);
 /* Final butterfly alone: x (n_planes, h, w). */
 int dcta_unfold_planes(const float* z, const float* dc, float* x, int64_t n_planes, int h, int w, void* stream);
 

@@ -122,45 +122,6 @@ def test_fold_maxabs_matches_tile_scores(D):
         assert torch.equal(fe._sorted_order(tiles, maxabs), fe._sorted_order(tiles))
 
 
-@pytest.mark.parametrize("n_img,size,k", [(8, 512, 448), (16, 256, 252), (24, 128, 112), (40, 512, 448)])
-def test_fold_chained_passes_match_separate_launches(D, n_img, size, k):
-    """Opt-in chained kernel (DCTA_CHAIN=1: both passes in one launch, the intermediate read back from L2, pass-2
-    tiles gated on per-sub-batch counters): bit-identical to the two separate launches.  The switch is read once
-    per process, so the chained run happens in a child process."""
-    import os
-    import subprocess
-    import sys
-    import tempfile
-    torch.manual_seed(n_img)
-    x = torch.rand(n_img, 3, size, size, device="cuda")
-    qhi, qlo, qdc = D.util.rgb_to_ipt_fold(x)
-    tiles, maxabs = D.util.dct2_fwd_fold(qhi, qlo, qdc, k, k, tile_p=14, channels=3, with_maxabs=True)
-    planes = D.util.dct2_fwd_fold(qhi, qlo, qdc, k, k, out_shape=(n_img, 3))
-    back = D.util.idct2_truncated_fold(planes, size, size)
-    torch.cuda.synchronize()
-    code = f"""
-import sys, torch
-sys.path.insert(0, {repr(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))})
-import dct_autoencoder_b200 as D
-torch.manual_seed({n_img})
-x = torch.rand({n_img}, 3, {size}, {size}, device="cuda")
-qhi, qlo, qdc = D.util.rgb_to_ipt_fold(x)
-tiles, maxabs = D.util.dct2_fwd_fold(qhi, qlo, qdc, {k}, {k}, tile_p=14, channels=3, with_maxabs=True)
-planes = D.util.dct2_fwd_fold(qhi, qlo, qdc, {k}, {k}, out_shape=({n_img}, 3))
-back = D.util.idct2_truncated_fold(planes, {size}, {size})
-torch.save(dict(tiles=tiles.cpu(), maxabs=maxabs.cpu(), planes=planes.cpu(), back=back.cpu()), sys.argv[1])
-"""
-    with tempfile.TemporaryDirectory() as d:
-        out = os.path.join(d, "chained.pt")
-        env = dict(os.environ, DCTA_CHAIN="1")
-        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=300)
-        ref = torch.load(out)
-    assert torch.equal(tiles.cpu(), ref["tiles"])
-    assert torch.equal(maxabs.cpu(), ref["maxabs"])
-    assert torch.equal(planes.cpu(), ref["planes"])
-    assert torch.equal(back.cpu(), ref["back"])
-
-
 @pytest.mark.parametrize("n_tok", [100, 128, 500, 1024, 1025, 2000, 3072, 4096, 5000])
 def test_sort_tokens_matches_torch_sort(D, n_tok):
     """Per-image descending sort (ties: ascending index), both kernels (register/shuffle variant up to 4096 keys)."""

@@ -234,3 +234,41 @@ def test_config2_full_batch_properties(D):
     plain = pipe.extractor.postprocess_batch(pipe.extractor.process_batch(x[:8]))
     assert float((plain - x[:8]).abs().mean()) < float((rec[:8] - x[:8]).abs().mean())
     assert bool(torch.isfinite(rec).all())
+
+
+def test_uint8_pixels_in_and_out(D):
+    """8-bit pixels on both sides (what the reference's callers hold: read_image(path) / 255 in, save_image out):
+    uint8 input == the fp32 input x / 255 bit for bit on every path; uint8 output == save_image's quantisation of the
+    fp32 output; the compact host round trip == the fp32 one after those two conversions, codes as wire records."""
+    torch.manual_seed(5)
+    # all 256 byte values: u8 -> float is torch's IEEE division, float -> u8 is floor(clamp(x)*255 + 0.5)
+    b = torch.arange(256, dtype=torch.uint8).repeat(3).cuda()[:767]
+    assert torch.equal(D.util.u8_to_unit(b), b.float() / 255)
+    v = torch.cat([torch.rand(1001, device="cuda") * 1.2 - 0.1, torch.tensor([0.0, 1.0, 0.5 / 255, 1.5 / 255, float("nan")], device="cuda")])
+    want = v.nan_to_num(0.0).clamp(0, 1).mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8)
+    assert torch.equal(D.util.unit_to_u8(v), want)
+
+    x8 = torch.randint(0, 256, (6, 3, 128, 160), dtype=torch.uint8)
+    xf = x8.float() / 255
+    pipe = _pipe(D, "tc", max_seq_len=9 * 11 * 3)
+    pipe.fit_norm(torch.rand(6, 3, 128, 160).cuda())
+    rec_f, codes_f = pipe.roundtrip(xf.cuda())
+    rec_8, codes_8 = pipe.roundtrip(x8.cuda(), out_dtype=torch.uint8)
+    assert torch.equal(codes_8, codes_f)
+    assert rec_8.dtype == torch.uint8 and torch.equal(rec_8, D.util.unit_to_u8(rec_f))
+    # staged modules and the per-image API take uint8 too
+    b8, bf = pipe.extractor.process_batch(x8.cuda()), pipe.extractor.process_batch(xf.cuda())
+    assert b8.patches.dtype == torch.float32 and torch.equal(b8.patches, bf.patches)
+    i8, i_f = pipe.extractor.preprocess(x8[0]), pipe.extractor.preprocess(xf[0])
+    assert torch.equal(i8["patches"], i_f["patches"]) and torch.equal(i8["positions"], i_f["positions"])
+    assert torch.equal(pipe.extractor.postprocess_batch(bf, out_dtype=torch.uint8), D.util.unit_to_u8(pipe.extractor.postprocess_batch(bf)))
+    # host to host, compact: uint8 in, uint8 + wire records out
+    out_img, records, counts = pipe.roundtrip_host(x8.pin_memory(), chunk=4, compact=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out_img, rec_8.cpu()) and counts.tolist() == [9 * 11 * 3] * 6
+    batch, _ = pipe.encode_codes(xf.cuda())
+    blobs = D.to_bytes(batch, codes_f, 2 ** 14)
+    for i, blob in enumerate(blobs):
+        assert blob[D.dct_patches.WIRE_HEADER_BYTES:] == records[i, :int(counts[i])].numpy().tobytes()
+        dp, c2 = D.from_bytes(blob)
+        assert torch.equal(c2, codes_f[i])
