@@ -2,6 +2,13 @@
 """Benchmark of the encode+decode transform path (BASELINE.json metric: images/s at 512^2, patch 14).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+                    [--config 2|3a|3b|4|5] [--global-batch G]
+
+`--config` selects the BASELINE.json configuration (default 2 = the headline metric; the driver runs that one):
+  3a / 3b  synthetic 1024^2, batch 128, max_seq_len 1024: pure top-k cap / beta = 0.004 variable k + row packing
+  4        VectorQuantize nearest code, codebook 8192 x 256, 512 x 3072 tokens (metric: tokens/s)
+  5        4096 images of 512^2 in total, sharded G / N per GPU (strong scaling), one PatchNorm statistic-fit step
+           with its all-reduce, then the config-2 pipeline
 
 One "step" = one pass of the whole path over one batch of synthetic images:
   RGB -> IPT -> truncated 2-D DCT -> token grid -> score / sort / pack -> PatchNorm -> LFQ
@@ -47,6 +54,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dct-impl", default="tc", choices=["tc", "tc_plain", "fp32"],
                     help="tc = tcgen05 split-precision GEMMs (default), fp32 = exact FFMA GEMMs")
+    ap.add_argument("--config", default="2", choices=["2", "3a", "3b", "4", "5"])
+    ap.add_argument("--global-batch", type=int, default=4096, help="config 5: images in total over all GPUs")
     return ap.parse_args()
 
 
@@ -170,71 +179,184 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------- GPU arm
-def run_ours(a):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """One rank: device, process group, timing helpers."""
 
-    import dct_autoencoder_b200 as D
-    from dct_autoencoder_b200 import _lib
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _lib.load()
+        import dct_autoencoder_b200 as D
+        from dct_autoencoder_b200 import _lib
+        self.torch, self.dist, self.D, self.lib = torch, dist, D, _lib
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            # create the NCCL communicator NOW (first collective = hundreds of ms), outside everything timed
+            t = torch.zeros(1, device=self.dev)
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        _lib.load()
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            self.peaks = {}
+        self.hbm = float(self.peaks.get("hbm_gbs", 6650.0))
+        self.peak_tf = float(self.peaks.get("bf16_tflops_sustained", 1400.0))
+        self.peak_src = "measured (MEASURED_PEAKS.json)" if self.peaks else "fallback (B200_PROFILING.md)"
 
-    B, S = a.batch, a.size
-    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072, dct_impl=a.dct_impl)
-    pn = D.PatchNorm(32, 32, 14, 3).to(dev)
-    lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).to(dev).eval()
-    pipe = D.TransformPipeline(fe, pn, lfq)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    # PatchNorm statistics fitted on a different batch (all-reduced over the ranks when world > 1)
-    g = torch.Generator(device=dev)
-    g.manual_seed(1000 + rank)
-    fit_x = torch.rand(min(B, 64), 3, S, S, device=dev, generator=g)
-    t0 = time.perf_counter()
-    pipe.fit_norm(fit_x)
-    torch.cuda.synchronize()
-    fit_ms = 1e3 * (time.perf_counter() - t0)
-    del fit_x
-
-    g.manual_seed(rank)
-    x = torch.rand(B, 3, S, S, device=dev, generator=g)        # 805 MB at B=256: larger than the 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
+    def timed(self, fn, steps, warmup):
+        """ms for `steps` calls: barrier + synchronize on both sides, CUDA events, MAX over ranks."""
+        torch = self.torch
         for _ in range(warmup):
             fn()
-        barrier()
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
+        self.barrier()
         ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             ms = float(t)
         return ms
 
+    def finish(self, line):
+        if self.rank == 0:
+            print(json.dumps(line), flush=True)
+        if self.world > 1:
+            self.dist.destroy_process_group()
+        return 0
+
+
+def traffic_from_profiles(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed summary of the
+    `ncu --set full` capture of this workload (profiles/traffic.json, written by profiles/summarize.py traffic)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t.get(key)
+        return (float(e["bytes_per_launch"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def make_pipe(ctx, max_seq_len=3072, beta=0.0, dct_impl="tc"):
+    D = ctx.D
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, beta, 32, 32, max_seq_len, dct_impl=dct_impl)
+    pn = D.PatchNorm(32, 32, 14, 3).to(ctx.dev)
+    lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).to(ctx.dev).eval()
+    return D.TransformPipeline(fe, pn, lfq)
+
+
+def fit_norm_timed(ctx, pipe, fit_x, steps=10):
+    """The PatchNorm statistic fit (main.py:115-149: `steps` update steps, default 10 in main.py:297), with its two
+    all-reduces per step when world > 1.  Returns a dict: first (cold) step, warm step time (CUDA events, max over
+    ranks), the two all-reduces alone, and whether every rank ended with identical tables."""
+    torch, dist = ctx.torch, ctx.dist
+    t0 = time.perf_counter()
+    pipe.fit_norm(fit_x)
+    torch.cuda.synchronize()
+    first_ms = 1e3 * (time.perf_counter() - t0)
+    ms = ctx.timed(lambda: pipe.fit_norm(fit_x), steps, 1)
+    out = dict(fit_first_step_ms=first_ms, fit_step_ms=ms / steps, fit_steps_timed=steps,
+               fit_images_per_rank=int(fit_x.shape[0]))
+    if ctx.world > 1:
+        n_pos, z = 3 * 32 * 32, 196
+        packed = torch.zeros(n_pos + n_pos * z, device=ctx.dev)
+        abs_dev = torch.zeros(n_pos * z, device=ctx.dev)
+
+        def two_allreduces():
+            dist.all_reduce(packed)
+            dist.all_reduce(abs_dev)
+        out["allreduce_pair_ms"] = ctx.timed(two_allreduces, 20, 3) / 20
+        out["allreduce_bytes"] = int(packed.numel() * 4 + abs_dev.numel() * 4)
+        same = True
+        for t in (pipe.norm.n.data, pipe.norm.median.data, pipe.norm.b.data):
+            hi, lo = t.clone(), t.clone()
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            same = same and bool(torch.equal(hi, lo))
+        out["stats_identical_across_ranks"] = same
+    return out
+
+
+def e2e_host(ctx, pipe, x, steps, chunk):
+    """End to end through the public host API (TransformPipeline.roundtrip_host): pinned host buffers in, pinned host
+    buffers out, copies inside the timed region.  Returns (fp32-contract dict, compact-mode dict)."""
+    torch, D = ctx.torch, ctx.D
+    B = x.shape[0]
+    old_affinity = os.sched_getaffinity(0)
+    numa_bound = D.util.bind_to_gpu_numa(ctx.dev)      # pinned buffers live on the allocating thread's NUMA node
+    hx = torch.empty(tuple(x.shape), dtype=torch.float32).pin_memory()
+    hx.copy_(x)
+    h_rec = torch.empty(tuple(x.shape), dtype=torch.float32).pin_memory()
+    s, c = pipe.extractor.max_seq_len, pipe.quantizer.num_codebooks
+    h_codes = torch.empty((B, s, c), dtype=torch.int64).pin_memory()
+    ms = ctx.timed(lambda: pipe.roundtrip_host(hx, h_rec, h_codes, chunk=chunk), steps, 2)
+    fp32 = dict(value=ctx.world * B * steps / (ms / 1e3), unit=UNIT, h2d_bytes_per_step=hx.numel() * 4 * ctx.world,
+                d2h_bytes_per_step=(h_rec.numel() * 4 + h_codes.numel() * 8) * ctx.world, ms_per_step=ms / steps,
+                contract="the reference's types: fp32 images in, fp32 images + int64 codes out")
+    # compact: the same computation with 8-bit pixels on both sides of the link and the codes as wire records
+    hx8 = (hx * 255).round().to(torch.uint8).pin_memory()
+    h_rec8 = torch.empty(tuple(x.shape), dtype=torch.uint8).pin_memory()
+    rec_bytes = D.dct_patches.wire_record_bytes(c, pipe.quantizer.codebook_dim)
+    h_wire = torch.empty((B, s, rec_bytes), dtype=torch.uint8).pin_memory()
+    h_counts = torch.empty(B, dtype=torch.int32).pin_memory()
+    ms8 = ctx.timed(lambda: pipe.roundtrip_host(hx8, h_rec8, h_wire, chunk=chunk, compact=True, out_counts=h_counts),
+                    steps, 2)
+    compact = dict(value=ctx.world * B * steps / (ms8 / 1e3), unit=UNIT, h2d_bytes_per_step=hx8.numel() * ctx.world,
+                   d2h_bytes_per_step=(h_rec8.numel() + h_wire.numel() + h_counts.numel() * 4) * ctx.world,
+                   ms_per_step=ms8 / steps,
+                   contract="uint8 pixels in (read as x/255, exact), uint8 pixels out (save_image quantisation), codes as "
+                            "27-byte wire records (u16 c|h|w + 14x14 code bits): same codes, 4x fewer PCIe bytes")
+    if numa_bound:
+        os.sched_setaffinity(0, old_affinity)
+    return fp32, compact
+
+
+def run_ours(a):
+    ctx = Ctx()
+    if a.config in ("3a", "3b"):
+        return run_config3(ctx, a)
+    if a.config == "4":
+        return run_config4(ctx, a)
+    if a.config == "5":
+        return run_config5(ctx, a)
+    torch, D, _lib = ctx.torch, ctx.D, ctx.lib
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    B, S = a.batch, a.size
+    pipe = make_pipe(ctx, dct_impl=a.dct_impl)
+    fe, pn = pipe.extractor, pipe.norm
+
+    # PatchNorm statistics fitted on a different batch (all-reduced over the ranks when world > 1)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    fit_x = torch.rand(min(B, 64), 3, S, S, device=dev, generator=g)
+    fit = fit_norm_timed(ctx, pipe, fit_x)
+    del fit_x
+
+    g.manual_seed(rank)
+    x = torch.rand(B, 3, S, S, device=dev, generator=g)        # 805 MB at B=256: larger than the 126 MB L2
+
     # ---- device-resident throughput (value)
     def step():
-        rec, codes = pipe.roundtrip(x)
-        return rec, codes
+        return pipe.roundtrip(x)
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
     if sampler:
         sampler.start()
     for _ in range(a.warmup):
@@ -242,7 +364,7 @@ def run_ours(a):
     torch.cuda.synchronize()
     skip = sampler.mark() if sampler else 0
     l0 = _lib.launch_count
-    ms = timed(step, a.steps, 0)
+    ms = ctx.timed(step, a.steps, 0)
     launches = _lib.launch_count - l0
     if sampler and ms < 400:       # keep the GPU under the same load until a few samples exist
         t_end = time.time() + 0.5
@@ -254,30 +376,26 @@ def run_ours(a):
     mode = ("fused: PatchNorm + LFQ code words formed in the forward DCT epilogue, decode straight from code words "
             "(bit-identical to staged)") if pipe.fusable() else "staged"
 
+    # ---- the same step replayed from a CUDA graph (one driver call per step, no Python between the launches)
+    graphed = None
+    try:
+        gr = pipe.graphed(x)
+        ms_g = ctx.timed(lambda: gr(), a.steps, 2)
+        graphed = dict(value=world * B * a.steps / (ms_g / 1e3), unit=UNIT, ms_per_step=ms_g / a.steps,
+                       launches_per_replay=gr.launches,
+                       note="TransformPipeline.graphed(x): the same launches captured once in a CUDA graph")
+        del gr
+    except Exception as e:          # capture is an optimisation of the host side, never a requirement
+        graphed = dict(error=str(e)[:200])
+
     # ---- the same job through the drop-in modules one by one (every intermediate materialised)
     staged_steps = max(2, min(a.steps, 5))
-    ms_staged = timed(lambda: pipe.roundtrip_staged(x), staged_steps, 1)
+    ms_staged = ctx.timed(lambda: pipe.roundtrip_staged(x), staged_steps, 1)
     staged_value = world * B * staged_steps / (ms_staged / 1e3)
 
     # ---- end to end through the public API with HOST buffers (pinned in, pinned out)
-    # pinned buffers live on the NUMA node of the allocating thread: allocate next to the GPU (no-op on one node)
-    old_affinity = os.sched_getaffinity(0)
-    numa_bound = D.util.bind_to_gpu_numa(dev)
-    hx = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
-    hx.copy_(x)
-    h_rec = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
-    h_codes = torch.empty((B, 3072, 14), dtype=torch.int64).pin_memory()
-
-    def step_e2e():
-        # public host-to-host call: pinned host images in, pinned host images + codes out;
-        # H2D, kernels and D2H of successive 32-image chunks overlap on three streams
-        pipe.roundtrip_host(hx, h_rec, h_codes, chunk=a.chunk)
-
     e2e_steps = max(2, min(a.steps, 8))
-    ms_e2e = timed(step_e2e, e2e_steps, 2)
-    e2e_value = world * B * e2e_steps / (ms_e2e / 1e3)
-    if numa_bound:
-        os.sched_setaffinity(0, old_affinity)
+    e2e, e2e_compact = e2e_host(ctx, pipe, x, e2e_steps, a.chunk)
 
     # ---- per-stage device times (CUDA events around each public call) for the roofline object
     stages = stage_times(torch, D, pipe, x, dev, reps=3)
@@ -285,14 +403,7 @@ def run_ours(a):
     flops_fwd = 3 * 2 * S * K * (S + K) * B          # C*2*H*K*(W+K) per image
     dct_ms = stages["dct_fwd"]
     achieved = flops_fwd / (dct_ms / 1e3) / 1e12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
-    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    peak_tf, peak_src, hbm = ctx.peak_tf, ctx.peak_src, ctx.hbm
     if fe.dct_impl == "tc" and D.util.fold_ok(S, S, K, K):
         # fold_gemm_kernel: 4 launches per step (forward passes 1-2, inverse passes 1-2).  After the fold the
         # kernel is bounded by HBM (its operands and outputs stream once), not by the tensor pipe.
@@ -314,21 +425,21 @@ def run_ours(a):
         gemm_ms = stages[fwd_key] + stages["dct_inv"]
         achieved_gbs = sum(alg) * B / (gemm_ms / 1e3) / 1e9
         tens = (flops_fwd / (stages[fwd_key] / 1e3) / 1e12)
+        traffic, traffic_src = (traffic_from_profiles("dct_gemm_launches_b256_512") if (B == 256 and S == 512 and "dct_fwd_codes" in stages)
+                                else (None, None))
         roofline = dict(bound="hbm", kernel="fold_gemm_kernel x3 + fold_codes_kernel (the 4 DCT GEMM launches of the timed step: "
                         "forward pass 1, forward pass 2 -> code words, inverse passes 1-2; "
                         "cta_group::2 tcgen05 fp16x3 split precision, folded basis resident in shared memory)",
                         achieved=achieved_gbs, peak=hbm, unit="GB/s", frac=achieved_gbs / hbm,
-                        # dram__bytes_read + write per launch, ncu --set full of this workload (profiles/r02v_kernels_ncu_full_b256.txt:
-                        # 1470 MB forward pass 1, 821 MB fold_codes_kernel, 1272 / 1459 MB inverse passes)
-                        traffic=(1.256e9 if (B == 256 and S == 512 and "dct_fwd_codes" in stages) else None),
+                        traffic=traffic, traffic_source=traffic_src,
                         launches_per_step=4, avg_launch_ms=gemm_ms / 4,
                         algorithmic_bytes_per_launch=sum(alg) * B / 4,
-                        peak_source=("measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback"),
+                        peak_source=peak_src,
                         tensor=dict(achieved=tens, peak=peak_tf, unit="TFLOP/s", frac=tens / peak_tf,
                                     note="forward passes: SURVEY 8(d) flops 3*2*H*K*(W+K) per image (plain basis GEMMs); the "
                                          "folded kernel executes 1/2 of them, each as 3 tensor MMAs, so frac <= 2/3"),
-                        note="achieved = algorithmic operand + output bytes of the 4 launches / their CUDA-event time; "
-                             "traffic: see profiles/ (ncu dram bytes per launch)")
+                        note="achieved = algorithmic operand + output bytes of the 4 launches / their CUDA-event time "
+                             "(the kernels' OWN hi/lo operands, not SURVEY 8d's fused bound: that is pipeline_hbm.fused)")
     else:
         if fe.dct_impl in ("tc", "tc_plain"):
             kname = "gemm_split_kernel (forward DCT: 2 launches, tcgen05 fp16x3 split precision)"
@@ -356,14 +467,16 @@ def run_ours(a):
                 config=dict(WORKLOAD, global_batch=B * world, per_gpu_batch=B, parallelism=f"image-sharded x{world}",
                             dct_impl=a.dct_impl, mode=mode,
                             l2="inputs (805 MB/GPU at B=256) larger than L2, no flush needed",
-                            patchnorm_fit_ms=fit_ms),
-                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=hx.numel() * 4 * world,
-                         d2h_bytes_per_step=(h_rec.numel() * 4 + h_codes.numel() * 8) * world,
-                         ms_per_step=ms_e2e / e2e_steps),
+                            patchnorm_fit=fit),
+                e2e=e2e, e2e_compact=e2e_compact,
                 gpu_launches=launches, clocks=clocks, roofline=roofline, pipeline_hbm=pipeline_hbm,
+                graphed=graphed,
                 staged=dict(value=staged_value, unit=UNIT, ms_per_step=ms_staged / staged_steps,
                             note="same job through the drop-in modules one by one (roundtrip_staged)"),
                 stages_ms=stages)
+    if world > 1:
+        line["e2e"]["note"] = ("all ranks share the host's memory and PCIe root complex: the host-to-host rate saturates there, "
+                               "not on a collective (see e2e_compact for the same job with 4x fewer link bytes)")
 
     if rank == 0 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -372,11 +485,117 @@ def run_ours(a):
         line["cpu_baseline"] = dict(value=ips, unit=UNIT, cores=procs, kind="port",
                                     sample=f"{n} images of {S}x{S} over {procs} worker processes, {dt:.1f} s "
                                            "(oracle/dcta_oracle.py run_pipeline)")
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return ctx.finish(line)
+
+
+def run_config3(ctx, a):
+    """BASELINE config 3: synthetic 1024^2, batch 128, max_seq_len 1024 (73 x 73 tiles -> 3072 in-bounds candidates).
+    3a: beta = 0, pure top-k cap, one image per row.  3b: random.seed(42), beta = 0.004: variable k drawn on the host in
+    the reference's RNG order, several images per row, padding, multi-image decode."""
+    import random
+    torch, D = ctx.torch, ctx.D
+    B, S = (a.batch if a.batch != 256 else 128), 1024
+    beta = 0.004 if a.config == "3b" else 0.0
+    pipe = make_pipe(ctx, max_seq_len=1024, beta=beta, dct_impl=a.dct_impl)
+    g = torch.Generator(device=ctx.dev)
+    g.manual_seed(1000 + ctx.rank)
+    random.seed(7)
+    fit = fit_norm_timed(ctx, pipe, torch.rand(16, 3, S, S, device=ctx.dev, generator=g), steps=3)
+    g.manual_seed(ctx.rank)
+    x = torch.rand(B, 3, S, S, device=ctx.dev, generator=g)       # 1.6 GB: larger than L2
+    random.seed(42)
+    ks = [pipe.extractor._choose_k(3072) for _ in range(B)]        # the reference's draw order, one per image
+    batch, codes = pipe.encode_codes(x, ks)
+    rows, tokens = int(codes.shape[0]), int((~batch.key_pad_mask).sum())
+    l0 = ctx.lib.launch_count
+    ms = ctx.timed(lambda: pipe.roundtrip(x, ks), a.steps, a.warmup)
+    launches = ctx.lib.launch_count - l0
+    value = ctx.world * B * a.steps / (ms / 1e3)
+    line = dict(metric=f"encode+decode images/sec at 1024^2 patch14 (config {a.config})", value=value, unit=UNIT,
+                n_gpus=ctx.world, steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"config{a.config}: synthetic 1024x1024 RGB fp32, patch 14, max_patch 32x32, beta={beta}, "
+                                     "max_seq_len 1024, PatchNorm frozen, LFQ 14x14bit, decode to RGB",
+                            image_size=S, patch_size=14, global_batch=B * ctx.world, per_gpu_batch=B,
+                            rows=rows, tokens=tokens, tokens_per_image_min=min(ks), tokens_per_image_max=max(ks),
+                            fusable=pipe.fusable(), l2="inputs (1.6 GB/GPU) larger than L2", patchnorm_fit=fit),
+                gpu_launches=launches,
+                pipeline_hbm=dict(bound="hbm", achieved=(2 * 3 * S * S * 4) * B * a.steps / (ms / 1e3) / 1e9, peak=ctx.hbm,
+                                  unit="GB/s", note="image in + image out only (the fully-fused bound of this config)"))
+    line["pipeline_hbm"]["frac"] = line["pipeline_hbm"]["achieved"] / ctx.hbm
+    return ctx.finish(line)
+
+
+def run_config4(ctx, a):
+    """BASELINE config 4: VectorQuantize(dim=256, codebook_size=8192) eval forward on randn(512, 3072, 256), codebook
+    normal_() seed 3, mask = ones.  The token batch is processed in slices of 64 x 3072 tokens."""
+    torch, D = ctx.torch, ctx.D
+    dev = ctx.dev
+    vq = D.VectorQuantize(dim=256, codebook_size=8192).to(dev).eval()
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    vq._codebook.embed.copy_(torch.randn(1, 8192, 256, device=dev, generator=g))
+    g.manual_seed(ctx.rank)
+    n_slices, sl = 8, 64
+    x = torch.randn(sl, 3072, 256, device=dev, generator=g)       # one slice (201 MB > L2), reused for the 8 slices
+    mask = torch.ones(sl, 3072, dtype=torch.bool, device=dev)
+    T = n_slices * sl * 3072
+
+    def step():
+        for _ in range(n_slices):
+            q, ind, _ = vq(x, mask=mask)
+        return ind
+    l0 = ctx.lib.launch_count
+    ms = ctx.timed(step, a.steps, a.warmup)
+    launches = ctx.lib.launch_count - l0
+    flops = 2.0 * T * 8192 * 256
+    tf = flops * a.steps / (ms / 1e3) / 1e12
+    line = dict(metric="VectorQuantize nearest-code tokens/sec, codebook 8192 x 256 (config 4)",
+                value=ctx.world * T * a.steps / (ms / 1e3), unit="tokens/s", n_gpus=ctx.world, steps=a.steps,
+                warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload="config4: VectorQuantize eval forward, randn(512, 3072, 256) x codebook 8192 x 256, "
+                                     "nearest code + gather, indices int64", tokens=T, impl=vq.vq_impl),
+                gpu_launches=launches,
+                roofline=dict(bound="tensor", kernel="vq nearest-code distance GEMM (tcgen05) + argmin epilogue",
+                              achieved=tf, peak=ctx.peak_tf, unit="TFLOP/s", frac=tf / ctx.peak_tf, traffic=None,
+                              peak_source=ctx.peak_src,
+                              note="algorithmic flops 2*T*8192*256 (SURVEY 8d); the whole forward incl. operand "
+                                   "preparation, |e|^2 and the gather"))
+    return ctx.finish(line)
+
+
+def run_config5(ctx, a):
+    """BASELINE config 5: G = 4096 images of 512^2 in total, sharded G / N per GPU (strong scaling); one PatchNorm
+    statistic-fit step with its all-reduce on the first 64 images of each shard, then the config-2 pipeline over the
+    whole shard in batches of 256."""
+    torch, D = ctx.torch, ctx.D
+    G, S, Bc = a.global_batch, a.size, 256
+    assert G % ctx.world == 0
+    per = G // ctx.world
+    pipe = make_pipe(ctx, dct_impl=a.dct_impl)
+    g = torch.Generator(device=ctx.dev)
+    g.manual_seed(ctx.rank)                                        # SURVEY 8d: seed = rank
+    n_buf = min(per, 1024)                                         # distinct images resident per GPU (3.2 GB per 256)
+    x = torch.rand(n_buf, 3, S, S, device=ctx.dev, generator=g)
+    fit = fit_norm_timed(ctx, pipe, x[:64], steps=10)
+    chunks = [x[(i % n_buf):(i % n_buf) + min(Bc, per - i)] for i in range(0, per, Bc)]
+
+    def step():
+        for c in chunks:
+            pipe.roundtrip(c)
+    l0 = ctx.lib.launch_count
+    ms = ctx.timed(step, a.steps, a.warmup)
+    launches = ctx.lib.launch_count - l0
+    line = dict(metric=METRIC, value=G * a.steps / (ms / 1e3), unit=UNIT, n_gpus=ctx.world, steps=a.steps,
+                warmup=a.warmup, ms_per_step=ms / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(WORKLOAD, workload="config5: " + WORKLOAD["workload"][len("config2: "):] +
+                            f"; {G} images in total, {per} per GPU in batches of {Bc}, statistic fit all-reduced over the ranks",
+                            global_batch=G, per_gpu_batch=per, parallelism=f"image-sharded x{ctx.world}",
+                            patchnorm_fit=fit, l2="805 MB per 256-image batch, larger than L2"),
+                gpu_launches=launches)
+    return ctx.finish(line)
 
 
 def stage_times(torch, D, pipe, x, dev, reps=3):
