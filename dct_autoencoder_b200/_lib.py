@@ -28,6 +28,8 @@ SIGNATURES = {
     "dcta_last_error": [],
     "dcta_abi_version": [],
     "dcta_compiled_arch": [],
+    "dcta_basis_elems": [c_int, c_int, c_int],
+    "dcta_basis_init": [c_int, c_int, c_int, P, P, P],
     "dcta_rgb_to_ipt": [P, P, c_int64, c_int64, P, P, P],
     "dcta_ipt_to_rgb": [P, P, c_int64, c_int64, P, P, P],
     "dcta_u8_to_unit_f32": [P, P, c_int64, P],
@@ -95,7 +97,8 @@ SIGNATURES = {
     "dcta_wire_pack": [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P],
     "dcta_wire_unpack": [P, c_int64, c_int, c_int, c_int, P, P, P, P],
 }
-_RESTYPES = {"dcta_last_error": c_char_p}
+_RESTYPES = {"dcta_last_error": c_char_p, "dcta_basis_elems": c_int64}
+BASIS_F32, BASIS_SPLIT_FWD, BASIS_SPLIT_INV, BASIS_FOLD_FWD, BASIS_FOLD_INV = range(5)
 REDUCE_SCRATCH = 2048  # DCTA_REDUCE_SCRATCH
 
 # kernels launched by one call of each entry point (memsets not counted)

@@ -19,3 +19,99 @@ void set_error(const char* fmt, ...) {
 extern "C" const char* dcta_last_error(void) { return dcta::g_err; }
 extern "C" int dcta_abi_version(void) { return 2; }
 extern "C" int dcta_compiled_arch(void) { return 100; }
+
+// ------------------------------------------------------------------------------ basis tables (host side)
+// The orthonormal DCT-II matrix C_n[q, m] = s_q cos(pi (2m + 1) q / 2n), s_0 = sqrt(1/n), s_q = sqrt(2/n)
+// (the definition behind util.py:333-338 / torch_dct "ortho"), evaluated in double and laid out as each GEMM path
+// reads it.  Pure host arithmetic into caller-provided HOST buffers: the caller uploads them once per
+// (n, k, layout) and keeps the device copies (the "basis-table cache handle" of the boundary is the caller's).
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include <vector>
+
+namespace dcta {
+static const double kBasisScale = 1024.0;      // kScaleBasis (gemm_tc.cu) == kFScaleBasis (dct_fold.cu)
+
+static double basis_at(int n, int q, int m) {
+    if (q == 0) return sqrt(1.0 / n);
+    return cos(M_PI * (2.0 * m + 1.0) * q / (2.0 * n)) * sqrt(2.0 / n);
+}
+static void split_store(double v, __half* hi, __half* lo, int64_t i) {
+    const __half h = __double2half(v);
+    hi[i] = h;
+    lo[i] = __double2half(v - (double)__half2float(h));
+}
+static int64_t round8(int64_t v) { return (v + 7) / 8 * 8; }
+}  // namespace dcta
+
+extern "C" int64_t dcta_basis_elems(int layout, int n, int k) {
+    using namespace dcta;
+    switch (layout) {
+        case DCTA_BASIS_F32: return (int64_t)k * n;
+        case DCTA_BASIS_SPLIT_FWD: return (int64_t)k * round8(n);
+        case DCTA_BASIS_SPLIT_INV: return (int64_t)n * round8(k);
+        case DCTA_BASIS_FOLD_FWD: return 2ll * (k / 2) * (n / 2);
+        case DCTA_BASIS_FOLD_INV: return 2ll * (n / 2) * round8(k / 2);
+    }
+    return -1;
+}
+
+extern "C" int dcta_basis_init(int layout, int n, int k, void* hi_host, void* lo_host, float* row_scale_host) {
+    using namespace dcta;
+    DCTA_REQUIRE(n > 0 && k > 0 && k <= n, "basis_init: needs 0 < k <= n");
+    DCTA_REQUIRE(hi_host != nullptr, "basis_init: null output");
+    if (layout == DCTA_BASIS_F32) {
+        float* out = static_cast<float*>(hi_host);
+        for (int q = 0; q < k; ++q)
+            for (int m = 0; m < n; ++m) out[(int64_t)q * n + m] = (float)basis_at(n, q, m);
+        return DCTA_OK;
+    }
+    DCTA_REQUIRE(lo_host != nullptr, "basis_init: null lo plane");
+    __half* hi = static_cast<__half*>(hi_host);
+    __half* lo = static_cast<__half*>(lo_host);
+    const int64_t elems = dcta_basis_elems(layout, n, k);
+    DCTA_REQUIRE(elems > 0, "basis_init: unknown layout %d", layout);
+    for (int64_t i = 0; i < elems; ++i) { hi[i] = __double2half(0.0); lo[i] = hi[i]; }
+    switch (layout) {
+        case DCTA_BASIS_SPLIT_FWD: {          // (k, round8(n)): C * 2^10, row 0 stored as the exact constant 32
+            DCTA_REQUIRE(row_scale_host != nullptr, "basis_init: forward layouts need row_scale");
+            const int64_t ld = round8(n);
+            for (int q = 0; q < k; ++q) {
+                for (int m = 0; m < n; ++m) split_store(q == 0 ? 32.0 : basis_at(n, q, m) * kBasisScale, hi, lo, q * ld + m);
+                row_scale_host[q] = (float)(q == 0 ? sqrt(1.0 / n) / 32.0 : 1.0 / kBasisScale);
+            }
+            return DCTA_OK;
+        }
+        case DCTA_BASIS_SPLIT_INV: {          // (n, round8(k)): (C * 2^10)^T
+            const int64_t ld = round8(k);
+            for (int m = 0; m < n; ++m)
+                for (int q = 0; q < k; ++q) split_store(basis_at(n, q, m) * kBasisScale, hi, lo, m * ld + q);
+            return DCTA_OK;
+        }
+        case DCTA_BASIS_FOLD_FWD: {           // (2, k/2, n/2): group g = rows of parity g, first half of the samples
+            DCTA_REQUIRE(row_scale_host != nullptr, "basis_init: forward layouts need row_scale");
+            DCTA_REQUIRE(n % 2 == 0 && k % 2 == 0, "basis_init: the folded layouts need even n and k");
+            const int k2 = k / 2, n2 = n / 2;
+            for (int g = 0; g < 2; ++g)
+                for (int j = 0; j < k2; ++j) {
+                    const int q = 2 * j + g;
+                    for (int m = 0; m < n2; ++m)
+                        split_store(q == 0 ? 32.0 : basis_at(n, q, m) * kBasisScale, hi, lo, ((int64_t)g * k2 + j) * n2 + m);
+                    row_scale_host[g * k2 + j] = (float)(q == 0 ? sqrt(1.0 / n) / 32.0 : 1.0 / kBasisScale);
+                }
+            return DCTA_OK;
+        }
+        case DCTA_BASIS_FOLD_INV: {           // (2, n/2, round8(k/2)): the transposes
+            DCTA_REQUIRE(n % 2 == 0 && k % 2 == 0, "basis_init: the folded layouts need even n and k");
+            const int k2 = k / 2, n2 = n / 2;
+            const int64_t ld = round8(k2);
+            for (int g = 0; g < 2; ++g)
+                for (int m = 0; m < n2; ++m)
+                    for (int j = 0; j < k2; ++j)
+                        split_store(basis_at(n, 2 * j + g, m) * kBasisScale, hi, lo, ((int64_t)g * n2 + m) * ld + j);
+            return DCTA_OK;
+        }
+    }
+    return DCTA_ERR_INVALID_ARG;
+}

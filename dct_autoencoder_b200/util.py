@@ -154,13 +154,25 @@ def ipt_to_rgb(x: torch.Tensor) -> torch.Tensor:
     return _colorspace(x, "dcta_ipt_to_rgb", _M_IPT_INV, _M_LMS2RGB)
 
 
+def _basis_tables(layout: int, n: int, k: int, shape, with_scale: bool):
+    """Host tables from ``dcta_basis_init`` (csrc/api.cu: the one place the DCT basis is generated, in double)."""
+    lib = _lib.load()
+    elems = int(lib.dcta_basis_elems(layout, n, k))
+    assert elems == int(np.prod(shape)), (layout, n, k, shape, elems)
+    f32 = layout == _lib.BASIS_F32
+    hi = np.empty(shape, np.float32 if f32 else np.float16)
+    lo = None if f32 else np.empty(shape, np.float16)
+    rs = np.empty(int(np.prod(shape[:-1])), np.float32) if with_scale else None
+    rc = lib.dcta_basis_init(layout, n, k, hi.ctypes.data, None if lo is None else lo.ctypes.data,
+                             None if rs is None else rs.ctypes.data)
+    if rc != 0:
+        raise _lib.DctaError(f"dcta_basis_init failed ({rc}): {_lib.last_error()}")
+    return hi, lo, rs
+
+
 @lru_cache(maxsize=64)
 def _basis_host(n: int, k: int) -> np.ndarray:
-    q = np.arange(k, dtype=np.float64)[:, None]
-    m = np.arange(n, dtype=np.float64)[None, :]
-    c = np.cos(np.pi * (2 * m + 1) * q / (2 * n)) * math.sqrt(2.0 / n)
-    c[0, :] = math.sqrt(1.0 / n)
-    return c.astype(np.float32)
+    return _basis_tables(_lib.BASIS_F32, n, k, (k, n), False)[0]
 
 
 _BASIS_CACHE = {}
@@ -313,24 +325,14 @@ def split_basis(n: int, k: int, device, transposed: bool):
     hit = _SPLIT_CACHE.get(key)
     if hit is not None:
         return hit
-    q = np.arange(k, dtype=np.float64)[:, None]
-    m = np.arange(n, dtype=np.float64)[None, :]
-    c = np.cos(np.pi * (2 * m + 1) * q / (2 * n)) * math.sqrt(2.0 / n)
-    c[0, :] = math.sqrt(1.0 / n)
     if not transposed:
         ld = _round8(n)
-        s = np.zeros((k, ld), np.float64)
-        s[:, :n] = c * _SCALE_BASIS
-        s[0, :n] = 32.0
-        rs = np.full(k, 1.0 / _SCALE_BASIS, np.float64)
-        rs[0] = math.sqrt(1.0 / n) / 32.0
-        row_scale = torch.from_numpy(rs.astype(np.float32)).to(device)
+        hi, lo, rs = _basis_tables(_lib.BASIS_SPLIT_FWD, n, k, (k, ld), True)
+        row_scale = torch.from_numpy(rs).to(device)
     else:
         ld = _round8(k)
-        s = np.zeros((n, ld), np.float64)
-        s[:, :k] = (c * _SCALE_BASIS).T
+        hi, lo, _ = _basis_tables(_lib.BASIS_SPLIT_INV, n, k, (n, ld), False)
         row_scale = None
-    hi, lo = _split_host(s)
     out = (torch.from_numpy(hi).to(device), torch.from_numpy(lo).to(device), row_scale, ld)
     _SPLIT_CACHE[key] = out
     return out
@@ -467,23 +469,12 @@ def fold_basis(n: int, k: int, device, transposed: bool):
     if hit is not None:
         return hit
     k2, n2 = k // 2, n // 2
-    q = np.arange(k, dtype=np.float64)[:, None]
-    m = np.arange(n2, dtype=np.float64)[None, :]
-    c = np.cos(np.pi * (2 * m + 1) * q / (2 * n)) * math.sqrt(2.0 / n)
-    c[0, :] = math.sqrt(1.0 / n)
-    groups = np.stack([c[0::2], c[1::2]])            # (2, k/2, n/2)
     if not transposed:
-        s = groups * _SCALE_BASIS
-        s[0, 0, :] = 32.0
-        rs = np.full((2, k2), 1.0 / _SCALE_BASIS, np.float64)
-        rs[0, 0] = math.sqrt(1.0 / n) / 32.0
-        row_scale = torch.from_numpy(rs.astype(np.float32)).to(device)
+        hi, lo, rs = _basis_tables(_lib.BASIS_FOLD_FWD, n, k, (2, k2, n2), True)
+        row_scale = torch.from_numpy(rs.reshape(2, k2)).to(device)
     else:
-        ld = _round8(k2)
-        s = np.zeros((2, n2, ld), np.float64)
-        s[:, :, :k2] = np.transpose(groups * _SCALE_BASIS, (0, 2, 1))
+        hi, lo, _ = _basis_tables(_lib.BASIS_FOLD_INV, n, k, (2, n2, _round8(k2)), False)
         row_scale = None
-    hi, lo = _split_host(s)
     out = (torch.from_numpy(hi).to(device), torch.from_numpy(lo).to(device), row_scale)
     _FOLD_CACHE[key] = out
     return out

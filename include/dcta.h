@@ -37,6 +37,26 @@ int dcta_abi_version(void);
 /* Compute capability the library was compiled for (100 for sm_100a). */
 int dcta_compiled_arch(void);
 
+/* ------------------------------------------------------------------ basis tables ---------- */
+/* The orthonormal DCT-II matrix behind UT:333-338 (torch_dct "ortho"): C_n[q, m] = s_q cos(pi (2m+1) q / 2n),
+ * evaluated in double on the HOST and written, in the layout the named GEMM path reads, into caller-provided
+ * HOST buffers (no allocation, no device work: upload once per (layout, n, k) and keep the device copies).
+ *   DCTA_BASIS_F32        hi = float (k, n)                                  -> dcta_dct2_fwd / dcta_dct2_inv
+ *   DCTA_BASIS_SPLIT_FWD  hi, lo = fp16 (k, round8(n)), C * 2^10 with row 0 stored as the constant 32;
+ *                         row_scale (k) undoes the scaling                    -> dcta_dct2_fwd_tc
+ *   DCTA_BASIS_SPLIT_INV  hi, lo = fp16 (n, round8(k)) = the transpose        -> dcta_dct2_inv_tc
+ *   DCTA_BASIS_FOLD_FWD   hi, lo = fp16 (2, k/2, n/2): group g holds rows 2j+g over the first half of the samples;
+ *                         row_scale (2, k/2)                                  -> dcta_dct2_fwd_fold[_codes]
+ *   DCTA_BASIS_FOLD_INV   hi, lo = fp16 (2, n/2, round8(k/2)) = the transposes -> dcta_dct2_inv_fold
+ * hi + lo carries 22 significand bits of every entry.  dcta_basis_elems: elements per plane (-1: unknown layout). */
+#define DCTA_BASIS_F32 0
+#define DCTA_BASIS_SPLIT_FWD 1
+#define DCTA_BASIS_SPLIT_INV 2
+#define DCTA_BASIS_FOLD_FWD 3
+#define DCTA_BASIS_FOLD_INV 4
+int64_t dcta_basis_elems(int layout, int n, int k);
+int dcta_basis_init(int layout, int n, int k, void* hi_host, void* lo_host, float* row_scale_host);
+
 /* ------------------------------------------------------------------ colour space ---------- */
 /* UT:70-82 rgb_to_ipt (rgb_to_lms UT:56-60, channel_mult UT:46-47).
  * rgb, ipt: (n_img, 3, plane).  m_rgb2lms_host, m_ipt_host: 3x3 row-major fp32 HOST matrices

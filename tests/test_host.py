@@ -377,3 +377,37 @@ def test_table_cache_is_keyed_by_device_and_evicts_lru(D):
         assert fe._keepalive == [c] and c is a
     finally:
         torch.Tensor.pin_memory = orig
+
+
+@pytest.mark.parametrize("n,k", [(512, 448), (256, 252), (1024, 448), (90, 84), (16, 16)])
+def test_basis_init_matches_the_float64_definition(D, n, k):
+    """dcta_basis_init (host arithmetic in libdcta, no GPU): every layout equals the orthonormal DCT-II definition
+    evaluated with numpy in float64 -- fp32 table to the last bit, hi + lo of the split tables to 2^-21 relative
+    (and hi/lo themselves bit for bit wherever numpy's cos and libm's agree to the double's last place)."""
+    lib = D._lib.load()
+    L = D._lib
+    q = np.arange(k, dtype=np.float64)[:, None]
+    m = np.arange(n, dtype=np.float64)[None, :]
+    c = np.cos(np.pi * (2 * m + 1) * q / (2 * n)) * np.sqrt(2.0 / n)
+    c[0, :] = np.sqrt(1.0 / n)
+    from dct_autoencoder_b200.util import _basis_tables, _round8
+    f32, _, _ = _basis_tables(L.BASIS_F32, n, k, (k, n), False)
+    assert np.abs(f32.astype(np.float64) - c).max() <= 2.0 ** -24 * np.abs(c).max() * 1.01
+    assert (f32 != c.astype(np.float32)).mean() < 1e-3
+    hi, lo, rs = _basis_tables(L.BASIS_SPLIT_FWD, n, k, (k, _round8(n)), True)
+    got = (hi.astype(np.float64) + lo.astype(np.float64))[:, :n] * rs.astype(np.float64)[:, None]
+    assert np.abs(got - c).max() <= 2.0 ** -21 * np.abs(c).max()
+    assert np.all(hi[0, :n] == 32.0) and np.all(lo[0, :n] == 0.0) and not hi[:, n:].any()
+    hi_t, lo_t, _ = _basis_tables(L.BASIS_SPLIT_INV, n, k, (n, _round8(k)), False)
+    got = (hi_t.astype(np.float64) + lo_t.astype(np.float64))[:, :k].T / 1024.0
+    assert np.abs(got - c).max() <= 2.0 ** -21 * np.abs(c).max()
+    if n % 2 == 0 and k % 2 == 0:
+        fh, fl, frs = _basis_tables(L.BASIS_FOLD_FWD, n, k, (2, k // 2, n // 2), True)
+        got = (fh.astype(np.float64) + fl.astype(np.float64)) * frs.reshape(2, k // 2, 1).astype(np.float64)
+        want = np.stack([c[0::2, :n // 2], c[1::2, :n // 2]])
+        assert np.abs(got - want).max() <= 2.0 ** -21 * np.abs(c).max()
+        ih, il, _ = _basis_tables(L.BASIS_FOLD_INV, n, k, (2, n // 2, _round8(k // 2)), False)
+        got = np.transpose((ih.astype(np.float64) + il.astype(np.float64))[:, :, :k // 2], (0, 2, 1)) / 1024.0
+        assert np.abs(got - want).max() <= 2.0 ** -21 * np.abs(c).max()
+    assert lib.dcta_basis_elems(99, n, k) == -1
+    assert lib.dcta_basis_init(L.BASIS_F32, 8, 9, f32.ctypes.data, None, None) == -1      # k > n
