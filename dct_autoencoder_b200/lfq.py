@@ -3,8 +3,10 @@ same keyword-only constructor, ``forward(x, mask) -> (x, indices, commit_loss, d
 ``indices_to_codes``, buffers ``mask`` (persistent), ``zero`` / ``codebook`` (not persistent).
 
 The sign quantisation, the MSB-first bit packing into int64 indices, ``indices_to_codes``, the
-masked commitment loss and the ``distance`` tensor are libdcta kernels; the optional
-``project_in`` / ``project_out`` are plain ``nn.Linear`` library GEMMs, as in the reference.
+masked commitment loss and the ``distance`` tensor are libdcta kernels.  The optional ``project_in`` /
+``project_out`` are ``nn.Linear`` modules (same state-dict keys as the reference); without autograd (eval under
+``torch.no_grad``) they run on the split-precision tcgen05 GEMM (linear.py), with autograd PyTorch differentiates
+them as in the reference.
 """
 from math import ceil, log2
 
@@ -12,6 +14,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from .linear import linear_bias_rows
 from .util import to_device_f32
 
 
@@ -124,6 +127,14 @@ class LFQ(nn.Module):
     def dtype(self):
         return self.zero.dtype
 
+    def _project(self, lin: nn.Module, x: torch.Tensor) -> torch.Tensor:
+        """project_in / project_out: libdcta GEMM when nothing has to be differentiated."""
+        if not self.has_projections:
+            return x
+        if torch.is_grad_enabled() or not x.is_cuda:
+            return lin(x)
+        return linear_bias_rows(x, lin).to(x.dtype)
+
     def _flat_tokens(self, t: torch.Tensor) -> int:
         return t.numel() // t.shape[-1]
 
@@ -142,7 +153,7 @@ class LFQ(nn.Module):
                       float(self.codebook_scale), _lib.stream_ptr(idx.device))
         codes = codes.to(self.dtype)
         if project_out:
-            codes = self.project_out(codes)
+            codes = self._project(self.project_out, codes)
         if is_img_or_video:
             codes = codes.movedim(-1, 1)     # 'b ... d -> b d ...'
         return codes
@@ -160,7 +171,7 @@ class LFQ(nn.Module):
         assert x.shape[-1] == self.dim, f"expected dimension of {self.dim} but received {x.shape[-1]}"
         _lib.require_cuda(x)
 
-        x = self.project_in(x)
+        x = self._project(self.project_in, x)
         b, n, _ = x.shape
         c, d = self.num_codebooks, self.codebook_dim
         original_input = x
@@ -183,7 +194,7 @@ class LFQ(nn.Module):
             distance = self.zero
             commit_loss = self.zero
 
-        out = self.project_out(out)
+        out = self._project(self.project_out, out)
 
         if is_img_or_video:
             out = out.reshape(out.shape[0], *spatial, out.shape[-1]).movedim(-1, 1)

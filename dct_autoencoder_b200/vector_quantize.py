@@ -16,6 +16,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from .linear import linear_bias_rows
 from .util import to_device_f32
 
 
@@ -131,8 +132,16 @@ class VectorQuantize(nn.Module):
         codes = torch.stack([codebook[i][flat[..., i]] for i in range(h)], dim=2)  # b n h d
         return codes.reshape(*indices.shape[:-1], -1)
 
+    def _project(self, lin: nn.Module, x: torch.Tensor) -> torch.Tensor:
+        """project_in / project_out (vector_quantize.py:869, 1028) on the libdcta GEMM when no autograd is needed."""
+        if not self.has_projections:
+            return x
+        if torch.is_grad_enabled() or not x.is_cuda:
+            return lin(x)
+        return linear_bias_rows(x, lin).to(x.dtype)
+
     def get_output_from_indices(self, indices):
-        return self.project_out(self.get_codes_from_indices(indices))
+        return self._project(self.project_out, self.get_codes_from_indices(indices))
 
     def forward(self, x, indices=None, mask=None, sample_codebook_temp=None, freeze_codebook=False):
         """vector_quantize.py:837-1050, eval branch."""
@@ -153,7 +162,7 @@ class VectorQuantize(nn.Module):
         if need_transpose:
             x = x.transpose(1, 2)
         _lib.require_cuda(x)
-        x = self.project_in(x)
+        x = self._project(self.project_in, x)
         b, n, _ = x.shape
         h, embed = self.heads, self._codebook.embed
         d = embed.shape[-1]
@@ -179,7 +188,7 @@ class VectorQuantize(nn.Module):
         if only_one:
             ind = ind[:, 0]
         loss = torch.tensor([0.0], device=x.device)
-        q = self.project_out(q)
+        q = self._project(self.project_out, q)
         if need_transpose:
             q = q.transpose(1, 2)
         if self.accept_image_fmap:

@@ -374,6 +374,24 @@ int dcta_decode_codes_split(const int64_t* codes, const int32_t* slot_map, const
                             int W, float eps, int c, int d, float scale, void* y_hi, void* y_lo,
                             float* dc, void* stream);
 
+/* ------------------------------------------------------------------ model glue */
+/* The row-wise pieces of modeling_dct_autoencoder.py:60-63 (to_patch_embedding = Linear + LayerNorm(eps 1e-4)),
+ * :101-112 ((channel, h, w) position embeddings), :85-88 (proj_out = LayerNorm + Linear) on packed token rows; the
+ * contractions themselves go through dcta_gemm_split.
+ *
+ * dcta_ln_pos_rows: out[t] = LN(x[t]) * gamma + beta   [gamma/beta nullable together: no LayerNorm]
+ *                            + bias                     [nullable]
+ *                            + pos_h[positions[t,0]] + pos_w[positions[t,1]] + pos_c[channels[t]]   [nullable together]
+ *   x, out (n_rows, f) fp32, out must not alias x; biased variance, eps inside the square root (torch layer_norm).
+ * dcta_split_rows_rowscale: rows (n_rows, d) [-> LayerNorm when gamma given] -> fp16 hi/lo planes (n_rows, ld) of
+ *   y * s_row with a power-of-two scale per row (max|y| * s_row in [2^9, 2^10)), and row_scale[t] = post / s_row:
+ *   the `row_scale` argument of dcta_gemm_split (post = 1 / the scale of the other operand). */
+int dcta_ln_pos_rows(const float* x, const float* gamma, const float* beta, float eps, const float* bias,
+                     const float* pos_c, const float* pos_h, const float* pos_w, const int64_t* channels,
+                     const int64_t* positions, float* out, int64_t n_rows, int f, void* stream);
+int dcta_split_rows_rowscale(const float* x, const float* gamma, const float* beta, float eps, void* hi, void* lo,
+                             float* row_scale, float post, int64_t n_rows, int d, int64_t ld, void* stream);
+
 /* ------------------------------------------------------------------ VectorQuantize -------- */
 /* VQ:29-33 cdist + VQ:467-469 argmax(-dist) + VQ:222-226/477 gather, never materialising the
  * (n_tok, n_codes) distance matrix.

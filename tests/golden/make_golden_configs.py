@@ -16,6 +16,10 @@ config1.npz   BASELINE config 1: the reference's own images/*.jpg (13 files; `bo
               one full-precision reconstruction; psnr (16,) of each reconstruction against its input; lfq16_* = the
               conf/patch14-l.json quantiser (LFQ dim 196, 8192 x 16 codebooks, 196->208->196 projections,
               manual_seed(2)) applied to the first 128 PatchNorm-normalised tokens of image 0.
+glue.npz      the reference's DCTAutoencoder (modeling_dct_autoencoder.py) with its two CLIPEncoder stacks replaced by
+              the identity: encode() (to_patch_embedding + encoder position embeddings + LFQ 256 -> 16 x 13 bits ->
+              256) and decode_from_codes() (indices_to_codes + decoder position embeddings + proj_out + inverse
+              PatchNorm) on a packed 3-image batch; every parameter is stored so the test loads the same weights.
 to_dict.json  the reference's to_dict (DP:54-87) on a packed 3-image batch with 3-codebook codes, and
 to_dict.npz   the batch it was computed from + from_dict's (DP:90-122) outputs for object 1.
 """
@@ -117,4 +121,55 @@ save("to_dict", patches_shape=np.asarray(bt.patches.shape), key_pad_mask=bt.key_
      fd_channels=dp1.patch_channels, fd_positions=dp1.patch_positions, fd_key_pad_mask=dp1.key_pad_mask,
      fd_image_ids=dp1.batched_image_ids, fd_attn_mask=dp1.attn_mask, fd_codes=codes1,
      fd_patches=dp1.patches)
+
+# ---------------------------------------------------------------------------- model glue (identity transformer stacks)
+import types  # noqa: E402
+
+from dct_autoencoder.configuration_dct_autoencoder import DCTAutoencoderConfig  # noqa: E402
+from dct_autoencoder.modeling_dct_autoencoder import DCTAutoencoder  # noqa: E402
+
+torch.manual_seed(31)
+tiny = dict(hidden_size=256, intermediate_size=64, num_attention_heads=2, num_hidden_layers=1)
+cfg = DCTAutoencoderConfig(image_channels=3, patch_size=14, max_patch_h=6, max_patch_w=6, vq_codebook_size=8192,
+                           vq_num_codebooks=16, vq_type="lfq", encoder_config=tiny, decoder_config=tiny)
+model = DCTAutoencoder(cfg).eval()
+
+
+class _IdentityStack(torch.nn.Module):
+    def forward(self, hidden, attention_mask=None):
+        return types.SimpleNamespace(last_hidden_state=hidden)
+
+
+model.encoder, model.decoder = _IdentityStack(), _IdentityStack()
+with torch.no_grad():
+    model.to_patch_embedding[1].weight.uniform_(0.5, 1.5)
+    model.to_patch_embedding[1].bias.normal_(0, 0.1)
+    model.proj_out[0].weight.uniform_(0.5, 1.5)
+    model.proj_out[0].bias.normal_(0, 0.1)
+    model.patchnorm.median.normal_(0, 0.2)
+    model.patchnorm.b.uniform_(0.2, 1.0)
+model.patchnorm.frozen = True
+fx = DCTAutoencoderFeatureExtractor(channels=3, patch_size=14, sample_patches_beta=0.0, max_patch_h=6, max_patch_w=6,
+                                    max_seq_len=120)
+ims = [torch.rand(3, 70, 56), torch.rand(3, 42, 84), torch.rand(3, 84, 84)]
+bt = next(fx.iter_batches(iter([dict_collate([fx.preprocess(im) for im in ims])]), None))
+gl = dict(in_patches=bt.patches.clone(), key_pad_mask=bt.key_pad_mask, image_ids=bt.batched_image_ids,
+          channels=bt.patch_channels, positions=bt.patch_positions,
+          patch_sizes=np.asarray(bt.patch_sizes, dtype=np.int64), original_sizes=np.asarray(bt.original_sizes, dtype=np.int64))
+with torch.no_grad():
+    emb = model.to_patch_embedding(model.patchnorm(bt))
+    enc, codes, commit, dist = model.encode(bt.shallow_copy(), do_normalize=True)
+    gl.update(embedded=emb, enc_patches=enc.patches, codes=codes.to(torch.int16))
+    dec = model.decode_from_codes(codes, do_inv_norm=True, key_pad_mask=bt.key_pad_mask, attn_mask=bt.attn_mask,
+                                  batched_image_ids=bt.batched_image_ids, patch_channels=bt.patch_channels,
+                                  patch_positions=bt.patch_positions, patch_sizes=bt.patch_sizes,
+                                  original_sizes=bt.original_sizes)
+    gl.update(dec_patches=dec.patches)
+    pre = model.vq_model.project_in(model.to_patch_embedding(model.patchnorm(bt)) +
+                                    model.encoder_pos_embed_height[bt.h_indices] + model.encoder_pos_embed_width[bt.w_indices] +
+                                    model.encoder_pos_embed_channel[bt.patch_channels])
+    gl.update(lfq_pre=pre)
+for k, v in model.state_dict().items():
+    gl["w:" + k] = v
+save("glue", **gl)
 print("done")
