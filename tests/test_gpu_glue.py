@@ -34,7 +34,7 @@ def test_linear_rows_matches_float64(D, t, k, n):
     y = linear_rows(x, w)
     ref = x.double() @ w.double().T
     scale = (x.double().abs() @ w.double().abs().T)                    # forward error bound of an fp32 dot product
-    assert float(((y.double() - ref).abs() / scale).max()) < 4e-7
+    assert float(((y.double() - ref).abs() / scale).max()) < 2e-6      # (a sequential fp32 dot product: up to k * 2^-24; the tensor-core accumulator truncates)
     ln = torch.nn.LayerNorm(k, eps=1e-4).cuda()
     with torch.no_grad():
         ln.weight.uniform_(0.5, 1.5)
