@@ -89,6 +89,10 @@ SIGNATURES = {
                             c_float, c_float, c_int, c_int, c_float, P, P, P, P, P, P, P],
     "dcta_decode_codes_split": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, c_int,
                                 P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P],
+    "dcta_lfq_entropy_ctas": [],
+    "dcta_lfq_entropy_factorized": [P, P, c_int64, c_int, c_int, c_float, c_float, c_float, P, P, P, P],
+    "dcta_lfq_entropy_factorized_backward": [P, P, c_int64, c_int, c_int, c_float, c_float, P, P, P, P, P],
+    "dcta_lfq_commit_backward": [P, P, P, P, P, c_int64, c_int, c_float, P],
     "dcta_ln_pos_rows": [P, P, P, c_float, P, P, P, P, P, P, P, c_int64, c_int, P],
     "dcta_split_rows_rowscale": [P, P, P, c_float, P, P, P, c_float, c_int64, c_int, c_int64, P],
     "dcta_row_sumsq": [P, P, c_int64, c_int, P],
@@ -115,7 +119,8 @@ KERNELS_PER_CALL = {
     "dcta_gemm_split": 1, "dcta_split_f32": 1, "dcta_rgb_to_ipt_split": 2, "dcta_unpatchify_split": 1,
     "dcta_split_planes_centered": 2, "dcta_split_coef_planes": 1,
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,
-    "dcta_ln_pos_rows": 1, "dcta_split_rows_rowscale": 1,
+    "dcta_ln_pos_rows": 1, "dcta_split_rows_rowscale": 1, "dcta_lfq_entropy_ctas": 0, "dcta_lfq_entropy_factorized": 2,
+    "dcta_lfq_entropy_factorized_backward": 1, "dcta_lfq_commit_backward": 2,
     "dcta_row_sumsq": 1, "dcta_split_rows": 1, "dcta_vq_nearest_tc": 2,
     "dcta_pack_codes_lfq": 2, "dcta_decode_codes_split": 1,
     "dcta_fold_supported": 0, "dcta_fold_codes_supported": 0, "dcta_rgb_to_ipt_fold": 2, "dcta_rgb_u8_to_ipt_fold": 2, "dcta_unfold_ipt_to_rgb_u8": 1, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,

@@ -15,7 +15,7 @@ from torch import nn
 
 from . import _lib
 from .linear import linear_bias_rows
-from .util import to_device_f32
+from .util import FactorizedDistance, to_device_f32
 
 
 def _exists(v):
@@ -42,10 +42,16 @@ class _CommitLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, mask = ctx.saved_tensors
-        q = torch.where(x > 0, ctx.scale, -ctx.scale)
-        m = mask.reshape(mask.shape + (1,) * (x.ndim - mask.ndim)).to(x.dtype)
-        denom = mask.sum().to(x.dtype) * x.shape[-1]
-        return g * 2 * (x - q) * m / denom, None, None
+        xf = to_device_f32(x.detach())
+        cd = xf.shape[-1]
+        m = mask.reshape(-1).to(torch.uint8).contiguous()
+        gx = torch.empty_like(xf)
+        nv = torch.empty(1, dtype=torch.float32, device=xf.device)
+        gout = g.detach().reshape(1).to(torch.float32).contiguous()
+        with torch.cuda.device(xf.device):
+            _lib.call("dcta_lfq_commit_backward", _lib.ptr(xf), _lib.ptr(m), _lib.ptr(gout), _lib.ptr(nv), _lib.ptr(gx),
+                      xf.numel() // cd, cd, float(ctx.scale), _lib.stream_ptr(xf.device))
+        return gx.to(x.dtype), None, None
 
 
 class _Distance(torch.autograd.Function):
@@ -79,8 +85,13 @@ class LFQ(nn.Module):
         num_codebooks=1,
         keep_num_codebooks_dim=None,
         codebook_scale=1.0,
+        dense_distance_limit=2 ** 28,
     ):
+        """``dense_distance_limit`` (not in the reference): in training mode ``forward`` returns the dense ``distance``
+        tensor of lfq.py:191 while it has at most this many elements, and a ``util.FactorizedDistance`` -- which
+        ``util.compute_entropy_loss`` consumes without ever forming (b, n, c, 2^d) -- beyond it."""
         super().__init__()
+        self.dense_distance_limit = dense_distance_limit
         assert _exists(dim) or _exists(codebook_size), "either dim or codebook_size must be specified for LFQ"
         assert not _exists(codebook_size) or log2(codebook_size).is_integer(), (
             f"your codebook size must be a power of 2 for lookup free quantization "
@@ -187,7 +198,10 @@ class LFQ(nn.Module):
         if self.training:
             xa = self.activation(x)
             out = xa - xa.detach() + quantized          # straight-through (lfq.py:179-181)
-            distance = _Distance.apply(original_input.reshape(b, n, c, d), self.codebook_scale, self.codebook)
+            if b * n * c * 2 ** d <= self.dense_distance_limit:
+                distance = _Distance.apply(original_input.reshape(b, n, c, d), self.codebook_scale, self.codebook)
+            else:
+                distance = FactorizedDistance(original_input.reshape(b, n, c, d), self.codebook_scale)
             commit_loss = _CommitLoss.apply(original_input, mask.to(x.device), self.codebook_scale)
         else:
             out = quantized

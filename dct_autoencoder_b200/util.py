@@ -269,8 +269,75 @@ def masked_mean(x: torch.Tensor, m: torch.Tensor, dim=None):
     return x.sum() if dim is None else x.sum(dim=dim)
 
 
-def compute_entropy_loss(affinity: torch.Tensor, mask: torch.Tensor, temperature=0.01, eps=1e-9):
-    """util.py:355-387 on a dense ``affinity`` (b, s, d, z); ``mask`` (b, s) False at padding."""
+class FactorizedDistance:
+    """What ``LFQ.forward`` returns as ``distance`` at scale: the quantiser's input ``x`` (b, n, c, d) and the codebook
+    scale instead of the dense ``-2 x . codebook^T`` tensor (b, n, c, 2^d) of lfq.py:191 (721 GB at 786 k tokens x 14 x
+    2^14).  ``compute_entropy_loss`` -- its one consumer (main.py:63-65, modeling_dct_autoencoder.py:195-199) -- evaluates
+    the same loss from it through the factorisation of the softmax over a +-s codebook; ``dense()`` materialises the
+    reference's tensor for small shapes."""
+
+    def __init__(self, x: torch.Tensor, codebook_scale: float):
+        self.x, self.codebook_scale = x, float(codebook_scale)
+        self.dtype, self.device = x.dtype, x.device
+
+    @property
+    def shape(self):
+        return tuple(self.x.shape[:-1]) + (2 ** self.x.shape[-1],)
+
+    def float(self):
+        return self
+
+    def to(self, *_args, **_kw):
+        return self
+
+    def dense(self) -> torch.Tensor:
+        x = to_device_f32(self.x.detach())
+        b, n, c, d = x.shape
+        out = torch.empty((b, n, c, 2 ** d), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("dcta_lfq_distance", _lib.ptr(x), _lib.ptr(out), b * n, c, d, self.codebook_scale,
+                      _lib.stream_ptr(x.device))
+        return out
+
+
+class _FactorizedEntropy(torch.autograd.Function):
+    """util.py:355-387 on a FactorizedDistance, forward and backward in csrc/lfq_entropy.cu."""
+
+    @staticmethod
+    def forward(ctx, x, mask, scale, temperature, eps):
+        xf = to_device_f32(x.detach())
+        b, n, c, d = xf.shape
+        dev = xf.device
+        m = mask.to(dev).reshape(b * n).to(torch.uint8).contiguous()
+        ctas = int(_lib.load().dcta_lfq_entropy_ctas())
+        partial = torch.empty(ctas * (2 ** d + 2), dtype=torch.float32, device=dev)
+        tables = torch.empty(2 * 2 ** d, dtype=torch.float32, device=dev)
+        result = torch.empty(4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("dcta_lfq_entropy_factorized", _lib.ptr(xf), _lib.ptr(m), b * n, c, d, float(scale), float(temperature),
+                      float(eps), _lib.ptr(partial), _lib.ptr(tables), _lib.ptr(result), _lib.stream_ptr(dev))
+        ctx.save_for_backward(xf, m, tables, result)
+        ctx.cfg = (float(scale), float(temperature), x.dtype)
+        return result[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        xf, m, tables, result = ctx.saved_tensors
+        scale, temperature, og = ctx.cfg
+        b, n, c, d = xf.shape
+        gx = torch.empty_like(xf)
+        gout = g.detach().reshape(1).to(torch.float32).contiguous()
+        with torch.cuda.device(xf.device):
+            _lib.call("dcta_lfq_entropy_factorized_backward", _lib.ptr(xf), _lib.ptr(m), b * n, c, d, scale, temperature,
+                      _lib.ptr(tables), _lib.ptr(result), _lib.ptr(gout), _lib.ptr(gx), _lib.stream_ptr(xf.device))
+        return gx.to(og), None, None, None, None
+
+
+def compute_entropy_loss(affinity, mask: torch.Tensor, temperature=0.01, eps=1e-9):
+    """util.py:355-387.  ``affinity``: the dense (b, s, d, z) tensor, or the ``FactorizedDistance`` that ``LFQ.forward``
+    returns in training mode at scale (differentiable w.r.t. the quantiser's input); ``mask`` (b, s) False at padding."""
+    if isinstance(affinity, FactorizedDistance):
+        return _FactorizedEntropy.apply(affinity.x, mask, affinity.codebook_scale, temperature, eps).to(affinity.dtype)
     og = affinity.dtype
     a = to_device_f32(affinity)
     b, s, d, z = a.shape

@@ -374,6 +374,27 @@ int dcta_decode_codes_split(const int64_t* codes, const int32_t* slot_map, const
                             int W, float eps, int c, int d, float scale, void* y_hi, void* y_lo,
                             float* dc, void* stream);
 
+/* ------------------------------------------------------------------ LFQ training terms at scale */
+/* UT:355-387 compute_entropy_loss applied to LFQ's distance (LFQ:191) WITHOUT the (n_tok, c, 2^d) tensor: with a +-s
+ * codebook the softmax over the 2^d sign patterns is a product of d Bernoulli distributions, p_i(1) = sigmoid(-4 s x_i / T),
+ * so the per-sample entropy is a sum of d binary entropies and the average distribution is accumulated as a sum of
+ * outer products of the 2^ceil(d/2) and 2^floor(d/2) half-products (csrc/lfq_entropy.cu).  d <= 14.
+ *   x (n_tok, c*d) fp32: the quantiser's (projected) input; mask (n_tok) uint8, 1 = valid token;
+ *   partial_scratch: dcta_lfq_entropy_ctas() * (2^d + 2) floats;
+ *   tables (2 * 2^d): [avg_probs | d avg_entropy / d avg_probs], kept for the backward pass;
+ *   result (4): [loss, valid tokens, sample entropy, avg entropy].
+ * dcta_lfq_entropy_factorized_backward: grad_x (n_tok, c*d) = grad_out[0] * d loss / d x (zero on masked tokens).
+ * dcta_lfq_commit_backward: gradient of dcta_lfq_commit_loss (LFQ:195-200): grad_out[0] * 2 (x - q) / (n_valid c d). */
+int dcta_lfq_entropy_ctas(void);
+int dcta_lfq_entropy_factorized(const float* x, const uint8_t* mask, int64_t n_tok, int c, int d, float codebook_scale,
+                                float temperature, float eps, float* partial_scratch, float* tables, float* result,
+                                void* stream);
+int dcta_lfq_entropy_factorized_backward(const float* x, const uint8_t* mask, int64_t n_tok, int c, int d,
+                                         float codebook_scale, float temperature, const float* tables, const float* result,
+                                         const float* grad_out, float* grad_x, void* stream);
+int dcta_lfq_commit_backward(const float* x, const uint8_t* mask, const float* grad_out, float* n_valid_scratch,
+                             float* grad_x, int64_t n_tok, int cd, float scale, void* stream);
+
 /* ------------------------------------------------------------------ model glue */
 /* The row-wise pieces of modeling_dct_autoencoder.py:60-63 (to_patch_embedding = Linear + LayerNorm(eps 1e-4)),
  * :101-112 ((channel, h, w) position embeddings), :85-88 (proj_out = LayerNorm + Linear) on packed token rows; the
