@@ -338,6 +338,17 @@ def compute_entropy_loss(affinity, mask: torch.Tensor, temperature=0.01, eps=1e-
     returns in training mode at scale (differentiable w.r.t. the quantiser's input); ``mask`` (b, s) False at padding."""
     if isinstance(affinity, FactorizedDistance):
         return _FactorizedEntropy.apply(affinity.x, mask, affinity.codebook_scale, temperature, eps).to(affinity.dtype)
+    if torch.is_grad_enabled() and affinity.requires_grad:
+        # a DENSE affinity that has to be differentiated (small by construction: LFQ hands out the factorised form beyond
+        # dense_distance_limit): the reference's own torch expression, so autograd sees it
+        a = affinity.to(torch.float32).reshape(-1, affinity.shape[-2], affinity.shape[-1])
+        m = mask.reshape(-1).to(a.device)
+        logits = a / temperature + eps
+        probs, log_probs = logits.softmax(dim=-1), torch.nn.functional.log_softmax(logits, dim=-1)
+        avg_probs = masked_mean(probs, m, dim=0).mean(dim=0)
+        avg_entropy = -1 * (avg_probs * (avg_probs + eps).log()).sum()
+        sample_entropy = -1 * masked_mean((probs * log_probs).sum(dim=-1), m)
+        return (sample_entropy - avg_entropy).to(affinity.dtype)
     og = affinity.dtype
     a = to_device_f32(affinity)
     b, s, d, z = a.shape

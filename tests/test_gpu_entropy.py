@@ -115,6 +115,7 @@ def test_factorized_entropy_at_the_benchmark_shape(D):
     assert bool(torch.isfinite(x.grad).all()) and not bool(x.grad[~mask].any())
     # saturated inputs: every softmax is one-hot, the loss is minus the entropy of the code histogram
     xs = torch.randn(8, 3072, c, d, device="cuda")
+    xs = torch.sign(xs) * (0.5 + xs.abs())                  # |x| >= 0.5: |u| >= 200, every Bernoulli is saturated
     ms = torch.ones(8, 3072, dtype=torch.bool, device="cuda")
     ls = compute_entropy_loss(FactorizedDistance(xs, 1.0), ms)
     idx = ((xs > 0).long() * (2 ** torch.arange(d - 1, -1, -1, device="cuda"))).sum(-1).reshape(-1)
