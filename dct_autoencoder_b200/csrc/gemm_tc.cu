@@ -39,9 +39,6 @@ struct EpiArgs {
     const float* col_scale;   // optional per-column (n) factor (persistent kernel)
     float alpha;              // global factor
     const float* alpha_dev;   // optional device scalar multiplied into alpha (scale chosen on the device)
-    const float* col_bias;    // mode 3: per-column (n) additive term, e.g. |e_j|^2
-    float* part_val;          // mode 3: (M, gridDim.x) per-row minimum of this CTA's columns
-    int32_t* part_idx;        // mode 3: its column index (first minimum)
     const float* dc;          // optional per-batch constant handled outside the GEMM (see dc_mode)
     int dc_mode;              // 0: none, 1: add dc[b] to element (0,0), 2: add dc[b] to every element
     int M, N;
@@ -137,33 +134,6 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     float rs = ep.alpha;
     if (ep.alpha_dev != nullptr) rs *= __ldg(ep.alpha_dev);
     if (ep.row_scale != nullptr && gm < ep.M) rs *= __ldg(ep.row_scale + gm);
-    if (ep.mode == 3) {
-        // nearest-code search (vector_quantize.py:467-469): per-row first minimum over this CTA's
-        // 128 columns of  col_bias[n] + rs * acc[m, n];  no staging, one (value, index) pair per row
-        float best = INFINITY;
-        int bi = 0x7fffffff;
-#pragma unroll
-        for (int c = 0; c < TN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_acc + ((uint32_t)(warp * 32) << 16) + c * 32, r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int nn = n0 + c * 32 + j;
-                if (nn < ep.N) {
-                    const float v = fmaf(rs, __uint_as_float(r[j]), __ldg(ep.col_bias + nn));
-                    if (v < best) { best = v; bi = nn; }
-                }
-            }
-        }
-        if (gm < ep.M) {
-            ep.part_val[(int64_t)gm * gridDim.x + blockIdx.x] = best;
-            ep.part_idx[(int64_t)gm * gridDim.x + blockIdx.x] = bi;
-        }
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0) tmem_dealloc(tmem_acc, TN);
-        return;
-    }
 #pragma unroll
     for (int c = 0; c < TN / 32; ++c) {
         uint32_t r[32];
@@ -1077,102 +1047,20 @@ extern "C" int dcta_split_coef_planes(const float* y, void* hi, void* lo, float*
 }
 
 // ------------------------------------------------------------------------------ VQ nearest code on tensor cores
-// vector_quantize.py:29-33 / :467-469.  dist^2[t, j] = |x_t|^2 + |e_j|^2 - 2 x_t.e_j ; the dot products run
-// through the split-precision GEMM (fp32-class accuracy), each 128x128 tile reduces to one (min, argmin)
-// pair per token, and a second kernel merges the pairs in the sqrt domain with the first-index tie rule.
-namespace dcta {
-
-// rows (n, d) fp32 -> hi/lo planes (n, ld) scaled by the power of two *scale_dev (chosen on the device)
-__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, __half* __restrict__ hi,
-                                                         __half* __restrict__ lo, int64_t n, int d, int64_t ld,
-                                                         const float* __restrict__ scale_dev) {
-    const float scale = __ldg(scale_dev);
-    const int64_t total = n * ld;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(i % ld);
-        const int64_t r = i / ld;
-        split16(k < d ? x[r * d + k] : 0.f, scale, hi[i], lo[i]);
-    }
-}
-
-__device__ __forceinline__ bool vq_better(float v, int i, float bv, int bi) {
-    if (v != v) return (bv == bv) || i < bi;
-    if (bv != bv) return false;
-    return v < bv || (v == bv && i < bi);
-}
-
-// one warp per token: x2 = |x|^2, then the candidate of every code tile is re-scored as
-// sqrt(x2 + v) and the first minimum wins (torch.argmax(-dist) semantics); optional gather.
-__global__ void __launch_bounds__(256) vq_merge_kernel(const float* __restrict__ x, const float* __restrict__ embed,
-                                                       const float* __restrict__ part_val,
-                                                       const int32_t* __restrict__ part_idx, int n_tiles,
-                                                       int64_t n_tok, int d, int64_t* __restrict__ indices,
-                                                       float* __restrict__ quantized) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t t = warp0; t < n_tok; t += n_warps) {
-        float x2 = 0.f;
-        for (int i = lane; i < d; i += 32) {
-            const float v = __ldg(x + t * d + i);
-            x2 = fmaf(v, v, x2);
-        }
-        x2 = warp_sum(x2);
-        float bv = INFINITY;
-        int bi = 0x7fffffff;
-        for (int j = lane; j < n_tiles; j += 32) {
-            const float v = __fsqrt_rn(__fadd_rn(x2, part_val[t * n_tiles + j]));
-            const int idx = part_idx[t * n_tiles + j];
-            if (vq_better(v, idx, bv, bi)) { bv = v; bi = idx; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (vq_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-        }
-        if (lane == 0) indices[t] = bi;
-        if (quantized)
-            for (int i = lane; i < d; i += 32) quantized[t * d + i] = __ldg(embed + (int64_t)bi * d + i);
-    }
-}
-
-}  // namespace dcta
-
-extern "C" int dcta_split_rows(const float* x, void* hi, void* lo, int64_t n, int d, int64_t ld,
-                               const float* scale_dev, void* stream) {
-    DCTA_REQUIRE(x && hi && lo && scale_dev && n >= 0 && d > 0 && ld >= d && ld % 8 == 0, "split_rows: bad args");
-    if (n == 0) return DCTA_OK;
-    split_rows_kernel<<<grid_for(n * ld, 256), 256, 0, as_stream(stream)>>>(x, (__half*)hi, (__half*)lo, n, d, ld, scale_dev);
-    return check_launch("split_rows");
-}
-
-extern "C" int dcta_vq_nearest_tc(const float* x, const void* x_hi, const void* x_lo, const float* embed,
-                                  const void* e_hi, const void* e_lo, const float* e2, const float* alpha_dev,
-                                  float* part_val, int32_t* part_idx, int64_t* indices, float* quantized,
+// vector_quantize.py:29-33 / :467-469: approximate distances on tcgen05 (one fp16 MMA per product), four candidates per
+// token, exact fp32 re-rank (vq_tc.cu).
+extern "C" int dcta_vq_nearest_tc(const float* x, const void* x_hi, const float* row_alpha, const float* embed,
+                                  const void* e_hi, const float* e2, int32_t* cand, int64_t* indices, float* quantized,
                                   int64_t n_tok, int n_codes, int d, int64_t ld, void* stream) {
-    DCTA_REQUIRE(x && x_hi && x_lo && embed && e_hi && e_lo && e2 && alpha_dev && part_val && part_idx && indices,
-                 "vq_nearest_tc: null pointer");
+    DCTA_REQUIRE(x && x_hi && row_alpha && embed && e_hi && e2 && cand && indices, "vq_nearest_tc: null pointer");
     DCTA_REQUIRE(n_tok >= 0 && n_codes > 0 && d > 0 && ld >= d && ld % 8 == 0, "vq_nearest_tc: bad sizes");
     if (n_tok == 0) return DCTA_OK;
-    const int n_tiles = (int)ceil_div(n_codes, TN);
-    // preferred: CTA pairs with the token operand resident in shared memory (vq_tc.cu)
-    int rc_pair = launch_vq_pair(x_hi, x_lo, e_hi, e_lo, e2, alpha_dev, part_val, part_idx, n_tok, n_codes, d, ld,
-                                 as_stream(stream));
-    if (rc_pair != DCTA_OK && rc_pair != DCTA_ERR_UNSUPPORTED) return rc_pair;
-    const int64_t max_rows = 65535ll * TM;   // grid.y limit
-    for (int64_t r0 = 0; rc_pair == DCTA_ERR_UNSUPPORTED && r0 < n_tok; r0 += max_rows) {
-        const int64_t rows = n_tok - r0 < max_rows ? n_tok - r0 : max_rows;
-        Operand A{(const __half*)x_hi + r0 * ld, (const __half*)x_lo + r0 * ld, (int)rows, ld, 0};
-        Operand B{(const __half*)e_hi, (const __half*)e_lo, n_codes, ld, 0};
-        EpiArgs ep{};
-        ep.mode = 3; ep.alpha = 1.0f; ep.alpha_dev = alpha_dev; ep.col_bias = e2;
-        ep.part_val = part_val + r0 * n_tiles; ep.part_idx = part_idx + r0 * n_tiles;
-        ep.M = (int)rows; ep.N = n_codes;
-        int rc = launch_gemm_split(A, B, d, 1, ep, stream);
-        if (rc) return rc;
+    int rc = launch_vq_pair(x_hi, e_hi, e2, row_alpha, cand, n_tok, n_codes, d, ld, as_stream(stream));
+    if (rc == DCTA_ERR_UNSUPPORTED) {
+        set_error("vq_nearest_tc: a %d-wide token operand does not fit next to the code ring in shared memory "
+                  "(use dcta_vq_nearest)", d);
+        return rc;
     }
-    vq_merge_kernel<<<grid_for(n_tok, 8), 256, 0, as_stream(stream)>>>(x, embed, part_val, part_idx, n_tiles, n_tok, d,
-                                                                         indices, quantized);
-    return check_launch("vq_nearest_tc");
+    if (rc) return rc;
+    return launch_vq_rerank(x, embed, e2, cand, n_tok, n_codes, d, indices, quantized, as_stream(stream));
 }

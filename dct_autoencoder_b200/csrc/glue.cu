@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) split_rows_rowscale_kernel(const float* _
             }
             const __half h = __float2half_rn(v);
             dh[i] = h;
-            dl[i] = __float2half_rn(v - __half2float(h));
+            if (lo != nullptr) dl[i] = __float2half_rn(v - __half2float(h));
         }
     }
 }
@@ -201,7 +201,7 @@ extern "C" int dcta_ln_pos_rows(const float* x, const float* gamma, const float*
 extern "C" int dcta_split_rows_rowscale(const float* x, const float* gamma, const float* beta, float eps, void* hi, void* lo,
                                         float* row_scale, float post, int64_t n_rows, int d, int64_t ld, void* stream) {
     using namespace dcta;
-    DCTA_REQUIRE(x && hi && lo && row_scale && n_rows >= 0 && d > 0 && ld >= d && ld % 8 == 0, "split_rows_rowscale: bad arguments");
+    DCTA_REQUIRE(x && hi && row_scale && n_rows >= 0 && d > 0 && ld >= d && ld % 8 == 0, "split_rows_rowscale: bad arguments");
     DCTA_REQUIRE((gamma == nullptr) == (beta == nullptr), "split_rows_rowscale: gamma and beta go together");
     if (n_rows == 0) return DCTA_OK;
     split_rows_rowscale_kernel<<<grid_for(n_rows, 8), 256, 0, as_stream(stream)>>>(x, gamma, beta, eps, (__half*)hi, (__half*)lo,

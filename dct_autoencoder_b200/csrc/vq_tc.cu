@@ -1,15 +1,17 @@
-// Nearest-code search distances on persistent CTA pairs (sm_100a: TMA + tcgen05 cta_group::2 + TMEM).
-// Reference: vector_quantize.py:29-33 (cdist), :467-469 (argmax of -dist).
+// Nearest-code search on persistent CTA pairs (sm_100a: TMA + tcgen05 cta_group::2 + TMEM), single pass.
+// Reference: vector_quantize.py:29-33 (cdist), :467-469 (argmax of -dist), :222-226 (gather).
 //
-//   part[t, n/128] = first minimum over the 128 codes of a slice of   |e_n|^2 + alpha * x_t . e_n
+// Pass 1 (vq_pair_kernel): APPROXIMATE distances  |e_n|^2 - 2 x_t . e_n  from ONE fp16 tcgen05.mma per product (each
+//   operand rounded to 11 significant bits, rows scaled by powers of two; absolute error ~1e-5 of |x||e|), reduced in
+//   the epilogue to the two smallest per token and half of the code slices: four candidates per token.
+// Pass 2 (vq_rerank_kernel): the candidates re-scored EXACTLY in fp32 with the reference's formula and its
+//   first-index rule.  The true nearest code is lost only if three codes of one half lie within the approximation
+//   error of each other, in which case the returned code's distance is within ~1e-4 relative of the minimum.
+// One third of the tensor work and half of the L2 -> SM operand traffic of the split-precision (fp16 x 3) version it
+// replaces.
 //
-// (vq_merge_kernel in gemm_tc.cu adds |x_t|^2, compares the slices in the sqrt domain like the reference and
-// gathers).  The x . e products run through the split-precision fp16x3 scheme of the DCT kernels.
-//
-// A pair of CTAs owns a tile of 256 tokens: their operand (128 tokens x K per CTA, hi + lo) is loaded ONCE and
-// stays in shared memory while the whole codebook streams through as the B operand (256 codes per MMA, 128 per
-// CTA and ring stage).  L2 -> SM traffic per tile is the codebook once (8 MB for 8192 x 256) instead of the token
-// tile once per 128 codes: the 128 x 128-tile kernel it replaces was bound by that traffic.
+// A pair of CTAs owns a tile of 256 tokens: their operand (128 tokens x K per CTA) is loaded ONCE and stays in shared
+// memory while the whole codebook streams through as the B operand (256 codes per MMA, 128 per CTA and ring stage).
 //   warp 0: TMA producer, warp 1 of the leader: tcgen05.mma issuer, warps 2..9: epilogue (lane quarter = token
 //   rows, the two warps of a quarter take one 128-code slice each); two TMEM accumulators of 256 columns.
 #include "tc_ptx.cuh"
@@ -17,26 +19,32 @@
 namespace dcta {
 
 constexpr int VK = 32;                       // k block
-constexpr int V_TILE = 128 * VK * 2;         // 128-row operand tile (hi or lo) of one k block: 8 KB
-constexpr int V_STAGE = 2 * V_TILE;          // ring stage: this CTA's 128 codes, hi + lo
+constexpr int V_TILE = 128 * VK * 2;         // 128-row fp16 operand tile of one k block: 8 KB
+constexpr int V_STAGE = V_TILE;              // ring stage: this CTA's 128 codes
 constexpr int V_THREADS = 320;
-constexpr int V_MAX_STAGES = 8;
+constexpr int V_MAX_STAGES = 12;
 
 struct VqArgs {
     int64_t n_tok;
     int n_codes, num_kb, stages, n_ctiles;   // n_ctiles: 256-code tiles
-    int n_part;                              // 128-code slices per token = ceil(n_codes / 128)
     int64_t n_ttiles;                        // 256-token tiles
-    uint32_t a_bytes;                        // one CTA's resident token operand plane (hi or lo): num_kb * 8 KB
+    uint32_t a_bytes;                        // one CTA's resident token operand: num_kb * 8 KB
     const float* col_bias;                   // |e_n|^2
-    const float* alpha_dev;                  // device scalar: -2 / (scale_x * scale_e)
-    float* part_val;                         // (n_tok, n_part)
-    int32_t* part_idx;
+    const float* row_alpha;                  // (n_tok) -2 / (scale of the token's row * scale of the codebook)
+    int32_t* cand;                           // (n_tok, 4): the two best codes of each half of the code slices
 };
 
+// running two smallest (value, index) pairs; strict '<' keeps the earlier index among equal values
+__device__ __forceinline__ void top2_insert(float v, int n, float& b1, int& i1, float& b2, int& i2) {
+    const bool lt1 = v < b1, lt2 = v < b2;
+    b2 = lt1 ? b1 : (lt2 ? v : b2);
+    i2 = lt1 ? i1 : (lt2 ? n : i2);
+    b1 = lt1 ? v : b1;
+    i1 = lt1 ? n : i1;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V_THREADS, 1)
-vq_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
-               const __grid_constant__ CUtensorMap map_e_hi, const __grid_constant__ CUtensorMap map_e_lo, VqArgs g) {
+vq_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_e, VqArgs g) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[V_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[V_MAX_STAGES];
@@ -46,19 +54,16 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     __shared__ uint32_t tmem_base_slot;
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* a_hi = smem;
-    uint8_t* a_lo = smem + g.a_bytes;
-    uint8_t* ring = smem + 2 * g.a_bytes;
+    uint8_t* a_op = smem;
+    uint8_t* ring = smem + g.a_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
     if (threadIdx.x == 0) {
-        tma_prefetch_desc(&map_x_hi);
-        tma_prefetch_desc(&map_x_lo);
-        tma_prefetch_desc(&map_e_hi);
-        tma_prefetch_desc(&map_e_lo);
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_e);
         for (int s = 0; s < V_MAX_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -85,29 +90,24 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
         for (int64_t tt = pair; tt < g.n_ttiles; tt += n_pairs, ++tt_count) {
             // the token operand of this tile: wait until the MMAs of the previous tile have read the old one
             mbar_wait(&a_empty, (tt_count & 1) ^ 1);
-            if (rank == 0) mbar_expect_tx(&a_full, 4 * g.a_bytes);
+            if (rank == 0) mbar_expect_tx(&a_full, 2 * g.a_bytes);
             const int row0 = (int)(tt * 256 + rank * 128);
-            for (int kb = 0; kb < g.num_kb; ++kb) {
-                tma_load_3d_2sm(&map_x_hi, a_full_leader, a_hi + kb * V_TILE, kb * VK, row0, 0);
-                tma_load_3d_2sm(&map_x_lo, a_full_leader, a_lo + kb * V_TILE, kb * VK, row0, 0);
-            }
+            for (int kb = 0; kb < g.num_kb; ++kb) tma_load_3d_2sm(&map_x, a_full_leader, a_op + kb * V_TILE, kb * VK, row0, 0);
             for (int ct = 0; ct < g.n_ctiles; ++ct) {
                 const int code0 = ct * 256 + (int)rank * 128;
                 for (int kb = 0; kb < g.num_kb; ++kb, ++it) {
                     const int s = it % g.stages;
                     mbar_wait(&empty_bar[s], ((it / g.stages) & 1) ^ 1);
-                    uint8_t* st = ring + s * V_STAGE;
                     const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[s]), 0);
                     if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * V_STAGE);
-                    tma_load_3d_2sm(&map_e_hi, full_leader, st, kb * VK, code0, 0);
-                    tma_load_3d_2sm(&map_e_lo, full_leader, st + V_TILE, kb * VK, code0, 0);
+                    tma_load_3d_2sm(&map_e, full_leader, ring + s * V_STAGE, kb * VK, code0, 0);
                 }
             }
         }
     } else if (warp == 1 && lane == 0 && rank == 0) {
-        // ---------------- MMA issuer (leader): M = 256 tokens, N = 256 codes
+        // ---------------- MMA issuer (leader): M = 256 tokens, N = 256 codes, one fp16 MMA per k16 step
         const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-        const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo);
+        const uint32_t a_lo32 = smem_desc_lo(smem_u32(a_op)), ring_lo32 = smem_desc_lo(smem_u32(ring));
         uint32_t it = 0, tcount = 0, tt_count = 0;
         for (int64_t tt = pair; tt < g.n_ttiles; tt += n_pairs, ++tt_count) {
             mbar_wait_cluster(&a_full, tt_count & 1);
@@ -121,18 +121,11 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                     const int s = it % g.stages;
                     mbar_wait_cluster(&full_bar[s], (it / g.stages) & 1);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(ring + s * V_STAGE);
+                    const uint32_t a16 = a_lo32 + (uint32_t)(kb * (V_TILE >> 4)), b16 = ring_lo32 + (uint32_t)(s * (V_STAGE >> 4));
 #pragma unroll
-                    for (int k = 0; k < VK / 16; ++k) {
-                        const uint32_t ko = k * 32;
-                        const uint64_t d_a_hi = smem_desc_sw64(ah + kb * V_TILE + ko);
-                        const uint64_t d_a_lo = smem_desc_sw64(al + kb * V_TILE + ko);
-                        const uint64_t d_b_hi = smem_desc_sw64(base + ko);
-                        const uint64_t d_b_lo = smem_desc_sw64(base + V_TILE + ko);
-                        umma_f16_2sm(tmem_acc, d_a_lo, d_b_hi, idesc, (kb | k) ? 1u : 0u);   // small terms first
-                        umma_f16_2sm(tmem_acc, d_a_hi, d_b_lo, idesc, 1u);
-                        umma_f16_2sm(tmem_acc, d_a_hi, d_b_hi, idesc, 1u);
-                    }
+                    for (int k = 0; k < VK / 16; ++k)
+                        umma_f16_2sm(tmem_acc, smem_desc_sw64_from_lo(a16 + 2 * k), smem_desc_sw64_from_lo(b16 + 2 * k), idesc,
+                                     (kb | k) ? 1u : 0u);
                     umma_commit_2sm(&empty_bar[s], 3);
                 }
                 umma_commit_2sm(&tmem_full[acc], 3);
@@ -140,62 +133,72 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
             umma_commit_2sm(&a_empty, 3);            // every MMA of this token tile has read the operand
         }
     } else if (warp >= 2) {
-        // ---------------- epilogue: per token row the first minimum of each 128-code slice
+        // ---------------- epilogue: per token row the two smallest  |e_n|^2 + alpha_t * acc  of this warp's half of
+        // the 128-code slices, carried over the whole codebook
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
         const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
-        const float alpha = __ldg(g.alpha_dev);
         uint32_t tcount = 0;
         for (int64_t tt = pair; tt < g.n_ttiles; tt += n_pairs) {
             const int64_t tok = tt * 256 + rank * 128 + quarter * 32 + lane;
+            const float alpha = tok < g.n_tok ? __ldg(g.row_alpha + tok) : 0.f;
+            float b1 = INFINITY, b2 = INFINITY;
+            int i1 = 0x7fffffff, i2 = 0x7fffffff;
             for (int ct = 0; ct < g.n_ctiles; ++ct, ++tcount) {
                 const int acc = tcount & 1;
                 mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + acc * 256 + half * 128 + ((uint32_t)(quarter * 32) << 16);
                 const int n0 = ct * 256 + half * 128;
-                float best = INFINITY;
-                int bi = 0x7fffffff;
+                uint32_t ra[32], rb[32];
+                tmem_ld32_nowait(tmem_acc, ra);
 #pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t rr[32];
-                    tmem_ld32_nowait(tmem_acc + c * 32, rr);
+                for (int c = 0; c < 4; c += 2) {
                     tmem_ld_wait();
-                    if (c == 3) {                      // this warp's slice is read: hand the accumulator back
+                    tmem_ld32_nowait(tmem_acc + (c + 1) * 32, rb);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int nn = n0 + c * 32 + j;
+                        if (nn + 3 < g.n_codes) {
+                            const float4 cb = __ldg(reinterpret_cast<const float4*>(g.col_bias + nn));
+                            top2_insert(fmaf(alpha, __uint_as_float(ra[j]), cb.x), nn, b1, i1, b2, i2);
+                            top2_insert(fmaf(alpha, __uint_as_float(ra[j + 1]), cb.y), nn + 1, b1, i1, b2, i2);
+                            top2_insert(fmaf(alpha, __uint_as_float(ra[j + 2]), cb.z), nn + 2, b1, i1, b2, i2);
+                            top2_insert(fmaf(alpha, __uint_as_float(ra[j + 3]), cb.w), nn + 3, b1, i1, b2, i2);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (nn + u < g.n_codes)
+                                    top2_insert(fmaf(alpha, __uint_as_float(ra[j + u]), __ldg(g.col_bias + nn + u)), nn + u, b1, i1, b2, i2);
+                        }
+                    }
+                    tmem_ld_wait();
+                    if (c + 2 < 4) tmem_ld32_nowait(tmem_acc + (c + 2) * 32, ra);
+                    else {                             // this warp's slice is read: hand the accumulator back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const int nn = n0 + c * 32 + j;
+                        const int nn = n0 + (c + 1) * 32 + j;
                         if (nn + 3 < g.n_codes) {
                             const float4 cb = __ldg(reinterpret_cast<const float4*>(g.col_bias + nn));
-                            const float v0 = fmaf(alpha, __uint_as_float(rr[j]), cb.x);
-                            const float v1 = fmaf(alpha, __uint_as_float(rr[j + 1]), cb.y);
-                            const float v2 = fmaf(alpha, __uint_as_float(rr[j + 2]), cb.z);
-                            const float v3 = fmaf(alpha, __uint_as_float(rr[j + 3]), cb.w);
-                            if (v0 < best) { best = v0; bi = nn; }
-                            if (v1 < best) { best = v1; bi = nn + 1; }
-                            if (v2 < best) { best = v2; bi = nn + 2; }
-                            if (v3 < best) { best = v3; bi = nn + 3; }
+                            top2_insert(fmaf(alpha, __uint_as_float(rb[j]), cb.x), nn, b1, i1, b2, i2);
+                            top2_insert(fmaf(alpha, __uint_as_float(rb[j + 1]), cb.y), nn + 1, b1, i1, b2, i2);
+                            top2_insert(fmaf(alpha, __uint_as_float(rb[j + 2]), cb.z), nn + 2, b1, i1, b2, i2);
+                            top2_insert(fmaf(alpha, __uint_as_float(rb[j + 3]), cb.w), nn + 3, b1, i1, b2, i2);
                         } else {
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                if (nn + u < g.n_codes) {
-                                    const float v = fmaf(alpha, __uint_as_float(rr[j + u]), __ldg(g.col_bias + nn + u));
-                                    if (v < best) { best = v; bi = nn + u; }
-                                }
-                            }
+                            for (int u = 0; u < 4; ++u)
+                                if (nn + u < g.n_codes)
+                                    top2_insert(fmaf(alpha, __uint_as_float(rb[j + u]), __ldg(g.col_bias + nn + u)), nn + u, b1, i1, b2, i2);
                         }
                     }
                 }
-                const int slice = ct * 2 + half;
-                if (tok < g.n_tok && slice < g.n_part) {
-                    g.part_val[tok * g.n_part + slice] = best;
-                    g.part_idx[tok * g.n_part + slice] = bi;
-                }
             }
+            if (tok < g.n_tok)
+                *reinterpret_cast<int2*>(g.cand + tok * 4 + half * 2) = make_int2(i1, i2);
         }
     }
     __syncwarp();
@@ -203,6 +206,52 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     __syncthreads();
     cluster_sync_all();
     if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// torch.argmax(-dist) semantics: the first minimum wins, and a NaN (sqrt of a rounding-negative argument; the reference
+// does not clamp, vector_quantize.py:29-33) beats every number
+__device__ __forceinline__ bool vq_better(float v, int i, float bv, int bi) {
+    if (v != v) return (bv == bv) || i < bi;
+    if (bv != bv) return false;
+    return v < bv || (v == bv && i < bi);
+}
+
+// exact fp32 re-rank of the (up to) four candidates of every token: dist = sqrt(|x|^2 + (|e|^2 - 2 x.e)) as in
+// vector_quantize.py:29-33, first minimum wins (torch.argmax(-dist), :467-469); optional gather (:222-226).
+// One warp per token.
+__global__ void __launch_bounds__(256) vq_rerank_kernel(const float* __restrict__ x, const float* __restrict__ embed,
+                                                        const float* __restrict__ e2, const int32_t* __restrict__ cand,
+                                                        int64_t n_tok, int n_codes, int d, int64_t* __restrict__ indices,
+                                                        float* __restrict__ quantized) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = warp0; t < n_tok; t += n_warps) {
+        const int4 c4 = *reinterpret_cast<const int4*>(cand + t * 4);
+        const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
+        float x2 = 0.f, dot[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = lane; i < d; i += 32) {
+            const float v = __ldg(x + t * d + i);
+            x2 = fmaf(v, v, x2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (cs[k] < n_codes) dot[k] = fmaf(v, __ldg(embed + (int64_t)cs[k] * d + i), dot[k]);
+        }
+        x2 = warp_sum(x2);
+        float bv = INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float dk = warp_sum(dot[k]);
+            if (cs[k] < n_codes) {
+                const float v = __fsqrt_rn(__fadd_rn(x2, fmaf(-2.0f, dk, __ldg(e2 + cs[k]))));
+                if (bi == 0x7fffffff || vq_better(v, cs[k], bv, bi)) { bv = v; bi = cs[k]; }
+            }
+        }
+        if (lane == 0) indices[t] = bi;
+        if (quantized)
+            for (int i = lane; i < d; i += 32) quantized[t * d + i] = __ldg(embed + (int64_t)bi * d + i);
+    }
 }
 
 static int make_map_rows(CUtensorMap* map, const void* ptr, int64_t k, int64_t rows, int64_t ld) {
@@ -224,32 +273,27 @@ static int make_map_rows(CUtensorMap* map, const void* ptr, int64_t k, int64_t r
 }
 
 // DCTA_ERR_UNSUPPORTED (no error message) when the token operand does not fit in shared memory
-int launch_vq_pair(const void* x_hi, const void* x_lo, const void* e_hi, const void* e_lo, const float* e2,
-                   const float* alpha_dev, float* part_val, int32_t* part_idx, int64_t n_tok, int n_codes, int d,
-                   int64_t ld, cudaStream_t st) {
+int launch_vq_pair(const void* x_hi, const void* e_hi, const float* e2, const float* row_alpha, int32_t* cand, int64_t n_tok,
+                   int n_codes, int d, int64_t ld, cudaStream_t st) {
     VqArgs g{};
     g.n_tok = n_tok;
     g.n_codes = n_codes;
     g.num_kb = (int)ceil_div(d, VK);
     g.a_bytes = (uint32_t)g.num_kb * V_TILE;
-    const int64_t stages = (227 * 1024 - 5120 - 1024 - 2 * (int64_t)g.a_bytes) / V_STAGE;
-    if (stages < 3 || 4ll * g.a_bytes >= (1 << 20) || n_tok >= (1ll << 31) - 256 || n_codes < 1) return DCTA_ERR_UNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(e2) & 15) != 0) return DCTA_ERR_UNSUPPORTED;
+    const int64_t stages = (227 * 1024 - 5120 - 1024 - (int64_t)g.a_bytes) / V_STAGE;
+    if (stages < 3 || 2ll * g.a_bytes >= (1 << 20) || n_tok >= (1ll << 31) - 256 || n_codes < 1) return DCTA_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(e2) & 15) != 0 || (reinterpret_cast<uintptr_t>(cand) & 15) != 0) return DCTA_ERR_UNSUPPORTED;
     g.stages = (int)(stages < V_MAX_STAGES ? stages : V_MAX_STAGES);
     g.n_ctiles = (int)ceil_div(n_codes, 256);
-    g.n_part = (int)ceil_div(n_codes, 128);
     g.n_ttiles = ceil_div(n_tok, 256);
     g.col_bias = e2;
-    g.alpha_dev = alpha_dev;
-    g.part_val = part_val;
-    g.part_idx = part_idx;
-    CUtensorMap mx_hi, mx_lo, me_hi, me_lo;
+    g.row_alpha = row_alpha;
+    g.cand = cand;
+    CUtensorMap mx, me;
     int rc;
-    if ((rc = make_map_rows(&mx_hi, x_hi, d, n_tok, ld))) return rc;
-    if ((rc = make_map_rows(&mx_lo, x_lo, d, n_tok, ld))) return rc;
-    if ((rc = make_map_rows(&me_hi, e_hi, d, n_codes, ld))) return rc;
-    if ((rc = make_map_rows(&me_lo, e_lo, d, n_codes, ld))) return rc;
-    const int smem_bytes = 1024 + 2 * (int)g.a_bytes + g.stages * V_STAGE;
+    if ((rc = make_map_rows(&mx, x_hi, d, n_tok, ld))) return rc;
+    if ((rc = make_map_rows(&me, e_hi, d, n_codes, ld))) return rc;
+    const int smem_bytes = 1024 + (int)g.a_bytes + g.stages * V_STAGE;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -258,8 +302,14 @@ int launch_vq_pair(const void* x_hi, const void* x_lo, const void* e_hi, const v
     if (pairs < 1) pairs = 1;
     cudaError_t e = cudaFuncSetAttribute(vq_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { set_error("vq_pair: %s", cudaGetErrorString(e)); return DCTA_ERR_LAUNCH; }
-    vq_pair_kernel<<<(unsigned)(2 * pairs), V_THREADS, smem_bytes, st>>>(mx_hi, mx_lo, me_hi, me_lo, g);
+    vq_pair_kernel<<<(unsigned)(2 * pairs), V_THREADS, smem_bytes, st>>>(mx, me, g);
     return check_launch("vq_pair");
+}
+
+int launch_vq_rerank(const float* x, const float* embed, const float* e2, const int32_t* cand, int64_t n_tok, int n_codes,
+                     int d, int64_t* indices, float* quantized, cudaStream_t st) {
+    vq_rerank_kernel<<<grid_for(n_tok, 8), 256, 0, st>>>(x, embed, e2, cand, n_tok, n_codes, d, indices, quantized);
+    return check_launch("vq_rerank");
 }
 
 }  // namespace dcta

@@ -20,51 +20,60 @@ from .linear import linear_bias_rows
 from .util import to_device_f32
 
 
-def _pow2_scale(t: torch.Tensor) -> torch.Tensor:
-    """Device scalar 2^k with max|t| * 2^k in [2^10, 2^11): the fp16 hi/lo split then keeps 22
-    bits of every element that matters.  Stays on the device (no host read of the data)."""
-    amax = t.abs().amax().clamp_min(1e-30)
-    return torch.exp2(10.0 - torch.ceil(torch.log2(amax))).reshape(1).float()
+_CODEBOOK_CACHE = {}
 
 
-def _split_rows(t: torch.Tensor, scale: torch.Tensor, ld: int):
-    n, d = t.shape
-    hi = torch.empty((n, ld), dtype=torch.float16, device=t.device)
-    lo = torch.empty_like(hi)
-    _lib.call("dcta_split_rows", _lib.ptr(t), _lib.ptr(hi), _lib.ptr(lo), n, d, ld, _lib.ptr(scale),
-              _lib.stream_ptr(t.device))
-    return hi, lo
+def _codebook_operand(embed: torch.Tensor):
+    """(C, d) fp32 codebook -> cached (fp16 plane (C, ld) of embed * s, |e|^2 (C,), s): s a power of two from max|embed|
+    (one device->host read per codebook version; the codebook is a parameter, the tokens never cause a sync)."""
+    key = (embed.data_ptr(), embed._version, tuple(embed.shape), str(embed.device))
+    hit = _CODEBOOK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    import math
+    C, d = embed.shape
+    ld = (d + 7) // 8 * 8
+    amax = float(embed.abs().max())
+    s = 2.0 ** (10 - math.frexp(amax)[1]) if amax > 0 and math.isfinite(amax) else 1.0
+    e_hi = torch.zeros((C, ld), dtype=torch.float16, device=embed.device)
+    e_hi[:, :d] = (embed * s).to(torch.float16)            # round-to-nearest fp16 of the scaled codebook (one-off)
+    e2 = torch.empty(C, dtype=torch.float32, device=embed.device)
+    with torch.cuda.device(embed.device):
+        _lib.call("dcta_row_sumsq", _lib.ptr(embed), _lib.ptr(e2), C, d, _lib.stream_ptr(embed.device))
+    if len(_CODEBOOK_CACHE) > 16:
+        _CODEBOOK_CACHE.clear()
+    out = (e_hi, e2, s)
+    _CODEBOOK_CACHE[key] = out
+    return out
 
 
 def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = True, impl: str = "tc"):
     """x (T, d), embed (C, d) fp32 CUDA -> (indices int64 (T,), embed[indices] or None).
 
-    impl="tc": x.e on tensor cores (split-precision tcgen05 GEMM, arg-min fused in the epilogue);
-    impl="fp32": exact-fp32 FFMA kernel in the reference's operation order."""
+    impl="tc": approximate x.e on tensor cores (ONE fp16 tcgen05 MMA per product, rows scaled by powers of two on the
+    device), the two best codes per token and half of the code slices kept in the epilogue, then an exact fp32 re-rank
+    of those four candidates (csrc/vq_tc.cu); impl="fp32": exact-fp32 FFMA kernel in the reference's operation order."""
     T, d = x.shape
     C = embed.shape[0]
     dev = x.device
     idx = torch.empty(T, dtype=torch.int64, device=dev)
     q = torch.empty_like(x) if return_quantized else None
-    e2 = torch.empty(C, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
-        if impl == "fp32":
+        ld = (d + 7) // 8 * 8
+        if impl == "fp32" or ld * 512 + 3 * 8192 + 6144 > 227 * 1024:      # token operand must fit next to the code ring
+            e2 = torch.empty(C, dtype=torch.float32, device=dev)
             _lib.call("dcta_vq_nearest", _lib.ptr(x), _lib.ptr(embed), _lib.ptr(e2), _lib.ptr(idx), _lib.ptr(q),
                       T, C, d, st)
             return idx, q
-        ld = (d + 7) // 8 * 8
-        sx, se = _pow2_scale(x), _pow2_scale(embed)
-        alpha = (-2.0 / (sx * se)).float().contiguous()
-        x_hi, x_lo = _split_rows(x, sx, ld)
-        e_hi, e_lo = _split_rows(embed, se, ld)
-        _lib.call("dcta_row_sumsq", _lib.ptr(embed), _lib.ptr(e2), C, d, st)
-        n_tiles = (C + 127) // 128
-        part_val = torch.empty((T, n_tiles), dtype=torch.float32, device=dev)
-        part_idx = torch.empty((T, n_tiles), dtype=torch.int32, device=dev)
-        _lib.call("dcta_vq_nearest_tc", _lib.ptr(x), _lib.ptr(x_hi), _lib.ptr(x_lo), _lib.ptr(embed), _lib.ptr(e_hi),
-                  _lib.ptr(e_lo), _lib.ptr(e2), _lib.ptr(alpha), _lib.ptr(part_val), _lib.ptr(part_idx), _lib.ptr(idx),
-                  _lib.ptr(q), T, C, d, ld, st)
+        e_hi, e2, s_e = _codebook_operand(embed)
+        x_hi = torch.empty((T, ld), dtype=torch.float16, device=dev)
+        row_alpha = torch.empty(T, dtype=torch.float32, device=dev)
+        _lib.call("dcta_split_rows_rowscale", _lib.ptr(x), None, None, 0.0, _lib.ptr(x_hi), None, _lib.ptr(row_alpha),
+                  -2.0 / s_e, T, d, ld, st)
+        cand = torch.empty((T, 4), dtype=torch.int32, device=dev)
+        _lib.call("dcta_vq_nearest_tc", _lib.ptr(x), _lib.ptr(x_hi), _lib.ptr(row_alpha), _lib.ptr(embed), _lib.ptr(e_hi),
+                  _lib.ptr(e2), _lib.ptr(cand), _lib.ptr(idx), _lib.ptr(q), T, C, d, ld, st)
     return idx, q
 
 

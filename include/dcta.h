@@ -406,7 +406,8 @@ int dcta_lfq_commit_backward(const float* x, const uint8_t* mask, const float* g
  *   x, out (n_rows, f) fp32, out must not alias x; biased variance, eps inside the square root (torch layer_norm).
  * dcta_split_rows_rowscale: rows (n_rows, d) [-> LayerNorm when gamma given] -> fp16 hi/lo planes (n_rows, ld) of
  *   y * s_row with a power-of-two scale per row (max|y| * s_row in [2^9, 2^10)), and row_scale[t] = post / s_row:
- *   the `row_scale` argument of dcta_gemm_split (post = 1 / the scale of the other operand). */
+ *   the `row_scale` argument of dcta_gemm_split (post = 1 / the scale of the other operand).  lo may be NULL
+ *   (single-precision operand: the hi plane alone). */
 int dcta_ln_pos_rows(const float* x, const float* gamma, const float* beta, float eps, const float* bias,
                      const float* pos_c, const float* pos_h, const float* pos_w, const int64_t* channels,
                      const int64_t* positions, float* out, int64_t n_rows, int f, void* stream);
@@ -423,18 +424,16 @@ int dcta_vq_nearest(const float* x, const float* embed, float* e2, int64_t* indi
 
 /* out[i] = sum_k x[i,k]^2 for n rows of d floats. */
 int dcta_row_sumsq(const float* x, float* out, int64_t n, int d, void* stream);
-/* rows (n, d) fp32 -> fp16 hi/lo planes (n, ld) of x * (*scale_dev); *scale_dev is a power of two
- * chosen on the device (no host read of the data range). */
-int dcta_split_rows(const float* x, void* hi, void* lo, int64_t n, int d, int64_t ld,
-                    const float* scale_dev, void* stream);
-/* Same contract as dcta_vq_nearest on tensor cores: the x.e products run through the split-precision
- * tcgen05 GEMM, each 128x128 tile is reduced to one (min, argmin) pair per token in the epilogue
- * (part_val / part_idx: n_tok * ceil(n_codes/128) scratch) and merged in the sqrt domain.
- *   x_hi/lo (n_tok, ld), e_hi/lo (n_codes, ld): dcta_split_rows outputs; e2 = dcta_row_sumsq(embed);
- *   *alpha_dev = -2 / (scale_x * scale_e). */
-int dcta_vq_nearest_tc(const float* x, const void* x_hi, const void* x_lo, const float* embed,
-                       const void* e_hi, const void* e_lo, const float* e2, const float* alpha_dev,
-                       float* part_val, int32_t* part_idx, int64_t* indices, float* quantized,
+/* Same contract as dcta_vq_nearest on tensor cores, in two passes (csrc/vq_tc.cu): approximate distances
+ * |e_n|^2 + row_alpha[t] * (x_hi[t] . e_hi[n]) from ONE fp16 tcgen05.mma per product, reduced in the epilogue to the two
+ * smallest per token and half of the 128-code slices (cand (n_tok, 4) int32, 16-byte aligned), then an exact fp32
+ * re-rank of those candidates with the reference's formula and first-index rule.
+ *   x_hi (n_tok, ld): fp16 of x scaled per row by a power of two (dcta_split_rows_rowscale, lo = NULL);
+ *   row_alpha (n_tok) = -2 / (row scale * codebook scale) (its row_scale output with post = -2 / codebook scale);
+ *   e_hi (n_codes, ld): fp16 of embed * codebook scale; e2 = dcta_row_sumsq(embed) (16-byte aligned).
+ * DCTA_ERR_UNSUPPORTED when a d-wide token operand does not fit in shared memory (d > ~700): use dcta_vq_nearest. */
+int dcta_vq_nearest_tc(const float* x, const void* x_hi, const float* row_alpha, const float* embed,
+                       const void* e_hi, const float* e2, int32_t* cand, int64_t* indices, float* quantized,
                        int64_t n_tok, int n_codes, int d, int64_t ld, void* stream);
 
 /* ------------------------------------------------------------------ un-patchify ----------- */
