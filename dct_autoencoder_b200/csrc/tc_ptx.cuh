@@ -89,6 +89,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
 // descriptors of a k-step are formed from a precomputed low word (start address >> 4) with one add each.
 constexpr uint32_t kDescSw64Hi = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);    // SBO 512 B, version 1, SWIZZLE_64B
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr) { return (saddr & 0x3ffff) >> 4; }
+// the same for rows of 128 bytes (64 fp16 of K), SWIZZLE_128B: 8-row atoms of 1024 B (SBO = 1024 B, layout type 2);
+// a K = 16 slice inside the row is addressed by advancing the start address by 32 bytes
+constexpr uint32_t kDescSw128Hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t smem_desc_sw128_from_lo(uint32_t lo) { return ((uint64_t)kDescSw128Hi << 32) | lo; }
 __device__ __forceinline__ uint64_t smem_desc_sw64_from_lo(uint32_t lo) { return ((uint64_t)kDescSw64Hi << 32) | lo; }
 
 

@@ -12,23 +12,26 @@
 //
 // A pair of CTAs owns a tile of 256 tokens: their operand (128 tokens x K per CTA) is loaded ONCE and stays in shared
 // memory while the whole codebook streams through as the B operand (256 codes per MMA, 128 per CTA and ring stage).
+// Operand tiles are 128 rows x 64 k (128-byte rows, SWIZZLE_128B).
 //   warp 0: TMA producer, warp 1 of the leader: tcgen05.mma issuer, warps 2..9: epilogue (lane quarter = token
 //   rows, the two warps of a quarter take one 128-code slice each); two TMEM accumulators of 256 columns.
 #include "tc_ptx.cuh"
 
 namespace dcta {
 
-constexpr int VK = 32;                       // k block
-constexpr int V_TILE = 128 * VK * 2;         // 128-row fp16 operand tile of one k block: 8 KB
+constexpr int VK = 64;                       // k block: 128-byte rows (SWIZZLE_128B) -- half the TMA row requests of 64-byte rows,
+                                             // which bounded the kernel at ~2.7 cycles per row per SM
+constexpr int V_TILE = 128 * VK * 2;         // 128-row fp16 operand tile of one k block: 16 KB
 constexpr int V_STAGE = V_TILE;              // ring stage: this CTA's 128 codes
 constexpr int V_THREADS = 320;
-constexpr int V_MAX_STAGES = 12;
+constexpr int V_MAX_STAGES = 8;
 
 struct VqArgs {
     int64_t n_tok;
     int n_codes, num_kb, stages, n_ctiles;   // n_ctiles: 256-code tiles
     int64_t n_ttiles;                        // 256-token tiles
     uint32_t a_bytes;                        // one CTA's resident token operand: num_kb * 8 KB
+    uint32_t e2_bytes;                       // |e_n|^2 of the whole codebook, staged in shared memory (padded to 256 codes)
     const float* col_bias;                   // |e_n|^2
     const float* row_alpha;                  // (n_tok) -2 / (scale of the token's row * scale of the codebook)
     int32_t* cand;                           // (n_tok, 4): the two best codes of each half of the code slices
@@ -56,6 +59,11 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* a_op = smem;
     uint8_t* ring = smem + g.a_bytes;
+    float* s_e2 = reinterpret_cast<float*>(ring + g.stages * V_STAGE);
+    // |e_n|^2 of every code: read by every epilogue thread for every token tile.  With 200+ KB of shared memory carved
+    // out, L1 holds almost nothing and each of those reads was an L2 round trip on the epilogue's critical path
+    // (ncu: 60 % of the stall samples on the FFMA consuming it).  +inf past the last code: those columns never win.
+    for (int i = threadIdx.x; i < (int)(g.e2_bytes >> 2); i += V_THREADS) s_e2[i] = i < g.n_codes ? __ldg(g.col_bias + i) : INFINITY;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -78,7 +86,7 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     }
     if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();                                  // (also publishes s_e2)
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
@@ -124,7 +132,7 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const uint32_t a16 = a_lo32 + (uint32_t)(kb * (V_TILE >> 4)), b16 = ring_lo32 + (uint32_t)(s * (V_STAGE >> 4));
 #pragma unroll
                     for (int k = 0; k < VK / 16; ++k)
-                        umma_f16_2sm(tmem_acc, smem_desc_sw64_from_lo(a16 + 2 * k), smem_desc_sw64_from_lo(b16 + 2 * k), idesc,
+                        umma_f16_2sm(tmem_acc, smem_desc_sw128_from_lo(a16 + 2 * k), smem_desc_sw128_from_lo(b16 + 2 * k), idesc,
                                      (kb | k) ? 1u : 0u);
                     umma_commit_2sm(&empty_bar[s], 3);
                 }
@@ -142,8 +150,28 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int64_t tt = pair; tt < g.n_ttiles; tt += n_pairs) {
             const int64_t tok = tt * 256 + rank * 128 + quarter * 32 + lane;
             const float alpha = tok < g.n_tok ? __ldg(g.row_alpha + tok) : 0.f;
+            // Running two smallest values of the row.  After the first few hundred codes an element rarely beats the
+            // current second best (probability 2 / codes seen), so a quad of columns is first reduced to its minimum
+            // (3 FMNMX) and the 4 ordered inserts run only when some lane of the warp needs them (warp-uniform branch):
+            // ~4 instead of ~12 instructions per element (ncu: the epilogue, not the MMA, bounded the kernel).
             float b1 = INFINITY, b2 = INFINITY;
             int i1 = 0x7fffffff, i2 = 0x7fffffff;
+            auto process = [&](const uint32_t (&rr)[32], int nbase) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int nn = nbase + j;
+                    const float4 cb = *reinterpret_cast<const float4*>(s_e2 + nn);
+                    const float v0 = fmaf(alpha, __uint_as_float(rr[j]), cb.x), v1 = fmaf(alpha, __uint_as_float(rr[j + 1]), cb.y);
+                    const float v2 = fmaf(alpha, __uint_as_float(rr[j + 2]), cb.z), v3 = fmaf(alpha, __uint_as_float(rr[j + 3]), cb.w);
+                    const float m = fminf(fminf(v0, v1), fminf(v2, v3));
+                    if (__any_sync(0xffffffffu, m < b2)) {
+                        top2_insert(v0, nn, b1, i1, b2, i2);
+                        top2_insert(v1, nn + 1, b1, i1, b2, i2);
+                        top2_insert(v2, nn + 2, b1, i1, b2, i2);
+                        top2_insert(v3, nn + 3, b1, i1, b2, i2);
+                    }
+                }
+            };
             for (int ct = 0; ct < g.n_ctiles; ++ct, ++tcount) {
                 const int acc = tcount & 1;
                 mbar_wait(&tmem_full[acc], (tcount >> 1) & 1);
@@ -156,22 +184,7 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 for (int c = 0; c < 4; c += 2) {
                     tmem_ld_wait();
                     tmem_ld32_nowait(tmem_acc + (c + 1) * 32, rb);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int nn = n0 + c * 32 + j;
-                        if (nn + 3 < g.n_codes) {
-                            const float4 cb = __ldg(reinterpret_cast<const float4*>(g.col_bias + nn));
-                            top2_insert(fmaf(alpha, __uint_as_float(ra[j]), cb.x), nn, b1, i1, b2, i2);
-                            top2_insert(fmaf(alpha, __uint_as_float(ra[j + 1]), cb.y), nn + 1, b1, i1, b2, i2);
-                            top2_insert(fmaf(alpha, __uint_as_float(ra[j + 2]), cb.z), nn + 2, b1, i1, b2, i2);
-                            top2_insert(fmaf(alpha, __uint_as_float(ra[j + 3]), cb.w), nn + 3, b1, i1, b2, i2);
-                        } else {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (nn + u < g.n_codes)
-                                    top2_insert(fmaf(alpha, __uint_as_float(ra[j + u]), __ldg(g.col_bias + nn + u)), nn + u, b1, i1, b2, i2);
-                        }
-                    }
+                    process(ra, n0 + c * 32);
                     tmem_ld_wait();
                     if (c + 2 < 4) tmem_ld32_nowait(tmem_acc + (c + 2) * 32, ra);
                     else {                             // this warp's slice is read: hand the accumulator back
@@ -179,22 +192,7 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0);
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int nn = n0 + (c + 1) * 32 + j;
-                        if (nn + 3 < g.n_codes) {
-                            const float4 cb = __ldg(reinterpret_cast<const float4*>(g.col_bias + nn));
-                            top2_insert(fmaf(alpha, __uint_as_float(rb[j]), cb.x), nn, b1, i1, b2, i2);
-                            top2_insert(fmaf(alpha, __uint_as_float(rb[j + 1]), cb.y), nn + 1, b1, i1, b2, i2);
-                            top2_insert(fmaf(alpha, __uint_as_float(rb[j + 2]), cb.z), nn + 2, b1, i1, b2, i2);
-                            top2_insert(fmaf(alpha, __uint_as_float(rb[j + 3]), cb.w), nn + 3, b1, i1, b2, i2);
-                        } else {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (nn + u < g.n_codes)
-                                    top2_insert(fmaf(alpha, __uint_as_float(rb[j + u]), __ldg(g.col_bias + nn + u)), nn + u, b1, i1, b2, i2);
-                        }
-                    }
+                    process(rb, n0 + (c + 1) * 32);
                 }
             }
             if (tok < g.n_tok)
@@ -266,7 +264,7 @@ static int make_map_rows(CUtensorMap* map, const void* ptr, int64_t k, int64_t r
     cuuint32_t box[3] = {VK, 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return DCTA_ERR_LAUNCH; }
     return DCTA_OK;
@@ -280,7 +278,8 @@ int launch_vq_pair(const void* x_hi, const void* e_hi, const float* e2, const fl
     g.n_codes = n_codes;
     g.num_kb = (int)ceil_div(d, VK);
     g.a_bytes = (uint32_t)g.num_kb * V_TILE;
-    const int64_t stages = (227 * 1024 - 5120 - 1024 - (int64_t)g.a_bytes) / V_STAGE;
+    g.e2_bytes = (uint32_t)(ceil_div(n_codes, 256) * 256 * 4);
+    const int64_t stages = (227 * 1024 - 5120 - 1024 - (int64_t)g.a_bytes - (int64_t)g.e2_bytes) / V_STAGE;
     if (stages < 3 || 2ll * g.a_bytes >= (1 << 20) || n_tok >= (1ll << 31) - 256 || n_codes < 1) return DCTA_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(e2) & 15) != 0 || (reinterpret_cast<uintptr_t>(cand) & 15) != 0) return DCTA_ERR_UNSUPPORTED;
     g.stages = (int)(stages < V_MAX_STAGES ? stages : V_MAX_STAGES);
@@ -293,7 +292,7 @@ int launch_vq_pair(const void* x_hi, const void* e_hi, const float* e2, const fl
     int rc;
     if ((rc = make_map_rows(&mx, x_hi, d, n_tok, ld))) return rc;
     if ((rc = make_map_rows(&me, e_hi, d, n_codes, ld))) return rc;
-    const int smem_bytes = 1024 + (int)g.a_bytes + g.stages * V_STAGE;
+    const int smem_bytes = 1024 + (int)g.a_bytes + g.stages * V_STAGE + (int)g.e2_bytes;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

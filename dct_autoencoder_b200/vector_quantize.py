@@ -61,7 +61,9 @@ def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = 
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
         ld = (d + 7) // 8 * 8
-        if impl == "fp32" or ld * 512 + 3 * 8192 + 6144 > 227 * 1024:      # token operand must fit next to the code ring
+        # the token operand (16 KB per 64 columns) and |e|^2 of the codebook stay in shared memory next to a ring of >= 3 stages
+        fits = (227 * 1024 - 6144 - (d + 63) // 64 * 16384 - (C + 255) // 256 * 1024) // 16384 >= 3
+        if impl == "fp32" or not fits:
             e2 = torch.empty(C, dtype=torch.float32, device=dev)
             _lib.call("dcta_vq_nearest", _lib.ptr(x), _lib.ptr(embed), _lib.ptr(e2), _lib.ptr(idx), _lib.ptr(q),
                       T, C, d, st)
