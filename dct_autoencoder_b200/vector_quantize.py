@@ -10,6 +10,7 @@ Codebook LEARNING (k-means init, EMA updates, dead-code expiry, affine re-parame
 codebooks, gumbel/reinmax sampling, orthogonal regularisation and their all-reduces) is outside
 the transform path and is not implemented: ``forward`` in training mode raises.
 """
+import collections
 from typing import Optional
 
 import torch
@@ -20,16 +21,25 @@ from .linear import linear_bias_rows
 from .util import to_device_f32
 
 
-_CODEBOOK_CACHE = {}
+_CODEBOOK_CACHE = collections.OrderedDict()      # key -> (embed, e_hi, e2, s); at most 8 codebooks
+
+
+def invalidate_codebook_cache():
+    """Forget every cached codebook operand (call after writing a codebook through ``.data``, which does not bump
+    the version counter the cache keys on)."""
+    _CODEBOOK_CACHE.clear()
 
 
 def _codebook_operand(embed: torch.Tensor):
     """(C, d) fp32 codebook -> cached (fp16 plane (C, ld) of embed * s, |e|^2 (C,), s): s a power of two from max|embed|
-    (one device->host read per codebook version; the codebook is a parameter, the tokens never cause a sync)."""
-    key = (embed.data_ptr(), embed._version, tuple(embed.shape), str(embed.device))
+    (one device->host read per codebook version; the codebook is a parameter, the tokens never cause a sync).
+    The entry keeps a reference to ``embed``: while it is cached its memory cannot be recycled for another tensor, so
+    (address, version counter) identifies the contents."""
+    key = (embed.data_ptr(), embed._version, tuple(embed.shape), tuple(embed.stride()), str(embed.device))
     hit = _CODEBOOK_CACHE.get(key)
     if hit is not None:
-        return hit
+        _CODEBOOK_CACHE.move_to_end(key)
+        return hit[1:]
     import math
     C, d = embed.shape
     ld = (d + 7) // 8 * 8
@@ -40,11 +50,10 @@ def _codebook_operand(embed: torch.Tensor):
     e2 = torch.empty(C, dtype=torch.float32, device=embed.device)
     with torch.cuda.device(embed.device):
         _lib.call("dcta_row_sumsq", _lib.ptr(embed), _lib.ptr(e2), C, d, _lib.stream_ptr(embed.device))
-    if len(_CODEBOOK_CACHE) > 16:
-        _CODEBOOK_CACHE.clear()
-    out = (e_hi, e2, s)
-    _CODEBOOK_CACHE[key] = out
-    return out
+    _CODEBOOK_CACHE[key] = (embed, e_hi, e2, s)
+    while len(_CODEBOOK_CACHE) > 8:
+        _CODEBOOK_CACHE.popitem(last=False)
+    return e_hi, e2, s
 
 
 def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = True, impl: str = "tc"):
