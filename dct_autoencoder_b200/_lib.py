@@ -61,6 +61,10 @@ SIGNATURES = {
     "dcta_unpatchify_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P],
     "dcta_decode_codes_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P, P],
+    "dcta_decode_codes_inv_fold_scratch_bytes": [c_int64, c_int, c_int, c_int],
+    "dcta_decode_codes_inv_fold_supported": [c_int, c_int, c_int, c_int, c_int, c_int, c_int],
+    "dcta_decode_codes_inv_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P, P],
     "dcta_fold_coef_planes": [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_dct2_inv_fold": [P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_unfold_ipt_to_rgb": [P, P, P, c_int64, c_int, c_int, P, P, P],
@@ -102,7 +106,8 @@ SIGNATURES = {
     "dcta_wire_pack": [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P, P, P],
     "dcta_wire_unpack": [P, c_int64, c_int, c_int, c_int, P, P, P, P],
 }
-_RESTYPES = {"dcta_last_error": c_char_p, "dcta_basis_elems": c_int64}
+_RESTYPES = {"dcta_last_error": c_char_p, "dcta_basis_elems": c_int64,
+             "dcta_decode_codes_inv_fold_scratch_bytes": c_int64}
 BASIS_F32, BASIS_SPLIT_FWD, BASIS_SPLIT_INV, BASIS_FOLD_FWD, BASIS_FOLD_INV = range(5)
 REDUCE_SCRATCH = 2048  # DCTA_REDUCE_SCRATCH
 
@@ -123,7 +128,8 @@ KERNELS_PER_CALL = {
     "dcta_row_sumsq": 1, "dcta_vq_nearest_tc": 2,
     "dcta_pack_codes_lfq": 2, "dcta_decode_codes_split": 1,
     "dcta_fold_supported": 0, "dcta_fold_codes_supported": 0, "dcta_rgb_to_ipt_fold": 2, "dcta_rgb_u8_to_ipt_fold": 2, "dcta_unfold_ipt_to_rgb_u8": 1, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
-    "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 2, "dcta_fold_coef_planes": 1, "dcta_dct2_inv_fold": 2,
+    "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 2, "dcta_decode_codes_inv_fold": 4,
+    "dcta_decode_codes_inv_fold_scratch_bytes": 0, "dcta_decode_codes_inv_fold_supported": 0, "dcta_fold_coef_planes": 1, "dcta_dct2_inv_fold": 2,
     "dcta_unfold_ipt_to_rgb": 1, "dcta_unfold_planes": 1, "dcta_sort_tokens_maxabs": 1, "dcta_dct2_fwd_fold_codes": 3, "dcta_pack_codes_grid": 2,
 }
 launch_count = 0

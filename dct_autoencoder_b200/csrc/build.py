@@ -35,11 +35,45 @@ def digest():
     return h.hexdigest()
 
 
+def _headers():
+    root = os.path.dirname(PKG)
+    hs = [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith((".cuh", ".h"))]
+    return hs + [os.path.join(root, "include", "dcta.h")]
+
+
+def _obj_digest(src):
+    h = hashlib.sha256()
+    for f in [src] + _headers():
+        h.update(open(f, "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()[:24]
+
+
 def build(force=False, verbose=False):
+    """One object per source, compiled in parallel and cached by content under csrc/_obj (git-ignored, not sent to
+    the GPU box), then linked into libdcta.so."""
     d = digest()
     if not force and os.path.exists(OUT) and os.path.exists(STAMP) and open(STAMP).read().strip() == d:
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + ["-o", OUT, "-lcudart"]
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in FLAGS if f != "--shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + "." + _obj_digest(src) + ".o")
+        if force or not os.path.exists(obj):
+            for old in os.listdir(objdir):
+                if old.startswith(os.path.basename(src)[:-3] + "."):
+                    os.remove(os.path.join(objdir, old))
+            cmd = [NVCC] + cflags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            print("[dcta build]", " ".join(cmd), flush=True)
+            subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    cmd = [NVCC, "--shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", OUT, "-lcudart"]
     print("[dcta build]", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     with open(STAMP, "w") as f:

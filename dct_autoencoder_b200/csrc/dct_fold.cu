@@ -69,6 +69,24 @@ struct FoldEpi {
                                  // accumulated with atomicMax on the bit pattern (the buffer must start at zero)
 };
 
+// GEN variant of fold_gemm_kernel (inverse pass 1 straight from LFQ code words): the data operand is not loaded but
+// GENERATED in shared memory by four producer warps.  A de-quantised, de-normalised coefficient is one of two values per
+// position (median +- scale * sd, lfq.py:118-120 + patchnorm.py:177), so a data tile is a table of value pairs (shared by
+// every image) selected by one bit per element.  A pair tile = 8 images x 32 coefficient rows i of one (a, channel):
+// each 32-lane TMEM quarter is one image, so the transposed output stores stay 64-byte runs and one 8 KB table block
+// serves four images.
+struct FoldGen {
+    const uint4* tab;       // [b][a][channel][i block][k block][4 parts][128 producer threads]: see decode_gen_tables_kernel
+    const uint16_t* bv;     // [b][a][group of 4 images][channel][i block][k block][image][32 rows][4 chunks of 8 columns]:
+                            // sign bits | valid bits << 8
+    int n_img, C, kh2, n_iblk;
+    int n_work;             // work items of a slice: ceil(n_img / 8) * 2 * C * n_iblk
+    int64_t n_planes;
+};
+constexpr int F_GEN_THREADS = 128;     // groups of four producer warps taking alternate stages
+constexpr int F_GEN_STAGES = 5;                 // ring of table blocks (8 KB) + the sign/valid words of 4 images (4 x 256 B)
+constexpr int F_GEN_STAGE = 8192 + 4 * 256;
+
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, M = 256 (pair), N = n_tile
 __device__ __forceinline__ uint32_t fold_idesc(int n_tile) {
     return (1u << 4) | ((uint32_t)(n_tile >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -159,17 +177,20 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&rr)[32], const int3
     }
 }
 
-template <int MODE>   // 0: fp16 hi/lo output, 1: fp32 output (plain or token grid)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
+template <int MODE, bool GEN = false>   // MODE 0: fp16 hi/lo output, 1: fp32 output (plain or token grid)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS + (GEN ? F_GEN_THREADS : 0), 1)
 fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                 FoldGemm g, FoldEpi ep) {
+                 FoldGemm g, FoldEpi ep, FoldGen gen) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[F_MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[F_MAX_STAGES];
     __shared__ __align__(8) uint64_t tmem_full[2];
     __shared__ __align__(8) uint64_t tmem_empty[2];
     __shared__ __align__(8) uint64_t basis_bar;
+    __shared__ __align__(8) uint64_t gen_full[F_GEN_STAGES];
+    __shared__ __align__(8) uint64_t gen_empty[F_GEN_STAGES];
+    __shared__ __align__(8) uint2 sel_lut[GEN ? 256 : 1];    // GEN: sign byte -> the four PRMT selectors of its bit pairs
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) int32_t col_off[288];     // n_tile + one chunk of slack (guarded reads past the end)
     __shared__ __align__(16) float col_scale[288];
@@ -180,6 +201,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     uint8_t* basis_lo = smem + g.basis_bytes;
     uint8_t* ring = smem + 2 * g.basis_bytes;
     unsigned* smax = reinterpret_cast<unsigned*>(ring + g.stages * F_STAGE);
+    uint8_t* gen_ring = ring + g.stages * F_STAGE + g.score_groups * 128 * 4;     // GEN only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -188,7 +210,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int slice = pair % n_slices;
     const int grp = slice & 1, nt = slice >> 1;
     const int pair_in_slice = pair / n_slices, pairs_per_slice = n_pairs / n_slices;
-    const int n_work = (g.n_seg >> 1) * g.tiles_per_seg;        // work items of this slice
+    const int n_work = GEN ? gen.n_work : (g.n_seg >> 1) * g.tiles_per_seg;        // work items of this slice
     const int n_lim = min(g.n_tile, g.n_valid - nt * g.n_tile);  // valid columns of this slice
 
     if (threadIdx.x == 0) {
@@ -197,7 +219,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         tma_prefetch_desc(&map_b_hi);
         tma_prefetch_desc(&map_b_lo);
         for (int s = 0; s < F_MAX_STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], GEN ? 8 : 1);   // GEN: the four producer warps of a group, both CTAs
             mbar_init(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -205,6 +227,10 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             mbar_init(&tmem_empty[a], 16);    // 8 epilogue warps in each CTA of the pair
         }
         mbar_init(&basis_bar, 1);
+        for (int t = 0; t < F_GEN_STAGES; ++t) {
+            mbar_init(&gen_full[t], 1);
+            mbar_init(&gen_empty[t], 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // per-slice output tables: where basis row n goes and what it is multiplied by
@@ -237,6 +263,15 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         col_grp[n] = grp_v;
     }
     for (int i = threadIdx.x; i < g.score_groups * 128; i += blockDim.x) smax[i] = 0u;
+    if (GEN) {
+        // selector of a pair of elements: bytes 0-3 = the "bit is 1" word, 4-7 = the "bit is 0" word; low half <- first bit
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            uint32_t sel[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) sel[m] = (((((uint32_t)i >> (2 * m)) & 3u) * 0x2244u) & 0x4444u) ^ 0x7654u;
+            sel_lut[i] = make_uint2(sel[0] | (sel[1] << 16), sel[2] | (sel[3] << 16));
+        }
+    }
     if (warp == 2) tmem_alloc_2sm(&tmem_base_slot, 512);
     tc_fence_before();
     __syncthreads();
@@ -258,7 +293,32 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
         int s = 0;
         uint32_t ph = 1;                                 // parity of a free slot
-        for (int w = pair_in_slice; w < n_work; w += pairs_per_slice) {
+        if (GEN) {
+            // table blocks and sign/valid words of this CTA's four images, one ring stage per k block
+            int t = 0;
+            uint32_t tph = 1;
+            const uint32_t gen_s = smem_u32(gen_ring);
+            const int64_t n_grp4 = (gen.n_img + 3) >> 2;
+            for (int w = pair_in_slice; w < n_work; w += pairs_per_slice) {
+                const int iblk = w % gen.n_iblk;
+                int u = w / gen.n_iblk;
+                const int ch = u % gen.C;
+                u /= gen.C;
+                const int a = u & 1, g4 = (u >> 1) * 2 + (int)rank;
+                const uint4* tp = gen.tab + ((((int64_t)(grp * 2 + a) * gen.C + ch) * gen.n_iblk + iblk) * g.num_kb) * 512;
+                const uint16_t* bp = gen.bv + (((((int64_t)(grp * 2 + a) * n_grp4 + g4) * gen.C + ch) * gen.n_iblk + iblk) * g.num_kb) * 512;
+                const bool has_img = g4 < n_grp4;
+                for (int kb = 0; kb < g.num_kb; ++kb, tp += 512, bp += 512) {
+                    mbar_wait(&gen_empty[t], tph);
+                    const uint32_t dst = gen_s + (uint32_t)t * F_GEN_STAGE;
+                    mbar_expect_tx(&gen_full[t], has_img ? 8192u + 1024u : 8192u);
+                    bulk_copy_g2s(dst, tp, 8192u, &gen_full[t]);
+                    if (has_img) bulk_copy_g2s(dst + 8192u, bp, 1024u, &gen_full[t]);
+                    if (++t == F_GEN_STAGES) { t = 0; tph ^= 1u; }
+                }
+            }
+        }
+        for (int w = pair_in_slice; !GEN && w < n_work; w += pairs_per_slice) {
             const int seg = (w / g.tiles_per_seg) * 2 + grp;
             const int row0 = (w % g.tiles_per_seg) * 256 + (int)rank * 128;
             for (int kb = 0; kb < g.num_kb; ++kb) {
@@ -307,7 +367,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             }
             umma_commit_2sm(&tmem_full[acc], 3);         // accumulator complete in both CTAs
         }
-    } else if (warp >= 2) {
+    } else if (warp >= 2 && warp < F_THREADS / 32) {
         // ---------------- epilogue warps: TMEM lane quarter = warp & 3, 32-column chunks alternate between
         // the two warps of a quarter
         const int quarter = warp & 3, chalf = (warp - 2) >> 2;
@@ -318,10 +378,27 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const bool dc_slice = (ep.dc != nullptr) && grp == 0 && nt == 0;
         uint32_t tcount = 0;
         for (int w = pair_in_slice; w < n_work; w += pairs_per_slice, ++tcount) {
-            const int seg = (w / g.tiles_per_seg) * 2 + grp;
-            const int r = (w % g.tiles_per_seg) * 256 + (int)rank * 128 + quarter * 32 + lane;   // stacked row
-            const bool row_ok = r < g.rows_per_seg;
-            const int item = r / ep.rows_per_item, rin = r - item * ep.rows_per_item;
+            int seg, r, item, rin;
+            bool row_ok;
+            if (GEN) {
+                // w = ((image group * 2 + a) * C + channel) * n_iblk + i block; TMEM quarter = image of the group
+                const int iblk = w % gen.n_iblk;
+                int t = w / gen.n_iblk;
+                const int ch = t % gen.C;
+                t /= gen.C;
+                const int img = (t >> 1) * 8 + (int)rank * 4 + quarter;
+                seg = grp;
+                r = 0;
+                rin = iblk * 32 + lane;
+                item = (t & 1) * (int)gen.n_planes + img * gen.C + ch;
+                row_ok = img < gen.n_img && rin < gen.kh2;
+            } else {
+                seg = (w / g.tiles_per_seg) * 2 + grp;
+                r = (w % g.tiles_per_seg) * 256 + (int)rank * 128 + quarter * 32 + lane;   // stacked row
+                row_ok = r < g.rows_per_seg;
+                item = r / ep.rows_per_item;
+                rin = r - item * ep.rows_per_item;
+            }
             int64_t base;
             ScoreCtx sctx{};
             if (ep.mode == 2) {
@@ -418,6 +495,93 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
+        }
+    } else if (GEN && warp >= F_THREADS / 32) {
+        // ---------------- GEN: producer warps.  Thread pt = (row i of the 32-row block, 16-byte chunk c of the 64-byte
+        // operand row) handles that (i, c) for the four images of this CTA: the table values are loaded once
+        // (4 x 16 bytes: the hi / lo halves of the two candidate values of 8 columns, already paired for PRMT), and per
+        // image one byte of sign bits picks the halves -- two PRMT per pair of elements, two 16-byte shared stores per
+        // image row.  The table block and the sign words arrive through a small ring filled by warp 0 with bulk copies
+        // (loads issued by these warps themselves would be drained by the release fence of every hand-over: measured
+        // 2x slower).
+        const int pt = (int)threadIdx.x - F_THREADS;
+        const int il = pt >> 2, c = pt & 3;
+        const uint32_t sw_off = (uint32_t)il * 64u + (uint32_t)((c ^ ((il >> 1) & 3)) << 4);     // SWIZZLE_64B
+        const uint32_t ring_s = smem_u32(ring), gen_s = smem_u32(gen_ring);
+        const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
+        const int n_stages_total = ((n_work - pair_in_slice + pairs_per_slice - 1) / pairs_per_slice) * g.num_kb;
+        int s = 0, t = 0;
+        uint32_t ph = 1, tph = 0;
+        // block of ring stage t -> registers (table words, sign/valid words, selectors), then the stage is handed back
+        auto fetch = [&](int stage_no, uint4 (&T)[4], uint32_t (&bvv)[4], uint2 (&sls)[4]) {
+            const int w = pair_in_slice + (stage_no / g.num_kb) * pairs_per_slice;
+            const int img0 = ((w / (gen.n_iblk * gen.C)) >> 1) * 8 + (int)rank * 4;
+            const int n_here = max(0, min(4, gen.n_img - img0));
+            mbar_wait(&gen_full[t], tph);
+            const uint32_t src = gen_s + (uint32_t)t * F_GEN_STAGE;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(T[k].x), "=r"(T[k].y), "=r"(T[k].z), "=r"(T[k].w)
+                             : "r"(src + (uint32_t)k * 2048u + (uint32_t)pt * 16u));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint16_t v;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(src + 8192u + (uint32_t)q * 256u + (uint32_t)pt * 2u));
+                bvv[q] = q < n_here ? (uint32_t)v : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sls[q] = sel_lut[bvv[q] & 0xffu];
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(&gen_empty[t]);          // the block is in registers
+            if (++t == F_GEN_STAGES) { t = 0; tph ^= 1u; }
+        };
+        auto emit = [&](const uint4 (&T)[4], const uint32_t (&bvv)[4], const uint2 (&sls)[4]) {
+            mbar_wait(&empty_bar[s], ph);
+            const uint32_t st_hi = ring_s + (uint32_t)s * F_STAGE + sw_off, st_lo = st_hi + F_ATILE;
+            const uint32_t ph_[4] = {T[0].x, T[0].z, T[1].x, T[1].z}, nh_[4] = {T[0].y, T[0].w, T[1].y, T[1].w};
+            const uint32_t pl_[4] = {T[2].x, T[2].z, T[3].x, T[3].z}, nl_[4] = {T[2].y, T[2].w, T[3].y, T[3].w};
+            const bool all_valid = (bvv[0] & bvv[1] & bvv[2] & bvv[3]) >= 0xff00u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint2 sl = sls[q];                         // PRMT reads the low 16 bits of its selector
+                const uint32_t sel[4] = {sl.x, sl.x >> 16, sl.y, sl.y >> 16};
+                uint32_t wh[4], wl[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    wh[m] = __byte_perm(ph_[m], nh_[m], sel[m]);
+                    wl[m] = __byte_perm(pl_[m], nl_[m], sel[m]);
+                }
+                if (!all_valid) {                        // tokens that were not kept decode to zero coefficients
+                    const uint32_t valid = bvv[q] >> 8;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        const uint32_t vm = (((valid >> (2 * m)) & 1u) ? 0xffffu : 0u) | (((valid >> (2 * m + 1)) & 1u) ? 0xffff0000u : 0u);
+                        wh[m] &= vm;
+                        wl[m] &= vm;
+                    }
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_hi + (uint32_t)q * 2048u), "r"(wh[0]), "r"(wh[1]),
+                             "r"(wh[2]), "r"(wh[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_lo + (uint32_t)q * 2048u), "r"(wl[0]), "r"(wl[1]),
+                             "r"(wl[2]), "r"(wl[3]) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote_cta_release(full_leader0 + 8u * (uint32_t)s);
+            if (++s == g.stages) { s = 0; ph ^= 1u; }
+        };
+        // software pipeline: the next stage's block is being read while this one is written
+        uint4 Ta[4], Tb[4];
+        uint32_t ba[4], bb[4];
+        uint2 sa[4], sb[4];
+        if (n_stages_total > 0) fetch(0, Ta, ba, sa);
+#pragma unroll 1
+        for (int n = 0; n < n_stages_total; n += 2) {
+            if (n + 1 < n_stages_total) fetch(n + 1, Tb, bb, sb);
+            emit(Ta, ba, sa);
+            if (n + 1 >= n_stages_total) break;
+            if (n + 2 < n_stages_total) fetch(n + 2, Ta, ba, sa);
+            emit(Tb, bb, sb);
         }
     }
     __syncwarp();
@@ -799,40 +963,52 @@ static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0,
 }
 
 static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_seg, const FoldOperand& Bas, int n_valid,
-                            int K, FoldEpi ep, void* stream) {
+                            int K, FoldEpi ep, void* stream, const FoldGen* gen = nullptr) {
     if (rows_per_seg == 0 || n_seg == 0) return DCTA_OK;
     FoldGemm g{};
     const int score_groups = (ep.mode == 2 && ep.maxabs != nullptr) ? ep.tiles_h : 0;
-    if (!fold_geometry(n_valid, K, g, score_groups)) { set_error("fold_gemm: basis %d x %d does not fit in shared memory", n_valid, K); return DCTA_ERR_UNSUPPORTED; }
+    const int gen_bytes = gen ? F_GEN_STAGES * F_GEN_STAGE : 0;
+    if (!fold_geometry(n_valid, K, g, score_groups, gen_bytes)) { set_error("fold_gemm: basis %d x %d does not fit in shared memory", n_valid, K); return DCTA_ERR_UNSUPPORTED; }
     if (rows_per_seg >= (1ll << 31) - 256 || (n_seg & 1)) { set_error("fold_gemm: bad segment geometry"); return DCTA_ERR_INVALID_ARG; }
     g.n_seg = n_seg;
     g.rows_per_seg = (int)rows_per_seg;
     g.tiles_per_seg = (int)ceil_div(rows_per_seg, 256);
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_map3(&ma_hi, A.hi, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
-    if ((rc = make_map3(&ma_lo, A.lo, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
     if ((rc = make_map3(&mb_hi, Bas.hi, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
     if ((rc = make_map3(&mb_lo, Bas.lo, K, n_valid, 2, Bas.ld, Bas.seg_stride, g.n_tile / 2))) return rc;
-    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4;
+    if (gen) {                                    // the data operand is generated in shared memory: no tensor map
+        ma_hi = mb_hi;
+        ma_lo = mb_lo;
+    } else {
+        if ((rc = make_map3(&ma_hi, A.hi, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
+        if ((rc = make_map3(&ma_lo, A.lo, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
+    }
+    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4 + gen_bytes;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int n_slices = 2 * g.n_ntiles;
-    const int64_t work_per_slice = (int64_t)(n_seg / 2) * g.tiles_per_seg;
+    const int64_t work_per_slice = gen ? gen->n_work : (int64_t)(n_seg / 2) * g.tiles_per_seg;
     int64_t pps = (sms / 2) / n_slices;                      // pairs per slice
     if (pps < 1) pps = 1;
     if (pps > work_per_slice) pps = work_per_slice;
     const unsigned grid = (unsigned)(2 * pps * n_slices);
+    const FoldGen no_gen{};
     cudaError_t e;
-    if (ep.mode == 0 || ep.mode == 3) {          // fp16 hi/lo outputs
+    if (gen) {
+        if (ep.mode != 0) { set_error("fold_gemm: generated operands feed the fp16 hi/lo output only"); return DCTA_ERR_INVALID_ARG; }
+        e = cudaFuncSetAttribute(fold_gemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e == cudaSuccess)
+            fold_gemm_kernel<0, true><<<grid, F_THREADS + F_GEN_THREADS, smem_bytes, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, g, ep, *gen);
+    } else if (ep.mode == 0 || ep.mode == 3) {          // fp16 hi/lo outputs
         e = cudaFuncSetAttribute(fold_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e == cudaSuccess)
-            fold_gemm_kernel<0><<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, g, ep);
+            fold_gemm_kernel<0><<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, g, ep, no_gen);
     } else {
         e = cudaFuncSetAttribute(fold_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e == cudaSuccess)
-            fold_gemm_kernel<1><<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, g, ep);
+            fold_gemm_kernel<1><<<grid, F_THREADS, smem_bytes, as_stream(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, g, ep, no_gen);
     }
     if (e != cudaSuccess) { set_error("fold_gemm: %s", cudaGetErrorString(e)); return DCTA_ERR_LAUNCH; }
     return check_launch("fold_gemm");
@@ -1437,6 +1613,136 @@ __global__ void __launch_bounds__(256, 3) decode_codes_rows_kernel(const int64_t
     }
 }
 
+// ------------------------------------------------------------------------------ decode inside inverse pass 1 (GEN)
+// The two-value tables of decode_tables_kernel in the order the producer warps of fold_gemm_kernel<0, true> read them:
+// one 8 KB block per (b, a, channel, 32-row block of i, 32-column block of j) = [4 parts][128 threads pt = il*4 + c] uint4;
+// a uint4 of part 0 / 1 holds {P, N, P, N} words of the pairs (0, 1) / (2, 3) of chunk c (columns j = kb*32 + c*8 + k)
+// built from the fp16 HI halves, parts 2 / 3 the same from the LO halves: P = halves of the "bit is 1" values
+// median + s*sd of the pair's two columns, N = of the "bit is 0" values median - s*sd.  Coefficient (kh, kw) =
+// (2i + a, 2j + b); zero outside the plane and at the DC position (carried in dc[]).
+__global__ void __launch_bounds__(256) decode_gen_tables_kernel(LfqNormParams q, int p, int rows, int cols, int n_iblk,
+                                                                int num_kb, float scale, uint32_t* __restrict__ tab) {
+    const int64_t total = (int64_t)4 * q.C * n_iblk * num_kb * 2048;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int wi = (int)(idx & 3), pt = (int)((idx >> 2) & 127), part = (int)((idx >> 9) & 3);
+        int64_t r = idx >> 11;
+        const int kb = (int)(r % num_kb);
+        r /= num_kb;
+        const int iblk = (int)(r % n_iblk);
+        r /= n_iblk;
+        const int ch = (int)(r % q.C);
+        r /= q.C;
+        const int a = (int)(r & 1), b = (int)(r >> 1);
+        const int il = pt >> 2, c = pt & 3;
+        const int kh = 2 * (iblk * 32 + il) + a;
+        const int m = (part & 1) * 2 + (wi >> 1);
+        const bool neg = wi & 1, lo_half = part >> 1;
+        uint32_t word = 0u;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int kw = 2 * (kb * 32 + c * 8 + 2 * m + e) + b;
+            uint32_t v = 0u;
+            if (kh < rows && kw < cols && !(kh == 0 && kw == 0)) {
+                const int ty = kh / p, py = kh - ty * p, tx = kw / p, px = kw - tx * p;
+                if (ty < q.H && tx < q.W) {
+                    const int64_t el = (((int64_t)ch * q.H + ty) * q.W + tx) * q.z + py * p + px;
+                    const float sd = __fadd_rn(__fmul_rn(__ldg(q.b + el), kSqrt2f), q.eps);
+                    const float md = __ldg(q.median + el);
+                    v = pack_split16(__fadd_rn(__fmul_rn(neg ? -q.scale : q.scale, sd), md), scale);     // patchnorm.py:177
+                }
+            }
+            word |= (lo_half ? (v >> 16) : (v & 0xffffu)) << (16 * e);
+        }
+        tab[idx] = word;
+    }
+}
+
+// The sign bits of the code words (one LFQ codebook per patch row: c == d == p even, lfq.py:105-134) and the "token was
+// kept" bits of a batch, re-ordered for the producer warps: per (b, a, plane, 32-row block of i, 32-column block of j)
+// a 256-byte block [32 rows][4 chunks] of 16-bit words, low byte = sign bits of the 8 columns j = kb*32 + c*8 + k (bit k)
+// of coefficient row kh = 2i + a and column parity b, high byte = valid bits.  One CTA = one (plane, i block): 64
+// coefficient rows x groups of 8 tokens; a thread takes one row of 8 consecutive tokens, whose HW-bit fields of one
+// parity concatenate to exactly HW bytes.  The words are staged in shared memory in their final order -- the k blocks
+// of a (b, a, plane, i block) are contiguous in memory -- and written out with 16-byte stores.  Every token record
+// (p code words) is read completely inside one CTA.  Also dc[plane] (the DC coefficient, scaled for the unfold kernel).
+__device__ __forceinline__ uint32_t compress_even_bits16(uint32_t x) {      // bits 0, 2, 4, ... -> bits 0, 1, 2, ...
+    x &= 0x5555u;
+    x = (x | (x >> 1)) & 0x3333u;
+    x = (x | (x >> 2)) & 0x0f0fu;
+    x = (x | (x >> 4)) & 0x00ffu;
+    return x;
+}
+
+template <int HW>      // HW = p / 2 bits of one column parity per token
+__global__ void __launch_bounds__(512) codes_bitplanes_kernel(const int64_t* __restrict__ codes, const int32_t* __restrict__ slot_map,
+                                                              const int32_t* __restrict__ img_sel, int64_t n_img, int C, int th,
+                                                              int tw, int rows, int cols, int n_iblk, int num_kb, int n_grp,
+                                                              LfqNormParams q, uint16_t* __restrict__ bv, float* __restrict__ dc,
+                                                              float dc_factor) {
+    extern __shared__ __align__(16) uint16_t stage[];          // [b][a][kb][32 rows][4]
+    constexpr int p = 2 * HW;
+    const int64_t n_planes = n_img * C;
+    const int64_t plane = blockIdx.x;
+    const int iblk = blockIdx.y;
+    const int blk_words = num_kb * 128;                        // words of one (b, a)
+    for (int e = threadIdx.x; e < blk_words * 2; e += blockDim.x) reinterpret_cast<uint32_t*>(stage)[e] = 0u;
+    __syncthreads();
+    const int64_t k_img = plane / C;
+    const int ch = (int)(plane - k_img * C);
+    const int64_t img = img_sel ? img_sel[k_img] : k_img;
+    for (int t = threadIdx.x; t < 64 * n_grp; t += blockDim.x) {
+        const int rr = t / n_grp, G = t - rr * n_grp;           // rr = 2 * il + a
+        const int kh = iblk * 64 + rr;
+        if (kh >= rows) continue;
+        const int ty = kh / p, py = kh - ty * p;
+        const int n_tx = ty < th ? min(tw, cols / p) : 0;
+        const int32_t* smap = slot_map + ((img * C + ch) * th + (ty < th ? ty : 0)) * tw;
+        uint64_t s0 = 0, s1 = 0, sv = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int tx = G * 8 + u;
+            const int32_t slot = tx < n_tx ? __ldg(smap + tx) : -1;
+            if (slot >= 0) {
+                const uint32_t word = (uint32_t)__ldg(codes + (int64_t)slot * q.c + py);
+                const uint32_t r = __brev(word) >> (32 - p);                   // bit px of r = sign of column px
+                s0 |= (uint64_t)compress_even_bits16(r) << (HW * u);
+                s1 |= (uint64_t)compress_even_bits16(r >> 1) << (HW * u);
+                sv |= (uint64_t)((1u << HW) - 1u) << (HW * u);
+            }
+        }
+        if (kh == 0 && G == 0) {
+            float dcval = 0.0f;
+            if (sv & 1u) {
+                const int64_t el = (((int64_t)ch * q.H) * q.W) * q.z;
+                const float sd = __fadd_rn(__fmul_rn(__ldg(q.b + el), kSqrt2f), q.eps);
+                const float qv = (s0 & 1u) ? q.scale : -q.scale;
+                dcval = __fadd_rn(__fmul_rn(qv, sd), __ldg(q.median + el)) * dc_factor;
+            }
+            dc[plane] = dcval;
+        }
+        const int a = rr & 1, il = rr >> 1;
+#pragma unroll
+        for (int m = 0; m < HW; ++m) {
+            const int jb = G * HW + m;                           // byte of the row's bit string: columns j = 8 jb .. 8 jb + 7
+            if (jb < num_kb * 4) {
+                const uint32_t vb = (uint32_t)(sv >> (8 * m)) & 0xffu;
+                const int o = a * blk_words + (jb >> 2) * 128 + il * 4 + (jb & 3);
+                stage[o] = (uint16_t)(((uint32_t)(s0 >> (8 * m)) & 0xffu) | (vb << 8));
+                stage[o + 2 * blk_words] = (uint16_t)(((uint32_t)(s1 >> (8 * m)) & 0xffu) | (vb << 8));
+            }
+        }
+    }
+    __syncthreads();
+    // 256-byte blocks [32 rows][4] at [b][a][group of 4 images][channel][i block][k block][image in group], 16-byte stores
+    const int64_t n_grp4 = (n_img + 3) >> 2;
+    for (int e = threadIdx.x; e < 4 * num_kb * 16; e += blockDim.x) {
+        const int v = e & 15, kb = (e >> 4) % num_kb, ba = (e >> 4) / num_kb;
+        uint4* dst = reinterpret_cast<uint4*>(bv + ((((((int64_t)ba * n_grp4 + (k_img >> 2)) * C + ch) * n_iblk + iblk) * num_kb + kb) * 4 +
+                                                    (k_img & 3)) * 128) + v;
+        *dst = reinterpret_cast<const uint4*>(stage)[e];
+    }
+}
+
 // fp32 coefficient planes (n_planes, kh, kw) -> folded split quadrants (DC moved to dc[])
 __global__ void __launch_bounds__(256) fold_coef_kernel(const float* __restrict__ y, __half* __restrict__ hi,
                                                         __half* __restrict__ lo, float* __restrict__ dc,
@@ -1658,6 +1964,98 @@ extern "C" int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const vo
     e2.alpha = 1.0f / (kFScaleBasis * kFScaleQ);
     int rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)kh2, 2, B1, w2, kw2, e1, stream);
     if (rc) return rc;
+    return launch_fold_gemm(A2, n_planes * (int64_t)w2, 4, B2, h2, kh2, e2, stream);
+}
+
+// ---- decode from LFQ codes INSIDE inverse pass 1: the coefficient quadrants yq are never materialised
+static void decode_inv_sizes(int64_t n_img, int C, int kh, int kw, int& n_iblk, int& num_kb, int64_t& tab_bytes, int64_t& bv_bytes) {
+    n_iblk = (int)ceil_div(kh / 2, 32);
+    num_kb = (int)ceil_div(kw / 2, FK);
+    tab_bytes = (int64_t)4 * C * n_iblk * num_kb * 8192;
+    bv_bytes = (int64_t)4 * ((n_img + 3) / 4 * 4) * C * n_iblk * num_kb * 256;      // 32 rows x 4 chunks x 2 bytes per (i block, k block)
+}
+
+extern "C" int64_t dcta_decode_codes_inv_fold_scratch_bytes(int64_t n_img, int channels_n, int kh, int kw) {
+    int n_iblk, num_kb;
+    int64_t tab_bytes, bv_bytes;
+    decode_inv_sizes(n_img, channels_n, kh, kw, n_iblk, num_kb, tab_bytes, bv_bytes);
+    return tab_bytes + bv_bytes;
+}
+
+extern "C" int dcta_decode_codes_inv_fold_supported(int h, int w, int kh, int kw, int p, int c, int d) {
+    if (!fold_dims_ok(h, w, kh, kw) || p < 8 || p > 16 || (p & 1) || c != p || d != p || kh % p || kw % p) return 0;
+    FoldGemm g{};
+    return fold_geometry(w / 2, kw / 2, g, 0, F_GEN_STAGES * F_GEN_STAGE) && fold_geometry(h / 2, kh / 2, g);
+}
+
+extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
+                                          int channels_n, int th, int tw, int p, int kh, int kw, int h, int w,
+                                          const float* median, const float* b, int H, int W, float eps, int c, int d,
+                                          float scale, const void* bwt_hi, const void* bwt_lo, const void* bht_hi,
+                                          const void* bht_lo, void* work_hi, void* work_lo, float* z, float* dc,
+                                          void* scratch, void* stream) {
+    DCTA_REQUIRE(codes && slot_map && median && b && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && z && dc && scratch,
+                 "decode_codes_inv_fold: null pointer");
+    DCTA_REQUIRE(dcta_decode_codes_inv_fold_supported(h, w, kh, kw, p, c, d),
+                 "decode_codes_inv_fold: needs one LFQ codebook per patch row (c == d == p in 8..16), h, w multiples of 16, even kh, kw");
+    DCTA_REQUIRE(th <= H && tw <= W && kh / p <= H && kw / p <= W && n_img * channels_n < (1 << 24),
+                 "decode_codes_inv_fold: token grid outside the PatchNorm tables");
+    if (n_img == 0) return DCTA_OK;
+    const int64_t n_planes = n_img * channels_n;
+    const int h2 = h / 2, w2 = w / 2, kh2 = kh / 2, kw2 = kw / 2;
+    const int64_t ldq = ceil_div(kw2, 8) * 8, ldi = ceil_div(kh2, 8) * 8;
+    int n_iblk, num_kb;
+    int64_t tab_bytes, bv_bytes;
+    decode_inv_sizes(n_img, channels_n, kh, kw, n_iblk, num_kb, tab_bytes, bv_bytes);
+    uint32_t* tab = reinterpret_cast<uint32_t*>(scratch);
+    uint16_t* bv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(scratch) + tab_bytes);
+    LfqNormParams q{median, b, channels_n, H, W, p * p, eps, 0.f, 0.f, c, d, scale};
+    decode_gen_tables_kernel<<<grid_for(tab_bytes / 4, 256), 256, 0, as_stream(stream)>>>(q, p, kh, kw, n_iblk, num_kb, kFScaleY, tab);
+    {
+        const int n_grp = (int)ceil_div(kw / p, 8);
+        DCTA_REQUIRE(n_iblk <= 65535, "decode_codes_inv_fold: plane too tall for the bit-plane kernel");
+        const dim3 grid((unsigned)n_planes, (unsigned)n_iblk);
+        int threads = 64 * n_grp;
+        threads = threads > 512 ? 512 : (threads + 31) / 32 * 32;
+        const int stage_bytes = 4 * num_kb * 256;
+        const float dcf = 1.0f / sqrtf((float)h * (float)w);
+#define DCTA_BITPLANES(HW)                                                                                                   \
+    codes_bitplanes_kernel<HW><<<grid, threads, stage_bytes, as_stream(stream)>>>(codes, slot_map, img_sel, n_img, channels_n, th, \
+                                                                                  tw, kh, kw, n_iblk, num_kb, n_grp, q, bv, dc, dcf)
+        switch (p / 2) {
+            case 4: DCTA_BITPLANES(4); break;
+            case 5: DCTA_BITPLANES(5); break;
+            case 6: DCTA_BITPLANES(6); break;
+            case 7: DCTA_BITPLANES(7); break;
+            default: DCTA_BITPLANES(8); break;
+        }
+#undef DCTA_BITPLANES
+    }
+    int rc = check_launch("decode_codes_inv_fold (tables)");
+    if (rc) return rc;
+    // pass 1 with the generated operand: Q^T[b][a][plane][w'][i] = sum_j Y[2i+a, 2j+b] CW[2j+b, w']
+    FoldGen gen{};
+    gen.tab = reinterpret_cast<const uint4*>(tab);
+    gen.bv = bv;
+    gen.n_img = (int)n_img; gen.C = channels_n; gen.kh2 = kh2; gen.n_iblk = n_iblk; gen.n_planes = n_planes;
+    gen.n_work = (int)(ceil_div(n_img, 8) * 2 * channels_n * n_iblk);
+    FoldOperand A1{nullptr, nullptr, ldq, 0};
+    FoldOperand B1{(const __half*)bwt_hi, (const __half*)bwt_lo, ldq, (int64_t)w2 * ldq};
+    FoldEpi e1{};
+    e1.mode = 0; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
+    e1.rows_per_item = kh2; e1.seg_stride = 2 * n_planes * (int64_t)w2 * ldi; e1.item_stride = (int64_t)w2 * ldi;
+    e1.col_mul = 1; e1.col_add = 0; e1.col_stride = (int)ldi;
+    e1.alpha = kFScaleQ / (kFScaleBasis * kFScaleY);
+    rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)kh2, 2, B1, w2, kw2, e1, stream, &gen);
+    if (rc) return rc;
+    // pass 2 as in dcta_dct2_inv_fold
+    FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, ldi, n_planes * (int64_t)w2 * ldi};
+    FoldOperand B2{(const __half*)bht_hi, (const __half*)bht_lo, ldi, (int64_t)h2 * ldi};
+    FoldEpi e2{};
+    e2.mode = 1; e2.out_f32 = z; e2.rows_per_item = w2;
+    e2.seg_stride = n_planes * (int64_t)h2 * w2; e2.item_stride = (int64_t)h2 * w2;
+    e2.col_mul = 1; e2.col_add = 0; e2.col_stride = w2;
+    e2.alpha = 1.0f / (kFScaleBasis * kFScaleQ);
     return launch_fold_gemm(A2, n_planes * (int64_t)w2, 4, B2, h2, kh2, e2, stream);
 }
 

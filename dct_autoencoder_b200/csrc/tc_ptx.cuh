@@ -38,6 +38,11 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// 1-D bulk copy global -> this CTA's shared memory (16-byte aligned addresses and size), completion bytes on a local mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -118,6 +123,12 @@ __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
 // arrive on a barrier that may live in the peer CTA (address from mapa_u32)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// the same with CTA-scope release (the PTX default): for data that stays inside the arriving CTA -- shared-memory
+// tiles this CTA wrote for ITS OWN tensor core, whose MMA the pair leader issues after seeing the arrival.  The
+// cluster-scope version above compiles to MEMBAR.ALL.GPU + ERRBAR (a round trip to L2 on every hand-over).
+__device__ __forceinline__ void mbar_arrive_remote_cta_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // the same without release semantics: for hand-offs that are ordered by tcgen05 fences (TMEM reads), so that
 // the arrive does not wait for the warp's outstanding global stores

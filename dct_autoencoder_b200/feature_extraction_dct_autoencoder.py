@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from .dct_patches import DCTPatches
-from .util import (_round8, dct2, dct2_fwd_fold, dct2_fwd_fold_codes, dct2_fwd_tc, dct2_inv_fold, dct2_inv_tc, dct2_truncated,
+from .util import (_round8, dct2, decode_codes_inv_fold, decode_codes_inv_fold_ok, dct2_fwd_fold, dct2_fwd_fold_codes, dct2_fwd_tc, dct2_inv_fold, dct2_inv_tc, dct2_truncated,
                    exp_trunc_dist, fold_ok, idct2, idct2_truncated, ipt_to_rgb, rgb_to_ipt, rgb_to_ipt_fold,
                    rgb_to_ipt_split, tc_forward_ok, to_device_f32, to_device_pixels, unfold_ipt_to_rgb, unit_to_u8)
 
@@ -77,6 +77,9 @@ class DCTAutoencoderFeatureExtractor:
         self._table_cache_size = 64
         self._keepalive: Optional[List[torch.Tensor]] = None
         self._maxabs: Optional[torch.Tensor] = None
+        # decode from codes: generate the operand of inverse pass 1 in shared memory (no coefficient planes in HBM);
+        # False = the separate decode kernel followed by the plain inverse (tests compare the two bit for bit)
+        self.decode_in_gemm = True
 
     # ------------------------------------------------------------------ helpers
     def _dev(self, like: Optional[torch.Tensor] = None) -> torch.device:
@@ -645,6 +648,13 @@ class DCTAutoencoderFeatureExtractor:
             n, kh, kw = len(idx), gh * p, gw * p
             with torch.cuda.device(dev):
                 st = _lib.stream_ptr(dev)
+                if (self.dct_impl == "tc" and C == 3 and codes is not None and self.decode_in_gemm and
+                        decode_codes_inv_fold_ok(h, w, kh, kw, p, lfq.num_codebooks, lfq.codebook_dim)):
+                    z, dc = decode_codes_inv_fold(codes, slot_map, sel, n, C, th, tw, p, kh, kw, h, w, norm.median.data,
+                                                  norm.b.data, norm.max_patch_h, norm.max_patch_w, norm.eps,
+                                                  lfq.num_codebooks, lfq.codebook_dim, lfq.codebook_scale)
+                    yield idx, unfold_ipt_to_rgb(z, dc, h, w, out_dtype)
+                    continue
                 if self.dct_impl == "tc" and C == 3 and p >= 8 and fold_ok(h, w, kh, kw):
                     ldq = _round8(kw // 2)
                     y_hi = torch.empty((2, 2, n * C, kh // 2, ldq), dtype=torch.float16, device=dev)

@@ -659,6 +659,34 @@ def dct2_inv_fold(yq_hi: torch.Tensor, yq_lo: torch.Tensor, kh: int, kw: int, h:
     return z
 
 
+def decode_codes_inv_fold_ok(h: int, w: int, kh: int, kw: int, p: int, c: int, d: int) -> bool:
+    return bool(_lib.load().dcta_decode_codes_inv_fold_supported(h, w, kh, kw, p, c, d))
+
+
+def decode_codes_inv_fold(codes, slot_map, sel, n_img: int, channels: int, th: int, tw: int, p: int, kh: int, kw: int,
+                          h: int, w: int, median, b, H: int, W: int, eps: float, c: int, d: int, scale: float):
+    """LFQ codes -> quadrant transforms z (4, n_img*channels, h/2, w/2) + dc (n_img*channels): de-quantisation,
+    inverse PatchNorm and un-patchify (lfq.py:105-134, patchnorm.py:167-177, FE:607-656) happen in the operand
+    producer of inverse pass 1 (``dcta_decode_codes_inv_fold``); the coefficient planes are never written."""
+    dev = codes.device
+    n_planes = n_img * channels
+    bwt_hi, bwt_lo, _ = fold_basis(w, kw, dev, True)
+    bht_hi, bht_lo, _ = fold_basis(h, kh, dev, True)
+    ldi = _round8(kh // 2)
+    work_hi = torch.empty((2, 2, n_planes, w // 2, ldi), dtype=torch.float16, device=dev)
+    work_lo = torch.empty_like(work_hi)
+    z = torch.empty((4, n_planes, h // 2, w // 2), dtype=torch.float32, device=dev)
+    dc = torch.empty(n_planes, dtype=torch.float32, device=dev)
+    scratch = torch.empty(_lib.load().dcta_decode_codes_inv_fold_scratch_bytes(n_img, channels, kh, kw), dtype=torch.uint8,
+                          device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_decode_codes_inv_fold", _lib.ptr(codes), _lib.ptr(slot_map), _lib.ptr(sel), n_img, channels, th, tw,
+                  p, kh, kw, h, w, _lib.ptr(median), _lib.ptr(b), H, W, float(eps), c, d, float(scale), _lib.ptr(bwt_hi),
+                  _lib.ptr(bwt_lo), _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z),
+                  _lib.ptr(dc), _lib.ptr(scratch), _lib.stream_ptr(dev))
+    return z, dc
+
+
 def unfold_ipt_to_rgb(z: torch.Tensor, dc: Optional[torch.Tensor], h: int, w: int, out_dtype=torch.float32) -> torch.Tensor:
     """Final butterfly of the folded inverse fused with util.py:85-97: z (4, n_img*3, h/2, w/2) -> RGB (n_img, 3, h, w).
     ``out_dtype=torch.uint8``: 8-bit pixels, quantised in the same kernel as ``unit_to_u8`` does."""

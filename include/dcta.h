@@ -200,6 +200,21 @@ int dcta_decode_codes_fold(const int64_t* codes, const int32_t* slot_map, const 
                            int64_t n_img, int channels_n, int th, int tw, int p, int rows, int cols, int out_h,
                            int out_w, const float* median, const float* b, int H, int W, float eps, int c,
                            int d, float scale, void* yq_hi, void* yq_lo, float* dc, void* tab_scratch, void* stream);
+/* Decode from LFQ codes INSIDE inverse pass 1 (FE:607-656 revert_patching + PN:167-177 inverse_norm + LFQ:105-134
+ * indices_to_codes + the inverse DCT of FE:289-310 in three launches + the table kernel): the data operand of pass 1 is
+ * generated in shared memory from one sign bit per coefficient and a table of the two values a de-quantised,
+ * de-normalised coefficient can take, so the coefficient planes are never written.  Needs one codebook per patch row
+ * (c == d == p, 8 <= p <= 16).  Arguments as dcta_decode_codes_fold + dcta_dct2_inv_fold (kh = rows, kw = cols);
+ *   scratch: dcta_decode_codes_inv_fold_scratch_bytes(...) bytes, 256-byte aligned.
+ * Results are bit-identical to dcta_decode_codes_fold followed by dcta_dct2_inv_fold. */
+int64_t dcta_decode_codes_inv_fold_scratch_bytes(int64_t n_img, int channels_n, int kh, int kw);
+int dcta_decode_codes_inv_fold_supported(int h, int w, int kh, int kw, int p, int c, int d);
+int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
+                               int channels_n, int th, int tw, int p, int kh, int kw, int h, int w,
+                               const float* median, const float* b, int H, int W, float eps, int c, int d,
+                               float scale, const void* bwt_hi, const void* bwt_lo, const void* bht_hi,
+                               const void* bht_lo, void* work_hi, void* work_lo, float* z, float* dc,
+                               void* scratch, void* stream);
 /* fp32 coefficient planes y (n_planes, kh, kw) -> folded quadrants. */
 int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, float* dc, int64_t n_planes, int kh,
                           int kw, int out_h, int out_w, void* stream);

@@ -273,3 +273,38 @@ def test_uint8_pixels_in_and_out(D):
         assert blob[D.dct_patches.WIRE_HEADER_BYTES:] == records[i, :int(counts[i])].numpy().tobytes()
         dp, c2 = D.from_bytes(blob)
         assert torch.equal(c2, codes_f[i])
+
+
+@pytest.mark.parametrize("size,max_seq_len,n,beta", [
+    ((512, 512), 3072, 5, 0.0),        # the benchmark geometry: every token kept, 5 images (a partial group of 8)
+    ((256, 256), 700, 9, 0.0),         # top-k cut: dropped tokens decode to zero; 126 coefficient rows per parity
+    ((128, 160), 3072, 8, 0.01),       # variable k, odd row count per parity (63), K padded to a 32-column block
+    ((64, 48), 3072, 3, 0.0),          # one 32-row block, mostly padding
+])
+def test_decode_inside_inverse_pass1_is_bit_identical(D, size, max_seq_len, n, beta):
+    """dcta_decode_codes_inv_fold (the operand of inverse pass 1 generated in shared memory from the code bits,
+    csrc/dct_fold.cu fold_gemm_kernel<0, true>) against the separate decode kernel + plain inverse: same pixels,
+    bit for bit (FE:607-656, PN:167-177, LFQ:105-134, FE:289-310)."""
+    import random
+    from dct_autoencoder_b200.util import decode_codes_inv_fold_ok
+    torch.manual_seed(7)
+    h, w = size
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, beta, 32, 32, max_seq_len)
+    pn = D.PatchNorm(32, 32, 14, 3).cuda()
+    lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).cuda().eval()
+    pipe = D.TransformPipeline(fe, pn, lfq)
+    random.seed(5)
+    pipe.fit_norm(torch.rand(6, 3, h, w).cuda())
+    kh, kw = min(h // 14, 32) * 14, min(w // 14, 32) * 14
+    assert decode_codes_inv_fold_ok(h, w, kh, kw, 14, 14, 14)
+    x = torch.rand(n, 3, h, w).cuda()
+    batch, codes = pipe.encode_codes(x)
+    assert fe.decode_in_gemm
+    rec_gen = pipe.decode_codes(batch, codes)
+    rec_gen_u8 = pipe.decode_codes(batch, codes, out_dtype=torch.uint8)
+    fe.decode_in_gemm = False
+    rec_sep = pipe.decode_codes(batch, codes)
+    rec_sep_u8 = pipe.decode_codes(batch, codes, out_dtype=torch.uint8)
+    assert torch.isfinite(rec_gen).all()
+    assert torch.equal(rec_gen, rec_sep)
+    assert torch.equal(rec_gen_u8, rec_sep_u8)
