@@ -404,42 +404,50 @@ def run_ours(a):
     dct_ms = stages["dct_fwd"]
     achieved = flops_fwd / (dct_ms / 1e3) / 1e12
     peak_tf, peak_src, hbm = ctx.peak_tf, ctx.peak_src, ctx.hbm
-    if fe.dct_impl == "tc" and D.util.fold_ok(S, S, K, K):
-        # fold_gemm_kernel: 4 launches per step (forward passes 1-2, inverse passes 1-2).  After the fold the
-        # kernel is bounded by HBM (its operands and outputs stream once), not by the tensor pipe.
-        # Algorithmic bytes per launch: fp16 hi/lo quadrants in, next operand / fp32 tiles out.
+    launch_times = step_launch_times(ctx, step, reps=max(3, min(a.steps, 10)))
+    names = [n for n, _ in launch_times]
+    if (fe.dct_impl == "tc" and D.util.fold_ok(S, S, K, K) and names.count("fold_gemm") == 3 and names.count("fold_codes") == 1
+            and pipe.fusable()):
+        # The DCT GEMM launches of the TIMED step, each timed live by the library's own CUDA events on the launching
+        # stream (dcta_profile_begin / _end): forward pass 1, forward pass 2 -> code words (fold_codes_kernel),
+        # inverse pass 1 with the operand generated from code bits, inverse pass 2.
+        # Algorithmic bytes per launch: fp16 hi/lo operands in, next operand / code words / fp32 out.
         Kq, Sq = K // 2, S // 2
         xq = 3 * 4 * Sq * Sq * 4            # image quadrants, hi + lo fp16            (= 3*S*S*4)
         pt = 3 * 2 * K * Sq * 4             # forward intermediate P^T [a][plane][kw][h/2], hi + lo
-        yt = 3 * K * K * 4                  # fp32 token grid / coefficient quadrants hi + lo (same size)
         qt = 3 * 4 * Sq * Kq * 4            # inverse intermediate Q^T, hi + lo
         zq = 3 * 4 * Sq * Sq * 4            # fp32 quadrant transforms
-        alg = [xq + pt, pt + yt, yt + qt, qt + zq]
-        fwd_key = "dct_fwd"
-        if "dct_fwd_codes" in stages:
-            # the timed (fused) step runs forward pass 2 as fold_codes_kernel: P^T in, 14 code words (int32) + the
-            # maximum per token out instead of the fp32 token grid
-            n_tok = 3 * (K // 14) * (K // 14)
-            alg[1] = pt + n_tok * (14 * 4 + 4)
-            fwd_key = "dct_fwd_codes"
-        gemm_ms = stages[fwd_key] + stages["dct_inv"]
-        achieved_gbs = sum(alg) * B / (gemm_ms / 1e3) / 1e9
-        tens = (flops_fwd / (stages[fwd_key] / 1e3) / 1e12)
-        traffic, traffic_src = (traffic_from_profiles("dct_gemm_launches_b256_512") if (B == 256 and S == 512 and "dct_fwd_codes" in stages)
-                                else (None, None))
-        roofline = dict(bound="hbm", kernel="fold_gemm_kernel x3 + fold_codes_kernel (the 4 DCT GEMM launches of the timed step: "
-                        "forward pass 1, forward pass 2 -> code words, inverse passes 1-2; "
+        n_tok = 3 * (K // 14) * (K // 14)
+        bv = 3 * 4 * ((Kq + 31) // 32) * ((Kq + 31) // 32) * 256      # sign/valid words read by inverse pass 1
+        gi = [i for i, n in enumerate(names) if n == "fold_gemm"]
+        ci = names.index("fold_codes")
+        fam = [("fold_gemm_kernel<0> forward pass 1", launch_times[gi[0]][1], xq + pt, S * (K // 2) * Sq * 2 * 3 * 2),
+               ("fold_codes_kernel forward pass 2 -> LFQ code words", launch_times[ci][1], pt + n_tok * (14 * 4 + 4), 0),
+               ("fold_gemm_kernel<0, GEN> inverse pass 1, operand generated from code bits", launch_times[gi[1]][1], bv + qt, 0),
+               ("fold_gemm_kernel<1> inverse pass 2", launch_times[gi[2]][1], qt + zq, 0)]
+        gemm_ms = sum(f[1] for f in fam)
+        alg_total = sum(f[2] for f in fam) * B
+        achieved_gbs = alg_total / (gemm_ms / 1e3) / 1e9
+        tens = flops_fwd / ((fam[0][1] + fam[1][1]) / 1e3) / 1e12
+        traffic, traffic_src = (traffic_from_profiles("dct_gemm_launches_b256_512") if (B == 256 and S == 512) else (None, None))
+        roofline = dict(bound="hbm", kernel="fold_gemm_kernel x3 + fold_codes_kernel (the 4 DCT GEMM launches of the timed step; "
                         "cta_group::2 tcgen05 fp16x3 split precision, folded basis resident in shared memory)",
                         achieved=achieved_gbs, peak=hbm, unit="GB/s", frac=achieved_gbs / hbm,
                         traffic=traffic, traffic_source=traffic_src,
                         launches_per_step=4, avg_launch_ms=gemm_ms / 4,
-                        algorithmic_bytes_per_launch=sum(alg) * B / 4,
-                        peak_source=peak_src,
+                        algorithmic_bytes_per_launch=alg_total / 4,
+                        share_of_step=gemm_ms / sum(t for _, t in launch_times),
+                        launches=[dict(kernel=k, ms=t, algorithmic_bytes=ab * B, GBps=ab * B / (t / 1e3) / 1e9,
+                                       frac=ab * B / (t / 1e3) / 1e9 / hbm) for k, t, ab, _ in fam],
+                        peak_source=peak_src, timing="CUDA events recorded by libdcta after each launch of the timed step "
+                                                     "(dcta_profile_begin/_end), mean of several steps",
                         tensor=dict(achieved=tens, peak=peak_tf, unit="TFLOP/s", frac=tens / peak_tf,
                                     note="forward passes: SURVEY 8(d) flops 3*2*H*K*(W+K) per image (plain basis GEMMs); the "
                                          "folded kernel executes 1/2 of them, each as 3 tensor MMAs, so frac <= 2/3"),
-                        note="achieved = algorithmic operand + output bytes of the 4 launches / their CUDA-event time "
-                             "(the kernels' OWN hi/lo operands, not SURVEY 8d's fused bound: that is pipeline_hbm.fused)")
+                        note="achieved = algorithmic operand + output bytes of the 4 launches / their device time "
+                             "(the kernels' OWN hi/lo operands, not SURVEY 8d's fused bound: that is pipeline_hbm.fused); "
+                             "inverse pass 1 no longer reads coefficient planes, so it is bound by the tensor pipe and its "
+                             "epilogue, not by HBM")
     else:
         if fe.dct_impl in ("tc", "tc_plain"):
             kname = "gemm_split_kernel (forward DCT: 2 launches, tcgen05 fp16x3 split precision)"
@@ -473,7 +481,7 @@ def run_ours(a):
                 graphed=graphed,
                 staged=dict(value=staged_value, unit=UNIT, ms_per_step=ms_staged / staged_steps,
                             note="same job through the drop-in modules one by one (roundtrip_staged)"),
-                stages_ms=stages)
+                stages_ms=stages, launch_times_ms=[[n, round(t, 5)] for n, t in launch_times])
     if world > 1:
         line["e2e"]["note"] = ("all ranks share the host's memory and PCIe root complex: the host-to-host rate saturates there, "
                                "not on a collective (see e2e_compact for the same job with 4x fewer link bytes)")
@@ -596,6 +604,22 @@ def run_config5(ctx, a):
                             patchnorm_fit=fit, l2="805 MB per 256-image batch, larger than L2"),
                 gpu_launches=launches)
     return ctx.finish(line)
+
+
+def step_launch_times(ctx, step, reps=5):
+    """[(launch group, mean device ms)] of one step, from the library's own per-launch CUDA events
+    (dcta_profile_begin / dcta_profile_end: an event on the launching stream after every launch group)."""
+    _lib = ctx.lib
+    step()
+    ctx.torch.cuda.synchronize()
+    runs = []
+    for _ in range(reps):
+        with _lib.profile(ctx.dev) as prof:
+            step()
+        runs.append(prof.groups)
+    n = max(set(len(r) for r in runs), key=[len(r) for r in runs].count)      # steps with the usual launch sequence
+    runs = [r for r in runs if len(r) == n]
+    return [(runs[0][i][0], sum(r[i][1] for r in runs) / len(runs)) for i in range(n)]
 
 
 def stage_times(torch, D, pipe, x, dev, reps=3):

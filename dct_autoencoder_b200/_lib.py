@@ -9,7 +9,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcta.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class DctaError(RuntimeError):
@@ -28,6 +28,8 @@ SIGNATURES = {
     "dcta_last_error": [],
     "dcta_abi_version": [],
     "dcta_compiled_arch": [],
+    "dcta_profile_begin": [P],
+    "dcta_profile_end": [P, c_int, P, c_int],
     "dcta_basis_elems": [c_int, c_int, c_int],
     "dcta_basis_init": [c_int, c_int, c_int, P, P, P],
     "dcta_rgb_to_ipt": [P, P, c_int64, c_int64, P, P, P],
@@ -54,7 +56,7 @@ SIGNATURES = {
     "dcta_fold_planes": [P, P, P, P, P, c_int64, c_int, c_int, P],
     "dcta_dct2_fwd_fold": [P, P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "dcta_dct2_fwd_fold_codes": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_float, c_float, c_float, P,
-                                 c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
+                                 c_int, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "dcta_pack_codes_grid": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float,
                              c_float, c_int, c_int, P, P, P, P, P, P, P],
     "dcta_sort_tokens_maxabs": [P, P, P, c_int64, c_int, c_int, c_int, c_float, P, P],
@@ -64,7 +66,9 @@ SIGNATURES = {
     "dcta_decode_codes_inv_fold_scratch_bytes": [c_int64, c_int, c_int, c_int],
     "dcta_decode_codes_inv_fold_supported": [c_int, c_int, c_int, c_int, c_int, c_int, c_int],
     "dcta_decode_codes_inv_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                   P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P, P],
+                                   P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P, P, P],
+    "dcta_decode_gen_tables_bytes": [c_int, c_int, c_int],
+    "dcta_decode_gen_tables": [P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_float, P, P],
     "dcta_fold_coef_planes": [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_dct2_inv_fold": [P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_unfold_ipt_to_rgb": [P, P, P, c_int64, c_int, c_int, P, P, P],
@@ -107,7 +111,7 @@ SIGNATURES = {
     "dcta_wire_unpack": [P, c_int64, c_int, c_int, c_int, P, P, P, P],
 }
 _RESTYPES = {"dcta_last_error": c_char_p, "dcta_basis_elems": c_int64,
-             "dcta_decode_codes_inv_fold_scratch_bytes": c_int64}
+             "dcta_decode_codes_inv_fold_scratch_bytes": c_int64, "dcta_decode_gen_tables_bytes": c_int64}
 BASIS_F32, BASIS_SPLIT_FWD, BASIS_SPLIT_INV, BASIS_FOLD_FWD, BASIS_FOLD_INV = range(5)
 REDUCE_SCRATCH = 2048  # DCTA_REDUCE_SCRATCH
 
@@ -128,7 +132,7 @@ KERNELS_PER_CALL = {
     "dcta_row_sumsq": 1, "dcta_vq_nearest_tc": 2,
     "dcta_pack_codes_lfq": 2, "dcta_decode_codes_split": 1,
     "dcta_fold_supported": 0, "dcta_fold_codes_supported": 0, "dcta_rgb_to_ipt_fold": 2, "dcta_rgb_u8_to_ipt_fold": 2, "dcta_unfold_ipt_to_rgb_u8": 1, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
-    "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 2, "dcta_decode_codes_inv_fold": 4,
+    "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 2, "dcta_decode_codes_inv_fold": 3, "dcta_decode_gen_tables": 1, "dcta_decode_gen_tables_bytes": 0,
     "dcta_decode_codes_inv_fold_scratch_bytes": 0, "dcta_decode_codes_inv_fold_supported": 0, "dcta_fold_coef_planes": 1, "dcta_dct2_inv_fold": 2,
     "dcta_unfold_ipt_to_rgb": 1, "dcta_unfold_planes": 1, "dcta_sort_tokens_maxabs": 1, "dcta_dct2_fwd_fold_codes": 3, "dcta_pack_codes_grid": 2,
 }
@@ -192,3 +196,27 @@ def host_floats(values):
     """A ctypes float array (host pointer argument)."""
     vals = [float(v) for v in values]
     return (c_float * len(vals))(*vals)
+
+
+class profile:
+    """``with _lib.profile(device) as p: ...`` -> ``p.groups``: [(launch group name, device ms)] of every libdcta launch
+    group inside the block, from CUDA events recorded by the library on the launching stream (dcta_profile_begin / _end)."""
+
+    def __init__(self, device=None):
+        self.device = device
+        self.groups = []
+
+    def __enter__(self):
+        load().dcta_profile_begin(stream_ptr(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        cap, n_max = 1 << 16, 4096
+        names = ctypes.create_string_buffer(cap)
+        ms = (c_float * n_max)()
+        n = load().dcta_profile_end(names, cap, ms, n_max)
+        if n < 0:
+            raise DctaError("dcta_profile_end failed: " + last_error())
+        nm = names.value.decode().split("\n") if n else []
+        self.groups = [(nm[i], float(ms[i])) for i in range(min(n, n_max, len(nm)))]
+        return False

@@ -1,5 +1,6 @@
 // Error state and library identification for libdcta.so.
 #include <stdarg.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -14,10 +15,13 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+bool g_profile_on = false;
+cudaStream_t g_last_stream = nullptr;
+
 }  // namespace dcta
 
 extern "C" const char* dcta_last_error(void) { return dcta::g_err; }
-extern "C" int dcta_abi_version(void) { return 2; }
+extern "C" int dcta_abi_version(void) { return 3; }
 extern "C" int dcta_compiled_arch(void) { return 100; }
 
 // ------------------------------------------------------------------------------ basis tables (host side)
@@ -114,4 +118,65 @@ extern "C" int dcta_basis_init(int layout, int n, int k, void* hi_host, void* lo
         }
     }
     return DCTA_ERR_INVALID_ARG;
+}
+
+
+// ------------------------------------------------------------------------------ per-launch device times
+// dcta_profile_begin(stream) records a first event on `stream`; from then on every launch group the library checks
+// (check_launch) is followed by an event on its stream.  dcta_profile_end() waits for the last event and returns the
+// elapsed milliseconds between consecutive events together with the names given to check_launch: the device time of
+// each launch group, measured with CUDA events on the launching stream, without a profiler attached.
+#include <string>
+
+namespace dcta {
+static std::vector<cudaEvent_t> g_prof_events;
+static std::vector<std::string> g_prof_names;
+
+void profile_mark(const char* what) {
+    if (g_prof_events.size() >= 4096) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, g_last_stream);
+    g_prof_events.push_back(ev);
+    g_prof_names.push_back(what);
+}
+}  // namespace dcta
+
+extern "C" int dcta_profile_begin(void* stream) {
+    using namespace dcta;
+    for (cudaEvent_t ev : g_prof_events) cudaEventDestroy(ev);
+    g_prof_events.clear();
+    g_prof_names.clear();
+    g_last_stream = reinterpret_cast<cudaStream_t>(stream);
+    g_profile_on = true;
+    profile_mark("begin");
+    return DCTA_OK;
+}
+
+// names_out: the names joined by '\n' (truncated to names_cap bytes, NUL-terminated); ms_out: up to max_n durations.
+// Returns the number of launch groups recorded (<= max_n written), or a negative status.
+extern "C" int dcta_profile_end(char* names_out, int names_cap, float* ms_out, int max_n) {
+    using namespace dcta;
+    g_profile_on = false;
+    const int n = (int)g_prof_events.size() - 1;
+    if (n < 0) return 0;
+    cudaError_t e = cudaEventSynchronize(g_prof_events.back());
+    if (e != cudaSuccess) { set_error("profile_end: %s", cudaGetErrorString(e)); return DCTA_ERR_LAUNCH; }
+    std::string names;
+    for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, g_prof_events[i], g_prof_events[i + 1]);
+        if (ms_out && i < max_n) ms_out[i] = ms;
+        if (i) names += '\n';
+        names += g_prof_names[i + 1];
+    }
+    if (names_out && names_cap > 0) {
+        const size_t len = names.size() < (size_t)names_cap - 1 ? names.size() : (size_t)names_cap - 1;
+        memcpy(names_out, names.data(), len);
+        names_out[len] = 0;
+    }
+    for (cudaEvent_t ev : g_prof_events) cudaEventDestroy(ev);
+    g_prof_events.clear();
+    g_prof_names.clear();
+    return n;
 }

@@ -12,12 +12,19 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 
 void set_error(const char* fmt, ...);
 
+// dcta_profile_begin / dcta_profile_end (api.cu): while a profile is open, every check_launch() records a CUDA event
+// on the stream of the launch it checks, so that a caller gets device times per launch group without a profiler.
+extern bool g_profile_on;
+extern cudaStream_t g_last_stream;       // stream of the most recent as_stream() (one thread drives the library)
+void profile_mark(const char* what);
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
         return DCTA_ERR_LAUNCH;
     }
+    if (g_profile_on) profile_mark(what);
     return DCTA_OK;
 }
 
@@ -29,7 +36,10 @@ inline int check_launch(const char* what) {
         }                                    \
     } while (0)
 
-inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline cudaStream_t as_stream(void* s) {
+    g_last_stream = reinterpret_cast<cudaStream_t>(s);
+    return g_last_stream;
+}
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

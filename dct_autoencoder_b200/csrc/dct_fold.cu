@@ -1665,31 +1665,35 @@ __global__ void __launch_bounds__(256) decode_gen_tables_kernel(LfqNormParams q,
 // parity concatenate to exactly HW bytes.  The words are staged in shared memory in their final order -- the k blocks
 // of a (b, a, plane, i block) are contiguous in memory -- and written out with 16-byte stores.  Every token record
 // (p code words) is read completely inside one CTA.  Also dc[plane] (the DC coefficient, scaled for the unfold kernel).
-__device__ __forceinline__ uint32_t compress_even_bits16(uint32_t x) {      // bits 0, 2, 4, ... -> bits 0, 1, 2, ...
-    x &= 0x5555u;
-    x = (x | (x >> 1)) & 0x3333u;
-    x = (x | (x >> 2)) & 0x0f0fu;
-    x = (x | (x >> 4)) & 0x00ffu;
+// bits 0, 2, 4, ... of the low half -> bits 0, 1, 2, ... of the low half, and the same inside the high half
+__device__ __forceinline__ uint32_t compress_even_bits2x16(uint32_t x) {
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
     return x;
 }
 
 template <int HW>      // HW = p / 2 bits of one column parity per token
-__global__ void __launch_bounds__(512) codes_bitplanes_kernel(const int64_t* __restrict__ codes, const int32_t* __restrict__ slot_map,
-                                                              const int32_t* __restrict__ img_sel, int64_t n_img, int C, int th,
-                                                              int tw, int rows, int cols, int n_iblk, int num_kb, int n_grp,
-                                                              LfqNormParams q, uint16_t* __restrict__ bv, float* __restrict__ dc,
-                                                              float dc_factor) {
+__global__ void __launch_bounds__(256, 8) codes_bitplanes_kernel(const int64_t* __restrict__ codes, const int32_t* __restrict__ slot_map,
+                                                                 const int32_t* __restrict__ img_sel, int64_t n_img, int C, int th,
+                                                                 int tw, int rows, int cols, int n_iblk, int num_kb, int n_grp,
+                                                                 LfqNormParams q, uint16_t* __restrict__ bv, float* __restrict__ dc,
+                                                                 float dc_factor) {
     extern __shared__ __align__(16) uint16_t stage[];          // [b][a][kb][32 rows][4]
     constexpr int p = 2 * HW;
     const int64_t n_planes = n_img * C;
     const int64_t plane = blockIdx.x;
     const int iblk = blockIdx.y;
     const int blk_words = num_kb * 128;                        // words of one (b, a)
-    for (int e = threadIdx.x; e < blk_words * 2; e += blockDim.x) reinterpret_cast<uint32_t*>(stage)[e] = 0u;
+    if (iblk * 64 + 64 > rows)                                 // only the last block has rows that nobody writes
+        for (int e = threadIdx.x; e < blk_words / 2; e += blockDim.x) reinterpret_cast<uint4*>(stage)[e] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const int64_t k_img = plane / C;
     const int ch = (int)(plane - k_img * C);
     const int64_t img = img_sel ? img_sel[k_img] : k_img;
+    const uint32_t* codes32 = reinterpret_cast<const uint32_t*>(codes);          // low words of the int64 code words
+    const bool vec_slots = (tw & 7) == 0 && (reinterpret_cast<uintptr_t>(slot_map) & 15) == 0;
     for (int t = threadIdx.x; t < 64 * n_grp; t += blockDim.x) {
         const int rr = t / n_grp, G = t - rr * n_grp;           // rr = 2 * il + a
         const int kh = iblk * 64 + rr;
@@ -1697,16 +1701,26 @@ __global__ void __launch_bounds__(512) codes_bitplanes_kernel(const int64_t* __r
         const int ty = kh / p, py = kh - ty * p;
         const int n_tx = ty < th ? min(tw, cols / p) : 0;
         const int32_t* smap = slot_map + ((img * C + ch) * th + (ty < th ? ty : 0)) * tw;
+        int32_t slots[8];
+        if (vec_slots && G * 8 + 8 <= n_tx) {
+            const int4 s0 = __ldg(reinterpret_cast<const int4*>(smap) + G * 2), s1 = __ldg(reinterpret_cast<const int4*>(smap) + G * 2 + 1);
+            slots[0] = s0.x; slots[1] = s0.y; slots[2] = s0.z; slots[3] = s0.w;
+            slots[4] = s1.x; slots[5] = s1.y; slots[6] = s1.z; slots[7] = s1.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) slots[u] = G * 8 + u < n_tx ? __ldg(smap + G * 8 + u) : -1;
+        }
+        uint32_t words[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) words[u] = slots[u] >= 0 ? __ldg(codes32 + ((int64_t)slots[u] * q.c + py) * 2) : 0u;
         uint64_t s0 = 0, s1 = 0, sv = 0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int tx = G * 8 + u;
-            const int32_t slot = tx < n_tx ? __ldg(smap + tx) : -1;
-            if (slot >= 0) {
-                const uint32_t word = (uint32_t)__ldg(codes + (int64_t)slot * q.c + py);
-                const uint32_t r = __brev(word) >> (32 - p);                   // bit px of r = sign of column px
-                s0 |= (uint64_t)compress_even_bits16(r) << (HW * u);
-                s1 |= (uint64_t)compress_even_bits16(r >> 1) << (HW * u);
+            if (slots[u] >= 0) {
+                const uint32_t r = __brev(words[u]) >> (32 - p);                  // bit px of r = sign of column px
+                const uint32_t f = compress_even_bits2x16((r & 0xffffu) | ((r >> 1) << 16));   // even columns | odd columns << 16
+                s0 |= (uint64_t)(f & 0xffffu) << (HW * u);
+                s1 |= (uint64_t)(f >> 16) << (HW * u);
                 sv |= (uint64_t)((1u << HW) - 1u) << (HW * u);
             }
         }
@@ -1896,8 +1910,9 @@ extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, co
                                         const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
                                         const float* rs_h, void* work_hi, void* work_lo, float* maxabs,
                                         int32_t* code_grid, const float* median, const float* b, int H, int W,
-                                        float eps, float lo, float hi, int32_t* tame_scratch, int64_t n_planes, int h,
-                                        int w, int kh, int kw, int tile_p, int channels, void* stream) {
+                                        float eps, float lo, float hi, int32_t* tame_scratch, int tame_known,
+                                        int64_t n_planes, int h, int w, int kh, int kw, int tile_p, int channels,
+                                        void* stream) {
     DCTA_REQUIRE(xq_hi && xq_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && maxabs &&
                  code_grid && median && b && tame_scratch, "dct2_fwd_fold_codes: null pointer");
     DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_fwd_fold_codes: needs h, w multiples of 16 and even kh <= h, kw <= w");
@@ -1907,7 +1922,7 @@ extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, co
     if (n_planes == 0) return DCTA_OK;
     const int h2 = h / 2, w2 = w / 2;
     cudaStream_t st = as_stream(stream);
-    int rc = launch_b_tame(b, (int64_t)channels * H * W * tile_p * tile_p, tame_scratch, st);
+    int rc = tame_known ? DCTA_OK : launch_b_tame(b, (int64_t)channels * H * W * tile_p * tile_p, tame_scratch, st);
     if (rc) return rc;
     FoldOperand A1{(const __half*)xq_hi, (const __half*)xq_lo, w2, 2 * n_planes * (int64_t)h2 * w2};
     FoldOperand B1{(const __half*)bw_hi, (const __half*)bw_lo, w2, (int64_t)(kw / 2) * w2};
@@ -1975,11 +1990,32 @@ static void decode_inv_sizes(int64_t n_img, int C, int kh, int kw, int& n_iblk, 
     bv_bytes = (int64_t)4 * ((n_img + 3) / 4 * 4) * C * n_iblk * num_kb * 256;      // 32 rows x 4 chunks x 2 bytes per (i block, k block)
 }
 
+extern "C" int64_t dcta_decode_gen_tables_bytes(int channels_n, int kh, int kw) {
+    int n_iblk, num_kb;
+    int64_t tab_bytes, bv_bytes;
+    decode_inv_sizes(0, channels_n, kh, kw, n_iblk, num_kb, tab_bytes, bv_bytes);
+    return tab_bytes;
+}
+
 extern "C" int64_t dcta_decode_codes_inv_fold_scratch_bytes(int64_t n_img, int channels_n, int kh, int kw) {
     int n_iblk, num_kb;
     int64_t tab_bytes, bv_bytes;
     decode_inv_sizes(n_img, channels_n, kh, kw, n_iblk, num_kb, tab_bytes, bv_bytes);
-    return tab_bytes + bv_bytes;
+    return bv_bytes;
+}
+
+extern "C" int dcta_decode_gen_tables(const float* median, const float* b, int channels_n, int H, int W, float eps, int p,
+                                      int kh, int kw, float scale, void* tab, void* stream) {
+    DCTA_REQUIRE(median && b && tab, "decode_gen_tables: null pointer");
+    DCTA_REQUIRE(p >= 8 && p <= 16 && !(p & 1) && kh > 0 && kw > 0 && kh % p == 0 && kw % p == 0 && kh / p <= H && kw / p <= W,
+                 "decode_gen_tables: needs an even patch size in 8..16 and a token grid inside the PatchNorm tables");
+    int n_iblk, num_kb;
+    int64_t tab_bytes, bv_bytes;
+    decode_inv_sizes(0, channels_n, kh, kw, n_iblk, num_kb, tab_bytes, bv_bytes);
+    LfqNormParams q{median, b, channels_n, H, W, p * p, eps, 0.f, 0.f, p, p, scale};
+    decode_gen_tables_kernel<<<grid_for(tab_bytes / 4, 256), 256, 0, as_stream(stream)>>>(q, p, kh, kw, n_iblk, num_kb, kFScaleY,
+                                                                                          reinterpret_cast<uint32_t*>(tab));
+    return check_launch("decode_gen_tables");
 }
 
 extern "C" int dcta_decode_codes_inv_fold_supported(int h, int w, int kh, int kw, int p, int c, int d) {
@@ -1993,9 +2029,9 @@ extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* s
                                           const float* median, const float* b, int H, int W, float eps, int c, int d,
                                           float scale, const void* bwt_hi, const void* bwt_lo, const void* bht_hi,
                                           const void* bht_lo, void* work_hi, void* work_lo, float* z, float* dc,
-                                          void* scratch, void* stream) {
-    DCTA_REQUIRE(codes && slot_map && median && b && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && z && dc && scratch,
-                 "decode_codes_inv_fold: null pointer");
+                                          const void* tab_in, void* scratch, void* stream) {
+    DCTA_REQUIRE(codes && slot_map && median && b && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && z && dc &&
+                 tab_in && scratch, "decode_codes_inv_fold: null pointer");
     DCTA_REQUIRE(dcta_decode_codes_inv_fold_supported(h, w, kh, kw, p, c, d),
                  "decode_codes_inv_fold: needs one LFQ codebook per patch row (c == d == p in 8..16), h, w multiples of 16, even kh, kw");
     DCTA_REQUIRE(th <= H && tw <= W && kh / p <= H && kw / p <= W && n_img * channels_n < (1 << 24),
@@ -2007,10 +2043,9 @@ extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* s
     int n_iblk, num_kb;
     int64_t tab_bytes, bv_bytes;
     decode_inv_sizes(n_img, channels_n, kh, kw, n_iblk, num_kb, tab_bytes, bv_bytes);
-    uint32_t* tab = reinterpret_cast<uint32_t*>(scratch);
-    uint16_t* bv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(scratch) + tab_bytes);
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(tab_in);
+    uint16_t* bv = reinterpret_cast<uint16_t*>(scratch);
     LfqNormParams q{median, b, channels_n, H, W, p * p, eps, 0.f, 0.f, c, d, scale};
-    decode_gen_tables_kernel<<<grid_for(tab_bytes / 4, 256), 256, 0, as_stream(stream)>>>(q, p, kh, kw, n_iblk, num_kb, kFScaleY, tab);
     {
         const int n_grp = (int)ceil_div(kw / p, 8);
         DCTA_REQUIRE(n_iblk <= 65535, "decode_codes_inv_fold: plane too tall for the bit-plane kernel");
@@ -2031,7 +2066,7 @@ extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* s
         }
 #undef DCTA_BITPLANES
     }
-    int rc = check_launch("decode_codes_inv_fold (tables)");
+    int rc = check_launch("decode_codes_inv_fold (bit planes)");
     if (rc) return rc;
     // pass 1 with the generated operand: Q^T[b][a][plane][w'][i] = sum_j Y[2i+a, 2j+b] CW[2j+b, w']
     FoldGen gen{};

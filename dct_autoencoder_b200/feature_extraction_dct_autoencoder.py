@@ -650,8 +650,7 @@ class DCTAutoencoderFeatureExtractor:
                 st = _lib.stream_ptr(dev)
                 if (self.dct_impl == "tc" and C == 3 and codes is not None and self.decode_in_gemm and
                         decode_codes_inv_fold_ok(h, w, kh, kw, p, lfq.num_codebooks, lfq.codebook_dim)):
-                    z, dc = decode_codes_inv_fold(codes, slot_map, sel, n, C, th, tw, p, kh, kw, h, w, norm.median.data,
-                                                  norm.b.data, norm.max_patch_h, norm.max_patch_w, norm.eps,
+                    z, dc = decode_codes_inv_fold(codes, slot_map, sel, n, C, th, tw, p, kh, kw, h, w, norm,
                                                   lfq.num_codebooks, lfq.codebook_dim, lfq.codebook_scale)
                     yield idx, unfold_ipt_to_rgb(z, dc, h, w, out_dtype)
                     continue

@@ -49,6 +49,40 @@ class PatchNorm(nn.Module):
         self.min_val = min_val
         # sum the batch statistics over the default process group while fitting
         self.sync_stats = True
+        # quantities derived from (median, b) that the fused kernels reuse across calls (decode tables, the "every b is
+        # a tame divisor" flag): keyed by what they depend on, dropped whenever the statistics change
+        self._derived = {}
+        self._stats_version = 0
+        self._no_cache = False       # GraphedRoundtrip: derive inside the captured step, so that replays follow the tables
+
+    def invalidate_derived(self):
+        """Forget everything derived from the statistics.  Called by every path of this module that changes them
+        (statistic fitting, load_state_dict, .to()); call it yourself after writing ``median`` / ``b`` through
+        ``.data`` or a raw pointer, which leaves no trace the cache could see."""
+        self._derived.clear()
+        self._stats_version += 1
+
+    def derived(self, key, build):
+        """``build()`` once per ``key`` and state of the statistics (tensor identity and version counters)."""
+        if self._no_cache:
+            return build()
+        full = (key, self._stats_version, self.median.data_ptr(), self.b.data_ptr(), self.median._version, self.b._version)
+        hit = self._derived.get(full)
+        if hit is None:
+            if len(self._derived) > 16:
+                self._derived.clear()
+            hit = self._derived[full] = build()
+        return hit
+
+    def _apply(self, fn, *args, **kwargs):
+        self._derived.clear()
+        self._stats_version += 1
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._derived.clear()
+        self._stats_version += 1
+        return super()._load_from_state_dict(*args, **kwargs)
 
     @property
     def std(self) -> torch.Tensor:
@@ -118,6 +152,7 @@ class PatchNorm(nn.Module):
             _lib.call("dcta_patchnorm_update_b", _lib.ptr(b), _lib.ptr(n), _lib.ptr(packed), _lib.ptr(abs_dev),
                       n_pos, z, st)
             _lib.call("dcta_zero_padding", _lib.ptr(x), _lib.ptr(pad), _lib.ptr(out), n_tok, z, st)
+        self.invalidate_derived()
         return out if og == torch.float32 else out.to(og)
 
     # ------------------------------------------------------------------ public

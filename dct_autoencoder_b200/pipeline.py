@@ -209,6 +209,10 @@ class GraphedRoundtrip:
         # up and capturing, so that a later cache eviction cannot free memory the graph still reads.
         fe = pipe.extractor
         saved, fe._keepalive = fe._keepalive, []
+        norm = pipe.norm
+        saved_nc = getattr(norm, "_no_cache", False)
+        if hasattr(norm, "_no_cache"):
+            norm._no_cache = True       # what is derived from the statistics is recomputed inside the captured step
         try:
             with torch.cuda.stream(side):          # warm caches (tables, tensor maps, function attributes)
                 for _ in range(warmup):
@@ -221,6 +225,8 @@ class GraphedRoundtrip:
             self._tables = list(fe._keepalive)
         finally:
             fe._keepalive = saved
+            if hasattr(norm, "_no_cache"):
+                norm._no_cache = saved_nc
         self.launches = _lib.launch_count - l0     # kernels per replay
         self._lib = _lib
 

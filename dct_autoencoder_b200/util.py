@@ -631,13 +631,18 @@ def dct2_fwd_fold_codes(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: torch.Tens
     shape = (n_planes // channels, kh // tile_p, kw // tile_p, channels)
     maxabs = torch.empty(shape, dtype=torch.float32, device=dev)
     code_grid = torch.empty(shape + (tile_p,), dtype=torch.int32, device=dev)
-    tame = torch.empty(1, dtype=torch.int32, device=dev)
+    # the "every b is a tame divisor" flag depends on the statistics only: checked once per state of the tables
+    fresh = []
+    tame = norm.derived(("b_tame", str(dev)), lambda: fresh.append(1) or torch.empty(1, dtype=torch.int32, device=dev))
     with torch.cuda.device(dev):
         _lib.call("dcta_dct2_fwd_fold_codes", _lib.ptr(xq_hi), _lib.ptr(xq_lo), _lib.ptr(dc), _lib.ptr(bw_hi),
                   _lib.ptr(bw_lo), _lib.ptr(rs_w), _lib.ptr(bh_hi), _lib.ptr(bh_lo), _lib.ptr(rs_h), _lib.ptr(work_hi),
                   _lib.ptr(work_lo), _lib.ptr(maxabs), _lib.ptr(code_grid), _lib.ptr(norm.median.data),
                   _lib.ptr(norm.b.data), norm.max_patch_h, norm.max_patch_w, float(norm.eps), float(norm.min_val),
-                  float(norm.max_val), _lib.ptr(tame), n_planes, h, w, kh, kw, tile_p, channels, _lib.stream_ptr(dev))
+                  float(norm.max_val), _lib.ptr(tame), 0 if fresh else 1, n_planes, h, w, kh, kw, tile_p, channels,
+                  _lib.stream_ptr(dev))
+    if not fresh:
+        _lib.launch_count -= 1
     return maxabs, code_grid
 
 
@@ -664,12 +669,14 @@ def decode_codes_inv_fold_ok(h: int, w: int, kh: int, kw: int, p: int, c: int, d
 
 
 def decode_codes_inv_fold(codes, slot_map, sel, n_img: int, channels: int, th: int, tw: int, p: int, kh: int, kw: int,
-                          h: int, w: int, median, b, H: int, W: int, eps: float, c: int, d: int, scale: float):
+                          h: int, w: int, norm, c: int, d: int, scale: float):
     """LFQ codes -> quadrant transforms z (4, n_img*channels, h/2, w/2) + dc (n_img*channels): de-quantisation,
     inverse PatchNorm and un-patchify (lfq.py:105-134, patchnorm.py:167-177, FE:607-656) happen in the operand
-    producer of inverse pass 1 (``dcta_decode_codes_inv_fold``); the coefficient planes are never written."""
+    producer of inverse pass 1 (``dcta_decode_codes_inv_fold``); the coefficient planes are never written.
+    The two-value table is a function of the PatchNorm statistics: built once per state of ``norm``."""
     dev = codes.device
     n_planes = n_img * channels
+    lib = _lib.load()
     bwt_hi, bwt_lo, _ = fold_basis(w, kw, dev, True)
     bht_hi, bht_lo, _ = fold_basis(h, kh, dev, True)
     ldi = _round8(kh // 2)
@@ -677,13 +684,23 @@ def decode_codes_inv_fold(codes, slot_map, sel, n_img: int, channels: int, th: i
     work_lo = torch.empty_like(work_hi)
     z = torch.empty((4, n_planes, h // 2, w // 2), dtype=torch.float32, device=dev)
     dc = torch.empty(n_planes, dtype=torch.float32, device=dev)
-    scratch = torch.empty(_lib.load().dcta_decode_codes_inv_fold_scratch_bytes(n_img, channels, kh, kw), dtype=torch.uint8,
-                          device=dev)
+    scratch = torch.empty(lib.dcta_decode_codes_inv_fold_scratch_bytes(n_img, channels, kh, kw), dtype=torch.uint8, device=dev)
+    median, b = norm.median.data, norm.b.data
+    H, W, eps = norm.max_patch_h, norm.max_patch_w, float(norm.eps)
+
+    def build_table():
+        tab = torch.empty(lib.dcta_decode_gen_tables_bytes(channels, kh, kw), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("dcta_decode_gen_tables", _lib.ptr(median), _lib.ptr(b), channels, H, W, eps, p, kh, kw, float(scale),
+                      _lib.ptr(tab), _lib.stream_ptr(dev))
+        return tab
+
+    tab = norm.derived(("decode_tab", str(dev), channels, p, kh, kw, float(scale)), build_table)
     with torch.cuda.device(dev):
         _lib.call("dcta_decode_codes_inv_fold", _lib.ptr(codes), _lib.ptr(slot_map), _lib.ptr(sel), n_img, channels, th, tw,
-                  p, kh, kw, h, w, _lib.ptr(median), _lib.ptr(b), H, W, float(eps), c, d, float(scale), _lib.ptr(bwt_hi),
+                  p, kh, kw, h, w, _lib.ptr(median), _lib.ptr(b), H, W, eps, c, d, float(scale), _lib.ptr(bwt_hi),
                   _lib.ptr(bwt_lo), _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z),
-                  _lib.ptr(dc), _lib.ptr(scratch), _lib.stream_ptr(dev))
+                  _lib.ptr(dc), _lib.ptr(tab), _lib.ptr(scratch), _lib.stream_ptr(dev))
     return z, dc
 
 

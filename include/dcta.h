@@ -32,6 +32,12 @@ extern "C" {
 #define DCTA_ERR_UNSUPPORTED (-3)
 
 const char* dcta_last_error(void);
+/* Device time of every launch group between the two calls, measured with CUDA events recorded on the launching
+ * stream after each group (no profiler, no synchronisation until dcta_profile_end).  One thread at a time.
+ *   dcta_profile_end: names_out receives the group names joined by '\n' (NUL-terminated, at most names_cap bytes),
+ *   ms_out up to max_n durations in launch order; returns the number of groups. */
+int dcta_profile_begin(void* stream);
+int dcta_profile_end(char* names_out, int names_cap, float* ms_out, int max_n);
 /* ABI version of this header; bumped on any signature change. */
 int dcta_abi_version(void);
 /* Compute capability the library was compiled for (100 for sm_100a). */
@@ -180,14 +186,15 @@ int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, co
  * clamp((Y - median) / (b*sqrt2 + eps)) (PN:157-165, LFQ:175-187) of every coefficient and never writes the token grid.
  *   code_grid (n_planes/channels, kh/p, kw/p, channels, p) int32: code word of patch row r of every token, in
  *   token-grid order (dcta_pack_codes_grid gathers them into sorted, packed order);  maxabs as above;
- *   median, b (channels, H, W, p*p);  tame_scratch: one device int32. */
+ *   median, b (channels, H, W, p*p);  tame_scratch: one device int32 (the "every b is a tame divisor" flag);
+ *   tame_known != 0: tame_scratch already holds the flag of these tables (set by an earlier call), skip the check. */
 int dcta_fold_codes_supported(int h, int w, int kh, int kw, int tile_p);   /* 1 if the next entry point takes these sizes */
 int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
                              const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
                              const float* rs_h, void* work_hi, void* work_lo, float* maxabs, int32_t* code_grid,
                              const float* median, const float* b, int H, int W, float eps, float lo, float hi,
-                             int32_t* tame_scratch, int64_t n_planes, int h, int w, int kh, int kw, int tile_p,
-                             int channels, void* stream);
+                             int32_t* tame_scratch, int tame_known, int64_t n_planes, int h, int w, int kh, int kw,
+                             int tile_p, int channels, void* stream);
 /* FE:635-653 un-patchify into folded coefficient quadrants yq_hi/lo (2, 2, n_img*channels, rows/2, ldq)
  * [b][a][plane][i][j] = Y[2i+a, 2j+b] * 2^4, ldq = round8(cols/2); DC moved to dc as in dcta_unpatchify_split. */
 int dcta_unpatchify_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
@@ -201,12 +208,17 @@ int dcta_decode_codes_fold(const int64_t* codes, const int32_t* slot_map, const 
                            int out_w, const float* median, const float* b, int H, int W, float eps, int c,
                            int d, float scale, void* yq_hi, void* yq_lo, float* dc, void* tab_scratch, void* stream);
 /* Decode from LFQ codes INSIDE inverse pass 1 (FE:607-656 revert_patching + PN:167-177 inverse_norm + LFQ:105-134
- * indices_to_codes + the inverse DCT of FE:289-310 in three launches + the table kernel): the data operand of pass 1 is
- * generated in shared memory from one sign bit per coefficient and a table of the two values a de-quantised,
- * de-normalised coefficient can take, so the coefficient planes are never written.  Needs one codebook per patch row
- * (c == d == p, 8 <= p <= 16).  Arguments as dcta_decode_codes_fold + dcta_dct2_inv_fold (kh = rows, kw = cols);
- *   scratch: dcta_decode_codes_inv_fold_scratch_bytes(...) bytes, 256-byte aligned.
+ * indices_to_codes + the inverse DCT of FE:289-310): the data operand of pass 1 is generated in shared memory from one
+ * sign bit per coefficient and a table of the two values a de-quantised, de-normalised coefficient can take, so the
+ * coefficient planes are never written.  Needs one codebook per patch row (c == d == p, p even in 8..16).
+ *   dcta_decode_gen_tables: the two-value table of (median, b, eps, scale) for kh x kw coefficients,
+ *     dcta_decode_gen_tables_bytes(...) bytes; depends on the PatchNorm tables only, so it can be kept across calls.
+ *   dcta_decode_codes_inv_fold: arguments as dcta_decode_codes_fold + dcta_dct2_inv_fold (kh = rows, kw = cols);
+ *     tab: that table;  scratch: dcta_decode_codes_inv_fold_scratch_bytes(...) bytes, 256-byte aligned.
  * Results are bit-identical to dcta_decode_codes_fold followed by dcta_dct2_inv_fold. */
+int64_t dcta_decode_gen_tables_bytes(int channels_n, int kh, int kw);
+int dcta_decode_gen_tables(const float* median, const float* b, int channels_n, int H, int W, float eps, int p,
+                           int kh, int kw, float scale, void* tab, void* stream);
 int64_t dcta_decode_codes_inv_fold_scratch_bytes(int64_t n_img, int channels_n, int kh, int kw);
 int dcta_decode_codes_inv_fold_supported(int h, int w, int kh, int kw, int p, int c, int d);
 int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
@@ -214,7 +226,7 @@ int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* slot_map, co
                                const float* median, const float* b, int H, int W, float eps, int c, int d,
                                float scale, const void* bwt_hi, const void* bwt_lo, const void* bht_hi,
                                const void* bht_lo, void* work_hi, void* work_lo, float* z, float* dc,
-                               void* scratch, void* stream);
+                               const void* tab, void* scratch, void* stream);
 /* fp32 coefficient planes y (n_planes, kh, kw) -> folded quadrants. */
 int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, float* dc, int64_t n_planes, int kh,
                           int kw, int out_h, int out_w, void* stream);
