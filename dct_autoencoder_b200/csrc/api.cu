@@ -55,8 +55,8 @@ extern "C" int64_t dcta_basis_elems(int layout, int n, int k) {
         case DCTA_BASIS_F32: return (int64_t)k * n;
         case DCTA_BASIS_SPLIT_FWD: return (int64_t)k * round8(n);
         case DCTA_BASIS_SPLIT_INV: return (int64_t)n * round8(k);
-        case DCTA_BASIS_FOLD_FWD: return 2ll * (k / 2) * (n / 2);
-        case DCTA_BASIS_FOLD_INV: return 2ll * (n / 2) * round8(k / 2);
+        case DCTA_BASIS_FOLD_FWD: return 2ll * (k / 2) * round8((n + 1) / 2);
+        case DCTA_BASIS_FOLD_INV: return 2ll * ((n + 1) / 2) * round8(k / 2);
     }
     return -1;
 }
@@ -93,27 +93,34 @@ extern "C" int dcta_basis_init(int layout, int n, int k, void* hi_host, void* lo
                 for (int q = 0; q < k; ++q) split_store(basis_at(n, q, m) * kBasisScale, hi, lo, m * ld + q);
             return DCTA_OK;
         }
-        case DCTA_BASIS_FOLD_FWD: {           // (2, k/2, n/2): group g = rows of parity g, first half of the samples
+        case DCTA_BASIS_FOLD_FWD: {           // (2, k/2, round8(ceil(n/2))): group g = rows of parity g, first half of the
+            // samples (for odd n including the middle one, which pairs with itself: its odd rows are zero)
             DCTA_REQUIRE(row_scale_host != nullptr, "basis_init: forward layouts need row_scale");
-            DCTA_REQUIRE(n % 2 == 0 && k % 2 == 0, "basis_init: the folded layouts need even n and k");
-            const int k2 = k / 2, n2 = n / 2;
+            DCTA_REQUIRE(k % 2 == 0, "basis_init: the folded layouts need an even k");
+            const int k2 = k / 2, n2 = (n + 1) / 2;
+            const int64_t ldn = round8(n2);
             for (int g = 0; g < 2; ++g)
                 for (int j = 0; j < k2; ++j) {
                     const int q = 2 * j + g;
-                    for (int m = 0; m < n2; ++m)
-                        split_store(q == 0 ? 32.0 : basis_at(n, q, m) * kBasisScale, hi, lo, ((int64_t)g * k2 + j) * n2 + m);
+                    for (int m = 0; m < n2; ++m) {
+                        const bool zero = (n & 1) && (q & 1) && m == n2 - 1;      // cos(pi q / 2) of an odd q
+                        split_store(q == 0 ? 32.0 : (zero ? 0.0 : basis_at(n, q, m) * kBasisScale), hi, lo,
+                                    ((int64_t)g * k2 + j) * ldn + m);
+                    }
                     row_scale_host[g * k2 + j] = (float)(q == 0 ? sqrt(1.0 / n) / 32.0 : 1.0 / kBasisScale);
                 }
             return DCTA_OK;
         }
-        case DCTA_BASIS_FOLD_INV: {           // (2, n/2, round8(k/2)): the transposes
-            DCTA_REQUIRE(n % 2 == 0 && k % 2 == 0, "basis_init: the folded layouts need even n and k");
-            const int k2 = k / 2, n2 = n / 2;
+        case DCTA_BASIS_FOLD_INV: {           // (2, ceil(n/2), round8(k/2)): the transposes
+            DCTA_REQUIRE(k % 2 == 0, "basis_init: the folded layouts need an even k");
+            const int k2 = k / 2, n2 = (n + 1) / 2;
             const int64_t ld = round8(k2);
             for (int g = 0; g < 2; ++g)
                 for (int m = 0; m < n2; ++m)
-                    for (int j = 0; j < k2; ++j)
-                        split_store(basis_at(n, 2 * j + g, m) * kBasisScale, hi, lo, ((int64_t)g * n2 + m) * ld + j);
+                    for (int j = 0; j < k2; ++j) {
+                        const bool zero = (n & 1) && g == 1 && m == n2 - 1;
+                        split_store(zero ? 0.0 : basis_at(n, 2 * j + g, m) * kBasisScale, hi, lo, ((int64_t)g * n2 + m) * ld + j);
+                    }
             return DCTA_OK;
         }
     }

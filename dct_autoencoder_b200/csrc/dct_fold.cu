@@ -1613,6 +1613,137 @@ __global__ void __launch_bounds__(256, 3) decode_codes_rows_kernel(const int64_t
     }
 }
 
+// ------------------------------------------------------------------------------ any plane size (scalar variants)
+// One thread = one quadrant position (item, h', w') with h' < ceil(h/2), w' < ceil(w/2): the four mirrored samples of
+// each channel, the self-paired middle row / column of odd sizes counted once.  Quadrant rows have pitch `ld`.
+__device__ __forceinline__ float px_load(const float* p, int64_t i) { return __ldg(p + i); }
+__device__ __forceinline__ float px_load(const uint8_t* p, int64_t i) { return u8_to_unit(__ldg(p + i)); }
+__device__ __forceinline__ void px_store(float* p, int64_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void px_store(uint8_t* p, int64_t i, float v) { p[i] = (uint8_t)unit_to_u8(v); }
+
+template <typename TIn, bool COLOR>
+__global__ void __launch_bounds__(256) means_any_kernel(const TIn* __restrict__ x, float* __restrict__ mu, float* __restrict__ dc,
+                                                        int64_t plane, Mat3 A, Mat3 B, float dc_factor) {
+    constexpr int CH = COLOR ? 3 : 1;
+    __shared__ float red[3][8];
+    const int64_t item = blockIdx.x;
+    const TIn* src = x + item * CH * plane;
+    const int64_t step = plane > 8192 ? plane / 8192 : 1;       // any estimate is exact: what is removed is added back as DC
+    const int64_t count = (plane + step - 1) / step;
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int64_t k = threadIdx.x; k < count; k += blockDim.x) {
+        const int64_t i = k * step;
+        if (COLOR) {
+            float o0, o1, o2;
+            rgb_px_to_ipt_f(px_load(src, i), px_load(src, plane + i), px_load(src, 2 * plane + i), A, B, o0, o1, o2);
+            s[0] += o0; s[1] += o1; s[2] += o2;
+        } else {
+            s[0] += px_load(src, i);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const float v = warp_sum(s[c]);
+        if (lane == 0) red[c][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < CH) {
+        float t = 0.f;
+        for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+        const float m = t / (float)count;
+        mu[item * CH + threadIdx.x] = m;
+        dc[item * CH + threadIdx.x] = m * dc_factor;
+    }
+}
+
+template <typename TIn, bool COLOR>
+__global__ void __launch_bounds__(256) fold_any_kernel(const TIn* __restrict__ x, const float* __restrict__ mus,
+                                                       __half* __restrict__ hi, __half* __restrict__ lo, int64_t n_items, int h,
+                                                       int w, int ld, Mat3 A, Mat3 B, float scale) {
+    constexpr int CH = COLOR ? 3 : 1;
+    const int h2 = (h + 1) >> 1, w2 = (w + 1) >> 1;
+    const int64_t plane = (int64_t)h * w, n_planes = n_items * CH, quad = n_planes * h2 * (int64_t)ld;
+    const int64_t total = n_items * h2 * w2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xv = (int)(i % w2);
+        const int64_t t = i / w2;
+        const int y = (int)(t % h2);
+        const int64_t item = t / h2;
+        const TIn* src = x + item * CH * plane;
+        const int xr = w - 1 - xv, yb = h - 1 - y;
+        const bool self_col = xr == xv, self_row = yb == y;
+        const int64_t o[4] = {(int64_t)y * w + xv, (int64_t)y * w + xr, (int64_t)yb * w + xv, (int64_t)yb * w + xr};
+        float v[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (COLOR) rgb_px_to_ipt_f(px_load(src, o[k]), px_load(src, plane + o[k]), px_load(src, 2 * plane + o[k]), A, B,
+                                       v[k][0], v[k][1], v[k][2]);
+            else v[k][0] = px_load(src, o[k]);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const float mu = __ldg(mus + item * CH + c);
+            const float p1 = v[0][c] - mu, p2 = v[1][c] - mu, p3 = v[2][c] - mu, p4 = v[3][c] - mu;
+            const float s_top = self_col ? p1 : p1 + p2, d_top = self_col ? 0.f : p1 - p2;
+            const float s_bot = self_col ? p3 : p3 + p4, d_bot = self_col ? 0.f : p3 - p4;
+            const float q[4] = {self_row ? s_top : s_top + s_bot, self_row ? 0.f : s_top - s_bot,
+                                self_row ? d_top : d_top + d_bot, self_row ? 0.f : d_top - d_bot};   // [b*2 + a]
+            const int64_t oq = ((item * CH + c) * h2 + y) * (int64_t)ld + xv;
+#pragma unroll
+            for (int sI = 0; sI < 4; ++sI) {
+                const float sv = q[sI] * scale;
+                const __half hh = __float2half_rn(sv);
+                hi[sI * quad + oq] = hh;
+                lo[sI * quad + oq] = __float2half_rn(sv - __half2float(hh));
+            }
+        }
+    }
+}
+
+// z[s][plane][h'][w'] (dense, ceil(h/2) x ceil(w/2)) -> pixels
+template <bool COLOR, typename TOut>
+__global__ void __launch_bounds__(256) unfold_any_kernel(const float* __restrict__ z, const float* __restrict__ dc,
+                                                         TOut* __restrict__ out, int64_t n_items, int h, int w, Mat3 A, Mat3 B) {
+    constexpr int CH = COLOR ? 3 : 1;
+    const int h2 = (h + 1) >> 1, w2 = (w + 1) >> 1;
+    const int64_t plane = (int64_t)h * w, n_planes = n_items * CH, quad = n_planes * h2 * (int64_t)w2;
+    const int64_t total = n_items * h2 * w2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int xv = (int)(i % w2);
+        const int64_t t = i / w2;
+        const int y = (int)(t % h2);
+        const int64_t item = t / h2;
+        const int xr = w - 1 - xv, yb = h - 1 - y;
+        const bool self_col = xr == xv, self_row = yb == y;
+        float px[4][3];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int64_t oq = ((item * CH + c) * h2 + y) * (int64_t)w2 + xv;
+            float zz[4] = {z[oq], z[quad + oq], z[2 * quad + oq], z[3 * quad + oq]};       // [b*2 + a]
+            if (self_row) { zz[1] = 0.f; zz[3] = 0.f; }
+            if (self_col) { zz[2] = 0.f; zz[3] = 0.f; }
+            unbutterfly4(zz, dc ? __ldg(dc + item * CH + c) : 0.f, px[0][c], px[1][c], px[2][c], px[3][c]);
+        }
+        const int64_t o[4] = {(int64_t)y * w + xv, (int64_t)y * w + xr, (int64_t)yb * w + xv, (int64_t)yb * w + xr};
+        const bool wr[4] = {true, !self_col, !self_row, !self_col && !self_row};
+        TOut* dst = out + item * CH * plane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!wr[k]) continue;
+            if (COLOR) {
+                float r, g, b;
+                ipt_px_to_rgb_f(px[k][0], px[k][1], px[k][2], A, B, r, g, b);
+                px_store(dst, o[k], r);
+                px_store(dst, plane + o[k], g);
+                px_store(dst, 2 * plane + o[k], b);
+            } else {
+                px_store(dst, o[k], px[k][0]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ decode inside inverse pass 1 (GEN)
 // The two-value tables of decode_tables_kernel in the order the producer warps of fold_gemm_kernel<0, true> read them:
 // one 8 KB block per (b, a, channel, 32-row block of i, 32-column block of j) = [4 parts][128 threads pt = il*4 + c] uint4;
@@ -1791,65 +1922,84 @@ using namespace dcta;
 // quadrants carry 2^6 where the plain path carries 2^8, and the forward intermediate 2^5 instead of 2^6.
 static const float kFScaleX = 64.f, kFScaleP = 32.f, kFScaleY = 16.f, kFScaleQ = 64.f, kFScaleBasis = 1024.f;
 
+// Any plane size: a quadrant holds ceil(n / 2) samples per axis (for odd n the middle sample pairs with itself: it
+// enters the even rows once and the odd rows not at all, C[odd k, middle] = 0); rows are stored with an 8-element pitch.
 static bool fold_dims_ok(int h, int w, int kh, int kw) {
-    return h > 0 && w > 0 && h % 16 == 0 && w % 16 == 0 && kh > 0 && kw > 0 && kh % 2 == 0 && kw % 2 == 0 && kh <= h && kw <= w;
+    return h >= 2 && w >= 2 && kh > 0 && kw > 0 && kh % 2 == 0 && kw % 2 == 0 && kh <= h && kw <= w;
 }
+static inline int fold_half(int n) { return (n + 1) / 2; }
+static inline int fold_pitch(int n) { return (int)(ceil_div(fold_half(n), 8) * 8); }
+static inline bool fold_fast_dims(int h, int w) { return h % 16 == 0 && w % 16 == 0; }     // the vectorised colour kernels
 
 extern "C" int dcta_fold_supported(int h, int w, int kh, int kw) {
     if (!fold_dims_ok(h, w, kh, kw)) return 0;
     FoldGemm g{};
-    return fold_geometry(kw / 2, w / 2, g) && fold_geometry(kh / 2, h / 2, g, 64) && fold_geometry(w / 2, kw / 2, g) &&
-           fold_geometry(h / 2, kh / 2, g);
+    return fold_geometry(kw / 2, fold_half(w), g) && fold_geometry(kh / 2, fold_half(h), g, 64) &&
+           fold_geometry(fold_half(w), kw / 2, g) && fold_geometry(fold_half(h), kh / 2, g);
+}
+
+template <typename TIn>
+static int rgb_to_ipt_fold_any(const TIn* rgb, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch, int64_t n_img, int h,
+                               int w, const float* m_rgb2lms_host, const float* m_ipt_host, void* stream, const char* who) {
+    DCTA_REQUIRE(rgb && xq_hi && xq_lo && dc && sums_scratch && m_rgb2lms_host && m_ipt_host, "%s: null pointer", who);
+    DCTA_REQUIRE(h >= 2 && w >= 2 && n_img <= 65535, "%s: needs h, w >= 2 and at most 65535 images", who);
+    if (n_img == 0) return DCTA_OK;
+    Mat3 A, B;
+    for (int i = 0; i < 9; ++i) { A.m[i] = m_rgb2lms_host[i]; B.m[i] = m_ipt_host[i]; }
+    cudaStream_t st = as_stream(stream);
+    if (fold_fast_dims(h, w) && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0) {
+        const float* mus;
+        if constexpr (sizeof(TIn) == 1) mus = launch_ipt_plane_means_u8(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
+        else mus = launch_ipt_plane_means(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
+        rgb_to_ipt_fold_kernel<TIn><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, st>>>(
+            rgb, mus, (__half*)xq_hi, (__half*)xq_lo, n_img, h, w, A, B, kFScaleX);
+    } else {            // any size: scalar kernels, quadrant rows padded to 8 elements
+        float* mus = sums_scratch;
+        means_any_kernel<TIn, true><<<(unsigned)n_img, 256, 0, st>>>(rgb, mus, dc, (int64_t)h * w, A, B, sqrtf((float)h * (float)w));
+        fold_any_kernel<TIn, true><<<grid_for(n_img * fold_half(h) * fold_half(w), 256), 256, 0, st>>>(
+            rgb, mus, (__half*)xq_hi, (__half*)xq_lo, n_img, h, w, fold_pitch(w), A, B, kFScaleX);
+    }
+    return check_launch(who);
 }
 
 extern "C" int dcta_rgb_to_ipt_fold(const float* rgb, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
                                     int64_t n_img, int h, int w, const float* m_rgb2lms_host, const float* m_ipt_host,
                                     void* stream) {
-    DCTA_REQUIRE(rgb && xq_hi && xq_lo && dc && sums_scratch && m_rgb2lms_host && m_ipt_host, "rgb_to_ipt_fold: null pointer");
-    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 && n_img <= 65535,
-                 "rgb_to_ipt_fold: needs h, w multiples of 16, aligned input, at most 65535 images");
-    if (n_img == 0) return DCTA_OK;
-    Mat3 A, B;
-    for (int i = 0; i < 9; ++i) { A.m[i] = m_rgb2lms_host[i]; B.m[i] = m_ipt_host[i]; }
-    cudaStream_t st = as_stream(stream);
-    const float* mus = launch_ipt_plane_means(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
-    rgb_to_ipt_fold_kernel<float><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, st>>>(
-        rgb, mus, (__half*)xq_hi, (__half*)xq_lo, n_img, h, w, A, B, kFScaleX);
-    return check_launch("rgb_to_ipt_fold");
+    return rgb_to_ipt_fold_any(rgb, xq_hi, xq_lo, dc, sums_scratch, n_img, h, w, m_rgb2lms_host, m_ipt_host, stream,
+                               "rgb_to_ipt_fold");
 }
 
 extern "C" int dcta_rgb_u8_to_ipt_fold(const uint8_t* rgb, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
                                        int64_t n_img, int h, int w, const float* m_rgb2lms_host, const float* m_ipt_host,
                                        void* stream) {
-    DCTA_REQUIRE(rgb && xq_hi && xq_lo && dc && sums_scratch && m_rgb2lms_host && m_ipt_host, "rgb_u8_to_ipt_fold: null pointer");
-    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 3) == 0 && n_img <= 65535,
-                 "rgb_u8_to_ipt_fold: needs h, w multiples of 16, 4-byte aligned input, at most 65535 images");
-    if (n_img == 0) return DCTA_OK;
-    Mat3 A, B;
-    for (int i = 0; i < 9; ++i) { A.m[i] = m_rgb2lms_host[i]; B.m[i] = m_ipt_host[i]; }
-    cudaStream_t st = as_stream(stream);
-    const float* mus = launch_ipt_plane_means_u8(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
-    rgb_to_ipt_fold_kernel<uint8_t><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, st>>>(
-        rgb, mus, (__half*)xq_hi, (__half*)xq_lo, n_img, h, w, A, B, kFScaleX);
-    return check_launch("rgb_u8_to_ipt_fold");
+    return rgb_to_ipt_fold_any(rgb, xq_hi, xq_lo, dc, sums_scratch, n_img, h, w, m_rgb2lms_host, m_ipt_host, stream,
+                               "rgb_u8_to_ipt_fold");
 }
 
 extern "C" int dcta_fold_planes(const float* x, void* xq_hi, void* xq_lo, float* dc, float* sums_scratch,
                                 int64_t n_planes, int h, int w, void* stream) {
     DCTA_REQUIRE(x && xq_hi && xq_lo && dc && sums_scratch, "fold_planes: null pointer");
-    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && n_planes <= 65535,
-                 "fold_planes: needs h, w multiples of 16, aligned input, at most 65535 planes");
+    DCTA_REQUIRE(h >= 2 && w >= 2 && n_planes <= 65535 * 3, "fold_planes: needs h, w >= 2");
     if (n_planes == 0) return DCTA_OK;
     cudaStream_t st = as_stream(stream);
-    const float* mus = launch_plane_means(x, sums_scratch, dc, n_planes, h, w, st);
-    fold_planes_kernel<<<grid_for(n_planes * (h / 2) * (w / 8), 256), 256, 0, st>>>(
-        x, mus, (__half*)xq_hi, (__half*)xq_lo, n_planes, h, w, kFScaleX);
+    Mat3 A{}, B{};
+    if (fold_fast_dims(h, w) && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const float* mus = launch_plane_means(x, sums_scratch, dc, n_planes, h, w, st);
+        fold_planes_kernel<<<grid_for(n_planes * (h / 2) * (w / 8), 256), 256, 0, st>>>(x, mus, (__half*)xq_hi, (__half*)xq_lo,
+                                                                                      n_planes, h, w, kFScaleX);
+    } else {
+        float* mus = sums_scratch;
+        means_any_kernel<float, false><<<(unsigned)n_planes, 256, 0, st>>>(x, mus, dc, (int64_t)h * w, A, B, sqrtf((float)h * (float)w));
+        fold_any_kernel<float, false><<<grid_for(n_planes * fold_half(h) * fold_half(w), 256), 256, 0, st>>>(
+            x, mus, (__half*)xq_hi, (__half*)xq_lo, n_planes, h, w, fold_pitch(w), A, B, kFScaleX);
+    }
     return check_launch("fold_planes");
 }
 
-// forward: xq[b][a][plane][h/2][w/2] (scale 2^6) + removed DC -> token grid (tile_p > 0) or planes (n_planes, kh, kw)
-//   bw: (2, kw/2, w/2) folded basis of the width transform, group = column parity b; rs_w (2, kw/2) its row factors
-//   bh: (2, kh/2, h/2) for the height transform, group = row parity a; work: (2, n_planes, kw, h/2) hi/lo
+// forward: xq[b][a][plane][H2][ldw] (scale 2^6; H2 = ceil(h/2), W2 = ceil(w/2), ldw = round8(W2)) + removed DC
+//   -> token grid (tile_p > 0) or planes (n_planes, kh, kw)
+//   bw: (2, kw/2, ldw) folded basis of the width transform, group = column parity b; rs_w (2, kw/2) its row factors
+//   bh: (2, kh/2, ldh) for the height transform, group = row parity a; work: (2, n_planes, kw, ldh) hi/lo
 extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const float* dc, const void* bw_hi,
                                   const void* bw_lo, const float* rs_w, const void* bh_hi, const void* bh_lo,
                                   const float* rs_h, void* work_hi, void* work_lo, float* y, float* maxabs,
@@ -1858,23 +2008,23 @@ extern "C" int dcta_dct2_fwd_fold(const void* xq_hi, const void* xq_lo, const fl
     DCTA_REQUIRE(xq_hi && xq_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && y,
                  "dct2_fwd_fold: null pointer");
     DCTA_REQUIRE(maxabs == nullptr || tile_p > 0, "dct2_fwd_fold: maxabs needs the token-grid output");
-    DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_fwd_fold: needs h, w multiples of 16 and even kh <= h, kw <= w");
+    DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_fwd_fold: needs h, w >= 2 and even kh <= h, kw <= w");
     if (tile_p > 0)
         DCTA_REQUIRE(channels > 0 && kh % tile_p == 0 && kw % tile_p == 0 && n_planes % channels == 0,
                      "dct2_fwd_fold: kh/kw must be multiples of the patch size");
     if (n_planes == 0) return DCTA_OK;
-    const int h2 = h / 2, w2 = w / 2;
+    const int h2 = fold_half(h), w2 = fold_half(w), ldw = fold_pitch(w), ldh = fold_pitch(h);
     // pass 1: P[(a, plane, h'), j] = sum_w' xq[b][a][plane][h', w'] CW[2j+b, w'], stored as P^T[a][plane][kw = 2j+b][h']
-    FoldOperand A1{(const __half*)xq_hi, (const __half*)xq_lo, w2, 2 * n_planes * (int64_t)h2 * w2};
-    FoldOperand B1{(const __half*)bw_hi, (const __half*)bw_lo, w2, (int64_t)(kw / 2) * w2};
+    FoldOperand A1{(const __half*)xq_hi, (const __half*)xq_lo, ldw, 2 * n_planes * (int64_t)h2 * ldw};
+    FoldOperand B1{(const __half*)bw_hi, (const __half*)bw_lo, ldw, (int64_t)(kw / 2) * ldw};
     FoldEpi e1{};
     e1.mode = 0; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
-    e1.rows_per_item = h2; e1.seg_stride = 0; e1.item_stride = (int64_t)kw * h2;
-    e1.col_mul = 2; e1.col_add = 1; e1.col_stride = h2;
+    e1.rows_per_item = h2; e1.seg_stride = 0; e1.item_stride = (int64_t)kw * ldh;
+    e1.col_mul = 2; e1.col_add = 1; e1.col_stride = ldh;
     e1.alpha = kFScaleP / kFScaleX; e1.basis_scale = rs_w;
     // pass 2: Y[2i+a, kw] = sum_h' CH[2i+a, h'] P^T[a][plane][kw][h']   (+ the removed constant's DC at [0,0])
-    FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, h2, n_planes * (int64_t)kw * h2};
-    FoldOperand B2{(const __half*)bh_hi, (const __half*)bh_lo, h2, (int64_t)(kh / 2) * h2};
+    FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, ldh, n_planes * (int64_t)kw * ldh};
+    FoldOperand B2{(const __half*)bh_hi, (const __half*)bh_lo, ldh, (int64_t)(kh / 2) * ldh};
     FoldEpi e2{};
     e2.out_f32 = y; e2.rows_per_item = kw; e2.col_mul = 2; e2.col_add = 1;
     e2.alpha = 1.0f / kFScaleP; e2.basis_scale = rs_h; e2.dc = dc;
@@ -1915,28 +2065,28 @@ extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, co
                                         void* stream) {
     DCTA_REQUIRE(xq_hi && xq_lo && bw_hi && bw_lo && rs_w && bh_hi && bh_lo && rs_h && work_hi && work_lo && maxabs &&
                  code_grid && median && b && tame_scratch, "dct2_fwd_fold_codes: null pointer");
-    DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_fwd_fold_codes: needs h, w multiples of 16 and even kh <= h, kw <= w");
+    DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_fwd_fold_codes: needs h, w >= 2 and even kh <= h, kw <= w");
     DCTA_REQUIRE(dcta_fold_codes_supported(h, w, kh, kw, tile_p), "dct2_fwd_fold_codes: geometry not supported");
     DCTA_REQUIRE(channels > 0 && n_planes % channels == 0 && kh / tile_p <= H && kw / tile_p <= W,
                  "dct2_fwd_fold_codes: needs a token grid inside the PatchNorm tables");
     if (n_planes == 0) return DCTA_OK;
-    const int h2 = h / 2, w2 = w / 2;
+    const int h2 = fold_half(h), w2 = fold_half(w), ldw = fold_pitch(w), ldh = fold_pitch(h);
     cudaStream_t st = as_stream(stream);
     int rc = tame_known ? DCTA_OK : launch_b_tame(b, (int64_t)channels * H * W * tile_p * tile_p, tame_scratch, st);
     if (rc) return rc;
-    FoldOperand A1{(const __half*)xq_hi, (const __half*)xq_lo, w2, 2 * n_planes * (int64_t)h2 * w2};
-    FoldOperand B1{(const __half*)bw_hi, (const __half*)bw_lo, w2, (int64_t)(kw / 2) * w2};
+    FoldOperand A1{(const __half*)xq_hi, (const __half*)xq_lo, ldw, 2 * n_planes * (int64_t)h2 * ldw};
+    FoldOperand B1{(const __half*)bw_hi, (const __half*)bw_lo, ldw, (int64_t)(kw / 2) * ldw};
     FoldEpi e1{};
     // pass 1 writes P^T with its lines regrouped as [a][channel][token column][image][pj]: the 16 token columns of a
     // fold_codes_kernel tile are then 16 images at the SAME (channel, tw), i.e. they share their PatchNorm medians
     e1.mode = 3; e1.out_hi = (__half*)work_hi; e1.out_lo = (__half*)work_lo;
-    e1.rows_per_item = h2; e1.col_mul = 2; e1.col_add = 1; e1.col_stride = h2;
+    e1.rows_per_item = h2; e1.col_mul = 2; e1.col_add = 1; e1.col_stride = ldh;
     e1.p = tile_p; e1.channels = channels; e1.tiles_w = kw / tile_p; e1.batch = (int)(n_planes / channels);
     e1.alpha = kFScaleP / kFScaleX; e1.basis_scale = rs_w;
     rc = launch_fold_gemm(A1, 2 * n_planes * (int64_t)h2, 2, B1, kw / 2, w2, e1, stream);
     if (rc) return rc;
-    FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, h2, n_planes * (int64_t)kw * h2};
-    FoldOperand B2{(const __half*)bh_hi, (const __half*)bh_lo, h2, (int64_t)(kh / 2) * h2};
+    FoldOperand A2{(const __half*)work_hi, (const __half*)work_lo, ldh, n_planes * (int64_t)kw * ldh};
+    FoldOperand B2{(const __half*)bh_hi, (const __half*)bh_lo, ldh, (int64_t)(kh / 2) * ldh};
     const int64_t n_tok = (n_planes / channels) * (kh / tile_p) * (kw / tile_p) * channels;
     cudaMemsetAsync(maxabs, 0, sizeof(float) * n_tok, st);
     CodesArgs cg{};
@@ -1950,16 +2100,17 @@ extern "C" int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, co
     return rc;
 }
 
-// inverse: yq[b][a][plane][kh/2][ldq] (scale 2^4, DC removed) -> z[b*2+a][plane][h/2][w/2] fp32 quadrant transforms
-//   bwt: (2, w/2, ldq) = CW[2j+b, w']^T, bht: (2, h/2, ldi) = CH[2i+a, h']^T; work: (2, 2, n_planes, w/2, ldi) hi/lo
+// inverse: yq[b][a][plane][kh/2][ldq] (scale 2^4, DC removed) -> z[b*2+a][plane][H2][W2] fp32 quadrant transforms
+//   (H2 = ceil(h/2), W2 = ceil(w/2));  bwt: (2, W2, ldq) = CW[2j+b, w']^T, bht: (2, H2, ldi) = CH[2i+a, h']^T;
+//   work: (2, 2, n_planes, W2, ldi) hi/lo
 extern "C" int dcta_dct2_inv_fold(const void* yq_hi, const void* yq_lo, const void* bwt_hi, const void* bwt_lo,
                                   const void* bht_hi, const void* bht_lo, void* work_hi, void* work_lo, float* z,
                                   int64_t n_planes, int h, int w, int kh, int kw, void* stream) {
     DCTA_REQUIRE(yq_hi && yq_lo && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && z,
                  "dct2_inv_fold: null pointer");
-    DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_inv_fold: needs h, w multiples of 16 and even kh <= h, kw <= w");
+    DCTA_REQUIRE(fold_dims_ok(h, w, kh, kw), "dct2_inv_fold: needs h, w >= 2 and even kh <= h, kw <= w");
     if (n_planes == 0) return DCTA_OK;
-    const int h2 = h / 2, w2 = w / 2, kh2 = kh / 2, kw2 = kw / 2;
+    const int h2 = fold_half(h), w2 = fold_half(w), kh2 = kh / 2, kw2 = kw / 2;
     const int64_t ldq = ceil_div(kw2, 8) * 8, ldi = ceil_div(kh2, 8) * 8;
     // pass 1: Q[(a, plane, i), w'] = sum_j yq[b][a][plane][i, j] CW[2j+b, w'], stored as Q^T[b][a][plane][w'][i]
     FoldOperand A1{(const __half*)yq_hi, (const __half*)yq_lo, ldq, 2 * n_planes * (int64_t)kh2 * ldq};
@@ -2021,7 +2172,7 @@ extern "C" int dcta_decode_gen_tables(const float* median, const float* b, int c
 extern "C" int dcta_decode_codes_inv_fold_supported(int h, int w, int kh, int kw, int p, int c, int d) {
     if (!fold_dims_ok(h, w, kh, kw) || p < 8 || p > 16 || (p & 1) || c != p || d != p || kh % p || kw % p) return 0;
     FoldGemm g{};
-    return fold_geometry(w / 2, kw / 2, g, 0, F_GEN_STAGES * F_GEN_STAGE) && fold_geometry(h / 2, kh / 2, g);
+    return fold_geometry(fold_half(w), kw / 2, g, 0, F_GEN_STAGES * F_GEN_STAGE) && fold_geometry(fold_half(h), kh / 2, g);
 }
 
 extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
@@ -2033,12 +2184,12 @@ extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* s
     DCTA_REQUIRE(codes && slot_map && median && b && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && z && dc &&
                  tab_in && scratch, "decode_codes_inv_fold: null pointer");
     DCTA_REQUIRE(dcta_decode_codes_inv_fold_supported(h, w, kh, kw, p, c, d),
-                 "decode_codes_inv_fold: needs one LFQ codebook per patch row (c == d == p in 8..16), h, w multiples of 16, even kh, kw");
+                 "decode_codes_inv_fold: needs one LFQ codebook per patch row (c == d == p, p even in 8..16), even kh <= h, kw <= w");
     DCTA_REQUIRE(th <= H && tw <= W && kh / p <= H && kw / p <= W && n_img * channels_n < (1 << 24),
                  "decode_codes_inv_fold: token grid outside the PatchNorm tables");
     if (n_img == 0) return DCTA_OK;
     const int64_t n_planes = n_img * channels_n;
-    const int h2 = h / 2, w2 = w / 2, kh2 = kh / 2, kw2 = kw / 2;
+    const int h2 = fold_half(h), w2 = fold_half(w), kh2 = kh / 2, kw2 = kw / 2;
     const int64_t ldq = ceil_div(kw2, 8) * 8, ldi = ceil_div(kh2, 8) * 8;
     int n_iblk, num_kb;
     int64_t tab_bytes, bv_bytes;
@@ -2094,34 +2245,42 @@ extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* s
     return launch_fold_gemm(A2, n_planes * (int64_t)w2, 4, B2, h2, kh2, e2, stream);
 }
 
-extern "C" int dcta_unfold_ipt_to_rgb(const float* z, const float* dc, float* rgb, int64_t n_img, int h, int w,
-                                      const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream) {
-    DCTA_REQUIRE(z && rgb && m_ipt_inv_host && m_lms2rgb_host, "unfold_ipt_to_rgb: null pointer");
-    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0, "unfold_ipt_to_rgb: bad sizes");
+template <typename TOut>
+static int unfold_ipt_to_rgb_any(const float* z, const float* dc, TOut* rgb, int64_t n_img, int h, int w,
+                                 const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream, const char* who) {
+    DCTA_REQUIRE(z && rgb && m_ipt_inv_host && m_lms2rgb_host, "%s: null pointer", who);
+    DCTA_REQUIRE(h >= 2 && w >= 2, "%s: bad sizes", who);
     if (n_img == 0) return DCTA_OK;
     Mat3 A, B;
     for (int i = 0; i < 9; ++i) { A.m[i] = m_ipt_inv_host[i]; B.m[i] = m_lms2rgb_host[i]; }
-    unfold_kernel<true><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, rgb, n_img, h, w, A, B);
-    return check_launch("unfold_ipt_to_rgb");
+    if (fold_fast_dims(h, w) && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0)
+        unfold_kernel<true, TOut><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, rgb, n_img, h, w, A, B);
+    else
+        unfold_any_kernel<true, TOut><<<grid_for(n_img * fold_half(h) * fold_half(w), 256), 256, 0, as_stream(stream)>>>(
+            z, dc, rgb, n_img, h, w, A, B);
+    return check_launch(who);
+}
+
+extern "C" int dcta_unfold_ipt_to_rgb(const float* z, const float* dc, float* rgb, int64_t n_img, int h, int w,
+                                      const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream) {
+    return unfold_ipt_to_rgb_any(z, dc, rgb, n_img, h, w, m_ipt_inv_host, m_lms2rgb_host, stream, "unfold_ipt_to_rgb");
 }
 
 extern "C" int dcta_unfold_ipt_to_rgb_u8(const float* z, const float* dc, uint8_t* rgb, int64_t n_img, int h, int w,
                                          const float* m_ipt_inv_host, const float* m_lms2rgb_host, void* stream) {
-    DCTA_REQUIRE(z && rgb && m_ipt_inv_host && m_lms2rgb_host, "unfold_ipt_to_rgb_u8: null pointer");
-    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 3) == 0, "unfold_ipt_to_rgb_u8: bad sizes");
-    if (n_img == 0) return DCTA_OK;
-    Mat3 A, B;
-    for (int i = 0; i < 9; ++i) { A.m[i] = m_ipt_inv_host[i]; B.m[i] = m_lms2rgb_host[i]; }
-    unfold_kernel<true, uint8_t><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, rgb, n_img, h, w, A, B);
-    return check_launch("unfold_ipt_to_rgb_u8");
+    return unfold_ipt_to_rgb_any(z, dc, rgb, n_img, h, w, m_ipt_inv_host, m_lms2rgb_host, stream, "unfold_ipt_to_rgb_u8");
 }
 
 extern "C" int dcta_unfold_planes(const float* z, const float* dc, float* x, int64_t n_planes, int h, int w, void* stream) {
     DCTA_REQUIRE(z && x, "unfold_planes: null pointer");
-    DCTA_REQUIRE(h % 16 == 0 && w % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "unfold_planes: bad sizes");
+    DCTA_REQUIRE(h >= 2 && w >= 2, "unfold_planes: bad sizes");
     if (n_planes == 0) return DCTA_OK;
     Mat3 A{}, B{};
-    unfold_kernel<false><<<grid_for(n_planes * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, x, n_planes, h, w, A, B);
+    if (fold_fast_dims(h, w) && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+        unfold_kernel<false><<<grid_for(n_planes * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, x, n_planes, h, w, A, B);
+    else
+        unfold_any_kernel<false, float><<<grid_for(n_planes * fold_half(h) * fold_half(w), 256), 256, 0, as_stream(stream)>>>(
+            z, dc, x, n_planes, h, w, A, B);
     return check_launch("unfold_planes");
 }
 

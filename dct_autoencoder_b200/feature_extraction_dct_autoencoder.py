@@ -154,8 +154,8 @@ class DCTAutoencoderFeatureExtractor:
                 # folded: the colour transform writes the four mirrored sign combinations of each plane
                 hi, lo, dc = rgb_to_ipt_fold(x)
                 if th > 64:       # the epilogue's per-token max image covers at most 64 tile rows
-                    return dct2_fwd_fold(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c)
-                tiles, self._maxabs = dct2_fwd_fold(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c, with_maxabs=True)
+                    return dct2_fwd_fold(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c, hw=(h, w))
+                tiles, self._maxabs = dct2_fwd_fold(hi, lo, dc, th * p, tw * p, tile_p=p, channels=c, with_maxabs=True, hw=(h, w))
                 return tiles
             if self.dct_impl in ("tc", "tc_plain") and tc_forward_ok(h, w):
                 # tensor cores: colour transform writes the centred fp16 hi/lo operand planes directly
@@ -395,7 +395,7 @@ class DCTAutoencoderFeatureExtractor:
                        and bool(_lib.load().dcta_fold_codes_supported(h, w, th * p, tw * p, p)))
         if in_epilogue:
             hi, lo, dc = rgb_to_ipt_fold(x)
-            maxabs, code_grid = dct2_fwd_fold_codes(hi, lo, dc, th * p, tw * p, p, c, norm)
+            maxabs, code_grid = dct2_fwd_fold_codes(hi, lo, dc, th * p, tw * p, p, c, norm, hw=(h, w))
             del hi, lo
             order = torch.empty((b, n_tok), dtype=torch.int32, device=x.device)
             imp = _lib.host_floats(self.channel_importances.tolist()[:c] + [1.0] * max(0, c - len(self.channel_importances)))

@@ -530,7 +530,7 @@ _FOLD_CACHE = {}
 
 
 def fold_ok(h: int, w: int, kh: int, kw: int) -> bool:
-    """True if the folded path takes these sizes (h, w multiples of 16; kh, kw even; basis fits in shared memory)."""
+    """True if the folded path takes these sizes (any h, w >= 2; kh, kw even; basis fits in shared memory)."""
     return bool(_lib.load().dcta_fold_supported(int(h), int(w), int(kh), int(kw)))
 
 
@@ -538,17 +538,18 @@ def fold_basis(n: int, k: int, device, transposed: bool):
     """fp16 hi/lo planes of the folded orthonormal DCT-II basis: group g holds the rows of parity g,
     C_n[2j+g, :n/2] * 2^10.
 
-    forward  (transposed=False): (2, k/2, n/2); row 0 of group 0 (the constant 1/sqrt(n)) is stored as exactly 32;
-             also returns the fp32 (2, k/2) factors that undo the scaling.
-    inverse  (transposed=True):  (2, n/2, round8(k/2)) = the transposes; row_scale None."""
+    forward  (transposed=False): (2, k/2, round8(ceil(n/2))); row 0 of group 0 (the constant 1/sqrt(n)) is stored as
+             exactly 32; also returns the fp32 (2, k/2) factors that undo the scaling.
+    inverse  (transposed=True):  (2, ceil(n/2), round8(k/2)) = the transposes; row_scale None.
+    Odd n: the middle sample pairs with itself (it sits in the even rows once, the odd rows hold 0 there)."""
     device = torch.device(device)
     key = (n, k, transposed, device.type, device.index)
     hit = _FOLD_CACHE.get(key)
     if hit is not None:
         return hit
-    k2, n2 = k // 2, n // 2
+    k2, n2 = k // 2, (n + 1) // 2
     if not transposed:
-        hi, lo, rs = _basis_tables(_lib.BASIS_FOLD_FWD, n, k, (2, k2, n2), True)
+        hi, lo, rs = _basis_tables(_lib.BASIS_FOLD_FWD, n, k, (2, k2, _round8(n2)), True)
         row_scale = torch.from_numpy(rs.reshape(2, k2)).to(device)
     else:
         hi, lo, _ = _basis_tables(_lib.BASIS_FOLD_INV, n, k, (2, n2, _round8(k2)), False)
@@ -558,11 +559,16 @@ def fold_basis(n: int, k: int, device, transposed: bool):
     return out
 
 
+def fold_half(n: int) -> int:
+    """Samples per axis of a folded quadrant: ceil(n / 2) (odd n: the middle sample pairs with itself)."""
+    return (n + 1) // 2
+
+
 def rgb_to_ipt_fold(x: torch.Tensor):
     """util.py:70-82 fused with centring, the 2-D fold and the operand split: (b, 3, h, w) fp32 RGB ->
-    quadrants (2, 2, b*3, h/2, w/2) fp16 hi/lo (scale 2^6) + dc (b*3,)."""
+    quadrants (2, 2, b*3, ceil(h/2), round8(ceil(w/2))) fp16 hi/lo (scale 2^6) + dc (b*3,).  Any h, w >= 2."""
     b, c, h, w = x.shape
-    hi = torch.empty((2, 2, b * 3, h // 2, w // 2), dtype=torch.float16, device=x.device)
+    hi = torch.empty((2, 2, b * 3, fold_half(h), _round8(fold_half(w))), dtype=torch.float16, device=x.device)
     lo = torch.empty_like(hi)
     dc = torch.empty(b * 3, dtype=torch.float32, device=x.device)
     scratch = torch.empty(b * 3 * 33, dtype=torch.float32, device=x.device)
@@ -574,11 +580,11 @@ def rgb_to_ipt_fold(x: torch.Tensor):
 
 
 def fold_planes(x: torch.Tensor):
-    """fp32 planes (..., h, w) -> centred folded quadrants (2, 2, n_planes, h/2, w/2) hi/lo + dc."""
+    """fp32 planes (..., h, w) -> centred folded quadrants (2, 2, n_planes, ceil(h/2), round8(ceil(w/2))) hi/lo + dc."""
     x = x.contiguous()
     h, w = x.shape[-2:]
     n_planes = x.numel() // (h * w)
-    hi = torch.empty((2, 2, n_planes, h // 2, w // 2), dtype=torch.float16, device=x.device)
+    hi = torch.empty((2, 2, n_planes, fold_half(h), _round8(fold_half(w))), dtype=torch.float16, device=x.device)
     lo = torch.empty_like(hi)
     dc = torch.empty(n_planes, dtype=torch.float32, device=x.device)
     scratch = torch.empty(n_planes * 33, dtype=torch.float32, device=x.device)
@@ -589,15 +595,17 @@ def fold_planes(x: torch.Tensor):
 
 
 def dct2_fwd_fold(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: Optional[torch.Tensor], kh: int, kw: int,
-                  tile_p: int = 0, channels: int = 1, out_shape=None, with_maxabs: bool = False):
-    """Truncated forward DCT from folded quadrants (2, 2, n_planes, h/2, w/2).  ``with_maxabs`` (token grid
-    only) also returns amax|tile| per token (n_img, kh/p, kw/p, channels), reduced in the GEMM epilogue."""
+                  tile_p: int = 0, channels: int = 1, out_shape=None, with_maxabs: bool = False, hw=None):
+    """Truncated forward DCT from folded quadrants (2, 2, n_planes, ceil(h/2), round8(ceil(w/2))).  ``hw``: the plane
+    size (h, w); needed when it is not a multiple of 16 (default: twice the quadrant shape).  ``with_maxabs`` (token
+    grid only) also returns amax|tile| per token (n_img, kh/p, kw/p, channels), reduced in the GEMM epilogue."""
     n_planes, h2, w2 = xq_hi.shape[-3:]
-    h, w = 2 * h2, 2 * w2
+    h, w = hw if hw is not None else (2 * h2, 2 * w2)
+    assert fold_half(h) == h2 and _round8(fold_half(w)) == w2, "quadrant shape does not belong to this plane size"
     dev = xq_hi.device
     bw_hi, bw_lo, rs_w = fold_basis(w, kw, dev, False)
     bh_hi, bh_lo, rs_h = fold_basis(h, kh, dev, False)
-    work_hi = torch.empty((2, n_planes, kw, h2), dtype=torch.float16, device=dev)
+    work_hi = torch.empty((2, n_planes, kw, _round8(h2)), dtype=torch.float16, device=dev)
     work_lo = torch.empty_like(work_hi)
     if tile_p:
         y = torch.empty((n_planes // channels, kh // tile_p, kw // tile_p, channels, tile_p * tile_p),
@@ -617,16 +625,17 @@ def dct2_fwd_fold(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: Optional[torch.T
 
 
 def dct2_fwd_fold_codes(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: torch.Tensor, kh: int, kw: int, tile_p: int,
-                        channels: int, norm):
+                        channels: int, norm, hw=None):
     """Forward DCT from folded quadrants straight to LFQ code words (one codebook per patch row) of the
     PatchNorm-normalised coefficients: returns (maxabs (n_img, kh/p, kw/p, channels),
     code_grid (n_img, kh/p, kw/p, channels, p) int32) -- the token grid itself is never written."""
     n_planes, h2, w2 = xq_hi.shape[-3:]
-    h, w = 2 * h2, 2 * w2
+    h, w = hw if hw is not None else (2 * h2, 2 * w2)
+    assert fold_half(h) == h2 and _round8(fold_half(w)) == w2, "quadrant shape does not belong to this plane size"
     dev = xq_hi.device
     bw_hi, bw_lo, rs_w = fold_basis(w, kw, dev, False)
     bh_hi, bh_lo, rs_h = fold_basis(h, kh, dev, False)
-    work_hi = torch.empty((2, n_planes, kw, h2), dtype=torch.float16, device=dev)
+    work_hi = torch.empty((2, n_planes, kw, _round8(h2)), dtype=torch.float16, device=dev)
     work_lo = torch.empty_like(work_hi)
     shape = (n_planes // channels, kh // tile_p, kw // tile_p, channels)
     maxabs = torch.empty(shape, dtype=torch.float32, device=dev)
@@ -648,15 +657,15 @@ def dct2_fwd_fold_codes(xq_hi: torch.Tensor, xq_lo: torch.Tensor, dc: torch.Tens
 
 def dct2_inv_fold(yq_hi: torch.Tensor, yq_lo: torch.Tensor, kh: int, kw: int, h: int, w: int) -> torch.Tensor:
     """Folded coefficient quadrants (2, 2, n_planes, kh/2, round8(kw/2)) -> quadrant transforms
-    z (4, n_planes, h/2, w/2) fp32 (to be un-folded by ``unfold_ipt_to_rgb`` / ``unfold_planes``)."""
+    z (4, n_planes, ceil(h/2), ceil(w/2)) fp32 (to be un-folded by ``unfold_ipt_to_rgb`` / ``unfold_planes``)."""
     n_planes = yq_hi.shape[2]
     dev = yq_hi.device
     bwt_hi, bwt_lo, _ = fold_basis(w, kw, dev, True)
     bht_hi, bht_lo, _ = fold_basis(h, kh, dev, True)
     ldi = _round8(kh // 2)
-    work_hi = torch.empty((2, 2, n_planes, w // 2, ldi), dtype=torch.float16, device=dev)
+    work_hi = torch.empty((2, 2, n_planes, fold_half(w), ldi), dtype=torch.float16, device=dev)
     work_lo = torch.empty_like(work_hi)
-    z = torch.empty((4, n_planes, h // 2, w // 2), dtype=torch.float32, device=dev)
+    z = torch.empty((4, n_planes, fold_half(h), fold_half(w)), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.call("dcta_dct2_inv_fold", _lib.ptr(yq_hi), _lib.ptr(yq_lo), _lib.ptr(bwt_hi), _lib.ptr(bwt_lo),
                   _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z),
@@ -680,9 +689,9 @@ def decode_codes_inv_fold(codes, slot_map, sel, n_img: int, channels: int, th: i
     bwt_hi, bwt_lo, _ = fold_basis(w, kw, dev, True)
     bht_hi, bht_lo, _ = fold_basis(h, kh, dev, True)
     ldi = _round8(kh // 2)
-    work_hi = torch.empty((2, 2, n_planes, w // 2, ldi), dtype=torch.float16, device=dev)
+    work_hi = torch.empty((2, 2, n_planes, fold_half(w), ldi), dtype=torch.float16, device=dev)
     work_lo = torch.empty_like(work_hi)
-    z = torch.empty((4, n_planes, h // 2, w // 2), dtype=torch.float32, device=dev)
+    z = torch.empty((4, n_planes, fold_half(h), fold_half(w)), dtype=torch.float32, device=dev)
     dc = torch.empty(n_planes, dtype=torch.float32, device=dev)
     scratch = torch.empty(lib.dcta_decode_codes_inv_fold_scratch_bytes(n_img, channels, kh, kw), dtype=torch.uint8, device=dev)
     median, b = norm.median.data, norm.b.data
@@ -720,7 +729,7 @@ def unfold_ipt_to_rgb(z: torch.Tensor, dc: Optional[torch.Tensor], h: int, w: in
 def dct2_truncated_fold(x: torch.Tensor, kh: int, kw: int, tile_p: int = 0, channels: int = 1):
     """fp32 planes (..., h, w) -> truncated DCT through the folded tensor-core path."""
     hi, lo, dc = fold_planes(x)
-    return dct2_fwd_fold(hi, lo, dc, kh, kw, tile_p, channels, out_shape=tuple(x.shape[:-2]))
+    return dct2_fwd_fold(hi, lo, dc, kh, kw, tile_p, channels, out_shape=tuple(x.shape[:-2]), hw=tuple(x.shape[-2:]))
 
 
 def idct2_truncated_fold(y: torch.Tensor, h: int, w: int):

@@ -23,13 +23,17 @@ def D():
 def test_fold_supported_predicate(D):
     ok = D.util.fold_ok
     assert ok(512, 512, 448, 448) and ok(1024, 1024, 448, 448) and ok(256, 256, 252, 252) and ok(64, 64, 64, 64)
-    assert not ok(300, 456, 294, 448)        # h not a multiple of 16
+    assert ok(300, 456, 294, 448) and ok(300, 451, 294, 448) and ok(37, 53, 28, 42)      # any plane size
     assert not ok(512, 512, 441, 448)        # odd coefficient count
 
 
 @pytest.mark.parametrize("h,w,kh,kw,n", [(64, 64, 64, 64, 2), (128, 96, 112, 84, 2), (256, 256, 252, 252, 2),
                                           (512, 512, 448, 448, 1), (304, 464, 294, 448, 1), (1024, 1024, 448, 448, 1),
-                                          (512, 512, 512, 512, 1), (32, 48, 28, 42, 5)])
+                                          (512, 512, 512, 512, 1), (32, 48, 28, 42, 5),
+                                          # sizes that are not multiples of 16: padded pitches; odd sizes: the middle
+                                          # row / column pairs with itself
+                                          (300, 452, 294, 448, 2), (300, 451, 294, 448, 2), (301, 450, 294, 448, 1),
+                                          (37, 53, 28, 42, 3), (511, 513, 448, 448, 1), (18, 18, 14, 14, 2)])
 def test_fold_dct_matches_float64_definition(D, h, w, kh, kw, n):
     rng = np.random.default_rng(h * 7 + w)
     x = rng.random((n, 3, h, w), dtype=np.float32) * 2 - 0.5

@@ -62,20 +62,42 @@ def test_tc_and_fp32_pipelines_agree(D):
     assert float((ra - rb2).abs().max()) < 2e-5
 
 
-def test_odd_sizes_fall_back_to_exact_fp32_forward(D):
-    """w % 8 != 0 is not TMA-legal: the extractor uses the FFMA forward there (same API, same results
-    within tolerance) and the tensor-core inverse (padded pitches)."""
+@pytest.mark.parametrize("h,w", [(90, 101), (300, 451), (255, 320), (128, 112)])
+def test_any_image_size_runs_on_the_folded_tensor_core_path(D, h, w):
+    """Sizes that are not multiples of 16 (or are odd) stay on the folded tcgen05 path: quadrants of ceil(n/2) samples
+    with padded pitches, the middle row / column of an odd size paired with itself (csrc/dct_fold.cu fold_any_kernel).
+    Same tokens as the exact-fp32 FFMA extractor and the oracle within the DCT tolerance, same fused codes round trip."""
     torch.manual_seed(2)
-    x = torch.rand(2, 3, 90, 101).cuda()
+    x = torch.rand(3, 3, h, w).cuda()
     fe_tc = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072, dct_impl="tc")
     fe_32 = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072, dct_impl="fp32")
-    b1, b2 = fe_tc.process_batch(x), fe_32.process_batch(x)
-    assert torch.equal(b1.patches, b2.patches)
-    r1, r2 = fe_tc.postprocess_batch(b1), fe_32.postprocess_batch(b2)
-    assert float((r1 - r2).abs().max()) < 2e-5
+    _, _, th, tw = fe_tc._geometry(h, w)
+    assert D.util.fold_ok(h, w, th * 14, tw * 14)
+    l0 = D._lib.launch_count
+    g_tc = fe_tc._token_grid(x)
+    assert D._lib.launch_count - l0 == 4          # plane means + fold kernel + two fold_gemm launches: no FFMA kernel
+    g_32 = fe_32._token_grid(x)
+    scale = float(g_32.abs().max())
+    assert float((g_tc - g_32).abs().max()) <= 8e-7 * scale
     ofe = O.FeatureExtractor(3, 14, 0.0, 32, 32, 3072)
     it = ofe.preprocess(x[0].cpu().numpy())
-    assert np.abs(b1.patches[0, : it["patches"].shape[0]].cpu().numpy() - it["patches"]).max() < 1e-4
+    b1 = fe_tc.process_batch(x)
+    k = it["patches"].shape[0]
+    # same token set and order wherever the scores are not within the tie rule (random images: no near ties expected)
+    same = (b1.patch_positions[0, :k].cpu().numpy() == it["positions"]).all(-1) & (b1.patch_channels[0, :k].cpu().numpy() == it["channels"])
+    assert same.mean() > 0.99
+    assert np.abs(b1.patches[0, :k].cpu().numpy()[same] - it["patches"][same]).max() < 1e-4
+    r1, r2 = fe_tc.postprocess_batch(b1), fe_32.postprocess_batch(fe_32.process_batch(x))
+    assert float((r1 - r2).abs().max()) < 2e-5
+    # fused codes path (forward pass 2 -> code words, decode inside inverse pass 1) against the staged modules
+    pn = D.PatchNorm(32, 32, 14, 3).cuda()
+    lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).cuda().eval()
+    pipe = D.TransformPipeline(fe_tc, pn, lfq)
+    pipe.fit_norm(torch.rand(4, 3, h, w).cuda())
+    rec_s, codes_s = pipe.roundtrip(x, fused=False)
+    rec_f, codes_f = pipe.roundtrip(x)
+    assert torch.equal(codes_f, codes_s)
+    assert torch.equal(rec_f, rec_s)
 
 
 @pytest.mark.parametrize("beta,max_seq_len,size,patch,cb", [

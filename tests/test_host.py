@@ -379,7 +379,7 @@ def test_table_cache_is_keyed_by_device_and_evicts_lru(D):
         torch.Tensor.pin_memory = orig
 
 
-@pytest.mark.parametrize("n,k", [(512, 448), (256, 252), (1024, 448), (90, 84), (16, 16)])
+@pytest.mark.parametrize("n,k", [(512, 448), (256, 252), (1024, 448), (90, 84), (16, 16), (451, 448), (301, 294), (15, 14)])
 def test_basis_init_matches_the_float64_definition(D, n, k):
     """dcta_basis_init (host arithmetic in libdcta, no GPU): every layout equals the orthonormal DCT-II definition
     evaluated with numpy in float64 -- fp32 table to the last bit, hi + lo of the split tables to 2^-21 relative
@@ -401,12 +401,18 @@ def test_basis_init_matches_the_float64_definition(D, n, k):
     hi_t, lo_t, _ = _basis_tables(L.BASIS_SPLIT_INV, n, k, (n, _round8(k)), False)
     got = (hi_t.astype(np.float64) + lo_t.astype(np.float64))[:, :k].T / 1024.0
     assert np.abs(got - c).max() <= 2.0 ** -21 * np.abs(c).max()
-    if n % 2 == 0 and k % 2 == 0:
-        fh, fl, frs = _basis_tables(L.BASIS_FOLD_FWD, n, k, (2, k // 2, n // 2), True)
-        got = (fh.astype(np.float64) + fl.astype(np.float64)) * frs.reshape(2, k // 2, 1).astype(np.float64)
-        want = np.stack([c[0::2, :n // 2], c[1::2, :n // 2]])
+    if k % 2 == 0:
+        # folded layouts: ceil(n/2) samples per group, rows padded to 8; odd n: the middle sample pairs with itself and
+        # the odd rows hold an exact 0 there (cos(pi q / 2))
+        n2, ld = (n + 1) // 2, _round8((n + 1) // 2)
+        fh, fl, frs = _basis_tables(L.BASIS_FOLD_FWD, n, k, (2, k // 2, ld), True)
+        got = (fh.astype(np.float64) + fl.astype(np.float64))[:, :, :n2] * frs.reshape(2, k // 2, 1).astype(np.float64)
+        want = np.stack([c[0::2, :n2], c[1::2, :n2]])
         assert np.abs(got - want).max() <= 2.0 ** -21 * np.abs(c).max()
-        ih, il, _ = _basis_tables(L.BASIS_FOLD_INV, n, k, (2, n // 2, _round8(k // 2)), False)
+        assert not fh[:, :, n2:].any() and not fl[:, :, n2:].any()
+        if n % 2:
+            assert not fh[1, :, n2 - 1].any() and not fl[1, :, n2 - 1].any()
+        ih, il, _ = _basis_tables(L.BASIS_FOLD_INV, n, k, (2, n2, _round8(k // 2)), False)
         got = np.transpose((ih.astype(np.float64) + il.astype(np.float64))[:, :, :k // 2], (0, 2, 1)) / 1024.0
         assert np.abs(got - want).max() <= 2.0 ** -21 * np.abs(c).max()
     assert lib.dcta_basis_elems(99, n, k) == -1
