@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--dct-impl", default="tc")
     ap.add_argument("--staged", action="store_true", help="the drop-in modules one by one instead of the fused step")
+    ap.add_argument("--width", type=int, default=0, help="image width (default: --size)")
+    ap.add_argument("--launches", action="store_true", help="print the library's per-launch CUDA-event times of one step")
     a = ap.parse_args()
     import torch
     import dct_autoencoder_b200 as D
@@ -27,8 +29,8 @@ def main():
     pipe = D.TransformPipeline(fe, pn, lfq)
     g = torch.Generator(device=dev)
     g.manual_seed(1)
-    pipe.fit_norm(torch.rand(min(a.batch, 16), 3, a.size, a.size, device=dev, generator=g))
-    x = torch.rand(a.batch, 3, a.size, a.size, device=dev, generator=g)
+    pipe.fit_norm(torch.rand(min(a.batch, 16), 3, a.size, a.width or a.size, device=dev, generator=g))
+    x = torch.rand(a.batch, 3, a.size, a.width or a.size, device=dev, generator=g)
     step = (lambda: pipe.roundtrip_staged(x)) if a.staged else (lambda: pipe.roundtrip(x))
     for _ in range(a.warmup):
         step()
@@ -42,6 +44,11 @@ def main():
     torch.cuda.synchronize()
     print(f"batch {a.batch} size {a.size}: {e0.elapsed_time(e1) / a.steps:.3f} ms/step, "
           f"{(D._lib.launch_count - l0) // a.steps} launches/step")
+    if a.launches:
+        with D._lib.profile(dev) as prof:
+            step()
+        for name, ms in prof.groups:
+            print(f"  {ms * 1e3:9.1f} us  {name}")
 
 
 if __name__ == "__main__":
