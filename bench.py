@@ -5,6 +5,8 @@
                     [--config 2|3a|3b|4|5] [--global-batch G]
 
 `--config` selects the BASELINE.json configuration (default 2 = the headline metric; the driver runs that one):
+  2s       config 2 with the SECONDARY quantiser of SURVEY 8(d): LFQ(dim=196, codebook_size=8192, num_codebooks=16), i.e.
+           the conf/patch14-l.json quantiser with its 196 -> 208 -> 196 projections (weights manual_seed(2))
   3a / 3b  synthetic 1024^2, batch 128, max_seq_len 1024: pure top-k cap / beta = 0.004 variable k + row packing
   4        VectorQuantize nearest code, codebook 8192 x 256, 512 x 3072 tokens (metric: tokens/s)
   5        4096 images of 512^2 in total, sharded G / N per GPU (strong scaling), one PatchNorm statistic-fit step
@@ -54,7 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dct-impl", default="tc", choices=["tc", "tc_plain", "fp32"],
                     help="tc = tcgen05 split-precision GEMMs (default), fp32 = exact FFMA GEMMs")
-    ap.add_argument("--config", default="2", choices=["2", "3a", "3b", "4", "5"])
+    ap.add_argument("--config", default="2", choices=["2", "2s", "3a", "3b", "4", "5"])
     ap.add_argument("--global-batch", type=int, default=4096, help="config 5: images in total over all GPUs")
     return ap.parse_args()
 
@@ -332,6 +334,8 @@ def run_ours(a):
     ctx = Ctx()
     if a.config in ("3a", "3b"):
         return run_config3(ctx, a)
+    if a.config == "2s":
+        return run_config2s(ctx, a)
     if a.config == "4":
         return run_config4(ctx, a)
     if a.config == "5":
@@ -493,6 +497,44 @@ def run_ours(a):
         line["cpu_baseline"] = dict(value=ips, unit=UNIT, cores=procs, kind="port",
                                     sample=f"{n} images of {S}x{S} over {procs} worker processes, {dt:.1f} s "
                                            "(oracle/dcta_oracle.py run_pipeline)")
+    return ctx.finish(line)
+
+
+def run_config2s(ctx, a):
+    """Config 2 with the secondary quantiser: LFQ(dim=196, codebook_size=8192, num_codebooks=16) -- the
+    conf/patch14-l.json quantiser: project_in 196 -> 208, 16 codebooks x 13 bits, project_out 208 -> 196 (lfq.py:60-62,
+    164, 212).  The projections run on the split-precision tcgen05 GEMM (linear.py); every stage is a libdcta kernel."""
+    torch, D = ctx.torch, ctx.D
+    dev = ctx.dev
+    B, S = a.batch, 512
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072, dct_impl=a.dct_impl)
+    pn = D.PatchNorm(32, 32, 14, 3).to(dev)
+    torch.manual_seed(2)
+    lfq = D.LFQ(dim=196, codebook_size=8192, num_codebooks=16).to(dev).eval()
+    pipe = D.TransformPipeline(fe, pn, lfq)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + ctx.rank)
+    fit = fit_norm_timed(ctx, pipe, torch.rand(min(B, 64), 3, S, S, device=dev, generator=g))
+    g.manual_seed(ctx.rank)
+    x = torch.rand(B, 3, S, S, device=dev, generator=g)
+    l0 = ctx.lib.launch_count
+    ms = ctx.timed(lambda: pipe.roundtrip(x), a.steps, a.warmup)
+    launches = ctx.lib.launch_count - l0
+    times = step_launch_times(ctx, lambda: pipe.roundtrip(x), reps=3)
+    value = ctx.world * B * a.steps / (ms / 1e3)
+    staged_bytes = (26004480 + 2 * 3072 * 208 * 4 * 2) * B          # + project_in / project_out activations written and read
+    line = dict(metric="encode+decode images/sec at 512^2 patch14, LFQ 16 x 13 bit with 196->208->196 projections (config 2, secondary quantiser)",
+                value=value, unit=UNIT, n_gpus=ctx.world, steps=a.steps, warmup=a.warmup, ms_per_step=ms / a.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="config2 secondary: synthetic 512x512 RGB fp32, patch 14, max_patch 32x32, beta=0, max_seq_len 3072, "
+                                     "PatchNorm frozen, LFQ(dim=196, codebook_size=8192, num_codebooks=16) with projections, decode to RGB",
+                            image_size=S, patch_size=14, global_batch=B * ctx.world, per_gpu_batch=B, fusable=pipe.fusable(),
+                            l2="inputs (805 MB/GPU at B=256) larger than L2", patchnorm_fit=fit),
+                gpu_launches=launches,
+                pipeline_hbm=dict(bound="hbm", achieved=staged_bytes * a.steps / (ms / 1e3) / 1e9, peak=ctx.hbm, unit="GB/s",
+                                  note="staged-API algorithmic bytes (SURVEY 8d) + the projection activations"),
+                launch_times_ms=[[n, round(t, 5)] for n, t in times])
+    line["pipeline_hbm"]["frac"] = line["pipeline_hbm"]["achieved"] / ctx.hbm
     return ctx.finish(line)
 
 

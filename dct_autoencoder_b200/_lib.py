@@ -39,7 +39,9 @@ SIGNATURES = {
     "dcta_dct2_fwd": [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "dcta_dct2_inv": [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_gemm_split": [P, P, c_int, c_int64, c_int64, P, P, c_int, c_int64, c_int64, c_int, c_int64, P, c_float,
-                        P, c_int64, c_int64, P],
+                        P, P, c_int64, c_int64, P],
+    "dcta_lfq_project_sign": [P, P, c_int64, c_int64, P, P, c_int, c_int64, c_int, P, P, c_float, P, c_int64, P, P],
+    "dcta_lfq_bits_to_codes": [P, c_int64, c_int, c_int, c_int, P, P],
     "dcta_split_f32": [P, P, P, c_int64, c_float, P],
     "dcta_split_planes_centered": [P, P, P, P, P, c_int64, c_int, c_int, P],
     "dcta_split_coef_planes": [P, P, P, P, c_int64, c_int, c_int, c_int64, c_int, c_int, P],
@@ -124,7 +126,7 @@ KERNELS_PER_CALL = {
     "dcta_zero_padding": 1, "dcta_lfq_quantize": 1, "dcta_lfq_indices_to_codes": 1, "dcta_lfq_commit_loss": 2,
     "dcta_lfq_distance": 1, "dcta_entropy_loss": 2, "dcta_perplexity": 2, "dcta_vq_nearest": 2,
     "dcta_build_slot_map": 1, "dcta_unpatchify": 1, "dcta_wire_pack": 1, "dcta_wire_unpack": 1,
-    "dcta_gemm_split": 1, "dcta_split_f32": 1, "dcta_rgb_to_ipt_split": 2, "dcta_unpatchify_split": 1,
+    "dcta_gemm_split": 1, "dcta_lfq_project_sign": 1, "dcta_lfq_bits_to_codes": 1, "dcta_split_f32": 1, "dcta_rgb_to_ipt_split": 2, "dcta_unpatchify_split": 1,
     "dcta_split_planes_centered": 2, "dcta_split_coef_planes": 1,
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,
     "dcta_ln_pos_rows": 1, "dcta_split_rows_rowscale": 1, "dcta_lfq_entropy_ctas": 0, "dcta_lfq_entropy_factorized": 2,

@@ -31,6 +31,12 @@ static_assert(TM * EPI_PITCH * 4 <= STAGES * STAGE_BYTES, "epilogue staging must
 struct EpiArgs {
     int mode;                 // 0: fp32 planes, 1: fp16 hi/lo planes, 2: fp32 token grid, 3: arg-min partials,
                               // 4: fp16 hi/lo planes written TRANSPOSED, out[b][n*ld + m] (persistent kernel)
+                              // 5: LFQ sign (lfq.py:175-187): out_hi = +-lfq_scale as fp16 (the operand of project_out),
+                              //    sign_bits[m][n tile][j] = ballot of (column n0 + 4*lane + j > 0)
+    const float* col_bias;    // optional per-column (n) bias added after the scaling (modes 0, 1, 5)
+    uint32_t* sign_bits;      // mode 5
+    float lfq_scale;          // mode 5
+    int a_lo_zero;            // the A operand has no lo plane (exact fp16 values): two MMAs per k step, no A_lo loads
     float* out_f32;
     __half* out_hi;
     __half* out_lo;
@@ -90,9 +96,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             const uint32_t ph = (kb / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* st = smem + s * STAGE_BYTES;
-            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            mbar_expect_tx(&full_bar[s], ep.a_lo_zero ? STAGE_BYTES - TILE_BYTES : STAGE_BYTES);
             tma_load_3d(&map_a_hi, &full_bar[s], st, kb * TK, m0, ab);
-            tma_load_3d(&map_a_lo, &full_bar[s], st + TILE_BYTES, kb * TK, m0, ab);
+            if (!ep.a_lo_zero) tma_load_3d(&map_a_lo, &full_bar[s], st + TILE_BYTES, kb * TK, m0, ab);
             tma_load_3d(&map_b_hi, &full_bar[s], st + 2 * TILE_BYTES, kb * TK, n0, bb);
             tma_load_3d(&map_b_lo, &full_bar[s], st + 3 * TILE_BYTES, kb * TK, n0, bb);
         }
@@ -111,8 +117,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const uint64_t a_lo = smem_desc_sw64(base + TILE_BYTES + ko);
                 const uint64_t b_hi = smem_desc_sw64(base + 2 * TILE_BYTES + ko);
                 const uint64_t b_lo = smem_desc_sw64(base + 3 * TILE_BYTES + ko);
-                umma_f16(tmem_acc, a_lo, b_hi, kIdesc, (kb | k) ? 1u : 0u);   // small terms first
-                umma_f16(tmem_acc, a_hi, b_lo, kIdesc, 1u);
+                if (ep.a_lo_zero) {
+                    umma_f16(tmem_acc, a_hi, b_lo, kIdesc, (kb | k) ? 1u : 0u);
+                } else {
+                    umma_f16(tmem_acc, a_lo, b_hi, kIdesc, (kb | k) ? 1u : 0u);   // small terms first
+                    umma_f16(tmem_acc, a_hi, b_lo, kIdesc, 1u);
+                }
                 umma_f16(tmem_acc, a_hi, b_hi, kIdesc, 1u);
             }
             umma_commit(&empty_bar[s]);          // frees the stage when these MMAs have read it
@@ -166,15 +176,44 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         plane_off = (int64_t)batch * ep.batch_stride + n;
     }
     const bool pair_ok = (p % 2 == 0);           // columns (n, n+1) and (n+2, n+3) never straddle a tile
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ep.col_bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < n_valid) bias4[j] = __ldg(ep.col_bias + n + j);
+    }
     for (int rr = 0; rr < 32; ++rr) {
         const int m = m0 + warp * 32 + rr;
         if (m >= ep.M) break;
-        if (n_valid <= 0) continue;
+        if (n_valid <= 0 && ep.mode != 5) continue;
         float4 v;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                      : "r"(stage + (uint32_t)((warp * 32 + rr) * EPI_PITCH + lane * 4) * 4));
         if (ep.dc_mode == 2) { v.x += dcv; v.y += dcv; v.z += dcv; v.w += dcv; }
         else if (ep.dc_mode == 1 && m == 0 && n == 0) v.x += dcv;
+        v.x += bias4[0]; v.y += bias4[1]; v.z += bias4[2]; v.w += bias4[3];
+        if (ep.mode == 5) {
+            // LFQ: x > 0 -> +scale and bit 1, anything else (0, NaN, negative) -> -scale and bit 0 (lfq.py:175, 187)
+            const float a[4] = {v.x, v.y, v.z, v.w};
+            __half h[4];
+            uint32_t bal[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool pos = j < n_valid && a[j] > 0.0f;
+                h[j] = __float2half_rn(pos ? ep.lfq_scale : -ep.lfq_scale);
+                bal[j] = __ballot_sync(0xffffffffu, pos);
+            }
+            if (lane < 4) ep.sign_bits[((int64_t)m * gridDim.x + blockIdx.x) * 4 + lane] = bal[lane];
+            if (n_valid > 0) {
+                const int64_t o = plane_off + (int64_t)m * ep.ld;
+                if (n_valid >= 4) {
+                    *reinterpret_cast<uint2*>(ep.out_hi + o) = *reinterpret_cast<const uint2*>(h);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < n_valid) ep.out_hi[o + j] = h[j];
+                }
+            }
+            continue;
+        }
         if (ep.mode == 0) {
             float* dst = ep.out_f32 + plane_off + (int64_t)m * ep.ld;
             if (n_valid >= 4 && (ep.ld & 3) == 0) {
@@ -843,16 +882,61 @@ static const int kSumStride = 64;  // plane-mean estimate from every 64th run of
 
 extern "C" int dcta_gemm_split(const void* a_hi, const void* a_lo, int a_rows, int64_t a_ld, int64_t a_batch_stride,
                                const void* b_hi, const void* b_lo, int b_rows, int64_t b_ld, int64_t b_batch_stride,
-                               int k, int64_t batch, const float* row_scale, float alpha, float* out, int64_t out_ld,
-                               int64_t out_batch_stride, void* stream) {
-    DCTA_REQUIRE(a_hi && a_lo && b_hi && b_lo && out, "gemm_split: null pointer");
+                               int k, int64_t batch, const float* row_scale, float alpha, const float* col_bias, float* out,
+                               int64_t out_ld, int64_t out_batch_stride, void* stream) {
+    DCTA_REQUIRE(a_hi && b_hi && b_lo && out, "gemm_split: null pointer");
     DCTA_REQUIRE(a_rows > 0 && b_rows > 0 && k > 0 && batch >= 0, "gemm_split: bad sizes");
-    Operand A{(const __half*)a_hi, (const __half*)a_lo, a_rows, a_ld, a_batch_stride};
+    Operand A{(const __half*)a_hi, (const __half*)(a_lo ? a_lo : a_hi), a_rows, a_ld, a_batch_stride};
     Operand B{(const __half*)b_hi, (const __half*)b_lo, b_rows, b_ld, b_batch_stride};
     EpiArgs ep{};
     ep.mode = 0; ep.out_f32 = out; ep.ld = out_ld; ep.batch_stride = out_batch_stride;
     ep.row_scale = row_scale; ep.alpha = alpha; ep.M = a_rows; ep.N = b_rows;
+    ep.col_bias = col_bias; ep.a_lo_zero = a_lo == nullptr;
     return launch_gemm_split(A, B, k, batch, ep, stream);
+}
+
+// LFQ with projections in eval (lfq.py:136-227 with has_projections): project_in + bias + sign in the GEMM epilogue.
+//   a_hi/a_lo (rows, a_ld): the split rows of the normalised tokens (dcta_split_rows_rowscale), row_scale their factors;
+//   w_hi/w_lo (n, w_ld): project_in.weight split; bias (n) [nullable];
+//   q_hi (rows, q_ld) fp16: +-codebook_scale, the operand of project_out (its lo plane is zero: see dcta_gemm_split);
+//   sign_bits (rows, ceil(n / 128), 4) uint32: word j of a 128-column tile holds column 4*lane + j in bit `lane`.
+extern "C" int dcta_lfq_project_sign(const void* a_hi, const void* a_lo, int64_t rows, int64_t a_ld, const void* w_hi,
+                                     const void* w_lo, int n, int64_t w_ld, int k, const float* row_scale, const float* bias,
+                                     float codebook_scale, void* q_hi, int64_t q_ld, uint32_t* sign_bits, void* stream) {
+    DCTA_REQUIRE(a_hi && a_lo && w_hi && w_lo && q_hi && sign_bits, "lfq_project_sign: null pointer");
+    DCTA_REQUIRE(rows >= 0 && rows <= 65535ll * TM && n > 0 && k > 0 && q_ld % 8 == 0 && q_ld >= n, "lfq_project_sign: bad sizes");
+    if (rows == 0) return DCTA_OK;
+    Operand A{(const __half*)a_hi, (const __half*)a_lo, (int)rows, a_ld, 0};
+    Operand B{(const __half*)w_hi, (const __half*)w_lo, n, w_ld, 0};
+    EpiArgs ep{};
+    ep.mode = 5; ep.out_hi = (__half*)q_hi; ep.ld = q_ld; ep.batch_stride = 0;
+    ep.row_scale = row_scale; ep.alpha = 1.0f; ep.M = (int)rows; ep.N = n;
+    ep.col_bias = bias; ep.sign_bits = sign_bits; ep.lfq_scale = codebook_scale;
+    return launch_gemm_split(A, B, k, 1, ep, stream);
+}
+
+// sign_bits of dcta_lfq_project_sign -> indices (rows, c) int64, MSB first within a codebook (lfq.py:87, 187)
+__global__ void __launch_bounds__(256) lfq_bits_to_codes_kernel(const uint32_t* __restrict__ bits, int64_t rows, int n_tiles,
+                                                                int c, int d, int64_t* __restrict__ codes) {
+    const int64_t total = rows * c;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / c;
+        const int cb = (int)(i - m * c);
+        const uint32_t* row = bits + m * n_tiles * 4;
+        int64_t code = 0;
+        for (int b = 0; b < d; ++b) {
+            const int col = cb * d + b, t = col >> 7, r = col & 127;
+            code = (code << 1) | ((__ldg(row + t * 4 + (r & 3)) >> (r >> 2)) & 1u);
+        }
+        codes[i] = code;
+    }
+}
+
+extern "C" int dcta_lfq_bits_to_codes(const uint32_t* sign_bits, int64_t rows, int n, int c, int d, int64_t* codes, void* stream) {
+    DCTA_REQUIRE(sign_bits && codes && c > 0 && d > 0 && d <= 62 && c * d == n, "lfq_bits_to_codes: bad args");
+    if (rows == 0) return DCTA_OK;
+    lfq_bits_to_codes_kernel<<<grid_for(rows * c, 256), 256, 0, as_stream(stream)>>>(sign_bits, rows, (int)ceil_div(n, TN), c, d, codes);
+    return check_launch("lfq_bits_to_codes");
 }
 
 extern "C" int dcta_split_f32(const float* x, void* hi, void* lo, int64_t n, float scale, void* stream) {

@@ -14,7 +14,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .linear import linear_bias_rows
+from .linear import lfq_project_quantize, linear_bias_rows
 from .util import FactorizedDistance, to_device_f32
 
 
@@ -182,9 +182,21 @@ class LFQ(nn.Module):
         assert x.shape[-1] == self.dim, f"expected dimension of {self.dim} but received {x.shape[-1]}"
         _lib.require_cuda(x)
 
+        c, d = self.num_codebooks, self.codebook_dim
+        if self.has_projections and not self.training and not torch.is_grad_enabled() and x.is_cuda:
+            # eval with projections: project_in + sign + index packing in one GEMM kernel, project_out on the exact
+            # +-scale operand (linear.lfq_project_quantize); nothing of size (b, n, c*d) is written as fp32
+            out, indices = lfq_project_quantize(x, self.project_in, self.project_out, c, d, self.codebook_scale)
+            out = out.to(x.dtype)
+            if is_img_or_video:
+                out = out.reshape(out.shape[0], *spatial, out.shape[-1]).movedim(-1, 1)
+                indices = indices.reshape(indices.shape[0], *spatial, c)
+            if not self.keep_num_codebooks_dim:
+                indices = indices[..., 0]
+            return out, indices, self.zero, self.zero
+
         x = self._project(self.project_in, x)
         b, n, _ = x.shape
-        c, d = self.num_codebooks, self.codebook_dim
         original_input = x
 
         xf = to_device_f32(x.detach())

@@ -44,10 +44,34 @@ def _split_weight(weight: torch.Tensor):
     return out
 
 
+def _split_rows(x2: torch.Tensor, w_inv: float, ln: Optional[nn.LayerNorm] = None):
+    """fp32 rows (t, k) -> fp16 hi/lo planes (t, round8(k)) scaled per row by a power of two + the factors that undo the
+    scaling (times ``w_inv``); ``ln``: a LayerNorm applied to the rows first."""
+    t, k = x2.shape
+    dev = x2.device
+    ld = _round8(k)
+    a_hi = torch.empty((t, ld), dtype=torch.float16, device=dev)
+    a_lo = torch.empty_like(a_hi)
+    row_scale = torch.empty(t, dtype=torch.float32, device=dev)
+    gamma = beta = None
+    eps = 0.0
+    if ln is not None:
+        gamma, beta, eps = to_device_f32(ln.weight.detach()), to_device_f32(ln.bias.detach()), float(ln.eps)
+    with torch.cuda.device(dev):
+        _lib.call("dcta_split_rows_rowscale", _lib.ptr(x2), _lib.ptr(gamma), _lib.ptr(beta), eps, _lib.ptr(a_hi), _lib.ptr(a_lo),
+                  _lib.ptr(row_scale), float(w_inv), t, k, ld, _lib.stream_ptr(dev))
+    return a_hi, a_lo, row_scale
+
+
+_GEMM_ROWS = 65535 * 128            # rows per launch of the basic tcgen05 GEMM (grid.y limit)
+
+
 @torch.no_grad()
-def linear_rows(x: torch.Tensor, weight: torch.Tensor, ln: Optional[nn.LayerNorm] = None) -> torch.Tensor:
-    """``F.linear(LN(x), weight)`` (no bias) for x (..., K) on the split-precision tensor-core GEMM.
-    ``ln``: a LayerNorm applied to the rows first, fused into the operand preparation (proj_out)."""
+def linear_rows(x: torch.Tensor, weight: torch.Tensor, ln: Optional[nn.LayerNorm] = None,
+                bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear(LN(x), weight, bias)`` for x (..., K) on the split-precision tensor-core GEMM.
+    ``ln``: a LayerNorm applied to the rows first, fused into the operand preparation (proj_out);
+    ``bias``: added in the GEMM epilogue."""
     _lib.require_cuda(x)
     k = x.shape[-1]
     n = weight.shape[0]
@@ -57,24 +81,65 @@ def linear_rows(x: torch.Tensor, weight: torch.Tensor, ln: Optional[nn.LayerNorm
     dev = x2.device
     w_hi, w_lo, w_inv = _split_weight(weight)
     ld = _round8(k)
-    a_hi = torch.empty((t, ld), dtype=torch.float16, device=dev)
-    a_lo = torch.empty_like(a_hi)
-    row_scale = torch.empty(t, dtype=torch.float32, device=dev)
+    a_hi, a_lo, row_scale = _split_rows(x2, w_inv, ln)
     out = torch.empty((t, n), dtype=torch.float32, device=dev)
-    gamma = beta = None
-    eps = 0.0
-    if ln is not None:
-        gamma, beta, eps = to_device_f32(ln.weight.detach()), to_device_f32(ln.bias.detach()), float(ln.eps)
-    step = 65535 * 128            # rows per launch of the basic tcgen05 GEMM (grid.y limit)
+    if bias is not None:
+        bias = to_device_f32(bias.detach())
     with torch.cuda.device(dev):
         st = _lib.stream_ptr(dev)
-        _lib.call("dcta_split_rows_rowscale", _lib.ptr(x2), _lib.ptr(gamma), _lib.ptr(beta), eps, _lib.ptr(a_hi), _lib.ptr(a_lo),
-                  _lib.ptr(row_scale), float(w_inv), t, k, ld, st)
-        for r0 in range(0, t, step):
-            rows = min(step, t - r0)
+        for r0 in range(0, t, _GEMM_ROWS):
+            rows = min(_GEMM_ROWS, t - r0)
             _lib.call("dcta_gemm_split", a_hi[r0:].data_ptr(), a_lo[r0:].data_ptr(), rows, ld, 0, _lib.ptr(w_hi), _lib.ptr(w_lo),
-                      n, ld, 0, k, 1, row_scale[r0:].data_ptr(), 1.0, out[r0:].data_ptr(), n, 0, st)
+                      n, ld, 0, k, 1, row_scale[r0:].data_ptr(), 1.0, _lib.ptr(bias), out[r0:].data_ptr(), n, 0, st)
     return out.reshape(x.shape[:-1] + (n,))
+
+
+@torch.no_grad()
+def lfq_project_quantize(x: torch.Tensor, project_in: nn.Linear, project_out: Optional[nn.Linear], num_codebooks: int,
+                         codebook_dim: int, codebook_scale: float):
+    """LFQ with projections in eval (lfq.py:136-227): ``project_in`` + bias + sign + index packing in ONE GEMM kernel
+    (``dcta_lfq_project_sign``; the (t, c*d) activations are never written as fp32), the +-scale codes as an exact fp16
+    operand, ``project_out`` + bias as a two-MMA GEMM on it.  Returns (project_out(q) (..., dim) fp32 or the codes
+    (..., c*d) when ``project_out`` is None, indices (..., c) int64)."""
+    _lib.require_cuda(x)
+    k = x.shape[-1]
+    n = num_codebooks * codebook_dim
+    assert project_in.weight.shape == (n, k)
+    x2 = to_device_f32(x).reshape(-1, k)
+    t = x2.shape[0]
+    dev = x2.device
+    w_hi, w_lo, w_inv = _split_weight(project_in.weight)
+    ld = _round8(k)
+    a_hi, a_lo, row_scale = _split_rows(x2, w_inv)
+    ldq = _round8(n)
+    q_hi = torch.empty((t, ldq), dtype=torch.float16, device=dev) if ldq == n else torch.zeros((t, ldq), dtype=torch.float16, device=dev)
+    n_tiles = (n + 127) // 128
+    bits = torch.empty((t, n_tiles, 4), dtype=torch.int32, device=dev)
+    idx = torch.empty((t, num_codebooks), dtype=torch.int64, device=dev)
+    b_in = None if project_in.bias is None else to_device_f32(project_in.bias.detach())
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        for r0 in range(0, t, _GEMM_ROWS):
+            rows = min(_GEMM_ROWS, t - r0)
+            _lib.call("dcta_lfq_project_sign", a_hi[r0:].data_ptr(), a_lo[r0:].data_ptr(), rows, ld, _lib.ptr(w_hi), _lib.ptr(w_lo),
+                      n, ld, k, row_scale[r0:].data_ptr(), _lib.ptr(b_in), float(codebook_scale), q_hi[r0:].data_ptr(), ldq,
+                      bits[r0:].data_ptr(), st)
+        _lib.call("dcta_lfq_bits_to_codes", _lib.ptr(bits), t, n, num_codebooks, codebook_dim, _lib.ptr(idx), st)
+        del a_hi, a_lo
+        if project_out is None:
+            out = q_hi[:, :n].float()
+        else:
+            dim = project_out.weight.shape[0]
+            assert project_out.weight.shape[1] == n
+            o_hi, o_lo, o_inv = _split_weight(project_out.weight)
+            b_out = None if project_out.bias is None else to_device_f32(project_out.bias.detach())
+            out = torch.empty((t, dim), dtype=torch.float32, device=dev)
+            for r0 in range(0, t, _GEMM_ROWS):
+                rows = min(_GEMM_ROWS, t - r0)
+                # A = q_hi (exact fp16, no lo plane); the weight's scale is undone by alpha
+                _lib.call("dcta_gemm_split", q_hi[r0:].data_ptr(), None, rows, ldq, 0, _lib.ptr(o_hi), _lib.ptr(o_lo), dim, ldq, 0,
+                          n, 1, None, float(o_inv), _lib.ptr(b_out), out[r0:].data_ptr(), dim, 0, st)
+    return out.reshape(x.shape[:-1] + (out.shape[-1],)), idx.reshape(x.shape[:-1] + (num_codebooks,))
 
 
 @torch.no_grad()
@@ -106,6 +171,5 @@ def ln_pos_rows(x: torch.Tensor, ln: Optional[nn.LayerNorm] = None, bias: Option
 
 @torch.no_grad()
 def linear_bias_rows(x: torch.Tensor, linear: nn.Linear) -> torch.Tensor:
-    """``linear(x)`` for an nn.Linear with (optional) bias: tensor-core GEMM + one bias pass."""
-    y = linear_rows(x, linear.weight)
-    return y if linear.bias is None else ln_pos_rows(y, bias=linear.bias)
+    """``linear(x)`` for an nn.Linear with (optional) bias: tensor-core GEMM, bias added in its epilogue."""
+    return linear_rows(x, linear.weight, bias=linear.bias)

@@ -103,11 +103,22 @@ int dcta_dct2_inv(const float* y, const float* ch, const float* cw, float* work,
  * pitch that is a multiple of 8 and a 16-byte aligned base (TMA).
  *
  * dcta_gemm_split: D[b] (a_rows x b_rows, fp32, pitch out_ld) = alpha * row_scale[m] *
- *   sum_k A[b][m,k] * B[b][n,k];  a/b_batch_stride == 0 means the operand is shared by all b. */
+ *   sum_k A[b][m,k] * B[b][n,k] + col_bias[n];  a/b_batch_stride == 0 means the operand is shared by all b.
+ *   a_lo [nullable]: NULL = the A values are exact fp16 (e.g. the +-1 LFQ codes): two MMAs per k step, no A_lo loads.
+ *   row_scale, col_bias [nullable]. */
 int dcta_gemm_split(const void* a_hi, const void* a_lo, int a_rows, int64_t a_ld, int64_t a_batch_stride,
                     const void* b_hi, const void* b_lo, int b_rows, int64_t b_ld, int64_t b_batch_stride,
-                    int k, int64_t batch, const float* row_scale, float alpha, float* out, int64_t out_ld,
-                    int64_t out_batch_stride, void* stream);
+                    int k, int64_t batch, const float* row_scale, float alpha, const float* col_bias, float* out,
+                    int64_t out_ld, int64_t out_batch_stride, void* stream);
+/* LFQ with projections in eval (lfq.py:136-227, has_projections): project_in GEMM + bias + sign in one kernel.
+ *   a_hi/a_lo (rows, a_ld): split rows of the tokens (dcta_split_rows_rowscale) with their row_scale;
+ *   w_hi/w_lo (n, w_ld): project_in.weight split; bias (n) [nullable];
+ *   q_hi (rows, q_ld) fp16 = +-codebook_scale: the A operand of project_out (pass a_lo = NULL to dcta_gemm_split);
+ *   sign_bits (rows, ceil(n/128), 4) uint32 -> dcta_lfq_bits_to_codes: indices (rows, c) int64, MSB first (LFQ:87, 187). */
+int dcta_lfq_project_sign(const void* a_hi, const void* a_lo, int64_t rows, int64_t a_ld, const void* w_hi,
+                          const void* w_lo, int n, int64_t w_ld, int k, const float* row_scale, const float* bias,
+                          float codebook_scale, void* q_hi, int64_t q_ld, uint32_t* sign_bits, void* stream);
+int dcta_lfq_bits_to_codes(const uint32_t* sign_bits, int64_t rows, int n, int c, int d, int64_t* codes, void* stream);
 /* hi = rn16(x*scale), lo = rn16(x*scale - hi), elementwise over n values. */
 int dcta_split_f32(const float* x, void* hi, void* lo, int64_t n, float scale, void* stream);
 /* The tensor core accumulates in fp32 with truncation, so the producers below remove a per-plane

@@ -42,7 +42,7 @@ def _gemm_split(D, a, b, row_scale=None, alpha=1.0):
     rs = None if row_scale is None else torch.from_numpy(row_scale.astype(np.float32)).cuda()
     _lib.call("dcta_gemm_split", _lib.ptr(ah), _lib.ptr(al), M, ld, 0 if a_shared else M * ld,
               _lib.ptr(bh), _lib.ptr(bl), N, ld, 0 if b_shared else N * ld, K, batch, _lib.ptr(rs), float(alpha),
-              _lib.ptr(out), N, M * N, _lib.stream_ptr())
+              None, _lib.ptr(out), N, M * N, _lib.stream_ptr())
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
