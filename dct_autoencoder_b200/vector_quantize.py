@@ -6,9 +6,12 @@ gather :222-226): ``forward(x, indices=None, mask=None, ...) -> (quantize, embed
 ``codebook`` property, ``get_codes_from_indices``, ``get_output_from_indices``; module/buffer
 names follow the reference (``_codebook.embed`` ...) so its checkpoints load.
 
-Codebook LEARNING (k-means init, EMA updates, dead-code expiry, affine re-parametrisation, cosine
-codebooks, gumbel/reinmax sampling, orthogonal regularisation and their all-reduces) is outside
-the transform path and is not implemented: ``forward`` in training mode raises.
+Codebook LEARNING for the default configuration of the reference's class -- an EMA Euclidean codebook
+(``ema_update=True``, ``learnable_codebook=False``) with optional k-means initialisation, dead-code expiry, the
+commitment loss and the straight-through estimator (vector_quantize.py:180-220, :417-434, :479-500, :944-1003) -- runs on
+libdcta kernels (csrc/vq_train.cu) with the reference's all-reduces of the batch statistics.  Affine
+re-parametrisation, cosine codebooks, learnable codebooks, gumbel/reinmax sampling and orthogonal regularisation
+are not implemented and raise.
 """
 import collections
 from typing import Optional
@@ -88,31 +91,140 @@ def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = 
     return idx, q
 
 
-class EuclideanCodebook(nn.Module):
-    """State holder with the reference's buffer names (vector_quantize.py:287-296)."""
+def _all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    """vector_quantize.py:283-284 ``all_reduce_fn``: sum over the default process group (NCCL / gloo); no-op alone."""
+    dist = torch.distributed
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t
 
-    def __init__(self, dim, codebook_size, num_codebooks=1):
+
+def _sample_vectors(samples: torch.Tensor, num: int) -> torch.Tensor:
+    """vector_quantize.py:104-112."""
+    n = samples.shape[0]
+    if n >= num:
+        idx = torch.randperm(n, device=samples.device)[:num]
+    else:
+        idx = torch.randint(0, n, (num,), device=samples.device)
+    return samples[idx]
+
+
+class EuclideanCodebook(nn.Module):
+    """State with the reference's buffer names (vector_quantize.py:287-296) + the learning steps on libdcta kernels."""
+
+    def __init__(self, dim, codebook_size, num_codebooks=1, kmeans_init=False, kmeans_iters=10, decay=0.8, eps=1e-5,
+                 threshold_ema_dead_code=0, reset_cluster_size=None, sync=None, ema_update=True):
         super().__init__()
         embed = torch.empty(num_codebooks, codebook_size, dim)
-        nn.init.kaiming_uniform_(embed)                       # uniform_init, vector_quantize.py:52-55
+        if kmeans_init:
+            embed.zero_()                                      # vector_quantize.py:262-263
+        else:
+            nn.init.kaiming_uniform_(embed)                   # uniform_init, vector_quantize.py:52-55
         self.codebook_size = codebook_size
         self.num_codebooks = num_codebooks
-        self.register_buffer("initted", torch.Tensor([True]))
+        self.kmeans_iters = kmeans_iters
+        self.decay, self.eps = decay, eps
+        self.threshold_ema_dead_code = threshold_ema_dead_code
+        self.reset_cluster_size = reset_cluster_size if reset_cluster_size is not None else threshold_ema_dead_code
+        self.sync = sync                                       # None: whenever torch.distributed has more than one rank
+        self.ema_update = ema_update
+        self.register_buffer("initted", torch.Tensor([not kmeans_init]))
         self.register_buffer("cluster_size", torch.zeros(num_codebooks, codebook_size))
         self.register_buffer("embed_avg", embed.clone())
         self.register_buffer("embed", embed)
 
+    def _reduce(self, t):
+        return _all_reduce_sum_(t) if self.sync in (None, True) else t
+
+    def cluster_stats(self, head: int, x: torch.Tensor, ind: torch.Tensor, mask: Optional[torch.Tensor]):
+        """(counts (C,), sums (C, d)) of the tokens ``x`` (T, d) assigned to ``ind`` (T,), masked tokens left out."""
+        C, d = self.embed.shape[1:]
+        counts = torch.empty(C, dtype=torch.float32, device=x.device)
+        sums = torch.empty((C, d), dtype=torch.float32, device=x.device)
+        m = None if mask is None else mask.reshape(-1).to(torch.uint8).contiguous()
+        with torch.cuda.device(x.device):
+            _lib.call("dcta_vq_cluster_stats", _lib.ptr(x), _lib.ptr(ind), _lib.ptr(m), x.shape[0], d, C, _lib.ptr(counts),
+                      _lib.ptr(sums), _lib.stream_ptr(x.device))
+        return counts, sums
+
+    @torch.no_grad()
+    def init_embed_(self, head: int, x: torch.Tensor, mask: Optional[torch.Tensor], impl: str):
+        """k-means initialisation on the first training batch (vector_quantize.py:180-220, :334-355)."""
+        data = x if mask is None else x[mask.reshape(-1)]
+        means = _sample_vectors(data, self.codebook_size).contiguous()
+        d = means.shape[-1]
+        counts = None
+        for _ in range(self.kmeans_iters):
+            buckets, _ = nearest_code(data, means, return_quantized=False, impl=impl)
+            counts, sums = self.cluster_stats(head, data, buckets, None)
+            self._reduce(counts)
+            # the reference all-reduces the MEANS of the ranks (new_means / bins, then all_reduce: vector_quantize.py:210-211)
+            with torch.cuda.device(x.device):
+                if self.sync in (None, True) and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                        and torch.distributed.get_world_size() > 1:
+                    local = torch.zeros_like(means)
+                    _lib.call("dcta_vq_kmeans_means", _lib.ptr(local), _lib.ptr(counts), _lib.ptr(sums), self.codebook_size, d,
+                              _lib.stream_ptr(x.device))
+                    _all_reduce_sum_(local)
+                    means = torch.where((counts == 0)[:, None], means, local)
+                else:
+                    _lib.call("dcta_vq_kmeans_means", _lib.ptr(means), _lib.ptr(counts), _lib.ptr(sums), self.codebook_size, d,
+                              _lib.stream_ptr(x.device))
+            invalidate_codebook_cache()
+        self.embed.data[head].copy_(means)
+        self.embed_avg.data[head].copy_(means * counts[:, None])
+        self.cluster_size.data[head].copy_(counts)
+
+    @torch.no_grad()
+    def ema_update_(self, head: int, x: torch.Tensor, ind: torch.Tensor, mask: Optional[torch.Tensor]):
+        """vector_quantize.py:479-500 for one codebook: batch statistics (all-reduced), lerp of the running statistics,
+        Laplace-smoothed normalisation."""
+        counts, sums = self.cluster_stats(head, x, ind, mask)
+        self._reduce(counts)
+        self._reduce(sums)
+        C, d = sums.shape
+        total = torch.empty(1, dtype=torch.float32, device=x.device)
+        emb, cs, avg = self.embed.data[head], self.cluster_size.data[head], self.embed_avg.data[head]
+        assert emb.is_contiguous() and cs.is_contiguous() and avg.is_contiguous()
+        with torch.cuda.device(x.device):
+            _lib.call("dcta_vq_ema_update", _lib.ptr(emb), _lib.ptr(cs), _lib.ptr(avg), _lib.ptr(counts), _lib.ptr(sums), C, d,
+                      float(self.decay), float(self.eps), _lib.ptr(total), _lib.stream_ptr(x.device))
+        invalidate_codebook_cache()           # the kernel wrote the codebook behind torch's version counter
+
+    @torch.no_grad()
+    def expire_codes_(self, head: int, x: torch.Tensor):
+        """vector_quantize.py:403-434: codes whose running cluster size fell below the threshold are replaced by random
+        batch vectors (one device->host read of the number of expired codes, as in the reference)."""
+        if self.threshold_ema_dead_code == 0:
+            return
+        expired = self.cluster_size[head] < self.threshold_ema_dead_code
+        n = int(expired.sum())
+        if n == 0:
+            return
+        sampled = _sample_vectors(x, n)
+        self.embed.data[head][expired] = sampled
+        self.cluster_size.data[head][expired] = self.reset_cluster_size
+        self.embed_avg.data[head][expired] = sampled * self.reset_cluster_size
+        invalidate_codebook_cache()
+
 
 class VectorQuantize(nn.Module):
-    def __init__(self, dim, codebook_size, codebook_dim=None, heads=1, separate_codebook_per_head=False,
-                 channel_last=True, accept_image_fmap=False, use_cosine_sim=False, affine_param=False,
-                 vq_impl: str = "tc", **training_kwargs):
+    def __init__(self, dim, codebook_size, codebook_dim=None, heads=1, separate_codebook_per_head=False, decay=0.8,
+                 eps=1e-5, freeze_codebook=False, kmeans_init=False, kmeans_iters=10, sync_kmeans=True,
+                 use_cosine_sim=False, threshold_ema_dead_code=0, channel_last=True, accept_image_fmap=False,
+                 commitment_weight=1.0, sync_codebook=None, ema_update=True, learnable_codebook=False,
+                 affine_param=False, vq_impl: str = "tc", **unsupported):
         super().__init__()
         assert vq_impl in ("tc", "fp32")
-        self.vq_impl = vq_impl      # "tc": tcgen05 split-precision distance GEMM; "fp32": exact FFMA kernel
-        if use_cosine_sim or affine_param:
-            raise NotImplementedError("cosine-similarity / affine-parametrised codebooks are training "
-                                      "machinery outside the transform path")
+        self.vq_impl = vq_impl      # "tc": tcgen05 nearest-code search; "fp32": exact FFMA kernel
+        if use_cosine_sim or affine_param or learnable_codebook or not ema_update:
+            raise NotImplementedError("cosine-similarity, affine-parametrised and learnable (non-EMA) codebooks are "
+                                      "not implemented: only the EMA Euclidean codebook is")
+        bad = {k: v for k, v in unsupported.items()
+               if k in ("commitment_use_cross_entropy_loss", "orthogonal_reg_weight", "stochastic_sample_codes",
+                        "straight_through", "reinmax", "in_place_codebook_optimizer", "sync_update_v") and v}
+        if bad:
+            raise NotImplementedError(f"VectorQuantize options outside the implemented codebook learning: {sorted(bad)}")
         self.dim = dim
         self.heads = heads
         self.separate_codebook_per_head = separate_codebook_per_head
@@ -122,12 +234,15 @@ class VectorQuantize(nn.Module):
         self.project_in = nn.Linear(dim, codebook_input_dim) if requires_projection else nn.Identity()
         self.project_out = nn.Linear(codebook_input_dim, dim) if requires_projection else nn.Identity()
         self.has_projections = requires_projection
+        self.commitment_weight = commitment_weight
+        self.freeze_codebook = freeze_codebook
         self._codebook = EuclideanCodebook(codebook_dim, codebook_size,
-                                           num_codebooks=heads if separate_codebook_per_head else 1)
+                                           num_codebooks=heads if separate_codebook_per_head else 1,
+                                           kmeans_init=kmeans_init, kmeans_iters=kmeans_iters, decay=decay, eps=eps,
+                                           threshold_ema_dead_code=threshold_ema_dead_code, sync=sync_codebook)
         self.codebook_size = codebook_size
         self.accept_image_fmap = accept_image_fmap
         self.channel_last = channel_last
-        self.training_kwargs = training_kwargs
 
     @property
     def codebook(self):
@@ -164,10 +279,9 @@ class VectorQuantize(nn.Module):
         return self._project(self.project_out, self.get_codes_from_indices(indices))
 
     def forward(self, x, indices=None, mask=None, sample_codebook_temp=None, freeze_codebook=False):
-        """vector_quantize.py:837-1050, eval branch."""
-        if self.training:
-            raise NotImplementedError("VectorQuantize training (codebook learning) is outside the transform "
-                                      "path; call .eval()")
+        """vector_quantize.py:837-1050.  In training mode the EMA codebook is updated (k-means initialisation on the first
+        batch, EMA of the all-reduced batch statistics, dead-code expiry), ``quantize`` carries the straight-through
+        gradient and ``loss`` is the commitment loss."""
         if indices is not None:
             raise NotImplementedError("cross-entropy loss on given indices is a training feature")
         orig_input = x
@@ -186,7 +300,23 @@ class VectorQuantize(nn.Module):
         b, n, _ = x.shape
         h, embed = self.heads, self._codebook.embed
         d = embed.shape[-1]
-        xf = to_device_f32(x)
+        xf = to_device_f32(x.detach())
+        cb = self._codebook
+        learn = self.training and not (freeze_codebook or self.freeze_codebook)
+        # tokens and mask as the codebook sees them: 'h b n d' per head, or heads folded into the batch '(b h) n d'
+        if h > 1 and self.separate_codebook_per_head:
+            views = [xf.reshape(b, n, h, d)[:, :, i].reshape(b * n, d).contiguous() for i in range(h)]
+            masks = [None if mask is None else mask.reshape(-1)] * h
+        elif h > 1:
+            views = [xf.reshape(b, n, h, d).permute(0, 2, 1, 3).reshape(b * h * n, d).contiguous()]
+            masks = [None if mask is None else mask[:, None, :].expand(b, h, n).reshape(-1)]
+        else:
+            views = [xf.reshape(b * n, d)]
+            masks = [None if mask is None else mask.reshape(-1)]
+        if self.training and not bool(cb.initted):
+            for i, (v, m) in enumerate(zip(views, masks)):
+                cb.init_embed_(i, v, m, self.vq_impl)                       # vector_quantize.py:334-355
+            cb.initted.fill_(1.0)
         ef = to_device_f32(embed)
         if h > 1 and self.separate_codebook_per_head:
             xs = xf.reshape(b, n, h, d).permute(2, 0, 1, 3).contiguous()    # 'h b n d'
@@ -203,11 +333,29 @@ class VectorQuantize(nn.Module):
             ind = idx.reshape(b, n)
             q = qf.reshape(b, n, d)
         q = q.to(x.dtype)
+        loss = torch.tensor([0.0], device=x.device, requires_grad=self.training)
+        if self.training:
+            if learn:
+                # EMA update from this batch's assignments (the quantised vectors above still come from the OLD codebook)
+                if h > 1 and self.separate_codebook_per_head:
+                    flat_ind = [ind[..., i].reshape(-1).contiguous() for i in range(h)]
+                elif h > 1:
+                    flat_ind = [ind.permute(0, 2, 1).reshape(-1).contiguous()]
+                else:
+                    flat_ind = [ind.reshape(-1)]
+                for i, (v, m, fi) in enumerate(zip(views, masks, flat_ind)):
+                    cb.ema_update_(i, v, fi, m)
+                    cb.expire_codes_(i, v)
+            # commitment loss against the detached codes, straight-through estimator (vector_quantize.py:944-952, :976-1003)
+            if self.commitment_weight > 0:
+                se = (q.detach() - x) ** 2
+                commit = se[mask].mean() if mask is not None else se.mean()
+                loss = loss + commit * self.commitment_weight
+            q = x + (q - x).detach()
         if self.accept_image_fmap:
             ind = ind.reshape(b, height, width, *ind.shape[2:])
         if only_one:
             ind = ind[:, 0]
-        loss = torch.tensor([0.0], device=x.device)
         q = self._project(self.project_out, q)
         if need_transpose:
             q = q.transpose(1, 2)

@@ -473,6 +473,18 @@ int dcta_row_sumsq(const float* x, float* out, int64_t n, int d, void* stream);
 int dcta_vq_nearest_tc(const float* x, const void* x_hi, const float* row_alpha, const float* embed,
                        const void* e_hi, const float* e2, int32_t* cand, int64_t* indices, float* quantized,
                        int64_t n_tok, int n_codes, int d, int64_t ld, void* stream);
+/* VectorQuantize codebook learning (VQ:180-220 k-means, VQ:479-500 EMA update).
+ *   dcta_vq_cluster_stats: counts (n_codes) = tokens per code, sums (n_codes, d) = sum of their vectors, over the
+ *     tokens with mask[t] != 0 (mask uint8, nullable); both outputs are zeroed first (reduce-ready: all-reduce them
+ *     across ranks before the update, as the reference does).
+ *   dcta_vq_ema_update: cluster_size <- lerp(cluster_size, counts, 1-decay), embed_avg <- lerp(embed_avg, sums, 1-decay),
+ *     embed <- embed_avg / (laplace_smoothing(cluster_size, n_codes, eps) * sum(cluster_size)); total_scratch: 1 float.
+ *   dcta_vq_kmeans_means: means[c] <- sums[c] / counts[c] for non-empty clusters. */
+int dcta_vq_cluster_stats(const float* x, const int64_t* indices, const uint8_t* mask, int64_t n_tok, int d,
+                          int n_codes, float* counts, float* sums, void* stream);
+int dcta_vq_ema_update(float* embed, float* cluster_size, float* embed_avg, const float* counts, const float* sums,
+                       int n_codes, int d, float decay, float eps, float* total_scratch, void* stream);
+int dcta_vq_kmeans_means(float* means, const float* counts, const float* sums, int n_codes, int d, void* stream);
 
 /* ------------------------------------------------------------------ un-patchify ----------- */
 /* FE:619-643: slot_map (n_img, channels, th, tw) i32 = flat token index (row*s + slot) of the LAST

@@ -621,6 +621,67 @@ class VectorQuantize:
 
 
 # --------------------------------------------------------------------------------------
+# VectorQuantize codebook learning: k-means initialisation and the EMA update
+# --------------------------------------------------------------------------------------
+def laplace_smoothing(x: np.ndarray, n_categories: int, eps=1e-5) -> np.ndarray:
+    """VQ:100-102."""
+    return (x + f32(eps)) / (x.sum(-1, keepdims=True) + f32(n_categories * eps))
+
+
+def vq_kmeans(samples: np.ndarray, means0: np.ndarray, num_iters: int = 10):
+    """VQ:180-220 for one codebook from given initial means (the reference draws them with ``sample_fn``):
+    ``samples`` (N, d), ``means0`` (C, d) -> (means (C, d), bins (C,)).  Empty clusters keep their mean."""
+    samples = samples.astype(f32)
+    means = means0.astype(f32).copy()
+    C = means.shape[0]
+    bins = np.zeros(C, np.int64)
+    for _ in range(num_iters):
+        buckets, _, _ = vq_nearest(samples, means)                                          # argmax(-cdist), VQ:198-200
+        bins = np.bincount(buckets, minlength=C)                                            # VQ:201
+        new = np.zeros_like(means)
+        np.add.at(new, buckets, samples)                                                    # scatter_add_, VQ:209
+        new = new / np.maximum(bins, 1)[:, None].astype(f32)                                # VQ:205, 210
+        means = np.where((bins == 0)[:, None], means, new)                                  # VQ:216-220
+    return means, bins
+
+
+def vq_ema_update(x: np.ndarray, ind: np.ndarray, mask: Optional[np.ndarray], cluster_size: np.ndarray,
+                  embed_avg: np.ndarray, decay: float, eps: float):
+    """VQ:479-500: ``x`` (T, d) tokens, ``ind`` (T,) their codes, ``mask`` (T,) True where the token counts.
+    Returns the updated (embed, cluster_size, embed_avg)."""
+    C = cluster_size.shape[0]
+    keep = np.ones(x.shape[0], bool) if mask is None else mask.astype(bool)
+    batch_n = np.bincount(ind[keep], minlength=C).astype(f32)                               # embed_onehot.sum, VQ:486
+    batch_sum = np.zeros_like(embed_avg, dtype=f32)
+    np.add.at(batch_sum, ind[keep], x[keep].astype(f32))                                   # einsum 'h n d, h n c -> h c d', VQ:491
+    w = f32(1 - decay)
+    cluster_size = cluster_size + w * (batch_n - cluster_size)                              # lerp_, VQ:38-42, 489
+    embed_avg = embed_avg + w * (batch_sum - embed_avg)                                     # VQ:493
+    smoothed = laplace_smoothing(cluster_size, C, eps) * cluster_size.sum(-1, keepdims=True)   # VQ:495
+    embed = embed_avg / smoothed[:, None]                                                   # VQ:497-498
+    return embed.astype(f32), cluster_size.astype(f32), embed_avg.astype(f32)
+
+
+def vq_train_step(x: np.ndarray, mask: Optional[np.ndarray], embed: np.ndarray, cluster_size: np.ndarray,
+                  embed_avg: np.ndarray, decay=0.8, eps=1e-5, commitment_weight=1.0):
+    """One training forward of VectorQuantize with an EMA Euclidean codebook, one head, no projections
+    (VQ:837-1050 + VQ:436-507): ``x`` (b, n, d), ``mask`` (b, n).  Returns (quantize, indices, loss, new embed,
+    new cluster_size, new embed_avg); dead-code expiry (VQ:417-434) is not part of it."""
+    b, n, d = x.shape
+    flat = x.reshape(b * n, d).astype(f32)
+    ind, _, _ = vq_nearest(flat, embed)
+    q = embed[ind].astype(f32)                                                              # uses the codebook BEFORE the update
+    m = None if mask is None else mask.reshape(-1)
+    new_embed, new_cs, new_avg = vq_ema_update(flat, ind, m, cluster_size, embed_avg, decay, eps)
+    se = (q - flat) ** 2                                                                    # F.mse_loss(..., 'none'), VQ:986
+    loss = (se[m].mean() if m is not None else se.mean()) * f32(commitment_weight)          # VQ:990-994
+    quant = q.reshape(b, n, d)
+    if mask is not None:
+        quant = np.where(mask[..., None], quant, x)                                         # VQ:1043-1048
+    return quant.astype(f32), ind.reshape(b, n), np.asarray([loss], f32), new_embed, new_cs, new_avg
+
+
+# --------------------------------------------------------------------------------------
 # whole path, used by bench.py's cpu_baseline / --impl reference legs
 # --------------------------------------------------------------------------------------
 def run_pipeline(images: np.ndarray, fe: FeatureExtractor, norm: PatchNorm, lfq: LFQ):

@@ -273,3 +273,22 @@ def test_pipeline(golden):
     np.testing.assert_allclose(np.stack(rec), g["rec"], atol=5e-3)
     psnr = -10 * np.log10(np.mean((np.stack(rec) - g["rec"]) ** 2) + 1e-20)
     assert psnr > 60
+
+
+def test_vq_training_oracle_matches_reference_golden(golden):
+    """k-means (VQ:180-220) and the EMA codebook update + commitment loss (VQ:479-500, 837-1050) against the
+    unmodified reference run in training mode (tests/golden/make_golden_vq_train.py)."""
+    g = golden("vq_train")
+    means, bins = O.vq_kmeans(g["km_samples"][0], g["km_means0"][0], 10)
+    assert np.array_equal(bins, g["km_bins"][0])
+    np.testing.assert_allclose(means, g["km_means"][0], rtol=2e-6, atol=2e-7)
+    embed, cs, avg = g["ema_embed0"][0], np.zeros(64, np.float32), g["ema_embed0"][0].copy()
+    for step in range(2):
+        q, ind, loss, embed, cs, avg = O.vq_train_step(g[f"ema_x{step}"], g["ema_mask"], embed, cs, avg, decay=0.8,
+                                                       eps=1e-5, commitment_weight=0.7)
+        assert np.array_equal(ind, g[f"ema_ind{step}"])
+        np.testing.assert_allclose(q, g[f"ema_q{step}"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(loss, g[f"ema_loss{step}"], rtol=2e-6)
+        np.testing.assert_allclose(cs, g[f"ema_cluster_size{step + 1}"][0], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(avg, g[f"ema_embed_avg{step + 1}"][0], rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(embed, g[f"ema_embed{step + 1}"][0], rtol=5e-6, atol=1e-7)
