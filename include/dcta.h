@@ -473,6 +473,12 @@ int dcta_row_sumsq(const float* x, float* out, int64_t n, int d, void* stream);
 int dcta_vq_nearest_tc(const float* x, const void* x_hi, const float* row_alpha, const float* embed,
                        const void* e_hi, const float* e2, int32_t* cand, int64_t* indices, float* quantized,
                        int64_t n_tok, int n_codes, int d, int64_t ld, void* stream);
+/* Antialiased bilinear resize of n_planes planes (ih, iw) -> (oh, ow) fp32: the `crop` step of the reference's loader
+ * (dataset.py:59-73, torchvision Resize(antialias=True) on a float tensor = F.interpolate(mode="bilinear",
+ * antialias=True, align_corners=False)).  _u8: 8-bit input pixels read as u / 255. */
+int dcta_resize_bilinear_aa(const float* in, float* out, int64_t n_planes, int ih, int iw, int oh, int ow, void* stream);
+int dcta_resize_bilinear_aa_u8(const uint8_t* in, float* out, int64_t n_planes, int ih, int iw, int oh, int ow, void* stream);
+
 /* VectorQuantize codebook learning (VQ:180-220 k-means, VQ:479-500 EMA update).
  *   dcta_vq_cluster_stats: counts (n_codes) = tokens per code, sums (n_codes, d) = sum of their vectors, over the
  *     tokens with mask[t] != 0 (mask uint8, nullable); both outputs are zeroed first (reduce-ready: all-reduce them
