@@ -455,8 +455,11 @@ def test_vq_golden(D, golden):
     rows = ok.all(-1)
     np.testing.assert_allclose(npy(q)[rows], g["b_q"][rows], atol=1e-5)
     assert "_codebook.embed" in v.state_dict()
+    # training of the EMA codebook is covered by tests/test_gpu_vq_train.py; the variants that are not implemented refuse
     with pytest.raises(NotImplementedError):
-        v.train()(cu(g["a_x"]))
+        D.VectorQuantize(dim=8, codebook_size=16, affine_param=True)
+    with pytest.raises(NotImplementedError):
+        D.VectorQuantize(dim=8, codebook_size=16, learnable_codebook=True, ema_update=False)
 
 
 @pytest.mark.parametrize("T,C,d", [(1000, 512, 64), (300, 8192, 256), (129, 100, 7)])

@@ -18,12 +18,13 @@ def main():
     ap.add_argument("--dct-impl", default="tc")
     ap.add_argument("--staged", action="store_true", help="the drop-in modules one by one instead of the fused step")
     ap.add_argument("--width", type=int, default=0, help="image width (default: --size)")
+    ap.add_argument("--max-seq-len", type=int, default=3072)
     ap.add_argument("--launches", action="store_true", help="print the library's per-launch CUDA-event times of one step")
     a = ap.parse_args()
     import torch
     import dct_autoencoder_b200 as D
     dev = torch.device("cuda", 0)
-    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, 3072, dct_impl=a.dct_impl)
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 0.0, 32, 32, a.max_seq_len, dct_impl=a.dct_impl)
     pn = D.PatchNorm(32, 32, 14, 3).to(dev)
     lfq = D.LFQ(codebook_size=2 ** 14, num_codebooks=14).to(dev).eval()
     pipe = D.TransformPipeline(fe, pn, lfq)
