@@ -368,7 +368,10 @@ class DCTAutoencoderFeatureExtractor:
     def _lfq_fusable(self, norm, lfq) -> bool:
         """Projection-free LFQ in eval mode on frozen (or eval) fp32 PatchNorm tables that were built for
         this extractor's token geometry."""
+        # keep_num_codebooks_dim False (a single codebook): the staged module returns (rows, s) indices, the fused kernels
+        # (rows, s, 1) -- not fused, so that the output shape never depends on which path ran
         return (getattr(lfq, "has_projections", True) is False and not lfq.training
+                and getattr(lfq, "keep_num_codebooks_dim", True)
                 and (norm.frozen or not norm.training)
                 and norm.channels == self.channels and norm.patch_size == self.patch_size
                 and lfq.num_codebooks * lfq.codebook_dim == norm.patch_size ** 2 <= 256
