@@ -918,24 +918,38 @@ extern "C" int dcta_lfq_project_sign(const void* a_hi, const void* a_lo, int64_t
 // sign_bits of dcta_lfq_project_sign -> indices (rows, c) int64, MSB first within a codebook (lfq.py:87, 187)
 __global__ void __launch_bounds__(256) lfq_bits_to_codes_kernel(const uint32_t* __restrict__ bits, int64_t rows, int n_tiles,
                                                                 int c, int d, int64_t* __restrict__ codes) {
-    const int64_t total = rows * c;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t m = i / c;
-        const int cb = (int)(i - m * c);
-        const uint32_t* row = bits + m * n_tiles * 4;
-        int64_t code = 0;
-        for (int b = 0; b < d; ++b) {
-            const int col = cb * d + b, t = col >> 7, r = col & 127;
-            code = (code << 1) | ((__ldg(row + t * 4 + (r & 3)) >> (r >> 2)) & 1u);
+    // one thread per token: its sign words (at most 8 tiles x 4 words) in registers, then every codebook's bits
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < rows; m += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t w[32];
+        const uint4* row = reinterpret_cast<const uint4*>(bits + m * n_tiles * 4);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            if (t < n_tiles) {
+                const uint4 v = __ldg(row + t);
+                w[4 * t] = v.x; w[4 * t + 1] = v.y; w[4 * t + 2] = v.z; w[4 * t + 3] = v.w;
+            }
         }
-        codes[i] = code;
+        int col = 0;
+        for (int cb = 0; cb < c; ++cb) {
+            int64_t code = 0;
+            for (int b = 0; b < d; ++b, ++col) {
+                // w[(col >> 7) * 4 + (col & 3)] without a dynamically indexed register array: select over the tiles
+                const int j = col & 3, L = (col >> 2) & 31, t = col >> 7;
+                uint32_t word = 0;
+#pragma unroll
+                for (int tt = 0; tt < 8; ++tt)
+                    if (tt == t) word = j == 0 ? w[4 * tt] : (j == 1 ? w[4 * tt + 1] : (j == 2 ? w[4 * tt + 2] : w[4 * tt + 3]));
+                code = (code << 1) | ((word >> L) & 1u);
+            }
+            codes[m * c + cb] = code;
+        }
     }
 }
 
 extern "C" int dcta_lfq_bits_to_codes(const uint32_t* sign_bits, int64_t rows, int n, int c, int d, int64_t* codes, void* stream) {
-    DCTA_REQUIRE(sign_bits && codes && c > 0 && d > 0 && d <= 62 && c * d == n, "lfq_bits_to_codes: bad args");
+    DCTA_REQUIRE(sign_bits && codes && c > 0 && d > 0 && d <= 62 && c * d == n && n <= 1024, "lfq_bits_to_codes: bad args");
     if (rows == 0) return DCTA_OK;
-    lfq_bits_to_codes_kernel<<<grid_for(rows * c, 256), 256, 0, as_stream(stream)>>>(sign_bits, rows, (int)ceil_div(n, TN), c, d, codes);
+    lfq_bits_to_codes_kernel<<<grid_for(rows, 256), 256, 0, as_stream(stream)>>>(sign_bits, rows, (int)ceil_div(n, TN), c, d, codes);
     return check_launch("lfq_bits_to_codes");
 }
 

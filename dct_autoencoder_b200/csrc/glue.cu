@@ -171,6 +171,78 @@ __global__ void __launch_bounds__(256) split_rows_rowscale_kernel(const float* _
     }
 }
 
+// The same with the row held in registers: d a multiple of 4 and at most 128 * CH (CH float4 per lane), 16-byte aligned
+// rows; one pass over global memory, 128-bit loads, 64-bit stores of four halves per plane.
+template <int CH>
+__global__ void __launch_bounds__(256) split_rows_rowscale_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta, float eps,
+                                                                      __half* __restrict__ hi, __half* __restrict__ lo,
+                                                                      float* __restrict__ row_scale, float post, int64_t n_rows,
+                                                                      int d, int64_t ld) {
+    const int lane = threadIdx.x & 31;
+    const int d4 = d >> 2, ld4 = (int)(ld >> 2);
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = warp0; t < n_rows; t += n_warps) {
+        const float4* src = reinterpret_cast<const float4*>(x + t * d);
+        float4 v[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int i = lane + 32 * c;
+            v[c] = i < d4 ? ld_stream(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (gamma != nullptr) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+            const float mean = warp_sum(s) / (float)d;
+            float q = 0.f;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                if (lane + 32 * c < d4) {
+                    const float e0 = v[c].x - mean, e1 = v[c].y - mean, e2 = v[c].z - mean, e3 = v[c].w - mean;
+                    q += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+                }
+            }
+            const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int i = lane + 32 * c;
+                if (i < d4) {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i), b = __ldg(reinterpret_cast<const float4*>(beta) + i);
+                    v[c].x = fmaf((v[c].x - mean) * rstd, g.x, b.x);
+                    v[c].y = fmaf((v[c].y - mean) * rstd, g.y, b.y);
+                    v[c].z = fmaf((v[c].z - mean) * rstd, g.z, b.z);
+                    v[c].w = fmaf((v[c].w - mean) * rstd, g.w, b.w);
+                }
+            }
+        }
+        float amax = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[c].x), fabsf(v[c].y)), fmaxf(fabsf(v[c].z), fabsf(v[c].w))));
+        amax = warp_max(amax);
+        int e = 0;
+        if (amax > 0.f && amax < 3.0e38f) { (void)frexpf(amax, &e); e = 10 - e; }
+        e = max(-100, min(100, e));
+        const float s_row = ldexpf(1.0f, e);
+        if (lane == 0) row_scale[t] = post * ldexpf(1.0f, -e);
+        uint2* dh = reinterpret_cast<uint2*>(hi + t * ld);
+        uint2* dl = lo ? reinterpret_cast<uint2*>(lo + t * ld) : nullptr;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int i = lane + 32 * c;
+            if (i >= ld4) continue;
+            const float a[4] = {v[c].x * s_row, v[c].y * s_row, v[c].z * s_row, v[c].w * s_row};      // zero past d
+            const __half2 h01 = __floats2half2_rn(a[0], a[1]), h23 = __floats2half2_rn(a[2], a[3]);
+            dh[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            if (dl) {
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(a[0] - f01.x, a[1] - f01.y), l23 = __floats2half2_rn(a[2] - f23.x, a[3] - f23.y);
+                dl[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            }
+        }
+    }
+}
+
 }  // namespace dcta
 
 extern "C" int dcta_ln_pos_rows(const float* x, const float* gamma, const float* beta, float eps, const float* bias,
@@ -204,7 +276,22 @@ extern "C" int dcta_split_rows_rowscale(const float* x, const float* gamma, cons
     DCTA_REQUIRE(x && hi && row_scale && n_rows >= 0 && d > 0 && ld >= d && ld % 8 == 0, "split_rows_rowscale: bad arguments");
     DCTA_REQUIRE((gamma == nullptr) == (beta == nullptr), "split_rows_rowscale: gamma and beta go together");
     if (n_rows == 0) return DCTA_OK;
-    split_rows_rowscale_kernel<<<grid_for(n_rows, 8), 256, 0, as_stream(stream)>>>(x, gamma, beta, eps, (__half*)hi, (__half*)lo,
-                                                                                  row_scale, post, n_rows, d, ld);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0;
+    const int ch = (int)((ld / 4 + 31) / 32);          // float4 per lane (the zero padding up to ld included)
+    cudaStream_t st = as_stream(stream);
+    const int grid = grid_for(n_rows, 8);
+#define DCTA_SPLIT_CASE(N)                                                                                                  \
+    case N: split_rows_rowscale_vec_kernel<N><<<grid, 256, 0, st>>>(x, gamma, beta, eps, (__half*)hi, (__half*)lo, row_scale, \
+                                                                     post, n_rows, d, ld); break;
+    if (d % 4 == 0 && aligned && ch >= 1 && ch <= 8) {
+        switch (ch) {
+            DCTA_SPLIT_CASE(1) DCTA_SPLIT_CASE(2) DCTA_SPLIT_CASE(3) DCTA_SPLIT_CASE(4)
+            DCTA_SPLIT_CASE(5) DCTA_SPLIT_CASE(6) DCTA_SPLIT_CASE(7) DCTA_SPLIT_CASE(8)
+        }
+    } else {
+        split_rows_rowscale_kernel<<<grid, 256, 0, st>>>(x, gamma, beta, eps, (__half*)hi, (__half*)lo, row_scale, post, n_rows, d, ld);
+    }
+#undef DCTA_SPLIT_CASE
     return check_launch("split_rows_rowscale");
 }
