@@ -417,3 +417,34 @@ def test_basis_init_matches_the_float64_definition(D, n, k):
         assert np.abs(got - want).max() <= 2.0 ** -21 * np.abs(c).max()
     assert lib.dcta_basis_elems(99, n, k) == -1
     assert lib.dcta_basis_init(L.BASIS_F32, 8, 9, f32.ctypes.data, None, None) == -1      # k > n
+
+
+def test_loader_host_logic(tmp_path):
+    """dataset.py host side (no GPU): torchvision's smaller-edge rule, shard URL expansion, webdataset sample grouping."""
+    import io
+    import json
+    import tarfile
+    from torchvision import transforms
+    from dct_autoencoder_b200 import dataset as DS
+    for h, w, size in [(900, 1300, 531), (1300, 900, 531), (1000, 1000, 768), (769, 40, 39), (333, 1001, 255)]:
+        want = tuple(transforms.Resize(size)(torch.zeros(1, h, w)).shape[-2:])
+        assert DS._resize_smaller_edge(h, w, size) == want, (h, w, size)
+    assert DS.expand_urls("a/s-{0008..0011}.tar") == ["a/s-0008.tar", "a/s-0009.tar", "a/s-0010.tar", "a/s-0011.tar"]
+    path = os.path.join(tmp_path, "x-0000.tar")
+    with tarfile.open(path, "w") as tf:
+        for key, members in (("dir/aaa", {"jpg": b"J1", "json": json.dumps({"height": 5, "width": 6}).encode(), "txt": b"t"}),
+                             ("dir/bbb", {"jpeg": b"J2", "json": b"{}"})):
+            for ext, data in members.items():
+                ti = tarfile.TarInfo(f"{key}.{ext}")
+                ti.size = len(data)
+                tf.addfile(ti, io.BytesIO(data))
+    got = list(DS.iter_tar_samples(os.path.join(tmp_path, "x-*.tar")))
+    assert [g["__key__"] for g in got] == ["dir/aaa", "dir/bbb"]
+    assert got[0]["jpg"] == b"J1" and json.loads(got[0]["json"])["width"] == 6 and "txt" not in got[0]
+    assert got[1]["jpeg"] == b"J2"
+    assert DS.dict_collate([{"a": 1, "b": 2}, {"a": 3, "b": 4}]) == {"a": [1, 3], "b": [2, 4]}
+    assert DS.tuple_collate([(1, 2), (3, 4)]) == [[1, 3], [2, 4]]
+    fe_like = type("P", (), dict(patch_size=14, max_patch_w=32, max_patch_h=32))()
+    assert DS.max_image_size(fe_like) == 768
+    with pytest.raises(Exception):
+        DS.decode_jpegs([b"x"], "cpu")          # the loader delivers to the GPU: no CPU product path
