@@ -373,9 +373,9 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
                 const int s = it % PSTAGES;
                 mbar_wait(&empty_bar[s], ((it / PSTAGES) & 1) ^ 1);
                 uint8_t* st = smem + s * Cfg::kStage;
-                mbar_expect_tx(&full_bar[s], Cfg::kStage);
+                mbar_expect_tx(&full_bar[s], ep.a_lo_zero ? Cfg::kStage - TILE_BYTES : Cfg::kStage);
                 tma_load_3d(&map_a_hi, &full_bar[s], st, kb * TK, tm * TM, ab);
-                tma_load_3d(&map_a_lo, &full_bar[s], st + TILE_BYTES, kb * TK, tm * TM, ab);
+                if (!ep.a_lo_zero) tma_load_3d(&map_a_lo, &full_bar[s], st + TILE_BYTES, kb * TK, tm * TM, ab);
                 tma_load_3d(&map_b_hi, &full_bar[s], st + 2 * TILE_BYTES, kb * TK, tn * TNP, bb);
                 tma_load_3d(&map_b_lo, &full_bar[s], st + 2 * TILE_BYTES + Cfg::kBTile, kb * TK, tn * TNP, bb);
             }
@@ -400,8 +400,12 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
                     const uint64_t a_lo = smem_desc_sw64(base + TILE_BYTES + ko);
                     const uint64_t b_hi = smem_desc_sw64(base + 2 * TILE_BYTES + ko);
                     const uint64_t b_lo = smem_desc_sw64(base + 2 * TILE_BYTES + Cfg::kBTile + ko);
-                    umma_f16(tmem_acc, a_lo, b_hi, Cfg::kIdesc, (kb | k) ? 1u : 0u);
-                    umma_f16(tmem_acc, a_hi, b_lo, Cfg::kIdesc, 1u);
+                    if (ep.a_lo_zero) {
+                        umma_f16(tmem_acc, a_hi, b_lo, Cfg::kIdesc, (kb | k) ? 1u : 0u);
+                    } else {
+                        umma_f16(tmem_acc, a_lo, b_hi, Cfg::kIdesc, (kb | k) ? 1u : 0u);
+                        umma_f16(tmem_acc, a_hi, b_lo, Cfg::kIdesc, 1u);
+                    }
                     umma_f16(tmem_acc, a_hi, b_hi, Cfg::kIdesc, 1u);
                 }
                 umma_commit(&empty_bar[s]);
@@ -497,15 +501,44 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
                 } else {
                     plane_off = (int64_t)batch * ep.batch_stride + n;
                 }
+                float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (ep.col_bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (j < n_valid) bias4[j] = __ldg(ep.col_bias + n + j);
+                }
                 for (int rr_ = 0; rr_ < 32; ++rr_) {
                     const int m = m0 + quarter * 32 + rr_;
                     if (m >= ep.M) break;
-                    if (n_valid <= 0) continue;
+                    if (n_valid <= 0 && ep.mode != 5) continue;
                     float4 v;
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                                  : "r"(stage + (uint32_t)(rr_ * EPI_PITCH + lane * 4) * 4));
                     if (ep.dc_mode == 2) { v.x += dcv; v.y += dcv; v.z += dcv; v.w += dcv; }
                     else if (ep.dc_mode == 1 && m == 0 && n == 0) v.x += dcv;
+                    v.x += bias4[0]; v.y += bias4[1]; v.z += bias4[2]; v.w += bias4[3];
+                    if (ep.mode == 5) {
+                        // LFQ sign + ballots of one 128-column half (a single N tile: n0 == 0), see gemm_split_kernel
+                        const float a[4] = {v.x, v.y, v.z, v.w};
+                        __half h[4];
+                        uint32_t bal[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool pos = j < n_valid && a[j] > 0.0f;
+                            h[j] = __float2half_rn(pos ? ep.lfq_scale : -ep.lfq_scale);
+                            bal[j] = __ballot_sync(0xffffffffu, pos);
+                        }
+                        if (lane < 4 && cbeg < ep.N) ep.sign_bits[((int64_t)m * ((ep.N + 127) >> 7) + half) * 4 + lane] = bal[lane];
+                        if (n_valid > 0) {
+                            const int64_t o = plane_off + (int64_t)m * ep.ld;
+                            if (n_valid >= 4) {
+                                *reinterpret_cast<uint2*>(ep.out_hi + o) = *reinterpret_cast<const uint2*>(h);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) if (j < n_valid) ep.out_hi[o + j] = h[j];
+                            }
+                        }
+                        continue;
+                    }
                     if (ep.mode == 0) {
                         float* dst = ep.out_f32 + plane_off + (int64_t)m * ep.ld;
                         if (n_valid >= 4 && (ep.ld & 3) == 0) {
@@ -892,6 +925,9 @@ extern "C" int dcta_gemm_split(const void* a_hi, const void* a_lo, int a_rows, i
     ep.mode = 0; ep.out_f32 = out; ep.ld = out_ld; ep.batch_stride = out_batch_stride;
     ep.row_scale = row_scale; ep.alpha = alpha; ep.M = a_rows; ep.N = b_rows;
     ep.col_bias = col_bias; ep.a_lo_zero = a_lo == nullptr;
+    if (batch == 1 && b_rows <= 256 && a_rows >= 4096)          // tall-skinny linear layer: one N tile, persistent kernel
+        return b_rows <= 224 ? launch_gemm_persistent<224>(A, B, k, batch, ep, stream)
+                             : launch_gemm_persistent<256>(A, B, k, batch, ep, stream);
     return launch_gemm_split(A, B, k, batch, ep, stream);
 }
 
@@ -912,44 +948,33 @@ extern "C" int dcta_lfq_project_sign(const void* a_hi, const void* a_lo, int64_t
     ep.mode = 5; ep.out_hi = (__half*)q_hi; ep.ld = q_ld; ep.batch_stride = 0;
     ep.row_scale = row_scale; ep.alpha = 1.0f; ep.M = (int)rows; ep.N = n;
     ep.col_bias = bias; ep.sign_bits = sign_bits; ep.lfq_scale = codebook_scale;
+    // one N tile: the persistent kernel reads the tokens once and overlaps its epilogue with the next tile
+    if (n <= 224) return launch_gemm_persistent<224>(A, B, k, 1, ep, stream);
+    if (n <= 256) return launch_gemm_persistent<256>(A, B, k, 1, ep, stream);
     return launch_gemm_split(A, B, k, 1, ep, stream);
 }
 
 // sign_bits of dcta_lfq_project_sign -> indices (rows, c) int64, MSB first within a codebook (lfq.py:87, 187)
 __global__ void __launch_bounds__(256) lfq_bits_to_codes_kernel(const uint32_t* __restrict__ bits, int64_t rows, int n_tiles,
                                                                 int c, int d, int64_t* __restrict__ codes) {
-    // one thread per token: its sign words (at most 8 tiles x 4 words) in registers, then every codebook's bits
-    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < rows; m += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t w[32];
-        const uint4* row = reinterpret_cast<const uint4*>(bits + m * n_tiles * 4);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            if (t < n_tiles) {
-                const uint4 v = __ldg(row + t);
-                w[4 * t] = v.x; w[4 * t + 1] = v.y; w[4 * t + 2] = v.z; w[4 * t + 3] = v.w;
-            }
+    const int64_t total = rows * c;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / c;
+        const int cb = (int)(i - m * c);
+        const uint32_t* row = bits + m * n_tiles * 4;
+        int64_t code = 0;
+        for (int b = 0; b < d; ++b) {
+            const int col = cb * d + b, t = col >> 7, r = col & 127;
+            code = (code << 1) | ((__ldg(row + t * 4 + (r & 3)) >> (r >> 2)) & 1u);
         }
-        int col = 0;
-        for (int cb = 0; cb < c; ++cb) {
-            int64_t code = 0;
-            for (int b = 0; b < d; ++b, ++col) {
-                // w[(col >> 7) * 4 + (col & 3)] without a dynamically indexed register array: select over the tiles
-                const int j = col & 3, L = (col >> 2) & 31, t = col >> 7;
-                uint32_t word = 0;
-#pragma unroll
-                for (int tt = 0; tt < 8; ++tt)
-                    if (tt == t) word = j == 0 ? w[4 * tt] : (j == 1 ? w[4 * tt + 1] : (j == 2 ? w[4 * tt + 2] : w[4 * tt + 3]));
-                code = (code << 1) | ((word >> L) & 1u);
-            }
-            codes[m * c + cb] = code;
-        }
+        codes[i] = code;
     }
 }
 
 extern "C" int dcta_lfq_bits_to_codes(const uint32_t* sign_bits, int64_t rows, int n, int c, int d, int64_t* codes, void* stream) {
     DCTA_REQUIRE(sign_bits && codes && c > 0 && d > 0 && d <= 62 && c * d == n && n <= 1024, "lfq_bits_to_codes: bad args");
     if (rows == 0) return DCTA_OK;
-    lfq_bits_to_codes_kernel<<<grid_for(rows, 256), 256, 0, as_stream(stream)>>>(sign_bits, rows, (int)ceil_div(n, TN), c, d, codes);
+    lfq_bits_to_codes_kernel<<<grid_for(rows * c, 256), 256, 0, as_stream(stream)>>>(sign_bits, rows, (int)ceil_div(n, TN), c, d, codes);
     return check_launch("lfq_bits_to_codes");
 }
 
