@@ -69,6 +69,8 @@ SIGNATURES = {
     "dcta_decode_codes_inv_fold_supported": [c_int, c_int, c_int, c_int, c_int, c_int, c_int],
     "dcta_decode_codes_inv_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                    P, P, c_int, c_int, c_float, c_int, c_int, c_float, P, P, P, P, P, P, P, P, P, P, P],
+    "dcta_decode_grid_inv_fold": [P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_float, c_float,
+                                  P, P, P, P, P, P, P, P, P, P, P],
     "dcta_decode_gen_tables_bytes": [c_int, c_int, c_int],
     "dcta_decode_gen_tables": [P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_float, P, P],
     "dcta_fold_coef_planes": [P, P, P, P, c_int64, c_int, c_int, c_int, c_int, P],
@@ -139,7 +141,7 @@ KERNELS_PER_CALL = {
     "dcta_row_sumsq": 1, "dcta_vq_nearest_tc": 2, "dcta_vq_cluster_stats": 1, "dcta_resize_bilinear_aa": 1, "dcta_resize_bilinear_aa_u8": 1, "dcta_vq_ema_update": 2, "dcta_vq_kmeans_means": 1,
     "dcta_pack_codes_lfq": 2, "dcta_decode_codes_split": 1,
     "dcta_fold_supported": 0, "dcta_fold_codes_supported": 0, "dcta_rgb_to_ipt_fold": 2, "dcta_rgb_u8_to_ipt_fold": 2, "dcta_unfold_ipt_to_rgb_u8": 1, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
-    "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 2, "dcta_decode_codes_inv_fold": 3, "dcta_decode_gen_tables": 1, "dcta_decode_gen_tables_bytes": 0,
+    "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 2, "dcta_decode_codes_inv_fold": 3, "dcta_decode_grid_inv_fold": 3, "dcta_decode_gen_tables": 1, "dcta_decode_gen_tables_bytes": 0,
     "dcta_decode_codes_inv_fold_scratch_bytes": 0, "dcta_decode_codes_inv_fold_supported": 0, "dcta_fold_coef_planes": 1, "dcta_dct2_inv_fold": 2,
     "dcta_unfold_ipt_to_rgb": 1, "dcta_unfold_planes": 1, "dcta_sort_tokens_maxabs": 1, "dcta_dct2_fwd_fold_codes": 3, "dcta_pack_codes_grid": 2,
 }

@@ -1888,6 +1888,72 @@ __global__ void __launch_bounds__(256, 8) codes_bitplanes_kernel(const int64_t* 
     }
 }
 
+// The same bit planes straight from the CODE GRID the forward pass wrote (code words in token-grid order,
+// (n_img, th, tw, C, p) int32), for a round trip that kept every token: no slot map, no gather through the packed codes.
+template <int HW>
+__global__ void __launch_bounds__(256, 8) codes_bitplanes_grid_kernel(const int32_t* __restrict__ grid, int64_t n_img, int C, int th,
+                                                                      int tw, int rows, int cols, int n_iblk, int num_kb, int n_grp,
+                                                                      LfqNormParams q, uint16_t* __restrict__ bv,
+                                                                      float* __restrict__ dc, float dc_factor) {
+    extern __shared__ __align__(16) uint16_t stage[];          // [b][a][kb][32 rows][4]
+    constexpr int p = 2 * HW;
+    const int64_t plane = blockIdx.x;
+    const int iblk = blockIdx.y;
+    const int blk_words = num_kb * 128;
+    if (iblk * 64 + 64 > rows)
+        for (int e = threadIdx.x; e < blk_words / 2; e += blockDim.x) reinterpret_cast<uint4*>(stage)[e] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const int64_t img = plane / C;
+    const int ch = (int)(plane - img * C);
+    const int n_tx = min(tw, cols / p);
+    for (int t = threadIdx.x; t < 64 * n_grp; t += blockDim.x) {
+        const int rr = t / n_grp, G = t - rr * n_grp;
+        const int kh = iblk * 64 + rr;
+        if (kh >= rows) continue;
+        const int ty = kh / p, py = kh - ty * p;
+        const int32_t* row = grid + (((img * th + ty) * tw) * C + ch) * (int64_t)p + py;      // + tx * C * p
+        uint32_t words[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) words[u] = G * 8 + u < n_tx ? (uint32_t)__ldg(row + (int64_t)(G * 8 + u) * C * p) : 0u;
+        uint64_t s0 = 0, s1 = 0, sv = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (G * 8 + u < n_tx) {
+                const uint32_t r = __brev(words[u]) >> (32 - p);
+                const uint32_t f = compress_even_bits2x16((r & 0xffffu) | ((r >> 1) << 16));
+                s0 |= (uint64_t)(f & 0xffffu) << (HW * u);
+                s1 |= (uint64_t)(f >> 16) << (HW * u);
+                sv |= (uint64_t)((1u << HW) - 1u) << (HW * u);
+            }
+        }
+        if (kh == 0 && G == 0) {
+            const int64_t el = (((int64_t)ch * q.H) * q.W) * q.z;
+            const float sd = __fadd_rn(__fmul_rn(__ldg(q.b + el), kSqrt2f), q.eps);
+            const float qv = (s0 & 1u) ? q.scale : -q.scale;
+            dc[plane] = __fadd_rn(__fmul_rn(qv, sd), __ldg(q.median + el)) * dc_factor;
+        }
+        const int a = rr & 1, il = rr >> 1;
+#pragma unroll
+        for (int m = 0; m < HW; ++m) {
+            const int jb = G * HW + m;
+            if (jb < num_kb * 4) {
+                const uint32_t vb = (uint32_t)(sv >> (8 * m)) & 0xffu;
+                const int o = a * blk_words + (jb >> 2) * 128 + il * 4 + (jb & 3);
+                stage[o] = (uint16_t)(((uint32_t)(s0 >> (8 * m)) & 0xffu) | (vb << 8));
+                stage[o + 2 * blk_words] = (uint16_t)(((uint32_t)(s1 >> (8 * m)) & 0xffu) | (vb << 8));
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t n_grp4 = (n_img + 3) >> 2;
+    for (int e = threadIdx.x; e < 4 * num_kb * 16; e += blockDim.x) {
+        const int v = e & 15, kb = (e >> 4) % num_kb, ba = (e >> 4) / num_kb;
+        uint4* dst = reinterpret_cast<uint4*>(bv + ((((((int64_t)ba * n_grp4 + (img >> 2)) * C + ch) * n_iblk + iblk) * num_kb + kb) * 4 +
+                                                    (img & 3)) * 128) + v;
+        *dst = reinterpret_cast<const uint4*>(stage)[e];
+    }
+}
+
 // fp32 coefficient planes (n_planes, kh, kw) -> folded split quadrants (DC moved to dc[])
 __global__ void __launch_bounds__(256) fold_coef_kernel(const float* __restrict__ y, __half* __restrict__ hi,
                                                         __half* __restrict__ lo, float* __restrict__ dc,
@@ -2175,14 +2241,13 @@ extern "C" int dcta_decode_codes_inv_fold_supported(int h, int w, int kh, int kw
     return fold_geometry(fold_half(w), kw / 2, g, 0, F_GEN_STAGES * F_GEN_STAGE) && fold_geometry(fold_half(h), kh / 2, g);
 }
 
-extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
-                                          int channels_n, int th, int tw, int p, int kh, int kw, int h, int w,
-                                          const float* median, const float* b, int H, int W, float eps, int c, int d,
-                                          float scale, const void* bwt_hi, const void* bwt_lo, const void* bht_hi,
-                                          const void* bht_lo, void* work_hi, void* work_lo, float* z, float* dc,
-                                          const void* tab_in, void* scratch, void* stream) {
-    DCTA_REQUIRE(codes && slot_map && median && b && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo && z && dc &&
-                 tab_in && scratch, "decode_codes_inv_fold: null pointer");
+static int decode_inv_fold_impl(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel, const int32_t* code_grid,
+                                int64_t n_img, int channels_n, int th, int tw, int p, int kh, int kw, int h, int w,
+                                const float* median, const float* b, int H, int W, float eps, int c, int d, float scale,
+                                const void* bwt_hi, const void* bwt_lo, const void* bht_hi, const void* bht_lo, void* work_hi,
+                                void* work_lo, float* z, float* dc, const void* tab_in, void* scratch, void* stream) {
+    DCTA_REQUIRE((code_grid || (codes && slot_map)) && median && b && bwt_hi && bwt_lo && bht_hi && bht_lo && work_hi && work_lo &&
+                 z && dc && tab_in && scratch, "decode_codes_inv_fold: null pointer");
     DCTA_REQUIRE(dcta_decode_codes_inv_fold_supported(h, w, kh, kw, p, c, d),
                  "decode_codes_inv_fold: needs one LFQ codebook per patch row (c == d == p, p even in 8..16), even kh <= h, kw <= w");
     DCTA_REQUIRE(th <= H && tw <= W && kh / p <= H && kw / p <= W && n_img * channels_n < (1 << 24),
@@ -2208,13 +2273,27 @@ extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* s
 #define DCTA_BITPLANES(HW)                                                                                                   \
     codes_bitplanes_kernel<HW><<<grid, threads, stage_bytes, as_stream(stream)>>>(codes, slot_map, img_sel, n_img, channels_n, th, \
                                                                                   tw, kh, kw, n_iblk, num_kb, n_grp, q, bv, dc, dcf)
-        switch (p / 2) {
-            case 4: DCTA_BITPLANES(4); break;
-            case 5: DCTA_BITPLANES(5); break;
-            case 6: DCTA_BITPLANES(6); break;
-            case 7: DCTA_BITPLANES(7); break;
-            default: DCTA_BITPLANES(8); break;
+#define DCTA_BITPLANES_GRID(HW)                                                                                              \
+    codes_bitplanes_grid_kernel<HW><<<grid, threads, stage_bytes, as_stream(stream)>>>(code_grid, n_img, channels_n, th, tw, kh, \
+                                                                                       kw, n_iblk, num_kb, n_grp, q, bv, dc, dcf)
+        if (code_grid) {
+            switch (p / 2) {
+                case 4: DCTA_BITPLANES_GRID(4); break;
+                case 5: DCTA_BITPLANES_GRID(5); break;
+                case 6: DCTA_BITPLANES_GRID(6); break;
+                case 7: DCTA_BITPLANES_GRID(7); break;
+                default: DCTA_BITPLANES_GRID(8); break;
+            }
+        } else {
+            switch (p / 2) {
+                case 4: DCTA_BITPLANES(4); break;
+                case 5: DCTA_BITPLANES(5); break;
+                case 6: DCTA_BITPLANES(6); break;
+                case 7: DCTA_BITPLANES(7); break;
+                default: DCTA_BITPLANES(8); break;
+            }
         }
+#undef DCTA_BITPLANES_GRID
 #undef DCTA_BITPLANES
     }
     int rc = check_launch("decode_codes_inv_fold (bit planes)");
@@ -2243,6 +2322,29 @@ extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* s
     e2.col_mul = 1; e2.col_add = 0; e2.col_stride = w2;
     e2.alpha = 1.0f / (kFScaleBasis * kFScaleQ);
     return launch_fold_gemm(A2, n_planes * (int64_t)w2, 4, B2, h2, kh2, e2, stream);
+}
+
+extern "C" int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
+                                          int channels_n, int th, int tw, int p, int kh, int kw, int h, int w,
+                                          const float* median, const float* b, int H, int W, float eps, int c, int d,
+                                          float scale, const void* bwt_hi, const void* bwt_lo, const void* bht_hi,
+                                          const void* bht_lo, void* work_hi, void* work_lo, float* z, float* dc,
+                                          const void* tab_in, void* scratch, void* stream) {
+    DCTA_REQUIRE(codes && slot_map, "decode_codes_inv_fold: null pointer");
+    return decode_inv_fold_impl(codes, slot_map, img_sel, nullptr, n_img, channels_n, th, tw, p, kh, kw, h, w, median, b, H, W, eps,
+                                c, d, scale, bwt_hi, bwt_lo, bht_hi, bht_lo, work_hi, work_lo, z, dc, tab_in, scratch, stream);
+}
+
+// The same from the code grid of dcta_dct2_fwd_fold_codes (every token kept: a round trip without a top-k cut)
+extern "C" int dcta_decode_grid_inv_fold(const int32_t* code_grid, int64_t n_img, int channels_n, int p, int kh, int kw, int h,
+                                         int w, const float* median, const float* b, int H, int W, float eps, float scale,
+                                         const void* bwt_hi, const void* bwt_lo, const void* bht_hi, const void* bht_lo,
+                                         void* work_hi, void* work_lo, float* z, float* dc, const void* tab_in, void* scratch,
+                                         void* stream) {
+    DCTA_REQUIRE(code_grid && p > 0 && kh % p == 0 && kw % p == 0, "decode_grid_inv_fold: bad arguments");
+    return decode_inv_fold_impl(nullptr, nullptr, nullptr, code_grid, n_img, channels_n, kh / p, kw / p, p, kh, kw, h, w, median, b,
+                                H, W, eps, p, p, scale, bwt_hi, bwt_lo, bht_hi, bht_lo, work_hi, work_lo, z, dc, tab_in, scratch,
+                                stream);
 }
 
 template <typename TOut>

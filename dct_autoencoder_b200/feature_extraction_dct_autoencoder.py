@@ -379,10 +379,13 @@ class DCTAutoencoderFeatureExtractor:
                 and norm.b.dtype == torch.float32 and norm.b.device == norm.median.device)
 
     @torch.no_grad()
-    def process_batch_to_codes(self, images: torch.Tensor, norm, lfq, ks: Optional[Sequence[int]] = None):
+    def process_batch_to_codes(self, images: torch.Tensor, norm, lfq, ks: Optional[Sequence[int]] = None,
+                               return_grid: bool = False):
         """``process_batch`` -> ``norm(batch)`` -> ``lfq(., mask)`` with the three intermediate patch
         tensors kept in registers (csrc/fused_lfq.cu).  Returns (DCTPatches with ``patches=None``,
-        codes (rows, s, codebooks) int64), bit-identical to the staged calls."""
+        codes (rows, s, codebooks) int64), bit-identical to the staged calls.
+        ``return_grid``: also return the code grid (b, th, tw, c, p) int32 the forward pass wrote when EVERY token of every
+        image was kept (else None): ``postprocess_codes_batch(..., code_grid=)`` then decodes without a slot map."""
         assert self._lfq_fusable(norm, lfq)
         x = to_device_pixels(images, self._dev(images), keep_u8=True)     # uint8 pixels stay bytes until the colour kernel
         if norm.median.device != x.device:
@@ -443,10 +446,13 @@ class DCTAutoencoderFeatureExtractor:
                            _data={}, _row_num_images=[len(r) for r in rows])
         if not lfq.keep_num_codebooks_dim:       # lfq.py:224-225: a single codebook loses its axis
             codes = codes[..., 0]
+        if return_grid:
+            return batch, codes, (code_grid if in_epilogue and all(k == n_tok for k in ks) else None)
         return batch, codes
 
     @torch.no_grad()
-    def postprocess_codes_batch(self, x: DCTPatches, codes: torch.Tensor, norm, lfq, out_dtype=torch.float32) -> torch.Tensor:
+    def postprocess_codes_batch(self, x: DCTPatches, codes: torch.Tensor, norm, lfq, out_dtype=torch.float32,
+                                code_grid: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``lfq.indices_to_codes`` -> ``norm.inverse_norm`` -> ``postprocess_batch`` with the
         de-quantised patches kept in registers; same-size batches, tensor-core DCT path.
         ``out_dtype=torch.uint8``: 8-bit pixels, quantised like torchvision's save_image (util.unit_to_u8)."""
@@ -456,7 +462,8 @@ class DCTAutoencoderFeatureExtractor:
             codes = codes[..., None]
         if norm.median.device != codes.device:
             raise _lib.DctaError(f"PatchNorm tables live on {norm.median.device}, the codes on {codes.device}")
-        (idx, rgb), = self._decode_groups(x, codes=codes.contiguous(), norm=norm, lfq=lfq, out_dtype=out_dtype)
+        (idx, rgb), = self._decode_groups(x, codes=codes.contiguous(), norm=norm, lfq=lfq, out_dtype=out_dtype,
+                                          code_grid=code_grid)
         return rgb
 
     def _group_patches_by_max_seq_len(self, batched_patches, batched_positions=None,
@@ -623,7 +630,7 @@ class DCTAutoencoderFeatureExtractor:
         return res
 
     def _decode_groups(self, x: DCTPatches, codes: Optional[torch.Tensor] = None, norm=None, lfq=None,
-                       out_dtype=torch.float32):
+                       out_dtype=torch.float32, code_grid: Optional[torch.Tensor] = None):
         """Token rows -> RGB, one kernel sequence per group of images that share (tile grid,
         original size).  Yields (image indices, rgb (n, c, h, w)).  The zero padding of FE:300-304
         is implicit in the truncated inverse basis.  With ``codes`` the tokens are de-quantised and
@@ -639,6 +646,19 @@ class DCTAutoencoderFeatureExtractor:
             dev = codes.device
         tiles = [(min(int(a), self.max_patch_h), min(int(b), self.max_patch_w)) for a, b in x.patch_sizes]
         th, tw = max(a for a, _ in tiles), max(b for _, b in tiles)
+        if code_grid is not None:
+            # a same-size batch that kept every token, straight from the forward pass's code grid (roundtrip): the sign
+            # bits are read in grid order, no slot map
+            gh, gw = tiles[0]
+            h, w = (int(v) for v in x.original_sizes[0])
+            n, kh, kw = len(tiles), gh * p, gw * p
+            if (self.dct_impl == "tc" and C == 3 and self.decode_in_gemm and len(set(tiles)) == 1
+                    and len(set(map(tuple, x.original_sizes))) == 1 and tuple(code_grid.shape) == (n, gh, gw, C, p)
+                    and decode_codes_inv_fold_ok(h, w, kh, kw, p, lfq.num_codebooks, lfq.codebook_dim)):
+                z, dc = decode_codes_inv_fold(None, None, None, n, C, gh, gw, p, kh, kw, h, w, norm, lfq.num_codebooks,
+                                              lfq.codebook_dim, lfq.codebook_scale, code_grid=code_grid)
+                yield list(range(n)), unfold_ipt_to_rgb(z, dc, h, w, out_dtype)
+                return
         slot_map, n_img = self._slot_map(x, th, tw)
         assert n_img == len(tiles), f"{n_img} images in the rows but {len(tiles)} patch_sizes"
         groups: Dict[Tuple[int, int, int, int], List[int]] = {}

@@ -111,8 +111,18 @@ class TransformPipeline:
         if not fused:
             rec, codes = self.roundtrip_staged(images, ks)
             return (rec if out_dtype == torch.float32 else unit_to_u8(rec)), codes
-        batch, codes = self.encode_codes(images, ks)
-        return self.decode_codes(batch, codes, out_dtype), codes
+        batch, codes, rec = self._fused_roundtrip(images, ks, out_dtype)
+        return rec, codes
+
+    def _fused_roundtrip(self, images, ks, out_dtype):
+        """encode_codes + decode_codes; the decode of a batch that kept every token reads the sign bits straight from the
+        forward pass's code grid (no slot map, no gather through the packed codes; same pixels)."""
+        batch, codes, grid = self.extractor.process_batch_to_codes(images, self.norm, self.quantizer, ks, return_grid=True)
+        if grid is not None:
+            rec = self.extractor.postprocess_codes_batch(batch, codes, self.norm, self.quantizer, out_dtype, code_grid=grid)
+        else:
+            rec = self.decode_codes(batch, codes, out_dtype)
+        return batch, codes, rec
 
     def graphed(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None, fused: Optional[bool] = None):
         """``roundtrip`` of a fixed-shape device batch captured once in a CUDA graph; see GraphedRoundtrip."""
@@ -156,8 +166,10 @@ class TransformPipeline:
                 ev_in = s_in.record_event()
             main.wait_event(ev_in)
             x.record_stream(main)
-            batch, codes = self.encode_codes(x)
-            rec = self.decode_codes(batch, codes, out_dtype)
+            batch, codes, rec = self._fused_roundtrip(x, None, out_dtype) if self.fusable() else (None, None, None)
+            if batch is None:
+                batch, codes = self.encode_codes(x)
+                rec = self.decode_codes(batch, codes, out_dtype)
             assert codes.shape[0] == x.shape[0], "roundtrip_host needs one image per row (k == max_seq_len)"
             counts = None
             if compact:

@@ -678,12 +678,14 @@ def decode_codes_inv_fold_ok(h: int, w: int, kh: int, kw: int, p: int, c: int, d
 
 
 def decode_codes_inv_fold(codes, slot_map, sel, n_img: int, channels: int, th: int, tw: int, p: int, kh: int, kw: int,
-                          h: int, w: int, norm, c: int, d: int, scale: float):
+                          h: int, w: int, norm, c: int, d: int, scale: float, code_grid=None):
     """LFQ codes -> quadrant transforms z (4, n_img*channels, h/2, w/2) + dc (n_img*channels): de-quantisation,
     inverse PatchNorm and un-patchify (lfq.py:105-134, patchnorm.py:167-177, FE:607-656) happen in the operand
     producer of inverse pass 1 (``dcta_decode_codes_inv_fold``); the coefficient planes are never written.
-    The two-value table is a function of the PatchNorm statistics: built once per state of ``norm``."""
-    dev = codes.device
+    The two-value table is a function of the PatchNorm statistics: built once per state of ``norm``.
+    ``code_grid``: the (n_img, kh/p, kw/p, channels, p) int32 code grid of ``dct2_fwd_fold_codes`` for a batch that kept
+    every token -- the sign bits are then read from it directly (no slot map, no gather through ``codes``)."""
+    dev = codes.device if codes is not None else code_grid.device
     n_planes = n_img * channels
     lib = _lib.load()
     bwt_hi, bwt_lo, _ = fold_basis(w, kw, dev, True)
@@ -706,10 +708,17 @@ def decode_codes_inv_fold(codes, slot_map, sel, n_img: int, channels: int, th: i
 
     tab = norm.derived(("decode_tab", str(dev), channels, p, kh, kw, float(scale)), build_table)
     with torch.cuda.device(dev):
-        _lib.call("dcta_decode_codes_inv_fold", _lib.ptr(codes), _lib.ptr(slot_map), _lib.ptr(sel), n_img, channels, th, tw,
-                  p, kh, kw, h, w, _lib.ptr(median), _lib.ptr(b), H, W, eps, c, d, float(scale), _lib.ptr(bwt_hi),
-                  _lib.ptr(bwt_lo), _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z),
-                  _lib.ptr(dc), _lib.ptr(tab), _lib.ptr(scratch), _lib.stream_ptr(dev))
+        if code_grid is not None:
+            assert tuple(code_grid.shape) == (n_img, kh // p, kw // p, channels, p) and code_grid.dtype == torch.int32
+            _lib.call("dcta_decode_grid_inv_fold", _lib.ptr(code_grid), n_img, channels, p, kh, kw, h, w, _lib.ptr(median),
+                      _lib.ptr(b), H, W, eps, float(scale), _lib.ptr(bwt_hi), _lib.ptr(bwt_lo), _lib.ptr(bht_hi),
+                      _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z), _lib.ptr(dc), _lib.ptr(tab),
+                      _lib.ptr(scratch), _lib.stream_ptr(dev))
+        else:
+            _lib.call("dcta_decode_codes_inv_fold", _lib.ptr(codes), _lib.ptr(slot_map), _lib.ptr(sel), n_img, channels, th, tw,
+                      p, kh, kw, h, w, _lib.ptr(median), _lib.ptr(b), H, W, eps, c, d, float(scale), _lib.ptr(bwt_hi),
+                      _lib.ptr(bwt_lo), _lib.ptr(bht_hi), _lib.ptr(bht_lo), _lib.ptr(work_hi), _lib.ptr(work_lo), _lib.ptr(z),
+                      _lib.ptr(dc), _lib.ptr(tab), _lib.ptr(scratch), _lib.stream_ptr(dev))
     return z, dc
 
 

@@ -238,6 +238,13 @@ int dcta_decode_codes_inv_fold(const int64_t* codes, const int32_t* slot_map, co
                                float scale, const void* bwt_hi, const void* bwt_lo, const void* bht_hi,
                                const void* bht_lo, void* work_hi, void* work_lo, float* z, float* dc,
                                const void* tab, void* scratch, void* stream);
+/* The same straight from the code grid dcta_dct2_fwd_fold_codes wrote ((n_img, kh/p, kw/p, channels, p) int32), for a
+ * round trip that kept every token: no slot map and no gather through the packed codes.  Same results. */
+int dcta_decode_grid_inv_fold(const int32_t* code_grid, int64_t n_img, int channels_n, int p, int kh, int kw, int h,
+                              int w, const float* median, const float* b, int H, int W, float eps, float scale,
+                              const void* bwt_hi, const void* bwt_lo, const void* bht_hi, const void* bht_lo,
+                              void* work_hi, void* work_lo, float* z, float* dc, const void* tab, void* scratch,
+                              void* stream);
 /* fp32 coefficient planes y (n_planes, kh, kw) -> folded quadrants. */
 int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, float* dc, int64_t n_planes, int kh,
                           int kw, int out_h, int out_w, void* stream);

@@ -330,3 +330,14 @@ def test_decode_inside_inverse_pass1_is_bit_identical(D, size, max_seq_len, n, b
     assert torch.isfinite(rec_gen).all()
     assert torch.equal(rec_gen, rec_sep)
     assert torch.equal(rec_gen_u8, rec_sep_u8)
+    # roundtrip(): when every token was kept the decode reads the forward pass's code grid (dcta_decode_grid_inv_fold)
+    fe.decode_in_gemm = True
+    random.seed(5)
+    l0 = D._lib.launch_count
+    rec_rt, codes_rt = pipe.roundtrip(x)
+    n_launch = D._lib.launch_count - l0
+    random.seed(5)
+    batch2, codes2 = pipe.encode_codes(x)
+    assert torch.equal(codes_rt, codes2) and torch.equal(rec_rt, pipe.decode_codes(batch2, codes2))
+    kept_all = beta == 0.0 and max_seq_len >= (min(h // 14, 32) * min(w // 14, 32) * 3)
+    assert n_launch == (11 if kept_all else 12), n_launch       # no slot-map kernel on the grid path
