@@ -53,7 +53,6 @@ class PatchNorm(nn.Module):
         # a tame divisor" flag): keyed by what they depend on, dropped whenever the statistics change
         self._derived = {}
         self._stats_version = 0
-        self._no_cache = False       # GraphedRoundtrip: derive inside the captured step, so that replays follow the tables
 
     def invalidate_derived(self):
         """Forget everything derived from the statistics.  Called by every path of this module that changes them
@@ -64,8 +63,6 @@ class PatchNorm(nn.Module):
 
     def derived(self, key, build):
         """``build()`` once per ``key`` and state of the statistics (tensor identity and version counters)."""
-        if self._no_cache:
-            return build()
         full = (key, self._stats_version, self.median.data_ptr(), self.b.data_ptr(), self.median._version, self.b._version)
         hit = self._derived.get(full)
         if hit is None:

@@ -202,8 +202,9 @@ class GraphedRoundtrip:
     call, which a graph replay removes (one driver call per step, no allocator traffic, launch gaps of a
     microsecond).  The graph reads ``images`` in place (the tensor given at capture time) and writes the
     same two output tensors on every replay; call it with another tensor of the same shape to have it
-    copied in first.  PatchNorm tables and the quantiser are read through their device pointers, so
-    in-place updates of their values are seen by later replays.  Only for a fixed token count per image
+    copied in first.  The captured kernels read tables derived from the PatchNorm statistics (decode tables, the
+    tame-divisor flag) that were built at capture time: after the statistics change (fitting, ``load_state_dict``,
+    ``.to()``, ``invalidate_derived()``) a replay raises -- build a new graph.  Only for a fixed token count per image
     (``sample_patches_beta == 0`` or explicit ``ks``): the packing tables are part of the capture."""
 
     def __init__(self, pipe: "TransformPipeline", images: torch.Tensor, ks: Optional[Sequence[int]] = None,
@@ -222,9 +223,6 @@ class GraphedRoundtrip:
         fe = pipe.extractor
         saved, fe._keepalive = fe._keepalive, []
         norm = pipe.norm
-        saved_nc = getattr(norm, "_no_cache", False)
-        if hasattr(norm, "_no_cache"):
-            norm._no_cache = True       # what is derived from the statistics is recomputed inside the captured step
         try:
             with torch.cuda.stream(side):          # warm caches (tables, tensor maps, function attributes)
                 for _ in range(warmup):
@@ -235,14 +233,18 @@ class GraphedRoundtrip:
             with torch.cuda.graph(self.graph):
                 self.rec, self.codes = pipe.roundtrip(images, ks, fused)
             self._tables = list(fe._keepalive)
+            # what the kernels read of the statistics' derived tables: kept alive here, valid while the statistics are
+            self._derived = list(getattr(norm, "_derived", {}).values())
+            self._stats_version = getattr(norm, "_stats_version", None)
         finally:
             fe._keepalive = saved
-            if hasattr(norm, "_no_cache"):
-                norm._no_cache = saved_nc
         self.launches = _lib.launch_count - l0     # kernels per replay
         self._lib = _lib
 
     def __call__(self, images: Optional[torch.Tensor] = None):
+        if getattr(self.pipe.norm, "_stats_version", None) != self._stats_version:
+            raise RuntimeError("the PatchNorm statistics changed since this graph was captured: its decode tables are stale; "
+                               "capture a new one (TransformPipeline.graphed)")
         if images is not None and images.data_ptr() != self.images.data_ptr():
             assert images.shape == self.images.shape
             self.images.copy_(images)

@@ -225,6 +225,14 @@ def test_graphed_roundtrip_replays_the_eager_step(D):
     gs = pipe.graphed(x, fused=False)
     r4, c4 = gs()
     assert torch.equal(r4, want_rec) and torch.equal(c4, want_codes)
+    # the captured kernels read tables derived from the statistics: after a re-fit a replay must refuse, a new graph works
+    pipe.fit_norm(torch.rand(4, 3, 256, 256).cuda())
+    with pytest.raises(RuntimeError):
+        g()
+    g2 = pipe.graphed(x)
+    r5, c5 = g2()
+    w5, wc5 = pipe.roundtrip(x)
+    assert torch.equal(r5, w5) and torch.equal(c5, wc5) and not torch.equal(r5, want_rec)
 
 
 def test_config2_full_batch_properties(D):
