@@ -296,6 +296,39 @@ def fit_norm_timed(ctx, pipe, fit_x, steps=10):
     return out
 
 
+def link_bandwidth(ctx, nbytes=256 << 20, reps=4):
+    """Pinned-memory copy rates of this box (GB/s): host->device alone, device->host alone, and per direction with
+    both running -- the denominator of `e2e` (boxes of the pool differ by 3x here, the kernels do not)."""
+    torch = ctx.torch
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=ctx.dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=ctx.dev)
+    s1, s2 = torch.cuda.Stream(ctx.dev), torch.cuda.Stream(ctx.dev)
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+
+    def rate(fns):
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for f in fns:
+                f()
+        torch.cuda.synchronize()
+        return nbytes * reps / (time.perf_counter() - t0) / 1e9
+
+    out = dict(h2d_GBps=rate([h2d]), d2h_GBps=rate([d2h]), both_GBps_per_direction=rate([h2d, d2h]))
+    return {k: round(v, 2) for k, v in out.items()}
+
+
 def e2e_host(ctx, pipe, x, steps, chunk):
     """End to end through the public host API (TransformPipeline.roundtrip_host): pinned host buffers in, pinned host
     buffers out, copies inside the timed region.  Returns (fp32-contract dict, compact-mode dict)."""
@@ -303,6 +336,7 @@ def e2e_host(ctx, pipe, x, steps, chunk):
     B = x.shape[0]
     old_affinity = os.sched_getaffinity(0)
     numa_bound = D.util.bind_to_gpu_numa(ctx.dev)      # pinned buffers live on the allocating thread's NUMA node
+    link = link_bandwidth(ctx)
     hx = torch.empty(tuple(x.shape), dtype=torch.float32).pin_memory()
     hx.copy_(x)
     h_rec = torch.empty(tuple(x.shape), dtype=torch.float32).pin_memory()
@@ -312,6 +346,9 @@ def e2e_host(ctx, pipe, x, steps, chunk):
     fp32 = dict(value=ctx.world * B * steps / (ms / 1e3), unit=UNIT, h2d_bytes_per_step=hx.numel() * 4 * ctx.world,
                 d2h_bytes_per_step=(h_rec.numel() * 4 + h_codes.numel() * 8) * ctx.world, ms_per_step=ms / steps,
                 contract="the reference's types: fp32 images in, fp32 images + int64 codes out")
+    # the floor the link of THIS box sets for those bytes (both directions busy at once), and how close the step is
+    floor_ms = max(hx.numel() * 4, h_rec.numel() * 4 + h_codes.numel() * 8) / (link["both_GBps_per_direction"] * 1e6)
+    fp32.update(link=link, link_floor_ms=floor_ms, frac_of_link_floor=floor_ms / (ms / steps))
     # compact: the same computation with 8-bit pixels on both sides of the link and the codes as wire records
     hx8 = (hx * 255).round().to(torch.uint8).pin_memory()
     h_rec8 = torch.empty(tuple(x.shape), dtype=torch.uint8).pin_memory()

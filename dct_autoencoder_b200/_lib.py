@@ -207,6 +207,15 @@ def host_floats(values):
     return (c_float * len(vals))(*vals)
 
 
+_profile_depth = 0
+
+
+def profile_active() -> bool:
+    """True inside a ``profile`` block: per-launch times are differences of events on ONE stream, so callers that
+    would spread their launches over two streams keep them on one meanwhile."""
+    return _profile_depth > 0
+
+
 class profile:
     """``with _lib.profile(device) as p: ...`` -> ``p.groups``: [(launch group name, device ms)] of every libdcta launch
     group inside the block, from CUDA events recorded by the library on the launching stream (dcta_profile_begin / _end)."""
@@ -216,10 +225,14 @@ class profile:
         self.groups = []
 
     def __enter__(self):
+        global _profile_depth
+        _profile_depth += 1
         load().dcta_profile_begin(stream_ptr(self.device))
         return self
 
     def __exit__(self, *exc):
+        global _profile_depth
+        _profile_depth -= 1
         cap, n_max = 1 << 16, 4096
         names = ctypes.create_string_buffer(cap)
         ms = (c_float * n_max)()

@@ -1087,51 +1087,79 @@ __device__ __forceinline__ void butterfly4(float p1, float p2, float p3, float p
     q[3] = d12 - d34;   // b = 1, a = 1
 }
 
+// fp16 hi/lo halves of four values that already carry their scale
+__device__ __forceinline__ void split16x4_scaled(const float (&v)[4], uint2& hi, uint2& lo) {
+    const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(v[0] - f01.x, v[1] - f01.y), l23 = __floats2half2_rn(v[2] - f23.x, v[3] - f23.y);
+    hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+
+// rgb_px_to_ipt_f with the operand scale and the centring folded in: Bs = scale * B (a power of two: exact) and
+// nmu[c] = -scale * mu[c] enter the last matrix product, so no instruction is spent on either.
+__device__ __forceinline__ void rgb_px_to_ipt_centred(float r, float g, float b, const Mat3& A, const Mat3& Bs,
+                                                      const float (&nmu)[3], float& o0, float& o1, float& o2) {
+    float l = fmaf(A.m[2], b, fmaf(A.m[1], g, A.m[0] * r));
+    float m = fmaf(A.m[5], b, fmaf(A.m[4], g, A.m[3] * r));
+    float s = fmaf(A.m[8], b, fmaf(A.m[7], g, A.m[6] * r));
+    l = signed_pow_fwd<false>(l, 0.43f);
+    m = signed_pow_fwd<false>(m, 0.43f);
+    s = signed_pow_fwd<false>(s, 0.43f);
+    o0 = fmaf(Bs.m[2], s, fmaf(Bs.m[1], m, fmaf(Bs.m[0], l, nmu[0])));
+    o1 = fmaf(Bs.m[5], s, fmaf(Bs.m[4], m, fmaf(Bs.m[3], l, nmu[1])));
+    o2 = fmaf(Bs.m[8], s, fmaf(Bs.m[7], m, fmaf(Bs.m[6], l, nmu[2])));
+}
+
 // util.py:70-82 rgb_to_ipt fused with centring, the 2-D fold and the fp16 hi/lo split:
 // xq[b][a][plane][h'][w'], plane = img * 3 + c.  One thread = 4 consecutive w' of one (img, h').
+// The kernel is bound by instruction issue before HBM (48 pow per thread), so everything that is not colour math is
+// kept off the per-pixel path: scale and centring live in the matrix (Bs, nmu), offsets inside an image are 32-bit.
 template <typename TIn>       // float in [0, 1], or uint8 (read as u8 / 255)
-__global__ void __launch_bounds__(256) rgb_to_ipt_fold_kernel(const TIn* __restrict__ rgb, const float* __restrict__ mus,
+__global__ void __launch_bounds__(256, 4) rgb_to_ipt_fold_kernel(const TIn* __restrict__ rgb, const float* __restrict__ mus,
                                                               __half* __restrict__ hi, __half* __restrict__ lo,
-                                                              int64_t n_img, int h, int w, Mat3 A, Mat3 B, float scale) {
-    const int h2 = h >> 1, w8 = w >> 3;                 // w8: float4 groups of the half row
-    const int64_t total = n_img * h2 * w8;
-    const int64_t plane4 = (int64_t)h * w / 4, q4 = (int64_t)h2 * (w >> 1) / 4;   // in float4 / uint2 units
-    const int64_t n_planes = n_img * 3;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int xv = (int)(i % w8);
-        const int64_t t = i / w8;
-        const int y = (int)(t % h2);
-        const int64_t img = t / h2;
-        const TIn* src = rgb + img * 3 * plane4 * 4;
-        const int64_t top = (int64_t)y * (w >> 2), bot = (int64_t)(h - 1 - y) * (w >> 2);
-        const int xl = xv, xr = (w >> 2) - 1 - xv;
+                                                              int64_t n_img, int h, int w, Mat3 A, Mat3 Bs, float scale) {
+    const int h2 = h >> 1, w8 = w >> 3, w4 = w >> 2;    // w8: float4 groups of the half row
+    const uint32_t plane4 = (uint32_t)h * w4, q4 = (uint32_t)h2 * w8;             // in float4 / uint2 units
+    const int64_t quad = n_img * 3 * (int64_t)q4;                                 // one quadrant of all planes
+    // grid: (blocks per image, images) -- one item per thread, 32-bit index arithmetic inside an image
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item < q4) {
+        const int y = (int)(item / (uint32_t)w8);
+        const int xv = (int)(item - (uint32_t)y * w8);
+        const int64_t img = blockIdx.y;
+        const TIn* src = rgb + img * 3 * (int64_t)plane4 * 4;
+        const float nmu[3] = {-scale * __ldg(mus + img * 3), -scale * __ldg(mus + img * 3 + 1), -scale * __ldg(mus + img * 3 + 2)};
+        const uint32_t top = (uint32_t)y * w4, bot = (uint32_t)(h - 1 - y) * w4;
+        const uint32_t xl = xv, xr = w4 - 1 - xv;
         float ipt[4][3][4];          // [corner: top-left, top-right, bottom-left, bottom-right][channel][pixel]
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int64_t o = ((k & 2) ? bot : top) + ((k & 1) ? xr : xl);
+            const uint32_t o = ((k & 2) ? bot : top) + ((k & 1) ? xr : xl);
             const float4 c0 = ld_px4(src, o), c1 = ld_px4(src, plane4 + o), c2 = ld_px4(src, 2 * plane4 + o);
             const float r[4] = {c0.x, c0.y, c0.z, c0.w}, gg[4] = {c1.x, c1.y, c1.z, c1.w}, bb[4] = {c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rgb_px_to_ipt_f(r[j], gg[j], bb[j], A, B, ipt[k][0][j], ipt[k][1][j], ipt[k][2][j]);
+            for (int j = 0; j < 4; ++j)
+                rgb_px_to_ipt_centred(r[j], gg[j], bb[j], A, Bs, nmu, ipt[k][0][j], ipt[k][1][j], ipt[k][2][j]);
         }
+        uint2* ph = reinterpret_cast<uint2*>(hi) + ((img * 3 * h2 + y) * (int64_t)w8 + xv);
+        uint2* pl = reinterpret_cast<uint2*>(lo) + ((img * 3 * h2 + y) * (int64_t)w8 + xv);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float mu = __ldg(mus + img * 3 + c);
             float q[4][4];           // [quadrant][pixel]
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float qq[4];
-                butterfly4(ipt[0][c][j] - mu, ipt[1][c][3 - j] - mu, ipt[2][c][j] - mu, ipt[3][c][3 - j] - mu, qq);
+                butterfly4(ipt[0][c][j], ipt[1][c][3 - j], ipt[2][c][j], ipt[3][c][3 - j], qq);
 #pragma unroll
                 for (int s = 0; s < 4; ++s) q[s][j] = qq[s];
             }
-            const int64_t o = ((img * 3 + c) * h2 + y) * (int64_t)(w >> 3) + xv;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 uint2 vh, vl;
-                split16x4(q[s], scale, vh, vl);
-                reinterpret_cast<uint2*>(hi)[s * n_planes * q4 + o] = vh;
-                reinterpret_cast<uint2*>(lo)[s * n_planes * q4 + o] = vl;
+                split16x4_scaled(q[s], vh, vl);
+                ph[s * quad + c * q4] = vh;
+                pl[s * quad + c * q4] = vl;
             }
         }
     }
@@ -2017,8 +2045,10 @@ static int rgb_to_ipt_fold_any(const TIn* rgb, void* xq_hi, void* xq_lo, float* 
         const float* mus;
         if constexpr (sizeof(TIn) == 1) mus = launch_ipt_plane_means_u8(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
         else mus = launch_ipt_plane_means(rgb, sums_scratch, dc, n_img, h, w, A, B, st);
-        rgb_to_ipt_fold_kernel<TIn><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, st>>>(
-            rgb, mus, (__half*)xq_hi, (__half*)xq_lo, n_img, h, w, A, B, kFScaleX);
+        Mat3 Bs;                                       // the operand scale (a power of two) folded into the matrix
+        for (int i = 0; i < 9; ++i) Bs.m[i] = B.m[i] * kFScaleX;
+        rgb_to_ipt_fold_kernel<TIn><<<dim3((unsigned)ceil_div((int64_t)(h / 2) * (w / 8), 256), (unsigned)n_img), 256, 0, st>>>(
+            rgb, mus, (__half*)xq_hi, (__half*)xq_lo, n_img, h, w, A, Bs, kFScaleX);
     } else {            // any size: scalar kernels, quadrant rows padded to 8 elements
         float* mus = sums_scratch;
         means_any_kernel<TIn, true><<<(unsigned)n_img, 256, 0, st>>>(rgb, mus, dc, (int64_t)h * w, A, B, sqrtf((float)h * (float)w));

@@ -13,6 +13,7 @@ Additions that the reference does not have (its API is per-image):
 ``postprocess_batch``.  They produce exactly what the per-image path followed by
 ``iter_batches(batch_size=None)`` / ``postprocess`` produces.
 """
+import contextlib
 from collections import OrderedDict
 from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
@@ -380,12 +381,15 @@ class DCTAutoencoderFeatureExtractor:
 
     @torch.no_grad()
     def process_batch_to_codes(self, images: torch.Tensor, norm, lfq, ks: Optional[Sequence[int]] = None,
-                               return_grid: bool = False):
+                               return_grid: bool = False, pack_stream: Optional["torch.cuda.Stream"] = None):
         """``process_batch`` -> ``norm(batch)`` -> ``lfq(., mask)`` with the three intermediate patch
         tensors kept in registers (csrc/fused_lfq.cu).  Returns (DCTPatches with ``patches=None``,
         codes (rows, s, codebooks) int64), bit-identical to the staged calls.
         ``return_grid``: also return the code grid (b, th, tw, c, p) int32 the forward pass wrote when EVERY token of every
-        image was kept (else None): ``postprocess_codes_batch(..., code_grid=)`` then decodes without a slot map."""
+        image was kept (else None): ``postprocess_codes_batch(..., code_grid=)`` then decodes without a slot map.
+        ``pack_stream``: when every token was kept, the sort and the gather into the packed API tensors are launched on
+        that stream (the decode that follows only needs the code grid, so both run beside it); the caller MUST call
+        ``join_pack()`` on the stream it uses before touching ``codes`` or the batch's tensors."""
         assert self._lfq_fusable(norm, lfq)
         x = to_device_pixels(images, self._dev(images), keep_u8=True)     # uint8 pixels stay bytes until the colour kernel
         if norm.median.device != x.device:
@@ -403,11 +407,6 @@ class DCTAutoencoderFeatureExtractor:
             hi, lo, dc = rgb_to_ipt_fold(x)
             maxabs, code_grid = dct2_fwd_fold_codes(hi, lo, dc, th * p, tw * p, p, c, norm, hw=(h, w))
             del hi, lo
-            order = torch.empty((b, n_tok), dtype=torch.int32, device=x.device)
-            imp = _lib.host_floats(self.channel_importances.tolist()[:c] + [1.0] * max(0, c - len(self.channel_importances)))
-            with torch.cuda.device(x.device):
-                _lib.call("dcta_sort_tokens_maxabs", _lib.ptr(maxabs), None, _lib.ptr(order), b, th, tw, c,
-                          float(self.patch_sample_magnitude_weight), imp, _lib.stream_ptr(x.device))
         else:
             if x.dtype == torch.uint8:
                 x = to_device_pixels(x)
@@ -416,6 +415,7 @@ class DCTAutoencoderFeatureExtractor:
         if ks is None:
             ks = [self._choose_k(n_tok) for _ in range(b)]
         ks = self._check_ks(ks, b, n_tok)
+        all_kept = in_epilogue and all(k == n_tok for k in ks)
         state = self._next_fit(ks)
         rows = state.rows + ([state.row] if state.row else [])
         tab, offs = self._tables(rows, dict(enumerate(ks)), x.device)
@@ -425,9 +425,20 @@ class DCTAutoencoderFeatureExtractor:
         chan = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
         ids = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
         pad = torch.empty((n_rows, s), dtype=torch.bool, device=x.device)
-        with torch.cuda.device(x.device):
+        if in_epilogue:
+            order = torch.empty((b, n_tok), dtype=torch.int32, device=x.device)
+            pad_codes = torch.empty(lfq.num_codebooks, dtype=torch.int64, device=x.device)
+        # Every tensor above is allocated on the caller's stream; with a pack stream only the LAUNCHES of the
+        # sort and the gather move over, after an event on the caller's stream, and everything they touch stays
+        # referenced until join_pack() -- so no block can be handed out again while the side stream still uses it.
+        side = pack_stream if (pack_stream is not None and all_kept and not _lib.profile_active()) else None
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.device(x.device), (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
             if in_epilogue:
-                pad_codes = torch.empty(lfq.num_codebooks, dtype=torch.int64, device=x.device)
+                imp = _lib.host_floats(self.channel_importances.tolist()[:c] + [1.0] * max(0, c - len(self.channel_importances)))
+                _lib.call("dcta_sort_tokens_maxabs", _lib.ptr(maxabs), None, _lib.ptr(order), b, th, tw, c,
+                          float(self.patch_sample_magnitude_weight), imp, _lib.stream_ptr(x.device))
                 _lib.call("dcta_pack_codes_grid", _lib.ptr(code_grid), _lib.ptr(order), tab.data_ptr() + offs[0],
                           tab.data_ptr() + offs[1], n_rows, s, th, tw, c, _lib.ptr(norm.median.data), _lib.ptr(norm.b.data),
                           norm.max_patch_h, norm.max_patch_w, float(norm.eps), float(norm.min_val), float(norm.max_val),
@@ -441,14 +452,24 @@ class DCTAutoencoderFeatureExtractor:
                           float(norm.eps), float(norm.min_val), float(norm.max_val), lfq.num_codebooks,
                           lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(tame), _lib.ptr(codes), _lib.ptr(pos),
                           _lib.ptr(chan), _lib.ptr(ids), _lib.ptr(pad), _lib.stream_ptr(x.device))
+        if side is not None:
+            self._pack_pending = (side, x.device, [maxabs, code_grid, order, pad_codes, tab, codes, pos, chan, ids, pad])
         batch = DCTPatches(patches=None, key_pad_mask=pad, batched_image_ids=ids, patch_channels=chan,
                            patch_positions=pos, patch_sizes=[(ph, pw)] * b, original_sizes=[(h, w)] * b,
                            _data={}, _row_num_images=[len(r) for r in rows])
         if not lfq.keep_num_codebooks_dim:       # lfq.py:224-225: a single codebook loses its axis
             codes = codes[..., 0]
         if return_grid:
-            return batch, codes, (code_grid if in_epilogue and all(k == n_tok for k in ks) else None)
+            return batch, codes, (code_grid if all_kept else None)
         return batch, codes
+
+    def join_pack(self):
+        """Make the current stream wait for the sort + gather a ``process_batch_to_codes(pack_stream=)`` call left on its
+        side stream, and release what that work was reading."""
+        pending, self._pack_pending = getattr(self, "_pack_pending", None), None
+        if pending is not None:
+            side, dev, _keep = pending
+            torch.cuda.current_stream(dev).wait_stream(side)
 
     @torch.no_grad()
     def postprocess_codes_batch(self, x: DCTPatches, codes: torch.Tensor, norm, lfq, out_dtype=torch.float32,
@@ -659,6 +680,7 @@ class DCTAutoencoderFeatureExtractor:
                                               lfq.codebook_dim, lfq.codebook_scale, code_grid=code_grid)
                 yield list(range(n)), unfold_ipt_to_rgb(z, dc, h, w, out_dtype)
                 return
+        self.join_pack()          # everything below reads the packed tensors (a no-op unless a pack stream is in use)
         slot_map, n_img = self._slot_map(x, th, tw)
         assert n_img == len(tiles), f"{n_img} images in the rows but {len(tiles)} patch_sizes"
         groups: Dict[Tuple[int, int, int, int], List[int]] = {}

@@ -204,6 +204,37 @@ def test_codes_in_the_dct_epilogue_for_other_tile_sizes(D, patch, size, max_seq_
     assert torch.equal(pipe.decode_codes(batch_f, codes_f), rec_s)
 
 
+def test_pack_on_the_side_stream_changes_nothing(D):
+    """The fused round trip launches the sort and the gather into the packed tensors on a second stream when every token
+    was kept (the decode only needs the code grid): results, metadata and repeated steps are those of one stream."""
+    torch.manual_seed(11)
+    pipe = _pipe(D, "tc")
+    assert pipe.overlap_pack
+    pipe.fit_norm(torch.rand(4, 3, 512, 512).cuda())
+    xs = [torch.rand(12, 3, 512, 512).cuda() for _ in range(3)]
+    pipe.overlap_pack = False
+    want = []
+    for x in xs:
+        batch, codes, rec = pipe._fused_roundtrip(x, None, torch.float32)
+        want.append((rec.clone(), codes.clone(), batch.patch_positions.clone(), batch.patch_channels.clone(),
+                     batch.batched_image_ids.clone(), batch.key_pad_mask.clone()))
+    pipe.overlap_pack = True
+    for rep in range(3):               # back-to-back steps recycle the allocator's blocks: a missing join shows up here
+        got = [pipe._fused_roundtrip(x, None, torch.float32) for x in xs]
+        torch.cuda.synchronize()
+        for (batch, codes, rec), w in zip(got, want):
+            assert torch.equal(rec, w[0]) and torch.equal(codes, w[1])
+            assert torch.equal(batch.patch_positions, w[2]) and torch.equal(batch.patch_channels, w[3])
+            assert torch.equal(batch.batched_image_ids, w[4]) and torch.equal(batch.key_pad_mask, w[5])
+    assert getattr(pipe.extractor, "_pack_pending", None) is None
+    # a top-k cut needs the packed codes for the decode: nothing is moved to the side stream, same results either way
+    ks = [2000] * 12
+    r1, c1 = pipe.roundtrip(xs[0], ks)
+    pipe.overlap_pack = False
+    r2, c2 = pipe.roundtrip(xs[0], ks)
+    assert torch.equal(r1, r2) and torch.equal(c1, c2)
+
+
 def test_graphed_roundtrip_replays_the_eager_step(D):
     torch.manual_seed(4)
     pipe = _pipe(D, "tc")
