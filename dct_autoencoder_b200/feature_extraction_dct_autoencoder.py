@@ -14,6 +14,8 @@ Additions that the reference does not have (its API is per-image):
 ``iter_batches(batch_size=None)`` / ``postprocess`` produces.
 """
 import contextlib
+import json
+import os
 from collections import OrderedDict
 from typing import Any, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
@@ -81,6 +83,53 @@ class DCTAutoencoderFeatureExtractor:
         # decode from codes: generate the operand of inverse pass 1 in shared memory (no coefficient planes in HBM);
         # False = the separate decode kernel followed by the plain inverse (tests compare the two bit for bit)
         self.decode_in_gemm = True
+
+    # ------------------------------------------------------------------ save / load
+    # The reference inherits transformers' FeatureExtractionMixin (FE:80); this class keeps that surface for the
+    # constructor arguments without importing transformers: the same `preprocessor_config.json` (sorted keys, indent 2,
+    # "feature_extractor_type"), readable by either side.
+    _CONFIG_NAME = "preprocessor_config.json"
+    _CONFIG_KEYS = ("channels", "patch_size", "sample_patches_beta", "max_patch_h", "max_patch_w", "max_seq_len",
+                    "channel_importances", "patch_sample_magnitude_weight", "dct_impl")
+
+    def to_dict(self) -> Dict[str, Any]:
+        out = {k: getattr(self, k) for k in self._CONFIG_KEYS}
+        out["channel_importances"] = [float(v) for v in self.channel_importances.tolist()]
+        out["feature_extractor_type"] = "DCTAutoencoderFeatureExtractor"
+        return out
+
+    def to_json_string(self) -> str:
+        return json.dumps(self.to_dict(), indent=2, sort_keys=True) + "\n"
+
+    def save_pretrained(self, save_directory, **kwargs):
+        os.makedirs(save_directory, exist_ok=True)
+        path = os.path.join(save_directory, self._CONFIG_NAME)
+        with open(path, "w", encoding="utf-8") as f:
+            f.write(self.to_json_string())
+        return [path]
+
+    @classmethod
+    def from_dict(cls, config: Dict[str, Any], **kwargs):
+        cfg = {k: v for k, v in dict(config, **kwargs).items() if k in cls._CONFIG_KEYS or k == "device"}
+        missing = [k for k in cls._CONFIG_KEYS[:6] if k not in cfg]
+        if missing:
+            raise ValueError(f"feature extractor config lacks {missing}")
+        if "channel_importances" in cfg:
+            cfg["channel_importances"] = tuple(float(v) for v in cfg["channel_importances"])
+        return cls(**cfg)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, **kwargs):
+        path = str(pretrained_model_name_or_path)
+        if os.path.isdir(path):
+            path = os.path.join(path, cls._CONFIG_NAME)
+        if not os.path.isfile(path):
+            raise EnvironmentError(f"no {cls._CONFIG_NAME} at {pretrained_model_name_or_path} (local paths only: no hub access)")
+        with open(path, encoding="utf-8") as f:
+            return cls.from_dict(json.load(f), **kwargs)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__} {self.to_json_string()}"
 
     # ------------------------------------------------------------------ helpers
     def _dev(self, like: Optional[torch.Tensor] = None) -> torch.device:

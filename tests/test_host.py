@@ -448,3 +448,29 @@ def test_loader_host_logic(tmp_path):
     assert DS.max_image_size(fe_like) == 768
     with pytest.raises(Exception):
         DS.decode_jpegs([b"x"], "cpu")          # the loader delivers to the GPU: no CPU product path
+
+
+def test_extractor_save_and_load_preprocessor_config(D, tmp_path):
+    """FE:80: the reference inherits FeatureExtractionMixin; the same preprocessor_config.json round-trips here, and
+    transformers' own mixin reads the file we write (same keys, "feature_extractor_type")."""
+    import json
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, 2.5, 32, 24, 1024, channel_importances=(4.0, 1.0, 2.0),
+                                          patch_sample_magnitude_weight=0.25)
+    files = fe.save_pretrained(tmp_path / "proc")
+    assert [os.path.basename(f) for f in files] == ["preprocessor_config.json"]
+    cfg = json.load(open(files[0]))
+    assert cfg["feature_extractor_type"] == "DCTAutoencoderFeatureExtractor" and cfg["max_patch_w"] == 24
+    for src in (tmp_path / "proc", files[0]):
+        fe2 = D.DCTAutoencoderFeatureExtractor.from_pretrained(src)
+        assert fe2.to_dict() == fe.to_dict()
+        assert torch.equal(fe2.channel_importances, fe.channel_importances)
+    fe3 = D.DCTAutoencoderFeatureExtractor.from_pretrained(tmp_path / "proc", max_seq_len=77)
+    assert fe3.max_seq_len == 77 and fe3.patch_size == 14
+    with pytest.raises(EnvironmentError):
+        D.DCTAutoencoderFeatureExtractor.from_pretrained(tmp_path / "nothing-here")
+    with pytest.raises(ValueError):
+        D.DCTAutoencoderFeatureExtractor.from_dict({"channels": 3})
+    # the file is what transformers' mixin expects
+    from transformers.feature_extraction_utils import FeatureExtractionMixin
+    d, _ = FeatureExtractionMixin.get_feature_extractor_dict(str(tmp_path / "proc"))
+    assert d["patch_size"] == 14 and d["channel_importances"] == [4.0, 1.0, 2.0]
