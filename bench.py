@@ -531,7 +531,10 @@ def run_ours(a):
                 graphed=graphed,
                 staged=dict(value=staged_value, unit=UNIT, ms_per_step=ms_staged / staged_steps,
                             note="same job through the drop-in modules one by one (roundtrip_staged)"),
-                stages_ms=stages, launch_times_ms=[[n, round(t, 5)] for n, t in launch_times])
+                stages_ms=stages, launch_times_ms=[[n, round(t, 5)] for n, t in launch_times],
+                launch_times_note="per-launch device times of the same step with every launch on ONE stream (differences of "
+                                  "consecutive CUDA events): in the timed step sort_tokens and pack_codes_grid run on a side "
+                                  "stream beside the decode (TransformPipeline.overlap_pack), so ms_per_step is below their sum")
     if world > 1:
         line["e2e"]["note"] = ("all ranks share the host's memory and PCIe root complex: the host-to-host rate saturates there, "
                                "not on a collective (see e2e_compact for the same job with 4x fewer link bytes)")
@@ -619,6 +622,7 @@ def run_config3(ctx, a):
                 pipeline_hbm=dict(bound="hbm", achieved=(2 * 3 * S * S * 4) * B * a.steps / (ms / 1e3) / 1e9, peak=ctx.hbm,
                                   unit="GB/s", note="image in + image out only (the fully-fused bound of this config)"))
     line["pipeline_hbm"]["frac"] = line["pipeline_hbm"]["achieved"] / ctx.hbm
+    line["launch_times_ms"] = [[n, round(t, 5)] for n, t in step_launch_times(ctx, lambda: pipe.roundtrip(x, ks), reps=3)]
     return ctx.finish(line)
 
 
