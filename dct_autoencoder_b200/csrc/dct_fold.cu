@@ -46,6 +46,9 @@ struct FoldGemm {
     int score_groups;     // > 0: tile rows of the token grid; a [score_groups][128] max|value| image follows the ring
     int chunk_w;          // accumulator columns an epilogue warp takes at a time (multiple of 4, <= 32; an even
                           // number of chunks covers n_tile so that the two warps of a lane quarter get equal shares)
+    int lo_streamed;      // 1: only the hi plane of the basis is resident; this CTA's lo tile of the current k block
+                          // travels in the ring behind the data (K too long for both planes, e.g. 1024-sample axes)
+    uint32_t stage_bytes; // F_STAGE, + the lo tile rounded to 1 KB when lo_streamed
 };
 
 struct FoldEpi {
@@ -198,10 +201,10 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* basis_hi = smem;
-    uint8_t* basis_lo = smem + g.basis_bytes;
-    uint8_t* ring = smem + 2 * g.basis_bytes;
-    unsigned* smax = reinterpret_cast<unsigned*>(ring + g.stages * F_STAGE);
-    uint8_t* gen_ring = ring + g.stages * F_STAGE + g.score_groups * 128 * 4;     // GEN only
+    uint8_t* basis_lo = smem + g.basis_bytes;                                    // unused when lo_streamed
+    uint8_t* ring = smem + (g.lo_streamed ? ((g.basis_bytes + 1023u) & ~1023u) : 2 * g.basis_bytes);   // 1 KB aligned
+    unsigned* smax = reinterpret_cast<unsigned*>(ring + g.stages * g.stage_bytes);
+    uint8_t* gen_ring = ring + g.stages * g.stage_bytes + g.score_groups * 128 * 4;     // GEN only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -284,11 +287,11 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t basis_bar_leader = mapa_u32(smem_u32(&basis_bar), 0);
         const int half_rows = g.n_tile >> 1;
         const uint32_t btile = (uint32_t)half_rows * 64;
-        if (rank == 0) mbar_expect_tx(&basis_bar, 4 * g.basis_bytes);
+        const int brow = nt * g.n_tile + (int)rank * half_rows;
+        if (rank == 0) mbar_expect_tx(&basis_bar, (g.lo_streamed ? 2 : 4) * g.basis_bytes);
         for (int kb = 0; kb < g.num_kb; ++kb) {
-            const int row = nt * g.n_tile + (int)rank * half_rows;
-            tma_load_3d_2sm(&map_b_hi, basis_bar_leader, basis_hi + kb * btile, kb * FK, row, grp);
-            tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * btile, kb * FK, row, grp);
+            tma_load_3d_2sm(&map_b_hi, basis_bar_leader, basis_hi + kb * btile, kb * FK, brow, grp);
+            if (!g.lo_streamed) tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * btile, kb * FK, brow, grp);
         }
         const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
         int s = 0;
@@ -323,11 +326,12 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const int row0 = (w % g.tiles_per_seg) * 256 + (int)rank * 128;
             for (int kb = 0; kb < g.num_kb; ++kb) {
                 mbar_wait(&empty_bar[s], ph);
-                uint8_t* st = ring + s * F_STAGE;
+                uint8_t* st = ring + s * g.stage_bytes;
                 const uint32_t full_leader = full_leader0 + 8u * s;
-                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * F_STAGE);
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * F_STAGE + (g.lo_streamed ? 2 * btile : 0u));
                 tma_load_3d_2sm(&map_a_hi, full_leader, st, kb * FK, row0, seg);
                 tma_load_3d_2sm(&map_a_lo, full_leader, st + F_ATILE, kb * FK, row0, seg);
+                if (g.lo_streamed) tma_load_3d_2sm(&map_b_lo, full_leader, st + F_STAGE, kb * FK, brow, grp);
                 if (++s == g.stages) { s = 0; ph ^= 1u; }
             }
         }
@@ -337,7 +341,7 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const uint32_t idesc = fold_idesc(g.n_tile);
         const uint32_t btile16 = ((uint32_t)(g.n_tile >> 1) * 64) >> 4;
         const uint32_t bh = smem_desc_lo(smem_u32(basis_hi)), bl = smem_desc_lo(smem_u32(basis_lo));
-        const uint32_t ring16 = smem_desc_lo(smem_u32(ring));
+        const uint32_t ring16 = smem_desc_lo(smem_u32(ring)), stage16 = g.stage_bytes >> 4;
         mbar_wait_cluster(&basis_bar, 0);
         tc_fence_after();
         uint32_t tcount = 0, ph = 0;
@@ -351,13 +355,14 @@ fold_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             for (int kb = 0; kb < g.num_kb; ++kb, b16 += btile16) {
                 mbar_wait_cluster(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t a16 = ring16 + (uint32_t)s * (F_STAGE >> 4);
+                const uint32_t a16 = ring16 + (uint32_t)s * stage16;
+                const uint32_t bl16 = g.lo_streamed ? a16 + (F_STAGE >> 4) : bl + b16;
 #pragma unroll
                 for (int k = 0; k < FK / 16; ++k) {
                     const uint64_t a_hi = smem_desc_sw64_from_lo(a16 + 2 * k);
                     const uint64_t a_lo = smem_desc_sw64_from_lo(a16 + (F_ATILE >> 4) + 2 * k);
                     const uint64_t b_hi = smem_desc_sw64_from_lo(bh + b16 + 2 * k);
-                    const uint64_t b_lo = smem_desc_sw64_from_lo(bl + b16 + 2 * k);
+                    const uint64_t b_lo = smem_desc_sw64_from_lo(bl16 + 2 * k);
                     umma_f16_2sm(tmem_acc, a_lo, b_hi, idesc, (kb | k) ? 1u : 0u);   // small terms first
                     umma_f16_2sm(tmem_acc, a_hi, b_lo, idesc, 1u);
                     umma_f16_2sm(tmem_acc, a_hi, b_hi, idesc, 1u);
@@ -948,7 +953,22 @@ static bool fold_geometry(int n_valid, int K, FoldGemm& g, int score_groups = 0,
     for (int nn = (int)ceil_div(n_valid, 256); nn <= 16; ++nn) {
         const int n_tile = (int)ceil_div(ceil_div(n_valid, nn), 16) * 16;
         const int64_t basis = (int64_t)g.num_kb * (n_tile / 2) * 64;
-        const int64_t stages = (F_SMEM_LIMIT - extra_static - 1024 - 2 * basis - score_bytes) / F_STAGE;
+        int64_t stages = (F_SMEM_LIMIT - extra_static - 1024 - 2 * basis - score_bytes) / F_STAGE;
+        g.lo_streamed = 0;
+        g.stage_bytes = F_STAGE;
+        if (n_tile <= 256 && stages < 3 && extra_static == 0) {
+            // Both planes of the basis do not fit beside the ring.  Halving the slice (nn + 1) would stream every data
+            // tile twice and run MMAs of half the width, which are bound by their shared-memory operand reads; keeping
+            // the hi plane resident and sending the CTA's lo tile of each k block through the ring costs
+            // n_tile/2 x 64 bytes per stage instead (it never leaves L2).
+            const int64_t lo_tile = ceil_div((int64_t)(n_tile / 2) * 64, 1024) * 1024;
+            const int64_t st2 = (F_SMEM_LIMIT - 1024 - ceil_div(basis, 1024) * 1024 - score_bytes) / (F_STAGE + lo_tile);
+            if (st2 >= 3) {
+                stages = st2;
+                g.lo_streamed = 1;
+                g.stage_bytes = (uint32_t)(F_STAGE + lo_tile);
+            }
+        }
         if (n_tile <= 256 && stages >= 3) {
             g.n_tile = n_tile;
             g.n_ntiles = nn;
@@ -984,7 +1004,9 @@ static int launch_fold_gemm(const FoldOperand& A, int64_t rows_per_seg, int n_se
         if ((rc = make_map3(&ma_hi, A.hi, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
         if ((rc = make_map3(&ma_lo, A.lo, K, rows_per_seg, n_seg, A.ld, A.seg_stride, 128))) return rc;
     }
-    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * F_STAGE + g.score_groups * 128 * 4 + gen_bytes;
+    const int smem_bytes = 1024 + (g.lo_streamed ? (int)(ceil_div((int64_t)g.basis_bytes, 1024) * 1024) : 2 * (int)g.basis_bytes) +
+                           g.stages * (int)g.stage_bytes +
+                           g.score_groups * 128 * 4 + gen_bytes;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
