@@ -308,8 +308,11 @@ static int launch_gemm_split(const Operand& A, const Operand& B, int K, int64_t 
 // split into two accumulators so that the epilogue of tile i overlaps the main loop of tile i+1.
 //   warp 0 / one lane : TMA producer (ring of PSTAGES stages: A 128x32 hi/lo + B TNPx32 hi/lo)
 //   warp 1 / one lane : tcgen05.mma issuer (M=128, N=TNP), commits free ring stages and publish accumulators
-//   warps 2..5        : epilogue (TMEM lane quarter = warp & 3); accumulator handed back as soon as it has
-//                       been read out, stores proceed from registers / the per-warp staging slice
+//   warps 2..9        : epilogue, two warps per TMEM lane quarter (quarter = warp & 3): they read alternate 32-column
+//                       chunks out of TMEM into the quarter's staging slice, meet at a named barrier, and each stores
+//                       16 of the 32 rows, four rows in flight at a time (one warp per scheduler with one row in
+//                       flight left the store-out exposed: 20 k cycles per tile against 4.7 k of MMAs at K = 196);
+//                       the accumulator is handed back as soon as it has been read out
 constexpr int PSTAGES = 3;
 constexpr int P_EPI_BYTES = TM * EPI_PITCH * 4;          // 128 x 132 fp32 staging (one 128-column half)
 
@@ -321,8 +324,10 @@ struct PCfg {
     static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TNP >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 };
 
+constexpr int P_THREADS = 320;
+
 template <int TNP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(P_THREADS, 1)
 gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                              int a_batched, int b_batched, int num_k_blocks, int tiles_m, int tiles_n, int n_batch,
@@ -350,7 +355,7 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);     // one arrival per epilogue warp
+            mbar_init(&tmem_empty[a], 8);     // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -415,7 +420,9 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
     } else if (warp >= 2) {
         // ---------------- epilogue warps
         const int quarter = warp & 3;                     // TMEM lanes 32*quarter .. +31
+        const int chalf = (warp - 2) >> 2;                // which of the quarter's two warps
         const uint32_t stage = smem_u32(smem + PSTAGES * Cfg::kStage) + (uint32_t)(quarter * 32 * EPI_PITCH) * 4;
+        auto quarter_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
         const int p = ep.tile_p, zz = p * p;
         const bool pair_ok = (p % 2 == 0);
         const float alpha = ep.alpha * (ep.alpha_dev ? __ldg(ep.alpha_dev) : 1.0f);
@@ -439,11 +446,13 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
                 // transposed hi/lo store straight from registers: out[b][n * ld + m]; for a fixed column
                 // the 32 lanes of the warp hold 32 consecutive m -> one 64-byte store per plane
                 const int64_t obase = (int64_t)batch * ep.batch_stride + gm;
+                constexpr int kChunks = TNP / 32;
+                const int last_c = ((kChunks - 1) & 1) == chalf ? kChunks - 1 : kChunks - 2;
 #pragma unroll 1
-                for (int c = 0; c < TNP / 32; ++c) {
+                for (int c = chalf; c < kChunks; c += 2) {
                     uint32_t rr[32];
                     tmem_ld32(tmem_acc + c * 32, rr);
-                    if (c == TNP / 32 - 1) {          // accumulator fully read: hand it back to the MMA warp
+                    if (c == last_c) {                // this warp's share of the accumulator is read: hand it back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
@@ -469,7 +478,7 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
             for (int half = 0; half < (TNP + 127) / 128; ++half) {
                 const int cbeg = half * 128;
                 const int ccnt = (TNP - cbeg) < 128 ? (TNP - cbeg) : 128;      // 128 or 96
-                for (int c = 0; c < ccnt / 32; ++c) {
+                for (int c = chalf; c < ccnt / 32; c += 2) {
                     uint32_t rr[32];
                     tmem_ld32(tmem_acc + cbeg + c * 32, rr);
                     const uint32_t dst = stage + (uint32_t)(lane * EPI_PITCH + c * 32) * 4;
@@ -484,7 +493,7 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
                 }
-                __syncwarp();
+                quarter_sync();                       // both warps' chunks are in the staging slice
                 const int n = n0 + cbeg + lane * 4;
                 const int n_valid = (lane * 4 < ccnt) ? ep.N - n : 0;
                 int64_t col_off[4] = {0, 0, 0, 0};
@@ -506,13 +515,18 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
 #pragma unroll
                     for (int j = 0; j < 4; ++j) if (j < n_valid) bias4[j] = __ldg(ep.col_bias + n + j);
                 }
-                for (int rr_ = 0; rr_ < 32; ++rr_) {
-                    const int m = m0 + quarter * 32 + rr_;
+                for (int r4 = chalf * 16; r4 < chalf * 16 + 16; r4 += 4) {
+                  float4 v4[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v4[u].x), "=f"(v4[u].y), "=f"(v4[u].z), "=f"(v4[u].w)
+                                   : "r"(stage + (uint32_t)((r4 + u) * EPI_PITCH + lane * 4) * 4));
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int m = m0 + quarter * 32 + r4 + u;
                     if (m >= ep.M) break;
                     if (n_valid <= 0 && ep.mode != 5) continue;
-                    float4 v;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                                 : "r"(stage + (uint32_t)(rr_ * EPI_PITCH + lane * 4) * 4));
+                    float4 v = v4[u];
                     if (ep.dc_mode == 2) { v.x += dcv; v.y += dcv; v.z += dcv; v.w += dcv; }
                     else if (ep.dc_mode == 1 && m == 0 && n == 0) v.x += dcv;
                     v.x += bias4[0]; v.y += bias4[1]; v.z += bias4[2]; v.w += bias4[3];
@@ -576,8 +590,9 @@ gemm_split_persistent_kernel(const __grid_constant__ CUtensorMap map_a_hi, const
                             for (int j = 0; j < 4; ++j) if (j < n_valid) dst[col_off[j]] = a[j];
                         }
                     }
+                  }
                 }
-                __syncwarp();                         // staging slice is reused by the next half / tile
+                quarter_sync();                       // staging slice is reused by the next half / tile
             }
         }
     }
@@ -605,7 +620,7 @@ static int launch_gemm_persistent(const Operand& A, const Operand& B, int K, int
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-    gemm_split_persistent_kernel<TNP><<<grid, 192, PCfg<TNP>::kSmem, as_stream(stream)>>>(
+    gemm_split_persistent_kernel<TNP><<<grid, P_THREADS, PCfg<TNP>::kSmem, as_stream(stream)>>>(
         ma_hi, ma_lo, mb_hi, mb_lo, A.batch_stride != 0, B.batch_stride != 0, (int)ceil_div(K, TK), tiles_m, tiles_n,
         (int)batch, ep);
     return check_launch("gemm_split_persistent");
