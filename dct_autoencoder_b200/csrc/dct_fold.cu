@@ -1314,7 +1314,9 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ z
 // memory ONCE per CTA as [row][column group][8] (16-byte halves swizzled so that 128-bit reads are
 // conflict-free) and reused for every image.  FAST (one LFQ codebook per patch row, p <= 16): the 2 x p code
 // words of a thread's two tokens are read in one burst and boiled down to one byte of sign bits per row.
-template <bool CODES, bool FAST>
+// DENORM (with CODES = false): the patches are NORMALISED ones and PatchNorm.inverse_norm (patchnorm.py:167-177) is applied
+// on the way, from the same staged statistics -- the de-normalised patches are never written.
+template <bool CODES, bool FAST, bool DENORM = false>
 __global__ void __launch_bounds__(256, 4) unpatchify_fold_kernel(const float* __restrict__ patches,
                                                                  const int64_t* __restrict__ codes,
                                                                  const int32_t* __restrict__ slot_map,
@@ -1436,6 +1438,26 @@ __global__ void __launch_bounds__(256, 4) unpatchify_fold_kernel(const float* __
                     for (int j = 0; j < 8; ++j) {
                         const float* src = j < n_first ? src0 : src1;
                         v[j] = src ? __ldg(src + py * p + j) : 0.0f;
+                    }
+                }
+                if (DENORM) {
+                    // the statistics of the two tiles under these 8 columns, straight from the L2-resident tables (a
+                    // shared-memory copy per CTA costs more than it saves: it is shared by 8 images only)
+                    const int64_t st0 = (((int64_t)c * q.H + ty) * q.W + tx0) * q.z + py * p + px0;      // column j < n_first: + j
+                    const int64_t st1 = st0 - px0 + q.z - n_first;                                       // the others: + j
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const bool first = j < n_first;
+                        const bool on = (valid8 & (0x80u >> j)) != 0u;          // p, px0, n_first even: pairs share a tile
+                        float2 mv = make_float2(0.f, 0.f), bv = make_float2(0.f, 0.f);
+                        if (on) {
+                            const int64_t e = (first ? st0 : st1) + j;
+                            mv = __ldg(reinterpret_cast<const float2*>(q.median + e));
+                            bv = __ldg(reinterpret_cast<const float2*>(q.b + e));
+                        }
+                        const float s0 = __fadd_rn(__fmul_rn(bv.x, kSqrt2f), q.eps), s1 = __fadd_rn(__fmul_rn(bv.y, kSqrt2f), q.eps);
+                        v[j] = on ? __fadd_rn(__fmul_rn(v[j], s0), mv.x) : 0.0f;                          // patchnorm.py:177
+                        v[j + 1] = on ? __fadd_rn(__fmul_rn(v[j + 1], s1), mv.y) : 0.0f;
                     }
                 }
                 if (ty == 0 && py == 0 && xv == 0) {
@@ -2451,7 +2473,7 @@ extern "C" int dcta_fold_coef_planes(const float* y, void* yq_hi, void* yq_lo, f
 static int launch_unpatchify_fold(bool with_codes, const float* patches, const int64_t* codes, const int32_t* slot_map,
                                   const int32_t* img_sel, int64_t n_img, int C, int th, int tw, int p, int rows, int cols,
                                   int out_h, int out_w, const LfqNormParams& q, void* yq_hi, void* yq_lo, float* dc,
-                                  void* stream, const char* who, uint32_t* tab_scratch = nullptr) {
+                                  void* stream, const char* who, uint32_t* tab_scratch = nullptr, bool denorm = false) {
     DCTA_REQUIRE(slot_map && yq_hi && yq_lo && dc, "%s: null pointer", who);
     DCTA_REQUIRE(rows > 0 && cols > 0 && p > 0 && out_h > 0 && out_w > 0 && rows % 2 == 0 && cols % 2 == 0 && rows % p == 0,
                  "%s: needs even plane sizes and rows %% patch == 0", who);
@@ -2497,6 +2519,10 @@ static int launch_unpatchify_fold(bool with_codes, const float* patches, const i
             unpatchify_fold_kernel<true, false><<<(unsigned)n_ctas, block, smem_bytes, as_stream(stream)>>>(
                 patches, codes, slot_map, img_sel, n_img, imgs_per_cta, C, th, tw, p, rows, cols, ldq, q, (__half*)yq_hi,
                 (__half*)yq_lo, dc, dcf, kFScaleY);
+    } else if (denorm) {
+        unpatchify_fold_kernel<false, false, true><<<(unsigned)n_ctas, block, 0, as_stream(stream)>>>(
+            patches, codes, slot_map, img_sel, n_img, imgs_per_cta, C, th, tw, p, rows, cols, ldq, q, (__half*)yq_hi,
+            (__half*)yq_lo, dc, dcf, kFScaleY);
     } else {
         unpatchify_fold_kernel<false, false><<<(unsigned)n_ctas, block, 0, as_stream(stream)>>>(
             patches, codes, slot_map, img_sel, n_img, imgs_per_cta, C, th, tw, p, rows, cols, ldq, q, (__half*)yq_hi,
@@ -2513,6 +2539,19 @@ extern "C" int dcta_unpatchify_fold(const float* patches, const int32_t* slot_ma
     LfqNormParams q{};
     return launch_unpatchify_fold(false, patches, nullptr, slot_map, img_sel, n_img, channels_n, th, tw, p, rows, cols,
                                   out_h, out_w, q, yq_hi, yq_lo, dc, stream, "unpatchify_fold");
+}
+
+extern "C" int dcta_unpatchify_denorm_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
+                                           int channels_n, int th, int tw, int p, int rows, int cols, int out_h, int out_w,
+                                           const float* median, const float* b, int H, int W, float eps, void* yq_hi,
+                                           void* yq_lo, float* dc, void* stream) {
+    DCTA_REQUIRE(patches && median && b, "unpatchify_denorm_fold: null pointer");
+    DCTA_REQUIRE(th <= H && tw <= W && rows / p <= H, "unpatchify_denorm_fold: the token grid must lie inside the PatchNorm tables");
+    DCTA_REQUIRE(p % 2 == 0 && ((reinterpret_cast<uintptr_t>(median) | reinterpret_cast<uintptr_t>(b)) & 7) == 0,
+                 "unpatchify_denorm_fold: needs an even patch size and 8-byte aligned tables");
+    LfqNormParams q{median, b, channels_n, H, W, p * p, eps, 0.f, 0.f, 1, p * p, 1.0f};
+    return launch_unpatchify_fold(false, patches, nullptr, slot_map, img_sel, n_img, channels_n, th, tw, p, rows, cols,
+                                  out_h, out_w, q, yq_hi, yq_lo, dc, stream, "unpatchify_denorm_fold", nullptr, true);
 }
 
 extern "C" int dcta_decode_codes_fold(const int64_t* codes, const int32_t* slot_map, const int32_t* img_sel,

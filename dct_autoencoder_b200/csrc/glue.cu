@@ -9,6 +9,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "lfq_norm.cuh"
 
 namespace dcta {
 
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(256) split_rows_rowscale_vec_kernel(const floa
                                                                       const float* __restrict__ beta, float eps,
                                                                       __half* __restrict__ hi, __half* __restrict__ lo,
                                                                       float* __restrict__ row_scale, float post, int64_t n_rows,
-                                                                      int d, int64_t ld) {
+                                                                      int d, int64_t ld, PatchNormRows pn) {
     const int lane = threadIdx.x & 31;
     const int d4 = d >> 2, ld4 = (int)(ld >> 2);
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -189,6 +190,24 @@ __global__ void __launch_bounds__(256) split_rows_rowscale_vec_kernel(const floa
         for (int c = 0; c < CH; ++c) {
             const int i = lane + 32 * c;
             v[c] = i < d4 ? ld_stream(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (pn.channels != nullptr) {
+            // PatchNorm.forward, frozen statistics (patchnorm.py:157-165), on the row in registers: the normalised
+            // patches are never written (padding rows read the statistics at (0, 0, 0), like the reference)
+            const int64_t row = (int64_t)clamped_position(pn.channels, pn.positions, t, pn.C, pn.H, pn.W) * d4;
+            const float4* m4 = reinterpret_cast<const float4*>(pn.median) + row;
+            const float4* b4 = reinterpret_cast<const float4*>(pn.b) + row;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int i = lane + 32 * c;
+                if (i < d4) {
+                    const float4 mv = __ldg(m4 + i), bv = __ldg(b4 + i);
+                    v[c].x = patchnorm_value<false>(v[c].x, mv.x, bv.x, pn.eps, pn.lo, pn.hi);
+                    v[c].y = patchnorm_value<false>(v[c].y, mv.y, bv.y, pn.eps, pn.lo, pn.hi);
+                    v[c].z = patchnorm_value<false>(v[c].z, mv.z, bv.z, pn.eps, pn.lo, pn.hi);
+                    v[c].w = patchnorm_value<false>(v[c].w, mv.w, bv.w, pn.eps, pn.lo, pn.hi);
+                }
+            }
         }
         if (gamma != nullptr) {
             float s = 0.f;
@@ -270,28 +289,50 @@ extern "C" int dcta_ln_pos_rows(const float* x, const float* gamma, const float*
     return check_launch("ln_pos_rows");
 }
 
-extern "C" int dcta_split_rows_rowscale(const float* x, const float* gamma, const float* beta, float eps, void* hi, void* lo,
-                                        float* row_scale, float post, int64_t n_rows, int d, int64_t ld, void* stream) {
+static int launch_split_rows(const float* x, const float* gamma, const float* beta, float eps, void* hi, void* lo,
+                             float* row_scale, float post, int64_t n_rows, int d, int64_t ld, const dcta::PatchNormRows& pn,
+                             void* stream, const char* who) {
     using namespace dcta;
-    DCTA_REQUIRE(x && hi && row_scale && n_rows >= 0 && d > 0 && ld >= d && ld % 8 == 0, "split_rows_rowscale: bad arguments");
-    DCTA_REQUIRE((gamma == nullptr) == (beta == nullptr), "split_rows_rowscale: gamma and beta go together");
+    DCTA_REQUIRE(x && hi && row_scale && n_rows >= 0 && d > 0 && ld >= d && ld % 8 == 0, "%s: bad arguments", who);
+    DCTA_REQUIRE((gamma == nullptr) == (beta == nullptr), "%s: gamma and beta go together", who);
     if (n_rows == 0) return DCTA_OK;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0 &&
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+                           reinterpret_cast<uintptr_t>(pn.median) | reinterpret_cast<uintptr_t>(pn.b)) & 15) == 0 &&
                          ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0;
     const int ch = (int)((ld / 4 + 31) / 32);          // float4 per lane (the zero padding up to ld included)
     cudaStream_t st = as_stream(stream);
     const int grid = grid_for(n_rows, 8);
 #define DCTA_SPLIT_CASE(N)                                                                                                  \
     case N: split_rows_rowscale_vec_kernel<N><<<grid, 256, 0, st>>>(x, gamma, beta, eps, (__half*)hi, (__half*)lo, row_scale, \
-                                                                     post, n_rows, d, ld); break;
+                                                                     post, n_rows, d, ld, pn); break;
     if (d % 4 == 0 && aligned && ch >= 1 && ch <= 8) {
         switch (ch) {
             DCTA_SPLIT_CASE(1) DCTA_SPLIT_CASE(2) DCTA_SPLIT_CASE(3) DCTA_SPLIT_CASE(4)
             DCTA_SPLIT_CASE(5) DCTA_SPLIT_CASE(6) DCTA_SPLIT_CASE(7) DCTA_SPLIT_CASE(8)
         }
     } else {
+        if (pn.channels != nullptr) {
+            set_error("%s: the fused PatchNorm needs rows of a multiple of 4 (at most 1024) 16-byte aligned floats", who);
+            return DCTA_ERR_UNSUPPORTED;
+        }
         split_rows_rowscale_kernel<<<grid, 256, 0, st>>>(x, gamma, beta, eps, (__half*)hi, (__half*)lo, row_scale, post, n_rows, d, ld);
     }
 #undef DCTA_SPLIT_CASE
-    return check_launch("split_rows_rowscale");
+    return check_launch(who);
+}
+
+extern "C" int dcta_split_rows_rowscale(const float* x, const float* gamma, const float* beta, float eps, void* hi, void* lo,
+                                        float* row_scale, float post, int64_t n_rows, int d, int64_t ld, void* stream) {
+    return launch_split_rows(x, gamma, beta, eps, hi, lo, row_scale, post, n_rows, d, ld, dcta::PatchNormRows{}, stream,
+                             "split_rows_rowscale");
+}
+
+extern "C" int dcta_split_rows_patchnorm(const float* x, const int64_t* channels, const int64_t* positions, const float* median,
+                                         const float* b, int C, int H, int W, float eps, float clamp_lo, float clamp_hi,
+                                         void* hi, void* lo, float* row_scale, float post, int64_t n_rows, int d, int64_t ld,
+                                         void* stream) {
+    using namespace dcta;
+    DCTA_REQUIRE(channels && positions && median && b && C > 0 && H > 0 && W > 0, "split_rows_patchnorm: bad arguments");
+    const PatchNormRows pn{channels, positions, median, b, C, H, W, eps, clamp_lo, clamp_hi};
+    return launch_split_rows(x, nullptr, nullptr, 0.0f, hi, lo, row_scale, post, n_rows, d, ld, pn, stream, "split_rows_patchnorm");
 }

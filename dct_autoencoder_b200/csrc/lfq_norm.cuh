@@ -26,6 +26,40 @@ __device__ __forceinline__ unsigned norm_sign_bit(float xv, float mv, float bv, 
     return y > 0.0f;
 }
 
+// Row of the statistics tables a token reads: (channel, tile row, tile column) with torch's negative-index wrap,
+// clamped into the table (patchnorm.py:157-160)
+__device__ __forceinline__ int clamped_position(const int64_t* channels, const int64_t* positions, int64_t tok, int C,
+                                                int H, int W) {
+    int64_t c = channels[tok], h = positions[2 * tok], w = positions[2 * tok + 1];
+    // torch indexing wraps negative indices; out-of-range indices raise in the reference.
+    if (c < 0) c += C;
+    if (h < 0) h += H;
+    if (w < 0) w += W;
+    c = min(max(c, (int64_t)0), (int64_t)C - 1);
+    h = min(max(h, (int64_t)0), (int64_t)H - 1);
+    w = min(max(w, (int64_t)0), (int64_t)W - 1);
+    return (int)((c * H + h) * W + w);
+}
+
+// PatchNorm forward (frozen) / inverse of one value, in the reference's operation order with explicit roundings
+template <bool kInverse>
+__device__ __forceinline__ float patchnorm_value(float xv, float mv, float bv, float eps, float lo, float hi) {
+    const float sd = __fadd_rn(__fmul_rn(bv, kSqrt2f), eps);
+    if (kInverse) return __fadd_rn(__fmul_rn(xv, sd), mv);          // PN:177
+    const float y = __fdiv_rn(__fsub_rn(xv, mv), sd);                // PN:161
+    return y < lo ? lo : (y > hi ? hi : y);                          // PN:163 (NaN propagates, as torch.clamp)
+}
+
+// PatchNorm forward fused into a consumer of token rows (glue.cu: the operand split of the LFQ projection)
+struct PatchNormRows {
+    const int64_t* channels;    // (n_rows); nullptr = no normalisation
+    const int64_t* positions;   // (n_rows, 2)
+    const float* median;        // (C, H, W, z)
+    const float* b;
+    int C, H, W;
+    float eps, lo, hi;
+};
+
 // *flag = nonzero iff every b[i] is finite and in [0, 1e18] (fused_lfq.cu)
 int launch_b_tame(const float* b, int64_t n, int32_t* flag, cudaStream_t st);
 

@@ -6,32 +6,12 @@
 // All fp32 arithmetic uses explicit round-to-nearest intrinsics in the reference's operation
 // order (no fma contraction) so results are bit-identical to the reference's CPU fp32 path.
 #include "common.cuh"
+#include "lfq_norm.cuh"
 
 namespace dcta {
 
-constexpr float kSqrt2 = 1.41421356237309504880f;  // float32(2 ** 0.5), PN:158
-
 // ------------------------------------------------------------------------------ apply
-__device__ __forceinline__ int clamped_position(const int64_t* channels, const int64_t* positions, int64_t tok, int C,
-                                                int H, int W) {
-    int64_t c = channels[tok], h = positions[2 * tok], w = positions[2 * tok + 1];
-    // torch indexing wraps negative indices; out-of-range indices raise in the reference.
-    if (c < 0) c += C;
-    if (h < 0) h += H;
-    if (w < 0) w += W;
-    c = min(max(c, (int64_t)0), (int64_t)C - 1);
-    h = min(max(h, (int64_t)0), (int64_t)H - 1);
-    w = min(max(w, (int64_t)0), (int64_t)W - 1);
-    return (int)((c * H + h) * W + w);
-}
-
-template <bool kInverse>
-__device__ __forceinline__ float patchnorm_value(float xv, float mv, float bv, float eps, float lo, float hi) {
-    const float sd = __fadd_rn(__fmul_rn(bv, kSqrt2), eps);
-    if (kInverse) return __fadd_rn(__fmul_rn(xv, sd), mv);          // PN:177
-    const float y = __fdiv_rn(__fsub_rn(xv, mv), sd);                // PN:161
-    return y < lo ? lo : (y > hi ? hi : y);                          // PN:163 (NaN propagates, as torch.clamp)
-}
+// (clamped_position and patchnorm_value live in lfq_norm.cuh: the fused consumers use the same arithmetic)
 
 // kVec == 4 (z % 4 == 0, z <= 256): a warp takes 32 consecutive tokens, the position lookups (three dependent
 // 8-byte loads per token) run once, lane-parallel, and the tokens' words are then streamed with 128-bit

@@ -700,7 +700,7 @@ class DCTAutoencoderFeatureExtractor:
         return res
 
     def _decode_groups(self, x: DCTPatches, codes: Optional[torch.Tensor] = None, norm=None, lfq=None,
-                       out_dtype=torch.float32, code_grid: Optional[torch.Tensor] = None):
+                       out_dtype=torch.float32, code_grid: Optional[torch.Tensor] = None, denorm=None):
         """Token rows -> RGB, one kernel sequence per group of images that share (tile grid,
         original size).  Yields (image indices, rgb (n, c, h, w)).  The zero padding of FE:300-304
         is implicit in the truncated inverse basis.  With ``codes`` the tokens are de-quantised and
@@ -711,6 +711,19 @@ class DCTAutoencoderFeatureExtractor:
             _lib.require_cuda(x.patches)
             patches = to_device_f32(x.patches)
             dev = patches.device
+            if denorm is not None:
+                sizes = {(min(int(a), self.max_patch_h), min(int(b), self.max_patch_w), int(o[0]), int(o[1]))
+                         for (a, b), o in zip(x.patch_sizes, x.original_sizes)}
+                fusable = (self.dct_impl == "tc" and C == 3 and p >= 8 and p % 2 == 0 and denorm.median.device == dev
+                           and denorm.median.dtype == torch.float32
+                           and denorm.patch_size == p and denorm.channels == C
+                           and all(a <= denorm.max_patch_h and b <= denorm.max_patch_w and fold_ok(h, w, a * p, b * p)
+                                   for a, b, h, w in sizes))
+                if not fusable:              # the plain order of the reference: de-normalise, then un-patchify
+                    y = x.shallow_copy()
+                    y.patches = patches
+                    patches = denorm.inverse_norm(y)
+                    denorm = None
         else:
             patches = None
             dev = codes.device
@@ -761,6 +774,11 @@ class DCTAutoencoderFeatureExtractor:
                                   norm.max_patch_h, norm.max_patch_w, float(norm.eps), lfq.num_codebooks,
                                   lfq.codebook_dim, float(lfq.codebook_scale), _lib.ptr(y_hi), _lib.ptr(y_lo),
                                   _lib.ptr(dc), _lib.ptr(tab), st)
+                    elif denorm is not None:
+                        _lib.call("dcta_unpatchify_denorm_fold", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
+                                  th, tw, p, kh, kw, h, w, _lib.ptr(denorm.median.data), _lib.ptr(denorm.b.data),
+                                  denorm.max_patch_h, denorm.max_patch_w, float(denorm.eps), _lib.ptr(y_hi), _lib.ptr(y_lo),
+                                  _lib.ptr(dc), st)
                     else:
                         _lib.call("dcta_unpatchify_fold", _lib.ptr(patches), _lib.ptr(slot_map), _lib.ptr(sel), n, C,
                                   th, tw, p, kh, kw, h, w, _lib.ptr(y_hi), _lib.ptr(y_lo), _lib.ptr(dc), st)
@@ -790,9 +808,12 @@ class DCTAutoencoderFeatureExtractor:
             yield idx, (unit_to_u8(rgb) if out_dtype == torch.uint8 else rgb)
 
     @torch.no_grad()
-    def postprocess_batch(self, x: DCTPatches, out_dtype=torch.float32) -> torch.Tensor:
+    def postprocess_batch(self, x: DCTPatches, out_dtype=torch.float32, denorm=None) -> torch.Tensor:
         """Same as ``torch.stack(postprocess(x))`` for batches whose images share one size.
-        ``out_dtype=torch.uint8``: 8-bit pixels, quantised like torchvision's save_image (util.unit_to_u8)."""
+        ``out_dtype=torch.uint8``: 8-bit pixels, quantised like torchvision's save_image (util.unit_to_u8).
+        ``denorm``: a PatchNorm whose ``inverse_norm`` (patchnorm.py:167-177) is applied to ``x.patches`` on the way into
+        the coefficient planes (the un-patchify kernel de-normalises what it gathers; same values as
+        ``x.patches = denorm.inverse_norm(x)`` first, without writing the de-normalised patches)."""
         assert len(set(map(tuple, x.original_sizes))) == 1 and len(set(map(tuple, x.patch_sizes))) == 1
-        (idx, rgb), = self._decode_groups(x, out_dtype=out_dtype)
+        (idx, rgb), = self._decode_groups(x, out_dtype=out_dtype, denorm=denorm)
         return rgb

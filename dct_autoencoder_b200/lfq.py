@@ -169,8 +169,11 @@ class LFQ(nn.Module):
             codes = codes.movedim(-1, 1)     # 'b ... d -> b d ...'
         return codes
 
-    def forward(self, x: torch.Tensor, mask=None):
-        """lfq.py:136-227.  ``mask`` (b, n): False where padding is (required, lfq.py:153-154)."""
+    def forward(self, x: torch.Tensor, mask=None, *, patchnorm=None):
+        """lfq.py:136-227.  ``mask`` (b, n): False where padding is (required, lfq.py:153-154).
+        ``patchnorm`` (not in the reference; eval with projections only): ``(PatchNorm, channels, positions)`` -- ``x`` holds
+        UN-normalised patches and the frozen PatchNorm is applied inside the operand split of ``project_in``; the result
+        equals ``forward(norm(batch), mask)`` bit for bit."""
         is_img_or_video = x.ndim >= 4
         if mask is None:
             raise NotImplementedError("mask")
@@ -186,7 +189,8 @@ class LFQ(nn.Module):
         if self.has_projections and not self.training and not torch.is_grad_enabled() and x.is_cuda:
             # eval with projections: project_in + sign + index packing in one GEMM kernel, project_out on the exact
             # +-scale operand (linear.lfq_project_quantize); nothing of size (b, n, c*d) is written as fp32
-            out, indices = lfq_project_quantize(x, self.project_in, self.project_out, c, d, self.codebook_scale)
+            out, indices = lfq_project_quantize(x, self.project_in, self.project_out, c, d, self.codebook_scale,
+                                                patchnorm=patchnorm)
             out = out.to(x.dtype)
             if is_img_or_video:
                 out = out.reshape(out.shape[0], *spatial, out.shape[-1]).movedim(-1, 1)
@@ -195,6 +199,7 @@ class LFQ(nn.Module):
                 indices = indices[..., 0]
             return out, indices, self.zero, self.zero
 
+        assert patchnorm is None, "patchnorm= is fused only into the eval path with projections (no_grad, CUDA input)"
         x = self._project(self.project_in, x)
         b, n, _ = x.shape
         original_input = x

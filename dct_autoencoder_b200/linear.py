@@ -44,9 +44,11 @@ def _split_weight(weight: torch.Tensor):
     return out
 
 
-def _split_rows(x2: torch.Tensor, w_inv: float, ln: Optional[nn.LayerNorm] = None):
+def _split_rows(x2: torch.Tensor, w_inv: float, ln: Optional[nn.LayerNorm] = None, patchnorm=None):
     """fp32 rows (t, k) -> fp16 hi/lo planes (t, round8(k)) scaled per row by a power of two + the factors that undo the
-    scaling (times ``w_inv``); ``ln``: a LayerNorm applied to the rows first."""
+    scaling (times ``w_inv``); ``ln``: a LayerNorm applied to the rows first; ``patchnorm = (PatchNorm, channels (t,),
+    positions (t, 2))``: the rows are un-normalised patches and ``PatchNorm.forward`` (frozen statistics) is applied to
+    them in the same pass (``dcta_split_rows_patchnorm``)."""
     t, k = x2.shape
     dev = x2.device
     ld = _round8(k)
@@ -57,6 +59,18 @@ def _split_rows(x2: torch.Tensor, w_inv: float, ln: Optional[nn.LayerNorm] = Non
     eps = 0.0
     if ln is not None:
         gamma, beta, eps = to_device_f32(ln.weight.detach()), to_device_f32(ln.bias.detach()), float(ln.eps)
+    if patchnorm is not None:
+        assert ln is None
+        norm, channels, positions = patchnorm
+        ch = channels.reshape(-1).to(torch.int64).contiguous()
+        ps = positions.reshape(-1, 2).to(torch.int64).contiguous()
+        assert ch.numel() == t and ps.shape[0] == t and k == norm.patch_size ** 2
+        with torch.cuda.device(dev):
+            _lib.call("dcta_split_rows_patchnorm", _lib.ptr(x2), _lib.ptr(ch), _lib.ptr(ps), _lib.ptr(norm.median.data),
+                      _lib.ptr(norm.b.data), norm.channels, norm.max_patch_h, norm.max_patch_w, float(norm.eps),
+                      float(norm.min_val), float(norm.max_val), _lib.ptr(a_hi), _lib.ptr(a_lo), _lib.ptr(row_scale),
+                      float(w_inv), t, k, ld, _lib.stream_ptr(dev))
+        return a_hi, a_lo, row_scale
     with torch.cuda.device(dev):
         _lib.call("dcta_split_rows_rowscale", _lib.ptr(x2), _lib.ptr(gamma), _lib.ptr(beta), eps, _lib.ptr(a_hi), _lib.ptr(a_lo),
                   _lib.ptr(row_scale), float(w_inv), t, k, ld, _lib.stream_ptr(dev))
@@ -96,7 +110,7 @@ def linear_rows(x: torch.Tensor, weight: torch.Tensor, ln: Optional[nn.LayerNorm
 
 @torch.no_grad()
 def lfq_project_quantize(x: torch.Tensor, project_in: nn.Linear, project_out: Optional[nn.Linear], num_codebooks: int,
-                         codebook_dim: int, codebook_scale: float):
+                         codebook_dim: int, codebook_scale: float, patchnorm=None):
     """LFQ with projections in eval (lfq.py:136-227): ``project_in`` + bias + sign + index packing in ONE GEMM kernel
     (``dcta_lfq_project_sign``; the (t, c*d) activations are never written as fp32), the +-scale codes as an exact fp16
     operand, ``project_out`` + bias as a two-MMA GEMM on it.  Returns (project_out(q) (..., dim) fp32 or the codes
@@ -110,7 +124,7 @@ def lfq_project_quantize(x: torch.Tensor, project_in: nn.Linear, project_out: Op
     dev = x2.device
     w_hi, w_lo, w_inv = _split_weight(project_in.weight)
     ld = _round8(k)
-    a_hi, a_lo, row_scale = _split_rows(x2, w_inv)
+    a_hi, a_lo, row_scale = _split_rows(x2, w_inv, patchnorm=patchnorm)     # patchnorm: see _split_rows
     ldq = _round8(n)
     q_hi = torch.empty((t, ldq), dtype=torch.float16, device=dev) if ldq == n else torch.zeros((t, ldq), dtype=torch.float16, device=dev)
     n_tiles = (n + 127) // 128

@@ -108,11 +108,34 @@ class TransformPipeline:
         pixels standing for ``x / 255``; ``out_dtype=torch.uint8`` returns 8-bit pixels (util.unit_to_u8)."""
         if fused is None:
             fused = self.fusable()
+            if not fused and self.proj_fusable() and self.extractor._dev(images) == self.norm.median.device:
+                return self._proj_roundtrip(images, ks, out_dtype)
         if not fused:
             rec, codes = self.roundtrip_staged(images, ks)
             return (rec if out_dtype == torch.float32 else unit_to_u8(rec)), codes
         batch, codes, rec = self._fused_roundtrip(images, ks, out_dtype)
         return rec, codes
+
+    def proj_fusable(self) -> bool:
+        """True for an LFQ WITH projections in eval mode behind frozen fp32 PatchNorm statistics on the folded tensor-core
+        path (the conf/patch14-l.json quantiser): PatchNorm then runs inside the operand split of ``project_in`` and its
+        inverse inside the un-patchify kernel, so neither the normalised nor the de-normalised patches are written."""
+        from .lfq import LFQ
+        fe, q, n = self.extractor, self.quantizer, self.norm
+        return (isinstance(q, LFQ) and q.has_projections and not q.training and q.dim == fe.patch_size ** 2
+                and fe.dct_impl == "tc" and fe.channels == 3 and fe.patch_size >= 8 and fe.patch_size % 2 == 0
+                and not fe._hooks_overridden("_transform_image_in") and not fe._hooks_overridden("_transform_image_out")
+                and (n.frozen or not n.training) and n.median.dtype == torch.float32 and n.median.is_cuda
+                and n.patch_size == fe.patch_size and n.channels == fe.channels)
+
+    def _proj_roundtrip(self, images, ks, out_dtype):
+        """roundtrip_staged with the two PatchNorm passes folded into their neighbours (bit-identical results)."""
+        batch = self.extractor.process_batch(images, ks)
+        out = self.quantizer(batch.patches, mask=~batch.key_pad_mask,
+                             patchnorm=(self.norm, batch.patch_channels, batch.patch_positions))
+        b = batch.shallow_copy()
+        b.patches = out[0]
+        return self.extractor.postprocess_batch(b, out_dtype, denorm=self.norm), out[1]
 
     def _fused_roundtrip(self, images, ks, out_dtype):
         """encode_codes + decode_codes; the decode of a batch that kept every token reads the sign bits straight from the

@@ -211,6 +211,13 @@ int dcta_dct2_fwd_fold_codes(const void* xq_hi, const void* xq_lo, const float* 
 int dcta_unpatchify_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
                          int channels_n, int th, int tw, int p, int rows, int cols, int out_h, int out_w,
                          void* yq_hi, void* yq_lo, float* dc, void* stream);
+/* The same from NORMALISED patches, with PatchNorm.inverse_norm (patchnorm.py:167-177: x * (b*sqrt2 + eps) + median) applied
+ * on the way: equals dcta_unpatchify_fold(dcta_patchnorm_apply(inverse)) bit for bit, the de-normalised patches are never
+ * written.  median, b (channels_n, H, W, p*p); th <= H, tw <= W. */
+int dcta_unpatchify_denorm_fold(const float* patches, const int32_t* slot_map, const int32_t* img_sel, int64_t n_img,
+                                int channels_n, int th, int tw, int p, int rows, int cols, int out_h, int out_w,
+                                const float* median, const float* b, int H, int W, float eps, void* yq_hi, void* yq_lo,
+                                float* dc, void* stream);
 /* The same from LFQ codes (contract of dcta_decode_codes_split).
  *   tab_scratch [nullable]: 2 * channels*H*p*ceil(W*p/8)*8 device uint32.  When given (and c == d == p <= 16) the two
  *   values a de-quantised coefficient can take at every position are tabulated once per call instead of once per CTA. */
@@ -458,6 +465,14 @@ int dcta_ln_pos_rows(const float* x, const float* gamma, const float* beta, floa
                      const int64_t* positions, float* out, int64_t n_rows, int f, void* stream);
 int dcta_split_rows_rowscale(const float* x, const float* gamma, const float* beta, float eps, void* hi, void* lo,
                              float* row_scale, float post, int64_t n_rows, int d, int64_t ld, void* stream);
+/* The same operand split with PatchNorm.forward (frozen statistics, patchnorm.py:157-165) applied to the row first:
+ *   x (n_rows, d = z) un-normalised patches, channels (n_rows) / positions (n_rows, 2) int64 of the packed batch
+ *   (padding rows read the statistics at (0, 0, 0), like the reference), median / b (C, H, W, z), clamp [clamp_lo, clamp_hi].
+ *   The planes equal dcta_split_rows_rowscale(dcta_patchnorm_apply(x)) bit for bit; the normalised patches are never
+ *   written.  Needs d % 4 == 0, d <= 1024 and 16-byte aligned rows / tables. */
+int dcta_split_rows_patchnorm(const float* x, const int64_t* channels, const int64_t* positions, const float* median,
+                              const float* b, int C, int H, int W, float eps, float clamp_lo, float clamp_hi, void* hi,
+                              void* lo, float* row_scale, float post, int64_t n_rows, int d, int64_t ld, void* stream);
 
 /* ------------------------------------------------------------------ VectorQuantize -------- */
 /* VQ:29-33 cdist + VQ:467-469 argmax(-dist) + VQ:222-226/477 gather, never materialising the

@@ -33,7 +33,11 @@ def test_fold_supported_predicate(D):
                                           # sizes that are not multiples of 16: padded pitches; odd sizes: the middle
                                           # row / column pairs with itself
                                           (300, 452, 294, 448, 2), (300, 451, 294, 448, 2), (301, 450, 294, 448, 1),
-                                          (37, 53, 28, 42, 3), (511, 513, 448, 448, 1), (18, 18, 14, 14, 2)])
+                                          (37, 53, 28, 42, 3), (511, 513, 448, 448, 1), (18, 18, 14, 14, 2),
+                                          # K > 256: the hi plane of the basis resident, its lo tiles streamed (and the
+                                          # sliced fallback where even that does not fit)
+                                          (1024, 768, 448, 448, 2), (1000, 1016, 448, 434, 1), (801, 1023, 448, 448, 1),
+                                          (1280, 720, 448, 448, 1), (1600, 1200, 448, 448, 1)])
 def test_fold_dct_matches_float64_definition(D, h, w, kh, kw, n):
     rng = np.random.default_rng(h * 7 + w)
     x = rng.random((n, 3, h, w), dtype=np.float32) * 2 - 0.5

@@ -235,6 +235,41 @@ def test_pack_on_the_side_stream_changes_nothing(D):
     assert torch.equal(r1, r2) and torch.equal(c1, c2)
 
 
+@pytest.mark.parametrize("beta,max_seq_len,size", [(0.0, 972, 256), (0.01, 512, 256), (0.0, 700, 300)])
+def test_projection_lfq_roundtrip_is_bit_identical_to_staged(D, beta, max_seq_len, size):
+    """conf/patch14-l.json's quantiser (LFQ with 196 -> 208 -> 196 projections): PatchNorm.forward runs inside the operand
+    split of project_in and inverse_norm inside the un-patchify kernel; codes and pixels are those of the staged modules
+    (padding rows, several images per row, top-k cuts included)."""
+    import random
+    torch.manual_seed(21)
+    random.seed(5)
+    fe = D.DCTAutoencoderFeatureExtractor(3, 14, beta, 32, 32, max_seq_len)
+    pn = D.PatchNorm(32, 32, 14, 3).cuda()
+    lfq = D.LFQ(dim=196, codebook_size=8192, num_codebooks=16).cuda().eval()
+    pipe = D.TransformPipeline(fe, pn, lfq)
+    pipe.fit_norm(torch.rand(5, 3, size, size + 16).cuda(), ks=[min(600, max_seq_len)] * 5)
+    x = torch.rand(7, 3, size, size + 16).cuda()
+    assert not pipe.fusable() and pipe.proj_fusable()
+    n_tok = (size // 14) * ((size + 16) // 14) * 3
+    ks = [max(1, min(n_tok, max_seq_len, int(v))) for v in torch.randint(50, 1200, (7,))] if beta > 0 else None
+    want_rec, want_codes = pipe.roundtrip_staged(x, ks)
+    rec, codes = pipe.roundtrip(x, ks)
+    assert torch.equal(codes, want_codes)
+    assert torch.equal(rec, want_rec)
+    # the two fused entry points on their own
+    batch = fe.process_batch(x, ks)
+    from dct_autoencoder_b200.linear import _split_rows
+    raw = batch.patches.reshape(-1, 196)
+    a = _split_rows(raw, 0.5, patchnorm=(pn, batch.patch_channels, batch.patch_positions))
+    b = _split_rows(pn(batch).reshape(-1, 196), 0.5)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+    q = batch.shallow_copy()
+    q.patches = torch.randn_like(batch.patches)
+    fused = fe.postprocess_batch(q, denorm=pn)
+    q.patches = pn.inverse_norm(q)
+    assert torch.equal(fused, fe.postprocess_batch(q))
+
+
 def test_graphed_roundtrip_replays_the_eager_step(D):
     torch.manual_seed(4)
     pipe = _pipe(D, "tc")
