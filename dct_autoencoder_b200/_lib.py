@@ -107,8 +107,9 @@ SIGNATURES = {
     "dcta_lfq_commit_backward": [P, P, P, P, P, c_int64, c_int, c_float, P],
     "dcta_ln_pos_rows": [P, P, P, c_float, P, P, P, P, P, P, P, c_int64, c_int, P],
     "dcta_split_rows_rowscale": [P, P, P, c_float, P, P, P, c_float, c_int64, c_int, c_int64, P],
-    "dcta_split_rows_patchnorm": [P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, c_float, c_int64,
+    "dcta_split_rows_patchnorm": [P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, P, P, P, c_float, c_int64,
                                   c_int, c_int64, P],
+    "dcta_pack_tiles_index": [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int64, P, P, P, P, P, P],
     "dcta_unpatchify_denorm_fold": [P, P, P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int,
                                     c_int, c_float, P, P, P, P],
     "dcta_row_sumsq": [P, P, c_int64, c_int, P],
@@ -140,7 +141,7 @@ KERNELS_PER_CALL = {
     "dcta_gemm_split": 1, "dcta_lfq_project_sign": 1, "dcta_lfq_bits_to_codes": 1, "dcta_split_f32": 1, "dcta_rgb_to_ipt_split": 2, "dcta_unpatchify_split": 1,
     "dcta_split_planes_centered": 2, "dcta_split_coef_planes": 1,
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,
-    "dcta_ln_pos_rows": 1, "dcta_split_rows_rowscale": 1, "dcta_split_rows_patchnorm": 1, "dcta_unpatchify_denorm_fold": 1, "dcta_lfq_entropy_ctas": 0, "dcta_lfq_entropy_factorized": 2,
+    "dcta_ln_pos_rows": 1, "dcta_split_rows_rowscale": 1, "dcta_split_rows_patchnorm": 1, "dcta_unpatchify_denorm_fold": 1, "dcta_pack_tiles_index": 1, "dcta_lfq_entropy_ctas": 0, "dcta_lfq_entropy_factorized": 2,
     "dcta_lfq_entropy_factorized_backward": 1, "dcta_lfq_commit_backward": 2,
     "dcta_row_sumsq": 1, "dcta_vq_nearest_tc": 2, "dcta_vq_cluster_stats": 1, "dcta_resize_bilinear_aa": 1, "dcta_resize_bilinear_aa_u8": 1, "dcta_vq_ema_update": 2, "dcta_vq_kmeans_means": 1,
     "dcta_pack_codes_lfq": 2, "dcta_decode_codes_split": 1,

@@ -184,12 +184,13 @@ __global__ void __launch_bounds__(256) split_rows_rowscale_vec_kernel(const floa
     const int d4 = d >> 2, ld4 = (int)(ld >> 2);
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t t = warp0; t < n_rows; t += n_warps) {
-        const float4* src = reinterpret_cast<const float4*>(x + t * d);
+        const int64_t t_src = pn.row_src ? (int64_t)__ldg(pn.row_src + t) : t;
+        const float4* src = reinterpret_cast<const float4*>(x + (t_src < 0 ? 0 : t_src) * d);
         float4 v[CH];
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
             const int i = lane + 32 * c;
-            v[c] = i < d4 ? ld_stream(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[c] = (i < d4 && t_src >= 0) ? ld_stream(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (pn.channels != nullptr) {
             // PatchNorm.forward, frozen statistics (patchnorm.py:157-165), on the row in registers: the normalised
@@ -327,12 +328,12 @@ extern "C" int dcta_split_rows_rowscale(const float* x, const float* gamma, cons
                              "split_rows_rowscale");
 }
 
-extern "C" int dcta_split_rows_patchnorm(const float* x, const int64_t* channels, const int64_t* positions, const float* median,
-                                         const float* b, int C, int H, int W, float eps, float clamp_lo, float clamp_hi,
-                                         void* hi, void* lo, float* row_scale, float post, int64_t n_rows, int d, int64_t ld,
-                                         void* stream) {
+extern "C" int dcta_split_rows_patchnorm(const float* x, const int32_t* row_src, const int64_t* channels,
+                                         const int64_t* positions, const float* median, const float* b, int C, int H, int W,
+                                         float eps, float clamp_lo, float clamp_hi, void* hi, void* lo, float* row_scale,
+                                         float post, int64_t n_rows, int d, int64_t ld, void* stream) {
     using namespace dcta;
     DCTA_REQUIRE(channels && positions && median && b && C > 0 && H > 0 && W > 0, "split_rows_patchnorm: bad arguments");
-    const PatchNormRows pn{channels, positions, median, b, C, H, W, eps, clamp_lo, clamp_hi};
+    const PatchNormRows pn{channels, positions, median, b, C, H, W, eps, clamp_lo, clamp_hi, row_src};
     return launch_split_rows(x, nullptr, nullptr, 0.0f, hi, lo, row_scale, post, n_rows, d, ld, pn, stream, "split_rows_patchnorm");
 }

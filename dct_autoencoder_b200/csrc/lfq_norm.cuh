@@ -58,6 +58,8 @@ struct PatchNormRows {
     const float* b;
     int C, H, W;
     float eps, lo, hi;
+    const int32_t* row_src;     // nullable: row t of the operand is row row_src[t] of x (-1: a row of zeros) -- the token
+                                // gather of the packed batch (dcta_pack_tiles_index) folded into this pass
 };
 
 // *flag = nonzero iff every b[i] is finite and in [0, 1e18] (fused_lfq.cu)

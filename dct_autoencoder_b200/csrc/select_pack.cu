@@ -421,7 +421,9 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
     const int32_t* __restrict__ row_seg_start, int n_rows, int s, int tw, int channels,
     int n_tok_img, int z, float* __restrict__ patches, int64_t* __restrict__ positions,
     int64_t* __restrict__ channels_out, int64_t* __restrict__ image_ids,
-    uint8_t* __restrict__ key_pad_mask) {
+    uint8_t* __restrict__ key_pad_mask, int32_t* __restrict__ src_index = nullptr) {
+    // src_index (kTiles, nullable): the token-grid row each slot reads (-1: padding); patches may then be NULL --
+    // the consumer gathers the rows itself (dcta_split_rows_patchnorm) and the packed patches are never written
     constexpr int kUnroll = 7;
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -449,12 +451,14 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
                 }
             }
             int64_t ph = 0, pw = 0, pc = 0, image_id = 0;
+            int32_t src_row = -1;
             if (seg >= 0) {
                 const dcta_segment sg = segs[seg];
                 const int j = off - sg.offset;
                 image_id = sg.image_id;
                 if (kTiles) {
                     const int tok = order[sg.img * n_tok_img + j];
+                    src_row = (int32_t)(sg.img * n_tok_img + tok);
                     src = reinterpret_cast<const float4*>(tiles + (sg.img * n_tok_img + tok) * z);
                     const int tile = tok / channels;
                     pc = tok - tile * channels;
@@ -472,7 +476,9 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(
             channels_out[slot] = pc;
             if (image_ids) image_ids[slot] = image_id;
             if (key_pad_mask) key_pad_mask[slot] = seg < 0;
+            if (src_index) src_index[slot] = src_row;
         }
+        if (patches == nullptr) continue;
         const int n4 = (int)min((int64_t)32, total - slot0) * z4;
         float4* dst = reinterpret_cast<float4*>(patches + slot0 * z);
         const unsigned long long src_bits = (unsigned long long)src;
@@ -600,6 +606,21 @@ extern "C" int dcta_pack_tiles(const float* tiles, const int32_t* order, const d
     else
         pack_kernel<true, 1><<<grid, 256, 0, as_stream(stream)>>>(tiles, order, nullptr, nullptr, nullptr, segs, row_seg_start, n_rows, s, tw, channels, n_tok_img, z, patches, positions, channels_out, image_ids, key_pad_mask);
     return check_launch("pack_tiles");
+}
+
+extern "C" int dcta_pack_tiles_index(const int32_t* order, const dcta_segment* segs, const int32_t* row_seg_start, int n_rows,
+                                     int s, int th, int tw, int channels, int64_t n_img, int64_t* positions,
+                                     int64_t* channels_out, int64_t* image_ids, uint8_t* key_pad_mask, int32_t* src_index,
+                                     void* stream) {
+    DCTA_REQUIRE(order && segs && row_seg_start && positions && channels_out && src_index, "pack_tiles_index: null pointer");
+    DCTA_REQUIRE(n_rows >= 0 && s > 0 && th > 0 && tw > 0 && channels > 0, "pack_tiles_index: bad sizes");
+    DCTA_REQUIRE(n_img * th * tw * channels < (1ll << 31), "pack_tiles_index: more than 2^31 tokens in the grid");
+    if (n_rows == 0) return DCTA_OK;
+    const int n_tok_img = th * tw * channels;
+    pack_rows_kernel<true><<<grid_for((int64_t)n_rows * s, 256), 256, 0, as_stream(stream)>>>(
+        nullptr, order, nullptr, nullptr, nullptr, segs, row_seg_start, n_rows, s, tw, channels, n_tok_img, 4, nullptr, positions,
+        channels_out, image_ids, key_pad_mask, src_index);
+    return check_launch("pack_tiles_index");
 }
 
 extern "C" int dcta_pack_lists(const float* const* src_patches, const int64_t* const* src_positions,

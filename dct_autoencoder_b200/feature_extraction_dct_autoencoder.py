@@ -414,6 +414,38 @@ class DCTAutoencoderFeatureExtractor:
                           patch_sizes=[(ph, pw)] * b, original_sizes=[(h, w)] * b,
                           _data={}, _row_num_images=[len(r) for r in rows])
 
+    @torch.no_grad()
+    def _process_batch_index(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None):
+        """``process_batch`` without the packed patches: (DCTPatches with ``patches=None``, token grid (tokens, p*p),
+        row_src (rows, s) int32 = the token-grid row of every slot, -1 for padding).  For consumers that stream the token
+        rows anyway and gather them themselves (the operand split of the LFQ projection)."""
+        x = to_device_pixels(images, self._dev(images))
+        b, c, h, w = x.shape
+        ph, pw, th, tw = self._geometry(h, w)
+        tiles, maxabs = self._token_grid(x, want_maxabs=True)
+        order = self._sorted_order(tiles, maxabs)
+        n_tok = th * tw * c
+        if ks is None:
+            ks = [self._choose_k(n_tok) for _ in range(b)]
+        ks = self._check_ks(ks, b, n_tok)
+        state = self._next_fit(ks)
+        rows = state.rows + ([state.row] if state.row else [])
+        tab, offs = self._tables(rows, dict(enumerate(ks)), x.device)
+        n_rows, s = len(rows), self.max_seq_len
+        pos = torch.empty((n_rows, s, 2), dtype=torch.int64, device=x.device)
+        chan = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
+        ids = torch.empty((n_rows, s), dtype=torch.int64, device=x.device)
+        pad = torch.empty((n_rows, s), dtype=torch.bool, device=x.device)
+        row_src = torch.empty((n_rows, s), dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.call("dcta_pack_tiles_index", _lib.ptr(order), tab.data_ptr() + offs[0], tab.data_ptr() + offs[1], n_rows, s,
+                      th, tw, c, b, _lib.ptr(pos), _lib.ptr(chan), _lib.ptr(ids), _lib.ptr(pad), _lib.ptr(row_src),
+                      _lib.stream_ptr(x.device))
+        batch = DCTPatches(patches=None, key_pad_mask=pad, batched_image_ids=ids, patch_channels=chan, patch_positions=pos,
+                           patch_sizes=[(ph, pw)] * b, original_sizes=[(h, w)] * b, _data={},
+                           _row_num_images=[len(r) for r in rows])
+        return batch, tiles.reshape(-1, self.patch_size ** 2), row_src
+
     # ------------------------------------------------------------------ fused PatchNorm + LFQ path
     def _lfq_fusable(self, norm, lfq) -> bool:
         """Projection-free LFQ in eval mode on frozen (or eval) fp32 PatchNorm tables that were built for

@@ -44,12 +44,16 @@ def _split_weight(weight: torch.Tensor):
     return out
 
 
-def _split_rows(x2: torch.Tensor, w_inv: float, ln: Optional[nn.LayerNorm] = None, patchnorm=None):
+def _split_rows(x2: torch.Tensor, w_inv: float, ln: Optional[nn.LayerNorm] = None, patchnorm=None, row_src=None):
     """fp32 rows (t, k) -> fp16 hi/lo planes (t, round8(k)) scaled per row by a power of two + the factors that undo the
     scaling (times ``w_inv``); ``ln``: a LayerNorm applied to the rows first; ``patchnorm = (PatchNorm, channels (t,),
     positions (t, 2))``: the rows are un-normalised patches and ``PatchNorm.forward`` (frozen statistics) is applied to
-    them in the same pass (``dcta_split_rows_patchnorm``)."""
+    them in the same pass (``dcta_split_rows_patchnorm``); ``row_src`` (t,) int32 (with ``patchnorm``): operand row i is
+    row ``row_src[i]`` of ``x2`` (zeros where -1) -- ``x2`` is then the token grid and the packed patches never exist."""
     t, k = x2.shape
+    if row_src is not None:
+        assert patchnorm is not None and row_src.dtype == torch.int32 and row_src.is_contiguous()
+        t = row_src.numel()
     dev = x2.device
     ld = _round8(k)
     a_hi = torch.empty((t, ld), dtype=torch.float16, device=dev)
@@ -66,7 +70,7 @@ def _split_rows(x2: torch.Tensor, w_inv: float, ln: Optional[nn.LayerNorm] = Non
         ps = positions.reshape(-1, 2).to(torch.int64).contiguous()
         assert ch.numel() == t and ps.shape[0] == t and k == norm.patch_size ** 2
         with torch.cuda.device(dev):
-            _lib.call("dcta_split_rows_patchnorm", _lib.ptr(x2), _lib.ptr(ch), _lib.ptr(ps), _lib.ptr(norm.median.data),
+            _lib.call("dcta_split_rows_patchnorm", _lib.ptr(x2), _lib.ptr(row_src), _lib.ptr(ch), _lib.ptr(ps), _lib.ptr(norm.median.data),
                       _lib.ptr(norm.b.data), norm.channels, norm.max_patch_h, norm.max_patch_w, float(norm.eps),
                       float(norm.min_val), float(norm.max_val), _lib.ptr(a_hi), _lib.ptr(a_lo), _lib.ptr(row_scale),
                       float(w_inv), t, k, ld, _lib.stream_ptr(dev))
@@ -110,7 +114,7 @@ def linear_rows(x: torch.Tensor, weight: torch.Tensor, ln: Optional[nn.LayerNorm
 
 @torch.no_grad()
 def lfq_project_quantize(x: torch.Tensor, project_in: nn.Linear, project_out: Optional[nn.Linear], num_codebooks: int,
-                         codebook_dim: int, codebook_scale: float, patchnorm=None):
+                         codebook_dim: int, codebook_scale: float, patchnorm=None, row_src=None):
     """LFQ with projections in eval (lfq.py:136-227): ``project_in`` + bias + sign + index packing in ONE GEMM kernel
     (``dcta_lfq_project_sign``; the (t, c*d) activations are never written as fp32), the +-scale codes as an exact fp16
     operand, ``project_out`` + bias as a two-MMA GEMM on it.  Returns (project_out(q) (..., dim) fp32 or the codes
@@ -120,11 +124,13 @@ def lfq_project_quantize(x: torch.Tensor, project_in: nn.Linear, project_out: Op
     n = num_codebooks * codebook_dim
     assert project_in.weight.shape == (n, k)
     x2 = to_device_f32(x).reshape(-1, k)
-    t = x2.shape[0]
+    t = x2.shape[0] if row_src is None else row_src.numel()
+    lead = x.shape[:-1] if row_src is None else tuple(row_src.shape)       # row_src (rows, s): the packed batch's shape
     dev = x2.device
     w_hi, w_lo, w_inv = _split_weight(project_in.weight)
     ld = _round8(k)
-    a_hi, a_lo, row_scale = _split_rows(x2, w_inv, patchnorm=patchnorm)     # patchnorm: see _split_rows
+    a_hi, a_lo, row_scale = _split_rows(x2, w_inv, patchnorm=patchnorm,      # patchnorm, row_src: see _split_rows
+                                        row_src=None if row_src is None else row_src.reshape(-1))
     ldq = _round8(n)
     q_hi = torch.empty((t, ldq), dtype=torch.float16, device=dev) if ldq == n else torch.zeros((t, ldq), dtype=torch.float16, device=dev)
     n_tiles = (n + 127) // 128
@@ -153,7 +159,7 @@ def lfq_project_quantize(x: torch.Tensor, project_in: nn.Linear, project_out: Op
                 # A = q_hi (exact fp16, no lo plane); the weight's scale is undone by alpha
                 _lib.call("dcta_gemm_split", q_hi[r0:].data_ptr(), None, rows, ldq, 0, _lib.ptr(o_hi), _lib.ptr(o_lo), dim, ldq, 0,
                           n, 1, None, float(o_inv), _lib.ptr(b_out), out[r0:].data_ptr(), dim, 0, st)
-    return out.reshape(x.shape[:-1] + (out.shape[-1],)), idx.reshape(x.shape[:-1] + (num_codebooks,))
+    return out.reshape(tuple(lead) + (out.shape[-1],)), idx.reshape(tuple(lead) + (num_codebooks,))
 
 
 @torch.no_grad()

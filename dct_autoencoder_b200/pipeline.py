@@ -130,12 +130,16 @@ class TransformPipeline:
 
     def _proj_roundtrip(self, images, ks, out_dtype):
         """roundtrip_staged with the two PatchNorm passes folded into their neighbours (bit-identical results)."""
-        batch = self.extractor.process_batch(images, ks)
-        out = self.quantizer(batch.patches, mask=~batch.key_pad_mask,
-                             patchnorm=(self.norm, batch.patch_channels, batch.patch_positions))
-        b = batch.shallow_copy()
-        b.patches = out[0]
-        return self.extractor.postprocess_batch(b, out_dtype, denorm=self.norm), out[1]
+        from .linear import lfq_project_quantize
+        q = self.quantizer
+        # the token gather of the packing step happens inside the operand split too: the packed patches never exist
+        batch, grid, row_src = self.extractor._process_batch_index(images, ks)
+        out, codes = lfq_project_quantize(grid, q.project_in, q.project_out, q.num_codebooks, q.codebook_dim, q.codebook_scale,
+                                          patchnorm=(self.norm, batch.patch_channels, batch.patch_positions), row_src=row_src)
+        if not q.keep_num_codebooks_dim:         # lfq.py:224-225
+            codes = codes[..., 0]
+        batch.patches = out
+        return self.extractor.postprocess_batch(batch, out_dtype, denorm=self.norm), codes
 
     def _fused_roundtrip(self, images, ks, out_dtype):
         """encode_codes + decode_codes; the decode of a batch that kept every token reads the sign bits straight from the

@@ -308,6 +308,12 @@ int dcta_pack_tiles(const float* tiles, const int32_t* order, const dcta_segment
                     const int32_t* row_seg_start, int n_rows, int s, int th, int tw, int channels,
                     int z, float* patches, int64_t* positions, int64_t* channels_out,
                     int64_t* image_ids, uint8_t* key_pad_mask, void* stream);
+/* The bookkeeping of dcta_pack_tiles without the copy: positions / channels_out / image_ids / key_pad_mask as above and
+ *   src_index (n_rows, s) int32 = the row of the token grid tiles (n_img * th*tw*channels, z) each slot would have read
+ *   (-1 for padding slots).  A consumer that streams the rows anyway gathers them itself (dcta_split_rows_patchnorm). */
+int dcta_pack_tiles_index(const int32_t* order, const dcta_segment* segs, const int32_t* row_seg_start, int n_rows, int s,
+                          int th, int tw, int channels, int64_t n_img, int64_t* positions, int64_t* channels_out,
+                          int64_t* image_ids, uint8_t* key_pad_mask, int32_t* src_index, void* stream);
 /* Same packing for per-image token lists produced earlier by preprocess (FE:180-287 iter_batches
  * path): src_* are device arrays of n_src device pointers, indexed by seg.img. */
 int dcta_pack_lists(const float* const* src_patches, const int64_t* const* src_positions,
@@ -468,11 +474,14 @@ int dcta_split_rows_rowscale(const float* x, const float* gamma, const float* be
 /* The same operand split with PatchNorm.forward (frozen statistics, patchnorm.py:157-165) applied to the row first:
  *   x (n_rows, d = z) un-normalised patches, channels (n_rows) / positions (n_rows, 2) int64 of the packed batch
  *   (padding rows read the statistics at (0, 0, 0), like the reference), median / b (C, H, W, z), clamp [clamp_lo, clamp_hi].
- *   The planes equal dcta_split_rows_rowscale(dcta_patchnorm_apply(x)) bit for bit; the normalised patches are never
- *   written.  Needs d % 4 == 0, d <= 1024 and 16-byte aligned rows / tables. */
-int dcta_split_rows_patchnorm(const float* x, const int64_t* channels, const int64_t* positions, const float* median,
-                              const float* b, int C, int H, int W, float eps, float clamp_lo, float clamp_hi, void* hi,
-                              void* lo, float* row_scale, float post, int64_t n_rows, int d, int64_t ld, void* stream);
+ *   row_src [nullable] (n_rows) int32: operand row t is row row_src[t] of x, or a row of zeros where it is -1 -- x is then
+ *   the TOKEN GRID and row_src the output of dcta_pack_tiles_index, i.e. the gather of FE:516-605 happens in this pass.
+ *   The planes equal dcta_split_rows_rowscale(dcta_patchnorm_apply(packed patches)) bit for bit; neither the packed nor
+ *   the normalised patches are written.  Needs d % 4 == 0, d <= 1024 and 16-byte aligned rows / tables. */
+int dcta_split_rows_patchnorm(const float* x, const int32_t* row_src, const int64_t* channels, const int64_t* positions,
+                              const float* median, const float* b, int C, int H, int W, float eps, float clamp_lo,
+                              float clamp_hi, void* hi, void* lo, float* row_scale, float post, int64_t n_rows, int d,
+                              int64_t ld, void* stream);
 
 /* ------------------------------------------------------------------ VectorQuantize -------- */
 /* VQ:29-33 cdist + VQ:467-469 argmax(-dist) + VQ:222-226/477 gather, never materialising the
