@@ -144,7 +144,7 @@ class TransformPipeline:
     def _fused_roundtrip(self, images, ks, out_dtype):
         """encode_codes + decode_codes; the decode of a batch that kept every token reads the sign bits straight from the
         forward pass's code grid (no slot map, no gather through the packed codes; same pixels)."""
-        dev = images.device if images.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        dev = self.extractor._dev(images)             # where the extractor will run (host images are uploaded there)
         side = self._pack_stream(dev) if self.overlap_pack else None
         batch, codes, grid = self.extractor.process_batch_to_codes(images, self.norm, self.quantizer, ks, return_grid=True,
                                                                    pack_stream=side)
