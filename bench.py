@@ -342,9 +342,19 @@ def e2e_host(ctx, pipe, x, steps, chunk):
     h_rec = torch.empty(tuple(x.shape), dtype=torch.float32).pin_memory()
     s, c = pipe.extractor.max_seq_len, pipe.quantizer.num_codebooks
     h_codes = torch.empty((B, s, c), dtype=torch.int64).pin_memory()
-    ms = ctx.timed(lambda: pipe.roundtrip_host(hx, h_rec, h_codes, chunk=chunk), steps, 2)
+    marks = []
+
+    def host_step():
+        pipe.roundtrip_host(hx, h_rec, h_codes, chunk=chunk)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
+    ms = ctx.timed(host_step, steps, 3)
+    torch.cuda.synchronize()
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(len(marks) - steps - 1, len(marks) - 1)]
     fp32 = dict(value=ctx.world * B * steps / (ms / 1e3), unit=UNIT, h2d_bytes_per_step=hx.numel() * 4 * ctx.world,
                 d2h_bytes_per_step=(h_rec.numel() * 4 + h_codes.numel() * 8) * ctx.world, ms_per_step=ms / steps,
+                ms_per_step_min=min(per_step), ms_per_step_max=max(per_step),
                 contract="the reference's types: fp32 images in, fp32 images + int64 codes out")
     # the floor the link of THIS box sets for those bytes (both directions busy at once), and how close the step is
     floor_ms = max(hx.numel() * 4, h_rec.numel() * 4 + h_codes.numel() * 8) / (link["both_GBps_per_direction"] * 1e6)
