@@ -22,6 +22,7 @@
 //     warps 2..9: epilogue, two warps per TMEM lane quarter; the 512 TMEM columns hold two accumulators
 //     so the epilogue of one tile overlaps the main loop of the next.
 #include "lfq_norm.cuh"
+#include <algorithm>
 #include "tc_ptx.cuh"
 
 namespace dcta {
@@ -1254,52 +1255,52 @@ __device__ __forceinline__ void unbutterfly4(const float (&z)[4], float dcv, flo
 // quadrant planes z[s][plane][h'][w'] -> un-folded IPT -> RGB (util.py:85-97); COLOR = false: plain planes out
 template <bool COLOR, typename TOut = float>     // TOut = uint8_t: 8-bit pixels as torchvision's save_image stores them
 __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ z, const float* __restrict__ dc,
-                                                     TOut* __restrict__ out, int64_t n_items, int h, int w, Mat3 A, Mat3 B) {
+                                                     TOut* __restrict__ out, int64_t n_items, int h, int w, Mat3 A, Mat3 B,
+                                                     int64_t item0) {
     constexpr int CH = COLOR ? 3 : 1;
-    const int h2 = h >> 1, w8 = w >> 3;
-    const int64_t total = n_items * h2 * w8;
-    const int64_t plane4 = (int64_t)h * w / 4, q4 = (int64_t)h2 * (w >> 1) / 4;
+    const int h2 = h >> 1, w8 = w >> 3, w4 = w >> 2;
+    const uint32_t plane4 = (uint32_t)h * w4, q4 = (uint32_t)h2 * w8;      // in float4 units
     const int64_t n_planes = n_items * CH;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int xv = (int)(i % w8);
-        const int64_t t = i / w8;
-        const int y = (int)(t % h2);
-        const int64_t item = t / h2;
-        float px[4][CH][4];          // [corner][channel][pixel]
+    // grid: (blocks per item, items) -- one (item, h', 4 columns) per thread, 32-bit index arithmetic inside an item
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= q4) return;
+    const int y = (int)(idx / (uint32_t)w8);
+    const int xv = (int)(idx - (uint32_t)y * w8);
+    const int64_t item = item0 + blockIdx.y;
+    float px[4][CH][4];          // [corner][channel][pixel]
 #pragma unroll
-        for (int c = 0; c < CH; ++c) {
-            const int64_t pl = item * CH + c;
-            const float dcv = dc ? __ldg(dc + pl) : 0.0f;
-            const int64_t o = (pl * h2 + y) * (int64_t)w8 + xv;
-            float4 q[4];
+    for (int c = 0; c < CH; ++c) {
+        const int64_t pl = item * CH + c;
+        const float dcv = dc ? __ldg(dc + pl) : 0.0f;
+        const float4* zp = reinterpret_cast<const float4*>(z) + (pl * q4 + idx);
+        float4 q[4];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) q[s] = ld_stream(reinterpret_cast<const float4*>(z) + s * n_planes * q4 + o);
-            const float qa[4][4] = {{q[0].x, q[0].y, q[0].z, q[0].w}, {q[1].x, q[1].y, q[1].z, q[1].w},
-                                    {q[2].x, q[2].y, q[2].z, q[2].w}, {q[3].x, q[3].y, q[3].z, q[3].w}};
+        for (int s = 0; s < 4; ++s) q[s] = ld_stream(zp + s * n_planes * (int64_t)q4);
+        const float qa[4][4] = {{q[0].x, q[0].y, q[0].z, q[0].w}, {q[1].x, q[1].y, q[1].z, q[1].w},
+                                {q[2].x, q[2].y, q[2].z, q[2].w}, {q[3].x, q[3].y, q[3].z, q[3].w}};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float zz[4] = {qa[0][j], qa[1][j], qa[2][j], qa[3][j]};
+            unbutterfly4(zz, dcv, px[0][c][j], px[1][c][3 - j], px[2][c][j], px[3][c][3 - j]);
+        }
+    }
+    TOut* dst = out + item * CH * (int64_t)plane4 * 4;
+    const uint32_t top = (uint32_t)y * w4, bot = (uint32_t)(h - 1 - y) * w4;
+    const uint32_t xr = w4 - 1 - xv;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (COLOR) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float zz[4] = {qa[0][j], qa[1][j], qa[2][j], qa[3][j]};
-                unbutterfly4(zz, dcv, px[0][c][j], px[1][c][3 - j], px[2][c][j], px[3][c][3 - j]);
+                float r, gg, bb;
+                ipt_px_to_rgb_f(px[k][0][j], px[k][CH > 1 ? 1 : 0][j], px[k][CH > 2 ? 2 : 0][j], A, B, r, gg, bb);
+                px[k][0][j] = r; px[k][CH > 1 ? 1 : 0][j] = gg; px[k][CH > 2 ? 2 : 0][j] = bb;
             }
         }
-        TOut* dst = out + item * CH * plane4 * 4;
-        const int64_t top = (int64_t)y * (w >> 2), bot = (int64_t)(h - 1 - y) * (w >> 2);
-        const int xr = (w >> 2) - 1 - xv;
+        const uint32_t o = ((k & 2) ? bot : top) + ((k & 1) ? xr : (uint32_t)xv);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (COLOR) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float r, gg, bb;
-                    ipt_px_to_rgb_f(px[k][0][j], px[k][CH > 1 ? 1 : 0][j], px[k][CH > 2 ? 2 : 0][j], A, B, r, gg, bb);
-                    px[k][0][j] = r; px[k][CH > 1 ? 1 : 0][j] = gg; px[k][CH > 2 ? 2 : 0][j] = bb;
-                }
-            }
-            const int64_t o = ((k & 2) ? bot : top) + ((k & 1) ? xr : xv);
-#pragma unroll
-            for (int c = 0; c < CH; ++c)
-                st_px4(dst, c * plane4 + o, make_float4(px[k][c][0], px[k][c][1], px[k][c][2], px[k][c][3]));
-        }
+        for (int c = 0; c < CH; ++c)
+            st_px4(dst, c * plane4 + o, make_float4(px[k][c][0], px[k][c][1], px[k][c][2], px[k][c][3]));
     }
 }
 
@@ -2430,7 +2431,9 @@ static int unfold_ipt_to_rgb_any(const float* z, const float* dc, TOut* rgb, int
     Mat3 A, B;
     for (int i = 0; i < 9; ++i) { A.m[i] = m_ipt_inv_host[i]; B.m[i] = m_lms2rgb_host[i]; }
     if (fold_fast_dims(h, w) && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0)
-        unfold_kernel<true, TOut><<<grid_for(n_img * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, rgb, n_img, h, w, A, B);
+        for (int64_t i0 = 0; i0 < n_img; i0 += 65535)          // grid.y limit
+            unfold_kernel<true, TOut><<<dim3((unsigned)ceil_div((int64_t)(h / 2) * (w / 8), 256), (unsigned)std::min<int64_t>(65535, n_img - i0)),
+                                        256, 0, as_stream(stream)>>>(z, dc, rgb, n_img, h, w, A, B, i0);
     else
         unfold_any_kernel<true, TOut><<<grid_for(n_img * fold_half(h) * fold_half(w), 256), 256, 0, as_stream(stream)>>>(
             z, dc, rgb, n_img, h, w, A, B);
@@ -2453,7 +2456,9 @@ extern "C" int dcta_unfold_planes(const float* z, const float* dc, float* x, int
     if (n_planes == 0) return DCTA_OK;
     Mat3 A{}, B{};
     if (fold_fast_dims(h, w) && (reinterpret_cast<uintptr_t>(x) & 15) == 0)
-        unfold_kernel<false><<<grid_for(n_planes * (h / 2) * (w / 8), 256), 256, 0, as_stream(stream)>>>(z, dc, x, n_planes, h, w, A, B);
+        for (int64_t i0 = 0; i0 < n_planes; i0 += 65535)       // grid.y limit
+            unfold_kernel<false><<<dim3((unsigned)ceil_div((int64_t)(h / 2) * (w / 8), 256), (unsigned)std::min<int64_t>(65535, n_planes - i0)),
+                                   256, 0, as_stream(stream)>>>(z, dc, x, n_planes, h, w, A, B, i0);
     else
         unfold_any_kernel<false, float><<<grid_for(n_planes * fold_half(h) * fold_half(w), 256), 256, 0, as_stream(stream)>>>(
             z, dc, x, n_planes, h, w, A, B);
