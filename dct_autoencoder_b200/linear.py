@@ -4,6 +4,8 @@ bias, position-embedding gathers) in csrc/glue.cu.  Inference only (``torch.no_g
 (lfq.py:60-62, 164, 212; vector_quantize.py:869, 1028)."""
 from typing import Optional
 
+import contextlib
+
 import torch
 from torch import nn
 
@@ -81,6 +83,17 @@ def _split_rows(x2: torch.Tensor, w_inv: float, ln: Optional[nn.LayerNorm] = Non
     return a_hi, a_lo, row_scale
 
 
+_side_streams = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    """One extra stream per device for output-only work that runs beside the next GEMM."""
+    key = str(dev)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(dev)
+    return _side_streams[key]
+
+
 _GEMM_ROWS = 65535 * 128            # rows per launch of the basic tcgen05 GEMM (grid.y limit)
 
 
@@ -144,7 +157,14 @@ def lfq_project_quantize(x: torch.Tensor, project_in: nn.Linear, project_out: Op
             _lib.call("dcta_lfq_project_sign", a_hi[r0:].data_ptr(), a_lo[r0:].data_ptr(), rows, ld, _lib.ptr(w_hi), _lib.ptr(w_lo),
                       n, ld, k, row_scale[r0:].data_ptr(), _lib.ptr(b_in), float(codebook_scale), q_hi[r0:].data_ptr(), ldq,
                       bits[r0:].data_ptr(), st)
-        _lib.call("dcta_lfq_bits_to_codes", _lib.ptr(bits), t, n, num_codebooks, codebook_dim, _lib.ptr(idx), st)
+        # the indices are an output only (project_out reads the +-scale operand): pack them on a side stream beside
+        # the second GEMM; `bits` and `idx` were allocated on this stream and stay referenced until the join below
+        side = None if (project_out is None or _lib.profile_active()) else _side_stream(dev)
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(dev))
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            _lib.call("dcta_lfq_bits_to_codes", _lib.ptr(bits), t, n, num_codebooks, codebook_dim, _lib.ptr(idx),
+                      _lib.stream_ptr(dev))
         del a_hi, a_lo
         if project_out is None:
             out = q_hi[:, :n].float()
@@ -159,6 +179,8 @@ def lfq_project_quantize(x: torch.Tensor, project_in: nn.Linear, project_out: Op
                 # A = q_hi (exact fp16, no lo plane); the weight's scale is undone by alpha
                 _lib.call("dcta_gemm_split", q_hi[r0:].data_ptr(), None, rows, ldq, 0, _lib.ptr(o_hi), _lib.ptr(o_lo), dim, ldq, 0,
                           n, 1, None, float(o_inv), _lib.ptr(b_out), out[r0:].data_ptr(), dim, 0, st)
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
     return out.reshape(tuple(lead) + (out.shape[-1],)), idx.reshape(tuple(lead) + (num_codebooks,))
 
 
