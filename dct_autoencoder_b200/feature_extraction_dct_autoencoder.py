@@ -472,6 +472,7 @@ class DCTAutoencoderFeatureExtractor:
         that stream (the decode that follows only needs the code grid, so both run beside it); the caller MUST call
         ``join_pack()`` on the stream it uses before touching ``codes`` or the batch's tensors."""
         assert self._lfq_fusable(norm, lfq)
+        self.join_pack()          # a caller that forgot: never drop the references of work still running on a side stream
         x = to_device_pixels(images, self._dev(images), keep_u8=True)     # uint8 pixels stay bytes until the colour kernel
         if norm.median.device != x.device:
             raise _lib.DctaError(f"PatchNorm tables live on {norm.median.device}, the images on {x.device}")
