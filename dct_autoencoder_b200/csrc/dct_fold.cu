@@ -614,7 +614,10 @@ struct CodesArgs {
     int n_data;             // data rows per pair tile = tokens_per_tile * p  (MMA N, multiple of 16, <= 256)
     int tokens_per_tile;
     uint32_t basis_bytes;   // one CTA's resident basis plane (hi or lo): num_kb * 128 * 64
-    uint32_t stage_bytes;   // one ring stage: this CTA's n_data/2 data rows, hi then lo
+    uint32_t stage_bytes;   // one ring stage: this CTA's n_data/2 data rows, hi then lo (+ the basis lo tile, lo_streamed)
+    int lo_streamed;        // 1: only the hi plane of the basis is resident, the lo tile of each k block rides in the ring
+                            // at offset lo_off of the stage (K too long for both planes: 1024-sample axes)
+    uint32_t lo_off;
     int p, channels, tiles_h, tiles_w;
     int batch;                  // images: the data rows are ordered [channel][token column tw][image][pj]
     float alpha;
@@ -805,8 +808,8 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* basis_hi = smem;
-    uint8_t* basis_lo = smem + g.basis_bytes;
-    uint8_t* ring = smem + 2 * g.basis_bytes;
+    uint8_t* basis_lo = smem + g.basis_bytes;                          // unused when lo_streamed
+    uint8_t* ring = smem + (g.lo_streamed ? 1 : 2) * g.basis_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -842,10 +845,10 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer
         const uint32_t basis_bar_leader = mapa_u32(smem_u32(&basis_bar), 0);
-        if (rank == 0) mbar_expect_tx(&basis_bar, 4 * g.basis_bytes);
+        if (rank == 0) mbar_expect_tx(&basis_bar, (g.lo_streamed ? 2 : 4) * g.basis_bytes);
         for (int kb = 0; kb < g.num_kb; ++kb) {          // this CTA's 128 basis rows (rows past n_valid are zero-filled)
             tma_load_3d_2sm(&map_b_hi, basis_bar_leader, basis_hi + kb * F_ATILE, kb * FK, (int)rank * 128, grp);
-            tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * F_ATILE, kb * FK, (int)rank * 128, grp);
+            if (!g.lo_streamed) tma_load_3d_2sm(&map_b_lo, basis_bar_leader, basis_lo + kb * F_ATILE, kb * FK, (int)rank * 128, grp);
         }
         const uint32_t full_leader0 = mapa_u32(smem_u32(&full_bar[0]), 0);
         int s = 0;
@@ -856,9 +859,10 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
                 mbar_wait(&empty_bar[s], ph);
                 uint8_t* st = ring + s * g.stage_bytes;
                 const uint32_t full_leader = full_leader0 + 8u * s;
-                if (rank == 0) mbar_expect_tx(&full_bar[s], 4 * dtile);
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 4 * dtile + (g.lo_streamed ? 2u * F_ATILE : 0u));
                 tma_load_3d_2sm(&map_d_hi, full_leader, st, kb * FK, row0, grp);
                 tma_load_3d_2sm(&map_d_lo, full_leader, st + dtile, kb * FK, row0, grp);
+                if (g.lo_streamed) tma_load_3d_2sm(&map_b_lo, full_leader, st + g.lo_off, kb * FK, (int)rank * 128, grp);
                 if (++s == g.stages) { s = 0; ph ^= 1u; }
             }
         }
@@ -882,10 +886,11 @@ fold_codes_kernel(const __grid_constant__ CUtensorMap map_d_hi, const __grid_con
                 mbar_wait_cluster(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t d16 = ring16 + (uint32_t)s * stage16;
+                const uint32_t al16 = g.lo_streamed ? d16 + (g.lo_off >> 4) : bl + a16;
 #pragma unroll
                 for (int k = 0; k < FK / 16; ++k) {
                     const uint64_t a_hi = smem_desc_sw64_from_lo(bh + a16 + 2 * k);
-                    const uint64_t a_lo = smem_desc_sw64_from_lo(bl + a16 + 2 * k);
+                    const uint64_t a_lo = smem_desc_sw64_from_lo(al16 + 2 * k);
                     const uint64_t b_hi = smem_desc_sw64_from_lo(d16 + 2 * k);
                     const uint64_t b_lo = smem_desc_sw64_from_lo(d16 + dtile16 + 2 * k);
                     // the same sequence of partial sums as fold_gemm_kernel (data_lo*basis_hi, data_hi*basis_lo,
@@ -1055,7 +1060,15 @@ static int launch_fold_codes(const FoldOperand& Data, int64_t rows_per_seg, cons
     g.num_kb = (int)ceil_div(K, FK);
     g.basis_bytes = (uint32_t)g.num_kb * F_ATILE;
     g.stage_bytes = (uint32_t)ceil_div((int64_t)g.n_data * 64, 1024) * 1024;      // hi + lo halves of n_data/2 rows each
-    const int64_t stages = (F_SMEM_LIMIT - 1024 - 2 * (int64_t)g.basis_bytes) / g.stage_bytes;
+    int64_t stages = (F_SMEM_LIMIT - 1024 - 2 * (int64_t)g.basis_bytes) / g.stage_bytes;
+    g.lo_streamed = 0;
+    g.lo_off = 0;
+    if (stages < 3) {             // long K: hi plane resident, lo tiles through the ring (see fold_geometry)
+        g.lo_streamed = 1;
+        g.lo_off = g.stage_bytes;
+        g.stage_bytes += F_ATILE;
+        stages = (F_SMEM_LIMIT - 1024 - (int64_t)g.basis_bytes) / g.stage_bytes;
+    }
     if (stages < 3 || 4ll * g.basis_bytes >= (1 << 20) || rows_per_seg >= (1ll << 31) - 256) return DCTA_ERR_UNSUPPORTED;
     g.stages = (int)(stages < F_MAX_STAGES ? stages : F_MAX_STAGES);
     CUtensorMap md_hi, md_lo, mb_hi, mb_lo;
@@ -1064,7 +1077,7 @@ static int launch_fold_codes(const FoldOperand& Data, int64_t rows_per_seg, cons
     if ((rc = make_map3(&md_lo, Data.lo, K, rows_per_seg, 2, Data.ld, Data.seg_stride, g.n_data / 2))) return rc;
     if ((rc = make_map3(&mb_hi, Bas.hi, K, n_valid, 2, Bas.ld, Bas.seg_stride, 128))) return rc;
     if ((rc = make_map3(&mb_lo, Bas.lo, K, n_valid, 2, Bas.ld, Bas.seg_stride, 128))) return rc;
-    const int smem_bytes = 1024 + 2 * (int)g.basis_bytes + g.stages * (int)g.stage_bytes;
+    const int smem_bytes = 1024 + (g.lo_streamed ? 1 : 2) * (int)g.basis_bytes + g.stages * (int)g.stage_bytes;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -2189,9 +2202,10 @@ extern "C" int dcta_fold_codes_supported(int h, int w, int kh, int kw, int tile_
     int tokens = 256 / tile_p;
     while (tokens > 0 && (tokens * tile_p) % 16) --tokens;
     if (tokens < 2) return 0;
-    const int64_t basis = ceil_div(h / 2, FK) * (int64_t)F_ATILE;
+    const int64_t basis = ceil_div(fold_half(h), FK) * (int64_t)F_ATILE;
     const int64_t stage = ceil_div((int64_t)tokens * tile_p * 64, 1024) * 1024;
-    return (F_SMEM_LIMIT - 1024 - 2 * basis) / stage >= 3 && 4 * basis < (1 << 20);
+    return ((F_SMEM_LIMIT - 1024 - 2 * basis) / stage >= 3 || (F_SMEM_LIMIT - 1024 - basis) / (stage + F_ATILE) >= 3) &&
+           4 * basis < (1 << 20);
 }
 
 // forward straight to LFQ code words (one codebook per patch row: c == d == tile_p): the pass-2 epilogue forms

@@ -106,6 +106,8 @@ def test_any_image_size_runs_on_the_folded_tensor_core_path(D, h, w):
     (0.0, 3072, (128, 128), 4, (4, 4)),        # vector kernel, several codebooks per 32-bit word
     (0.02, 300, (96, 120), 4, (2, 8)),         # codebook != patch row
     (0.0, 3072, (96, 96), 3, (3, 3)),          # z % 4 != 0: scalar kernel
+    # 1024-sample axes (K = 512): only the hi plane of the basis is resident in both forward kernels (BASELINE config 3)
+    (0.0, 1024, (1024, 1024), 14, (14, 14)), (0.0, 3072, (1024, 720), 14, (14, 14)),
 ])
 def test_fused_roundtrip_is_bit_identical_to_staged(D, beta, max_seq_len, size, patch, cb):
     """encode_codes / decode_codes (PatchNorm + LFQ inside the pack / un-patchify kernels) give the
@@ -170,8 +172,8 @@ def test_fused_codes_match_staged_when_values_tie_with_the_median(D):
     (16, (256, 256), 1024, 0.0),       # 16-column tiles: 16 token columns per 256-row data tile
     (8, (128, 192), 3072, 0.0),        # 8-column tiles: 32 token columns per tile
     (14, (512, 512), 3072, 0.0),       # config 2
-    (14, (1024, 1024), 1024, 0.004),   # config 3b: top-k cap, variable k, several images per row (the 512-wide basis does
-                                       # not fit next to the ring: token grid + pack_codes_vec_kernel is used instead)
+    (14, (1024, 1024), 1024, 0.004),   # config 3b: top-k cap, variable k, several images per row (K = 512: only the hi
+                                       # plane of the basis is resident, its lo tiles ride in the ring)
     (12, (192, 240), 700, 0.0),        # 12-column tiles: 20 token columns = 240 rows per tile
 ])
 def test_codes_in_the_dct_epilogue_for_other_tile_sizes(D, patch, size, max_seq_len, beta):
@@ -185,7 +187,7 @@ def test_codes_in_the_dct_epilogue_for_other_tile_sizes(D, patch, size, max_seq_
     x = torch.rand(n, 3, h, w).cuda()
     fe = D.DCTAutoencoderFeatureExtractor(3, patch, beta, 32, 32, max_seq_len)
     _, _, th, tw = fe._geometry(h, w)
-    assert bool(_lib.load().dcta_fold_codes_supported(h, w, th * patch, tw * patch, patch)) == (h < 1024)
+    assert bool(_lib.load().dcta_fold_codes_supported(h, w, th * patch, tw * patch, patch))
     pn = D.PatchNorm(32, 32, patch, 3).cuda()
     lfq = D.LFQ(codebook_size=2 ** patch, num_codebooks=patch).cuda().eval()
     pipe = D.TransformPipeline(fe, pn, lfq)
