@@ -80,6 +80,8 @@ class DCTAutoencoderFeatureExtractor:
         self._table_cache_size = 64
         self._keepalive: Optional[List[torch.Tensor]] = None
         self._maxabs: Optional[torch.Tensor] = None
+        # (side stream, device, tensors it still uses) of a process_batch_to_codes(pack_stream=) call until join_pack()
+        self._pack_pending = None
         # decode from codes: generate the operand of inverse pass 1 in shared memory (no coefficient planes in HBM);
         # False = the separate decode kernel followed by the plain inverse (tests compare the two bit for bit)
         self.decode_in_gemm = True
@@ -548,7 +550,7 @@ class DCTAutoencoderFeatureExtractor:
     def join_pack(self):
         """Make the current stream wait for the sort + gather a ``process_batch_to_codes(pack_stream=)`` call left on its
         side stream, and release what that work was reading."""
-        pending, self._pack_pending = getattr(self, "_pack_pending", None), None
+        pending, self._pack_pending = self._pack_pending, None
         if pending is not None:
             side, dev, _keep = pending
             torch.cuda.current_stream(dev).wait_stream(side)

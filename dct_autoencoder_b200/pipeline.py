@@ -38,6 +38,10 @@ class TransformPipeline:
         self.extractor = extractor
         self.norm = norm
         self.quantizer = quantizer
+        # fused round trip: launch the sort and the gather into the packed API tensors on a side stream beside the decode
+        # when every token was kept (False: every launch on the caller's stream)
+        self.overlap_pack = True
+        self._pack_streams = {}
 
     @torch.no_grad()
     def fit_norm(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None) -> None:
@@ -159,13 +163,10 @@ class TransformPipeline:
             self.extractor.join_pack()
         return batch, codes, rec
 
-    overlap_pack = True      # False: every launch of the fused round trip on the caller's stream
-
     def _pack_stream(self, dev):
-        streams = self.__dict__.setdefault("_pack_streams", {})
-        if dev not in streams:
-            streams[dev] = torch.cuda.Stream(dev)
-        return streams[dev]
+        if dev not in self._pack_streams:
+            self._pack_streams[dev] = torch.cuda.Stream(dev)
+        return self._pack_streams[dev]
 
     def graphed(self, images: torch.Tensor, ks: Optional[Sequence[int]] = None, fused: Optional[bool] = None):
         """``roundtrip`` of a fixed-shape device batch captured once in a CUDA graph; see GraphedRoundtrip."""
