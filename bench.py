@@ -672,6 +672,7 @@ def run_config4(ctx, a):
                               peak_source=ctx.peak_src,
                               note="algorithmic flops 2*T*8192*256 (SURVEY 8d); the whole forward incl. operand "
                                    "preparation, |e|^2 and the gather"))
+    line["launch_times_ms"] = [[n, round(t, 5)] for n, t in step_launch_times(ctx, step, reps=2)]
     return ctx.finish(line)
 
 

@@ -217,23 +217,44 @@ __device__ __forceinline__ bool vq_better(float v, int i, float bv, int bi) {
 // exact fp32 re-rank of the (up to) four candidates of every token: dist = sqrt(|x|^2 + (|e|^2 - 2 x.e)) as in
 // vector_quantize.py:29-33, first minimum wins (torch.argmax(-dist), :467-469); optional gather (:222-226).
 // One warp per token.
+// keep (nullable, n_tok bytes): where 0 the token keeps its own row in `quantized` (vector_quantize.py:1043-1048,
+// torch.where(mask, quantize, orig_input), for the projection-free layer) -- the index is computed either way.
+// VEC: d % 4 == 0 and 16-byte aligned rows: 128-bit loads, the token and its four candidates in flight together.
+template <bool VEC>
 __global__ void __launch_bounds__(256) vq_rerank_kernel(const float* __restrict__ x, const float* __restrict__ embed,
                                                         const float* __restrict__ e2, const int32_t* __restrict__ cand,
-                                                        int64_t n_tok, int n_codes, int d, int64_t* __restrict__ indices,
-                                                        float* __restrict__ quantized) {
+                                                        const uint8_t* __restrict__ keep, int64_t n_tok, int n_codes, int d,
+                                                        int64_t* __restrict__ indices, float* __restrict__ quantized) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int d4 = d >> 2;
     for (int64_t t = warp0; t < n_tok; t += n_warps) {
         const int4 c4 = *reinterpret_cast<const int4*>(cand + t * 4);
         const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
         float x2 = 0.f, dot[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int i = lane; i < d; i += 32) {
-            const float v = __ldg(x + t * d + i);
-            x2 = fmaf(v, v, x2);
+        if (VEC) {
+            const float4* xr = reinterpret_cast<const float4*>(x + t * d);
+            for (int i = lane; i < d4; i += 32) {
+                const float4 v = __ldg(xr + i);
+                float4 e[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (cs[k] < n_codes) dot[k] = fmaf(v, __ldg(embed + (int64_t)cs[k] * d + i), dot[k]);
+                for (int k = 0; k < 4; ++k)
+                    e[k] = cs[k] < n_codes ? __ldg(reinterpret_cast<const float4*>(embed + (int64_t)cs[k] * d) + i)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                x2 = fmaf(v.w, v.w, fmaf(v.z, v.z, fmaf(v.y, v.y, fmaf(v.x, v.x, x2))));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    dot[k] = fmaf(v.w, e[k].w, fmaf(v.z, e[k].z, fmaf(v.y, e[k].y, fmaf(v.x, e[k].x, dot[k]))));
+            }
+        } else {
+            for (int i = lane; i < d; i += 32) {
+                const float v = __ldg(x + t * d + i);
+                x2 = fmaf(v, v, x2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (cs[k] < n_codes) dot[k] = fmaf(v, __ldg(embed + (int64_t)cs[k] * d + i), dot[k]);
+            }
         }
         x2 = warp_sum(x2);
         float bv = INFINITY;
@@ -247,8 +268,15 @@ __global__ void __launch_bounds__(256) vq_rerank_kernel(const float* __restrict_
             }
         }
         if (lane == 0) indices[t] = bi;
-        if (quantized)
-            for (int i = lane; i < d; i += 32) quantized[t * d + i] = __ldg(embed + (int64_t)bi * d + i);
+        if (quantized) {
+            const float* src = (keep != nullptr && keep[t] == 0) ? x + t * d : embed + (int64_t)bi * d;
+            if (VEC) {
+                for (int i = lane; i < d4; i += 32)
+                    reinterpret_cast<float4*>(quantized + t * d)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+            } else {
+                for (int i = lane; i < d; i += 32) quantized[t * d + i] = __ldg(src + i);
+            }
+        }
     }
 }
 
@@ -305,9 +333,12 @@ int launch_vq_pair(const void* x_hi, const void* e_hi, const float* e2, const fl
     return check_launch("vq_pair");
 }
 
-int launch_vq_rerank(const float* x, const float* embed, const float* e2, const int32_t* cand, int64_t n_tok, int n_codes,
-                     int d, int64_t* indices, float* quantized, cudaStream_t st) {
-    vq_rerank_kernel<<<grid_for(n_tok, 8), 256, 0, st>>>(x, embed, e2, cand, n_tok, n_codes, d, indices, quantized);
+int launch_vq_rerank(const float* x, const float* embed, const float* e2, const int32_t* cand, const uint8_t* keep,
+                     int64_t n_tok, int n_codes, int d, int64_t* indices, float* quantized, cudaStream_t st) {
+    const bool vec = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(embed) |
+                                     reinterpret_cast<uintptr_t>(quantized)) & 15) == 0;
+    if (vec) vq_rerank_kernel<true><<<grid_for(n_tok, 8), 256, 0, st>>>(x, embed, e2, cand, keep, n_tok, n_codes, d, indices, quantized);
+    else vq_rerank_kernel<false><<<grid_for(n_tok, 8), 256, 0, st>>>(x, embed, e2, cand, keep, n_tok, n_codes, d, indices, quantized);
     return check_launch("vq_rerank");
 }
 

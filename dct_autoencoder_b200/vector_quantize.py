@@ -59,8 +59,10 @@ def _codebook_operand(embed: torch.Tensor):
     return e_hi, e2, s
 
 
-def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = True, impl: str = "tc"):
+def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = True, impl: str = "tc", keep=None):
     """x (T, d), embed (C, d) fp32 CUDA -> (indices int64 (T,), embed[indices] or None).
+    ``keep`` (T,) bool (tensor-core path only): tokens where it is False get their own row ``x[t]`` back instead of the
+    code (vector_quantize.py:1043-1048 folded into the gather).
 
     impl="tc": approximate x.e on tensor cores (ONE fp16 tcgen05 MMA per product, rows scaled by powers of two on the
     device), the two best codes per token and half of the code slices kept in the epilogue, then an exact fp32 re-rank
@@ -79,6 +81,8 @@ def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = 
             e2 = torch.empty(C, dtype=torch.float32, device=dev)
             _lib.call("dcta_vq_nearest", _lib.ptr(x), _lib.ptr(embed), _lib.ptr(e2), _lib.ptr(idx), _lib.ptr(q),
                       T, C, d, st)
+            if keep is not None and q is not None:
+                q = torch.where(keep.reshape(-1, 1), q, x)
             return idx, q
         e_hi, e2, s_e = _codebook_operand(embed)
         x_hi = torch.empty((T, ld), dtype=torch.float16, device=dev)
@@ -86,8 +90,9 @@ def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = 
         _lib.call("dcta_split_rows_rowscale", _lib.ptr(x), None, None, 0.0, _lib.ptr(x_hi), None, _lib.ptr(row_alpha),
                   -2.0 / s_e, T, d, ld, st)
         cand = torch.empty((T, 4), dtype=torch.int32, device=dev)
-        _lib.call("dcta_vq_nearest_tc", _lib.ptr(x), _lib.ptr(x_hi), _lib.ptr(row_alpha), _lib.ptr(embed), _lib.ptr(e_hi),
-                  _lib.ptr(e2), _lib.ptr(cand), _lib.ptr(idx), _lib.ptr(q), T, C, d, ld, st)
+        keep_u8 = None if keep is None else keep.reshape(-1).contiguous().view(torch.uint8)
+        _lib.call("dcta_vq_nearest_tc_masked", _lib.ptr(x), _lib.ptr(x_hi), _lib.ptr(row_alpha), _lib.ptr(embed), _lib.ptr(e_hi),
+                  _lib.ptr(e2), _lib.ptr(cand), _lib.ptr(keep_u8), _lib.ptr(idx), _lib.ptr(q), T, C, d, ld, st)
     return idx, q
 
 
@@ -329,9 +334,17 @@ class VectorQuantize(nn.Module):
             ind = idx.reshape(b, n, h)
             q = qf.reshape(b, n, h * d)
         else:
-            idx, qf = nearest_code(xf.reshape(b * n, d), ef[0].contiguous(), impl=self.vq_impl)
+            # eval, no projections, tokens-last input: the final torch.where(mask, quantize, orig_input)
+            # (vector_quantize.py:1043-1048) is folded into the gather of the re-rank kernel
+            mask_in_gather = (mask is not None and not self.training and x is orig_input and x.dtype == torch.float32
+                              and xf.data_ptr() == x.data_ptr() and isinstance(self.project_out, nn.Identity)
+                              and mask.dtype == torch.bool and mask.device == x.device)
+            idx, qf = nearest_code(xf.reshape(b * n, d), ef[0].contiguous(), impl=self.vq_impl,
+                                   keep=mask if mask_in_gather else None)
             ind = idx.reshape(b, n)
             q = qf.reshape(b, n, d)
+            if mask_in_gather:
+                mask = None                  # already applied
         q = q.to(x.dtype)
         loss = torch.tensor([0.0], device=x.device, requires_grad=self.training)
         if self.training:

@@ -504,6 +504,12 @@ int dcta_row_sumsq(const float* x, float* out, int64_t n, int d, void* stream);
 int dcta_vq_nearest_tc(const float* x, const void* x_hi, const float* row_alpha, const float* embed,
                        const void* e_hi, const float* e2, int32_t* cand, int64_t* indices, float* quantized,
                        int64_t n_tok, int n_codes, int d, int64_t ld, void* stream);
+/* The same with VQ:1043-1048 folded into the gather: keep [nullable] (n_tok) bytes, 0 = padding token whose row of
+ * `quantized` is its own input row x[t] (torch.where(mask, quantize, orig_input) of a projection-free layer); indices are
+ * computed for every token either way. */
+int dcta_vq_nearest_tc_masked(const float* x, const void* x_hi, const float* row_alpha, const float* embed,
+                              const void* e_hi, const float* e2, int32_t* cand, const uint8_t* keep, int64_t* indices,
+                              float* quantized, int64_t n_tok, int n_codes, int d, int64_t ld, void* stream);
 /* Antialiased bilinear resize of n_planes planes (ih, iw) -> (oh, ow) fp32: the `crop` step of the reference's loader
  * (dataset.py:59-73, torchvision Resize(antialias=True) on a float tensor = F.interpolate(mode="bilinear",
  * antialias=True, align_corners=False)).  _u8: 8-bit input pixels read as u / 255. */

@@ -154,3 +154,18 @@ def test_vq_module_uses_tc_by_default(D):
     assert float((ind != ind2).float().mean()) < 0.005
     same = ind == ind2
     assert torch.equal(q[same], q2[same])
+
+
+def test_vq_padding_mask_is_applied_in_the_gather(D):
+    """vector_quantize.py:1043-1048: torch.where(mask, quantize, orig_input).  For the projection-free layer in eval the
+    re-rank kernel's gather writes the input row of a masked token itself (no extra pass over the (b, n, d) tensors)."""
+    torch.manual_seed(0)
+    for dim in (64, 30):                        # 128-bit and scalar variants of the re-rank kernel
+        vq = D.VectorQuantize(dim=dim, codebook_size=512).cuda().eval()
+        x = torch.randn(3, 200, dim).cuda()
+        mask = torch.rand(3, 200).cuda() > 0.3
+        q, ind, _ = vq(x, mask=mask)
+        q_all, ind_all, _ = vq(x, mask=torch.ones_like(mask))
+        assert torch.equal(ind, ind_all)
+        assert torch.equal(q, torch.where(mask[..., None], q_all, x))
+        assert torch.equal(q_all, vq._codebook.embed[0][ind_all])
