@@ -346,7 +346,9 @@ class VectorQuantize(nn.Module):
             if mask_in_gather:
                 mask = None                  # already applied
         q = q.to(x.dtype)
-        loss = torch.tensor([0.0], device=x.device, requires_grad=self.training)
+        # (torch.zeros: an asynchronous fill -- torch.tensor([0.0], device=...) is a blocking copy from pageable memory
+        # that makes the host wait for the stream on every call)
+        loss = torch.zeros(1, device=x.device, requires_grad=self.training)
         if self.training:
             if learn:
                 # EMA update from this batch's assignments (the quantised vectors above still come from the OLD codebook)
