@@ -114,7 +114,7 @@ SIGNATURES = {
                                     c_int, c_float, P, P, P, P],
     "dcta_row_sumsq": [P, P, c_int64, c_int, P],
     "dcta_vq_nearest_tc": [P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int64, P],
-    "dcta_vq_nearest_tc_masked": [P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int64, P],
+    "dcta_vq_nearest_tc_masked": [P, P, P, P, P, P, P, P, P, P, P, P, c_int64, c_int, c_int, c_int64, P],
     "dcta_resize_bilinear_aa": [P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_resize_bilinear_aa_u8": [P, P, c_int64, c_int, c_int, c_int, c_int, P],
     "dcta_vq_cluster_stats": [P, P, P, c_int64, c_int, c_int, P, P, P],

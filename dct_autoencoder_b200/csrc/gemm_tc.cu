@@ -1188,30 +1188,31 @@ extern "C" int dcta_split_coef_planes(const float* y, void* hi, void* lo, float*
 // vector_quantize.py:29-33 / :467-469: approximate distances on tcgen05 (one fp16 MMA per product), four candidates per
 // token, exact fp32 re-rank (vq_tc.cu).
 extern "C" int dcta_vq_nearest_tc_masked(const float* x, const void* x_hi, const float* row_alpha, const float* embed,
-                                         const void* e_hi, const float* e2, int32_t* cand, const uint8_t* keep,
-                                         int64_t* indices, float* quantized, int64_t n_tok, int n_codes, int d,
-                                         int64_t ld, void* stream);
+                                         const void* e_hi, const float* e2, int32_t* cand, float* cand_val,
+                                         const float* e2_max, const uint8_t* keep, int64_t* indices, float* quantized,
+                                         int64_t n_tok, int n_codes, int d, int64_t ld, void* stream);
 
 extern "C" int dcta_vq_nearest_tc(const float* x, const void* x_hi, const float* row_alpha, const float* embed,
                                   const void* e_hi, const float* e2, int32_t* cand, int64_t* indices, float* quantized,
                                   int64_t n_tok, int n_codes, int d, int64_t ld, void* stream) {
-    return dcta_vq_nearest_tc_masked(x, x_hi, row_alpha, embed, e_hi, e2, cand, nullptr, indices, quantized, n_tok, n_codes,
-                                     d, ld, stream);
+    return dcta_vq_nearest_tc_masked(x, x_hi, row_alpha, embed, e_hi, e2, cand, nullptr, nullptr, nullptr, indices, quantized,
+                                     n_tok, n_codes, d, ld, stream);
 }
 
 extern "C" int dcta_vq_nearest_tc_masked(const float* x, const void* x_hi, const float* row_alpha, const float* embed,
-                                         const void* e_hi, const float* e2, int32_t* cand, const uint8_t* keep,
-                                         int64_t* indices, float* quantized, int64_t n_tok, int n_codes, int d,
-                                         int64_t ld, void* stream) {
+                                         const void* e_hi, const float* e2, int32_t* cand, float* cand_val,
+                                         const float* e2_max, const uint8_t* keep, int64_t* indices, float* quantized,
+                                         int64_t n_tok, int n_codes, int d, int64_t ld, void* stream) {
     DCTA_REQUIRE(x && x_hi && row_alpha && embed && e_hi && e2 && cand && indices, "vq_nearest_tc: null pointer");
+    DCTA_REQUIRE((cand_val == nullptr) == (e2_max == nullptr), "vq_nearest_tc: cand_val and e2_max go together");
     DCTA_REQUIRE(n_tok >= 0 && n_codes > 0 && d > 0 && ld >= d && ld % 8 == 0, "vq_nearest_tc: bad sizes");
     if (n_tok == 0) return DCTA_OK;
-    int rc = launch_vq_pair(x_hi, e_hi, e2, row_alpha, cand, n_tok, n_codes, d, ld, as_stream(stream));
+    int rc = launch_vq_pair(x_hi, e_hi, e2, row_alpha, cand, cand_val, n_tok, n_codes, d, ld, as_stream(stream));
     if (rc == DCTA_ERR_UNSUPPORTED) {
         set_error("vq_nearest_tc: a %d-wide token operand does not fit next to the code ring in shared memory "
                   "(use dcta_vq_nearest)", d);
         return rc;
     }
     if (rc) return rc;
-    return launch_vq_rerank(x, embed, e2, cand, keep, n_tok, n_codes, d, indices, quantized, as_stream(stream));
+    return launch_vq_rerank(x, embed, e2, cand, cand_val, e2_max, keep, n_tok, n_codes, d, indices, quantized, as_stream(stream));
 }

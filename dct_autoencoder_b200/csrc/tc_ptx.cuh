@@ -251,10 +251,11 @@ inline EncodeTiledFn get_encode_fn() {
 const float* launch_ipt_plane_means(const float* rgb, float* sums_scratch, float* dc, int64_t n_img, int h, int w,
                                     const Mat3& A, const Mat3& B, cudaStream_t st);
 // vq_tc.cu: nearest-code candidates on CTA pairs (DCTA_ERR_UNSUPPORTED when the geometry does not fit) + exact re-rank
-int launch_vq_pair(const void* x_hi, const void* e_hi, const float* e2, const float* row_alpha, int32_t* cand, int64_t n_tok,
-                   int n_codes, int d, int64_t ld, cudaStream_t st);
-int launch_vq_rerank(const float* x, const float* embed, const float* e2, const int32_t* cand, const uint8_t* keep,
-                     int64_t n_tok, int n_codes, int d, int64_t* indices, float* quantized, cudaStream_t st);
+int launch_vq_pair(const void* x_hi, const void* e_hi, const float* e2, const float* row_alpha, int32_t* cand, float* cand_val,
+                   int64_t n_tok, int n_codes, int d, int64_t ld, cudaStream_t st);
+int launch_vq_rerank(const float* x, const float* embed, const float* e2, const int32_t* cand, const float* cand_val,
+                     const float* e2_max, const uint8_t* keep, int64_t n_tok, int n_codes, int d, int64_t* indices,
+                     float* quantized, cudaStream_t st);
 const float* launch_ipt_plane_means_u8(const uint8_t* rgb, float* sums_scratch, float* dc, int64_t n_img, int h, int w,
                                        const Mat3& A, const Mat3& B, cudaStream_t st);
 const float* launch_plane_means(const float* x, float* sums_scratch, float* dc, int64_t n_planes, int h, int w,

@@ -35,6 +35,7 @@ struct VqArgs {
     const float* col_bias;                   // |e_n|^2
     const float* row_alpha;                  // (n_tok) -2 / (scale of the token's row * scale of the codebook)
     int32_t* cand;                           // (n_tok, 4): the two best codes of each half of the code slices
+    float* cand_val;                         // [nullable] (n_tok, 4): their approximate |e|^2 - 2 x.e
 };
 
 // running two smallest (value, index) pairs; strict '<' keeps the earlier index among equal values
@@ -195,8 +196,10 @@ vq_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     process(rb, n0 + (c + 1) * 32);
                 }
             }
-            if (tok < g.n_tok)
+            if (tok < g.n_tok) {
                 *reinterpret_cast<int2*>(g.cand + tok * 4 + half * 2) = make_int2(i1, i2);
+                if (g.cand_val) *reinterpret_cast<float2*>(g.cand_val + tok * 4 + half * 2) = make_float2(b1, b2);
+            }
         }
     }
     __syncwarp();
@@ -220,61 +223,116 @@ __device__ __forceinline__ bool vq_better(float v, int i, float bv, int bi) {
 // keep (nullable, n_tok bytes): where 0 the token keeps its own row in `quantized` (vector_quantize.py:1043-1048,
 // torch.where(mask, quantize, orig_input), for the projection-free layer) -- the index is computed either way.
 // VEC: d % 4 == 0 and 16-byte aligned rows: 128-bit loads, the token and its four candidates in flight together.
+// cand_val / e2_max [nullable together]: the approximate values of the four candidates and max_n |e_n|^2.  Every
+// approximate value is within E = 2^-8 |x| max|e| of the exact |e|^2 - 2 x.e (operands rounded to fp16: 2 * 2^-11 relative
+// per product, i.e. 2^-9 |x||e| on the value by Cauchy-Schwarz; the bound used is twice that and also covers the fp32
+// accumulation), and every code that is NOT a candidate has an approximate value >= the runner-up's.  So when the
+// runner-up exceeds the best by more than 2E the best candidate is the exact argmin (no tie is possible) and the four
+// exact distances need not be formed: only the token's own row is read (for |x|) and the winner's row gathered.
+// G lanes per token (G = 32: one warp per token, scalar loads; G = 8: four tokens per warp in flight, 128-bit loads --
+// the kernel is bound by the latency of its dependent loads (candidates -> rows), not by bytes).
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) vq_rerank_kernel(const float* __restrict__ x, const float* __restrict__ embed,
                                                         const float* __restrict__ e2, const int32_t* __restrict__ cand,
+                                                        const float* __restrict__ cand_val, const float* __restrict__ e2_max,
                                                         const uint8_t* __restrict__ keep, int64_t n_tok, int n_codes, int d,
                                                         int64_t* __restrict__ indices, float* __restrict__ quantized) {
-    const int lane = threadIdx.x & 31;
+    constexpr int G = VEC ? 8 : 32;                   // lanes per token
+    constexpr int TPW = 32 / G;                       // tokens per warp
+    const int lane = threadIdx.x & 31, gl = lane % G, sub = lane / G;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int d4 = d >> 2;
-    for (int64_t t = warp0; t < n_tok; t += n_warps) {
-        const int4 c4 = *reinterpret_cast<const int4*>(cand + t * 4);
+    const bool shortcut = VEC && cand_val != nullptr && e2_max != nullptr;
+    const float e_max = shortcut ? sqrtf(__ldg(e2_max)) : 0.f;
+    for (int64_t t0 = warp0 * TPW; t0 < n_tok; t0 += n_warps * TPW) {        // warp-uniform trip count
+        const int64_t t = t0 + sub;
+        const bool live = t < n_tok;
+        const int64_t tt = live ? t : n_tok - 1;                              // idle groups shadow the last token
+        const int4 c4 = *reinterpret_cast<const int4*>(cand + tt * 4);
         const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
         float x2 = 0.f, dot[4] = {0.f, 0.f, 0.f, 0.f};
-        if (VEC) {
-            const float4* xr = reinterpret_cast<const float4*>(x + t * d);
-            for (int i = lane; i < d4; i += 32) {
-                const float4 v = __ldg(xr + i);
-                float4 e[4];
+        int bi = 0x7fffffff;
+        bool decided = false;
+        if (shortcut) {
+            const float4 a4 = *reinterpret_cast<const float4*>(cand_val + tt * 4);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+            int kb = 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    e[k] = cs[k] < n_codes ? __ldg(reinterpret_cast<const float4*>(embed + (int64_t)cs[k] * d) + i)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                x2 = fmaf(v.w, v.w, fmaf(v.z, v.z, fmaf(v.y, v.y, fmaf(v.x, v.x, x2))));
+            for (int k = 1; k < 4; ++k) if (av[k] < av[kb]) kb = k;
+            float second = INFINITY;
+            int cbest = cs[0];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    dot[k] = fmaf(v.w, e[k].w, fmaf(v.z, e[k].z, fmaf(v.y, e[k].y, fmaf(v.x, e[k].x, dot[k]))));
+            for (int k = 0; k < 4; ++k) {
+                if (k != kb) second = fminf(second, av[k]);
+                else cbest = cs[k];
             }
-        } else {
-            for (int i = lane; i < d; i += 32) {
-                const float v = __ldg(x + t * d + i);
-                x2 = fmaf(v, v, x2);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (cs[k] < n_codes) dot[k] = fmaf(v, __ldg(embed + (int64_t)cs[k] * d + i), dot[k]);
+            const float4* xr = reinterpret_cast<const float4*>(x + tt * d);
+            float xs = 0.f;
+            for (int i = gl; i < d4; i += G) {
+                const float4 v = __ldg(xr + i);
+                xs = fmaf(v.w, v.w, fmaf(v.z, v.z, fmaf(v.y, v.y, fmaf(v.x, v.x, xs))));
+            }
+            xs = group_sum<G>(xs);
+            const float bound = 0.0078125f * sqrtf(xs) * e_max;              // 2E = 2 * 2^-8 |x| max|e|
+            if (cbest < n_codes && second - av[kb] > bound && xs < 3.0e38f) {   // (false for NaN / inf anywhere)
+                bi = cbest;
+                decided = true;
             }
         }
-        x2 = warp_sum(x2);
+        if (!decided) {
+            if (VEC) {
+                const float4* xr = reinterpret_cast<const float4*>(x + tt * d);
+                for (int i = gl; i < d4; i += G) {
+                    const float4 v = __ldg(xr + i);
+                    float4 e[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        e[k] = cs[k] < n_codes ? __ldg(reinterpret_cast<const float4*>(embed + (int64_t)cs[k] * d) + i)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x2 = fmaf(v.w, v.w, fmaf(v.z, v.z, fmaf(v.y, v.y, fmaf(v.x, v.x, x2))));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        dot[k] = fmaf(v.w, e[k].w, fmaf(v.z, e[k].z, fmaf(v.y, e[k].y, fmaf(v.x, e[k].x, dot[k]))));
+                }
+            } else {
+                for (int i = gl; i < d; i += G) {
+                    const float v = __ldg(x + tt * d + i);
+                    x2 = fmaf(v, v, x2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (cs[k] < n_codes) dot[k] = fmaf(v, __ldg(embed + (int64_t)cs[k] * d + i), dot[k]);
+                }
+            }
+        }
+        // (the reductions are executed by every lane: groups that took the shortcut contribute zeros and ignore the result)
+        x2 = group_sum<G>(x2);
         float bv = INFINITY;
-        int bi = 0x7fffffff;
+        int bj = 0x7fffffff;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float dk = warp_sum(dot[k]);
+            const float dk = group_sum<G>(dot[k]);
             if (cs[k] < n_codes) {
                 const float v = __fsqrt_rn(__fadd_rn(x2, fmaf(-2.0f, dk, __ldg(e2 + cs[k]))));
-                if (bi == 0x7fffffff || vq_better(v, cs[k], bv, bi)) { bv = v; bi = cs[k]; }
+                if (bj == 0x7fffffff || vq_better(v, cs[k], bv, bj)) { bv = v; bj = cs[k]; }
             }
         }
-        if (lane == 0) indices[t] = bi;
-        if (quantized) {
+        if (!decided) bi = bj;
+        if (live && gl == 0) indices[t] = bi;
+        if (live && quantized) {
             const float* src = (keep != nullptr && keep[t] == 0) ? x + t * d : embed + (int64_t)bi * d;
             if (VEC) {
-                for (int i = lane; i < d4; i += 32)
+                for (int i = gl; i < d4; i += G)
                     reinterpret_cast<float4*>(quantized + t * d)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
             } else {
-                for (int i = lane; i < d; i += 32) quantized[t * d + i] = __ldg(src + i);
+                for (int i = gl; i < d; i += G) quantized[t * d + i] = __ldg(src + i);
             }
         }
     }
@@ -299,9 +357,10 @@ static int make_map_rows(CUtensorMap* map, const void* ptr, int64_t k, int64_t r
 }
 
 // DCTA_ERR_UNSUPPORTED (no error message) when the token operand does not fit in shared memory
-int launch_vq_pair(const void* x_hi, const void* e_hi, const float* e2, const float* row_alpha, int32_t* cand, int64_t n_tok,
-                   int n_codes, int d, int64_t ld, cudaStream_t st) {
+int launch_vq_pair(const void* x_hi, const void* e_hi, const float* e2, const float* row_alpha, int32_t* cand, float* cand_val,
+                   int64_t n_tok, int n_codes, int d, int64_t ld, cudaStream_t st) {
     VqArgs g{};
+    g.cand_val = cand_val;
     g.n_tok = n_tok;
     g.n_codes = n_codes;
     g.num_kb = (int)ceil_div(d, VK);
@@ -333,12 +392,13 @@ int launch_vq_pair(const void* x_hi, const void* e_hi, const float* e2, const fl
     return check_launch("vq_pair");
 }
 
-int launch_vq_rerank(const float* x, const float* embed, const float* e2, const int32_t* cand, const uint8_t* keep,
-                     int64_t n_tok, int n_codes, int d, int64_t* indices, float* quantized, cudaStream_t st) {
+int launch_vq_rerank(const float* x, const float* embed, const float* e2, const int32_t* cand, const float* cand_val,
+                     const float* e2_max, const uint8_t* keep, int64_t n_tok, int n_codes, int d, int64_t* indices,
+                     float* quantized, cudaStream_t st) {
     const bool vec = d % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(embed) |
-                                     reinterpret_cast<uintptr_t>(quantized)) & 15) == 0;
-    if (vec) vq_rerank_kernel<true><<<grid_for(n_tok, 8), 256, 0, st>>>(x, embed, e2, cand, keep, n_tok, n_codes, d, indices, quantized);
-    else vq_rerank_kernel<false><<<grid_for(n_tok, 8), 256, 0, st>>>(x, embed, e2, cand, keep, n_tok, n_codes, d, indices, quantized);
+                                     reinterpret_cast<uintptr_t>(quantized) | reinterpret_cast<uintptr_t>(cand_val)) & 15) == 0;
+    if (vec) vq_rerank_kernel<true><<<grid_for(n_tok, 32), 256, 0, st>>>(x, embed, e2, cand, cand_val, e2_max, keep, n_tok, n_codes, d, indices, quantized);
+    else vq_rerank_kernel<false><<<grid_for(n_tok, 8), 256, 0, st>>>(x, embed, e2, cand, cand_val, e2_max, keep, n_tok, n_codes, d, indices, quantized);
     return check_launch("vq_rerank");
 }
 

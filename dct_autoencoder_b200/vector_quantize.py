@@ -34,7 +34,7 @@ def invalidate_codebook_cache():
 
 
 def _codebook_operand(embed: torch.Tensor):
-    """(C, d) fp32 codebook -> cached (fp16 plane (C, ld) of embed * s, |e|^2 (C,), s): s a power of two from max|embed|
+    """(C, d) fp32 codebook -> cached (fp16 plane (C, ld) of embed * s, |e|^2 (C,), s, max |e|^2 (1,)): s a power of two from max|embed|
     (one device->host read per codebook version; the codebook is a parameter, the tokens never cause a sync).
     The entry keeps a reference to ``embed``: while it is cached its memory cannot be recycled for another tensor, so
     (address, version counter) identifies the contents."""
@@ -53,10 +53,11 @@ def _codebook_operand(embed: torch.Tensor):
     e2 = torch.empty(C, dtype=torch.float32, device=embed.device)
     with torch.cuda.device(embed.device):
         _lib.call("dcta_row_sumsq", _lib.ptr(embed), _lib.ptr(e2), C, d, _lib.stream_ptr(embed.device))
-    _CODEBOOK_CACHE[key] = (embed, e_hi, e2, s)
+    e2_max = e2.max().reshape(1).contiguous()            # for the re-rank shortcut's error bound (stays on the device)
+    _CODEBOOK_CACHE[key] = (embed, e_hi, e2, s, e2_max)
     while len(_CODEBOOK_CACHE) > 8:
         _CODEBOOK_CACHE.popitem(last=False)
-    return e_hi, e2, s
+    return e_hi, e2, s, e2_max
 
 
 def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = True, impl: str = "tc", keep=None):
@@ -84,15 +85,17 @@ def nearest_code(x: torch.Tensor, embed: torch.Tensor, return_quantized: bool = 
             if keep is not None and q is not None:
                 q = torch.where(keep.reshape(-1, 1), q, x)
             return idx, q
-        e_hi, e2, s_e = _codebook_operand(embed)
+        e_hi, e2, s_e, e2_max = _codebook_operand(embed)
         x_hi = torch.empty((T, ld), dtype=torch.float16, device=dev)
         row_alpha = torch.empty(T, dtype=torch.float32, device=dev)
         _lib.call("dcta_split_rows_rowscale", _lib.ptr(x), None, None, 0.0, _lib.ptr(x_hi), None, _lib.ptr(row_alpha),
                   -2.0 / s_e, T, d, ld, st)
         cand = torch.empty((T, 4), dtype=torch.int32, device=dev)
+        cand_val = torch.empty((T, 4), dtype=torch.float32, device=dev)
         keep_u8 = None if keep is None else keep.reshape(-1).contiguous().view(torch.uint8)
         _lib.call("dcta_vq_nearest_tc_masked", _lib.ptr(x), _lib.ptr(x_hi), _lib.ptr(row_alpha), _lib.ptr(embed), _lib.ptr(e_hi),
-                  _lib.ptr(e2), _lib.ptr(cand), _lib.ptr(keep_u8), _lib.ptr(idx), _lib.ptr(q), T, C, d, ld, st)
+                  _lib.ptr(e2), _lib.ptr(cand), _lib.ptr(cand_val), _lib.ptr(e2_max), _lib.ptr(keep_u8), _lib.ptr(idx),
+                  _lib.ptr(q), T, C, d, ld, st)
     return idx, q
 
 

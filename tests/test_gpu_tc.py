@@ -169,3 +169,35 @@ def test_vq_padding_mask_is_applied_in_the_gather(D):
         assert torch.equal(ind, ind_all)
         assert torch.equal(q, torch.where(mask[..., None], q_all, x))
         assert torch.equal(q_all, vq._codebook.embed[0][ind_all])
+
+
+def test_vq_rerank_shortcut_returns_the_exact_rerank_indices(D):
+    """The second pass skips the exact re-scoring of a token whose best candidate leads the runner-up by more than twice
+    the rigorous error bound of the first pass: indices and codes equal those of the plain re-rank (dcta_vq_nearest_tc),
+    on well separated codes (shortcut taken) and on a codebook of near-duplicates (shortcut refused)."""
+    from dct_autoencoder_b200 import _lib
+    from dct_autoencoder_b200.vector_quantize import _codebook_operand, nearest_code
+    torch.manual_seed(3)
+    T, C, d = 5000, 2048, 128
+    x = torch.randn(T, d, device="cuda")
+    base = torch.randn(C // 2, d, device="cuda")
+    for embed in (torch.randn(C, d, device="cuda"),
+                  torch.cat([base, base + 1e-4 * torch.randn_like(base)]).contiguous()):
+        idx, q = nearest_code(x, embed)
+        e_hi, e2, s_e, _ = _codebook_operand(embed)
+        x_hi = torch.empty((T, d), dtype=torch.float16, device="cuda")
+        row_alpha = torch.empty(T, dtype=torch.float32, device="cuda")
+        st = _lib.stream_ptr(x.device)
+        _lib.call("dcta_split_rows_rowscale", _lib.ptr(x), None, None, 0.0, _lib.ptr(x_hi), None, _lib.ptr(row_alpha),
+                  -2.0 / s_e, T, d, d, st)
+        cand = torch.empty((T, 4), dtype=torch.int32, device="cuda")
+        idx0 = torch.empty(T, dtype=torch.int64, device="cuda")
+        q0 = torch.empty_like(x)
+        _lib.call("dcta_vq_nearest_tc", _lib.ptr(x), _lib.ptr(x_hi), _lib.ptr(row_alpha), _lib.ptr(embed), _lib.ptr(e_hi),
+                  _lib.ptr(e2), _lib.ptr(cand), _lib.ptr(idx0), _lib.ptr(q0), T, C, d, d, st)
+        assert torch.equal(idx, idx0) and torch.equal(q, q0)
+        # and both are the true nearest code up to the stated EPS_VQ
+        d2 = torch.cdist(x.double(), embed.double()) ** 2
+        best = d2.min(dim=1).values
+        got = d2.gather(1, idx[:, None])[:, 0]
+        assert bool(((got - best) <= 1e-4 * best).all())
