@@ -190,39 +190,68 @@ __device__ __forceinline__ float from_orderable(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// one CTA per position, one thread per coefficient; MSB-first radix select of the element of
-// rank (n-1)/2 (torch.median returns the LOWER middle for even n, PN:129).
-__global__ void __launch_bounds__(256) batch_median_kernel(const float* __restrict__ x,
-                                                           const int32_t* __restrict__ offsets,
-                                                           const int32_t* __restrict__ list,
-                                                           int n_pos, int z,
-                                                           float* __restrict__ packed) {
+// One CTA per (position, chunk of 32 coefficients): 8 token groups x 32 coefficient lanes.  The position's n values of
+// every coefficient of the chunk are loaded ONCE (128-byte rows) as orderable keys into shared memory, then an MSB-first
+// radix select finds the element of rank (n-1)/2 (torch.median returns the LOWER middle for even n, PN:129): per bit each
+// thread counts its n/8 tokens, the eight partial counts meet in a double-buffered table (one barrier per bit).  Lists
+// longer than kMedianSmemTokens fall back to counting straight from global memory (same arithmetic).  The first version
+// re-read the tokens from L2 once per bit: 1.04 ms of the 1.54 ms fit step at 64 images.
+constexpr int kMedianLanes = 32, kMedianGroups = 8, kMedianSmemTokens = 512;
+
+__global__ void __launch_bounds__(kMedianLanes * kMedianGroups)
+batch_median_kernel(const float* __restrict__ x, const int32_t* __restrict__ offsets,
+                    const int32_t* __restrict__ list, int n_pos, int z, float* __restrict__ packed) {
+    extern __shared__ uint32_t median_keys[];  // [kMedianSmemTokens][32]
+    __shared__ int partial[2][kMedianGroups][kMedianLanes];
     const int pid = blockIdx.x;
+    const int lane = threadIdx.x & (kMedianLanes - 1), grp = threadIdx.x / kMedianLanes;
+    const int zi = blockIdx.y * kMedianLanes + lane;
+    const bool live = zi < z;
     const int beg = offsets[pid], n = offsets[pid + 1] - beg;
-    if (threadIdx.x == 0) packed[pid] = (float)n;  // batch_n (PN:112-119)
+    if (blockIdx.y == 0 && threadIdx.x == 0) packed[pid] = (float)n;  // batch_n (PN:112-119)
     float* out = packed + n_pos + (int64_t)pid * z;
-    for (int zi = threadIdx.x; zi < z; zi += blockDim.x) {
-        float med = 0.0f;
-        if (n > 0) {
-            uint32_t prefix = 0, mask = 0;
-            int r = (n - 1) >> 1;
-            for (int bit = 31; bit >= 0; --bit) {
-                const uint32_t bm = 1u << bit;
-                int cnt0 = 0;
-                for (int t = 0; t < n; ++t) {
-                    const uint32_t k = orderable_key(__ldg(x + (int64_t)__ldg(list + beg + t) * z + zi));
-                    cnt0 += ((k & mask) == prefix) && !(k & bm);
-                }
-                if (r >= cnt0) {
-                    r -= cnt0;
-                    prefix |= bm;
-                }
-                mask |= bm;
-            }
-            med = from_orderable(prefix);
-        }
-        out[zi] = __fmul_rn(med, (float)n);  // batch_median * batch_n, ready to be summed over ranks
+    if (n == 0) {
+        if (grp == 0 && live) out[zi] = 0.0f;
+        return;
     }
+    const bool staged = n <= kMedianSmemTokens;
+    if (staged) {
+        for (int t = grp; t < n; t += kMedianGroups)
+            median_keys[t * kMedianLanes + lane] =
+                live ? orderable_key(__ldg(x + (int64_t)__ldg(list + beg + t) * z + zi)) : 0u;
+        __syncthreads();
+    }
+    uint32_t prefix = 0, mask = 0;
+    int r = (n - 1) >> 1;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t bm = 1u << bit;
+        int cnt0 = 0;
+        if (staged) {
+#pragma unroll 4
+            for (int t = grp; t < n; t += kMedianGroups) {
+                const uint32_t k = median_keys[t * kMedianLanes + lane];
+                cnt0 += ((k & mask) == prefix) && !(k & bm);
+            }
+        } else if (live) {
+            for (int t = grp; t < n; t += kMedianGroups) {
+                const uint32_t k = orderable_key(__ldg(x + (int64_t)__ldg(list + beg + t) * z + zi));
+                cnt0 += ((k & mask) == prefix) && !(k & bm);
+            }
+        }
+        int (*tab)[kMedianLanes] = partial[bit & 1];
+        tab[grp][lane] = cnt0;
+        __syncthreads();
+        cnt0 = 0;
+#pragma unroll
+        for (int g = 0; g < kMedianGroups; ++g) cnt0 += tab[g][lane];
+        if (r >= cnt0) {
+            r -= cnt0;
+            prefix |= bm;
+        }
+        mask |= bm;
+    }
+    // batch_median * batch_n, ready to be summed over ranks
+    if (grp == 0 && live) out[zi] = __fmul_rn(from_orderable(prefix), (float)n);
 }
 
 // median <- (median*n + sum_r batch_median_r*batch_n_r) / clamp(n + batch_n, 1)        PN:135-138
@@ -347,9 +376,12 @@ extern "C" int dcta_patchnorm_batch_median(const float* x, const int32_t* offset
                                            void* stream) {
     DCTA_REQUIRE(x && offsets && list && packed, "patchnorm_batch_median: null pointer");
     DCTA_REQUIRE(n_pos > 0 && z > 0, "patchnorm_batch_median: bad sizes");
-    int threads = ((z + 31) / 32) * 32;
-    if (threads > 256) threads = 256;
-    batch_median_kernel<<<n_pos, threads, 0, as_stream(stream)>>>(x, offsets, list, n_pos, z, packed);
+    constexpr int smem = kMedianSmemTokens * kMedianLanes * (int)sizeof(uint32_t);
+    if (cudaFuncSetAttribute(batch_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        return check_launch("patchnorm_batch_median (shared memory opt-in)");
+    const dim3 grid(n_pos, (z + kMedianLanes - 1) / kMedianLanes);
+    batch_median_kernel<<<grid, kMedianLanes * kMedianGroups, smem, as_stream(stream)>>>(x, offsets, list, n_pos, z,
+                                                                                        packed);
     return check_launch("patchnorm_batch_median");
 }
 

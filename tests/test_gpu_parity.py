@@ -331,6 +331,31 @@ def test_patchnorm_matches_oracle_bitwise(D):
     assert np.array_equal(npy(pn(ddp)), on.forward(odp))
 
 
+@pytest.mark.parametrize("H,W,b,s,p", [(1, 2, 40, 40, 14), (3, 3, 9, 64, 14), (2, 2, 6, 50, 6)])
+def test_patchnorm_median_long_and_short_lists(D, H, W, b, s, p):
+    """batch_median_kernel: lists beyond its shared-memory staging (800 tokens per position: counted from global memory),
+    lists inside it, coefficient counts that are not a multiple of its 32-lane chunk, even list lengths (lower median,
+    PN:129) and duplicated values: n, median bit-exact vs the oracle."""
+    rng = np.random.default_rng(11)
+    z = p * p
+    on = O.PatchNorm(H, W, p, 1)
+    pn = D.PatchNorm(H, W, p, 1).cuda().train()
+    for step in range(2):
+        x = np.round(rng.standard_normal((b, s, z)) * 8).astype(np.float32) / 4 - step   # many exact ties
+        ch = np.zeros((b, s), np.int64)
+        pos = np.stack([rng.integers(0, H, (b, s)), rng.integers(0, W, (b, s))], -1)
+        pad = np.arange(s)[None, :] >= rng.integers(s - 3, s + 1, (b, 1))
+        x[pad] = 0
+        pos[pad] = 0
+        odp = O.Patches(x, pad, np.zeros((b, s), np.int64), ch, pos, [], [])
+        ddp = D.DCTPatches(patches=cu(x), key_pad_mask=cu(pad), batched_image_ids=cu(np.zeros((b, s), np.int64)),
+                           patch_channels=cu(ch), patch_positions=cu(pos), patch_sizes=[], original_sizes=[])
+        assert np.array_equal(npy(pn(ddp)), on.forward(odp))
+        assert np.array_equal(npy(pn.n), on.n)
+        assert np.array_equal(npy(pn.median), on.median)
+        np.testing.assert_allclose(npy(pn.b), on.b, rtol=1e-6, atol=1e-7)
+
+
 def test_patchnorm_ignores_padding_outliers(D):
     """Intent of the reference's testnorm.py:18-55."""
     rng = np.random.default_rng(0)
