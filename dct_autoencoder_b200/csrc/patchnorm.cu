@@ -190,68 +190,147 @@ __device__ __forceinline__ float from_orderable(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// One CTA per (position, chunk of 32 coefficients): 8 token groups x 32 coefficient lanes.  The position's n values of
-// every coefficient of the chunk are loaded ONCE (128-byte rows) as orderable keys into shared memory, then an MSB-first
-// radix select finds the element of rank (n-1)/2 (torch.median returns the LOWER middle for even n, PN:129): per bit each
-// thread counts its n/8 tokens, the eight partial counts meet in a double-buffered table (one barrier per bit).  Lists
-// longer than kMedianSmemTokens fall back to counting straight from global memory (same arithmetic).  The first version
-// re-read the tokens from L2 once per bit: 1.04 ms of the 1.54 ms fit step at 64 images.
-constexpr int kMedianLanes = 32, kMedianGroups = 8, kMedianSmemTokens = 512;
+// Batch median per (position, coefficient): the element of rank (n-1)/2 of the position's list (torch.median returns
+// the LOWER middle for even n, PN:129), found by an MSB-first radix select on order-preserving keys -- bit sliced.
+// One CTA of 8 warps per position, one thread per coefficient of a 32-coefficient chunk.  A thread loads its 32 keys of a
+// token block into registers and transposes the 32 x 32 bit matrix in place (5 butterfly stages), so that word b holds
+// bit b of all 32 tokens; the select is then one AND + POPC per block and bit on a candidate mask instead of one
+// compare per token and bit.
+//   n <= 64   (a fit batch of up to 64 images: a position occurs at most once per image): every warp owns whole chunks,
+//             two token blocks in registers, no barrier: ~45 warp instructions per coefficient;
+//   n <= 512  the 8 warps share a chunk, two blocks each; the per-bit counts meet in a double-buffered table (one
+//             barrier per bit);
+//   longer    counted token by token from global memory, 8 token groups x 32 lanes.
+// The first version (one compare per token and bit, tokens re-read from L2 once per bit) took 1.04 ms of the 1.54 ms
+// fit step at 64 images; a shared-memory staged version of it 0.76 ms (issue-bound: ~560 warp instructions per
+// coefficient).
+constexpr int kMedianWarps = 8;
 
-__global__ void __launch_bounds__(kMedianLanes * kMedianGroups)
-batch_median_kernel(const float* __restrict__ x, const int32_t* __restrict__ offsets,
-                    const int32_t* __restrict__ list, int n_pos, int z, float* __restrict__ packed) {
-    extern __shared__ uint32_t median_keys[];  // [kMedianSmemTokens][32]
-    __shared__ int partial[2][kMedianGroups][kMedianLanes];
-    const int pid = blockIdx.x;
-    const int lane = threadIdx.x & (kMedianLanes - 1), grp = threadIdx.x / kMedianLanes;
-    const int zi = blockIdx.y * kMedianLanes + lane;
-    const bool live = zi < z;
-    const int beg = offsets[pid], n = offsets[pid + 1] - beg;
-    if (blockIdx.y == 0 && threadIdx.x == 0) packed[pid] = (float)n;  // batch_n (PN:112-119)
-    float* out = packed + n_pos + (int64_t)pid * z;
-    if (n == 0) {
-        if (grp == 0 && live) out[zi] = 0.0f;
+__device__ __forceinline__ void transpose_bits32(uint32_t (&a)[32]) {
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            const uint32_t t = ((a[k] >> j) ^ a[k + j]) & m;
+            a[k] ^= (t << j);
+            a[k + j] ^= t;
+        }
+    }
+}
+
+// bit planes of the tokens [t0, t0 + 32) of the list (tokens at or beyond n read as key 0; the candidate mask hides them)
+__device__ __forceinline__ void load_bit_planes(uint32_t (&p)[32], const float* __restrict__ x,
+                                                const int32_t* __restrict__ list, int t0, int n, int z, int zi,
+                                                bool live) {
+    if (t0 >= n) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) p[t] = 0u;
         return;
     }
-    const bool staged = n <= kMedianSmemTokens;
-    if (staged) {
-        for (int t = grp; t < n; t += kMedianGroups)
-            median_keys[t * kMedianLanes + lane] =
-                live ? orderable_key(__ldg(x + (int64_t)__ldg(list + beg + t) * z + zi)) : 0u;
-        __syncthreads();
-    }
-    uint32_t prefix = 0, mask = 0;
-    int r = (n - 1) >> 1;
-    for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t bm = 1u << bit;
-        int cnt0 = 0;
-        if (staged) {
-#pragma unroll 4
-            for (int t = grp; t < n; t += kMedianGroups) {
-                const uint32_t k = median_keys[t * kMedianLanes + lane];
-                cnt0 += ((k & mask) == prefix) && !(k & bm);
-            }
-        } else if (live) {
-            for (int t = grp; t < n; t += kMedianGroups) {
-                const uint32_t k = orderable_key(__ldg(x + (int64_t)__ldg(list + beg + t) * z + zi));
-                cnt0 += ((k & mask) == prefix) && !(k & bm);
-            }
-        }
-        int (*tab)[kMedianLanes] = partial[bit & 1];
-        tab[grp][lane] = cnt0;
-        __syncthreads();
-        cnt0 = 0;
 #pragma unroll
-        for (int g = 0; g < kMedianGroups; ++g) cnt0 += tab[g][lane];
-        if (r >= cnt0) {
-            r -= cnt0;
-            prefix |= bm;
-        }
-        mask |= bm;
+    for (int t = 0; t < 32; ++t)
+        p[t] = (t0 + t < n && live) ? orderable_key(__ldg(x + (int64_t)__ldg(list + t0 + t) * z + zi)) : 0u;
+    transpose_bits32(p);
+}
+
+__device__ __forceinline__ uint32_t first_bits(int count) {  // mask of min(max(count, 0), 32) low bits
+    return count >= 32 ? 0xFFFFFFFFu : (count <= 0 ? 0u : ((1u << count) - 1u));
+}
+
+__global__ void __launch_bounds__(32 * kMedianWarps, 3)
+batch_median_kernel(const float* __restrict__ x, const int32_t* __restrict__ offsets,
+                    const int32_t* __restrict__ list, int n_pos, int z, float* __restrict__ packed) {
+    __shared__ int partial[2][kMedianWarps][32];
+    const int pid = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunks = (z + 31) >> 5;
+    const int beg = offsets[pid], n = offsets[pid + 1] - beg;
+    if (threadIdx.x == 0) packed[pid] = (float)n;  // batch_n (PN:112-119)
+    float* out = packed + n_pos + (int64_t)pid * z;
+    list += beg;
+    if (n == 0) {
+        for (int zi = threadIdx.x; zi < z; zi += blockDim.x) out[zi] = 0.0f;
+        return;
     }
-    // batch_median * batch_n, ready to be summed over ranks
-    if (grp == 0 && live) out[zi] = __fmul_rn(from_orderable(prefix), (float)n);
+    const float fn = (float)n;  // results are batch_median * batch_n, ready to be summed over ranks
+    if (n <= 64) {
+        for (int chunk = warp; chunk < chunks; chunk += kMedianWarps) {
+            const int zi = chunk * 32 + lane;
+            const bool live = zi < z;
+            uint32_t p0[32], p1[32];
+            load_bit_planes(p0, x, list, 0, n, z, zi, live);
+            load_bit_planes(p1, x, list, 32, n, z, zi, live);
+            uint32_t cand0 = first_bits(n), cand1 = first_bits(n - 32), prefix = 0;
+            int r = (n - 1) >> 1;
+#pragma unroll
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint32_t z0 = cand0 & ~p0[bit], z1 = cand1 & ~p1[bit];
+                const int cnt0 = __popc(z0) + __popc(z1);
+                const bool up = r >= cnt0;
+                r -= up ? cnt0 : 0;
+                cand0 = up ? (cand0 & p0[bit]) : z0;
+                cand1 = up ? (cand1 & p1[bit]) : z1;
+                prefix |= up ? (1u << bit) : 0u;
+            }
+            if (live) out[zi] = __fmul_rn(from_orderable(prefix), fn);
+        }
+    } else if (n <= 64 * kMedianWarps) {
+        for (int chunk = 0; chunk < chunks; ++chunk) {
+            const int zi = chunk * 32 + lane;
+            const bool live = zi < z;
+            const int t0 = 32 * warp, t1 = 32 * (kMedianWarps + warp);
+            uint32_t p0[32], p1[32];
+            load_bit_planes(p0, x, list, t0, n, z, zi, live);
+            load_bit_planes(p1, x, list, t1, n, z, zi, live);
+            uint32_t cand0 = first_bits(n - t0), cand1 = first_bits(n - t1), prefix = 0;
+            int r = (n - 1) >> 1;
+#pragma unroll
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint32_t z0 = cand0 & ~p0[bit], z1 = cand1 & ~p1[bit];
+                int (*tab)[32] = partial[bit & 1];
+                tab[warp][lane] = __popc(z0) + __popc(z1);
+                __syncthreads();
+                int cnt0 = 0;
+#pragma unroll
+                for (int g = 0; g < kMedianWarps; ++g) cnt0 += tab[g][lane];
+                const bool up = r >= cnt0;
+                r -= up ? cnt0 : 0;
+                cand0 = up ? (cand0 & p0[bit]) : z0;
+                cand1 = up ? (cand1 & p1[bit]) : z1;
+                prefix |= up ? (1u << bit) : 0u;
+            }
+            if (warp == 0 && live) out[zi] = __fmul_rn(from_orderable(prefix), fn);
+        }
+    } else {
+        for (int chunk = 0; chunk < chunks; ++chunk) {
+            const int zi = chunk * 32 + lane;
+            const bool live = zi < z;
+            uint32_t prefix = 0, mask = 0;
+            int r = (n - 1) >> 1;
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint32_t bm = 1u << bit;
+                int cnt0 = 0;
+                if (live)
+                    for (int t = warp; t < n; t += kMedianWarps) {
+                        const uint32_t k = orderable_key(__ldg(x + (int64_t)__ldg(list + t) * z + zi));
+                        cnt0 += ((k & mask) == prefix) && !(k & bm);
+                    }
+                int (*tab)[32] = partial[bit & 1];
+                tab[warp][lane] = cnt0;
+                __syncthreads();
+                cnt0 = 0;
+#pragma unroll
+                for (int g = 0; g < kMedianWarps; ++g) cnt0 += tab[g][lane];
+                if (r >= cnt0) {
+                    r -= cnt0;
+                    prefix |= bm;
+                }
+                mask |= bm;
+            }
+            if (warp == 0 && live) out[zi] = __fmul_rn(from_orderable(prefix), fn);
+        }
+    }
 }
 
 // median <- (median*n + sum_r batch_median_r*batch_n_r) / clamp(n + batch_n, 1)        PN:135-138
@@ -376,12 +455,7 @@ extern "C" int dcta_patchnorm_batch_median(const float* x, const int32_t* offset
                                            void* stream) {
     DCTA_REQUIRE(x && offsets && list && packed, "patchnorm_batch_median: null pointer");
     DCTA_REQUIRE(n_pos > 0 && z > 0, "patchnorm_batch_median: bad sizes");
-    constexpr int smem = kMedianSmemTokens * kMedianLanes * (int)sizeof(uint32_t);
-    if (cudaFuncSetAttribute(batch_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-        return check_launch("patchnorm_batch_median (shared memory opt-in)");
-    const dim3 grid(n_pos, (z + kMedianLanes - 1) / kMedianLanes);
-    batch_median_kernel<<<grid, kMedianLanes * kMedianGroups, smem, as_stream(stream)>>>(x, offsets, list, n_pos, z,
-                                                                                        packed);
+    batch_median_kernel<<<n_pos, 32 * kMedianWarps, 0, as_stream(stream)>>>(x, offsets, list, n_pos, z, packed);
     return check_launch("patchnorm_batch_median");
 }
 

@@ -331,9 +331,9 @@ def test_patchnorm_matches_oracle_bitwise(D):
     assert np.array_equal(npy(pn(ddp)), on.forward(odp))
 
 
-@pytest.mark.parametrize("H,W,b,s,p", [(1, 2, 40, 40, 14), (3, 3, 9, 64, 14), (2, 2, 6, 50, 6)])
+@pytest.mark.parametrize("H,W,b,s,p", [(1, 2, 40, 40, 14), (3, 3, 9, 64, 14), (2, 2, 6, 50, 6), (4, 4, 12, 60, 14), (6, 6, 10, 70, 6)])
 def test_patchnorm_median_long_and_short_lists(D, H, W, b, s, p):
-    """batch_median_kernel: lists beyond its shared-memory staging (800 tokens per position: counted from global memory),
+    """batch_median_kernel: lists beyond its shared-memory staging (800 tokens per position: counted from global memory), lists of up to 64 tokens (the bit-sliced kernel, one and two token blocks),
     lists inside it, coefficient counts that are not a multiple of its 32-lane chunk, even list lengths (lower median,
     PN:129) and duplicated values: n, median bit-exact vs the oracle."""
     rng = np.random.default_rng(11)
