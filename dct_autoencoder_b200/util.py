@@ -673,6 +673,9 @@ def dct2_inv_fold(yq_hi: torch.Tensor, yq_lo: torch.Tensor, kh: int, kw: int, h:
     return z
 
 
+DECODE_COEF_LIMIT = 2.0 ** 11   # |AC coefficient| the fp16 hi/lo decode operand represents (numeric range)
+
+
 def decode_codes_inv_fold_ok(h: int, w: int, kh: int, kw: int, p: int, c: int, d: int) -> bool:
     return bool(_lib.load().dcta_decode_codes_inv_fold_supported(h, w, kh, kw, p, c, d))
 
@@ -700,6 +703,15 @@ def decode_codes_inv_fold(codes, slot_map, sel, n_img: int, channels: int, th: i
     H, W, eps = norm.max_patch_h, norm.max_patch_w, float(norm.eps)
 
     def build_table():
+        # the fp16 hi/lo operand carries |AC coefficient| < 2^11 (scale 16); the two values a code bit selects are
+        # median +- scale * (b * sqrt(2) + eps), so the statistics decide it: checked once per state, where the table is built
+        if not torch.cuda.is_current_stream_capturing():
+            peak = median.abs() + (b * 2 ** 0.5 + eps) * abs(float(scale))
+            peak[:, 0, 0, 0] = 0.0                                        # the DC term of every channel travels in fp32
+            if not bool((peak < DECODE_COEF_LIMIT).all()):
+                raise ValueError("PatchNorm statistics put de-normalised coefficients at or beyond 2^11 (max %.4g): the "
+                                 "tensor-core decode would overflow its fp16 operand planes; use dct_impl=\"fp32\" "
+                                 "for such statistics" % float(peak.max()))
         tab = torch.empty(lib.dcta_decode_gen_tables_bytes(channels, kh, kw), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.call("dcta_decode_gen_tables", _lib.ptr(median), _lib.ptr(b), channels, H, W, eps, p, kh, kw, float(scale),

@@ -417,3 +417,24 @@ def test_decode_inside_inverse_pass1_is_bit_identical(D, size, max_seq_len, n, b
     assert torch.equal(codes_rt, codes2) and torch.equal(rec_rt, pipe.decode_codes(batch2, codes2))
     kept_all = beta == 0.0 and max_seq_len >= (min(h // 14, 32) * min(w // 14, 32) * 3)
     assert n_launch == (11 if kept_all else 12), n_launch       # no slot-map kernel on the grid path
+
+
+def test_decode_refuses_statistics_beyond_the_fp16_operand_range(D):
+    """The tensor-core decode carries |AC coefficient| < 2^11 in its fp16 hi/lo planes; statistics that put
+    median +- scale*(b*sqrt(2)+eps) beyond that are refused where the two-value table is built instead of overflowing
+    silently (the reference's fp32 path, patchnorm.py:167-177, has no such limit: dct_impl="fp32" keeps it)."""
+    torch.manual_seed(0)
+    x = torch.rand(2, 3, 128, 112).cuda()
+    pipe = _pipe(D, "tc")
+    pipe.fit_norm(x)
+    rec, codes = pipe.roundtrip(x)
+    assert torch.isfinite(rec).all()
+    with torch.no_grad():
+        pipe.norm.b[1, 2, 3, 5] = 4000.0
+    with pytest.raises(ValueError, match="2\\^11"):
+        pipe.roundtrip(x)
+    with torch.no_grad():
+        pipe.norm.b[1, 2, 3, 5] = 1.0
+        pipe.norm.median[2, 0, 0, 0] = 1.0e5       # a DC term: carried in fp32, no limit
+    rec, _ = pipe.roundtrip(x)
+    assert torch.isfinite(rec).all()
