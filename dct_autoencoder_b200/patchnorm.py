@@ -111,8 +111,9 @@ class PatchNorm(nn.Module):
 
     # ------------------------------------------------------------------ statistic fitting
     @torch.no_grad()
-    def _update_stats(self, dct_patches: DCTPatches) -> torch.Tensor:
-        """patchnorm.py:101-155.  Returns the un-normalised patches with padding zeroed."""
+    def _update_stats(self, dct_patches: DCTPatches, want_output: bool = True) -> Optional[torch.Tensor]:
+        """patchnorm.py:101-155.  Returns the un-normalised patches with padding zeroed (``want_output=False``: the
+        caller discards them, as the fitting loop of main.py:115-149 does, and the copy is not made)."""
         og = dct_patches.patches.dtype
         x = to_device_f32(dct_patches.patches)
         dev = x.device
@@ -131,7 +132,7 @@ class PatchNorm(nn.Module):
         lists = torch.empty(2 * max(n_tok, 1), **i32)
         packed = torch.empty(n_pos + n_pos * z, dtype=torch.float32, device=dev)
         abs_dev = torch.empty(n_pos * z, dtype=torch.float32, device=dev)
-        out = torch.empty_like(x)
+        out = torch.empty_like(x) if want_output else None
         sync = self.sync_stats and stats_sync_enabled()
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
@@ -148,11 +149,20 @@ class PatchNorm(nn.Module):
                 all_reduce_sum_(abs_dev)
             _lib.call("dcta_patchnorm_update_b", _lib.ptr(b), _lib.ptr(n), _lib.ptr(packed), _lib.ptr(abs_dev),
                       n_pos, z, st)
-            _lib.call("dcta_zero_padding", _lib.ptr(x), _lib.ptr(pad), _lib.ptr(out), n_tok, z, st)
+            if want_output:
+                _lib.call("dcta_zero_padding", _lib.ptr(x), _lib.ptr(pad), _lib.ptr(out), n_tok, z, st)
         self.invalidate_derived()
+        if not want_output:
+            return None
         return out if og == torch.float32 else out.to(og)
 
     # ------------------------------------------------------------------ public
+    @torch.no_grad()
+    def fit_step(self, dct_patches: DCTPatches) -> None:
+        """One update of the running statistics (what ``forward`` does in training mode, patchnorm.py:101-150) without
+        forming the returned patches."""
+        self._update_stats(dct_patches, want_output=False)
+
     def forward(self, dct_patches: DCTPatches) -> torch.Tensor:
         """patchnorm.py:81-165.  Training and not frozen: update the running statistics and
         return the patches un-normalised (padding zeroed).  Otherwise

@@ -49,7 +49,7 @@ class TransformPipeline:
         was_training, was_frozen = self.norm.training, self.norm.frozen
         self.norm.train()
         self.norm.frozen = False
-        self.norm(self.extractor.process_batch(images, ks))
+        self.norm.fit_step(self.extractor.process_batch(images, ks))
         self.norm.frozen = True
         self.norm.train(was_training)
 
