@@ -228,9 +228,14 @@ __device__ __forceinline__ void load_bit_planes(uint32_t (&p)[32], const float* 
         for (int t = 0; t < 32; ++t) p[t] = 0u;
         return;
     }
+    // the block's 32 token indices: one coalesced load, then broadcast by shuffle (no dependent load per token)
+    const int lane = threadIdx.x & 31;
+    const int my_tok = (t0 + lane < n) ? __ldg(list + t0 + lane) : 0;
 #pragma unroll
-    for (int t = 0; t < 32; ++t)
-        p[t] = (t0 + t < n && live) ? orderable_key(__ldg(x + (int64_t)__ldg(list + t0 + t) * z + zi)) : 0u;
+    for (int t = 0; t < 32; ++t) {
+        const int tok = __shfl_sync(0xffffffffu, my_tok, t);
+        p[t] = (t0 + t < n && live) ? orderable_key(__ldg(x + (int64_t)tok * z + zi)) : 0u;
+    }
     transpose_bits32(p);
 }
 
