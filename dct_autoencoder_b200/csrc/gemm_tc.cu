@@ -940,9 +940,9 @@ extern "C" int dcta_gemm_split(const void* a_hi, const void* a_lo, int a_rows, i
     ep.mode = 0; ep.out_f32 = out; ep.ld = out_ld; ep.batch_stride = out_batch_stride;
     ep.row_scale = row_scale; ep.alpha = alpha; ep.M = a_rows; ep.N = b_rows;
     ep.col_bias = col_bias; ep.a_lo_zero = a_lo == nullptr;
-    if (batch == 1 && b_rows <= 256 && a_rows >= 4096)          // tall-skinny linear layer: one N tile, persistent kernel
-        return b_rows <= 224 ? launch_gemm_persistent<224>(A, B, k, batch, ep, stream)
-                             : launch_gemm_persistent<256>(A, B, k, batch, ep, stream);
+    // tall linear layer: the persistent kernel (epilogue of one tile behind the main loop of the next; a CTA keeps its
+    // N tile when the tile count per row divides the grid, so the weights stay in L2 / shared memory)
+    if (batch == 1 && a_rows >= 4096) return launch_gemm_auto(A, B, k, batch, ep, stream);
     return launch_gemm_split(A, B, k, batch, ep, stream);
 }
 
