@@ -18,7 +18,7 @@
 
 namespace dcta {
 
-constexpr int kPairs = 4;          // (token, codebook) pairs per block iteration
+constexpr int kPairs = 16;         // (token, codebook) pairs per block iteration (one barrier round per 16 rank-one updates)
 constexpr int kMaxD = 14;          // 2^7 x 2^7 table: 64 accumulators per thread
 
 struct EntArgs {
@@ -41,12 +41,13 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
     return red[0];
 }
 
-// per-dimension probabilities of kPairs pairs: sp[pb][i] = (p(bit=1), p(bit=0)); returns the pair's entropy
-// contribution (this thread's share) -- called by threads 0 .. kPairs*d-1
+// per-dimension probabilities of kP pairs: sp[pb][i] = (p(bit=1), p(bit=0)); returns the pairs' entropy
+// contribution (this thread's share)
+template <int kP>
 __device__ __forceinline__ float pair_probs(const EntArgs& a, int64_t n0, int tid, float2 (*sp)[16], float* sval, float* su) {
     float h = 0.f;
-    if (tid < kPairs * a.d) {
-        const int pb = tid / a.d, i = tid - pb * a.d;
+    for (int idx = tid; idx < kP * a.d; idx += 256) {
+        const int pb = idx / a.d, i = idx - pb * a.d;
         const int64_t n = n0 + pb;
         float2 p = make_float2(0.f, 0.f);
         float u = 0.f;
@@ -59,7 +60,7 @@ __device__ __forceinline__ float pair_probs(const EntArgs& a, int64_t n0, int ti
                 const float e = __expf(-fabsf(u));               // in (0, 1]
                 const float big = 1.f / (1.f + e), small = e * big;   // sigmoid(|u|), sigmoid(-|u|)
                 p = u >= 0.f ? make_float2(big, small) : make_float2(small, big);
-                h = log1pf(e) + fabsf(u) * small;                 // binary entropy of sigmoid(u), nats
+                h += log1pf(e) + fabsf(u) * small;                // binary entropy of sigmoid(u), nats
             }
         }
         sp[pb][i] = p;
@@ -69,27 +70,56 @@ __device__ __forceinline__ float pair_probs(const EntArgs& a, int64_t n0, int ti
     return h;
 }
 
-// U[pb][j1], V[pb][j2]: products of the per-dimension probabilities of each half (zero for masked pairs)
+// U[pair][j1], V[pair][j2]: products of the per-dimension probabilities of each half (zero for masked pairs).
+// One work item = the 2^HB values j = (m << LBITS) | g that share their LOW bits g (HB = min(D, 4) high bits m
+// enumerated by doubling: 30 multiplications for 16 values instead of 16 x 7), so that consecutive threads store to
+// consecutive addresses.  kTransposed: the tables are written as [j][pair] (the backward pass reads 8 pairs of one j);
+// kP: pairs per round.
+template <bool kTransposed, int kP>
 __device__ __forceinline__ void pair_factors(const EntArgs& a, int tid, const float2 (*sp)[16], const float* sval,
-                                             float (*sU)[128], float (*sV)[128]) {
-    const int NU = 1 << a.D1, NV = 1 << a.D2;
-    for (int idx = tid; idx < kPairs * (NU + NV); idx += 256) {
-        const int pb = idx / (NU + NV), r = idx - pb * (NU + NV);
-        float v = sval[pb];
-        if (r < NU) {
-            for (int i = 0; i < a.D1; ++i) v *= ((r >> (a.D1 - 1 - i)) & 1) ? sp[pb][i].x : sp[pb][i].y;
-            sU[pb][r] = v;
-        } else {
-            const int q = r - NU;
-            v = v != 0.f ? 1.f : 0.f;
-            for (int i = 0; i < a.D2; ++i) v *= ((q >> (a.D2 - 1 - i)) & 1) ? sp[pb][a.D1 + i].x : sp[pb][a.D1 + i].y;
-            sV[pb][q] = v;
+                                             float* sU, float* sV) {
+    const int HB1 = min(a.D1, 4), HB2 = min(a.D2, 4);
+    const int items_u = 1 << (a.D1 - HB1), items_v = 1 << (a.D2 - HB2);
+    const int per_pair = items_u + items_v;
+    for (int item = tid; item < kP * per_pair; item += 256) {
+        // transposed tables: consecutive threads take consecutive pairs (the fastest index of the table)
+        const int pb = kTransposed ? item % kP : item / per_pair;
+        const int rem = kTransposed ? item / kP : item - pb * per_pair;
+        const bool second = rem >= items_u;
+        const int g = second ? rem - items_u : rem;
+        const int D = second ? a.D2 : a.D1, HB = second ? HB2 : HB1, LBITS = D - HB;
+        const float2* p = &sp[pb][second ? a.D1 : 0];       // p[i]: dimension i of this half = bit D-1-i of j
+        float v = sval[pb];                                   // 1 for a valid pair, 0 for a masked one
+        for (int i = 0; i < LBITS; ++i) v *= ((g >> (LBITS - 1 - i)) & 1) ? p[HB + i].x : p[HB + i].y;
+        float t[16];
+        t[0] = v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < HB) {
+                const float2 pk = p[k];
+#pragma unroll
+                for (int m = (1 << k) - 1; m >= 0; --m) {
+                    const float tm = t[m];
+                    t[2 * m + 1] = tm * pk.x;
+                    t[2 * m] = tm * pk.y;
+                }
+            }
         }
+        float* out = second ? sV : sU;
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+            if (m < (1 << HB)) {
+                const int j = (m << LBITS) | g;
+                out[kTransposed ? j * kP + pb : pb * 128 + j] = t[m];
+            }
     }
 }
 
-// forward: partial[cta][2^d] = sum over this CTA's pairs of U (x) V;  stats[cta] = (entropy sum, valid pairs)
-__global__ void __launch_bounds__(256) lfq_entropy_fwd_kernel(EntArgs a, float* __restrict__ partial, float* __restrict__ stats) {
+// forward: partial[cta][2^d] = sum over this CTA's pairs of U (x) V;  stats[cta] = (entropy sum, valid pairs).
+// kRU x kRV: the register tile of a thread (threads as 16 x 16) when the halves have 128 / 64 entries (d = 13, 14: the
+// operands then come as 128-bit shared-memory loads); 0: any d, sizes at run time.
+template <int kRU, int kRV>
+__global__ void __launch_bounds__(256, 2) lfq_entropy_fwd_kernel(EntArgs a, float* __restrict__ partial, float* __restrict__ stats) {
     __shared__ float2 sp[kPairs][16];
     __shared__ float sval[kPairs];
     __shared__ __align__(16) float sU[kPairs][128];
@@ -97,7 +127,7 @@ __global__ void __launch_bounds__(256) lfq_entropy_fwd_kernel(EntArgs a, float* 
     __shared__ float red[8];
     const int tid = threadIdx.x;
     const int NU = 1 << a.D1, NV = 1 << a.D2;
-    const int RU = max(1, NU >> 4), RV = max(1, NV >> 4);         // tile of a thread: RU x RV, threads as 16 x 16
+    const int RU = kRU ? kRU : max(1, NU >> 4), RV = kRV ? kRV : max(1, NV >> 4);   // tile of a thread: RU x RV
     const int tu = tid >> 4, tv = tid & 15;
     const bool active = tu * RU < NU && tv * RV < NV;
     float acc[8][8];
@@ -109,23 +139,38 @@ __global__ void __launch_bounds__(256) lfq_entropy_fwd_kernel(EntArgs a, float* 
     const int64_t n_blocks = (a.n_pairs + kPairs - 1) / kPairs;
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         __syncthreads();                                  // the previous iteration's readers are done
-        h_sum += pair_probs(a, blk * kPairs, tid, sp, sval, nullptr);
+        h_sum += pair_probs<kPairs>(a, blk * kPairs, tid, sp, sval, nullptr);
         __syncthreads();
         if (tid < kPairs) n_valid += sval[tid];
-        pair_factors(a, tid, sp, sval, sU, sV);
+        pair_factors<false, kPairs>(a, tid, sp, sval, &sU[0][0], &sV[0][0]);
         __syncthreads();
         if (active) {
-#pragma unroll
+#pragma unroll 4
             for (int pb = 0; pb < kPairs; ++pb) {
+                // an 8-wide tile is two runs of 4, 64 apart: the 16 threads of a row then read 256 contiguous bytes per
+                // 128-bit load (a contiguous run of 8 per thread costs every load a two-way bank conflict)
                 float uu[8], vv[8];
+                if (kRU == 8) {
+                    *reinterpret_cast<float4*>(uu) = *reinterpret_cast<const float4*>(&sU[pb][tu * 4]);
+                    *reinterpret_cast<float4*>(uu + 4) = *reinterpret_cast<const float4*>(&sU[pb][64 + tu * 4]);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) uu[i] = i < RU ? sU[pb][tu * RU + i] : 0.f;
+                    for (int i = 0; i < 8; ++i) uu[i] = i < RU ? sU[pb][tu * RU + i] : 0.f;
+                }
+                if (kRV == 8) {
+                    *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(&sV[pb][tv * 4]);
+                    *reinterpret_cast<float4*>(vv + 4) = *reinterpret_cast<const float4*>(&sV[pb][64 + tv * 4]);
+                } else if (kRV == 4) {
+                    *reinterpret_cast<float4*>(vv) = *reinterpret_cast<const float4*>(&sV[pb][tv * 4]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) vv[j] = j < RV ? sV[pb][tv * RV + j] : 0.f;
+                    for (int j = 0; j < 8; ++j) vv[j] = j < RV ? sV[pb][tv * RV + j] : 0.f;
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(uu[i], vv[j], acc[i][j]);
+                    for (int j = 0; j < 8; ++j)
+                        if ((kRU == 0 || i < kRU) && (kRV == 0 || j < kRV)) acc[i][j] = fmaf(uu[i], vv[j], acc[i][j]);
             }
         }
     }
@@ -135,7 +180,11 @@ __global__ void __launch_bounds__(256) lfq_entropy_fwd_kernel(EntArgs a, float* 
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                if (i < RU && j < RV) out[((tu * RU + i) << a.D2) | (tv * RV + j)] = acc[i][j];
+                if (i < RU && j < RV) {
+                    const int r = kRU == 8 ? (i >> 2) * 64 + tu * 4 + (i & 3) : tu * RU + i;
+                    const int q = kRV == 8 ? (j >> 2) * 64 + tv * 4 + (j & 3) : tv * RV + j;
+                    out[(r << a.D2) | q] = acc[i][j];
+                }
     }
     const float hs = block_sum_256(h_sum, red);
     const float nv = block_sum_256(n_valid, red);
@@ -188,17 +237,24 @@ __global__ void __launch_bounds__(1024) lfq_entropy_final_kernel(const float* __
 
 // backward: grad_x[n, i] = g * du/dx * ( dS/du - dA/du ),  S = sample entropy, A = avg entropy
 //   dS/du_i = -(u_i p_i (1 - p_i)) / n_tok_valid;   dA/du_i = (E_n[G b_i] - p_i E_n[G]) / N_pairs_valid
+// Per round of kPairsB = 32 pairs two small GEMMs against the resident G (shared memory, rows padded to NV + 1):
+//   threads 0..127:   W1[r][pair] = sum_q G[r][q] V[q][pair]
+//   threads 128..255: W2[q][pair] = sum_r G[r][q] U[r][pair]
+// A thread owns 4 rows (columns) j = lane + 32 k and 8 pairs; the 32 lanes of a warp share the pairs, so the operand
+// comes as two broadcast 128-bit loads and G as four conflict-free scalar loads per 32 FMAs.  (A first version with
+// 2 x 8 tiles over 16 pairs spent its time in shared-memory wavefronts: ncu 78 % of the LSU peak, 43 ms.)  Then
+// T1 = U * W1 and T2 = V * W2 overwrite U and V, and one thread per (pair, dimension) sums them with and without its bit.
+constexpr int kPairsB = 32;
+
 __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const float* __restrict__ tables,
                                                               const float* __restrict__ result, const float* __restrict__ grad_out,
                                                               float* __restrict__ grad_x) {
     extern __shared__ __align__(16) float smem_g[];            // G as NU rows of (NV + 1) floats
-    __shared__ float2 sp[kPairs][16];
-    __shared__ float su[kPairs * 16];
-    __shared__ float sval[kPairs];
-    __shared__ __align__(16) float sU[kPairs][128];
-    __shared__ __align__(16) float sV[kPairs][128];
-    __shared__ __align__(16) float sT1[128][kPairs];           // U * (G V) per row j1
-    __shared__ __align__(16) float sT2[128][kPairs];           // V * (G^T U) per column j2
+    __shared__ float2 sp[kPairsB][16];
+    __shared__ float su[kPairsB * 16];
+    __shared__ float sval[kPairsB];
+    __shared__ __align__(16) float sUt[128][kPairsB];          // U[r][pair], then T1 = U * (G V)
+    __shared__ __align__(16) float sVt[128][kPairsB];          // V[q][pair], then T2 = V * (G^T U)
     const int tid = threadIdx.x;
     const int NU = 1 << a.D1, NV = 1 << a.D2, ldg = NV + 1;
     const int n_codes = 1 << a.d;
@@ -207,54 +263,70 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
     const float g = grad_out[0];
     const float inv_tok = n_tok > 0.f ? 1.f / n_tok : 0.f;
     const float inv_pairs = n_tok > 0.f ? 1.f / (n_tok * (float)a.c) : 0.f;
-    const int64_t n_blocks = (a.n_pairs + kPairs - 1) / kPairs;
+    const int64_t n_blocks = (a.n_pairs + kPairsB - 1) / kPairsB;
+    const bool first = tid < 128;
+    const int lane = tid & 31, ph = ((tid >> 5) & 3) * 8;       // rows (columns) lane + 32 k; pairs ph .. ph + 7
+    const int n_own = first ? NU : NV, n_red = first ? NV : NU;
+    const float (*opnd)[kPairsB] = first ? sVt : sUt;           // contracted operand
+    float (*mine)[kPairsB] = first ? sUt : sVt;                 // multiplies the result, then holds it
+    // G[j][x] (own rows: stride ldg between j, 1 between x) or G[x][j] (own columns)
+    const int jstep = first ? ldg : 1, xstep = first ? 1 : ldg;
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         __syncthreads();
-        (void)pair_probs(a, blk * kPairs, tid, sp, sval, su);
+        (void)pair_probs<kPairsB>(a, blk * kPairsB, tid, sp, sval, su);
         __syncthreads();
-        pair_factors(a, tid, sp, sval, sU, sV);
+        pair_factors<true, kPairsB>(a, tid, sp, sval, &sUt[0][0], &sVt[0][0]);
         __syncthreads();
-        if (tid < 128) {
-            // row r of G against V of the four pairs
-            const int r = tid;
-            if (r < NU) {
-                float w[kPairs] = {0.f, 0.f, 0.f, 0.f};
-                const float* grow = smem_g + r * ldg;
-                for (int q = 0; q < NV; ++q) {
-                    const float gv = grow[q];
+        float w[4][8];
 #pragma unroll
-                    for (int pb = 0; pb < kPairs; ++pb) w[pb] = fmaf(gv, sV[pb][q], w[pb]);
-                }
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int pb = 0; pb < kPairs; ++pb) sT1[r][pb] = w[pb] * sU[pb][r];
+            for (int e = 0; e < 8; ++e) w[k][e] = 0.f;
+        {
+            // rows beyond the table (small d) read row `lane` again; their results are dropped
+            const float* g0 = smem_g + (lane < n_own ? lane : 0) * jstep;
+            const int o1 = (lane + 32 < n_own ? 32 : 0) * jstep, o2 = (lane + 64 < n_own ? 64 : 0) * jstep,
+                      o3 = (lane + 96 < n_own ? 96 : 0) * jstep;
+#pragma unroll 2
+            for (int x = 0; x < n_red; ++x) {
+                const float* gx = g0 + x * xstep;
+                const float gv[4] = {gx[0], gx[o1], gx[o2], gx[o3]};
+                const float4 v0 = *reinterpret_cast<const float4*>(&opnd[x][ph]);
+                const float4 v1 = *reinterpret_cast<const float4*>(&opnd[x][ph + 4]);
+                const float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) w[k][e] = fmaf(gv[k], o[e], w[k][e]);
             }
-        } else {
-            const int q = tid - 128;
-            if (q < NV) {
-                float w[kPairs] = {0.f, 0.f, 0.f, 0.f};
-                for (int r = 0; r < NU; ++r) {
-                    const float gv = smem_g[r * ldg + q];
+        }
+        __syncthreads();                                         // every operand has been read: U, V may be overwritten
 #pragma unroll
-                    for (int pb = 0; pb < kPairs; ++pb) w[pb] = fmaf(gv, sU[pb][r], w[pb]);
-                }
-#pragma unroll
-                for (int pb = 0; pb < kPairs; ++pb) sT2[q][pb] = w[pb] * sV[pb][q];
+        for (int k = 0; k < 4; ++k) {
+            const int j = lane + 32 * k;
+            if (j < n_own) {
+                float4 m0 = *reinterpret_cast<const float4*>(&mine[j][ph]);
+                float4 m1 = *reinterpret_cast<const float4*>(&mine[j][ph + 4]);
+                m0.x *= w[k][0]; m0.y *= w[k][1]; m0.z *= w[k][2]; m0.w *= w[k][3];
+                m1.x *= w[k][4]; m1.y *= w[k][5]; m1.z *= w[k][6]; m1.w *= w[k][7];
+                *reinterpret_cast<float4*>(&mine[j][ph]) = m0;
+                *reinterpret_cast<float4*>(&mine[j][ph + 4]) = m1;
             }
         }
         __syncthreads();
-        if (tid < kPairs * a.d) {
-            const int pb = tid / a.d, i = tid - pb * a.d;
-            const int64_t n = blk * kPairs + pb;
+        for (int idx = tid; idx < kPairsB * a.d; idx += 256) {
+            const int pb = idx / a.d, i = idx - pb * a.d;
+            const int64_t n = blk * kPairsB + pb;
             if (n < a.n_pairs) {
                 float out = 0.f;
                 if (sval[pb] != 0.f) {
                     float eg = 0.f, egb = 0.f;                   // E[G], E[G b_i]
                     if (i < a.D1) {
                         const int sh = a.D1 - 1 - i;
-                        for (int r = 0; r < NU; ++r) { const float t = sT1[r][pb]; eg += t; if ((r >> sh) & 1) egb += t; }
+                        for (int r = 0; r < NU; ++r) { const float t = sUt[r][pb]; eg += t; if ((r >> sh) & 1) egb += t; }
                     } else {
                         const int sh = a.D2 - 1 - (i - a.D1);
-                        for (int q = 0; q < NV; ++q) { const float t = sT2[q][pb]; eg += t; if ((q >> sh) & 1) egb += t; }
+                        for (int q = 0; q < NV; ++q) { const float t = sVt[q][pb]; eg += t; if ((q >> sh) & 1) egb += t; }
                     }
                     const float p1 = sp[pb][i].x, p0 = sp[pb][i].y, u = su[pb * 16 + i];
                     const float ds = -(u * p1 * p0) * inv_tok;
@@ -311,7 +383,9 @@ extern "C" int dcta_lfq_entropy_factorized(const float* x, const uint8_t* mask, 
     const int grid = (int)(n_blocks < 1 ? 1 : (n_blocks < 2 * kNumSMs ? n_blocks : 2 * kNumSMs));
     float* stats = partial_scratch + (int64_t)dcta_lfq_entropy_ctas() * ((int64_t)1 << d);
     cudaStream_t st = as_stream(stream);
-    lfq_entropy_fwd_kernel<<<grid, 256, 0, st>>>(a, partial_scratch, stats);
+    if (a.D1 == 7 && a.D2 == 7) lfq_entropy_fwd_kernel<8, 8><<<grid, 256, 0, st>>>(a, partial_scratch, stats);
+    else if (a.D1 == 7 && a.D2 == 6) lfq_entropy_fwd_kernel<8, 4><<<grid, 256, 0, st>>>(a, partial_scratch, stats);
+    else lfq_entropy_fwd_kernel<0, 0><<<grid, 256, 0, st>>>(a, partial_scratch, stats);
     lfq_entropy_final_kernel<<<1, 1024, 0, st>>>(partial_scratch, stats, grid, c, d, eps, tables, result);
     return check_launch("lfq_entropy_factorized");
 }
@@ -326,7 +400,7 @@ extern "C" int dcta_lfq_entropy_factorized_backward(const float* x, const uint8_
     DCTA_REQUIRE(ent_args(a, x, mask, n_tok, c, d, codebook_scale, temperature),
                  "lfq_entropy_factorized_backward: codebook_dim %d outside 1..%d", d, kMaxD);
     if (n_tok == 0) return DCTA_OK;
-    const int64_t n_blocks = ceil_div(a.n_pairs, kPairs);
+    const int64_t n_blocks = ceil_div(a.n_pairs, kPairsB);
     const int grid = (int)(n_blocks < 2 * kNumSMs ? n_blocks : 2 * kNumSMs);
     const size_t smem = sizeof(float) * ((size_t)1 << a.D1) * (((size_t)1 << a.D2) + 1);
     if (smem > 40 * 1024)
