@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
     __shared__ float sval[kPairsB];
     __shared__ __align__(16) float sUt[128][kPairsB];          // U[r][pair], then T1 = U * (G V)
     __shared__ __align__(16) float sVt[128][kPairsB];          // V[q][pair], then T2 = V * (G^T U)
+    __shared__ float sPart[2][4][6][kPairsB];                  // per (half, quarter of the table): total + 5 low-bit sums
     const int tid = threadIdx.x;
     const int NU = 1 << a.D1, NV = 1 << a.D2, ldg = NV + 1;
     const int n_codes = 1 << a.d;
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
     const float inv_pairs = n_tok > 0.f ? 1.f / (n_tok * (float)a.c) : 0.f;
     const int64_t n_blocks = (a.n_pairs + kPairsB - 1) / kPairsB;
     const bool first = tid < 128;
+    const bool fast_sums = a.D1 >= 6 && a.D2 >= 6;             // quarters of 16 or 32 entries: d = 12, 13, 14
     const int lane = tid & 31, ph = ((tid >> 5) & 3) * 8;       // rows (columns) lane + 32 k; pairs ph .. ph + 7
     const int n_own = first ? NU : NV, n_red = first ? NV : NU;
     const float (*opnd)[kPairsB] = first ? sVt : sUt;           // contracted operand
@@ -314,6 +316,27 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
             }
         }
         __syncthreads();
+        if (fast_sums) {
+            // warp = (half, quarter of the table), lane = pair: the quarter's total and its sums over the entries with low
+            // bit b set, b < 5, with the bit pattern of the unrolled loop known at compile time (no divergence)
+            const int wq = tid >> 5, half = wq >> 2, seg = wq & 3;
+            const int L = (half ? NV : NU) >> 2;
+            const float (*tab)[kPairsB] = half ? sVt : sUt;
+            float tot = 0.f, lb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                if (e < L) {
+                    const float t = tab[seg * L + e][lane];
+                    tot += t;
+#pragma unroll
+                    for (int b = 0; b < 5; ++b) if (e & (1 << b)) lb[b] += t;
+                }
+            }
+            sPart[half][seg][0][lane] = tot;
+#pragma unroll
+            for (int b = 0; b < 5; ++b) sPart[half][seg][1 + b][lane] = lb[b];
+            __syncthreads();
+        }
         for (int idx = tid; idx < kPairsB * a.d; idx += 256) {
             const int pb = idx / a.d, i = idx - pb * a.d;
             const int64_t n = blk * kPairsB + pb;
@@ -321,7 +344,17 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
                 float out = 0.f;
                 if (sval[pb] != 0.f) {
                     float eg = 0.f, egb = 0.f;                   // E[G], E[G b_i]
-                    if (i < a.D1) {
+                    if (fast_sums) {
+                        const int half = i >= a.D1, Dh = half ? a.D2 : a.D1;
+                        const int sh = Dh - 1 - (half ? i - a.D1 : i), LB = Dh - 2;
+#pragma unroll
+                        for (int seg = 0; seg < 4; ++seg) {
+                            const float tot = sPart[half][seg][0][pb];
+                            eg += tot;
+                            if (sh < LB) egb += sPart[half][seg][1 + sh][pb];
+                            else if ((seg >> (sh - LB)) & 1) egb += tot;
+                        }
+                    } else if (i < a.D1) {
                         const int sh = a.D1 - 1 - i;
                         for (int r = 0; r < NU; ++r) { const float t = sUt[r][pb]; eg += t; if ((r >> sh) & 1) egb += t; }
                     } else {
@@ -403,8 +436,9 @@ extern "C" int dcta_lfq_entropy_factorized_backward(const float* x, const uint8_
     const int64_t n_blocks = ceil_div(a.n_pairs, kPairsB);
     const int grid = (int)(n_blocks < 2 * kNumSMs ? n_blocks : 2 * kNumSMs);
     const size_t smem = sizeof(float) * ((size_t)1 << a.D1) * (((size_t)1 << a.D2) + 1);
-    if (smem > 40 * 1024)
-        cudaFuncSetAttribute(lfq_entropy_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // static (45 KB) + dynamic shared memory exceed the 48 KB default for every d >= 9: always opt in
+    if (cudaFuncSetAttribute(lfq_entropy_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return check_launch("lfq_entropy_factorized_backward (shared memory opt-in)");
     lfq_entropy_bwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(a, tables, result, grad_out, grad_x);
     return check_launch("lfq_entropy_factorized_backward");
 }

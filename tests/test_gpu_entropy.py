@@ -35,7 +35,7 @@ def dense_loss_f64(x, mask, scale, temperature=0.01, eps=1e-9):
     return sample - avg_ent
 
 
-@pytest.mark.parametrize("c,d,scale_x", [(3, 4, 0.004), (2, 8, 0.01), (4, 7, 0.003), (1, 1, 0.01), (2, 11, 0.002), (14, 14, 0.0015)])
+@pytest.mark.parametrize("c,d,scale_x", [(3, 4, 0.004), (2, 8, 0.01), (4, 7, 0.003), (1, 1, 0.01), (2, 11, 0.002), (3, 12, 0.002), (16, 13, 0.002), (14, 14, 0.0015)])
 def test_factorized_entropy_matches_the_dense_formula(D, c, d, scale_x):
     from dct_autoencoder_b200.util import FactorizedDistance, compute_entropy_loss
     torch.manual_seed(d)
