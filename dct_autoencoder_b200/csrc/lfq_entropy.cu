@@ -70,6 +70,10 @@ __device__ __forceinline__ float pair_probs(const EntArgs& a, int64_t n0, int ti
     return h;
 }
 
+// [j][pair] tables of the backward pass (32 pairs = 8 chunks of 4 per row): the chunk index is XORed with j & 7, so that
+// the 128-bit accesses of 8 lanes on 8 consecutive rows (same pairs) fall on 8 different bank groups
+__device__ __forceinline__ int pair_slot(int j, int pb) { return j * 32 + (pb ^ ((j & 7) << 2)); }
+
 // U[pair][j1], V[pair][j2]: products of the per-dimension probabilities of each half (zero for masked pairs).
 // One work item = the 2^HB values j = (m << LBITS) | g that share their LOW bits g (HB = min(D, 4) high bits m
 // enumerated by doubling: 30 multiplications for 16 values instead of 16 x 7), so that consecutive threads store to
@@ -110,7 +114,7 @@ __device__ __forceinline__ void pair_factors(const EntArgs& a, int tid, const fl
         for (int m = 0; m < 16; ++m)
             if (m < (1 << HB)) {
                 const int j = (m << LBITS) | g;
-                out[kTransposed ? j * kP + pb : pb * 128 + j] = t[m];
+                out[kTransposed ? pair_slot(j, pb) : pb * 128 + j] = t[m];
             }
     }
 }
@@ -253,8 +257,9 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
     __shared__ float2 sp[kPairsB][16];
     __shared__ float su[kPairsB * 16];
     __shared__ float sval[kPairsB];
-    __shared__ __align__(16) float sUt[128][kPairsB];          // U[r][pair], then T1 = U * (G V)
-    __shared__ __align__(16) float sVt[128][kPairsB];          // V[q][pair], then T2 = V * (G^T U)
+    static_assert(kPairsB == 32, "pair_slot assumes rows of 32 pairs");
+    __shared__ __align__(16) float sUt[128 * kPairsB];         // U[r][pair] at pair_slot(r, pair), then T1 = U * (G V)
+    __shared__ __align__(16) float sVt[128 * kPairsB];         // V[q][pair], then T2 = V * (G^T U)
     __shared__ float sPart[2][4][6][kPairsB];                  // per (half, quarter of the table): total + 5 low-bit sums
     const int tid = threadIdx.x;
     const int NU = 1 << a.D1, NV = 1 << a.D2, ldg = NV + 1;
@@ -269,15 +274,15 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
     const bool fast_sums = a.D1 >= 6 && a.D2 >= 6;             // quarters of 16 or 32 entries: d = 12, 13, 14
     const int lane = tid & 31, ph = ((tid >> 5) & 3) * 8;       // rows (columns) lane + 32 k; pairs ph .. ph + 7
     const int n_own = first ? NU : NV, n_red = first ? NV : NU;
-    const float (*opnd)[kPairsB] = first ? sVt : sUt;           // contracted operand
-    float (*mine)[kPairsB] = first ? sUt : sVt;                 // multiplies the result, then holds it
+    const float* opnd = first ? sVt : sUt;                      // contracted operand
+    float* mine = first ? sUt : sVt;                            // multiplies the result, then holds it
     // G[j][x] (own rows: stride ldg between j, 1 between x) or G[x][j] (own columns)
     const int jstep = first ? ldg : 1, xstep = first ? 1 : ldg;
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         __syncthreads();
         (void)pair_probs<kPairsB>(a, blk * kPairsB, tid, sp, sval, su);
         __syncthreads();
-        pair_factors<true, kPairsB>(a, tid, sp, sval, &sUt[0][0], &sVt[0][0]);
+        pair_factors<true, kPairsB>(a, tid, sp, sval, sUt, sVt);
         __syncthreads();
         float w[4][8];
 #pragma unroll
@@ -293,8 +298,8 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
             for (int x = 0; x < n_red; ++x) {
                 const float* gx = g0 + x * xstep;
                 const float gv[4] = {gx[0], gx[o1], gx[o2], gx[o3]};
-                const float4 v0 = *reinterpret_cast<const float4*>(&opnd[x][ph]);
-                const float4 v1 = *reinterpret_cast<const float4*>(&opnd[x][ph + 4]);
+                const float4 v0 = *reinterpret_cast<const float4*>(opnd + pair_slot(x, ph));
+                const float4 v1 = *reinterpret_cast<const float4*>(opnd + pair_slot(x, ph + 4));
                 const float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -307,12 +312,13 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
         for (int k = 0; k < 4; ++k) {
             const int j = lane + 32 * k;
             if (j < n_own) {
-                float4 m0 = *reinterpret_cast<const float4*>(&mine[j][ph]);
-                float4 m1 = *reinterpret_cast<const float4*>(&mine[j][ph + 4]);
+                float4* q0 = reinterpret_cast<float4*>(mine + pair_slot(j, ph));
+                float4* q1 = reinterpret_cast<float4*>(mine + pair_slot(j, ph + 4));
+                float4 m0 = *q0, m1 = *q1;
                 m0.x *= w[k][0]; m0.y *= w[k][1]; m0.z *= w[k][2]; m0.w *= w[k][3];
                 m1.x *= w[k][4]; m1.y *= w[k][5]; m1.z *= w[k][6]; m1.w *= w[k][7];
-                *reinterpret_cast<float4*>(&mine[j][ph]) = m0;
-                *reinterpret_cast<float4*>(&mine[j][ph + 4]) = m1;
+                *q0 = m0;
+                *q1 = m1;
             }
         }
         __syncthreads();
@@ -321,12 +327,12 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
             // bit b set, b < 5, with the bit pattern of the unrolled loop known at compile time (no divergence)
             const int wq = tid >> 5, half = wq >> 2, seg = wq & 3;
             const int L = (half ? NV : NU) >> 2;
-            const float (*tab)[kPairsB] = half ? sVt : sUt;
+            const float* tab = half ? sVt : sUt;
             float tot = 0.f, lb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
                 if (e < L) {
-                    const float t = tab[seg * L + e][lane];
+                    const float t = tab[pair_slot(seg * L + e, lane)];
                     tot += t;
 #pragma unroll
                     for (int b = 0; b < 5; ++b) if (e & (1 << b)) lb[b] += t;
@@ -356,10 +362,10 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
                         }
                     } else if (i < a.D1) {
                         const int sh = a.D1 - 1 - i;
-                        for (int r = 0; r < NU; ++r) { const float t = sUt[r][pb]; eg += t; if ((r >> sh) & 1) egb += t; }
+                        for (int r = 0; r < NU; ++r) { const float t = sUt[pair_slot(r, pb)]; eg += t; if ((r >> sh) & 1) egb += t; }
                     } else {
                         const int sh = a.D2 - 1 - (i - a.D1);
-                        for (int q = 0; q < NV; ++q) { const float t = sVt[q][pb]; eg += t; if ((q >> sh) & 1) egb += t; }
+                        for (int q = 0; q < NV; ++q) { const float t = sVt[pair_slot(q, pb)]; eg += t; if ((q >> sh) & 1) egb += t; }
                     }
                     const float p1 = sp[pb][i].x, p0 = sp[pb][i].y, u = su[pb * 16 + i];
                     const float ds = -(u * p1 * p0) * inv_tok;
