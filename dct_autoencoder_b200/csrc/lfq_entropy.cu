@@ -379,23 +379,58 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
 }
 
 // lfq.py:195-200 backward of the masked commitment loss: grad_x = g * 2 (x - q) * mask / (n_valid * c * d)
+template <int kVec>
 __global__ void __launch_bounds__(256) lfq_commit_bwd_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
                                                              const float* __restrict__ grad_out, const float* __restrict__ n_valid_dev,
                                                              float* __restrict__ grad_x, int64_t n_tok, int cd, float scale) {
     const float nv = n_valid_dev[0];
     const float k = nv > 0.f ? 2.f * grad_out[0] / (nv * (float)cd) : 0.f;
-    const int64_t total = n_tok * cd;
+    const int64_t total = n_tok * cd / kVec;                      // chunks of kVec elements inside one token (cd % kVec == 0)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = x[i];
-        grad_x[i] = mask[i / cd] ? k * (v - (v > 0.f ? scale : -scale)) : 0.f;
+        const bool on = mask[i * kVec / cd] != 0;
+        if (kVec == 4) {
+            const float4 v = ld_stream(reinterpret_cast<const float4*>(x) + i);
+            float4 o;
+            o.x = on ? k * (v.x - (v.x > 0.f ? scale : -scale)) : 0.f;
+            o.y = on ? k * (v.y - (v.y > 0.f ? scale : -scale)) : 0.f;
+            o.z = on ? k * (v.z - (v.z > 0.f ? scale : -scale)) : 0.f;
+            o.w = on ? k * (v.w - (v.w > 0.f ? scale : -scale)) : 0.f;
+            st_stream(reinterpret_cast<float4*>(grad_x) + i, o);
+        } else {
+            const float v = x[i];
+            grad_x[i] = on ? k * (v - (v > 0.f ? scale : -scale)) : 0.f;
+        }
     }
 }
 
-__global__ void count_valid_kernel(const uint8_t* __restrict__ mask, int64_t n, float* __restrict__ out) {
+// number of valid tokens: one CTA (deterministic), 16 mask bytes per load, four loads in flight per thread
+__global__ void __launch_bounds__(256) count_valid_kernel(const uint8_t* __restrict__ mask, int64_t n, float* __restrict__ out) {
     __shared__ float red[8];
-    float s = 0.f;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += mask[i] ? 1.f : 0.f;
-    s = block_sum_256(s, red);
+    int cnt = 0;
+    const bool vec = (reinterpret_cast<uintptr_t>(mask) & 15) == 0;
+    const int64_t n16 = vec ? n / 16 : 0;
+    const uint4* m16 = reinterpret_cast<const uint4*>(mask);
+    for (int64_t i0 = threadIdx.x; i0 < n16; i0 += 4 * blockDim.x) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * blockDim.x;
+            v[u] = i < n16 ? __ldg(m16 + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // bytes are 0 / non-zero: fold every byte to its low bit, then count
+                uint32_t t = w[k];
+                t |= t >> 4; t |= t >> 2; t |= t >> 1;
+                cnt += __popc(t & 0x01010101u);
+            }
+        }
+    }
+    for (int64_t i = n16 * 16 + threadIdx.x; i < n; i += blockDim.x) cnt += mask[i] ? 1 : 0;
+    const float s = block_sum_256((float)cnt, red);
     if (threadIdx.x == 0) out[0] = s;
 }
 
@@ -456,6 +491,9 @@ extern "C" int dcta_lfq_commit_backward(const float* x, const uint8_t* mask, con
     if (n_tok == 0) return DCTA_OK;
     cudaStream_t st = as_stream(stream);
     count_valid_kernel<<<1, 256, 0, st>>>(mask, n_tok, n_valid_scratch);
-    lfq_commit_bwd_kernel<<<grid_for(n_tok * cd, 256), 256, 0, st>>>(x, mask, grad_out, n_valid_scratch, grad_x, n_tok, cd, scale);
+    if (cd % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad_x)) & 15) == 0)
+        lfq_commit_bwd_kernel<4><<<grid_for(n_tok * cd / 4, 256), 256, 0, st>>>(x, mask, grad_out, n_valid_scratch, grad_x, n_tok, cd, scale);
+    else
+        lfq_commit_bwd_kernel<1><<<grid_for(n_tok * cd, 256), 256, 0, st>>>(x, mask, grad_out, n_valid_scratch, grad_x, n_tok, cd, scale);
     return check_launch("lfq_commit_backward");
 }

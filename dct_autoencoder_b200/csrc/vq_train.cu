@@ -108,6 +108,140 @@ extern "C" int dcta_vq_ema_update(float* embed, float* cluster_size, float* embe
     return check_launch("vq_ema_update");
 }
 
+// ------------------------------------------------------------------------------ commitment loss
+// VQ:976-1003: loss = mean over the valid tokens and their dim elements of (q - x)^2, q detached; its gradient
+// together with the straight-through estimator's (VQ:944-952: the output q passes its gradient to x unchanged):
+//   grad_x = grad_q + grad_loss * 2 (x - q) * mask / (n_valid * dim).
+// One flat 128-bit pass each (the eager expressions cost six passes and a host synchronisation for se[mask]);
+// deterministic: per-CTA partial sums in fixed slots, summed by one CTA in a fixed order.
+namespace dcta {
+constexpr int kMseCtas = 4 * kNumSMs;
+
+template <int kVec>
+__global__ void __launch_bounds__(256) masked_mse_partial_kernel(const float* __restrict__ x, const float* __restrict__ q,
+                                                                 const uint8_t* __restrict__ mask, float* __restrict__ partial,
+                                                                 int64_t n_tok, int dim) {
+    __shared__ float red[8];
+    const int64_t n_chunks = n_tok * dim / kVec, stride = (int64_t)gridDim.x * blockDim.x;
+    float se = 0.f, cnt = 0.f;
+    for (int64_t it0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it0 < n_chunks; it0 += 2 * stride) {
+        float a[2][kVec], b[2][kVec], m[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t it = it0 + u * stride;
+            m[u] = 0.f;
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) { a[u][j] = 0.f; b[u][j] = 0.f; }
+            if (it < n_chunks) {
+                if (kVec == 4) {
+                    const float4 fa = ld_stream(reinterpret_cast<const float4*>(x) + it);
+                    const float4 fb = ld_stream(reinterpret_cast<const float4*>(q) + it);
+                    a[u][0] = fa.x; a[u][1 % kVec] = fa.y; a[u][2 % kVec] = fa.z; a[u][3 % kVec] = fa.w;
+                    b[u][0] = fb.x; b[u][1 % kVec] = fb.y; b[u][2 % kVec] = fb.z; b[u][3 % kVec] = fb.w;
+                } else {
+                    a[u][0] = x[it];
+                    b[u][0] = q[it];
+                }
+                const int64_t e = it * kVec, tok = e / dim;
+                m[u] = (mask == nullptr || mask[tok]) ? 1.f : 0.f;
+                if (e - tok * dim == 0) cnt += m[u];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float s4 = 0.f;
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) {
+                const float dq = b[u][j] - a[u][j];
+                s4 = fmaf(dq, dq, s4);
+            }
+            se = fmaf(m[u], s4, se);
+        }
+    }
+    se = warp_sum(se);
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = se; }
+    __syncthreads();
+    float s = 0.f;
+    if (threadIdx.x == 0) for (int w = 0; w < 8; ++w) s += red[w];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float n = 0.f;
+        for (int w = 0; w < 8; ++w) n += red[w];
+        partial[2 * blockIdx.x] = s;
+        partial[2 * blockIdx.x + 1] = n;
+    }
+}
+
+// result[0] = sum / (n_valid * dim) (0 / 0 = NaN like the mean of an empty selection), result[1] = n_valid
+__global__ void masked_mse_final_kernel(const float* __restrict__ partial, int n_partial, int dim, float* __restrict__ result) {
+    if (threadIdx.x != 0) return;
+    float s = 0.f, n = 0.f;
+    for (int i = 0; i < n_partial; ++i) { s += partial[2 * i]; n += partial[2 * i + 1]; }
+    result[0] = s / (n * (float)dim);
+    result[1] = n;
+}
+
+template <int kVec>
+__global__ void __launch_bounds__(256) masked_mse_bwd_kernel(const float* __restrict__ x, const float* __restrict__ q,
+                                                             const uint8_t* __restrict__ mask, const float* __restrict__ result,
+                                                             const float* __restrict__ grad_loss, const float* __restrict__ grad_q,
+                                                             float* __restrict__ grad_x, int64_t n_tok, int dim) {
+    const float nv = result[1];
+    const float k = 2.f * grad_loss[0] / (nv * (float)dim);
+    const int64_t total = n_tok * dim / kVec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool on = mask == nullptr || mask[i * kVec / dim] != 0;
+        if (kVec == 4) {
+            const float4 a = ld_stream(reinterpret_cast<const float4*>(x) + i);
+            const float4 b = ld_stream(reinterpret_cast<const float4*>(q) + i);
+            float4 g = grad_q ? ld_stream(reinterpret_cast<const float4*>(grad_q) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on) {
+                g.x = fmaf(k, a.x - b.x, g.x); g.y = fmaf(k, a.y - b.y, g.y);
+                g.z = fmaf(k, a.z - b.z, g.z); g.w = fmaf(k, a.w - b.w, g.w);
+            }
+            st_stream(reinterpret_cast<float4*>(grad_x) + i, g);
+        } else {
+            float g = grad_q ? grad_q[i] : 0.f;
+            if (on) g = fmaf(k, x[i] - q[i], g);
+            grad_x[i] = g;
+        }
+    }
+}
+}  // namespace dcta
+
+extern "C" int dcta_masked_mse(const float* x, const float* q, const uint8_t* mask, int64_t n_tok, int dim, float* scratch,
+                               float* result, void* stream) {
+    using namespace dcta;
+    DCTA_REQUIRE(x && q && scratch && result && n_tok >= 0 && dim > 0, "masked_mse: bad args");
+    const bool vec = dim % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(q)) & 15) == 0;
+    const int64_t chunks = n_tok * dim / (vec ? 4 : 1);
+    int grid = (int)ceil_div(chunks > 0 ? chunks : 1, 512);
+    if (grid > kMseCtas) grid = kMseCtas;
+    cudaStream_t st = as_stream(stream);
+    if (vec) masked_mse_partial_kernel<4><<<grid, 256, 0, st>>>(x, q, mask, scratch, n_tok, dim);
+    else masked_mse_partial_kernel<1><<<grid, 256, 0, st>>>(x, q, mask, scratch, n_tok, dim);
+    masked_mse_final_kernel<<<1, 32, 0, st>>>(scratch, grid, dim, result);
+    return check_launch("masked_mse");
+}
+
+extern "C" int dcta_masked_mse_scratch_floats(void) { return 2 * dcta::kMseCtas; }
+
+extern "C" int dcta_masked_mse_backward(const float* x, const float* q, const uint8_t* mask, const float* result,
+                                        const float* grad_loss, const float* grad_q, float* grad_x, int64_t n_tok, int dim,
+                                        void* stream) {
+    using namespace dcta;
+    DCTA_REQUIRE(x && q && result && grad_loss && grad_x && n_tok >= 0 && dim > 0, "masked_mse_backward: bad args");
+    if (n_tok == 0) return DCTA_OK;
+    const bool vec = dim % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(q) |
+                                      reinterpret_cast<uintptr_t>(grad_q) | reinterpret_cast<uintptr_t>(grad_x)) & 15) == 0;
+    if (vec) masked_mse_bwd_kernel<4><<<grid_for(n_tok * dim / 4, 256), 256, 0, as_stream(stream)>>>(x, q, mask, result, grad_loss, grad_q, grad_x, n_tok, dim);
+    else masked_mse_bwd_kernel<1><<<grid_for(n_tok * dim, 256), 256, 0, as_stream(stream)>>>(x, q, mask, result, grad_loss, grad_q, grad_x, n_tok, dim);
+    return check_launch("masked_mse_backward");
+}
+
 extern "C" int dcta_vq_kmeans_means(float* means, const float* counts, const float* sums, int n_codes, int d, void* stream) {
     DCTA_REQUIRE(means && counts && sums && n_codes > 0 && d > 0, "vq_kmeans_means: bad args");
     vq_kmeans_means_kernel<<<grid_for((int64_t)n_codes * d, 256), 256, 0, as_stream(stream)>>>(means, counts, sums, n_codes, d);

@@ -22,6 +22,20 @@ def _exists(v):
     return v is not None
 
 
+class _StraightThrough(torch.autograd.Function):
+    """lfq.py:179-181 ``x + (quantized - x).detach()``: the value is ``quantized`` (x - x is an exact zero for finite
+    x), the gradient goes to ``x`` unchanged -- without the two elementwise passes over (b, n, c*d) the expression costs
+    in eager mode.  (A non-finite x gives +-scale here where the expression would give NaN.)"""
+
+    @staticmethod
+    def forward(ctx, x, quantized):
+        return quantized.view_as(quantized)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 class _CommitLoss(torch.autograd.Function):
     """lfq.py:195-200: sum over valid tokens of (x - q)^2 / (n_valid * c * d)."""
 
@@ -214,7 +228,7 @@ class LFQ(nn.Module):
 
         if self.training:
             xa = self.activation(x)
-            out = xa - xa.detach() + quantized          # straight-through (lfq.py:179-181)
+            out = _StraightThrough.apply(xa, quantized) if xa.requires_grad else quantized   # straight-through (lfq.py:179-181)
             if b * n * c * 2 ** d <= self.dense_distance_limit:
                 distance = _Distance.apply(original_input.reshape(b, n, c, d), self.codebook_scale, self.codebook)
             else:

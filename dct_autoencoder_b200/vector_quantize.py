@@ -216,6 +216,36 @@ class EuclideanCodebook(nn.Module):
         invalidate_codebook_cache()
 
 
+class _CommitStraightThrough(torch.autograd.Function):
+    """(x, q detached, mask) -> (q with the straight-through gradient, mean over the valid tokens of (q - x)^2):
+    vector_quantize.py:944-952 and :976-1003.  A non-finite x gives q where ``x + (q - x).detach()`` would give NaN."""
+
+    @staticmethod
+    def forward(ctx, x, q, mask):
+        xc, qc = x.detach().contiguous(), q.contiguous()
+        dim = xc.shape[-1]
+        m = None if mask is None else mask.reshape(-1).to(torch.uint8).contiguous()
+        result = torch.empty(2, dtype=torch.float32, device=xc.device)
+        scratch = torch.empty(int(_lib.load().dcta_masked_mse_scratch_floats()), dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            _lib.call("dcta_masked_mse", _lib.ptr(xc), _lib.ptr(qc), _lib.ptr(m), xc.numel() // dim, dim, _lib.ptr(scratch),
+                      _lib.ptr(result), _lib.stream_ptr(xc.device))
+        ctx.save_for_backward(xc, qc, m, result)
+        return q.view_as(q), result[0]
+
+    @staticmethod
+    def backward(ctx, gq, gloss):
+        xc, qc, m, result = ctx.saved_tensors
+        dim = xc.shape[-1]
+        gq = None if gq is None else gq.to(torch.float32).contiguous()
+        gl = (torch.zeros(1, device=xc.device) if gloss is None else gloss.detach().reshape(1).to(torch.float32).contiguous())
+        gx = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            _lib.call("dcta_masked_mse_backward", _lib.ptr(xc), _lib.ptr(qc), _lib.ptr(m), _lib.ptr(result), _lib.ptr(gl),
+                      _lib.ptr(gq), _lib.ptr(gx), xc.numel() // dim, dim, _lib.stream_ptr(xc.device))
+        return gx, None, None
+
+
 class VectorQuantize(nn.Module):
     def __init__(self, dim, codebook_size, codebook_dim=None, heads=1, separate_codebook_per_head=False, decay=0.8,
                  eps=1e-5, freeze_codebook=False, kmeans_init=False, kmeans_iters=10, sync_kmeans=True,
@@ -365,11 +395,18 @@ class VectorQuantize(nn.Module):
                     cb.ema_update_(i, v, fi, m)
                     cb.expire_codes_(i, v)
             # commitment loss against the detached codes, straight-through estimator (vector_quantize.py:944-952, :976-1003)
-            if self.commitment_weight > 0:
-                se = (q.detach() - x) ** 2
-                commit = se[mask].mean() if mask is not None else se.mean()
+            if (self.commitment_weight > 0 and x.is_cuda and x.dtype == torch.float32 and q.dtype == torch.float32
+                    and (mask is None or mask.shape == x.shape[:-1])):
+                # both in one flat pass forward and one backward (csrc/vq_train.cu: masked_mse_*); the eager expressions
+                # below cost six passes over (b, n, dim) and a host synchronisation for se[mask]
+                q, commit = _CommitStraightThrough.apply(x, q.detach(), mask)
                 loss = loss + commit * self.commitment_weight
-            q = x + (q - x).detach()
+            else:
+                if self.commitment_weight > 0:
+                    se = (q.detach() - x) ** 2
+                    commit = se[mask].mean() if mask is not None else se.mean()
+                    loss = loss + commit * self.commitment_weight
+                q = x + (q - x).detach()
         if self.accept_image_fmap:
             ind = ind.reshape(b, height, width, *ind.shape[2:])
         if only_one:

@@ -534,6 +534,18 @@ int dcta_vq_ema_update(float* embed, float* cluster_size, float* embed_avg, cons
                        int n_codes, int d, float decay, float eps, float* total_scratch, void* stream);
 int dcta_vq_kmeans_means(float* means, const float* counts, const float* sums, int n_codes, int d, void* stream);
 
+/* VectorQuantize commitment loss with the straight-through estimator (VQ:944-952, 976-1003), forward and backward in one
+ * flat pass each.
+ *   dcta_masked_mse: result[0] = mean over the tokens with mask[t] != 0 (mask uint8 (n_tok), nullable = all) and their dim
+ *     elements of (q - x)^2, result[1] = number of those tokens; scratch: dcta_masked_mse_scratch_floats() floats.
+ *   dcta_masked_mse_backward: grad_x = grad_q (nullable = 0) + grad_loss[0] * 2 (x - q) * mask / (result[1] * dim). */
+int dcta_masked_mse_scratch_floats(void);
+int dcta_masked_mse(const float* x, const float* q, const uint8_t* mask, int64_t n_tok, int dim, float* scratch,
+                    float* result, void* stream);
+int dcta_masked_mse_backward(const float* x, const float* q, const uint8_t* mask, const float* result,
+                             const float* grad_loss, const float* grad_q, float* grad_x, int64_t n_tok, int dim,
+                             void* stream);
+
 /* ------------------------------------------------------------------ un-patchify ----------- */
 /* FE:619-643: slot_map (n_img, channels, th, tw) i32 = flat token index (row*s + slot) of the LAST
  * valid token at that position, -1 where none (the call fills it).
