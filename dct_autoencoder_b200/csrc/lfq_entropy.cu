@@ -19,6 +19,8 @@
 namespace dcta {
 
 constexpr int kPairs = 16;         // (token, codebook) pairs per block iteration (one barrier round per 16 rank-one updates)
+constexpr int kSpPitch = 17;        // float2 per pair in the probability table: an odd pitch, so that threads on consecutive
+                                   // pairs (the backward pass' factor generation) do not all hit the same banks
 constexpr int kMaxD = 14;          // 2^7 x 2^7 table: 64 accumulators per thread
 
 struct EntArgs {
@@ -44,7 +46,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
 // per-dimension probabilities of kP pairs: sp[pb][i] = (p(bit=1), p(bit=0)); returns the pairs' entropy
 // contribution (this thread's share)
 template <int kP>
-__device__ __forceinline__ float pair_probs(const EntArgs& a, int64_t n0, int tid, float2 (*sp)[16], float* sval, float* su) {
+__device__ __forceinline__ float pair_probs(const EntArgs& a, int64_t n0, int tid, float2 (*sp)[kSpPitch], float* sval, float* su) {
     float h = 0.f;
     for (int idx = tid; idx < kP * a.d; idx += 256) {
         const int pb = idx / a.d, i = idx - pb * a.d;
@@ -80,7 +82,7 @@ __device__ __forceinline__ int pair_slot(int j, int pb) { return j * 32 + (pb ^ 
 // consecutive addresses.  kTransposed: the tables are written as [j][pair] (the backward pass reads 8 pairs of one j);
 // kP: pairs per round.
 template <bool kTransposed, int kP>
-__device__ __forceinline__ void pair_factors(const EntArgs& a, int tid, const float2 (*sp)[16], const float* sval,
+__device__ __forceinline__ void pair_factors(const EntArgs& a, int tid, const float2 (*sp)[kSpPitch], const float* sval,
                                              float* sU, float* sV) {
     const int HB1 = min(a.D1, 4), HB2 = min(a.D2, 4);
     const int items_u = 1 << (a.D1 - HB1), items_v = 1 << (a.D2 - HB2);
@@ -124,7 +126,7 @@ __device__ __forceinline__ void pair_factors(const EntArgs& a, int tid, const fl
 // operands then come as 128-bit shared-memory loads); 0: any d, sizes at run time.
 template <int kRU, int kRV>
 __global__ void __launch_bounds__(256, 2) lfq_entropy_fwd_kernel(EntArgs a, float* __restrict__ partial, float* __restrict__ stats) {
-    __shared__ float2 sp[kPairs][16];
+    __shared__ float2 sp[kPairs][kSpPitch];
     __shared__ float sval[kPairs];
     __shared__ __align__(16) float sU[kPairs][128];
     __shared__ __align__(16) float sV[kPairs][128];
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
                                                               const float* __restrict__ result, const float* __restrict__ grad_out,
                                                               float* __restrict__ grad_x) {
     extern __shared__ __align__(16) float smem_g[];            // G as NU rows of (NV + 1) floats
-    __shared__ float2 sp[kPairsB][16];
+    __shared__ float2 sp[kPairsB][kSpPitch];
     __shared__ float su[kPairsB * 16];
     __shared__ float sval[kPairsB];
     static_assert(kPairsB == 32, "pair_slot assumes rows of 32 pairs");
@@ -294,17 +296,39 @@ __global__ void __launch_bounds__(256) lfq_entropy_bwd_kernel(EntArgs a, const f
             const float* g0 = smem_g + (lane < n_own ? lane : 0) * jstep;
             const int o1 = (lane + 32 < n_own ? 32 : 0) * jstep, o2 = (lane + 64 < n_own ? 64 : 0) * jstep,
                       o3 = (lane + 96 < n_own ? 96 : 0) * jstep;
-#pragma unroll 2
-            for (int x = 0; x < n_red; ++x) {
-                const float* gx = g0 + x * xstep;
-                const float gv[4] = {gx[0], gx[o1], gx[o2], gx[o3]};
-                const float4 v0 = *reinterpret_cast<const float4*>(opnd + pair_slot(x, ph));
-                const float4 v1 = *reinterpret_cast<const float4*>(opnd + pair_slot(x, ph + 4));
-                const float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            if ((n_red & 7) == 0) {
+                // eight steps at a time: (x & 7) is then a compile-time constant and the swizzled operand addresses are
+                // one XOR away from a per-block base (ncu: the per-step shifts / multiplies of pair_slot were a fifth of the
+                // loop's instructions)
+                for (int xb = 0; xb < n_red; xb += 8) {
+                    const float* gx0 = g0 + xb * xstep;
+                    const float* ob = opnd + xb * 32;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                    for (int j = 0; j < 8; ++j) {
+                        const float* gx = gx0 + j * xstep;
+                        const float gv[4] = {gx[0], gx[o1], gx[o2], gx[o3]};
+                        const int c0 = ph ^ (j << 2);
+                        const float4 v0 = *reinterpret_cast<const float4*>(ob + j * 32 + c0);
+                        const float4 v1 = *reinterpret_cast<const float4*>(ob + j * 32 + (c0 ^ 4));
+                        const float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) w[k][e] = fmaf(gv[k], o[e], w[k][e]);
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) w[k][e] = fmaf(gv[k], o[e], w[k][e]);
+                    }
+                }
+            } else {
+                for (int x = 0; x < n_red; ++x) {
+                    const float* gx = g0 + x * xstep;
+                    const float gv[4] = {gx[0], gx[o1], gx[o2], gx[o3]};
+                    const float4 v0 = *reinterpret_cast<const float4*>(opnd + pair_slot(x, ph));
+                    const float4 v1 = *reinterpret_cast<const float4*>(opnd + pair_slot(x, ph + 4));
+                    const float o[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) w[k][e] = fmaf(gv[k], o[e], w[k][e]);
+                }
             }
         }
         __syncthreads();                                         // every operand has been read: U, V may be overwritten
