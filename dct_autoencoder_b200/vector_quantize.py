@@ -137,9 +137,21 @@ class EuclideanCodebook(nn.Module):
         self.sync = sync                                       # None: whenever torch.distributed has more than one rank
         self.ema_update = ema_update
         self.register_buffer("initted", torch.Tensor([not kmeans_init]))
+        # host mirror of `initted` once it is known to be set (it never goes back): the reference reads the device flag on
+        # every training forward (vector_quantize.py:334-336), a host synchronisation per step
+        self._initted_host = not kmeans_init
         self.register_buffer("cluster_size", torch.zeros(num_codebooks, codebook_size))
         self.register_buffer("embed_avg", embed.clone())
         self.register_buffer("embed", embed)
+
+    def is_initted(self) -> bool:
+        if not self._initted_host:
+            self._initted_host = bool(self.initted)           # one device read, e.g. after load_state_dict
+        return self._initted_host
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._initted_host = False                           # whatever the checkpoint says: read it once
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def _reduce(self, t):
         return _all_reduce_sum_(t) if self.sync in (None, True) else t
@@ -351,10 +363,11 @@ class VectorQuantize(nn.Module):
         else:
             views = [xf.reshape(b * n, d)]
             masks = [None if mask is None else mask.reshape(-1)]
-        if self.training and not bool(cb.initted):
+        if self.training and not cb.is_initted():
             for i, (v, m) in enumerate(zip(views, masks)):
                 cb.init_embed_(i, v, m, self.vq_impl)                       # vector_quantize.py:334-355
             cb.initted.fill_(1.0)
+            cb._initted_host = True
         ef = to_device_f32(embed)
         if h > 1 and self.separate_codebook_per_head:
             xs = xf.reshape(b, n, h, d).permute(2, 0, 1, 3).contiguous()    # 'h b n d'
