@@ -1899,7 +1899,6 @@ __global__ void __launch_bounds__(256, 8) codes_bitplanes_kernel(const int64_t* 
                                                                  float dc_factor) {
     extern __shared__ __align__(16) uint16_t stage[];          // [b][a][kb][32 rows][4]
     constexpr int p = 2 * HW;
-    const int64_t n_planes = n_img * C;
     const int64_t plane = blockIdx.x;
     const int iblk = blockIdx.y;
     const int blk_words = num_kb * 128;                        // words of one (b, a)
