@@ -120,6 +120,7 @@ SIGNATURES = {
     "dcta_vq_cluster_stats": [P, P, P, c_int64, c_int, c_int, P, P, P],
     "dcta_vq_ema_update": [P, P, P, P, P, c_int, c_int, c_float, c_float, P, P],
     "dcta_masked_mse_scratch_floats": [],
+    "dcta_lfq_entropy_use_tensor_cores": [c_int],
     "dcta_masked_mse": [P, P, P, c_int64, c_int, P, P, P],
     "dcta_masked_mse_backward": [P, P, P, P, P, P, P, c_int64, c_int, P],
     "dcta_vq_kmeans_means": [P, P, P, c_int, c_int, P],
@@ -147,7 +148,7 @@ KERNELS_PER_CALL = {
     "dcta_dct2_fwd_tc": 2, "dcta_dct2_inv_tc": 2,
     "dcta_ln_pos_rows": 1, "dcta_split_rows_rowscale": 1, "dcta_split_rows_patchnorm": 1, "dcta_unpatchify_denorm_fold": 1, "dcta_pack_tiles_index": 1, "dcta_lfq_entropy_ctas": 0, "dcta_lfq_entropy_factorized": 2,
     "dcta_lfq_entropy_factorized_backward": 1, "dcta_lfq_commit_backward": 2,
-    "dcta_row_sumsq": 1, "dcta_vq_nearest_tc": 2, "dcta_vq_nearest_tc_masked": 2, "dcta_vq_cluster_stats": 1, "dcta_resize_bilinear_aa": 1, "dcta_resize_bilinear_aa_u8": 1, "dcta_vq_ema_update": 2, "dcta_vq_kmeans_means": 1, "dcta_masked_mse": 2, "dcta_masked_mse_backward": 1, "dcta_masked_mse_scratch_floats": 0,
+    "dcta_row_sumsq": 1, "dcta_vq_nearest_tc": 2, "dcta_vq_nearest_tc_masked": 2, "dcta_vq_cluster_stats": 1, "dcta_resize_bilinear_aa": 1, "dcta_resize_bilinear_aa_u8": 1, "dcta_vq_ema_update": 2, "dcta_vq_kmeans_means": 1, "dcta_masked_mse": 2, "dcta_masked_mse_backward": 1, "dcta_masked_mse_scratch_floats": 0, "dcta_lfq_entropy_use_tensor_cores": 0,
     "dcta_pack_codes_lfq": 2, "dcta_decode_codes_split": 1,
     "dcta_fold_supported": 0, "dcta_fold_codes_supported": 0, "dcta_rgb_to_ipt_fold": 2, "dcta_rgb_u8_to_ipt_fold": 2, "dcta_unfold_ipt_to_rgb_u8": 1, "dcta_fold_planes": 3, "dcta_dct2_fwd_fold": 2,
     "dcta_unpatchify_fold": 1, "dcta_decode_codes_fold": 2, "dcta_decode_codes_inv_fold": 3, "dcta_decode_grid_inv_fold": 3, "dcta_decode_gen_tables": 1, "dcta_decode_gen_tables_bytes": 0,

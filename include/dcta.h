@@ -444,6 +444,9 @@ int dcta_decode_codes_split(const int64_t* codes, const int32_t* slot_map, const
  * dcta_lfq_entropy_factorized_backward: grad_x (n_tok, c*d) = grad_out[0] * d loss / d x (zero on masked tokens).
  * dcta_lfq_commit_backward: gradient of dcta_lfq_commit_loss (LFQ:195-200): grad_out[0] * 2 (x - q) / (n_valid c d). */
 int dcta_lfq_entropy_ctas(void);
+/* d = 14: the forward contraction runs on tcgen05 (fp16 hi / lo operands generated in shared memory, fp32 accumulation in
+ * TMEM flushed every 1024 pairs); dcta_lfq_entropy_use_tensor_cores(0) selects the fp32 FMA kernel instead (default 1). */
+int dcta_lfq_entropy_use_tensor_cores(int on);
 int dcta_lfq_entropy_factorized(const float* x, const uint8_t* mask, int64_t n_tok, int c, int d, float codebook_scale,
                                 float temperature, float eps, float* partial_scratch, float* tables, float* result,
                                 void* stream);

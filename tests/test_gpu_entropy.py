@@ -122,3 +122,31 @@ def test_factorized_entropy_at_the_benchmark_shape(D):
     hist = torch.bincount(idx, minlength=2 ** d).double() / idx.numel()
     want = (hist * (hist + 1e-9).log()).sum()
     assert abs(float(ls) - float(want)) < 2e-3 * abs(float(want))
+
+
+def test_tensor_core_forward_equals_the_fma_forward(D):
+    """d = 14: the forward contraction on tcgen05 (fp16 hi / lo operands, TMEM accumulators flushed every 1024 pairs)
+    against the fp32 FMA kernel on the same input -- loss, entropies and the gradient that is computed from its tables;
+    token counts that leave a ragged last stage, several flush rounds per CTA, masked tokens, saturated and soft inputs."""
+    from dct_autoencoder_b200 import _lib
+    from dct_autoencoder_b200.util import FactorizedDistance, compute_entropy_loss
+    lib = _lib.load()
+    torch.manual_seed(5)
+    for (b, n, c, scale_x) in [(1, 3, 1, 0.002), (7, 501, 14, 0.002), (64, 3000, 14, 0.004), (3, 700, 5, 0.05)]:
+        x = (torch.randn(b, n, c, 14, device="cuda") * scale_x)
+        mask = torch.rand(b, n, device="cuda") > 0.2
+        mask[0, 0] = True
+        out = []
+        for on in (1, 0):
+            lib.dcta_lfq_entropy_use_tensor_cores(on)
+            try:
+                xr = x.clone().requires_grad_(True)
+                loss = compute_entropy_loss(FactorizedDistance(xr, 1.0), mask)
+                loss.backward()
+                out.append((float(loss), xr.grad.clone()))
+            finally:
+                lib.dcta_lfq_entropy_use_tensor_cores(1)
+        (l_tc, g_tc), (l_fma, g_fma) = out
+        assert abs(l_tc - l_fma) < 1e-5 * max(1.0, abs(l_fma)), (b, n, c, l_tc, l_fma)
+        gmax = float(g_fma.abs().max())
+        assert float((g_tc - g_fma).abs().max()) < 2e-5 * gmax
