@@ -470,8 +470,8 @@ int launch_lfq_entropy_final(const float* partial, const float* stats, int n_cta
     lfq_entropy_final_kernel<<<1, 1024, 0, st>>>(partial, stats, n_cta, c, d, eps, tables, result);
     return check_launch("lfq_entropy_factorized");
 }
-// lfq_entropy_tc.cu: the forward contraction on tcgen05 (d = 14)
-int launch_lfq_entropy_fwd_tc(const float* x, const uint8_t* mask, int64_t n_tok, int c, float u_scale, float eps,
+// lfq_entropy_tc.cu: the forward contraction on tcgen05 (d = 13, 14)
+int launch_lfq_entropy_fwd_tc(const float* x, const uint8_t* mask, int64_t n_tok, int c, int d, float u_scale, float eps,
                               float* partial_scratch, float* stats, float* tables, float* result, cudaStream_t st);
 
 }  // namespace dcta
@@ -497,8 +497,8 @@ extern "C" int dcta_lfq_entropy_factorized(const float* x, const uint8_t* mask, 
     const int grid = (int)(n_blocks < 1 ? 1 : (n_blocks < 2 * kNumSMs ? n_blocks : 2 * kNumSMs));
     float* stats = partial_scratch + (int64_t)dcta_lfq_entropy_ctas() * ((int64_t)1 << d);
     cudaStream_t st = as_stream(stream);
-    if (d == 14 && n_tok > 0 && g_entropy_tc)
-        return launch_lfq_entropy_fwd_tc(x, mask, n_tok, c, a.u_scale, eps, partial_scratch, stats, tables, result, st);
+    if ((d == 14 || d == 13) && n_tok > 0 && g_entropy_tc)
+        return launch_lfq_entropy_fwd_tc(x, mask, n_tok, c, d, a.u_scale, eps, partial_scratch, stats, tables, result, st);
     if (a.D1 == 7 && a.D2 == 7) lfq_entropy_fwd_kernel<8, 8><<<grid, 256, 0, st>>>(a, partial_scratch, stats);
     else if (a.D1 == 7 && a.D2 == 6) lfq_entropy_fwd_kernel<8, 4><<<grid, 256, 0, st>>>(a, partial_scratch, stats);
     else lfq_entropy_fwd_kernel<0, 0><<<grid, 256, 0, st>>>(a, partial_scratch, stats);

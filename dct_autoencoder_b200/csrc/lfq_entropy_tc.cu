@@ -1,4 +1,4 @@
-// Factorised LFQ entropy loss, forward, on the tensor cores (d = 14: two halves of 7 bits).
+// Factorised LFQ entropy loss, forward, on the tensor cores (d = 14: two halves of 7 bits; d = 13: 7 + 6, N = 64).
 //
 // The average distribution of util.py:355-387 over LFQ's factorised softmax (see lfq_entropy.cu) is
 //     avg[j1, j2] = (1/N) sum_n U_n[j1] * V_n[j2],
@@ -32,7 +32,6 @@ constexpr int kStages = 6;
 constexpr int kProducers = 2 * kStages, kThreads = 32 * (kProducers + 1 + 4);   // + MMA warp + 4 epilogue warps
 constexpr int kFlushStages = 32;                     // stages accumulated in TMEM before a flush
 constexpr float kScale = 16384.f, kUnscale = 1.f / (16384.f * 16384.f);
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // f32 acc, f16 x f16, M = N = 128
 constexpr int kSmem = kStages * kStage + 1024;
 }  // namespace etc
 
@@ -46,13 +45,14 @@ struct EntTcArgs {
 
 // the 128 products of 7 per-dimension probabilities (dimension 0 = the highest bit), scaled, as fp16 hi / lo into column
 // `lane` of a [128][32] SWIZZLE_64B tile; base[x] = tile + ((chunk ^ x) << 4) + (lane & 7) * 2
+template <int kDims>     // 7 or 6 dimensions in this half: 2^kDims rows
 __device__ __forceinline__ void emit_half(const float (&p1)[7], const float (&p0)[7], float v0, const uint32_t (&base_hi)[4]) {
+    constexpr int LB = kDims - 4;                    // low bits of the row index: dimensions 4 .. kDims - 1
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {                    // the three LOW bits of the row index: dimensions 4, 5, 6
+    for (int g = 0; g < (1 << LB); ++g) {
         float v = v0;
-        v *= (g & 4) ? p1[4] : p0[4];
-        v *= (g & 2) ? p1[5] : p0[5];
-        v *= (g & 1) ? p1[6] : p0[6];
+#pragma unroll
+        for (int i = 0; i < LB; ++i) v *= ((g >> (LB - 1 - i)) & 1) ? p1[4 + i] : p0[4 + i];
         float t[16];
         t[0] = v;
 #pragma unroll
@@ -74,7 +74,7 @@ __device__ __forceinline__ void emit_half(const float (&p1)[7], const float (&p0
             const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2), lw = *reinterpret_cast<const uint32_t*>(&l2);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int j = ((m + e) << 3) | g;    // row of the tile
+                const int j = ((m + e) << LB) | g;   // row of the tile
                 const uint32_t addr = base_hi[(j >> 1) & 3] + (uint32_t)j * 64u;
                 const uint16_t hv = (uint16_t)(e ? hw >> 16 : hw), lv = (uint16_t)(e ? lw >> 16 : lw);
                 asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(hv) : "memory");
@@ -84,9 +84,12 @@ __device__ __forceinline__ void emit_half(const float (&p1)[7], const float (&p0
     }
 }
 
+template <int kH2>       // bits of the second half: d = 7 + kH2 = 14 or 13
 __global__ void __launch_bounds__(etc::kThreads, 1)
 lfq_entropy_fwd_tc_kernel(EntTcArgs a, float* __restrict__ partial, float* __restrict__ stats) {
     using namespace etc;
+    constexpr int kDd = kH + kH2, kNV = 1 << kH2;
+    constexpr uint32_t kIdescN = (1u << 4) | ((uint32_t)(kNV >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[2], tmem_empty[2];
     __shared__ uint32_t tmem_base_slot;
@@ -128,9 +131,10 @@ lfq_entropy_fwd_tc_kernel(EntTcArgs a, float* __restrict__ partial, float* __res
             if (n < a.n_pairs) valid = a.mask[n / a.c] != 0;
             if (valid) {
                 v0 = kScale;
-                const float* xs = a.x + n * kD + half * kH;
+                const float* xs = a.x + n * kDd + half * kH;
 #pragma unroll
                 for (int i = 0; i < kH; ++i) {
+                    if (half && i >= kH2) { p1[i] = 0.f; p0[i] = 0.f; continue; }
                     const float u = a.u_scale * __ldg(xs + i);
                     const float e = __expf(-fabsf(u));                      // in (0, 1]
                     const float big = 1.f / (1.f + e), small = e * big;     // sigmoid(|u|), sigmoid(-|u|)
@@ -148,7 +152,8 @@ lfq_entropy_fwd_tc_kernel(EntTcArgs a, float* __restrict__ partial, float* __res
             uint32_t base[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) base[q] = tile + ((chunk ^ (uint32_t)q) << 4) + in_chunk;
-            emit_half(p1, p0, v0, base);
+            if (half) emit_half<kH2>(p1, p0, v0, base);
+            else emit_half<kH>(p1, p0, v0, base);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> the MMA's async-proxy reads
             __syncwarp();
             if (lane == 0) mbar_arrive_local(&full_bar[s]);
@@ -175,29 +180,29 @@ lfq_entropy_fwd_tc_kernel(EntTcArgs a, float* __restrict__ partial, float* __res
                     const uint32_t ko = k * 32;
                     const uint64_t u_hi = smem_desc_sw64(tile + ko), u_lo = smem_desc_sw64(tile + kTile + ko);
                     const uint64_t v_hi = smem_desc_sw64(tile + 2 * kTile + ko), v_lo = smem_desc_sw64(tile + 3 * kTile + ko);
-                    umma_f16(tmem_acc, u_lo, v_hi, kIdesc, (it % kFlushStages || k) ? 1u : 0u);
-                    umma_f16(tmem_acc, u_hi, v_lo, kIdesc, 1u);
-                    umma_f16(tmem_acc, u_hi, v_hi, kIdesc, 1u);
+                    umma_f16(tmem_acc, u_lo, v_hi, kIdescN, (it % kFlushStages || k) ? 1u : 0u);
+                    umma_f16(tmem_acc, u_hi, v_lo, kIdescN, 1u);
+                    umma_f16(tmem_acc, u_hi, v_hi, kIdescN, 1u);
                 }
                 umma_commit(&empty_bar[s]);
                 if (it % kFlushStages == kFlushStages - 1 || it == n_st - 1) umma_commit(&tmem_full[acc]);
             }
         }
     } else {
-        // ---------------- epilogue: TMEM lane quarter = warp & 3; row j1 = quarter * 32 + lane, all 128 columns j2
+        // ---------------- epilogue: TMEM lane quarter = warp & 3; row j1 = quarter * 32 + lane, all 2^kH2 columns j2
         const int quarter = warp & 3;
         const int n_rounds = (n_st + kFlushStages - 1) / kFlushStages;
-        float* out = partial + (int64_t)blockIdx.x * (kRows * kRows) + (int64_t)(quarter * 32 + lane) * kRows;
+        float* out = partial + (int64_t)blockIdx.x * (kRows * kNV) + (int64_t)(quarter * 32 + lane) * kNV;
         for (int rr = 0; rr < n_rounds; ++rr) {
             const int acc = rr & 1;
             mbar_wait(&tmem_full[acc], ((uint32_t)rr >> 1) & 1u);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * 128 + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-            for (int c4 = 0; c4 < 4; ++c4) {
+            for (int c4 = 0; c4 < kNV / 32; ++c4) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c4 * 32, r);
-                if (c4 == 3) {                                   // accumulator read out: hand it back
+                if (c4 == kNV / 32 - 1) {                        // accumulator read out: hand it back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_local(&tmem_empty[acc]);
@@ -230,7 +235,7 @@ lfq_entropy_fwd_tc_kernel(EntTcArgs a, float* __restrict__ partial, float* __res
 int launch_lfq_entropy_final(const float* partial, const float* stats, int n_cta, int c, int d, float eps, float* tables,
                              float* result, cudaStream_t st);
 
-int launch_lfq_entropy_fwd_tc(const float* x, const uint8_t* mask, int64_t n_tok, int c, float u_scale, float eps,
+int launch_lfq_entropy_fwd_tc(const float* x, const uint8_t* mask, int64_t n_tok, int c, int d, float u_scale, float eps,
                               float* partial_scratch, float* stats, float* tables, float* result, cudaStream_t st) {
     using namespace etc;
     EntTcArgs a{x, mask, n_tok * c, c, u_scale};
@@ -239,10 +244,11 @@ int launch_lfq_entropy_fwd_tc(const float* x, const uint8_t* mask, int64_t n_tok
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)(n_blocks < sms ? n_blocks : sms);
-    if (cudaFuncSetAttribute(lfq_entropy_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess)
+    auto kernel = d == 14 ? lfq_entropy_fwd_tc_kernel<7> : lfq_entropy_fwd_tc_kernel<6>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess)
         return check_launch("lfq_entropy_factorized (tensor-core forward, shared memory opt-in)");
-    lfq_entropy_fwd_tc_kernel<<<grid, kThreads, kSmem, st>>>(a, partial_scratch, stats);
-    return launch_lfq_entropy_final(partial_scratch, stats, grid, c, kD, eps, tables, result, st);
+    kernel<<<grid, kThreads, kSmem, st>>>(a, partial_scratch, stats);
+    return launch_lfq_entropy_final(partial_scratch, stats, grid, c, d, eps, tables, result, st);
 }
 
 }  // namespace dcta

@@ -125,15 +125,16 @@ def test_factorized_entropy_at_the_benchmark_shape(D):
 
 
 def test_tensor_core_forward_equals_the_fma_forward(D):
-    """d = 14: the forward contraction on tcgen05 (fp16 hi / lo operands, TMEM accumulators flushed every 1024 pairs)
+    """d = 14 and d = 13 (the conf/patch14-l.json quantiser): the forward contraction on tcgen05 (fp16 hi / lo operands, TMEM accumulators flushed every 1024 pairs)
     against the fp32 FMA kernel on the same input -- loss, entropies and the gradient that is computed from its tables;
     token counts that leave a ragged last stage, several flush rounds per CTA, masked tokens, saturated and soft inputs."""
     from dct_autoencoder_b200 import _lib
     from dct_autoencoder_b200.util import FactorizedDistance, compute_entropy_loss
     lib = _lib.load()
     torch.manual_seed(5)
-    for (b, n, c, scale_x) in [(1, 3, 1, 0.002), (7, 501, 14, 0.002), (64, 3000, 14, 0.004), (3, 700, 5, 0.05)]:
-        x = (torch.randn(b, n, c, 14, device="cuda") * scale_x)
+    for (b, n, c, scale_x, d) in [(1, 3, 1, 0.002, 14), (7, 501, 14, 0.002, 14), (64, 3000, 14, 0.004, 14), (3, 700, 5, 0.05, 14),
+                                  (5, 333, 16, 0.002, 13), (32, 3000, 16, 0.003, 13), (2, 90, 3, 0.08, 13)]:
+        x = (torch.randn(b, n, c, d, device="cuda") * scale_x)
         mask = torch.rand(b, n, device="cuda") > 0.2
         mask[0, 0] = True
         out = []

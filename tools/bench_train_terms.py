@@ -57,6 +57,14 @@ def main():
         compute_entropy_loss(FactorizedDistance(x, 1.0), mask).backward()
     report("factorised LFQ entropy loss fwd + bwd, %d x %d x 2^%d" % (T, c, d), entropy, T, dev)
 
+    x13 = (torch.randn(b, n, 16, 13, device=dev) * 0.002).requires_grad_(True)     # conf/patch14-l.json: 16 codebooks of 2^13
+
+    def entropy13():
+        x13.grad = None
+        compute_entropy_loss(FactorizedDistance(x13, 1.0), mask).backward()
+    report("factorised LFQ entropy loss fwd + bwd, %d x 16 x 2^13 (conf/patch14-l.json)" % T, entropy13, T, dev)
+    del x13
+
     lfq = D.LFQ(codebook_size=2 ** d, num_codebooks=c).to(dev).train()
     xf = x.detach().reshape(b, n, c * d).requires_grad_(True)
 
